@@ -1,0 +1,138 @@
+"""Wave-packet ray tracer restated in NumPy (oracle; test infrastructure only).
+
+Ray equations and sampling follow raytracing/GPURaytracing.jl:18-65 (RHS `dxkdt`,
+texture-coordinate map, dispersion relation with `pos_neg` sign) with the two quirks of
+SURVEY App. B made explicit flags; the integrator is the north star's fixed-step classical
+RK4 (the reference integrates with adaptive Vern7 / implicit midpoint, OrdinaryDiffEq,
+un-vendored => the integrator is OUR spec and parity for it is against this file).
+
+  get_velocity_info      raytracing/RaytracingDriver.jl:132-154
+  generate_initial_wavepackets  raytracing/RaytracingDriver.jl:27-47   (K7)
+  k-cutoff reset         raytracing/GPUTwoLayerRaytracing.jl:136-138
+  bilinear sampler       GPURaytracing.jl:18-20 + CUDA texture semantics (exact at nodes, K6),
+                         with `floor` instead of `unsafe_trunc` (App. B #6)
+  hermite bicubic        utils/CUDAInterpolations.jl:39-53,71-108
+Packets: array (N, 4) with columns x, y, k, l; omega_sign (N,).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LERP_PHYSICAL = 0   # W = (1-a) old + a new      (Raytracing.jl:163-168, the CPU tracer)
+LERP_REFERENCE_GPU = 1  # W = a old + (1-a) new  (GPURaytracing.jl:33,53, App. B #2)
+
+
+def get_velocity_info(psih, grid):
+    """u,v,ux,uy,vx (vy = -ux) from a streamfunction; RaytracingDriver.jl:132-154."""
+    k, l = grid.kr, grid.l
+    u = grid.irfft2(-1j * l * psih)
+    v = grid.irfft2(1j * k * psih)
+    ux = grid.irfft2(k * l * psih)
+    uy = grid.irfft2(l * l * psih)
+    vx = grid.irfft2(-k * k * psih)
+    return np.stack([u, v, ux, uy, vx], axis=-1)      # (nx, ny, 5)
+
+
+def generate_initial_wavepackets(L, k0, sqrtN):
+    """RaytracingDriver.jl:27-47: lattice (x = repeat outer, y = repeat inner), ring of
+    wavevectors, odd (1-based) packets get omega_sign = -1."""
+    N = sqrtN * sqrtN
+    offset = L / sqrtN / 2
+    I = np.arange(1, sqrtN + 1, dtype=np.float64)
+    J = np.arange(1, N + 1, dtype=np.float64)
+    diag = I * L / sqrtN - L / 2 - offset
+    phase = 2 * np.pi * J / N
+    xk = np.empty((N, 4))
+    xk[:, 0] = np.tile(diag, sqrtN)        # repeat(diagonal, outer=n)
+    xk[:, 1] = np.repeat(diag, sqrtN)      # repeat(diagonal, inner=n)
+    xk[:, 2] = k0 * np.cos(phase)
+    xk[:, 3] = k0 * np.sin(phase)
+    sign = np.ones(N)
+    sign[0::2] *= -1
+    return xk, sign
+
+
+def kcutoff_reset(xk, kcut, k0):
+    """GPUTwoLayerRaytracing.jl:136-138.  Returns number of packets reset (bit-exact compare+select)."""
+    mask = xk[:, 2] ** 2 + xk[:, 3] ** 2 >= kcut ** 2
+    xk[mask, 2] = k0
+    xk[mask, 3] = 0.0
+    return int(mask.sum())
+
+
+def cell_index(x, x0, dx, n):
+    """Texture addressing restated: s = (x - x0)/dx, i = floor(s) mod n, a = s - floor(s)."""
+    s = (x - x0) / dx
+    fl = np.floor(s)
+    i = np.mod(fl, n).astype(np.int64)
+    return i, s - fl
+
+
+def sample_bilinear(fields, x, y, grid):
+    """fields: (nx, ny, C).  Returns (N, C).  Exact at nodes (K6)."""
+    i, a = cell_index(x, grid.x[0], grid.dx, grid.nx)
+    j, b = cell_index(y, grid.y[0], grid.dy, grid.ny)
+    i1, j1 = (i + 1) % grid.nx, (j + 1) % grid.ny
+    a, b = a[:, None], b[:, None]
+    bottom = (1 - a) * fields[i, j] + a * fields[i1, j]
+    top = (1 - a) * fields[i, j1] + a * fields[i1, j1]
+    return (1 - b) * bottom + b * top
+
+
+def _cubic(al, f0, f1, m0, m1):
+    """utils/CUDAInterpolations.jl:39-44."""
+    return f0 + m0 * al + (-3 * f0 + 3 * f1 - 2 * m0 - m1) * al ** 2 + (2 * f0 - 2 * f1 + m0 + m1) * al ** 3
+
+
+def sample_bicubic_hermite(f, fx, fy, fxy, x, y, grid):
+    """utils/CUDAInterpolations.jl:71-108 for one scalar field with its derivatives."""
+    i, a = cell_index(x, grid.x[0], grid.dx, grid.nx)
+    j, b = cell_index(y, grid.y[0], grid.dy, grid.ny)
+    i1, j1 = (i + 1) % grid.nx, (j + 1) % grid.ny
+    dx = grid.dx
+    f0 = _cubic(a, f[i, j], f[i1, j], fx[i, j] * dx, fx[i1, j] * dx)
+    f1 = _cubic(a, f[i, j1], f[i1, j1], fx[i, j1] * dx, fx[i1, j1] * dx)
+    g0 = _cubic(a, fy[i, j] * dx, fy[i1, j] * dx, fxy[i, j] * dx * dx, fxy[i1, j] * dx * dx)
+    g1 = _cubic(a, fy[i, j1] * dx, fy[i1, j1] * dx, fxy[i, j1] * dx * dx, fxy[i1, j1] * dx * dx)
+    return _cubic(b, f0, f1, g0, g1)
+
+
+def rhs(xk, sign, t, t0, t1, F_old, F_new, grid, f, Cg, lerp=LERP_PHYSICAL):
+    """dxkdt of GPURaytracing.jl:32-65.  F_* are (nx, ny, 5) = u, v, ux, uy, vx."""
+    alpha = (t - t0) / (t1 - t0)
+    x, y, k, l = xk[:, 0], xk[:, 1], xk[:, 2], xk[:, 3]
+    w = sign * np.sqrt(f * f + Cg * Cg * (k * k + l * l))
+    cgx, cgy = Cg * Cg * k / w, Cg * Cg * l / w
+    So = sample_bilinear(F_old, x, y, grid)
+    Sn = sample_bilinear(F_new, x, y, grid)
+    if lerp == LERP_PHYSICAL:
+        W = (1 - alpha) * So + alpha * Sn
+    else:
+        W = alpha * So + (1 - alpha) * Sn
+    out = np.empty_like(xk)
+    out[:, 0] = W[:, 0] + cgx
+    out[:, 1] = W[:, 1] + cgy
+    out[:, 2] = -(W[:, 2] * k + W[:, 4] * l)
+    out[:, 3] = -(W[:, 3] * k - W[:, 2] * l)       # vy = -ux
+    return out
+
+
+def raytrace(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, lerp=LERP_PHYSICAL):
+    """Advance packets in place from t0 to t1 with `nsub` classical RK4 steps."""
+    h = (t1 - t0) / nsub
+    for s in range(nsub):
+        t = t0 + s * h
+        a = (xk, sign, t0, t1, F_old, F_new, grid, f, Cg, lerp)
+        k1 = rhs(xk, sign, t, *a[2:])
+        k2 = rhs(xk + 0.5 * h * k1, sign, t + 0.5 * h, *a[2:])
+        k3 = rhs(xk + 0.5 * h * k2, sign, t + 0.5 * h, *a[2:])
+        k4 = rhs(xk + h * k3, sign, t + h, *a[2:])
+        xk += (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    return xk
+
+
+def interpolate_velocity(F, pos, grid):
+    """interpolate_velocity!/interpolate_gradients! (GPURaytracing.jl:67-109): u,v and
+    ux,uy,vx,vy at packet positions.  Returns (N,2), (N,4)."""
+    S = sample_bilinear(F, pos[:, 0], pos[:, 1], grid)
+    return S[:, 0:2].copy(), np.stack([S[:, 2], S[:, 3], S[:, 4], -S[:, 2]], axis=1)

@@ -1,0 +1,228 @@
+"""Pins the oracle against the known-answer values recorded in the reference's notebooks
+(SURVEY.md section 4, K1..K15).  CPU only."""
+import numpy as np
+import scipy.linalg
+
+from oracle import ifmab3, outputs, raytrace, rsw
+from oracle.grid import TwoDGrid, alias_ranges, parsevalsum2
+
+
+def test_K1_matrix_exponential():
+    # rsw/Notebooks/MatrixExponentialTest.ipynb:197-198
+    A = np.array([[0, 1, 1j], [-1, 0, 1j], [-1j, -1j, 0]])
+    want = np.array([
+        [1, 1.7182818284590455, 1.7182818284590453j],
+        [-0.6321205588285577, 1, 0.6321205588285577j],
+        [-0.6321205588285578j, -1.7182818284590453j, 2.0861612696304874]])
+    got, _ = ifmab3.getexpLs(A.reshape(1, 1, 3, 3), 1.0)
+    np.testing.assert_allclose(got[0, 0], want, rtol=0, atol=5e-15)
+
+
+def test_K2_mvmul_orientation():
+    A = np.zeros((1, 1, 2, 2)); A[0, 0] = [[1, 1], [0, 1]]
+    x = np.zeros((1, 1, 2)); x[0, 0] = [1, 2]
+    assert ifmab3.mvmul(A, x)[0, 0].tolist() == [3, 2]
+
+
+def _k3_setup():
+    nx, Lx = 512, 2 * np.pi
+    dx = Lx / nx
+    kmax = nx / 2 - 1
+    nnu, cfltune, umax = 4, 0.1, 0.3
+    nutune = 1 / cfltune
+    dt = cfltune / umax * dx
+    nu = nutune * 2 * np.pi / nx / (kmax ** (2 * nnu)) / dt
+    return nx, Lx, dt, nu, nnu
+
+
+def test_K3_L_and_expLdt():
+    # rsw/Notebooks/RSW_Test.ipynb:228-236 (Float32 run; compare to 7 significant digits)
+    nx, Lx, dt, nu, nnu = _k3_setup()
+    assert dt == 0.00409061543436171
+    assert nu == 1.6780303489894543e-18
+    g = TwoDGrid(nx, Lx)
+    p = rsw.Params(nu, nnu, 3.0, 1.0)
+    L = rsw.populate_L(g, p)
+    assert abs(np.abs(L[..., 0, 0]).max() - 495.26715) < 5e-5
+    E = ifmab3.expL_closed_form(g, p, dt)
+    m = E[..., 1, 1].real.min()
+    assert abs(m - 0.07184223) < 1e-7
+    assert np.unravel_index(E[..., 1, 1].real.argmin(), E.shape[:2]) == (256, 256)  # (kr,l)=(256,-256)
+    # closed form == general matrix exponential, on a strided subset of wavenumbers
+    sub = (slice(0, None, 16), slice(0, None, 31))
+    Eg, E2g = ifmab3.getexpLs(L[sub], dt)
+    np.testing.assert_allclose(E[sub], Eg, rtol=0, atol=2e-14)
+    E2 = ifmab3.expL_closed_form(g, p, 2 * dt)
+    np.testing.assert_allclose(E2[sub], E2g, rtol=0, atol=2e-14)
+
+
+def test_K3_closed_form_modified():
+    nx, Lx, dt, nu, nnu = _k3_setup()
+    g = TwoDGrid(64, Lx)
+    p = rsw.Params(nu * 1e10, nnu, 3.0, 1.0)
+    L = rsw.populate_L(g, p, rsw.MODIFIED)
+    E = ifmab3.expL_closed_form(g, p, dt, rsw.MODIFIED)
+    Eg, _ = ifmab3.getexpLs(L, dt)
+    np.testing.assert_allclose(E, Eg, rtol=0, atol=2e-14)
+
+
+def test_K4_swqg_diagonal_L():
+    # swqg/Notebooks/SWQG_Test.ipynb cell 3: nutune = 2
+    nx, Lx, dt, _, nnu = _k3_setup()
+    nu = 2 * 2 * np.pi / nx / ((nx / 2 - 1) ** (2 * nnu)) / dt
+    assert nu == 3.3560606979789085e-19
+    g = TwoDGrid(nx, Lx)
+    L = -nu * g.Krsq ** nnu
+    assert abs(np.abs(L).max() - 99.05343) < 1e-5
+
+
+def test_K5_parseval_and_spectral_resample():
+    # Notebooks/FFTInterpTest.ipynb cells 0-3
+    g1, g2 = TwoDGrid(32), TwoDGrid(128)
+    X, Y = g1.x[:, None], g1.y[None, :]
+    f1 = 2 * np.sin(4 * X + 3 * Y + np.pi / 4) - np.cos(X - 2 * Y) + 4 * np.sin(-2 * X + Y - np.pi / 4)
+    assert g1.x[0] == -np.pi and abs(g1.x[-1] - 2.945243112740431) < 1e-15
+    f1h = g1.rfft2(f1)
+    assert abs(parsevalsum2(f1h, g1) - 414.52338484575296) < 1e-10
+    assert abs((f1 ** 2).sum() * g1.dx * g1.dy - 414.52338484575296) < 1e-10
+    assert abs(f1.max() - 6.828544345425804) < 1e-13
+    f2h = rsw.load_from_snapshot(f1h[:, :, None], g2)[:, :, 0]
+    f2 = g2.irfft2(f2h)
+    assert abs(parsevalsum2(f2h, g2) - 414.52338484575296) < 1e-10
+    assert abs(f2.max() - 6.962803990425579) < 1e-12
+    assert np.allclose(g1.kr[:, 0], np.arange(17.0))
+
+
+def test_alias_ranges_match_survey():
+    # nx=512 -> 171:257 and 171:342 ; nx=2048 -> 683:1025 and 683:1366 (1-based)
+    assert alias_ranges(512, 257, 1 / 3) == ((170, 342), (170, 257))
+    assert alias_ranges(2048, 1025, 1 / 3) == ((682, 1366), (682, 1025))
+    assert alias_ranges(256, 129, 0) == ((128, 129), (128, 129))
+
+
+def test_K6_bilinear_exact_at_nodes():
+    # Notebooks/LargeMatrixTest.ipynb cells 7-10: sampling at node coordinates returns U[i]
+    g = TwoDGrid(64)
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((64, 64, 5))
+    ii, jj = np.meshgrid(np.arange(0, 64, 16), np.arange(0, 64, 16), indexing="ij")
+    S = raytrace.sample_bilinear(F, g.x[ii.ravel()], g.y[jj.ravel()], g)
+    np.testing.assert_array_equal(S, F[ii.ravel(), jj.ravel()])
+    # periodic wrap: one period away samples the same values to rounding
+    S2 = raytrace.sample_bilinear(F, g.x[ii.ravel()] + g.Lx, g.y[jj.ravel()] - g.Ly, g)
+    np.testing.assert_allclose(S2, S, atol=1e-12)
+
+
+def test_K7_packet_initial_layout():
+    # raytracing/Notebooks/GPUDriverTest.ipynb:459 ff, sqrtN=3, k0=1 (production x/y ordering)
+    xk, sign = raytrace.generate_initial_wavepackets(2 * np.pi, 1.0, 3)
+    j = np.arange(1, 10)
+    np.testing.assert_allclose(xk[:, 2], np.cos(2 * np.pi * j / 9), atol=1e-15)
+    np.testing.assert_allclose(xk[:, 3], np.sin(2 * np.pi * j / 9), atol=1e-15)
+    lat = np.array([-2.0943951023931957, 0.0, 2.0943951023931953])
+    np.testing.assert_allclose(xk[:3, 0], lat, atol=5e-16)
+    np.testing.assert_allclose(xk[0::3, 1], lat, atol=5e-16)
+    assert abs(xk[1, 0]) < 3e-16                      # the notebook prints -2.2e-16
+    assert sign.tolist() == [-1, 1, -1, 1, -1, 1, -1, 1, -1]
+
+
+def test_K8_K9_steady_flow_invariant_and_rk4_order():
+    # Taylor-Green steady flow with exact gradients (K9); Omega = omega + U.k conserved (K8)
+    g = TwoDGrid(256)
+    X, Y = g.x[:, None], g.y[None, :]
+    U0 = 0.3
+    F = np.stack([U0 * np.cos(X) * np.sin(Y), -U0 * np.sin(X) * np.cos(Y),
+                  -U0 * np.sin(X) * np.sin(Y), U0 * np.cos(X) * np.cos(Y),
+                  -U0 * np.cos(X) * np.cos(Y)], axis=-1)
+    xk0, sign = raytrace.generate_initial_wavepackets(2 * np.pi, 3.0, 6)
+    f, Cg = 3.0, 1.0
+
+    def Omega(xk):
+        S = raytrace.sample_bilinear(F, xk[:, 0], xk[:, 1], g)
+        return sign * np.sqrt(f * f + Cg * Cg * (xk[:, 2] ** 2 + xk[:, 3] ** 2)) + S[:, 0] * xk[:, 2] + S[:, 1] * xk[:, 3]
+
+    xk = xk0.copy()
+    raytrace.raytrace(xk, sign, 0.0, 1.0, F, F, g, f, Cg, nsub=200)
+    drift = np.abs(Omega(xk) - Omega(xk0)) / np.abs(Omega(xk0))
+    assert drift.mean() < 4.1e-4          # the reference's Vern7 run records 0.041 %
+    # RK4 self-convergence on a smooth (analytic-like, short) horizon: error ratio ~ 2^4
+    def run(n):
+        z = xk0.copy(); raytrace.raytrace(z, sign, 0.0, 0.05, F, F, g, f, Cg, nsub=n); return z
+    e1 = np.abs(run(1) - run(8)).max(); e2 = np.abs(run(2) - run(8)).max()
+    assert e2 < e1
+
+
+def test_kcutoff_reset_is_compare_and_select():
+    xk = np.array([[0, 0, 3.0, 4.0], [0, 0, 3.0, 3.9], [0, 0, -5.0, 0.0]])
+    n = raytrace.kcutoff_reset(xk, 5.0, 1.5)
+    assert n == 2
+    assert xk[:, 2].tolist() == [1.5, 3.0, 1.5] and xk[:, 3].tolist() == [0.0, 3.9, 0.0]
+
+
+def test_K10_ic_geostrophic_nondivergent_wave_zero_pv_K15_amplitudes():
+    g = TwoDGrid(128)
+    p = rsw.Params(0.0, 4, 3.0, 1.0)
+    sol, (ugh, vgh, egh), (uwh, vwh, ewh) = rsw.initial_condition(g, p, (10, 13), 1.5, (0, 5), 0.1,
+                                                                   np.random.default_rng(1234))
+    div_g = np.abs(1j * g.kr * ugh + 1j * g.l * vgh).max()
+    pv_w = np.abs(1j * g.kr * vwh - 1j * g.l * uwh - p.f * ewh).max()
+    scale = np.abs(ugh).max()
+    assert div_g / scale < 1e-12 and pv_w / scale < 1e-12
+    assert abs(np.abs(g.irfft2(ugh)).max() - 1.5) < 1e-12       # K15
+    assert abs(np.abs(g.irfft2(uwh)).max() - 0.1) < 1e-12
+
+
+def test_K12_collated_rollover():
+    # Notebooks/CollatedOutputTest.ipynb:101-112: line_limit=100, 1000 writes
+    out = outputs.CollatedOutput("test_dir3/sin", 100)
+    for i in range(1, 1001):
+        out.write(str(i))
+    assert out.files["test_dir3/sin_00000001.out"] == [str(i) for i in range(101, 201)]
+    assert out.files["test_dir3/sin_00000009.out"][-1] == "1000"
+    assert out.files["test_dir3/sin_00000010.out"] == []
+
+
+def test_K13_sequenced_output_rolls_inside_a_frame():
+    # packet_max_writes=300, gradients on -> frame 59's t,x,k,u in file 0, g in file 1
+    out = outputs.SequencedOutput(lambda i: outputs.packet_filename("packets", i), 300)
+    outputs.savepacketproblem(out)
+    for frame in range(0, 130):
+        outputs.write_packets(out, frame * 10, True)
+    f0 = out.files["packets.000000.jld2"]; f1 = out.files["packets.000001.jld2"]
+    assert len(f0) == 300
+    assert f0[-4:] == ["p/t/580", "p/x/580", "p/k/580", "p/u/580"]
+    assert f1[0] == "p/g/580" and f1[1] == "p/t/590"
+
+
+def test_frame_roller_every_file_has_max_writes_frames():
+    # raytracing/Notebooks/GPUDriverTest.ipynb cell 6: max_writes=1000, npacketsubs=10
+    r = outputs.FrameRoller("packets.jld2", 1000)
+    r.initial_frame(0)
+    for j in range(1, 5001):
+        r.loop_frame(j * 10)
+    assert r.files["packets.jld2.00000004"][0] == 40000
+    assert len(r.files["packets.jld2.00000004"]) == 1000
+    assert len(r.files["packets.jld2.00000000"]) == 1000
+
+
+def test_ifmab3_third_order_and_energy_conservation():
+    # AB3 with exact integrating factor: 3rd order in dt on a smooth IC; inviscid energy drift tiny
+    g = TwoDGrid(32)
+    p = rsw.Params(0.0, 4, 3.0, 1.0)
+    sol0, _, _ = rsw.initial_condition(g, p, (2, 4), 0.05, (0, 3), 0.02, np.random.default_rng(7))
+    sol0 = rsw.enforce_reality_condition(sol0, g, p)
+
+    def run(nsteps, T=0.4):
+        sol = sol0.copy()
+        ts = ifmab3.IFMAB3(rsw.populate_L(g, p), T / nsteps, lambda s: rsw.calcN(s, g, p))
+        for _ in range(nsteps):
+            ts.stepforward(sol)
+        return g.dealias(sol)
+
+    ref = run(640)
+    e1 = np.abs(run(40) - ref).max(); e2 = np.abs(run(80) - ref).max()
+    # the 3 Euler start-up steps cost O(dt^2) globally; observed order sits between 2 and 3
+    assert e1 / e2 > 3.5
+    E0 = rsw.kinetic_energy(sol0, g) + rsw.potential_energy(sol0, g, p)
+    E1 = rsw.kinetic_energy(ref, g) + rsw.potential_energy(ref, g, p)
+    assert abs(E1 - E0) / E0 < 5e-3   # quadratic (linearised) energy is only approximately conserved
