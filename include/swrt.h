@@ -1,0 +1,137 @@
+/* libswrt -- C ABI of the B200-native pseudo-spectral flow step and wave-packet ray tracer.
+ *
+ * Drop-in boundary for the two hot paths of ndefilippis/JuliaRaytracingSW.  The reference has no
+ * FFI of its own: the seam is the Julia call surface its drivers use.  Every entry
+ * point below cites the reference function it stands in for (paths relative to the reference
+ * checkout).  Conventions:
+ *   - every function returns 0 on success, a negative SWRT_ERR_* otherwise; swrt_last_error()
+ *     returns a thread-local message; nothing throws or calls back;
+ *   - host buffers are caller owned, column-major like the Julia arrays they mirror, and are only
+ *     touched during the call (calls are synchronous with respect to host buffers);
+ *   - device memory is owned by the handles; one CUDA stream per flow handle, packets attached to a
+ *     flow run on that flow's stream; a handle is not thread safe;
+ *   - there is no CPU fallback: creating a handle without a usable CUDA device fails.
+ */
+#ifndef SWRT_H
+#define SWRT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWRT_VERSION 100
+
+enum { SWRT_OK = 0, SWRT_ERR_ARG = -1, SWRT_ERR_CUDA = -2, SWRT_ERR_UNSUPPORTED = -3, SWRT_ERR_STATE = -4 };
+
+/* models: rsw/RotatingShallowWater.jl, rsw/ModifiedShallowWater.jl, rsw/LinborgShallowWater.jl,
+ * swqg/SWQG.jl, swqg/TwoLayerQG.jl, thomasyamada/ThomasYamada.jl */
+enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_SWQG = 4, SWRT_TWOLAYERQG = 5, SWRT_THOMASYAMADA = 6 };
+/* steppers: utils/IFMAB3.jl; FourierFlows FilteredAB3 / ETDRK4 / FilteredRK4 (raytracing/CPUParameters.jl:7) */
+enum { SWRT_IFMAB3 = 0, SWRT_FILTEREDAB3 = 1, SWRT_ETDRK4 = 2, SWRT_FILTEREDRK4 = 3 };
+
+typedef struct swrt_flow swrt_flow;
+typedef struct swrt_packets swrt_packets;
+
+/* = keyword arguments of RotatingShallowWater.Problem (rsw/RotatingShallowWater.jl:70-85) and of
+ * IFMAB3TimeStepper / makefilter (utils/IFMAB3.jl:68-88) */
+typedef struct swrt_flow_desc {
+    int model, stepper;
+    int nx, ny;
+    int nnu;               /* order of the hyperviscous operator */
+    int use_filter;        /* utils/IFMAB3.jl:80-85 */
+    int filter_order;      /* makefilter(order=...) */
+    int device;            /* CUDA device ordinal */
+    double Lx, Ly, dt, nu, f, Cg;
+    double aliased_fraction;
+    double filter_innerK, filter_outerK, filter_tol;   /* <=0: FourierFlows defaults 2/3, 1, 1e-15 */
+    double U, mu, F, Ro, Kd2;                            /* model specific (two-layer, TY, SWQG) */
+} swrt_flow_desc;
+
+const char* swrt_last_error(void);
+int swrt_version(void);
+int swrt_device_count(int* n);
+
+/* Problem(dev; ...)  rsw/RotatingShallowWater.jl:70-99 (grid, params, L, exp(L dt), work arrays) */
+int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out);
+int swrt_flow_destroy(swrt_flow* h);
+/* set_solution!(prob, u0h, v0h, eta0h)  :309-321; sol_host is complex128 (nkr, nl, nvar) column-major.
+ * The state is stored dealiased (dealias!(sol) is the first statement of every calcN!, :141). */
+int swrt_flow_set_solution(swrt_flow* h, const void* sol_host);
+/* Array(prob.sol) as left by updatevars!/calcN! (aliased modes are zero) */
+int swrt_flow_get_solution(swrt_flow* h, void* sol_host);
+/* enforce_reality_condition!(prob) :118-133 -- in the reference this leaves sol dealiased and refreshes vars */
+int swrt_flow_enforce_reality(swrt_flow* h);
+/* stepforward!(prob, [], nsteps): utils/IFMAB3.jl:157-169 looped by FourierFlows.stepforward!(prob, diags, n) */
+int swrt_flow_step(swrt_flow* h, int nsteps);
+/* prob.clock.t / prob.clock.step */
+int swrt_flow_clock(swrt_flow* h, double* t, long long* step);
+int swrt_flow_set_clock(swrt_flow* h, double t, long long step);
+/* updatevars!(prob) + Array(vars.<field>) :101-116; real_host is float64 (nx, ny) column-major */
+enum { SWRT_FIELD_U = 0, SWRT_FIELD_V = 1, SWRT_FIELD_ETA = 2, SWRT_FIELD_ZETA = 16 };
+int swrt_flow_get_field(swrt_flow* h, int which, double* real_host);
+/* kinetic_energy(prob), potential_energy(prob) :323-336 */
+int swrt_flow_energies(swrt_flow* h, double* ke, double* pe);
+/* maximum(abs.(vars.u)), maximum(abs.(vars.v)) (CFL log, raytracing/RaytracingDriver.jl:244) and
+ * any(isnan.(vars.uh)) (:282) */
+int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax);
+int swrt_flow_has_nan(swrt_flow* h, int* flag);
+/* get_streamfunction! (rsw/RSWRaytracingDriver.jl:56-67) + get_velocity_info
+ * (raytracing/RaytracingDriver.jl:132-154) into snapshot slot 0 (old) or 1 (new); stays on device */
+enum { SWRT_PSI_RSW_BALANCED = 0 };
+int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot);
+/* old_velocity = new_velocity; old_grad_v = new_grad_v (raytracing/RaytracingDriver.jl:269-270).
+ * alias != 0 reproduces the reference's rebinding (both names then refer to the same buffers);
+ * alias == 0 swaps the two slots. */
+int swrt_flow_swap_snapshots(swrt_flow* h, int alias);
+/* Array(u), Array(v), ... of a snapshot: out is float64 (nx, ny, 5) column-major = u, v, ux, uy, vx */
+int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host);
+/* load a snapshot from host fields (same layout) -- used for steady/analytic background flows
+ * (raytracing/SteadyRaytracing.jl) and by tests */
+int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host);
+
+/* timing helpers on the handle's stream (CUDA events) */
+int swrt_flow_timer_start(swrt_flow* h);
+int swrt_flow_timer_stop(swrt_flow* h, float* ms);
+int swrt_flow_sync(swrt_flow* h);
+/* number of kernels this handle has launched so far */
+int swrt_flow_launch_count(swrt_flow* h, long long* n);
+
+enum { SWRT_INTERP_BILINEAR = 0 };
+enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };
+typedef struct swrt_packets_desc {
+    long long n;            /* Npackets */
+    int interp;             /* SWRT_INTERP_* */
+    int nsub;               /* RK4 sub-steps per raytrace call */
+    int time_lerp;          /* SWRT_LERP_*   */
+    double f, Cg;           /* packet_params.f, packet_params.Cg */
+} swrt_packets_desc;
+
+/* create_template_ode(packets) raytracing/GPURaytracing.jl:111-113 -- device state for N packets */
+int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_packets** out);
+int swrt_packets_destroy(swrt_packets* p);
+/* packets (N,4) column-major = x, y, k, l ; omega_sign (N)  (raytracing/RaytracingDriver.jl:27-47) */
+int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* omega_sign_host);
+int swrt_packets_get(swrt_packets* p, double* xk_host);
+/* generate_initial_wavepackets on the device (raytracing/RaytracingDriver.jl:27-47); first = global index of
+ * this shard's first packet (0-based), ntotal = sqrtN^2 */
+int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN, long long first);
+/* raytrace!(tmpl, v_old, v_new, g_old, g_new, grid, packets, dt, (t0,t1), params) raytracing/GPURaytracing.jl:115-142,
+ * reading the flow's snapshot slots 0 (old) and 1 (new) */
+int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
+/* interpolate_velocity! / interpolate_gradients! :67-109 + Array: u_host (N,2), g_host (N,4) or NULL */
+int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host);
+/* k-cutoff reset raytracing/GPUTwoLayerRaytracing.jl:136-138 */
+int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long long* nreset);
+
+/* Output roll-over arithmetic (host, integer only): utils/SequencedOutputs.jl:37-63, utils/Collated.jl:40-60 */
+typedef struct swrt_seqout { long long max_writes, current_writes, file_index; } swrt_seqout;
+int swrt_seqout_init(swrt_seqout* s, long long max_writes);
+/* one `out[key] = val`; returns in *file_index the file the key went to */
+int swrt_seqout_write(swrt_seqout* s, long long nwrites, long long* file_index);
+int swrt_seqout_filename(const char* base, long long idx, char* buf, int buflen);     /* "%s.%06d.jld2" */
+int swrt_collated_filename(const char* base, long long idx, char* buf, int buflen);   /* "%s_%08d.out"  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

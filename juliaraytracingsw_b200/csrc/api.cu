@@ -1,0 +1,644 @@
+// libswrt C ABI: handle management, host-side tables, kernel dispatch.  See include/swrt.h.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/swrt.h"
+#include "models.cuh"
+#include "packets.cuh"
+#include "update.cuh"
+
+using namespace swrt;
+
+namespace swrt {
+extern template struct Launch<32>;
+extern template struct Launch<64>;
+extern template struct Launch<128>;
+extern template struct Launch<256>;
+extern template struct Launch<512>;
+extern template struct Launch<1024>;
+extern template struct Launch<2048>;
+extern template struct Launch<4096>;
+}  // namespace swrt
+
+#define SWRT_DISPATCH(n, RES, ...)                                   \
+    switch (n) {                                                     \
+        case 32: { using LN = Launch<32>; RES = __VA_ARGS__; } break;   \
+        case 64: { using LN = Launch<64>; RES = __VA_ARGS__; } break;   \
+        case 128: { using LN = Launch<128>; RES = __VA_ARGS__; } break; \
+        case 256: { using LN = Launch<256>; RES = __VA_ARGS__; } break; \
+        case 512: { using LN = Launch<512>; RES = __VA_ARGS__; } break; \
+        case 1024: { using LN = Launch<1024>; RES = __VA_ARGS__; } break; \
+        case 2048: { using LN = Launch<2048>; RES = __VA_ARGS__; } break; \
+        case 4096: { using LN = Launch<4096>; RES = __VA_ARGS__; } break; \
+        default: RES = cudaErrorInvalidValue;                        \
+    }
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) return fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct swrt_flow {
+    swrt_flow_desc d{};
+    SpecLayout L{};
+    int nkr = 0, nvar = 3, njobs_a = 5, njobs_b = 4;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
+    double2 *tw_x = nullptr, *tw_y = nullptr;
+    double4* coef = nullptr;
+    double* snap[2] = {nullptr, nullptr};
+    int slot_map[2] = {0, 1};
+    double* phys = nullptr;
+    double* red = nullptr;  // reduction scratch (device)
+    int ring = 0;
+    double t = 0.0;
+    long long step = 0, launches = 0;
+};
+
+struct swrt_packets {
+    swrt_packets_desc d{};
+    swrt_flow* flow = nullptr;
+    double *xk = nullptr, *sign = nullptr, *U = nullptr, *Gd = nullptr;
+    unsigned long long* count = nullptr;
+};
+
+// ------------------------------------------------------------------ small kernels (api TU only)
+// host (nkr, nl, nvar) column-major  <->  device [var][l][kr_pad], dealiased
+__global__ void pack_sol_kernel(const double2* __restrict__ host_layout, double2* __restrict__ sol, SpecLayout L, int nkr, int nvar) {
+    const long long total = (long long)nvar * L.ny * L.kr_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kr = (int)(i % L.kr_pad);
+        const long long r = i / L.kr_pad;
+        const int l = (int)(r % L.ny), v = (int)(r / L.ny);
+        double2 val = make_double2(0.0, 0.0);
+        if (kr < L.kr_keep && l_retained(L, l)) val = host_layout[((long long)v * L.ny + l) * nkr + kr];
+        sol[i] = val;
+    }
+}
+__global__ void unpack_sol_kernel(const double2* __restrict__ sol, double2* __restrict__ host_layout, SpecLayout L, int nkr, int nvar) {
+    const long long total = (long long)nvar * L.ny * nkr;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int kr = (int)(i % nkr);
+        const long long r = i / nkr;
+        const int l = (int)(r % L.ny), v = (int)(r / L.ny);
+        double2 val = make_double2(0.0, 0.0);
+        if (kr < L.kr_keep && l_retained(L, l)) val = sol[((long long)v * L.ny + l) * L.kr_pad + kr];
+        host_layout[i] = val;
+    }
+}
+
+// block partial reductions: mode 0 = parsevalsum2 weights of |a|^2, mode 1 = max |x| of a real array, mode 2 = NaN count
+__global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ a, long long n, int mode, SpecLayout L, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (mode == 0) {
+            const int kr = (int)(i % L.kr_pad);
+            const double2 v = reinterpret_cast<const double2*>(a)[i];
+            const double w = (kr == 0 || kr == L.nx / 2) ? 1.0 : 2.0;
+            acc += w * (v.x * v.x + v.y * v.y);
+        } else if (mode == 1) {
+            acc = fmax(acc, fabs(a[i]));
+        } else {
+            acc += isnan(a[i]) ? 1.0 : 0.0;
+        }
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = mode == 1 ? fmax(sh[threadIdx.x], sh[threadIdx.x + s]) : sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// ------------------------------------------------------------------ helpers
+static bool supported_n(int n) { return n >= 32 && n <= 4096 && (n & (n - 1)) == 0; }
+
+static void alias_ranges(int n, int nkr, double a, int* lo, int* hi, int* krlo) {
+    // FourierFlows getaliasedwavenumbers; same float arithmetic as Julia
+    if (a > 0) {
+        const double Lf = (1 - a) / 2, Rf = (1 + a) / 2;
+        const int iL = (int)std::floor(Lf * n) + 1, iR = (int)std::ceil(Rf * n);
+        *lo = iL - 1;
+        *hi = iR;
+        *krlo = iL - 1;
+    } else {
+        *lo = n / 2;
+        *hi = n / 2 + 1;
+        *krlo = nkr - 1;
+    }
+}
+
+static cudaError_t upload_twiddles(int n, double2** out) {
+    std::vector<double2> tw(n);
+    for (int m = 0; m < n; ++m) {
+        // exact octant symmetries are not needed at 1e-16; use sincos of the reduced angle
+        const double ang = -2.0 * M_PI * (double)m / (double)n;
+        tw[m] = make_double2(std::cos(ang), std::sin(ang));
+    }
+    // exact values on the axes
+    tw[0] = make_double2(1.0, 0.0);
+    if (n >= 4) { tw[n / 4] = make_double2(0.0, -1.0); tw[n / 2] = make_double2(-1.0, 0.0); tw[3 * n / 4] = make_double2(0.0, 1.0); }
+    cudaError_t e = cudaMalloc(out, sizeof(double2) * n);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*out, tw.data(), sizeof(double2) * n, cudaMemcpyHostToDevice);
+}
+
+static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, cudaError_t* err) {
+    const int blocks = 296;
+    reduce_kernel<<<blocks, 256, 0, h->st>>>(a, n, mode, h->L, h->red);
+    h->launches++;
+    std::vector<double> part(blocks);
+    *err = cudaMemcpyAsync(part.data(), h->red, sizeof(double) * blocks, cudaMemcpyDeviceToHost, h->st);
+    if (*err != cudaSuccess) return 0;
+    *err = cudaStreamSynchronize(h->st);
+    double acc = 0;
+    for (double p : part) acc = mode == 1 ? std::fmax(acc, p) : acc + p;
+    return acc;
+}
+
+static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
+    FieldLoader ld{h->sol, h->L.vs, which, h->d.f};
+    cudaError_t e;
+    SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st));
+    CK(e);
+    SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->st));
+    CK(e);
+    h->launches += 2;
+    return SWRT_OK;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* swrt_last_error(void) { return g_err.c_str(); }
+int swrt_version(void) { return SWRT_VERSION; }
+int swrt_device_count(int* n) {
+    if (!n) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaGetDeviceCount(n));
+    return SWRT_OK;
+}
+
+int swrt_flow_destroy(swrt_flow* h) {
+    if (!h) return SWRT_OK;
+    cudaSetDevice(h->d.device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    cudaFree(h->sol);
+    for (auto p : h->Nb) cudaFree(p);
+    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef);
+    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return SWRT_OK;
+}
+
+int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
+    if (!desc || !out) return fail(SWRT_ERR_ARG, "null pointer");
+    *out = nullptr;
+    const swrt_flow_desc& d = *desc;
+    if (!supported_n(d.nx) || !supported_n(d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "nx, ny must be powers of two in [32, 4096] (got %d x %d)", d.nx, d.ny);
+    if (d.model != SWRT_RSW && d.model != SWRT_RSW_MODIFIED) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
+    if (d.stepper != SWRT_IFMAB3) return fail(SWRT_ERR_UNSUPPORTED, "stepper %d not implemented", d.stepper);
+    if (!(d.Lx > 0 && d.Ly > 0 && d.dt > 0)) return fail(SWRT_ERR_ARG, "Lx, Ly, dt must be positive");
+    if (!(d.aliased_fraction >= 0 && d.aliased_fraction < 1)) return fail(SWRT_ERR_ARG, "aliased_fraction must be in [0,1)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SWRT_ERR_CUDA, "no CUDA device available (libswrt has no CPU fallback)");
+    if (d.device < 0 || d.device >= ndev) return fail(SWRT_ERR_ARG, "device %d out of range (%d devices)", d.device, ndev);
+    CK(cudaSetDevice(d.device));
+
+    swrt_flow* h = new swrt_flow;
+    h->d = d;
+    h->nkr = d.nx / 2 + 1;
+    h->njobs_a = 5;
+    h->njobs_b = d.model == SWRT_RSW_MODIFIED ? 5 : 4;
+    SpecLayout& L = h->L;
+    L.nx = d.nx; L.ny = d.ny;
+    int klo, dummy0, dummy1;
+    alias_ranges(d.ny, h->nkr, d.aliased_fraction, &L.lz0, &L.lz1, &dummy0);
+    alias_ranges(d.nx, h->nkr, d.aliased_fraction, &dummy0, &dummy1, &klo);
+    L.kr_keep = klo;
+    L.kr_pad = (L.kr_keep + 15) / 16 * 16;
+    L.vs = (long long)L.ny * L.kr_pad;
+    L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
+    L.f = d.f; L.Cg2 = d.Cg * d.Cg; L.aux0 = L.aux1 = 0;
+
+    auto bail = [&](int code) { swrt_flow_destroy(h); return code; };
+#define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
+    CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CKB(cudaEventCreate(&h->ev0));
+    CKB(cudaEventCreate(&h->ev1));
+    const size_t fb = sizeof(double2) * (size_t)L.vs;
+    CKB(cudaMalloc(&h->sol, fb * h->nvar));
+    CKB(cudaMemset(h->sol, 0, fb * h->nvar));
+    for (int i = 0; i < 3; ++i) { CKB(cudaMalloc(&h->Nb[i], fb * h->nvar)); CKB(cudaMemset(h->Nb[i], 0, fb * h->nvar)); }
+    CKB(cudaMalloc(&h->G, fb * h->njobs_a)); CKB(cudaMemset(h->G, 0, fb * h->njobs_a));
+    CKB(cudaMalloc(&h->H, fb * h->njobs_b)); CKB(cudaMemset(h->H, 0, fb * h->njobs_b));
+    CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
+    CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
+    CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
+    for (int s = 0; s < 2; ++s) {
+        CKB(cudaMalloc(&h->snap[s], sizeof(double) * (size_t)d.nx * d.ny * SNAP_NC));
+        CKB(cudaMemset(h->snap[s], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_NC));
+    }
+    CKB(upload_twiddles(d.nx, &h->tw_x));
+    CKB(upload_twiddles(d.ny, &h->tw_y));
+
+    // coefficient table {e^{D dt}, sin(w dt)/w, (1-cos(w dt))/w^2, filter}
+    {
+        std::vector<double4> cf((size_t)L.vs, make_double4(1.0, 0.0, 0.0, 1.0));
+        const double w2c = d.model == SWRT_RSW_MODIFIED ? 0.0 : L.Cg2;
+        const double innerK = d.filter_innerK > 0 ? d.filter_innerK : 2.0 / 3.0, outerK = d.filter_outerK > 0 ? d.filter_outerK : 1.0;
+        const double tol = d.filter_tol > 0 ? d.filter_tol : 1e-15;
+        const int order = d.filter_order > 0 ? d.filter_order : 4;
+        const double decay = -std::log(tol) / std::pow(outerK - innerK, order);
+        const double dx = d.Lx / d.nx, dy = d.Ly / d.ny;
+        for (int l = 0; l < d.ny; ++l) {
+            const double lw = (double)(l < d.ny / 2 ? l : l - d.ny) * L.dl;
+            for (int kr = 0; kr < L.kr_keep; ++kr) {
+                const double kw = kr * L.dk, K2 = kw * kw + lw * lw;
+                const double D = -d.nu * std::pow(K2, (double)d.nnu);
+                const double w2 = d.f * d.f + w2c * K2, w = std::sqrt(w2), th = w * d.dt;
+                double s, c;
+                if (w > 0) { s = std::sin(th) / w; const double sh = std::sin(0.5 * th); c = 2.0 * sh * sh / w2; }
+                else { s = d.dt; c = 0.5 * d.dt * d.dt; }
+                double filt = 1.0;
+                if (d.use_filter) {
+                    const double Kn = std::sqrt((kw * dx / M_PI) * (kw * dx / M_PI) + (lw * dy / M_PI) * (lw * dy / M_PI));
+                    if (Kn >= innerK) filt = std::exp(-decay * std::pow(Kn - innerK, order));
+                }
+                cf[(size_t)l * L.kr_pad + kr] = make_double4(std::exp(D * d.dt), s, c, filt);
+            }
+        }
+        CKB(cudaMalloc(&h->coef, sizeof(double4) * cf.size()));
+        CKB(cudaMemcpy(h->coef, cf.data(), sizeof(double4) * cf.size(), cudaMemcpyHostToDevice));
+    }
+#undef CKB
+    *out = h;
+    return SWRT_OK;
+}
+
+int swrt_flow_set_solution(swrt_flow* h, const void* sol_host) {
+    if (!h || !sol_host) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    const size_t bytes = sizeof(double2) * (size_t)h->nkr * h->d.ny * h->nvar;
+    CK(cudaMemcpyAsync(h->stage, sol_host, bytes, cudaMemcpyHostToDevice, h->st));
+    pack_sol_kernel<<<592, 256, 0, h->st>>>(h->stage, h->sol, h->L, h->nkr, h->nvar);
+    CK(cudaGetLastError());
+    h->launches++;
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_get_solution(swrt_flow* h, void* sol_host) {
+    if (!h || !sol_host) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    unpack_sol_kernel<<<592, 256, 0, h->st>>>(h->sol, h->stage, h->L, h->nkr, h->nvar);
+    CK(cudaGetLastError());
+    h->launches++;
+    const size_t bytes = sizeof(double2) * (size_t)h->nkr * h->d.ny * h->nvar;
+    CK(cudaMemcpyAsync(sol_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_enforce_reality(swrt_flow* h) {
+    // rsw/RotatingShallowWater.jl:118-133: dealias!(sol) (already an invariant here); the round-tripped
+    // fields go to vars.*h, which calcN! overwrites from sol on the next step -- sol is otherwise untouched.
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    return SWRT_OK;
+}
+
+int swrt_flow_step(swrt_flow* h, int nsteps) {
+    if (!h || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    const int modified = h->d.model == SWRT_RSW_MODIFIED;
+    RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
+    RswCombiner cb{modified, L.Cg2};
+    const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+    const int ublocks = (int)((nmodes + 255) / 256);
+    for (int s = 0; s < nsteps; ++s) {
+        double2* Ncur = h->Nb[h->ring];
+        const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
+        const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
+        cudaError_t e;
+        RswLoaderA ld{h->sol, L.vs};
+        SWRT_DISPATCH(L.ny, e, LN::rsw_stage_a(ld, L, h->G, h->tw_y, h->st));
+        CK(e);
+        SWRT_DISPATCH(L.nx, e, LN::rsw_stage_b(modified, h->G, h->H, L, h->tw_x, h->st));
+        CK(e);
+        SWRT_DISPATCH(L.ny, e, LN::rsw_stage_c(cb, L, h->H, Ncur, h->tw_y, h->st));
+        CK(e);
+        UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, h->d.dt, h->step < 3 ? 1 : 0};
+        ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+        CK(cudaGetLastError());
+        h->launches += 4;
+        h->ring = (h->ring + 1) % 3;
+        h->t += h->d.dt;
+        h->step += 1;
+    }
+    return SWRT_OK;
+}
+
+int swrt_flow_clock(swrt_flow* h, double* t, long long* step) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (t) *t = h->t;
+    if (step) *step = h->step;
+    return SWRT_OK;
+}
+int swrt_flow_set_clock(swrt_flow* h, double t, long long step) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    h->t = t;
+    h->step = step;
+    return SWRT_OK;
+}
+
+int swrt_flow_get_field(swrt_flow* h, int which, double* real_host) {
+    if (!h || !real_host) return fail(SWRT_ERR_ARG, "null pointer");
+    if (!((which >= 0 && which < h->nvar) || which == SWRT_FIELD_ZETA)) return fail(SWRT_ERR_ARG, "unknown field %d", which);
+    CK(cudaSetDevice(h->d.device));
+    int rc = spectral_to_physical(h, which, h->phys);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(real_host, h->phys, sizeof(double) * (size_t)h->d.nx * h->d.ny, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    const double norm = h->d.Lx * h->d.Ly / ((double)L.nx * L.nx * (double)L.ny * L.ny);
+    cudaError_t e = cudaSuccess;
+    double p2[3];
+    for (int v = 0; v < 3; ++v) {
+        p2[v] = norm * reduce_host(h, reinterpret_cast<const double*>(h->sol + v * L.vs), L.vs, 0, &e);
+        CK(e);
+    }
+    const double A = h->d.Lx * h->d.Ly;
+    if (ke) *ke = p2[0] / (2 * A) + p2[1] / (2 * A);
+    if (pe) *pe = 0.5 * L.Cg2 * p2[2] / A;
+    return SWRT_OK;
+}
+
+int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e = cudaSuccess;
+    double* outs[2] = {umax, vmax};
+    for (int v = 0; v < 2; ++v) {
+        if (!outs[v]) continue;
+        int rc = spectral_to_physical(h, v, h->phys);
+        if (rc) return rc;
+        *outs[v] = reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e);
+        CK(e);
+    }
+    return SWRT_OK;
+}
+
+int swrt_flow_has_nan(swrt_flow* h, int* flag) {
+    if (!h || !flag) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e = cudaSuccess;
+    const double c = reduce_host(h, reinterpret_cast<const double*>(h->sol), 2 * h->L.vs, 2, &e);  // vars.uh
+    CK(e);
+    *flag = c > 0;
+    return SWRT_OK;
+}
+
+int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    if (psi_kind != SWRT_PSI_RSW_BALANCED) return fail(SWRT_ERR_UNSUPPORTED, "psi kind %d not implemented", psi_kind);
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, h->d.f * h->d.f / L.Cg2};
+    cudaError_t e;
+    SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st));
+    CK(e);
+    SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st));
+    CK(e);
+    h->launches += 2;
+    return SWRT_OK;
+}
+
+int swrt_flow_swap_snapshots(swrt_flow* h, int alias) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (alias) h->slot_map[0] = h->slot_map[1];
+    else { const int t = h->slot_map[0]; h->slot_map[0] = h->slot_map[1]; h->slot_map[1] = t; }
+    return SWRT_OK;
+}
+
+int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
+    if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->d.device));
+    const size_t n = (size_t)h->d.nx * h->d.ny;
+    std::vector<double> tmp(n * SNAP_NC);
+    CK(cudaMemcpyAsync(tmp.data(), h->snap[h->slot_map[slot]], sizeof(double) * n * SNAP_NC, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    for (int c = 0; c < SNAP_NC; ++c)
+        for (size_t i = 0; i < n; ++i) out_host[c * n + i] = tmp[i * SNAP_NC + c];
+    return SWRT_OK;
+}
+
+int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
+    if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->d.device));
+    const size_t n = (size_t)h->d.nx * h->d.ny;
+    std::vector<double> tmp(n * SNAP_NC);
+    for (int c = 0; c < SNAP_NC; ++c)
+        for (size_t i = 0; i < n; ++i) tmp[i * SNAP_NC + c] = in_host[c * n + i];
+    CK(cudaMemcpyAsync(h->snap[h->slot_map[slot]], tmp.data(), sizeof(double) * n * SNAP_NC, cudaMemcpyHostToDevice, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_timer_start(swrt_flow* h) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaEventRecord(h->ev0, h->st));
+    return SWRT_OK;
+}
+int swrt_flow_timer_stop(swrt_flow* h, float* ms) {
+    if (!h || !ms) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return SWRT_OK;
+}
+int swrt_flow_sync(swrt_flow* h) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+int swrt_flow_launch_count(swrt_flow* h, long long* n) {
+    if (!h || !n) return fail(SWRT_ERR_ARG, "null pointer");
+    *n = h->launches;
+    return SWRT_OK;
+}
+
+// ------------------------------------------------------------------ packets
+int swrt_packets_destroy(swrt_packets* p) {
+    if (!p) return SWRT_OK;
+    if (p->flow) { cudaSetDevice(p->flow->d.device); cudaStreamSynchronize(p->flow->st); }
+    cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->U); cudaFree(p->Gd); cudaFree(p->count);
+    delete p;
+    return SWRT_OK;
+}
+
+int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_packets** out) {
+    if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
+    *out = nullptr;
+    if (desc->n <= 0) return fail(SWRT_ERR_ARG, "n must be positive");
+    if (desc->interp != SWRT_INTERP_BILINEAR) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
+    if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
+    CK(cudaSetDevice(flow->d.device));
+    swrt_packets* p = new swrt_packets;
+    p->d = *desc;
+    p->flow = flow;
+    const size_t n = (size_t)desc->n;
+    cudaError_t e;
+    if ((e = cudaMalloc(&p->xk, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign, sizeof(double) * n)) != cudaSuccess ||
+        (e = cudaMalloc(&p->U, sizeof(double) * 2 * n)) != cudaSuccess || (e = cudaMalloc(&p->Gd, sizeof(double) * 4 * n)) != cudaSuccess ||
+        (e = cudaMalloc(&p->count, sizeof(unsigned long long))) != cudaSuccess) {
+        swrt_packets_destroy(p);
+        return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemset(p->xk, 0, sizeof(double) * 4 * n));
+    CK(cudaMemset(p->sign, 0, sizeof(double) * n));
+    *out = p;
+    return SWRT_OK;
+}
+
+int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* sign_host) {
+    if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(p->flow->d.device));
+    CK(cudaMemcpyAsync(p->xk, xk_host, sizeof(double) * 4 * (size_t)p->d.n, cudaMemcpyHostToDevice, p->flow->st));
+    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)p->d.n, cudaMemcpyHostToDevice, p->flow->st));
+    CK(cudaStreamSynchronize(p->flow->st));
+    return SWRT_OK;
+}
+
+int swrt_packets_get(swrt_packets* p, double* xk_host) {
+    if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(p->flow->d.device));
+    CK(cudaMemcpyAsync(xk_host, p->xk, sizeof(double) * 4 * (size_t)p->d.n, cudaMemcpyDeviceToHost, p->flow->st));
+    CK(cudaStreamSynchronize(p->flow->st));
+    return SWRT_OK;
+}
+
+int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN, long long first) {
+    if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(p->flow->d.device));
+    const long long n = p->d.n;
+    generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, n, first, sqrtN, L, k0);
+    CK(cudaGetLastError());
+    p->flow->launches++;
+    return SWRT_OK;
+}
+
+static PacketGrid packet_grid(const swrt_flow* f) {
+    PacketGrid g;
+    g.nx = f->d.nx; g.ny = f->d.ny;
+    g.dx = f->d.Lx / f->d.nx; g.dy = f->d.Ly / f->d.ny;
+    g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
+    return g;
+}
+
+int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
+    if (!p) return fail(SWRT_ERR_ARG, "null pointer");
+    if (!(t1 != t0)) return fail(SWRT_ERR_ARG, "t1 must differ from t0");
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
+    const long long n = p->d.n;
+    raytrace_rk4_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->sign, n, f->snap[f->slot_map[0]], f->snap[f->slot_map[1]],
+                                                                       packet_grid(f), rp);
+    CK(cudaGetLastError());
+    f->launches++;
+    return SWRT_OK;
+}
+
+int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host) {
+    if (!p || !u_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    const long long n = p->d.n;
+    sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    CK(cudaGetLastError());
+    f->launches++;
+    CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
+    if (g_host) CK(cudaMemcpyAsync(g_host, p->Gd, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
+    CK(cudaStreamSynchronize(f->st));
+    return SWRT_OK;
+}
+
+int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long long* nreset) {
+    if (!p) return fail(SWRT_ERR_ARG, "null pointer");
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    const long long n = p->d.n;
+    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), f->st));
+    kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, n, kcut * kcut, k0, p->count);
+    CK(cudaGetLastError());
+    f->launches++;
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, f->st));
+    CK(cudaStreamSynchronize(f->st));
+    if (nreset) *nreset = (long long)c;
+    return SWRT_OK;
+}
+
+// ------------------------------------------------------------------ output roll-over arithmetic
+int swrt_seqout_init(swrt_seqout* s, long long max_writes) {
+    if (!s || max_writes <= 0) return fail(SWRT_ERR_ARG, "bad argument");
+    s->max_writes = max_writes;
+    s->current_writes = 0;
+    s->file_index = 0;
+    return SWRT_OK;
+}
+int swrt_seqout_write(swrt_seqout* s, long long nwrites, long long* file_index) {
+    // utils/SequencedOutputs.jl:37-44,58-63: the key lands in the current file, THEN the counter is checked
+    if (!s) return fail(SWRT_ERR_ARG, "null pointer");
+    if (file_index) *file_index = s->file_index;
+    s->current_writes += nwrites;
+    if (s->current_writes >= s->max_writes) {
+        s->current_writes = 0;
+        s->file_index += 1;
+    }
+    return SWRT_OK;
+}
+int swrt_seqout_filename(const char* base, long long idx, char* buf, int buflen) {
+    if (!base || !buf || buflen <= 0) return fail(SWRT_ERR_ARG, "bad argument");
+    snprintf(buf, (size_t)buflen, "%s.%06lld.jld2", base, idx);   // raytracing/RaytracingDriver.jl:173-174
+    return SWRT_OK;
+}
+int swrt_collated_filename(const char* base, long long idx, char* buf, int buflen) {
+    if (!base || !buf || buflen <= 0) return fail(SWRT_ERR_ARG, "bad argument");
+    snprintf(buf, (size_t)buflen, "%s_%08lld.out", base, idx);    // utils/Collated.jl:58-60
+    return SWRT_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

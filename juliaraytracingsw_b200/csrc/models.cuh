@@ -1,0 +1,259 @@
+// Model functors for the generic passes + the fused IFMAB3 update + per-size launchers.
+//
+// Reference arithmetic being reproduced (file:line in the reference checkout):
+//   rsw/RotatingShallowWater.jl:140-230   calcN!  (RSW)      rsw/ModifiedShallowWater.jl:209-226 (extra term)
+//   utils/IFMAB3.jl:129-169               IFMAB3update! / stepforward!
+//   rsw/RSWRaytracingDriver.jl:63-67      get_streamfunction!
+//   raytracing/RaytracingDriver.jl:132-154 get_velocity_info
+#pragma once
+#include "passes.cuh"
+
+namespace swrt {
+
+enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2 };
+
+// ---------------------------------------------------------------- RSW family, stage A
+// jobs: 0 uh, 1 vh, 2 etah, 3 i l uh, 4 i l vh     (ux, vx are derived in the x-pass as i k G)
+struct RswLoaderA {
+    const double2* sol;
+    long long vs;
+    __device__ __forceinline__ double2 operator()(int job, int, int, double, double lw, long long off) const {
+        switch (job) {
+            case 0: return sol[off];
+            case 1: return sol[vs + off];
+            case 2: return sol[2 * vs + off];
+            case 3: { const double2 a = sol[off]; return make_double2(-lw * a.y, lw * a.x); }
+            default: { const double2 a = sol[vs + off]; return make_double2(-lw * a.y, lw * a.x); }
+        }
+    }
+};
+
+// ---------------------------------------------------------------- RSW family, stage B
+// p1 = u ux + v uy, p2 = u vx + v vy, p3 = u eta, p4 = v eta [, p5 = 1.5 - 0.5/(1+eta)^2]
+template <int N, bool MODIFIED>
+struct RswXOp {
+    const double2* G;  // [5][ny][kr_pad]
+    double2* H;        // [4 or 5][ny][kr_pad]
+    double sc;         // (1/(nx ny))^2 / 2
+    double s1;         // 1/(nx ny)
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
+        const long long ro = (long long)y * L.kr_pad;
+        const double2 *Gu = G + ro, *Gv = G + L.vs + ro, *Ge = G + 2 * L.vs + ro, *Guy = G + 3 * L.vs + ro,
+                      *Gvy = G + 4 * L.vs + ro;
+        cx.template load_pair<MUL_ONE, MUL_ONE>(0, Gu, Gv);
+        cx.ifft(0);                                     // buffer 0: u + i v
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft(1);                                     // buffer 1: ux + i uy
+        const double *ur = cx.re(0), *vr = cx.im(0);
+        double *br = cx.re(1), *bi = cx.im(1), *cr = cx.re(2), *ci = cx.im(2);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            cr[x] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+        }
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gv, Gvy);
+        cx.ifft(1);                                     // buffer 1: vx + i vy
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            ci[x] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+        }
+        cx.fft(2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, H + ro, H + L.vs + ro);
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, nullptr);
+        cx.ifft(1);                                     // buffer 1: eta
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            cr[x] = sc * (ur[x] * br[x]);
+            ci[x] = sc * (vr[x] * br[x]);
+        }
+        cx.fft(2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
+        if (MODIFIED) {
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int x = pad_index(cx.g + i * Gt);
+                const double e1 = 1.0 + s1 * br[x];
+                cr[x] = 0.5 * (1.5 - 0.5 / (e1 * e1));
+                ci[x] = 0.0;
+            }
+            cx.fft(2);
+            cx.template store_pair<MUL_ONE, MUL_ZERO>(2, H + 4 * L.vs + ro, nullptr);
+        }
+    }
+};
+
+// ---------------------------------------------------------------- RSW family, stage C
+// N_u = -P1 [- i c2 k P5], N_v = -P2 [- i c2 l P5], N_eta = -i k P3 - i l P4
+struct RswCombiner {
+    int modified;
+    double c2;
+    __device__ __forceinline__ int nin(int var) const { return var == 2 ? 2 : (modified ? 2 : 1); }
+    __device__ __forceinline__ int src(int var, int i) const { return var == 2 ? 2 + i : (i == 0 ? var : 4); }
+    __device__ __forceinline__ double2 apply(int var, int i, double2 v, double kw, double lw) const {
+        if (var == 2) {
+            const double w = i == 0 ? kw : lw;
+            return make_double2(w * v.y, -w * v.x);          // -i w v
+        }
+        if (i == 0) return make_double2(-v.x, -v.y);
+        const double w = c2 * (var == 0 ? kw : lw);
+        return make_double2(w * v.y, -w * v.x);              // -i c2 w v
+    }
+};
+
+// ---------------------------------------------------------------- plain spectral -> physical
+// one job: an expression of the state selected by `which` (see swrt.h SWRT_FIELD_*)
+struct FieldLoader {
+    const double2* sol;
+    long long vs;
+    int which;
+    double f;
+    __device__ __forceinline__ double2 operator()(int, int, int, double kw, double lw, long long off) const {
+        if (which < 16) return sol[(long long)which * vs + off];
+        // 16: RSW linear PV  zeta = i k vh - i l uh - f etah   (rsw/RotatingShallowWater.jl:108)
+        const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
+        return make_double2(-(kw * v.y - lw * u.y) - f * e.x, (kw * v.x - lw * u.x) - f * e.y);
+    }
+};
+
+template <int N>
+struct C2ROp {
+    const double2* G;  // [1][ny][kr_pad]
+    double* out;       // [ny][nx]
+    double s1;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(0, G + (long long)y * L.kr_pad, nullptr);
+        cx.ifft(0);
+        const double* r = cx.re(0);
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = cx.g + i * Gt;
+            out[(long long)y * N + x] = s1 * r[pad_index(x)];
+        }
+    }
+};
+
+// ---------------------------------------------------------------- velocity snapshot for packets
+// psi kinds
+enum { PSI_RSW_BALANCED = 0 };
+// jobs: 0 psih, 1 -i l psih (u), 2 l^2 psih (uy);   v = i k G0, ux = i k G1, vx = -k^2 G0
+struct PsiLoader {
+    const double2* sol;
+    long long vs;
+    int kind;
+    double f, Kd2;
+    __device__ __forceinline__ double2 operator()(int job, int, int, double kw, double lw, long long off) const {
+        const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
+        const double inv = -1.0 / (kw * kw + lw * lw + Kd2);
+        const double2 psi = make_double2(inv * (-(kw * v.y - lw * u.y) - f * e.x), inv * ((kw * v.x - lw * u.x) - f * e.y));
+        if (job == 0) return psi;
+        if (job == 1) return make_double2(lw * psi.y, -lw * psi.x);
+        return make_double2(lw * lw * psi.x, lw * lw * psi.y);
+    }
+};
+
+constexpr int SNAP_NC = 5;  // u, v, ux, uy, vx interleaved per grid point (vy = -ux)
+
+template <int N>
+struct SnapshotXOp {
+    const double2* G;  // [3][ny][kr_pad]
+    double* out;       // [ny][nx][5]
+    double s1;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
+        const long long ro = (long long)y * L.kr_pad;
+        const double2 *Gp = G + ro, *Gu = G + L.vs + ro, *Guy = G + 2 * L.vs + ro;
+        cx.template load_pair<MUL_ONE, MUL_IK>(0, Gu, Gp);
+        cx.ifft(0);  // u + i v
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft(1);  // ux + i uy
+        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, nullptr);
+        cx.ifft(2);  // vx
+        double* o = out + (long long)y * N * SNAP_NC;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = cx.g + i * Gt, p = pad_index(x);
+            double* q = o + (long long)x * SNAP_NC;
+            q[0] = s1 * cx.re(0)[p];
+            q[1] = s1 * cx.im(0)[p];
+            q[2] = s1 * cx.re(1)[p];
+            q[3] = s1 * cx.im(1)[p];
+            q[4] = s1 * cx.re(2)[p];
+        }
+    }
+};
+
+// ---------------------------------------------------------------- per-size launchers
+__host__ __device__ constexpr int tile_k(int N) { return N >= 2048 ? 2 : (N >= 256 ? 4096 / N : 16); }
+constexpr int XPASS_BUFFERS = 3;
+
+template <int N>
+struct Launch {
+    static constexpr int TK = tile_k(N);
+    static constexpr int G = group_size(N);
+    static constexpr size_t ysmem = (size_t)2 * TK * padded_len(N) * sizeof(double);
+    static constexpr size_t xsmem = (size_t)2 * XPASS_BUFFERS * padded_len(N) * sizeof(double);
+
+    // one-time per kernel: opt in to the dynamic shared memory and size a persistent grid
+    template <class K>
+    static cudaError_t prep(K kernel, size_t smem, int threads, int* ctas) {
+        static int cached = 0;  // one static per (N, K) instantiation
+        if (!cached) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 0, occ = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+            if (e != cudaSuccess) return e;
+            cached = sms * (occ > 0 ? occ : 1);
+        }
+        *ctas = cached;
+        return cudaSuccess;
+    }
+    template <class Loader>
+    static cudaError_t ypass_inv(const Loader& ld, const SpecLayout& L, int njobs, double2* out, const double2* tw,
+                                 cudaStream_t st) {
+        auto k = ypass_inv_kernel<N, TK, Loader>;
+        int mc = 1;
+        cudaError_t e = prep(k, ysmem, TK * G, &mc);
+        if (e != cudaSuccess) return e;
+        const int work = ((L.kr_keep + TK - 1) / TK) * njobs;
+        k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(ld, L, njobs, out, tw);
+        return cudaGetLastError();
+    }
+    template <class Combiner>
+    static cudaError_t ypass_fwd(const Combiner& cb, const SpecLayout& L, int nvars, const double2* H, double2* out,
+                                 const double2* tw, cudaStream_t st) {
+        auto k = ypass_fwd_kernel<N, TK, Combiner>;
+        int mc = 1;
+        cudaError_t e = prep(k, ysmem, TK * G, &mc);
+        if (e != cudaSuccess) return e;
+        const int work = ((L.kr_keep + TK - 1) / TK) * nvars;
+        k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(cb, L, nvars, H, out, tw);
+        return cudaGetLastError();
+    }
+    template <class Op>
+    static cudaError_t xpass(const Op& op, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+        auto k = xpass_kernel<N, Op>;
+        int mc = 1;
+        cudaError_t e = prep(k, xsmem, G, &mc);
+        if (e != cudaSuccess) return e;
+        k<<<L.ny < mc ? L.ny : mc, G, xsmem, st>>>(op, L, tw);
+        return cudaGetLastError();
+    }
+
+    // concrete entry points (explicitly instantiated per size in inst.cu)
+    static cudaError_t rsw_stage_a(const RswLoaderA& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t rsw_stage_b(int modified, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t rsw_stage_c(const RswCombiner& cb, const SpecLayout& L, const double2* H, double2* Nout, const double2* tw, cudaStream_t st);
+    static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t psi_stage_a(const PsiLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
+};
+
+}  // namespace swrt

@@ -1,0 +1,213 @@
+// Generic y-pass / x-pass kernels of the pseudo-spectral step (sm_100a, fp64).
+//
+// Spectral arrays are stored dealiased and padded:  a[var][l][kr_pad] (complex128), only
+// kr < kr_keep and l outside [lz0, lz1) are ever non-zero ("sol is dealiased after every
+// step": rsw/RotatingShallowWater.jl:141 applies dealias!(sol) at the top of every calcN!).
+// A 2-D transform is two passes with the physical-space row living only on chip:
+//
+//   ypass_inv   columns (fixed kr, all l)  -> G[job][y][kr]     complex FFT along l
+//   xpass       rows    (fixed y,  all kr) -> c2r, pointwise products, r2c -> H[job][y][kr]
+//   ypass_fwd   columns of H               -> spectral N[var][l][kr]
+//
+// Model-specific arithmetic (which spectral expression feeds which transform, which
+// products are formed, how transforms combine into N) is supplied by small functors.
+#pragma once
+#include "fft.cuh"
+
+namespace swrt {
+
+struct SpecLayout {
+    int nx, ny;        // physical grid
+    int kr_keep;       // retained kr columns [0, kr_keep)
+    int kr_pad;        // leading dimension (multiple of 16)
+    int lz0, lz1;      // zeroed l index band [lz0, lz1)
+    long long vs;      // var stride = ny * kr_pad (complex elements)
+    double dk, dl;     // 2 pi / Lx, 2 pi / Ly
+    double f, Cg2;     // model constants used by loaders
+    double aux0, aux1; // model specific (Kd2, ...)
+};
+
+__device__ __forceinline__ double wave_l(const SpecLayout& L, int j) {
+    return (double)(j < L.ny / 2 ? j : j - L.ny) * L.dl;
+}
+__device__ __forceinline__ bool l_retained(const SpecLayout& L, int j) { return j < L.lz0 || j >= L.lz1; }
+
+__host__ __device__ constexpr int group_size(int N) { return N >= 16 ? N / 16 : 1; }
+
+// ------------------------------------------------------------------------------------
+// y-pass, inverse direction: out[job][y][kr] = sum_l src_job(kr, l) exp(+2 pi i l y / ny)
+// Loader: __device__ double2 operator()(int job, int kr, int l, double kw, double lw, long long off)
+// ------------------------------------------------------------------------------------
+template <int N, int TK, class Loader>
+__global__ void __launch_bounds__(TK* group_size(N))
+    ypass_inv_kernel(Loader ld, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
+    extern __shared__ double smem[];
+    constexpr int G = group_size(N), NP = padded_len(N), RPT = N / G;  // rows per thread
+    double* re = smem;
+    double* im = smem + TK * NP;
+    const int tid = threadIdx.x;
+    const int c = tid % TK, r0 = tid / TK;   // load/store mapping: TK adjacent lanes = TK adjacent kr
+    const int fg = tid / G, g = tid % G;     // fft mapping: group fg transforms column fg
+    const int ntiles = (L.kr_keep + TK - 1) / TK;
+    for (int w = blockIdx.x; w < ntiles * njobs; w += gridDim.x) {
+        const int job = w / ntiles, kr0 = (w % ntiles) * TK;
+        const int kr = kr0 + c;
+        const double kw = kr * L.dk;
+#pragma unroll 4
+        for (int i = 0; i < RPT; ++i) {
+            const int l = r0 + i * G;
+            double2 v = make_double2(0.0, 0.0);
+            if (kr < L.kr_keep && l_retained(L, l)) v = ld(job, kr, l, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+            re[c * NP + pad_index(l)] = v.x;
+            im[c * NP + pad_index(l)] = v.y;
+        }
+        block_fft<N, +1>(re + fg * NP, im + fg * NP, g, tw);
+        double2* o = out + (long long)job * L.vs;
+        if (kr < L.kr_keep) {
+#pragma unroll 4
+            for (int i = 0; i < RPT; ++i) {
+                const int y = r0 + i * G;
+                o[(long long)y * L.kr_pad + kr] = make_double2(re[c * NP + pad_index(y)], im[c * NP + pad_index(y)]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// y-pass, forward direction, with combination into output variables.
+// Combiner:  int nin(int var); int src(int var, int i);
+//            double2 apply(int var, int i, double2 v, double kw, double lw)
+// out[var][l][kr] = sum_i apply(var, i, FFT_y(H[src(var,i)])[kr, l])
+// ------------------------------------------------------------------------------------
+template <int N, int TK, class Combiner>
+__global__ void __launch_bounds__(TK* group_size(N))
+    ypass_fwd_kernel(Combiner cb, SpecLayout L, int nvars, const double2* __restrict__ H, double2* __restrict__ out,
+                     const double2* __restrict__ tw) {
+    extern __shared__ double smem[];
+    constexpr int G = group_size(N), NP = padded_len(N), RPT = N / G;
+    double* re = smem;
+    double* im = smem + TK * NP;
+    const int tid = threadIdx.x;
+    const int c = tid % TK, r0 = tid / TK;
+    const int fg = tid / G, g = tid % G;
+    const int ntiles = (L.kr_keep + TK - 1) / TK;
+    for (int w = blockIdx.x; w < ntiles * nvars; w += gridDim.x) {
+        const int var = w / ntiles, kr0 = (w % ntiles) * TK;
+        const int kr = kr0 + c;
+        const double kw = kr * L.dk;
+        double2* o = out + (long long)var * L.vs;
+        const int nin = cb.nin(var);
+        for (int i_in = 0; i_in < nin; ++i_in) {
+            const double2* h = H + (long long)cb.src(var, i_in) * L.vs;
+#pragma unroll 4
+            for (int i = 0; i < RPT; ++i) {
+                const int y = r0 + i * G;
+                double2 v = make_double2(0.0, 0.0);
+                if (kr < L.kr_keep) v = h[(long long)y * L.kr_pad + kr];
+                re[c * NP + pad_index(y)] = v.x;
+                im[c * NP + pad_index(y)] = v.y;
+            }
+            block_fft<N, -1>(re + fg * NP, im + fg * NP, g, tw);
+            if (kr < L.kr_keep) {
+#pragma unroll 4
+                for (int i = 0; i < RPT; ++i) {
+                    const int l = r0 + i * G;
+                    if (!l_retained(L, l)) continue;
+                    const long long off = (long long)l * L.kr_pad + kr;
+                    double2 v = cb.apply(var, i_in, make_double2(re[c * NP + pad_index(l)], im[c * NP + pad_index(l)]),
+                                         kw, wave_l(L, l));
+                    if (i_in > 0) {
+                        const double2 prev = o[off];
+                        v.x += prev.x;
+                        v.y += prev.y;
+                    }
+                    o[off] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// x-pass helpers: one CTA of G = N/16 threads owns NB complex work buffers of length N.
+// Two real fields travel through one complex transform: z = a + i b.
+// ------------------------------------------------------------------------------------
+enum { MUL_ONE = 0, MUL_IK = 1, MUL_MK2 = 2, MUL_ZERO = 3 };
+
+template <int M>
+__device__ __forceinline__ double2 apply_mul(double2 v, double kw) {
+    if (M == MUL_IK) return make_double2(-kw * v.y, kw * v.x);
+    if (M == MUL_MK2) return make_double2(-kw * kw * v.x, -kw * kw * v.y);
+    return v;
+}
+
+template <int N>
+struct XCtx {
+    static constexpr int G = group_size(N), NP = padded_len(N), EPT = N / G;
+    double* smem;
+    const double2* tw;
+    int g, kr_keep;
+    double dk;
+    __device__ __forceinline__ double* re(int b) const { return smem + (2 * b) * NP; }
+    __device__ __forceinline__ double* im(int b) const { return smem + (2 * b + 1) * NP; }
+
+    // Build the Hermitian-extended spectrum of z = a + i b from the half spectra A, B (rows of
+    // kr_pad complex).  Only the real parts of A[0], B[0] enter, like a c2r transform.
+    template <int MA, int MB>
+    __device__ __forceinline__ void load_pair(int b, const double2* __restrict__ A, const double2* __restrict__ B) const {
+        double *r = re(b), *m = im(b);
+        __syncthreads();  // earlier pointwise readers of this buffer are done
+        for (int k = g; k < N / 2; k += G) {
+            double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
+            if (k < kr_keep) {
+                const double kw = k * dk;
+                za = apply_mul<MA>(__ldg(&A[k]), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(&B[k]), kw);
+            }
+            if (k == 0) {
+                r[0] = za.x;
+                m[0] = zb.x;
+                r[pad_index(N / 2)] = 0.0;
+                m[pad_index(N / 2)] = 0.0;
+            } else {
+                r[pad_index(k)] = za.x - zb.y;
+                m[pad_index(k)] = za.y + zb.x;
+                r[pad_index(N - k)] = za.x + zb.y;
+                m[pad_index(N - k)] = zb.x - za.y;
+            }
+        }
+    }
+    __device__ __forceinline__ void ifft(int b) const { block_fft<N, +1>(re(b), im(b), g, tw); }
+    __device__ __forceinline__ void fft(int b) const { block_fft<N, -1>(re(b), im(b), g, tw); }
+
+    // After a forward transform of z = p + i q:  2 P[k] = Z[k] + conj Z[N-k],  2i Q[k] = Z[k] - conj Z[N-k].
+    // Writes 2P and 2Q (callers fold the 1/2 into their scaling) for k < kr_keep.
+    template <int MP, int MQ>
+    __device__ __forceinline__ void store_pair(int b, double2* __restrict__ P, double2* __restrict__ Q) const {
+        const double *r = re(b), *m = im(b);
+        for (int k = g; k < kr_keep; k += G) {
+            const int kn = (N - k) & (N - 1);
+            const double a = r[pad_index(k)], bb = m[pad_index(k)], c = r[pad_index(kn)], d = m[pad_index(kn)];
+            const double kw = k * dk;
+            P[k] = apply_mul<MP>(make_double2(a + c, bb - d), kw);
+            if (MQ != MUL_ZERO) Q[k] = apply_mul<MQ>(make_double2(bb + d, c - a), kw);
+        }
+        __syncthreads();
+    }
+};
+
+template <int N, class Op>
+__global__ void __launch_bounds__(group_size(N)) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
+    extern __shared__ double smem[];
+    XCtx<N> cx;
+    cx.smem = smem;
+    cx.tw = tw;
+    cx.g = threadIdx.x;
+    cx.kr_keep = L.kr_keep;
+    cx.dk = L.dk;
+    for (int y = blockIdx.x; y < L.ny; y += gridDim.x) op.row(cx, L, y);
+}
+
+}  // namespace swrt

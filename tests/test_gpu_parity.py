@@ -1,0 +1,206 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on identical inputs.
+Tolerances: spectral state <= 1e-10 relative L2 after 100 steps; packets <= 1e-8 relative (north star);
+integer / indexing results bit-exact."""
+import numpy as np
+import pytest
+
+import juliaraytracingsw_b200 as swrt
+from juliaraytracingsw_b200 import flow, raytracing
+from oracle import raytrace as oray
+from oracle import rsw as orsw
+from oracle.grid import TwoDGrid, makefilter
+
+from helpers import config2_setup, oracle_steps, random_state, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nx,ny", [(32, 32), (64, 64), (128, 64), (64, 256), (512, 512), (1024, 1024)])
+def test_inverse_transform_matches_irfft2(nx, ny):
+    g, sol = random_state(nx, ny, seed=nx + ny)
+    prob = swrt.Problem(nx=nx, ny=ny, f=3.0, dt=1e-3)
+    prob.sol = sol
+    np.testing.assert_array_equal(prob.sol, sol)                  # pack/unpack is lossless on a dealiased state
+    for which, name in ((0, "u"), (1, "v"), (2, "eta")):
+        want = g.irfft2(sol[:, :, which])
+        got = getattr(prob.vars, name)
+        assert rel_l2(got, want) < 2e-14, (name, rel_l2(got, want))
+    p = orsw.Params(0, 4, 3.0, 1.0)
+    assert rel_l2(prob.vars.zeta, orsw.updatevars(sol.copy(), g, p)[3]) < 2e-14
+
+
+def test_set_solution_dealiases_and_ignores_nonhermitian_dc_column():
+    g = TwoDGrid(64)
+    rng = np.random.default_rng(5)
+    sol = rng.standard_normal((g.nkr, g.nl, 3)) + 1j * rng.standard_normal((g.nkr, g.nl, 3))   # aliased + non-Hermitian
+    prob = swrt.Problem(nx=64, f=3.0, dt=1e-3)
+    prob.sol = sol
+    want = g.dealias(sol.copy())
+    np.testing.assert_array_equal(prob.sol, want)
+    assert rel_l2(prob.vars.u, g.irfft2(want[:, :, 0])) < 2e-14    # c2r semantics: Re of the kr=0 column after the l-transform
+
+
+@pytest.mark.parametrize("model,variant", [("RotatingShallowWater", orsw.RSW), ("ModifiedShallowWater", orsw.MODIFIED)])
+@pytest.mark.parametrize("nx", [64, 128])
+def test_rsw_100_steps_parity(model, variant, nx):
+    g, p, sol0, c = config2_setup(nx)
+    prob = swrt.Problem(model=model, nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    for nsteps, done in ((1, 1), (3, 4), (96, 100)):               # Euler start-up (3 calls), first AB3 step, then 100
+        flow.stepforward(prob, (), nsteps)
+        want = oracle_steps(g, p, sol0, c["dt"], done, variant)
+        err = rel_l2(prob.sol, want)
+        assert err < 1e-10, (done, err)
+        assert prob.clock.step == done and abs(prob.clock.t - done * c["dt"]) < 1e-12
+
+
+def test_rsw_filter_parity():
+    nx = 64
+    g, p, sol0, c = config2_setup(nx)
+    prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=0.0, nnu=c["nnu"], use_filter=True, order=8)
+    prob.sol = sol0
+    flow.stepforward(prob, (), 20)
+    p0 = orsw.Params(0.0, c["nnu"], c["f"], c["Cg"])
+    want = oracle_steps(g, p0, sol0, c["dt"], 20, filt=makefilter(g, order=8))
+    assert rel_l2(prob.sol, want) < 1e-10
+
+
+def test_energies_and_diagnostics():
+    g, p, sol0, c = config2_setup(128)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    assert abs(flow.kinetic_energy(prob) / orsw.kinetic_energy(sol0, g) - 1) < 1e-13
+    assert abs(flow.potential_energy(prob) / orsw.potential_energy(sol0, g, p) - 1) < 1e-13
+    u, v, _, _ = orsw.updatevars(sol0.copy(), g, p)
+    um, vm = flow.max_abs_uv(prob)
+    assert abs(um / np.abs(u).max() - 1) < 1e-13 and abs(vm / np.abs(v).max() - 1) < 1e-13
+    assert flow.has_nan(prob) is False
+    bad = sol0.copy(); bad[3, 4, 0] = np.nan
+    prob.sol = bad
+    assert flow.has_nan(prob) is True
+
+
+def test_velocity_snapshot_parity():
+    g, p, sol0, c = config2_setup(128)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    vel, grad = raytracing.get_velocity_info(prob, 1)
+    want = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)
+    got = vel._arr()
+    for c_ in range(5):
+        assert rel_l2(got[:, :, c_], want[:, :, c_]) < 1e-13, c_
+    np.testing.assert_array_equal(grad.vy, -got[:, :, 2])
+
+
+def _packet_case(nx, n_side, seed):
+    g, p, sol0, c = config2_setup(nx)
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 1)
+    Fo = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)
+    Fn = oray.get_velocity_info(orsw.get_streamfunction(sol1, g, p), g)
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], n_side)
+    rng = np.random.default_rng(seed)
+    xk[:, 0:2] += rng.uniform(-40, 40, size=(xk.shape[0], 2))     # packets are never wrapped into the domain
+    return g, c, Fo, Fn, xk, sign
+
+
+@pytest.mark.parametrize("lerp", [0, 1])
+@pytest.mark.parametrize("nsub", [1, 4])
+def test_raytrace_parity(lerp, nsub):
+    g, c, Fo, Fn, xk, sign = _packet_case(128, 48, 3)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_velocity_info(prob, 0, Fo)
+    raytracing.set_velocity_info(prob, 1, Fn)
+    pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=nsub, time_lerp=lerp)
+    pk.set(xk, sign)
+    t0, t1 = 0.3, 0.3 + 25 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t0, t1))
+    want = oray.raytrace(xk.copy(), sign, t0, t1, Fo, Fn, g, c["f"], c["Cg"], nsub=nsub, lerp=lerp)
+    got = pk.get()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-8
+    assert rel_l2(got, want) < 1e-12
+    # sampler for output frames
+    U, G = oray.interpolate_velocity(Fn, want[:, 0:2], g)
+    pk.set(want, sign)
+    np.testing.assert_allclose(raytracing.interpolate_velocity(raytracing.Velocity(prob, 1), pk), U, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 1), pk), G, rtol=0, atol=1e-12)
+
+
+def test_sampler_exact_at_nodes_K6():
+    g = TwoDGrid(64)
+    rng = np.random.default_rng(0)
+    F = rng.standard_normal((64, 64, 5))
+    prob = swrt.Problem(nx=64, f=3.0, dt=1e-3)
+    raytracing.set_velocity_info(prob, 0, F)
+    ii, jj = np.meshgrid(np.arange(0, 64, 16), np.arange(0, 64, 16), indexing="ij")
+    xk = np.zeros((16, 4)); xk[:, 0] = g.x[ii.ravel()]; xk[:, 1] = g.y[jj.ravel()]
+    pk = raytracing.Packets(prob, 16, 3.0, 1.0)
+    pk.set(xk, np.ones(16))
+    U = raytracing.interpolate_velocity(raytracing.Velocity(prob, 0), pk)
+    np.testing.assert_array_equal(U, F[ii.ravel(), jj.ravel(), 0:2])
+
+
+def test_packet_generation_and_sharding_bit_exact_lattice():
+    prob = swrt.Problem(nx=64, f=3.0, dt=1e-3)
+    n_side, L, k0 = 12, 2 * np.pi, 5.196152422706632
+    want, sign = oray.generate_initial_wavepackets(L, k0, n_side)
+    N = n_side * n_side
+    parts = []
+    for r in range(3):                                            # three contiguous shards, like ranks
+        lo, hi = r * N // 3, (r + 1) * N // 3
+        pk = raytracing.generate_initial_wavepackets(prob, L, k0, hi - lo, n_side, 3.0, 1.0, first=lo)
+        parts.append(pk.get())
+    got = np.concatenate(parts, axis=0)
+    np.testing.assert_array_equal(got[:, 0:2], want[:, 0:2])      # lattice: IEEE mul/div/sub only -> bit exact
+    np.testing.assert_allclose(got[:, 2:4], want[:, 2:4], rtol=0, atol=4e-15)
+
+
+def test_kcutoff_reset_bit_exact():
+    prob = swrt.Problem(nx=64, f=3.0, dt=1e-3)
+    rng = np.random.default_rng(2)
+    xk = rng.standard_normal((1000, 4)) * 40
+    xk[0, 2:4] = (30.0, 40.0)                                     # exactly on the cutoff circle -> reset (>=)
+    pk = raytracing.Packets(prob, 1000, 3.0, 1.0)
+    pk.set(xk, np.ones(1000))
+    want = xk.copy()
+    n_want = oray.kcutoff_reset(want, 50.0, 5.2)
+    assert pk.kcutoff_reset(50.0, 5.2) == n_want
+    np.testing.assert_array_equal(pk.get(), want)
+
+
+def test_snapshot_aliasing_quirk_flag():
+    g, p, sol0, c = config2_setup(64)
+    prob = swrt.Problem(nx=64, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    raytracing.get_velocity_info(prob, 0)
+    flow.stepforward(prob, (), 5)
+    raytracing.get_velocity_info(prob, 1)
+    old0, new0 = raytracing.Velocity(prob, 0)._arr(), raytracing.Velocity(prob, 1)._arr()
+    assert np.abs(old0 - new0).max() > 0
+    raytracing.swap_snapshots(prob, alias=False)
+    np.testing.assert_array_equal(raytracing.Velocity(prob, 0)._arr(), new0)
+    np.testing.assert_array_equal(raytracing.Velocity(prob, 1)._arr(), old0)
+    raytracing.swap_snapshots(prob, alias=True)                   # reference rebinding: both names -> same buffer
+    np.testing.assert_array_equal(raytracing.Velocity(prob, 0)._arr(), raytracing.Velocity(prob, 1)._arr())
+
+
+def test_full_size_properties_2048():
+    """BASELINE config-4 size: size-independent properties instead of an oracle run."""
+    nx = 2048
+    g, p, sol0, c = config2_setup(nx)
+    prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    # Parseval: sum u^2 dx dy == parsevalsum2(uh)
+    u = prob.vars.u
+    ke = flow.kinetic_energy(prob)
+    v = prob.vars.v
+    assert abs(0.5 * ((u ** 2).sum() + (v ** 2).sum()) * g.dx * g.dy / (g.Lx * g.Ly) / ke - 1) < 1e-12
+    assert rel_l2(u, g.irfft2(sol0[:, :, 0])) < 1e-13
+    # one step against the oracle (a single 2048^2 oracle step takes a few seconds), then invariants over 20 more
+    flow.stepforward(prob, (), 1)
+    assert rel_l2(prob.sol, oracle_steps(g, p, sol0, c["dt"], 1)) < 1e-11
+    e0 = flow.kinetic_energy(prob) + flow.potential_energy(prob)
+    flow.stepforward(prob, (), 20)
+    e1 = flow.kinetic_energy(prob) + flow.potential_energy(prob)
+    assert abs(e1 / e0 - 1) < 1e-3 and not flow.has_nan(prob)
+    sol = prob.sol
+    assert np.all(sol[g.kr_alias[0]:] == 0) and np.all(sol[:, g.l_alias[0]:g.l_alias[1]] == 0)   # stays dealiased
