@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the coupled hot path: RSW 2048^2 IFMAB3 flow step + velocity snapshot + RK4 ray tracing
+of 16,777,216 wave packets (BASELINE.json config 4), one process per GPU, packets sharded in contiguous
+blocks over the ranks with a replicated flow (no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl swrt|reference]
+
+One JSON line on stdout (rank 0).  `value` = packet-steps/s with everything resident in HBM; `e2e` = the same
+step through the public API with pinned HOST packet buffers copied in and the output frame copied out every
+step; `roofline` = the dominant kernel; `spectral_step` = the flow-only step against the 42 F contract of
+SURVEY.md section 8(d); `cpu_baseline` = the NumPy/SciPy oracle on the host cores (bounded sample).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="swrt", choices=["swrt", "reference"])
+    ap.add_argument("--nx", type=int, default=2048)
+    ap.add_argument("--sqrt-packets", type=int, default=4096)
+    ap.add_argument("--nsub", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+WORKLOAD = "RSW {nx}^2 IFMAB3 flow step + velocity snapshot + RK4 ray tracing of {n} wave packets (BASELINE config 4)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU / reference arm
+def cpu_sample(args, steps, warmup, cores):
+    """The oracle (NumPy/SciPy restatement of the reference algorithm; the reference itself needs Julia, absent
+    here) on the host cores: the full 2048^2 flow step + velocity info, and RK4 ray tracing of a 2^18-packet sample
+    threaded over all cores; the packet cost is scaled to the full packet count."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import config2_setup
+    from oracle import ifmab3, raytrace as oray, rsw as orsw
+
+    nx, ntot = args.nx, args.sqrt_packets ** 2
+    nsample = min(ntot, 1 << 18)
+    g, p, sol, c = config2_setup(nx)
+    ts = ifmab3.IFMAB3(np.zeros((1, 1, 3, 3)), c["dt"], lambda s: orsw.calcN(s, g, p))
+    ts.expLdt = ifmab3.expL_closed_form(g, p, c["dt"])
+    ts.exp2Ldt = ifmab3.expL_closed_form(g, p, 2 * c["dt"])
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], int(round(nsample ** 0.5)))
+    nsample = xk.shape[0]
+    Fo = oray.get_velocity_info(orsw.get_streamfunction(sol, g, p), g)
+    chunks = np.array_split(np.arange(nsample), cores)
+    pool = ThreadPoolExecutor(cores)
+    t_flow = t_pk = 0.0
+    told = 0.0
+    for it in range(warmup + steps):
+        a = time.perf_counter()
+        ts.stepforward(sol)
+        Fn = oray.get_velocity_info(orsw.get_streamfunction(sol, g, p), g)
+        b = time.perf_counter()
+        tnew = told + c["dt"]
+
+        def work(idx):
+            z = xk[idx].copy()
+            oray.raytrace(z, sign[idx], told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub)
+            xk[idx] = z
+        list(pool.map(work, chunks))
+        cend = time.perf_counter()
+        Fo, told = Fn, tnew
+        if it >= warmup:
+            t_flow += b - a
+            t_pk += cend - b
+    pool.shutdown()
+    t_step = t_flow / steps + (t_pk / steps) * (ntot / nsample)
+    return dict(value=ntot / t_step, ms_per_step=1e3 * t_step, flow_ms=1e3 * t_flow / steps,
+                packet_ms_sample=1e3 * t_pk / steps, nsample=nsample,
+                sample=(f"per step: full {nx}^2 oracle flow step + velocity info, RK4 of {nsample} packets on {cores} threads "
+                        f"scaled x{ntot / nsample:.0f} to {ntot} packets; {steps} steps after {warmup} warm-up"))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 5))
+    r = cpu_sample(args, steps, min(args.warmup, 1), cores)
+    ntot = args.sqrt_packets ** 2
+    line = {
+        "impl": "reference", "metric": "packet-steps/s", "value": r["value"], "unit": "packet-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "nsub": args.nsub,
+                   "integrator": "RK4", "interp": "bilinear"},
+        "cpu_baseline": {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "packet-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/); the reference itself is Julia and cannot run here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_swrt(args):
+    import torch
+
+    import juliaraytracingsw_b200 as swrt
+    from juliaraytracingsw_b200 import drivers, flow, raytracing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl swrt needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    P = drivers.Parameters(nx=args.nx, sqrtNpackets=args.sqrt_packets, nsub=args.nsub)
+    ntot = P.Npackets
+    lo, hi = rank * ntot // world, (rank + 1) * ntot // world
+    nloc = hi - lo
+    prob, _ = drivers.initialize_problem(P, dev=local)
+    k0 = (P.ω0 ** 2 - P.f ** 2) ** 0.5 / P.background_Cg
+    packets = raytracing.generate_initial_wavepackets(prob, P.L, k0, nloc, P.sqrtNpackets, P.f, P.packet_Cg, nsub=P.nsub, first=lo)
+    raytracing.get_velocity_info(prob, 0)
+    t = prob.clock.t
+    K, W = args.steps, max(args.warmup, 3)
+
+    clocks = ClockSampler(local)
+    # ---- device-resident timed region
+    for _ in range(W):
+        t = drivers.coupled_step(prob, packets, t)
+    prob.sync(); barrier()
+    l0 = prob.launch_count()
+    prob.timer_start()
+    for _ in range(K):
+        t = drivers.coupled_step(prob, packets, t)
+    ms = prob.timer_stop()
+    barrier()
+    launches = prob.launch_count() - l0
+    ms = max_over_ranks(ms)
+    value = ntot * K / (ms * 1e-3)
+
+    # ---- same K steps with per-kernel CUDA events (roofline of the dominant kernel)
+    prob.profile(2)
+    for _ in range(K):
+        t = drivers.coupled_step(prob, packets, t)
+    prob.sync()
+    kern = prob.profile_report()
+    prob.profile(0)
+
+    # ---- flow-only step (BASELINE: "RSW 2048^2 spectral steps/s (HBM %roofline)")
+    prob.sync(); barrier()
+    prob.timer_start()
+    flow.stepforward(prob, (), K)
+    ms_flow = max_over_ranks(prob.timer_stop()) / K
+
+    # ---- end to end: pinned host packets in, output frame out, every step, through the public API
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda *shape: torch.empty(shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T  # Fortran-ordered view
+        h_xk, h_U, h_G = pin(nloc, 4), pin(nloc, 2), pin(nloc, 4)
+        h_sign = torch.empty(nloc, dtype=torch.float64, pin_memory=True).numpy()
+        packets.get(out=h_xk)
+        h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
+        Ke = max(3, min(K, 10))
+
+        def e2e_step(t):
+            packets.set(h_xk, h_sign)
+            t = drivers.coupled_step(prob, packets, t)
+            packets.get(out=h_xk)
+            raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), packets, output_G=h_G, output_U=h_U)
+            return t
+        t = e2e_step(t)
+        prob.sync(); barrier()
+        w0 = time.perf_counter()
+        prob.timer_start()
+        for _ in range(Ke):
+            t = e2e_step(t)
+        ms_e = prob.timer_stop()
+        wall = (time.perf_counter() - w0) * 1e3
+        barrier()
+        ms_e = max_over_ranks(max(ms_e, wall))
+        e2e = {"value": ntot * Ke / (ms_e * 1e-3), "unit": "packet-steps/s", "h2d_bytes_per_step": int(8 * 5 * nloc),
+               "d2h_bytes_per_step": int(8 * 10 * nloc), "steps": Ke, "ms_per_step": ms_e / Ke,
+               "what": "per step: packets (N,4)+sign from pinned host memory -> set; flow step + snapshot + raytrace; "
+                       "packets (N,4), velocity (N,2) and gradients (N,4) sampled and copied back (savepacketdata!)"}
+    clk = clocks.stop()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    F = 8.0 * args.nx * args.nx
+    # dominant kernel by accumulated device time over the K profiled steps
+    top = max(kern.items(), key=lambda kv: kv[1]["ms_total"])
+    name, rec = top
+    per_unit = {"raytrace_rk4_kernel": ("1280 B gathered per packet-step (4 RK4 stages x 2 time levels x 5 fields x 4 taps x 8 B) "
+                                        "+ 72 B packet state", (1280.0 + 72.0) * nloc * args.nsub)}
+    flow_bytes = {"ypass_inv_kernel<RswLoaderA>": 8 * F, "xpass_kernel<RswXOp>": 9 * F, "ypass_fwd_kernel<RswCombiner>": 7 * F,
+                  "ifmab3_update_rsw_kernel": 15 * F}
+    if name in per_unit:
+        what, by = per_unit[name]
+    else:
+        what, by = "SURVEY 8(d) F-units of this stage", flow_bytes.get(name, 0.0)
+    ach = by / (rec["ms_avg"] * 1e-3) / 1e9
+    roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": by, "per_unit": what, "avg_launch_ms": rec["ms_avg"], "peak_source": peak_src,
+                "share_of_step": rec["ms_total"] / sum(v["ms_total"] for v in kern.values())}
+    spectral = {"steps_per_s": 1e3 / ms_flow, "ms_per_step": ms_flow, "algorithmic_bytes_per_step": 42 * F,
+                "achieved": 42 * F / (ms_flow * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 42 * F / (ms_flow * 1e-3) / 1e9 / peak,
+                "contract": "B_step = 42 F, F = 8 nx^2 bytes (SURVEY.md 8d, RSW + IFMAB3)"}
+    line = {
+        "metric": "packet-steps/s", "value": value, "unit": "packet-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "packets_per_gpu": nloc,
+                   "nsub": args.nsub, "integrator": "RK4", "interp": "bilinear", "parallelism": f"packets sharded x{world}, flow replicated",
+                   "l2": "inputs_exceed_l2 (2 x 168 MB snapshot fields, 0.67 GB packets/GPU at N=1, 0.47 GB spectral work set vs 126 MB L2)"},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spectral_step": spectral,
+        "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"]} for k, v in kern.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = cpu_sample(args, 3, 1, cores)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "kind": "port", "sample": r["sample"],
+                                "flow_ms": r["flow_ms"], "spectral_steps_per_s": 1e3 / r["flow_ms"]}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_swrt(a)

@@ -62,6 +62,8 @@ SIGNATURES = {
     "swrt_flow_timer_stop": (_I, [_P, _PF]),
     "swrt_flow_sync": (_I, [_P]),
     "swrt_flow_launch_count": (_I, [_P, _PLL]),
+    "swrt_flow_profile": (_I, [_P, _I]),
+    "swrt_flow_profile_get": (_I, [_P, _I, _PD, _PLL, C.POINTER(C.c_char_p)]),
     "swrt_packets_create": (_I, [C.POINTER(PacketsDesc), _P, C.POINTER(_P)]),
     "swrt_packets_destroy": (_I, [_P]),
     "swrt_packets_set": (_I, [_P, _P, _P]),

@@ -69,7 +69,50 @@ struct swrt_flow {
     int ring = 0;
     double t = 0.0;
     long long step = 0, launches = 0;
+    // optional per-kernel timing (CUDA events around every launch on the handle's stream)
+    bool prof = false;
+    struct Rec { int id; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double prof_ms[16] = {0};
+    long long prof_n[16] = {0};
 };
+
+enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_OTHER, K_COUNT };
+static const char* kKernelNames[K_COUNT] = {"ypass_inv_kernel<RswLoaderA>", "xpass_kernel<RswXOp>", "ypass_fwd_kernel<RswCombiner>",
+                                            "ifmab3_update_rsw_kernel", "ypass_inv_kernel<PsiLoader>", "xpass_kernel<SnapshotXOp>",
+                                            "raytrace_rk4_kernel", "sample_kernel", "ypass_inv_kernel<FieldLoader>", "xpass_kernel<C2ROp>",
+                                            "other"};
+
+struct ProfScope {
+    swrt_flow* h;
+    int id;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(swrt_flow* h_, int id_) : h(h_), id(id_) {
+        h->launches++;
+        if (!h->prof) return;
+        auto get = [&]() { cudaEvent_t e; if (h->pool.empty()) cudaEventCreate(&e); else { e = h->pool.back(); h->pool.pop_back(); } return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, h->st);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, h->st);
+        h->recs.push_back({id, a, b});
+    }
+};
+static void prof_collect(swrt_flow* h) {
+    for (auto& r : h->recs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        h->prof_ms[r.id] += ms;
+        h->prof_n[r.id] += 1;
+        h->pool.push_back(r.a);
+        h->pool.push_back(r.b);
+    }
+    h->recs.clear();
+}
 
 struct swrt_packets {
     swrt_packets_desc d{};
@@ -163,8 +206,7 @@ static cudaError_t upload_twiddles(int n, double2** out) {
 
 static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, cudaError_t* err) {
     const int blocks = 296;
-    reduce_kernel<<<blocks, 256, 0, h->st>>>(a, n, mode, h->L, h->red);
-    h->launches++;
+    { ProfScope ps(h, K_OTHER); reduce_kernel<<<blocks, 256, 0, h->st>>>(a, n, mode, h->L, h->red); }
     std::vector<double> part(blocks);
     *err = cudaMemcpyAsync(part.data(), h->red, sizeof(double) * blocks, cudaMemcpyDeviceToHost, h->st);
     if (*err != cudaSuccess) return 0;
@@ -177,11 +219,10 @@ static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, 
 static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
     FieldLoader ld{h->sol, h->L.vs, which, h->d.f};
     cudaError_t e;
-    SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st));
+    { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st)); }
     CK(e);
-    SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->st));
+    { ProfScope ps(h, K_FIELD_B); SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->st)); }
     CK(e);
-    h->launches += 2;
     return SWRT_OK;
 }
 
@@ -205,6 +246,8 @@ int swrt_flow_destroy(swrt_flow* h) {
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef);
     cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
+    prof_collect(h);
+    for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st) cudaStreamDestroy(h->st);
@@ -302,9 +345,8 @@ int swrt_flow_set_solution(swrt_flow* h, const void* sol_host) {
     CK(cudaSetDevice(h->d.device));
     const size_t bytes = sizeof(double2) * (size_t)h->nkr * h->d.ny * h->nvar;
     CK(cudaMemcpyAsync(h->stage, sol_host, bytes, cudaMemcpyHostToDevice, h->st));
-    pack_sol_kernel<<<592, 256, 0, h->st>>>(h->stage, h->sol, h->L, h->nkr, h->nvar);
+    { ProfScope ps(h, K_OTHER); pack_sol_kernel<<<592, 256, 0, h->st>>>(h->stage, h->sol, h->L, h->nkr, h->nvar); }
     CK(cudaGetLastError());
-    h->launches++;
     CK(cudaStreamSynchronize(h->st));
     return SWRT_OK;
 }
@@ -312,9 +354,8 @@ int swrt_flow_set_solution(swrt_flow* h, const void* sol_host) {
 int swrt_flow_get_solution(swrt_flow* h, void* sol_host) {
     if (!h || !sol_host) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
-    unpack_sol_kernel<<<592, 256, 0, h->st>>>(h->sol, h->stage, h->L, h->nkr, h->nvar);
+    { ProfScope ps(h, K_OTHER); unpack_sol_kernel<<<592, 256, 0, h->st>>>(h->sol, h->stage, h->L, h->nkr, h->nvar); }
     CK(cudaGetLastError());
-    h->launches++;
     const size_t bytes = sizeof(double2) * (size_t)h->nkr * h->d.ny * h->nvar;
     CK(cudaMemcpyAsync(sol_host, h->stage, bytes, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -343,16 +384,15 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
         const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
         cudaError_t e;
         RswLoaderA ld{h->sol, L.vs};
-        SWRT_DISPATCH(L.ny, e, LN::rsw_stage_a(ld, L, h->G, h->tw_y, h->st));
+        { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::rsw_stage_a(ld, L, h->G, h->tw_y, h->st)); }
         CK(e);
-        SWRT_DISPATCH(L.nx, e, LN::rsw_stage_b(modified, h->G, h->H, L, h->tw_x, h->st));
+        { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::rsw_stage_b(modified, h->G, h->H, L, h->tw_x, h->st)); }
         CK(e);
-        SWRT_DISPATCH(L.ny, e, LN::rsw_stage_c(cb, L, h->H, Ncur, h->tw_y, h->st));
+        { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::rsw_stage_c(cb, L, h->H, Ncur, h->tw_y, h->st)); }
         CK(e);
         UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, h->d.dt, h->step < 3 ? 1 : 0};
-        ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+        { ProfScope ps(h, K_UPDATE); ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L); }
         CK(cudaGetLastError());
-        h->launches += 4;
         h->ring = (h->ring + 1) % 3;
         h->t += h->d.dt;
         h->step += 1;
@@ -433,11 +473,10 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     const SpecLayout& L = h->L;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, h->d.f * h->d.f / L.Cg2};
     cudaError_t e;
-    SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st));
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st)); }
     CK(e);
-    SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st));
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st)); }
     CK(e);
-    h->launches += 2;
     return SWRT_OK;
 }
 
@@ -490,6 +529,24 @@ int swrt_flow_sync(swrt_flow* h) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
     CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+int swrt_flow_profile(swrt_flow* h, int enable) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    prof_collect(h);
+    if (enable == 2) { for (int i = 0; i < 16; ++i) { h->prof_ms[i] = 0; h->prof_n[i] = 0; } enable = 1; }
+    h->prof = enable != 0;
+    return SWRT_OK;
+}
+int swrt_flow_profile_get(swrt_flow* h, int id, double* ms_total, long long* count, const char** name) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (id < 0 || id >= K_COUNT) return fail(SWRT_ERR_ARG, "kernel id out of range");
+    CK(cudaSetDevice(h->d.device));
+    prof_collect(h);
+    if (ms_total) *ms_total = h->prof_ms[id];
+    if (count) *count = h->prof_n[id];
+    if (name) *name = kKernelNames[id];
     return SWRT_OK;
 }
 int swrt_flow_launch_count(swrt_flow* h, long long* n) {
@@ -552,9 +609,8 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
     if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->flow->d.device));
     const long long n = p->d.n;
-    generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, n, first, sqrtN, L, k0);
+    { ProfScope ps(p->flow, K_OTHER); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, n, first, sqrtN, L, k0); }
     CK(cudaGetLastError());
-    p->flow->launches++;
     return SWRT_OK;
 }
 
@@ -573,10 +629,10 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     CK(cudaSetDevice(f->d.device));
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
     const long long n = p->d.n;
-    raytrace_rk4_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->sign, n, f->snap[f->slot_map[0]], f->snap[f->slot_map[1]],
-                                                                       packet_grid(f), rp);
+    { ProfScope ps(f, K_RAYTRACE);
+      raytrace_rk4_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->sign, n, f->snap[f->slot_map[0]], f->snap[f->slot_map[1]],
+                                                                         packet_grid(f), rp); }
     CK(cudaGetLastError());
-    f->launches++;
     return SWRT_OK;
 }
 
@@ -585,9 +641,8 @@ int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_hos
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
-    sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
-    f->launches++;
     CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
     if (g_host) CK(cudaMemcpyAsync(g_host, p->Gd, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
     CK(cudaStreamSynchronize(f->st));
@@ -600,9 +655,8 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
     CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), f->st));
-    kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, n, kcut * kcut, k0, p->count);
+    { ProfScope ps(f, K_OTHER); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, n, kcut * kcut, k0, p->count); }
     CK(cudaGetLastError());
-    f->launches++;
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, f->st));
     CK(cudaStreamSynchronize(f->st));

@@ -130,6 +130,19 @@ class Problem:
         check(lib().swrt_flow_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def profile(self, enable=2):
+        """Per-kernel CUDA-event timing on the handle's stream (2 = enable and clear, 0 = off)."""
+        check(lib().swrt_flow_profile(self._h, int(enable)))
+
+    def profile_report(self):
+        out = {}
+        for i in range(11):
+            ms, n, name = C.c_double(), C.c_longlong(), C.c_char_p()
+            check(lib().swrt_flow_profile_get(self._h, i, C.byref(ms), C.byref(n), C.byref(name)))
+            if n.value:
+                out[name.value.decode()] = dict(ms_total=ms.value, launches=n.value, ms_avg=ms.value / n.value)
+        return out
+
     def timer_start(self):
         check(lib().swrt_flow_timer_start(self._h))
 

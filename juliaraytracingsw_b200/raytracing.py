@@ -81,8 +81,11 @@ class Packets:
         s = None if frequency_sign is None else np.ascontiguousarray(frequency_sign, dtype=np.float64)
         check(lib().swrt_packets_set(self._h, a.ctypes.data_as(C.c_void_p), None if s is None else s.ctypes.data_as(C.c_void_p)))
 
-    def get(self):
-        out = np.empty((self.n, 4), dtype=np.float64, order="F")
+    def get(self, out=None):
+        """Array(packets); `out` may be a caller-owned (N, 4) Fortran-ordered buffer (e.g. pinned memory)."""
+        if out is None:
+            out = np.empty((self.n, 4), dtype=np.float64, order="F")
+        assert out.shape == (self.n, 4) and out.flags.f_contiguous and out.dtype == np.float64
         check(lib().swrt_packets_get(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -113,16 +116,17 @@ def raytrace(ode_template, velocity1, velocity2, gradient1, gradient2, grid, wav
     check(lib().swrt_packets_raytrace(wavepacket_array._h, float(tspan[0]), float(tspan[1])))
 
 
-def interpolate_velocity(velocity, packets):
+def interpolate_velocity(velocity, packets, output_U=None):
     """interpolate_velocity! :67-82 -> (N, 2) array of u, v at the packet positions."""
-    U = np.empty((packets.n, 2), dtype=np.float64, order="F")
+    U = np.empty((packets.n, 2), dtype=np.float64, order="F") if output_U is None else output_U
     check(lib().swrt_packets_sample(packets._h, velocity.slot, U.ctypes.data_as(C.c_void_p), None))
     return U
 
 
-def interpolate_gradients(gradient, packets):
-    """interpolate_gradients! :84-109 -> (N, 4) array of ux, uy, vx, vy at the packet positions."""
-    U = np.empty((packets.n, 2), dtype=np.float64, order="F")
-    G = np.empty((packets.n, 4), dtype=np.float64, order="F")
+def interpolate_gradients(gradient, packets, output_G=None, output_U=None):
+    """interpolate_gradients! :84-109 -> (N, 4) array of ux, uy, vx, vy at the packet positions
+    (the velocity is sampled in the same pass and returned in `output_U` when given)."""
+    U = np.empty((packets.n, 2), dtype=np.float64, order="F") if output_U is None else output_U
+    G = np.empty((packets.n, 4), dtype=np.float64, order="F") if output_G is None else output_G
     check(lib().swrt_packets_sample(packets._h, gradient.slot, U.ctypes.data_as(C.c_void_p), G.ctypes.data_as(C.c_void_p)))
     return G

@@ -187,6 +187,8 @@ def test_full_size_properties_2048():
     """BASELINE config-4 size: size-independent properties instead of an oracle run."""
     nx = 2048
     g, p, sol0, c = config2_setup(nx)
+    sol0 = orsw.enforce_reality_condition(sol0, g, p)            # Hermitian-consistent kr=0 column (Parseval needs it)
+    g.dealias(sol0)
     prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
     prob.sol = sol0
     # Parseval: sum u^2 dx dy == parsevalsum2(uh)
