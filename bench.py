@@ -203,18 +203,29 @@ def run_swrt(args):
     K, W = args.steps, max(args.warmup, 3)
 
     clocks = ClockSampler(local)
-    # ---- device-resident timed region
+
+    def timed(nsteps, t):
+        prob.sync(); barrier()
+        l0 = prob.launch_count()
+        prob.timer_start()
+        for _ in range(nsteps):
+            t = drivers.coupled_step(prob, packets, t)
+        ms = prob.timer_stop()
+        barrier()
+        return max_over_ranks(ms), prob.launch_count() - l0, t
+
+    # ---- packets on the reference's initial lattice (t = 0: neighbouring packets share cache lines)
     for _ in range(W):
         t = drivers.coupled_step(prob, packets, t)
-    prob.sync(); barrier()
-    l0 = prob.launch_count()
-    prob.timer_start()
-    for _ in range(K):
+    ms_lat, _, t = timed(K, t)
+    # ---- headline: positions pre-randomised U(-L/2, L/2), the fully mixed state (worst-case gathers)
+    xk0 = packets.get()
+    xk0[:, 0:2] = np.random.default_rng(1000 + rank).uniform(-P.L / 2, P.L / 2, size=(nloc, 2))
+    packets.set(xk0)
+    del xk0
+    for _ in range(W):
         t = drivers.coupled_step(prob, packets, t)
-    ms = prob.timer_stop()
-    barrier()
-    launches = prob.launch_count() - l0
-    ms = max_over_ranks(ms)
+    ms, launches, t = timed(K, t)
     value = ntot * K / (ms * 1e-3)
 
     # ---- same K steps with per-kernel CUDA events (roofline of the dominant kernel)
@@ -292,9 +303,11 @@ def run_swrt(args):
         "metric": "packet-steps/s", "value": value, "unit": "packet-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "packets_per_gpu": nloc,
-                   "nsub": args.nsub, "integrator": "RK4", "interp": "bilinear", "parallelism": f"packets sharded x{world}, flow replicated",
+                   "nsub": args.nsub, "integrator": "RK4", "interp": "bilinear",
+                   "packet_positions": "uniform random over the domain (fully mixed; the lattice start is value_lattice_t0)", "parallelism": f"packets sharded x{world}, flow replicated",
                    "l2": "inputs_exceed_l2 (2 x 168 MB snapshot fields, 0.67 GB packets/GPU at N=1, 0.47 GB spectral work set vs 126 MB L2)"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spectral_step": spectral,
+        "value_lattice_t0": ntot * K / (ms_lat * 1e-3),
         "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"]} for k, v in kern.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
