@@ -107,6 +107,8 @@ typedef struct swrt_packets_desc {
     int interp;             /* SWRT_INTERP_* */
     int nsub;               /* RK4 sub-steps per raytrace call */
     int time_lerp;          /* SWRT_LERP_*   */
+    int sort_every;         /* re-sort the device copy by grid cell every this many raytrace calls (0 = never);
+                               host-visible arrays always keep the caller's row order */
     double f, Cg;           /* packet_params.f, packet_params.Cg */
 } swrt_packets_desc;
 

@@ -2,8 +2,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/swrt.h"
@@ -62,8 +64,8 @@ struct swrt_flow {
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
-    double* snap[2] = {nullptr, nullptr};
-    int slot_map[2] = {0, 1};
+    double* snap = nullptr;      // S[ny][nx][2][5]: both snapshot halves interleaved (snapshot_layout.cuh)
+    int slot_map[2] = {0, 1};    // slot (0 = old, 1 = new) -> half
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
     int ring = 0;
@@ -78,11 +80,11 @@ struct swrt_flow {
     long long prof_n[16] = {0};
 };
 
-enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_OTHER, K_COUNT };
+enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_OTHER, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"ypass_inv_kernel<RswLoaderA>", "xpass_kernel<RswXOp>", "ypass_fwd_kernel<RswCombiner>",
                                             "ifmab3_update_rsw_kernel", "ypass_inv_kernel<PsiLoader>", "xpass_kernel<SnapshotXOp>",
                                             "raytrace_rk4_kernel", "sample_kernel", "ypass_inv_kernel<FieldLoader>", "xpass_kernel<C2ROp>",
-                                            "other"};
+                                            "packet_sort_kernels", "other"};
 
 struct ProfScope {
     swrt_flow* h;
@@ -117,8 +119,13 @@ static void prof_collect(swrt_flow* h) {
 struct swrt_packets {
     swrt_packets_desc d{};
     swrt_flow* flow = nullptr;
-    double *xk = nullptr, *sign = nullptr, *U = nullptr, *Gd = nullptr;
+    // state (sorted order) + alternates for the out-of-place sort; idx = original row of each packet
+    double *xk = nullptr, *sign = nullptr, *xk2 = nullptr, *sign2 = nullptr, *U = nullptr, *Gd = nullptr;
+    unsigned *idx = nullptr, *idx2 = nullptr, *keys = nullptr, *hist = nullptr, *sums = nullptr;
     unsigned long long* count = nullptr;
+    long long nbins = 0;
+    int since_sort = 1 << 30;   // raytrace calls since the last sort
+    bool permuted = false;
 };
 
 // ------------------------------------------------------------------ small kernels (api TU only)
@@ -245,7 +252,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef);
-    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
+    cudaFree(h->snap); cudaFree(h->phys); cudaFree(h->red);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -299,10 +306,8 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
-    for (int s = 0; s < 2; ++s) {
-        CKB(cudaMalloc(&h->snap[s], sizeof(double) * (size_t)d.nx * d.ny * SNAP_NC));
-        CKB(cudaMemset(h->snap[s], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_NC));
-    }
+    CKB(cudaMalloc(&h->snap, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
+    CKB(cudaMemset(h->snap, 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
     CKB(upload_twiddles(d.nx, &h->tw_x));
     CKB(upload_twiddles(d.ny, &h->tw_y));
 
@@ -475,7 +480,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap + h->slot_map[slot] * SNAP_NC, L, h->tw_x, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -490,24 +495,32 @@ int swrt_flow_swap_snapshots(swrt_flow* h, int alias) {
 int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const size_t n = (size_t)h->d.nx * h->d.ny;
-    std::vector<double> tmp(n * SNAP_NC);
-    CK(cudaMemcpyAsync(tmp.data(), h->snap[h->slot_map[slot]], sizeof(double) * n * SNAP_NC, cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
-    for (int c = 0; c < SNAP_NC; ++c)
-        for (size_t i = 0; i < n; ++i) out_host[c * n + i] = tmp[i * SNAP_NC + c];
+    const long long n = (long long)h->d.nx * h->d.ny;
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(double) * n * SNAP_NC));
+    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap, h->slot_map[slot], n, tmp); }
+    cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * SNAP_NC, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(tmp);
+    CK(e);
     return SWRT_OK;
 }
 
 int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const size_t n = (size_t)h->d.nx * h->d.ny;
-    std::vector<double> tmp(n * SNAP_NC);
-    for (int c = 0; c < SNAP_NC; ++c)
-        for (size_t i = 0; i < n; ++i) tmp[i * SNAP_NC + c] = in_host[c * n + i];
-    CK(cudaMemcpyAsync(h->snap[h->slot_map[slot]], tmp.data(), sizeof(double) * n * SNAP_NC, cudaMemcpyHostToDevice, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    const long long n = (long long)h->d.nx * h->d.ny;
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(double) * n * SNAP_NC));
+    cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * SNAP_NC, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) {
+        ProfScope ps(h, K_OTHER);
+        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, h->slot_map[slot], n, h->snap);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(tmp);
+    CK(e);
     return SWRT_OK;
 }
 
@@ -559,7 +572,8 @@ int swrt_flow_launch_count(swrt_flow* h, long long* n) {
 int swrt_packets_destroy(swrt_packets* p) {
     if (!p) return SWRT_OK;
     if (p->flow) { cudaSetDevice(p->flow->d.device); cudaStreamSynchronize(p->flow->st); }
-    cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->U); cudaFree(p->Gd); cudaFree(p->count);
+    cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->xk2); cudaFree(p->sign2); cudaFree(p->U); cudaFree(p->Gd);
+    cudaFree(p->idx); cudaFree(p->idx2); cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count);
     delete p;
     return SWRT_OK;
 }
@@ -567,41 +581,69 @@ int swrt_packets_destroy(swrt_packets* p) {
 int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_packets** out) {
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
-    if (desc->n <= 0) return fail(SWRT_ERR_ARG, "n must be positive");
+    if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
     if (desc->interp != SWRT_INTERP_BILINEAR) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
     if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
+    if (desc->sort_every < 0) return fail(SWRT_ERR_ARG, "sort_every must be >= 0");
     CK(cudaSetDevice(flow->d.device));
     swrt_packets* p = new swrt_packets;
     p->d = *desc;
     p->flow = flow;
+    p->nbins = (long long)flow->d.nx * flow->d.ny;
     const size_t n = (size_t)desc->n;
+    const size_t nsums = (size_t)(p->nbins / SCAN_BLOCK + 2) + (size_t)(p->nbins / SCAN_BLOCK / SCAN_BLOCK + 2) + 8;
     cudaError_t e;
     if ((e = cudaMalloc(&p->xk, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign, sizeof(double) * n)) != cudaSuccess ||
+        (e = cudaMalloc(&p->xk2, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign2, sizeof(double) * n)) != cudaSuccess ||
         (e = cudaMalloc(&p->U, sizeof(double) * 2 * n)) != cudaSuccess || (e = cudaMalloc(&p->Gd, sizeof(double) * 4 * n)) != cudaSuccess ||
-        (e = cudaMalloc(&p->count, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&p->idx, sizeof(unsigned) * n)) != cudaSuccess || (e = cudaMalloc(&p->idx2, sizeof(unsigned) * n)) != cudaSuccess ||
+        (e = cudaMalloc(&p->keys, sizeof(unsigned) * n)) != cudaSuccess || (e = cudaMalloc(&p->hist, sizeof(unsigned) * (size_t)p->nbins)) != cudaSuccess ||
+        (e = cudaMalloc(&p->sums, sizeof(unsigned) * nsums)) != cudaSuccess || (e = cudaMalloc(&p->count, sizeof(unsigned long long))) != cudaSuccess) {
         swrt_packets_destroy(p);
         return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
     }
-    CK(cudaMemset(p->xk, 0, sizeof(double) * 4 * n));
-    CK(cudaMemset(p->sign, 0, sizeof(double) * n));
+    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, flow->st));
+    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, flow->st));
+    { ProfScope ps(flow, K_OTHER); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, flow->st>>>(p->idx, (long long)n); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(flow->st));
     *out = p;
     return SWRT_OK;
 }
 
 int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* sign_host) {
     if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(p->flow->d.device));
-    CK(cudaMemcpyAsync(p->xk, xk_host, sizeof(double) * 4 * (size_t)p->d.n, cudaMemcpyHostToDevice, p->flow->st));
-    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)p->d.n, cudaMemcpyHostToDevice, p->flow->st));
-    CK(cudaStreamSynchronize(p->flow->st));
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    const long long n = p->d.n;
+    if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
+        { ProfScope ps(f, K_OTHER); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->sign, p->idx, n, 1, p->sign2); }
+        CK(cudaGetLastError());
+        std::swap(p->sign, p->sign2);
+    }
+    CK(cudaMemcpyAsync(p->xk, xk_host, sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice, f->st));
+    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, f->st));
+    { ProfScope ps(f, K_OTHER); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->idx, n); }
+    CK(cudaGetLastError());
+    p->permuted = false;
+    p->since_sort = 1 << 30;
+    CK(cudaStreamSynchronize(f->st));
     return SWRT_OK;
 }
 
 int swrt_packets_get(swrt_packets* p, double* xk_host) {
     if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(p->flow->d.device));
-    CK(cudaMemcpyAsync(xk_host, p->xk, sizeof(double) * 4 * (size_t)p->d.n, cudaMemcpyDeviceToHost, p->flow->st));
-    CK(cudaStreamSynchronize(p->flow->st));
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    const long long n = p->d.n;
+    const double* src = p->xk;
+    if (p->permuted) {
+        { ProfScope ps(f, K_OTHER); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, p->idx, n, 4, p->xk2); }
+        CK(cudaGetLastError());
+        src = p->xk2;
+    }
+    CK(cudaMemcpyAsync(xk_host, src, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
+    CK(cudaStreamSynchronize(f->st));
     return SWRT_OK;
 }
 
@@ -609,8 +651,10 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
     if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->flow->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(p->flow, K_OTHER); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, n, first, sqrtN, L, k0); }
+    { ProfScope ps(p->flow, K_OTHER); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
     CK(cudaGetLastError());
+    p->permuted = false;
+    p->since_sort = 1 << 30;
     return SWRT_OK;
 }
 
@@ -622,17 +666,59 @@ static PacketGrid packet_grid(const swrt_flow* f) {
     return g;
 }
 
+static cudaError_t exclusive_scan(swrt_flow* f, unsigned* a, long long nb, unsigned* scratch) {
+    const unsigned blocks = (unsigned)((nb + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if (blocks <= 1) {
+        ProfScope ps(f, K_SORT);
+        scan_block_kernel<<<1, SCAN_BLOCK, 0, f->st>>>(a, nb, nullptr);
+        return cudaGetLastError();
+    }
+    { ProfScope ps(f, K_SORT); scan_block_kernel<<<blocks, SCAN_BLOCK, 0, f->st>>>(a, nb, scratch); }
+    cudaError_t e = exclusive_scan(f, scratch, blocks, scratch + blocks);
+    if (e != cudaSuccess) return e;
+    { ProfScope ps(f, K_SORT); scan_add_kernel<<<blocks, SCAN_BLOCK, 0, f->st>>>(a, nb, scratch); }
+    return cudaGetLastError();
+}
+
+// counting sort of the packets by tiled cell key (packets.cuh); out of place, then swap the buffers
+static int sort_packets(swrt_packets* p) {
+    swrt_flow* f = p->flow;
+    const long long n = p->d.n;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, f->st));
+    { ProfScope ps(f, K_SORT); sort_hist_kernel<<<blocks, 256, 0, f->st>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
+    CK(cudaGetLastError());
+    CK(exclusive_scan(f, p->hist, p->nbins, p->sums));
+    { ProfScope ps(f, K_SORT); sort_scatter_kernel<<<blocks, 256, 0, f->st>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
+    CK(cudaGetLastError());
+    std::swap(p->xk, p->xk2);
+    std::swap(p->sign, p->sign2);
+    std::swap(p->idx, p->idx2);
+    p->permuted = true;
+    p->since_sort = 0;
+    return SWRT_OK;
+}
+
 int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     if (!(t1 != t0)) return fail(SWRT_ERR_ARG, "t1 must differ from t0");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
-    RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
+    if (p->d.sort_every > 0 && p->since_sort >= p->d.sort_every) {
+        int rc = sort_packets(p);
+        if (rc) return rc;
+    }
+    RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp, f->slot_map[0], f->slot_map[1]};
     const long long n = p->d.n;
+    static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 6; }();  // tuning knob
+    const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
-      raytrace_rk4_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->sign, n, f->snap[f->slot_map[0]], f->snap[f->slot_map[1]],
-                                                                         packet_grid(f), rp); }
+      if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
+      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
+      else if (minb <= 7) raytrace_rk4_kernel<6><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
+      else raytrace_rk4_kernel<8><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp); }
     CK(cudaGetLastError());
+    p->since_sort++;
     return SWRT_OK;
 }
 
@@ -641,7 +727,7 @@ int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_hos
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
+    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap, f->slot_map[slot], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
     if (g_host) CK(cudaMemcpyAsync(g_host, p->Gd, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));

@@ -7,6 +7,7 @@
 //   raytracing/RaytracingDriver.jl:132-154 get_velocity_info
 #pragma once
 #include "passes.cuh"
+#include "snapshot_layout.cuh"
 
 namespace swrt {
 
@@ -41,46 +42,55 @@ struct RswXOp {
         const long long ro = (long long)y * L.kr_pad;
         const double2 *Gu = G + ro, *Gv = G + L.vs + ro, *Ge = G + 2 * L.vs + ro, *Guy = G + 3 * L.vs + ro,
                       *Gvy = G + 4 * L.vs + ro;
+        // two shared buffers: 0 keeps u + i v for the whole row, 1 is the work buffer; products are formed
+        // in place at the thread's own x positions (p1 waits in registers for p2)
         cx.template load_pair<MUL_ONE, MUL_ONE>(0, Gu, Gv);
         cx.ifft(0);                                     // buffer 0: u + i v
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
         cx.ifft(1);                                     // buffer 1: ux + i uy
         const double *ur = cx.re(0), *vr = cx.im(0);
-        double *br = cx.re(1), *bi = cx.im(1), *cr = cx.re(2), *ci = cx.im(2);
+        double *br = cx.re(1), *bi = cx.im(1);
+        double p1[EPT];
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const int x = pad_index(cx.g + i * Gt);
-            cr[x] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+            p1[i] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
         }
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gv, Gvy);
         cx.ifft(1);                                     // buffer 1: vx + i vy
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const int x = pad_index(cx.g + i * Gt);
-            ci[x] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+            const double p2 = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+            br[x] = p1[i];
+            bi[x] = p2;
         }
-        cx.fft(2);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(2, H + ro, H + L.vs + ro);
+        cx.fft(1);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
         cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, nullptr);
         cx.ifft(1);                                     // buffer 1: eta
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const int x = pad_index(cx.g + i * Gt);
-            cr[x] = sc * (ur[x] * br[x]);
-            ci[x] = sc * (vr[x] * br[x]);
+            const double e = br[x];
+            if (MODIFIED) {
+                const double e1 = 1.0 + s1 * e;
+                p1[i] = 0.5 * (1.5 - 0.5 / (e1 * e1));
+            }
+            br[x] = sc * (ur[x] * e);
+            bi[x] = sc * (vr[x] * e);
         }
-        cx.fft(2);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(2, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
+        cx.fft(1);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
         if (MODIFIED) {
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int x = pad_index(cx.g + i * Gt);
-                const double e1 = 1.0 + s1 * br[x];
-                cr[x] = 0.5 * (1.5 - 0.5 / (e1 * e1));
-                ci[x] = 0.0;
+                br[x] = p1[i];
+                bi[x] = 0.0;
             }
-            cx.fft(2);
-            cx.template store_pair<MUL_ONE, MUL_ZERO>(2, H + 4 * L.vs + ro, nullptr);
+            cx.fft(1);
+            cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 4 * L.vs + ro, nullptr);
         }
     }
 };
@@ -155,12 +165,10 @@ struct PsiLoader {
     }
 };
 
-constexpr int SNAP_NC = 5;  // u, v, ux, uy, vx interleaved per grid point (vy = -ux)
-
 template <int N>
 struct SnapshotXOp {
     const double2* G;  // [3][ny][kr_pad]
-    double* out;       // [ny][nx][5]
+    double* out;       // [ny][nx][2][5], already offset to the half being written
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
@@ -170,32 +178,34 @@ struct SnapshotXOp {
         cx.ifft(0);  // u + i v
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
         cx.ifft(1);  // ux + i uy
-        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, nullptr);
-        cx.ifft(2);  // vx
-        double* o = out + (long long)y * N * SNAP_NC;
+        double* o = out + (long long)y * N * SNAP_STRIDE;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const int x = cx.g + i * Gt, p = pad_index(x);
-            double* q = o + (long long)x * SNAP_NC;
+            double* q = o + (long long)x * SNAP_STRIDE;
             q[0] = s1 * cx.re(0)[p];
             q[1] = s1 * cx.im(0)[p];
             q[2] = s1 * cx.re(1)[p];
             q[3] = s1 * cx.im(1)[p];
-            q[4] = s1 * cx.re(2)[p];
+        }
+        cx.template load_pair<MUL_MK2, MUL_ZERO>(1, Gp, nullptr);
+        cx.ifft(1);  // vx
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int x = cx.g + i * Gt;
+            o[(long long)x * SNAP_STRIDE + 4] = s1 * cx.re(1)[pad_index(x)];
         }
     }
 };
 
 // ---------------------------------------------------------------- per-size launchers
 __host__ __device__ constexpr int tile_k(int N) { return N >= 2048 ? 2 : (N >= 256 ? 4096 / N : 16); }
-constexpr int XPASS_BUFFERS = 3;
-
 template <int N>
 struct Launch {
     static constexpr int TK = tile_k(N);
     static constexpr int G = group_size(N);
-    static constexpr size_t ysmem = (size_t)2 * TK * padded_len(N) * sizeof(double);
-    static constexpr size_t xsmem = (size_t)2 * XPASS_BUFFERS * padded_len(N) * sizeof(double);
+    static constexpr size_t ysmem = (size_t)ypass_smem(N, TK);
+    static constexpr size_t xsmem = (size_t)xpass_smem(N);
 
     // one-time per kernel: opt in to the dynamic shared memory and size a persistent grid
     template <class K>
@@ -203,6 +213,8 @@ struct Launch {
         static int cached = 0;  // one static per (N, K) instantiation
         if (!cached) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
             int dev = 0, sms = 0, occ = 0;
             cudaGetDevice(&dev);

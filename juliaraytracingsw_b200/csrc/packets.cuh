@@ -1,6 +1,17 @@
 // Wave-packet ray tracer kernels (sm_100a, fp64): one thread per packet, state in registers,
-// `nsub` classical RK4 steps per launch, bilinear gathers from two time levels of the
-// interleaved background field F[y][x][5] = (u, v, ux, uy, vx), vy = -ux.
+// `nsub` classical RK4 steps per launch, bilinear gathers from the two time levels of the
+// background field.
+//
+// Field layout: S[y][x][2][5] doubles -- both time levels (halves A, B) of (u, v, ux, uy, vx)
+// interleaved per grid point (vy = -ux), 80 B = five 16-byte vectors per point, so the two x-taps of
+// a bilinear stencil are 160 contiguous bytes and one pass of ten LDG.128 per row fetches both
+// time levels.  Which half is "old" is a launch parameter (the snapshot kernel overwrites the
+// other half each flow step).
+//
+// Locality: packets are kept sorted by an 8x8-cell-tiled cell key (counting sort, re-run every
+// `sort_every` raytrace calls); `idx` remembers each packet's original row so that every
+// host-visible array is returned in the caller's order, bit for bit (per-packet arithmetic does
+// not depend on the storage order).
 //
 // Reference semantics: raytracing/GPURaytracing.jl:18-65 (dxkdt, texture-coordinate bilinear
 // sampling with wrap addressing, dispersion relation with frequency sign), :67-109
@@ -8,15 +19,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "snapshot_layout.cuh"
+
 namespace swrt {
 
 struct PacketGrid {
     int nx, ny;
     double x0, y0, dx, dy;
-};
-
-struct Sample5 {
-    double u, v, ux, uy, vx;
 };
 
 // s = (x - x0)/dx ; i = floor(s) mod n ; a = s - floor(s)   (division kept: index parity with the oracle)
@@ -30,39 +39,55 @@ __device__ __forceinline__ void cell(double x, double x0, double dx, int n, int&
     i1 = i0 + 1 == n ? 0 : i0 + 1;
 }
 
-__device__ __forceinline__ void bilinear5(const double* __restrict__ F, const PacketGrid& g, int i0, int i1, int j0, int j1,
-                                          double a, double b, double (&out)[5]) {
-    const double* p00 = F + ((long long)j0 * g.nx + i0) * 5;
-    const double* p10 = F + ((long long)j0 * g.nx + i1) * 5;
-    const double* p01 = F + ((long long)j1 * g.nx + i0) * 5;
-    const double* p11 = F + ((long long)j1 * g.nx + i1) * 5;
+// one x-row of the stencil: (1-a) S[j][i0] + a S[j][i1] for all ten interleaved values
+__device__ __forceinline__ void lerp_row(const double* __restrict__ S, long long p0, long long p1, double a, double (&r)[10]) {
+    const double2* q0 = reinterpret_cast<const double2*>(S + p0 * SNAP_STRIDE);
+    const double2* q1 = reinterpret_cast<const double2*>(S + p1 * SNAP_STRIDE);
+    double2 u[5], v[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const double bottom = (1.0 - a) * __ldg(p00 + c) + a * __ldg(p10 + c);
-        const double top = (1.0 - a) * __ldg(p01 + c) + a * __ldg(p11 + c);
-        out[c] = (1.0 - b) * bottom + b * top;
+    for (int q = 0; q < 5; ++q) u[q] = __ldg(q0 + q);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v[q] = __ldg(q1 + q);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        r[2 * q] = (1.0 - a) * u[q].x + a * v[q].x;
+        r[2 * q + 1] = (1.0 - a) * u[q].y + a * v[q].y;
     }
+}
+
+// bilinear interpolation of both halves at once; out[h*5 + c]
+__device__ __forceinline__ void bilinear10(const double* __restrict__ S, const PacketGrid& g, int i0, int i1, int j0, int j1,
+                                           double a, double b, double (&out)[10]) {
+    double bottom[10], top[10];
+    lerp_row(S, (long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, a, bottom);
+    lerp_row(S, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1, a, top);
+#pragma unroll
+    for (int c = 0; c < 10; ++c) out[c] = (1.0 - b) * bottom[c] + b * top[c];
 }
 
 struct RayParams {
     double f, Cg, t0, t1;
     int nsub, lerp;  // lerp: 0 physical ((1-a) old + a new), 1 reference GPU (a old + (1-a) new)
+    int old_half, new_half;
 };
 
-__device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, double alpha, const double* __restrict__ Fo,
-                                        const double* __restrict__ Fn, const PacketGrid& g, const RayParams& p,
-                                        double (&d)[4]) {
+__device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, double alpha, const double* __restrict__ S,
+                                        const PacketGrid& g, const RayParams& p, double (&d)[4]) {
     int i0, i1, j0, j1;
     double a, b;
     cell(s[0], g.x0, g.dx, g.nx, i0, i1, a);
     cell(s[1], g.y0, g.dy, g.ny, j0, j1, b);
-    double So[5], Sn[5];
-    bilinear5(Fo, g, i0, i1, j0, j1, a, b, So);
-    bilinear5(Fn, g, i0, i1, j0, j1, a, b, Sn);
+    double V[10];
+    bilinear10(S, g, i0, i1, j0, j1, a, b, V);
     const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
+    // weights of half A (V[0..5)) and half B (V[5..10)); wo*old + wn*new, the sum is commutative so the
+    // rounding equals the oracle's whichever half is "old"
+    const double wA = (p.old_half == 0 ? wo : 0.0) + (p.new_half == 0 ? wn : 0.0);
+    const double wB = (p.old_half == 1 ? wo : 0.0) + (p.new_half == 1 ? wn : 0.0);
     double W[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) W[c] = wo * So[c] + wn * Sn[c];
+    for (int c = 0; c < 5; ++c) W[c] = p.old_half == p.new_half ? (p.old_half == 0 ? wo * V[c] + wn * V[c] : wo * V[5 + c] + wn * V[5 + c])
+                                                                : wA * V[c] + wB * V[5 + c];
     const double k = s[2], l = s[3];
     const double w = sign * sqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));
     d[0] = W[0] + p.Cg * p.Cg * k / w;
@@ -72,9 +97,9 @@ __device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, doubl
 }
 
 // xk: (N,4) column-major = 4 arrays of N
-__global__ void __launch_bounds__(128) raytrace_rk4_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
-                                                           const double* __restrict__ Fo, const double* __restrict__ Fn,
-                                                           PacketGrid g, RayParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
+                                                              const double* __restrict__ S, PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
@@ -83,16 +108,16 @@ __global__ void __launch_bounds__(128) raytrace_rk4_kernel(double* __restrict__ 
     for (int it = 0; it < p.nsub; ++it) {
         const double t = p.t0 + it * h;
         double k1[4], k2[4], k3[4], k4[4], y[4];
-        ray_rhs(s, sg, (t - p.t0) / span, Fo, Fn, g, p, k1);
+        ray_rhs(s, sg, (t - p.t0) / span, S, g, p, k1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k1[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, Fo, Fn, g, p, k2);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, S, g, p, k2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k2[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, Fo, Fn, g, p, k3);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, S, g, p, k3);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + h * k3[c];
-        ray_rhs(y, sg, (t + h - p.t0) / span, Fo, Fn, g, p, k4);
+        ray_rhs(y, sg, (t + h - p.t0) / span, S, g, p, k4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
     }
@@ -102,23 +127,28 @@ __global__ void __launch_bounds__(128) raytrace_rk4_kernel(double* __restrict__ 
     xk[3 * n + i] = s[3];
 }
 
-// interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy
-__global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, long long n, const double* __restrict__ F,
-                                                     PacketGrid g, double* __restrict__ U, double* __restrict__ Gd) {
+// interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
+__global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
+                                                     const double* __restrict__ S, int half, PacketGrid g, double* __restrict__ U,
+                                                     double* __restrict__ Gd) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int i0, i1, j0, j1;
-    double a, b, S[5];
+    double a, b, V[10];
     cell(xk[i], g.x0, g.dx, g.nx, i0, i1, a);
     cell(xk[n + i], g.y0, g.dy, g.ny, j0, j1, b);
-    bilinear5(F, g, i0, i1, j0, j1, a, b, S);
-    U[i] = S[0];
-    U[n + i] = S[1];
+    bilinear10(S, g, i0, i1, j0, j1, a, b, V);
+    double Sv[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) Sv[c] = half == 0 ? V[c] : V[5 + c];
+    const long long o = idx[i];
+    U[o] = Sv[0];
+    U[n + o] = Sv[1];
     if (Gd) {
-        Gd[i] = S[2];
-        Gd[n + i] = S[3];
-        Gd[2 * n + i] = S[4];
-        Gd[3 * n + i] = -S[2];
+        Gd[o] = Sv[2];
+        Gd[n + o] = Sv[3];
+        Gd[2 * n + o] = Sv[4];
+        Gd[3 * n + o] = -Sv[2];
     }
 }
 
@@ -134,8 +164,8 @@ __global__ void kcutoff_kernel(double* __restrict__ xk, long long n, double kc2,
 }
 
 // generate_initial_wavepackets (raytracing/RaytracingDriver.jl:27-47); p = global 1-based packet index
-__global__ void generate_packets_kernel(double* __restrict__ xk, double* __restrict__ sign, long long n, long long first,
-                                        long long sqrtN, double L, double k0) {
+__global__ void generate_packets_kernel(double* __restrict__ xk, double* __restrict__ sign, unsigned* __restrict__ idx, long long n,
+                                        long long first, long long sqrtN, double L, double k0) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long p0 = first + i;  // 0-based global
@@ -148,6 +178,88 @@ __global__ void generate_packets_kernel(double* __restrict__ xk, double* __restr
     xk[2 * n + i] = k0 * cos(phase);
     xk[3 * n + i] = k0 * sin(phase);
     sign[i] = (p0 % 2 == 0) ? -1.0 : 1.0;
+    idx[i] = (unsigned)i;
+}
+
+__global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (unsigned)i;
+}
+
+// ---------------------------------------------------------------- counting sort by tiled cell key
+__device__ __forceinline__ unsigned cell_key(double x, double y, const PacketGrid& g) {
+    int i0, i1, j0, j1;
+    double a;
+    cell(x, g.x0, g.dx, g.nx, i0, i1, a);
+    cell(y, g.y0, g.dy, g.ny, j0, j1, a);
+    return (unsigned)((((j0 >> 3) * (g.nx >> 3) + (i0 >> 3)) << 6) + ((j0 & 7) << 3) + (i0 & 7));
+}
+
+__global__ void sort_hist_kernel(const double* __restrict__ xk, long long n, PacketGrid g, unsigned* __restrict__ keys,
+                                 unsigned* __restrict__ hist) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = cell_key(xk[i], xk[n + i], g);
+    keys[i] = k;
+    atomicAdd(&hist[k], 1u);
+}
+
+// exclusive scan of `hist` (nb elements) in three launches: per-block scan, scan of block sums (one block), add
+constexpr int SCAN_BLOCK = 1024;
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_block_kernel(unsigned* __restrict__ a, long long nb, unsigned* __restrict__ sums) {
+    __shared__ unsigned sh[SCAN_BLOCK];
+    const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
+    const unsigned v = i < nb ? a[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < SCAN_BLOCK; off <<= 1) {
+        const unsigned t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    if (i < nb) a[i] = sh[threadIdx.x] - v;  // exclusive
+    if (threadIdx.x == SCAN_BLOCK - 1 && sums) sums[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void scan_add_kernel(unsigned* __restrict__ a, long long nb, const unsigned* __restrict__ sums) {
+    const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
+    if (i < nb) a[i] += sums[blockIdx.x];
+}
+
+// scatter packet i to its sorted slot and move its state (the order inside a cell is arbitrary)
+__global__ void sort_scatter_kernel(const double* __restrict__ xk, const double* __restrict__ sign, const unsigned* __restrict__ idx,
+                                    const unsigned* __restrict__ keys, unsigned* __restrict__ offsets, long long n,
+                                    double* __restrict__ xk2, double* __restrict__ sign2, unsigned* __restrict__ idx2) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned pos = atomicAdd(&offsets[keys[i]], 1u);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xk2[c * n + pos] = xk[c * n + i];
+    sign2[pos] = sign[i];
+    idx2[pos] = idx[i];
+}
+
+// host-visible order: out[c][idx[i]] = xk[c][i]
+__global__ void unpermute_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n, int ncols,
+                                 double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long o = idx[i];
+    for (int c = 0; c < ncols; ++c) out[c * n + o] = xk[c * n + i];
+}
+
+// snapshot half <-> planar (nx, ny, 5) host layout staging
+__global__ void snap_to_planar_kernel(const double* __restrict__ S, int half, long long npts, double* __restrict__ planar) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+#pragma unroll
+    for (int c = 0; c < SNAP_NC; ++c) planar[c * npts + i] = S[i * SNAP_STRIDE + half * SNAP_NC + c];
+}
+__global__ void planar_to_snap_kernel(const double* __restrict__ planar, int half, long long npts, double* __restrict__ S) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+#pragma unroll
+    for (int c = 0; c < SNAP_NC; ++c) S[i * SNAP_STRIDE + half * SNAP_NC + c] = planar[c * npts + i];
 }
 
 }  // namespace swrt

@@ -33,16 +33,35 @@ __device__ __forceinline__ double wave_l(const SpecLayout& L, int j) {
 __device__ __forceinline__ bool l_retained(const SpecLayout& L, int j) { return j < L.lz0 || j >= L.lz1; }
 
 __host__ __device__ constexpr int group_size(int N) { return N >= 16 ? N / 16 : 1; }
+// column stride (in doubles) of the y-pass tile: >= padded_len(N) and == 16/TK (mod 16) so that the TK adjacent
+// columns touched by one half-warp fall into disjoint 8-byte banks
+__host__ __device__ constexpr int col_stride(int N, int TK) {
+    int cs = padded_len(N);
+    const int want = (16 / TK) % 16;
+    while (cs % 16 != want) ++cs;
+    return cs;
+}
+constexpr int kSmemPerSM = 227 * 1024;
+__host__ __device__ constexpr int clamp_blocks(long long smem_bytes, int threads) {
+    int b = (int)(kSmemPerSM / (smem_bytes + 1024));
+    const int by_threads = 1536 / threads;          // keep >= ~42 registers per thread available
+    if (b > by_threads) b = by_threads;
+    if (b > 8) b = 8;
+    return b < 1 ? 1 : b;
+}
+__host__ __device__ constexpr long long ypass_smem(int N, int TK) { return 2LL * TK * col_stride(N, TK) * 8; }
+constexpr int XPASS_BUFFERS = 2;
+__host__ __device__ constexpr long long xpass_smem(int N) { return 2LL * XPASS_BUFFERS * padded_len(N) * 8; }
 
 // ------------------------------------------------------------------------------------
 // y-pass, inverse direction: out[job][y][kr] = sum_l src_job(kr, l) exp(+2 pi i l y / ny)
 // Loader: __device__ double2 operator()(int job, int kr, int l, double kw, double lw, long long off)
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Loader>
-__global__ void __launch_bounds__(TK* group_size(N))
+__global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
     ypass_inv_kernel(Loader ld, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
-    constexpr int G = group_size(N), NP = padded_len(N), RPT = N / G;  // rows per thread
+    constexpr int G = group_size(N), NP = col_stride(N, TK), RPT = N / G;  // rows per thread
     double* re = smem;
     double* im = smem + TK * NP;
     const int tid = threadIdx.x;
@@ -81,11 +100,11 @@ __global__ void __launch_bounds__(TK* group_size(N))
 // out[var][l][kr] = sum_i apply(var, i, FFT_y(H[src(var,i)])[kr, l])
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
-__global__ void __launch_bounds__(TK* group_size(N))
+__global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
     ypass_fwd_kernel(Combiner cb, SpecLayout L, int nvars, const double2* __restrict__ H, double2* __restrict__ out,
                      const double2* __restrict__ tw) {
     extern __shared__ double smem[];
-    constexpr int G = group_size(N), NP = padded_len(N), RPT = N / G;
+    constexpr int G = group_size(N), NP = col_stride(N, TK), RPT = N / G;
     double* re = smem;
     double* im = smem + TK * NP;
     const int tid = threadIdx.x;
@@ -199,7 +218,7 @@ struct XCtx {
 };
 
 template <int N, class Op>
-__global__ void __launch_bounds__(group_size(N)) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
+__global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N), group_size(N))) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     XCtx<N> cx;
     cx.smem = smem;

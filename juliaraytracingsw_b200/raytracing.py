@@ -62,9 +62,9 @@ def swap_snapshots(prob, alias=False):
 class Packets:
     """Device-resident wave packets = `create_template_ode(packets)` + the packet arrays."""
 
-    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL):
+    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16):
         self.prob, self.n = prob, int(n)
-        d = PacketsDesc(n=self.n, interp=0, nsub=int(nsub), time_lerp=int(time_lerp), f=f, Cg=Cg)
+        d = PacketsDesc(n=self.n, interp=0, nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
         self._h = C.c_void_p()
         check(lib().swrt_packets_create(C.byref(d), prob._h, C.byref(self._h)))
 
@@ -98,9 +98,10 @@ class Packets:
         return n.value
 
 
-def generate_initial_wavepackets(prob, L, k0, Npackets, sqrtNpackets, f, Cg, nsub=1, first=0, time_lerp=LERP_PHYSICAL):
+def generate_initial_wavepackets(prob, L, k0, Npackets, sqrtNpackets, f, Cg, nsub=1, first=0, time_lerp=LERP_PHYSICAL,
+                                 sort_every=16):
     """raytracing/RaytracingDriver.jl:27-47; `first`/`Npackets` select a contiguous shard of the lattice."""
-    p = Packets(prob, Npackets, f, Cg, nsub=nsub, time_lerp=time_lerp)
+    p = Packets(prob, Npackets, f, Cg, nsub=nsub, time_lerp=time_lerp, sort_every=sort_every)
     p.generate(L, k0, sqrtNpackets, first)
     return p
 

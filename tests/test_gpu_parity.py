@@ -125,6 +125,32 @@ def test_raytrace_parity(lerp, nsub):
     np.testing.assert_allclose(raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 1), pk), G, rtol=0, atol=1e-12)
 
 
+def test_cell_sort_keeps_caller_order_bit_exact():
+    """The device copy is re-sorted by grid cell for locality; every host-visible array keeps the caller's rows."""
+    g, c, Fo, Fn, xk, sign = _packet_case(64, 40, 11)
+    prob = swrt.Problem(nx=64, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_velocity_info(prob, 0, Fo)
+    raytracing.set_velocity_info(prob, 1, Fn)
+    outs = []
+    for sort_every in (0, 1, 3):
+        pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=2, sort_every=sort_every)
+        pk.set(xk, sign)
+        t = 0.0
+        for _ in range(7):
+            raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t, t + c["dt"]))
+            t += c["dt"]
+        n_reset = pk.kcutoff_reset(5.3, c["k0"])
+        outs.append((pk.get(), raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 1), pk), n_reset))
+        pk.set(outs[-1][0])                                       # positions only: the signs must survive in caller order
+        raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t, t + c["dt"]))
+        outs[-1] += (pk.get(),)
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o[0], outs[0][0])
+        np.testing.assert_array_equal(o[1], outs[0][1])
+        assert o[2] == outs[0][2]
+        np.testing.assert_array_equal(o[3], outs[0][3])
+
+
 def test_sampler_exact_at_nodes_K6():
     g = TwoDGrid(64)
     rng = np.random.default_rng(0)
