@@ -663,6 +663,7 @@ static PacketGrid packet_grid(const swrt_flow* f) {
     g.nx = f->d.nx; g.ny = f->d.ny;
     g.dx = f->d.Lx / f->d.nx; g.dy = f->d.Ly / f->d.ny;
     g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
+    g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
     return g;
 }
 
@@ -710,7 +711,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     }
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp, f->slot_map[0], f->slot_map[1]};
     const long long n = p->d.n;
-    static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 6; }();  // tuning knob
+    static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knob
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
       if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);

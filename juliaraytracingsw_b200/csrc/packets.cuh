@@ -25,12 +25,14 @@ namespace swrt {
 
 struct PacketGrid {
     int nx, ny;
-    double x0, y0, dx, dy;
+    double x0, y0, dx, dy, inv_dx, inv_dy;
 };
 
-// s = (x - x0)/dx ; i = floor(s) mod n ; a = s - floor(s)   (division kept: index parity with the oracle)
-__device__ __forceinline__ void cell(double x, double x0, double dx, int n, int& i0, int& i1, double& a) {
-    const double s = (x - x0) / dx;
+// s = (x - x0)/dx ; i = floor(s) mod n ; a = s - floor(s).  The division is a multiplication by 1/dx (fp64 division
+// costs ~15 issue slots): s can differ from the oracle's by one ulp, which moves the interpolated value by O(1e-16)
+// (bilinear interpolation is continuous across cell edges).
+__device__ __forceinline__ void cell(double x, double x0, double inv_dx, int n, int& i0, int& i1, double& a) {
+    const double s = (x - x0) * inv_dx;
     const double fl = floor(s);
     a = s - fl;
     long long ii = (long long)fl % n;
@@ -75,8 +77,8 @@ __device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, doubl
                                         const PacketGrid& g, const RayParams& p, double (&d)[4]) {
     int i0, i1, j0, j1;
     double a, b;
-    cell(s[0], g.x0, g.dx, g.nx, i0, i1, a);
-    cell(s[1], g.y0, g.dy, g.ny, j0, j1, b);
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
     double V[10];
     bilinear10(S, g, i0, i1, j0, j1, a, b, V);
     const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
@@ -89,9 +91,9 @@ __device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, doubl
     for (int c = 0; c < 5; ++c) W[c] = p.old_half == p.new_half ? (p.old_half == 0 ? wo * V[c] + wn * V[c] : wo * V[5 + c] + wn * V[5 + c])
                                                                 : wA * V[c] + wB * V[5 + c];
     const double k = s[2], l = s[3];
-    const double w = sign * sqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));
-    d[0] = W[0] + p.Cg * p.Cg * k / w;
-    d[1] = W[1] + p.Cg * p.Cg * l / w;
+    const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));   // Cg^2 / omega
+    d[0] = W[0] + cg * k;
+    d[1] = W[1] + cg * l;
     d[2] = -(W[2] * k + W[4] * l);
     d[3] = -(W[3] * k - W[2] * l);
 }
@@ -104,20 +106,20 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
     if (i >= n) return;
     double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
     const double sg = sign[i];
-    const double h = (p.t1 - p.t0) / p.nsub, span = p.t1 - p.t0;
+    const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
         const double t = p.t0 + it * h;
         double k1[4], k2[4], k3[4], k4[4], y[4];
-        ray_rhs(s, sg, (t - p.t0) / span, S, g, p, k1);
+        ray_rhs(s, sg, (t - p.t0) * inv_span, S, g, p, k1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k1[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, S, g, p, k2);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, k2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k2[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) / span, S, g, p, k3);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, k3);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + h * k3[c];
-        ray_rhs(y, sg, (t + h - p.t0) / span, S, g, p, k4);
+        ray_rhs(y, sg, (t + h - p.t0) * inv_span, S, g, p, k4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
     }
@@ -135,8 +137,8 @@ __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ 
     if (i >= n) return;
     int i0, i1, j0, j1;
     double a, b, V[10];
-    cell(xk[i], g.x0, g.dx, g.nx, i0, i1, a);
-    cell(xk[n + i], g.y0, g.dy, g.ny, j0, j1, b);
+    cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
     bilinear10(S, g, i0, i1, j0, j1, a, b, V);
     double Sv[5];
 #pragma unroll
@@ -190,8 +192,8 @@ __global__ void iota_kernel(unsigned* __restrict__ idx, long long n) {
 __device__ __forceinline__ unsigned cell_key(double x, double y, const PacketGrid& g) {
     int i0, i1, j0, j1;
     double a;
-    cell(x, g.x0, g.dx, g.nx, i0, i1, a);
-    cell(y, g.y0, g.dy, g.ny, j0, j1, a);
+    cell(x, g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y, g.y0, g.inv_dy, g.ny, j0, j1, a);
     return (unsigned)((((j0 >> 3) * (g.nx >> 3) + (i0 >> 3)) << 6) + ((j0 & 7) << 3) + (i0 & 7));
 }
 
