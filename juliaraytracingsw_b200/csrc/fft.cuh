@@ -200,4 +200,83 @@ __device__ __forceinline__ void block_fft(double* re, double* im, int g, const d
     FftStages<N, 1, SIGN>::run(re, im, g, tw, active);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-interface variants (N >= 32).  "Strided register layout": thread g owns the 16 elements
+// n = g + m N/16, m = 0..15.  That is exactly what the first Stockham stage consumes (radix 16, P = 1)
+// and -- because the last stage of radix R writes j + t N/R with j = g + b N/16 -- also what the last
+// stage produces (m = b + t 16/R).  So data can enter the transform from registers (straight from
+// global memory) and leave it in registers (straight to global memory, or into the next transform's
+// first stage after a pointwise product) without the two extra shared-memory passes.
+// ---------------------------------------------------------------------------------------------
+template <int N, int SIGN>
+__device__ __forceinline__ void fft_first_stage_regs(double2 (&v)[16], double* __restrict__ re, double* __restrict__ im, int g) {
+    static_assert(N >= 32, "register interface needs N >= 32");
+    Dft<16, SIGN>::run(v);
+    __syncthreads();  // earlier readers of this buffer are done
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int idx = pad_index(g * 16 + t);
+        re[idx] = v[t].x;
+        im[idx] = v[t].y;
+    }
+    __syncthreads();
+}
+
+template <int N, int R, int P, int SIGN>
+__device__ __forceinline__ void fft_last_stage_regs(const double* __restrict__ re, const double* __restrict__ im, int g,
+                                                    const double2* __restrict__ tw, double2 (&out)[16]) {
+    constexpr int G = N / 16, B = 16 / R, T = N / R;
+    static_assert(P * R == N, "last stage");
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const int j = g + b * G;
+        double2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const int idx = pad_index(j + t * T);
+            v[t] = make_double2(re[idx], im[idx]);
+        }
+        double2 w1 = __ldg(&tw[j]);  // k = j (j < T = P), table stride N / (P R) = 1
+        if (SIGN > 0) w1.y = -w1.y;
+        double2 w[R];
+        w[1 % R] = w1;
+#pragma unroll
+        for (int t = 2; t < R; ++t) w[t] = (t & 1) ? cmul(w[t - 1], w1) : cmul(w[t / 2], w[t / 2]);
+#pragma unroll
+        for (int t = 1; t < R; ++t) v[t] = cmul(v[t], w[t]);
+        Dft<R, SIGN>::run(v);
+#pragma unroll
+        for (int t = 0; t < R; ++t) out[b + t * B] = v[t];
+    }
+}
+
+__host__ __device__ constexpr int last_stage_P(int N) {
+    int P = 16;
+    while (N / P > 16) P *= 16;
+    return P;
+}
+template <int N, int P, int SIGN>
+__device__ __forceinline__ void fft_middle_stages(double* re, double* im, int g, const double2* tw) {
+    if constexpr (N / P > 16) {  // radix-16 stages strictly between the first and the last
+        fft_stage<N, 16, P, SIGN>(re, im, g, tw, true);
+        fft_middle_stages<N, P * 16, SIGN>(re, im, g, tw);
+    }
+}
+
+// registers in -> registers out (both in the strided register layout); `re/im` is the work buffer
+template <int N, int SIGN>
+__device__ __forceinline__ void block_fft_regs(double2 (&v)[16], double* re, double* im, int g, const double2* tw) {
+    fft_first_stage_regs<N, SIGN>(v, re, im, g);
+    fft_middle_stages<N, 16, SIGN>(re, im, g, tw);
+    constexpr int LP = last_stage_P(N);
+    fft_last_stage_regs<N, N / LP, LP, SIGN>(re, im, g, tw, v);
+}
+
+// registers in -> shared memory out (natural order), ends with a barrier
+template <int N, int SIGN>
+__device__ __forceinline__ void block_fft_regs_in(double2 (&v)[16], double* re, double* im, int g, const double2* tw) {
+    fft_first_stage_regs<N, SIGN>(v, re, im, g);
+    FftStages<N, 16, SIGN>::run(re, im, g, tw, true);
+}
+
 }  // namespace swrt

@@ -56,40 +56,38 @@ __host__ __device__ constexpr long long xpass_smem(int N) { return 2LL * XPASS_B
 // ------------------------------------------------------------------------------------
 // y-pass, inverse direction: out[job][y][kr] = sum_l src_job(kr, l) exp(+2 pi i l y / ny)
 // Loader: __device__ double2 operator()(int job, int kr, int l, double kw, double lw, long long off)
+//
+// Thread (g, c) = (tid / TK, tid % TK) owns rows g + m N/16 of column kr0 + c: the values go from global
+// memory straight into the first FFT stage and from the last stage straight back to global memory; the TK
+// adjacent lanes of a row access TK adjacent complex numbers (16 TK contiguous bytes).
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Loader>
 __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
     ypass_inv_kernel(Loader ld, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
-    constexpr int G = group_size(N), NP = col_stride(N, TK), RPT = N / G;  // rows per thread
-    double* re = smem;
-    double* im = smem + TK * NP;
+    constexpr int G = group_size(N), NP = col_stride(N, TK);
     const int tid = threadIdx.x;
-    const int c = tid % TK, r0 = tid / TK;   // load/store mapping: TK adjacent lanes = TK adjacent kr
-    const int fg = tid / G, g = tid % G;     // fft mapping: group fg transforms column fg
+    const int c = tid % TK, g = tid / TK;
+    double* re = smem + c * NP;
+    double* im = smem + (TK + c) * NP;
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     for (int w = blockIdx.x; w < ntiles * njobs; w += gridDim.x) {
-        const int job = w / ntiles, kr0 = (w % ntiles) * TK;
-        const int kr = kr0 + c;
+        const int job = w / ntiles, kr = (w % ntiles) * TK + c;
         const double kw = kr * L.dk;
-#pragma unroll 4
-        for (int i = 0; i < RPT; ++i) {
-            const int l = r0 + i * G;
-            double2 v = make_double2(0.0, 0.0);
-            if (kr < L.kr_keep && l_retained(L, l)) v = ld(job, kr, l, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
-            re[c * NP + pad_index(l)] = v.x;
-            im[c * NP + pad_index(l)] = v.y;
+        const bool col_ok = kr < L.kr_keep;
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int l = g + m * G;
+            v[m] = make_double2(0.0, 0.0);
+            if (col_ok && l_retained(L, l)) v[m] = ld(job, kr, l, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
         }
-        block_fft<N, +1>(re + fg * NP, im + fg * NP, g, tw);
-        double2* o = out + (long long)job * L.vs;
-        if (kr < L.kr_keep) {
-#pragma unroll 4
-            for (int i = 0; i < RPT; ++i) {
-                const int y = r0 + i * G;
-                o[(long long)y * L.kr_pad + kr] = make_double2(re[c * NP + pad_index(y)], im[c * NP + pad_index(y)]);
-            }
+        block_fft_regs<N, +1>(v, re, im, g, tw);
+        if (col_ok) {
+            double2* o = out + (long long)job * L.vs + kr;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) o[(long long)(g + m * G) * L.kr_pad] = v[m];
         }
-        __syncthreads();
     }
 }
 
@@ -104,47 +102,41 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
     ypass_fwd_kernel(Combiner cb, SpecLayout L, int nvars, const double2* __restrict__ H, double2* __restrict__ out,
                      const double2* __restrict__ tw) {
     extern __shared__ double smem[];
-    constexpr int G = group_size(N), NP = col_stride(N, TK), RPT = N / G;
-    double* re = smem;
-    double* im = smem + TK * NP;
+    constexpr int G = group_size(N), NP = col_stride(N, TK);
     const int tid = threadIdx.x;
-    const int c = tid % TK, r0 = tid / TK;
-    const int fg = tid / G, g = tid % G;
+    const int c = tid % TK, g = tid / TK;
+    double* re = smem + c * NP;
+    double* im = smem + (TK + c) * NP;
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     for (int w = blockIdx.x; w < ntiles * nvars; w += gridDim.x) {
-        const int var = w / ntiles, kr0 = (w % ntiles) * TK;
-        const int kr = kr0 + c;
+        const int var = w / ntiles, kr = (w % ntiles) * TK + c;
         const double kw = kr * L.dk;
-        double2* o = out + (long long)var * L.vs;
+        const bool col_ok = kr < L.kr_keep;
+        double2* o = out + (long long)var * L.vs + kr;
         const int nin = cb.nin(var);
         for (int i_in = 0; i_in < nin; ++i_in) {
-            const double2* h = H + (long long)cb.src(var, i_in) * L.vs;
-#pragma unroll 4
-            for (int i = 0; i < RPT; ++i) {
-                const int y = r0 + i * G;
-                double2 v = make_double2(0.0, 0.0);
-                if (kr < L.kr_keep) v = h[(long long)y * L.kr_pad + kr];
-                re[c * NP + pad_index(y)] = v.x;
-                im[c * NP + pad_index(y)] = v.y;
+            const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr;
+            double2 v[16];
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                v[m] = make_double2(0.0, 0.0);
+                if (col_ok) v[m] = h[(long long)(g + m * G) * L.kr_pad];
             }
-            block_fft<N, -1>(re + fg * NP, im + fg * NP, g, tw);
-            if (kr < L.kr_keep) {
-#pragma unroll 4
-                for (int i = 0; i < RPT; ++i) {
-                    const int l = r0 + i * G;
+            block_fft_regs<N, -1>(v, re, im, g, tw);
+            if (col_ok) {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int l = g + m * G;
                     if (!l_retained(L, l)) continue;
-                    const long long off = (long long)l * L.kr_pad + kr;
-                    double2 v = cb.apply(var, i_in, make_double2(re[c * NP + pad_index(l)], im[c * NP + pad_index(l)]),
-                                         kw, wave_l(L, l));
+                    double2 r = cb.apply(var, i_in, v[m], kw, wave_l(L, l));
                     if (i_in > 0) {
-                        const double2 prev = o[off];
-                        v.x += prev.x;
-                        v.y += prev.y;
+                        const double2 prev = o[(long long)l * L.kr_pad];
+                        r.x += prev.x;
+                        r.y += prev.y;
                     }
-                    o[off] = v;
+                    o[(long long)l * L.kr_pad] = r;
                 }
             }
-            __syncthreads();
         }
     }
 }
@@ -200,6 +192,29 @@ struct XCtx {
     }
     __device__ __forceinline__ void ifft(int b) const { block_fft<N, +1>(re(b), im(b), g, tw); }
     __device__ __forceinline__ void fft(int b) const { block_fft<N, -1>(re(b), im(b), g, tw); }
+
+    // Register-interface versions (fft.cuh): v[m] <-> x (or k) = g + m N/16.
+    // Hermitian-extended spectrum of z = a + i b straight from the half spectra in global memory.
+    template <int MA, int MB>
+    __device__ __forceinline__ void load_pair_regs(double2 (&v)[16], const double2* __restrict__ A, const double2* __restrict__ B) const {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = g + m * G;
+            const int k = m < 8 ? x : N - x;            // m < 8  <=>  x < N/2
+            double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
+            if (k < kr_keep) {                           // also excludes k = N/2 (kr_keep <= N/2)
+                const double kw = k * dk;
+                za = apply_mul<MA>(__ldg(&A[k]), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(&B[k]), kw);
+            }
+            if (m < 8) v[m] = (m == 0 && x == 0) ? make_double2(za.x, zb.x) : make_double2(za.x - zb.y, za.y + zb.x);
+            else v[m] = make_double2(za.x + zb.y, zb.x - za.y);
+        }
+    }
+    // inverse transform, registers in -> registers out, work buffer b
+    __device__ __forceinline__ void ifft_regs(double2 (&v)[16], int b) const { block_fft_regs<N, +1>(v, re(b), im(b), g, tw); }
+    // forward transform, registers in -> shared memory buffer b (natural order; then store_pair)
+    __device__ __forceinline__ void fft_regs_in(double2 (&v)[16], int b) const { block_fft_regs_in<N, -1>(v, re(b), im(b), g, tw); }
 
     // After a forward transform of z = p + i q:  2 P[k] = Z[k] + conj Z[N-k],  2i Q[k] = Z[k] - conj Z[N-k].
     // Writes 2P and 2Q (callers fold the 1/2 into their scaling) for k < kr_keep.
