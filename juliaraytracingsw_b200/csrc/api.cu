@@ -711,10 +711,18 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     }
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp, f->slot_map[0], f->slot_map[1]};
     const long long n = p->d.n;
-    static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knob
+    static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
+    static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 1; }();
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
-      if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
+      if (cached) {
+#define SWRT_RT(MB, OH, NH) raytrace_rk4_cached_kernel<MB, OH, NH><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp)
+          const int oh = rp.old_half, nh = rp.new_half;
+          if (cached == 1) { if (oh == 0 && nh == 1) SWRT_RT(3, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(3, 1, 0); else if (oh == 0) SWRT_RT(3, 0, 0); else SWRT_RT(3, 1, 1); }
+          else { if (oh == 0 && nh == 1) SWRT_RT(4, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(4, 1, 0); else if (oh == 0) SWRT_RT(4, 0, 0); else SWRT_RT(4, 1, 1); }
+#undef SWRT_RT
+      }
+      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
       else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
       else if (minb <= 7) raytrace_rk4_kernel<6><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
       else raytrace_rk4_kernel<8><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp); }

@@ -33,63 +33,64 @@ struct RswLoaderA {
 // p1 = u ux + v uy, p2 = u vx + v vy, p3 = u eta, p4 = v eta [, p5 = 1.5 - 0.5/(1+eta)^2]
 template <int N, bool MODIFIED>
 struct RswXOp {
+    static constexpr int NBUF = 2;
     const double2* G;  // [5][ny][kr_pad]
     double2* H;        // [4 or 5][ny][kr_pad]
     double sc;         // (1/(nx ny))^2 / 2
     double s1;         // 1/(nx ny)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
-        constexpr int Gt = XCtx<N>::G;
+        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
         const long long ro = (long long)y * L.kr_pad;
         const double2 *Gu = G + ro, *Gv = G + L.vs + ro, *Ge = G + 2 * L.vs + ro, *Guy = G + 3 * L.vs + ro,
                       *Gvy = G + 4 * L.vs + ro;
-        // Thread g owns x = g + m N/16 (m = 0..15) of every physical row: inverse transforms deliver their
-        // results in registers, products are formed there and go straight into the forward transform.
-        // Buffer 0 only parks u, v at the thread's own x (no other thread reads them); buffer 1 is the FFT work space.
-        double *ur = cx.re(0), *vr = cx.im(0);
-        double2 v[16];
-        double p1[16];
-        cx.template load_pair_regs<MUL_ONE, MUL_ONE>(v, Gu, Gv);
-        cx.ifft_regs(v, 1);                             // u + i v
+        // two shared buffers: 0 keeps u + i v for the whole row, 1 is the work buffer; products are formed
+        // in place at the thread's own x positions (p1 waits in registers for p2)
+        cx.template load_pair<MUL_ONE, MUL_ONE>(0, Gu, Gv);
+        cx.ifft(0);                                     // buffer 0: u + i v
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft(1);                                     // buffer 1: ux + i uy
+        const double *ur = cx.re(0), *vr = cx.im(0);
+        double *br = cx.re(1), *bi = cx.im(1);
+        double p1[EPT];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int x = pad_index(cx.g + m * Gt);
-            ur[x] = v[m].x;
-            vr[x] = v[m].y;
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            p1[i] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
         }
-        cx.template load_pair_regs<MUL_IK, MUL_ONE>(v, Gu, Guy);
-        cx.ifft_regs(v, 1);                             // ux + i uy
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gv, Gvy);
+        cx.ifft(1);                                     // buffer 1: vx + i vy
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int x = pad_index(cx.g + m * Gt);
-            p1[m] = sc * (ur[x] * v[m].x + vr[x] * v[m].y);
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            const double p2 = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+            br[x] = p1[i];
+            bi[x] = p2;
         }
-        cx.template load_pair_regs<MUL_IK, MUL_ONE>(v, Gv, Gvy);
-        cx.ifft_regs(v, 1);                             // vx + i vy
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int x = pad_index(cx.g + m * Gt);
-            v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
-        }
-        cx.fft_regs_in(v, 1);
+        cx.fft(1);
         cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
-        cx.template load_pair_regs<MUL_ONE, MUL_ZERO>(v, Ge, nullptr);
-        cx.ifft_regs(v, 1);                             // eta
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, nullptr);
+        cx.ifft(1);                                     // buffer 1: eta
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int x = pad_index(cx.g + m * Gt);
-            const double e = v[m].x;
+        for (int i = 0; i < EPT; ++i) {
+            const int x = pad_index(cx.g + i * Gt);
+            const double e = br[x];
             if (MODIFIED) {
                 const double e1 = 1.0 + s1 * e;
-                p1[m] = 0.5 * (1.5 - 0.5 / (e1 * e1));
+                p1[i] = 0.5 * (1.5 - 0.5 / (e1 * e1));
             }
-            v[m] = make_double2(sc * (ur[x] * e), sc * (vr[x] * e));
+            br[x] = sc * (ur[x] * e);
+            bi[x] = sc * (vr[x] * e);
         }
-        cx.fft_regs_in(v, 1);
+        cx.fft(1);
         cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
         if (MODIFIED) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) v[m] = make_double2(p1[m], 0.0);
-            cx.fft_regs_in(v, 1);
+            for (int i = 0; i < EPT; ++i) {
+                const int x = pad_index(cx.g + i * Gt);
+                br[x] = p1[i];
+                bi[x] = 0.0;
+            }
+            cx.fft(1);
             cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 4 * L.vs + ro, nullptr);
         }
     }
@@ -130,6 +131,7 @@ struct FieldLoader {
 
 template <int N>
 struct C2ROp {
+    static constexpr int NBUF = 2;
     const double2* G;  // [1][ny][kr_pad]
     double* out;       // [ny][nx]
     double s1;
@@ -164,35 +166,31 @@ struct PsiLoader {
 
 template <int N>
 struct SnapshotXOp {
+    static constexpr int NBUF = 3;
     const double2* G;  // [3][ny][kr_pad]
     double* out;       // [ny][nx][2][5], already offset to the half being written
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
-        constexpr int Gt = XCtx<N>::G;
+        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
         const long long ro = (long long)y * L.kr_pad;
         const double2 *Gp = G + ro, *Gu = G + L.vs + ro, *Guy = G + 2 * L.vs + ro;
-        double2 v[16];
+        cx.template load_pair<MUL_ONE, MUL_IK>(0, Gu, Gp);
+        cx.ifft(0);  // u + i v
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft(1);  // ux + i uy
+        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, nullptr);
+        cx.ifft(2);  // vx
         double* o = out + (long long)y * N * SNAP_STRIDE;
-        cx.template load_pair_regs<MUL_ONE, MUL_IK>(v, Gu, Gp);
-        cx.ifft_regs(v, 1);  // u + i v
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            double* q = o + (long long)(cx.g + m * Gt) * SNAP_STRIDE;
-            q[0] = s1 * v[m].x;
-            q[1] = s1 * v[m].y;
+        for (int i = 0; i < EPT; ++i) {
+            const int x = cx.g + i * Gt, p = pad_index(x);
+            double* q = o + (long long)x * SNAP_STRIDE;   // the point's 40-byte half is written in one go
+            q[0] = s1 * cx.re(0)[p];
+            q[1] = s1 * cx.im(0)[p];
+            q[2] = s1 * cx.re(1)[p];
+            q[3] = s1 * cx.im(1)[p];
+            q[4] = s1 * cx.re(2)[p];
         }
-        cx.template load_pair_regs<MUL_IK, MUL_ONE>(v, Gu, Guy);
-        cx.ifft_regs(v, 1);  // ux + i uy
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            double* q = o + (long long)(cx.g + m * Gt) * SNAP_STRIDE;
-            q[2] = s1 * v[m].x;
-            q[3] = s1 * v[m].y;
-        }
-        cx.template load_pair_regs<MUL_MK2, MUL_ZERO>(v, Gp, nullptr);
-        cx.ifft_regs(v, 1);  // vx
-#pragma unroll
-        for (int m = 0; m < 16; ++m) o[(long long)(cx.g + m * Gt) * SNAP_STRIDE + 4] = s1 * v[m].x;
     }
 };
 
@@ -203,7 +201,6 @@ struct Launch {
     static constexpr int TK = tile_k(N);
     static constexpr int G = group_size(N);
     static constexpr size_t ysmem = (size_t)ypass_smem(N, TK);
-    static constexpr size_t xsmem = (size_t)xpass_smem(N);
 
     // one-time per kernel: opt in to the dynamic shared memory and size a persistent grid
     template <class K>
@@ -249,10 +246,11 @@ struct Launch {
     template <class Op>
     static cudaError_t xpass(const Op& op, const SpecLayout& L, const double2* tw, cudaStream_t st) {
         auto k = xpass_kernel<N, Op>;
+        constexpr size_t smem = (size_t)xpass_smem(N, Op::NBUF);
         int mc = 1;
-        cudaError_t e = prep(k, xsmem, G, &mc);
+        cudaError_t e = prep(k, smem, G, &mc);
         if (e != cudaSuccess) return e;
-        k<<<L.ny < mc ? L.ny : mc, G, xsmem, st>>>(op, L, tw);
+        k<<<L.ny < mc ? L.ny : mc, G, smem, st>>>(op, L, tw);
         return cudaGetLastError();
     }
 

@@ -50,8 +50,7 @@ __host__ __device__ constexpr int clamp_blocks(long long smem_bytes, int threads
     return b < 1 ? 1 : b;
 }
 __host__ __device__ constexpr long long ypass_smem(int N, int TK) { return 2LL * TK * col_stride(N, TK) * 8; }
-constexpr int XPASS_BUFFERS = 2;
-__host__ __device__ constexpr long long xpass_smem(int N) { return 2LL * XPASS_BUFFERS * padded_len(N) * 8; }
+__host__ __device__ constexpr long long xpass_smem(int N, int nbuf) { return 2LL * nbuf * padded_len(N) * 8; }
 
 // ------------------------------------------------------------------------------------
 // y-pass, inverse direction: out[job][y][kr] = sum_l src_job(kr, l) exp(+2 pi i l y / ny)
@@ -233,7 +232,7 @@ struct XCtx {
 };
 
 template <int N, class Op>
-__global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N), group_size(N))) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
+__global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N, Op::NBUF), group_size(N))) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     XCtx<N> cx;
     cx.smem = smem;
