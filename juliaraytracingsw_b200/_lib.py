@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libswrt.so")
+LIB_PATH = os.environ.get("SWRT_LIB", os.path.join(_HERE, "lib", "libswrt.so"))   # SWRT_LIB: A/B-test another build
 
 
 class SwrtError(RuntimeError):

@@ -712,14 +712,15 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp, f->slot_map[0], f->slot_map[1]};
     const long long n = p->d.n;
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
-    static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 1; }();
+    static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3..6 = cached kernel with that many CTAs/SM
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
       if (cached) {
 #define SWRT_RT(MB, OH, NH) raytrace_rk4_cached_kernel<MB, OH, NH><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp)
           const int oh = rp.old_half, nh = rp.new_half;
-          if (cached == 1) { if (oh == 0 && nh == 1) SWRT_RT(3, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(3, 1, 0); else if (oh == 0) SWRT_RT(3, 0, 0); else SWRT_RT(3, 1, 1); }
-          else { if (oh == 0 && nh == 1) SWRT_RT(4, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(4, 1, 0); else if (oh == 0) SWRT_RT(4, 0, 0); else SWRT_RT(4, 1, 1); }
+#define SWRT_RT4(MB) { if (oh == 0 && nh == 1) SWRT_RT(MB, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(MB, 1, 0); else if (oh == 0) SWRT_RT(MB, 0, 0); else SWRT_RT(MB, 1, 1); }
+          if (cached == 3) SWRT_RT4(3) else if (cached == 5) SWRT_RT4(5) else if (cached == 6) SWRT_RT4(6) else SWRT_RT4(4)
+#undef SWRT_RT4
 #undef SWRT_RT
       }
       else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);

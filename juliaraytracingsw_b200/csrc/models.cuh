@@ -195,7 +195,10 @@ struct SnapshotXOp {
 };
 
 // ---------------------------------------------------------------- per-size launchers
-__host__ __device__ constexpr int tile_k(int N) { return N >= 2048 ? 2 : (N >= 256 ? 4096 / N : 16); }
+#ifndef SWRT_TK_LARGE
+#define SWRT_TK_LARGE 4   // columns per y-pass CTA for N >= 2048 (tuning knob)
+#endif
+__host__ __device__ constexpr int tile_k(int N) { return N >= 2048 ? SWRT_TK_LARGE : (N >= 256 ? 4096 / N : 16); }
 template <int N>
 struct Launch {
     static constexpr int TK = tile_k(N);

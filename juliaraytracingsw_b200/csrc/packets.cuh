@@ -35,10 +35,9 @@ __device__ __forceinline__ void cell(double x, double x0, double inv_dx, int n, 
     const double s = (x - x0) * inv_dx;
     const double fl = floor(s);
     a = s - fl;
-    long long ii = (long long)fl % n;
-    if (ii < 0) ii += n;
-    i0 = (int)ii;
-    i1 = i0 + 1 == n ? 0 : i0 + 1;
+    // n is a power of two (api.cu: supported_n): the periodic wrap is a mask, also for negative cells
+    i0 = (int)((long long)fl & (long long)(n - 1));
+    i1 = (i0 + 1) & (n - 1);
 }
 
 // one x-row of the stencil: (1-a) S[j][i0] + a S[j][i1] for all ten interleaved values
