@@ -1,0 +1,149 @@
+# SWRT.jl -- thin ccall layer over libswrt.so (include/swrt.h), mirroring the call surface the reference's
+# drivers use: Problem / set_solution! / stepforward! / updatevars! / raytrace! / interpolate_*!.
+#
+# UNVERIFIED IN THIS REPOSITORY'S CI: no Julia toolchain exists in the build image; this file is the binding a
+# maintainer of ndefilippis/JuliaRaytracingSW would add (see INTEGRATION.md).  It uses only Base + Libdl.
+module SWRT
+
+using Libdl
+
+const libswrt = get(ENV, "SWRT_LIB", joinpath(@__DIR__, "..", "juliaraytracingsw_b200", "lib", "libswrt.so"))
+
+struct SwrtError <: Exception
+    code::Cint
+    msg::String
+end
+check(rc::Cint) = rc == 0 ? nothing : throw(SwrtError(rc, unsafe_string(ccall((:swrt_last_error, libswrt), Cstring, ()))))
+
+# --- descriptors: field order == include/swrt.h ---------------------------------------------------------------
+Base.@kwdef struct FlowDesc
+    model::Cint = 0;  stepper::Cint = 0
+    nx::Cint = 128;   ny::Cint = 128
+    nnu::Cint = 4;    use_filter::Cint = 0;  filter_order::Cint = 4;  device::Cint = 0
+    Lx::Cdouble = 2π; Ly::Cdouble = 2π; dt::Cdouble = 5e-2; nu::Cdouble = 1e-16; f::Cdouble = 1.0; Cg::Cdouble = 1.0
+    aliased_fraction::Cdouble = 1/3
+    filter_innerK::Cdouble = 2/3; filter_outerK::Cdouble = 1.0; filter_tol::Cdouble = 1e-15
+    U::Cdouble = 0.0; mu::Cdouble = 0.0; F::Cdouble = 0.0; Ro::Cdouble = 0.0; Kd2::Cdouble = 0.0
+end
+
+Base.@kwdef struct PacketsDesc
+    n::Clonglong
+    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16
+    f::Cdouble = 1.0; Cg::Cdouble = 1.0
+end
+
+const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1)
+
+# --- flow: RotatingShallowWater.Problem and friends (rsw/RotatingShallowWater.jl:70-133, 309-336) ---------------
+mutable struct Problem
+    h::Ptr{Cvoid}
+    nx::Int; ny::Int; nkr::Int; dt::Float64
+    function Problem(; model = "RotatingShallowWater", nx = 128, ny = nx, Lx = 2π, Ly = Lx, ν = 1e-16, nν = 4, f = 1.0, Cg = 1.0,
+                     dt = 5e-2, aliased_fraction = 1/3, use_filter = false, order = 4, dev = 0)
+        d = FlowDesc(model = MODELS[model], nx = nx, ny = ny, Lx = Lx, Ly = Ly, nu = ν, nnu = nν, f = f, Cg = Cg, dt = dt,
+                     aliased_fraction = aliased_fraction, use_filter = use_filter, filter_order = order, device = dev)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:swrt_flow_create, libswrt), Cint, (Ref{FlowDesc}, Ref{Ptr{Cvoid}}), d, out))
+        p = new(out[], nx, ny, nx ÷ 2 + 1, dt)
+        finalizer(q -> ccall((:swrt_flow_destroy, libswrt), Cint, (Ptr{Cvoid},), q.h), p)
+        return p
+    end
+end
+
+"set_solution!(prob, u0h, v0h, η0h): arrays (nkr, nl) ComplexF64"
+function set_solution!(prob::Problem, u0h, v0h, η0h)
+    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, 3)
+    sol[:, :, 1] .= u0h; sol[:, :, 2] .= v0h; sol[:, :, 3] .= η0h
+    check(ccall((:swrt_flow_set_solution, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, sol))
+end
+"Array(prob.sol)"
+function solution(prob::Problem)
+    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, 3)
+    check(ccall((:swrt_flow_get_solution, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, sol))
+    return sol
+end
+enforce_reality_condition!(prob::Problem) = check(ccall((:swrt_flow_enforce_reality, libswrt), Cint, (Ptr{Cvoid},), prob.h))
+"stepforward!(prob, diags, nsteps) -- diags: objects with .freq and increment!(d, prob)"
+function stepforward!(prob::Problem, diags = [], nsteps::Integer = 1)
+    if isempty(diags)
+        check(ccall((:swrt_flow_step, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, nsteps))
+    else
+        for _ in 1:nsteps
+            check(ccall((:swrt_flow_step, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, 1))
+            s = clock(prob).step
+            for d in diags
+                s % d.freq == 0 && d.increment!(d, prob)
+            end
+        end
+    end
+end
+function clock(prob::Problem)
+    t = Ref{Cdouble}(0); s = Ref{Clonglong}(0)
+    check(ccall((:swrt_flow_clock, libswrt), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Clonglong}), prob.h, t, s))
+    return (t = t[], step = Int(s[]), dt = prob.dt)
+end
+"updatevars!(prob) + Array(vars.<field>): which = 0 u, 1 v, 2 η, 16 ζ"
+function field(prob::Problem, which::Integer)
+    a = Array{Float64}(undef, prob.nx, prob.ny)
+    check(ccall((:swrt_flow_get_field, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), prob.h, which, a))
+    return a
+end
+function energies(prob::Problem)
+    ke = Ref{Cdouble}(0); pe = Ref{Cdouble}(0)
+    check(ccall((:swrt_flow_energies, libswrt), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}), prob.h, ke, pe))
+    return (kinetic_energy = ke[], potential_energy = pe[])
+end
+kinetic_energy(prob::Problem) = energies(prob).kinetic_energy
+potential_energy(prob::Problem) = energies(prob).potential_energy
+
+# --- packets: raytracing/GPURaytracing.jl -----------------------------------------------------------------------
+"get_streamfunction! + get_velocity_info into snapshot slot (0 = old, 1 = new)"
+get_velocity_info!(prob::Problem, slot::Integer; psi_kind = 0) =
+    check(ccall((:swrt_flow_velocity_snapshot, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint), prob.h, psi_kind, slot))
+"old_velocity = new_velocity; old_grad_v = new_grad_v"
+swap_snapshots!(prob::Problem; alias = false) =
+    check(ccall((:swrt_flow_swap_snapshots, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, alias))
+
+mutable struct Packets
+    h::Ptr{Cvoid}
+    n::Int
+    prob::Problem
+    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16)
+        d = PacketsDesc(n = n, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:swrt_packets_create, libswrt), Cint, (Ref{PacketsDesc}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), d, prob.h, out))
+        p = new(out[], n, prob)
+        finalizer(q -> ccall((:swrt_packets_destroy, libswrt), Cint, (Ptr{Cvoid},), q.h), p)
+        return p
+    end
+end
+"generate_initial_wavepackets(dev, L, k0, Npackets, sqrtNpackets) on the device; `first` = 0-based global row of this shard"
+function generate_initial_wavepackets(prob, L, k0, Npackets, sqrtNpackets; f, Cg, first = 0, kw...)
+    p = Packets(prob, Npackets; f, Cg, kw...)
+    check(ccall((:swrt_packets_generate, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Clonglong, Clonglong), p.h, L, k0, sqrtNpackets, first))
+    return p
+end
+set_packets!(p::Packets, xk::Matrix{Float64}, ωsign::Vector{Float64}) =
+    check(ccall((:swrt_packets_set, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), p.h, xk, ωsign))
+function Base.Array(p::Packets)
+    xk = Matrix{Float64}(undef, p.n, 4)
+    check(ccall((:swrt_packets_get, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), p.h, xk))
+    return xk
+end
+create_template_ode(p::Packets) = p
+"raytrace!(tmpl, v_old, v_new, g_old, g_new, grid, packets, dt, (t0, t1), params) -- snapshot slots 0/1 of the flow"
+raytrace!(tmpl, v1, v2, g1, g2, grid, p::Packets, dt, tspan, params = nothing) =
+    check(ccall((:swrt_packets_raytrace, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), p.h, tspan[1], tspan[2]))
+"interpolate_velocity!/interpolate_gradients! + Array: returns (U (N,2), G (N,4))"
+function interpolate_velocity_and_gradients(p::Packets, slot::Integer)
+    U = Matrix{Float64}(undef, p.n, 2); G = Matrix{Float64}(undef, p.n, 4)
+    check(ccall((:swrt_packets_sample, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), p.h, slot, U, G))
+    return U, G
+end
+function kcutoff_reset!(p::Packets, k_cutoff, k0)
+    n = Ref{Clonglong}(0)
+    check(ccall((:swrt_packets_kcutoff_reset, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Clonglong}), p.h, k_cutoff, k0, n))
+    return Int(n[])
+end
+
+end # module
