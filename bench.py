@@ -282,20 +282,30 @@ def run_swrt(args):
     peak, peak_src = load_peaks()
     F = 8.0 * args.nx * args.nx
     # dominant kernel by accumulated device time over the K profiled steps
-    top = max(kern.items(), key=lambda kv: kv[1]["ms_total"])
-    name, rec = top
-    per_unit = {"raytrace_rk4_kernel": ("1280 B gathered per packet-step (4 RK4 stages x 2 time levels x 5 fields x 4 taps x 8 B) "
-                                        "+ 72 B packet state", (1280.0 + 72.0) * nloc * args.nsub)}
-    flow_bytes = {"ypass_inv_kernel<RswLoaderA>": 8 * F, "xpass_kernel<RswXOp>": 9 * F, "ypass_fwd_kernel<RswCombiner>": 7 * F,
-                  "ifmab3_update_rsw_kernel": 15 * F}
-    if name in per_unit:
-        what, by = per_unit[name]
+    kern_k = {k: v for k, v in kern.items() if k != "packet_sort_kernels"}
+    name, rec = max(kern_k.items(), key=lambda kv: kv[1]["ms_total"])
+    share = rec["ms_total"] / sum(v["ms_total"] for v in kern.values())
+    if name == "raytrace_rk4_kernel":
+        # Compulsory HBM bytes of one launch: packet state in and out (x,y,k,l,sign read; x,y,k,l written = 72 B) plus
+        # every grid point of the two-level snapshot field once (80 B per point).  The 1280 B per packet-step that the
+        # four RK4 stages GATHER are served from registers/L1/L2 once packets are cell-sorted and the
+        # stencil is cached, so they are reported separately (gather_*), not as HBM traffic.
+        by = 72.0 * nloc * args.nsub + 80.0 * args.nx * args.nx
+        what = "72 B packet state per packet-step + 80 B per grid point of the two-level snapshot field once per launch"
+        extra = {"gather_bytes_per_launch": 1280.0 * nloc * args.nsub,
+                 "gather_achieved_gbs": 1280.0 * nloc * args.nsub / (rec["ms_avg"] * 1e-3) / 1e9,
+                 "gather_note": "SURVEY 8d figure (4 stages x 2 levels x 5 fields x 4 taps x 8 B); on-chip after sort + stencil cache",
+                 # ncu --set full, profiles/r01_d_ncu_raytrace_cached_16M.csv: dram read 1.007 GB + write 0.504 GB per launch
+                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, 16,777,216 packets on one GPU"}
+        traffic = 1.511e9 * (nloc / 16777216.0) if args.nx == 2048 else None
     else:
-        what, by = "SURVEY 8(d) F-units of this stage", flow_bytes.get(name, 0.0)
+        flow_bytes = {"ypass_inv_kernel<RswLoaderA>": 8 * F, "xpass_kernel<RswXOp>": 9 * F, "ypass_fwd_kernel<RswCombiner>": 7 * F,
+                      "ifmab3_update_rsw_kernel": 15 * F, "ypass_inv_kernel<PsiLoader>": 4 * F, "xpass_kernel<SnapshotXOp>": 8 * F}
+        by, what, extra, traffic = flow_bytes.get(name, 0.0), "F-units of this stage of the 42 F (+10 F snapshot) contract, SURVEY 8d", {}, None
     ach = by / (rec["ms_avg"] * 1e-3) / 1e9
-    roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    roofline = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": by, "per_unit": what, "avg_launch_ms": rec["ms_avg"], "peak_source": peak_src,
-                "share_of_step": rec["ms_total"] / sum(v["ms_total"] for v in kern.values())}
+                "share_of_step": share, **extra}
     spectral = {"steps_per_s": 1e3 / ms_flow, "ms_per_step": ms_flow, "algorithmic_bytes_per_step": 42 * F,
                 "achieved": 42 * F / (ms_flow * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 42 * F / (ms_flow * 1e-3) / 1e9 / peak,
                 "contract": "B_step = 42 F, F = 8 nx^2 bytes (SURVEY.md 8d, RSW + IFMAB3)"}
