@@ -272,6 +272,16 @@ __device__ __forceinline__ void block_fft_regs(double2 (&v)[16], double* re, dou
     fft_last_stage_regs<N, N / LP, LP, SIGN>(re, im, g, tw, v);
 }
 
+// shared memory in (natural order, written by other threads) -> registers out (strided register layout)
+template <int N, int SIGN>
+__device__ __forceinline__ void block_fft_regs_out(double* re, double* im, int g, const double2* tw, double2 (&v)[16]) {
+    __syncthreads();
+    fft_stage<N, 16, 1, SIGN>(re, im, g, tw, true);
+    fft_middle_stages<N, 16, SIGN>(re, im, g, tw);
+    constexpr int LP = last_stage_P(N);
+    fft_last_stage_regs<N, N / LP, LP, SIGN>(re, im, g, tw, v);
+}
+
 // registers in -> shared memory out (natural order), ends with a barrier
 template <int N, int SIGN>
 __device__ __forceinline__ void block_fft_regs_in(double2 (&v)[16], double* re, double* im, int g, const double2* tw) {

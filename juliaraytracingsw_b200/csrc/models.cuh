@@ -39,58 +39,59 @@ struct RswXOp {
     double sc;         // (1/(nx ny))^2 / 2
     double s1;         // 1/(nx ny)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
-        constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
+        constexpr int Gt = XCtx<N>::G;
         const long long ro = (long long)y * L.kr_pad;
         const double2 *Gu = G + ro, *Gv = G + L.vs + ro, *Ge = G + 2 * L.vs + ro, *Guy = G + 3 * L.vs + ro,
                       *Gvy = G + 4 * L.vs + ro;
-        // two shared buffers: 0 keeps u + i v for the whole row, 1 is the work buffer; products are formed
-        // in place at the thread's own x positions (p1 waits in registers for p2)
-        cx.template load_pair<MUL_ONE, MUL_ONE>(0, Gu, Gv);
-        cx.ifft(0);                                     // buffer 0: u + i v
-        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
-        cx.ifft(1);                                     // buffer 1: ux + i uy
-        const double *ur = cx.re(0), *vr = cx.im(0);
-        double *br = cx.re(1), *bi = cx.im(1);
-        double p1[EPT];
+        // Thread g owns x = g + m N/16 (m = 0..15) of the physical row.  Inverse transforms are loaded through shared
+        // memory (Hermitian extension needs k and N-k) but deliver their result in registers (last FFT stage); products
+        // are formed there and enter the forward transform's first stage directly.  Buffer 0 only parks u, v at the
+        // thread's own x (no other thread reads them); buffer 1 is the FFT work space.
+        double *ur = cx.re(0), *vr = cx.im(0);
+        double2 v[16];
+        double p1[16];
+        cx.template load_pair<MUL_ONE, MUL_ONE>(1, Gu, Gv);
+        cx.ifft_regs_out(1, v);                          // u + i v
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int x = pad_index(cx.g + i * Gt);
-            p1[i] = sc * (ur[x] * br[x] + vr[x] * bi[x]);
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            ur[x] = v[m].x;
+            vr[x] = v[m].y;
+        }
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft_regs_out(1, v);                          // ux + i uy
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            p1[m] = sc * (ur[x] * v[m].x + vr[x] * v[m].y);
         }
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gv, Gvy);
-        cx.ifft(1);                                     // buffer 1: vx + i vy
+        cx.ifft_regs_out(1, v);                          // vx + i vy
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int x = pad_index(cx.g + i * Gt);
-            const double p2 = sc * (ur[x] * br[x] + vr[x] * bi[x]);
-            br[x] = p1[i];
-            bi[x] = p2;
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
         }
-        cx.fft(1);
+        cx.fft_regs_in(v, 1);
         cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
         cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, nullptr);
-        cx.ifft(1);                                     // buffer 1: eta
+        cx.ifft_regs_out(1, v);                          // eta
 #pragma unroll
-        for (int i = 0; i < EPT; ++i) {
-            const int x = pad_index(cx.g + i * Gt);
-            const double e = br[x];
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            const double e = v[m].x;
             if (MODIFIED) {
                 const double e1 = 1.0 + s1 * e;
-                p1[i] = 0.5 * (1.5 - 0.5 / (e1 * e1));
+                p1[m] = 0.5 * (1.5 - 0.5 / (e1 * e1));
             }
-            br[x] = sc * (ur[x] * e);
-            bi[x] = sc * (vr[x] * e);
+            v[m] = make_double2(sc * (ur[x] * e), sc * (vr[x] * e));
         }
-        cx.fft(1);
+        cx.fft_regs_in(v, 1);
         cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
         if (MODIFIED) {
 #pragma unroll
-            for (int i = 0; i < EPT; ++i) {
-                const int x = pad_index(cx.g + i * Gt);
-                br[x] = p1[i];
-                bi[x] = 0.0;
-            }
-            cx.fft(1);
+            for (int m = 0; m < 16; ++m) v[m] = make_double2(p1[m], 0.0);
+            cx.fft_regs_in(v, 1);
             cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 4 * L.vs + ro, nullptr);
         }
     }

@@ -210,6 +210,8 @@ struct XCtx {
             else v[m] = make_double2(za.x + zb.y, zb.x - za.y);
         }
     }
+    // inverse transform of buffer b (filled by load_pair) -> registers out
+    __device__ __forceinline__ void ifft_regs_out(int b, double2 (&v)[16]) const { block_fft_regs_out<N, +1>(re(b), im(b), g, tw, v); }
     // inverse transform, registers in -> registers out, work buffer b
     __device__ __forceinline__ void ifft_regs(double2 (&v)[16], int b) const { block_fft_regs<N, +1>(v, re(b), im(b), g, tw); }
     // forward transform, registers in -> shared memory buffer b (natural order; then store_pair)
