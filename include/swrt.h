@@ -67,17 +67,23 @@ int swrt_flow_step(swrt_flow* h, int nsteps);
 int swrt_flow_clock(swrt_flow* h, double* t, long long* step);
 int swrt_flow_set_clock(swrt_flow* h, double t, long long step);
 /* updatevars!(prob) + Array(vars.<field>) :101-116; real_host is float64 (nx, ny) column-major */
-enum { SWRT_FIELD_U = 0, SWRT_FIELD_V = 1, SWRT_FIELD_ETA = 2, SWRT_FIELD_ZETA = 16 };
+enum { SWRT_FIELD_U = 0, SWRT_FIELD_V = 1, SWRT_FIELD_ETA = 2, SWRT_FIELD_ZETA = 16,
+       /* QG models (swqg/SWQG.jl:109-125, swqg/TwoLayerQG.jl:113-129): state variable j = q_j; add the layer index */
+       SWRT_FIELD_QG_PSI = 32, SWRT_FIELD_QG_U = 40, SWRT_FIELD_QG_V = 48, SWRT_FIELD_QG_ZETA = 56 };
 int swrt_flow_get_field(swrt_flow* h, int which, double* real_host);
-/* kinetic_energy(prob), potential_energy(prob) :323-336 */
+/* kinetic_energy(prob), potential_energy(prob): rsw/RotatingShallowWater.jl:323-336, swqg/SWQG.jl:205-222,
+ * swqg/TwoLayerQG.jl:221-250 (two-layer: ke = KE_1 + KE_2; the per-layer values through swrt_flow_layer_kinetic_energy) */
 int swrt_flow_energies(swrt_flow* h, double* ke, double* pe);
+int swrt_flow_layer_kinetic_energy(swrt_flow* h, int layer, double* ke);
 /* maximum(abs.(vars.u)), maximum(abs.(vars.v)) (CFL log, raytracing/RaytracingDriver.jl:244) and
  * any(isnan.(vars.uh)) (:282) */
 int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax);
 int swrt_flow_has_nan(swrt_flow* h, int* flag);
 /* get_streamfunction! (rsw/RSWRaytracingDriver.jl:56-67) + get_velocity_info
  * (raytracing/RaytracingDriver.jl:132-154) into snapshot slot 0 (old) or 1 (new); stays on device */
-enum { SWRT_PSI_RSW_BALANCED = 0 };
+/* RSW balanced psi; SWQG psi (swqg/RaytracingDriver.jl); two-layer baroclinic 0.5(psi1-psi2) (swqg/TwoLayerRaytracingDriver.jl:232)
+ * and layer mean (psi1+psi2)/2 (raytracing/TwoLayerRaytracing.jl:122) */
+enum { SWRT_PSI_RSW_BALANCED = 0, SWRT_PSI_SWQG = 1, SWRT_PSI_TWOLAYER_BAROCLINIC = 2, SWRT_PSI_TWOLAYER_MEAN = 3 };
 int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot);
 /* old_velocity = new_velocity; old_grad_v = new_grad_v (raytracing/RaytracingDriver.jl:269-270).
  * alias != 0 reproduces the reference's rebinding (both names then refer to the same buffers);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "swrt_flow_set_clock": (_I, [_P, _D, _LL]),
     "swrt_flow_get_field": (_I, [_P, _I, _P]),
     "swrt_flow_energies": (_I, [_P, _PD, _PD]),
+    "swrt_flow_layer_kinetic_energy": (_I, [_P, _I, _PD]),
     "swrt_flow_max_abs_uv": (_I, [_P, _PD, _PD]),
     "swrt_flow_has_nan": (_I, [_P, _PI]),
     "swrt_flow_velocity_snapshot": (_I, [_P, _I, _I]),

@@ -1,5 +1,6 @@
 // libswrt C ABI: handle management, host-side tables, kernel dispatch.  See include/swrt.h.
 #include <cmath>
+#include <complex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,7 @@ struct swrt_flow {
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
+    double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
     double* snap = nullptr;      // S[ny][nx][2][5]: both snapshot halves interleaved (snapshot_layout.cuh)
     int slot_map[2] = {0, 1};    // slot (0 = old, 1 = new) -> half
     double* phys = nullptr;
@@ -224,7 +226,7 @@ static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, 
 }
 
 static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
-    FieldLoader ld{h->sol, h->L.vs, which, h->d.f};
+    FieldLoader ld{h->sol, h->L.vs, which, h->nvar, h->d.f, h->L.aux0};
     cudaError_t e;
     { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st)); }
     CK(e);
@@ -251,7 +253,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
-    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef);
+    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab);
     cudaFree(h->snap); cudaFree(h->phys); cudaFree(h->red);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
@@ -267,8 +269,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     *out = nullptr;
     const swrt_flow_desc& d = *desc;
     if (!supported_n(d.nx) || !supported_n(d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "nx, ny must be powers of two in [32, 4096] (got %d x %d)", d.nx, d.ny);
-    if (d.model != SWRT_RSW && d.model != SWRT_RSW_MODIFIED) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
-    if (d.stepper != SWRT_IFMAB3) return fail(SWRT_ERR_UNSUPPORTED, "stepper %d not implemented", d.stepper);
+    const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG;
+    if (!rsw_family && d.model != SWRT_SWQG && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
+    if (d.stepper != SWRT_IFMAB3 && !(d.stepper == SWRT_FILTEREDAB3 && d.model == SWRT_SWQG))
+        return fail(SWRT_ERR_UNSUPPORTED, "stepper %d not implemented for model %d (FilteredAB3 needs a diagonal L)", d.stepper, d.model);
     if (!(d.Lx > 0 && d.Ly > 0 && d.dt > 0)) return fail(SWRT_ERR_ARG, "Lx, Ly, dt must be positive");
     if (!(d.aliased_fraction >= 0 && d.aliased_fraction < 1)) return fail(SWRT_ERR_ARG, "aliased_fraction must be in [0,1)");
     int ndev = 0;
@@ -279,8 +283,9 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     swrt_flow* h = new swrt_flow;
     h->d = d;
     h->nkr = d.nx / 2 + 1;
-    h->njobs_a = 5;
-    h->njobs_b = d.model == SWRT_RSW_MODIFIED ? 5 : 4;
+    h->nvar = model_nvar(d.model);
+    h->njobs_a = model_njobs_a(d.model) > 3 ? model_njobs_a(d.model) : 3;   // the snapshot pass needs 3 slots of G
+    h->njobs_b = model_njobs_b(d.model);
     SpecLayout& L = h->L;
     L.nx = d.nx; L.ny = d.ny;
     int klo, dummy0, dummy1;
@@ -290,7 +295,9 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     L.kr_pad = (L.kr_keep + 15) / 16 * 16;
     L.vs = (long long)L.ny * L.kr_pad;
     L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
-    L.f = d.f; L.Cg2 = d.Cg * d.Cg; L.aux0 = L.aux1 = 0;
+    L.f = d.f; L.Cg2 = d.Cg * d.Cg; L.aux1 = 0;
+    // model constant used by the loaders: Kd2 = f^2/Cg^2 (SWQG, swqg/SWQG.jl:85; RSW balanced psi) or F (two-layer, swqg/TwoLayerQG.jl:79)
+    L.aux0 = d.model == SWRT_TWOLAYERQG ? d.F : (d.Kd2 > 0 ? d.Kd2 : d.f * d.f / L.Cg2);
 
     auto bail = [&](int code) { swrt_flow_destroy(h); return code; };
 #define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
@@ -311,34 +318,65 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(upload_twiddles(d.nx, &h->tw_x));
     CKB(upload_twiddles(d.ny, &h->tw_y));
 
-    // coefficient table {e^{D dt}, sin(w dt)/w, (1-cos(w dt))/w^2, filter}
+    // coefficient table {e^{D dt}, sin(w dt)/w | D, (1-cos(w dt))/w^2, filter}; two-layer QG: tabulated 2x2 exponentials
     {
         std::vector<double4> cf((size_t)L.vs, make_double4(1.0, 0.0, 0.0, 1.0));
+        std::vector<double2> E, E2;
+        if (d.model == SWRT_TWOLAYERQG) { E.assign((size_t)4 * L.vs, make_double2(0, 0)); E2 = E; }
         const double w2c = d.model == SWRT_RSW_MODIFIED ? 0.0 : L.Cg2;
         const double innerK = d.filter_innerK > 0 ? d.filter_innerK : 2.0 / 3.0, outerK = d.filter_outerK > 0 ? d.filter_outerK : 1.0;
         const double tol = d.filter_tol > 0 ? d.filter_tol : 1e-15;
         const int order = d.filter_order > 0 ? d.filter_order : 4;
         const double decay = -std::log(tol) / std::pow(outerK - innerK, order);
         const double dx = d.Lx / d.nx, dy = d.Ly / d.ny;
+        using cplx = std::complex<double>;
+        auto expm2 = [](cplx a, cplx b, cplx c, cplx dd, cplx* o) {   // e^s [cosh q I + sinh(q)/q (A - s I)]  
+            const cplx s = 0.5 * (a + dd), q = std::sqrt(0.25 * (a - dd) * (a - dd) + b * c);
+            const cplx sh = std::abs(q) < 1e-8 ? 1.0 + q * q / 6.0 : std::sinh(q) / q, ch = std::cosh(q), es = std::exp(s);
+            o[0] = es * (ch + sh * (a - s)); o[1] = es * sh * b; o[2] = es * sh * c; o[3] = es * (ch + sh * (dd - s));
+        };
         for (int l = 0; l < d.ny; ++l) {
             const double lw = (double)(l < d.ny / 2 ? l : l - d.ny) * L.dl;
             for (int kr = 0; kr < L.kr_keep; ++kr) {
                 const double kw = kr * L.dk, K2 = kw * kw + lw * lw;
                 const double D = -d.nu * std::pow(K2, (double)d.nnu);
-                const double w2 = d.f * d.f + w2c * K2, w = std::sqrt(w2), th = w * d.dt;
-                double s, c;
-                if (w > 0) { s = std::sin(th) / w; const double sh = std::sin(0.5 * th); c = 2.0 * sh * sh / w2; }
-                else { s = d.dt; c = 0.5 * d.dt * d.dt; }
+                const size_t off = (size_t)l * L.kr_pad + kr;
                 double filt = 1.0;
-                if (d.use_filter) {
+                if (d.use_filter || d.stepper == SWRT_FILTEREDAB3) {
                     const double Kn = std::sqrt((kw * dx / M_PI) * (kw * dx / M_PI) + (lw * dy / M_PI) * (lw * dy / M_PI));
                     if (Kn >= innerK) filt = std::exp(-decay * std::pow(Kn - innerK, order));
                 }
-                cf[(size_t)l * L.kr_pad + kr] = make_double4(std::exp(D * d.dt), s, c, filt);
+                if (rsw_family) {
+                    const double w2 = d.f * d.f + w2c * K2, w = std::sqrt(w2), th = w * d.dt;
+                    double s, c;
+                    if (w > 0) { s = std::sin(th) / w; const double sh = std::sin(0.5 * th); c = 2.0 * sh * sh / w2; }
+                    else { s = d.dt; c = 0.5 * d.dt * d.dt; }
+                    cf[off] = make_double4(std::exp(D * d.dt), s, c, filt);
+                } else if (d.model == SWRT_SWQG) {
+                    cf[off] = make_double4(std::exp(D * d.dt), D, 0.0, filt);
+                } else {   // two-layer QG, swqg/TwoLayerQG.jl:184-198 (evaluated in double; the reference's Float32 temporaries are a bug)
+                    const double F = d.F, U = d.U, K2inv = K2 > 0 ? 1.0 / K2 : 0.0;
+                    const cplx p0(0.0, -2.0 * kw * F * U), p1 = cplx(0.0, 2.0 * kw * F * U) + d.mu * K2;
+                    const double sc = 1.0 / (K2 + 2 * F) * K2inv;
+                    const double S00 = (-K2 - F) * sc, S01 = -F * sc;
+                    cplx a = p0 * S00 + cplx(D, -kw * U), b = p0 * S01, c = p1 * S01, dd = p1 * S00 + cplx(D, kw * U);
+                    cplx o[4];
+                    expm2(a * d.dt, b * d.dt, c * d.dt, dd * d.dt, o);
+                    for (int q = 0; q < 4; ++q) E[(size_t)q * L.vs + off] = make_double2(o[q].real(), o[q].imag());
+                    expm2(a * (2 * d.dt), b * (2 * d.dt), c * (2 * d.dt), dd * (2 * d.dt), o);
+                    for (int q = 0; q < 4; ++q) E2[(size_t)q * L.vs + off] = make_double2(o[q].real(), o[q].imag());
+                    cf[off] = make_double4(1.0, 0.0, 0.0, filt);
+                }
             }
         }
         CKB(cudaMalloc(&h->coef, sizeof(double4) * cf.size()));
         CKB(cudaMemcpy(h->coef, cf.data(), sizeof(double4) * cf.size(), cudaMemcpyHostToDevice));
+        if (!E.empty()) {
+            CKB(cudaMalloc(&h->Etab, sizeof(double2) * E.size()));
+            CKB(cudaMemcpy(h->Etab, E.data(), sizeof(double2) * E.size(), cudaMemcpyHostToDevice));
+            CKB(cudaMalloc(&h->E2tab, sizeof(double2) * E2.size()));
+            CKB(cudaMemcpy(h->E2tab, E2.data(), sizeof(double2) * E2.size(), cudaMemcpyHostToDevice));
+        }
     }
 #undef CKB
     *out = h;
@@ -378,9 +416,9 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
     if (!h || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    const int modified = h->d.model == SWRT_RSW_MODIFIED;
+    const int model = h->d.model;
+    const bool modified = model == SWRT_RSW_MODIFIED;
     RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
-    RswCombiner cb{modified, L.Cg2};
     const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
     const int ublocks = (int)((nmodes + 255) / 256);
     for (int s = 0; s < nsteps; ++s) {
@@ -388,15 +426,24 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
         const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
         const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
         cudaError_t e;
-        RswLoaderA ld{h->sol, L.vs};
-        { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::rsw_stage_a(ld, L, h->G, h->tw_y, h->st)); }
+        { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, h->sol, h->G, L, h->tw_y, h->st)); }
         CK(e);
-        { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::rsw_stage_b(modified, h->G, h->H, L, h->tw_x, h->st)); }
+        { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->st)); }
         CK(e);
-        { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::rsw_stage_c(cb, L, h->H, Ncur, h->tw_y, h->st)); }
+        { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, h->H, Ncur, L, h->tw_y, h->st)); }
         CK(e);
         UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, h->d.dt, h->step < 3 ? 1 : 0};
-        { ProfScope ps(h, K_UPDATE); ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L); }
+        {
+            ProfScope ps(h, K_UPDATE);
+            if (model == SWRT_SWQG) {
+                if (h->d.stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+                else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+            } else if (model == SWRT_TWOLAYERQG) {
+                ifmab3_update_table_kernel<2><<<ublocks, 256, 0, h->st>>>(ua, h->Etab, h->E2tab, L);
+            } else {
+                ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+            }
+        }
         CK(cudaGetLastError());
         h->ring = (h->ring + 1) % 3;
         h->t += h->d.dt;
@@ -420,7 +467,10 @@ int swrt_flow_set_clock(swrt_flow* h, double t, long long step) {
 
 int swrt_flow_get_field(swrt_flow* h, int which, double* real_host) {
     if (!h || !real_host) return fail(SWRT_ERR_ARG, "null pointer");
-    if (!((which >= 0 && which < h->nvar) || which == SWRT_FIELD_ZETA)) return fail(SWRT_ERR_ARG, "unknown field %d", which);
+    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG;
+    const bool ok = (which >= 0 && which < h->nvar) || (!qg && which == SWRT_FIELD_ZETA) ||
+                    (qg && which >= SWRT_FIELD_QG_PSI && which < SWRT_FIELD_QG_PSI + 32 && ((which - 32) & 7) < h->nvar);
+    if (!ok) return fail(SWRT_ERR_ARG, "unknown field %d for model %d", which, h->d.model);
     CK(cudaSetDevice(h->d.device));
     int rc = spectral_to_physical(h, which, h->phys);
     if (rc) return rc;
@@ -429,20 +479,50 @@ int swrt_flow_get_field(swrt_flow* h, int which, double* real_host) {
     return SWRT_OK;
 }
 
+static double spectral_diag(swrt_flow* h, int which, int arg, cudaError_t* err) {
+    const int blocks = 296;
+    { ProfScope ps(h, K_OTHER); spectral_diag_kernel<<<blocks, 256, 0, h->st>>>(h->sol, h->L, which, arg, h->nvar, h->L.aux0, h->red); }
+    std::vector<double> part(blocks);
+    *err = cudaMemcpyAsync(part.data(), h->red, sizeof(double) * blocks, cudaMemcpyDeviceToHost, h->st);
+    if (*err != cudaSuccess) return 0;
+    *err = cudaStreamSynchronize(h->st);
+    double acc = 0;
+    for (double p : part) acc += p;
+    const SpecLayout& L = h->L;
+    return acc * h->d.Lx * h->d.Ly / ((double)L.nx * L.nx * (double)L.ny * L.ny);   // parsevalsum normalisation
+}
+
 int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    const double norm = h->d.Lx * h->d.Ly / ((double)L.nx * L.nx * (double)L.ny * L.ny);
-    cudaError_t e = cudaSuccess;
-    double p2[3];
-    for (int v = 0; v < 3; ++v) {
-        p2[v] = norm * reduce_host(h, reinterpret_cast<const double*>(h->sol + v * L.vs), L.vs, 0, &e);
-        CK(e);
-    }
     const double A = h->d.Lx * h->d.Ly;
-    if (ke) *ke = p2[0] / (2 * A) + p2[1] / (2 * A);
-    if (pe) *pe = 0.5 * L.Cg2 * p2[2] / A;
+    cudaError_t e = cudaSuccess;
+    double k = 0, p = 0;
+    if (h->d.model == SWRT_SWQG) {            // swqg/SWQG.jl:205-222
+        k = spectral_diag(h, DIAG_QG_K2PSI2, 0, &e) / (2 * A); CK(e);
+        p = L.aux0 * spectral_diag(h, DIAG_QG_PSI2, 0, &e) / (2 * A); CK(e);
+    } else if (h->d.model == SWRT_TWOLAYERQG) {   // swqg/TwoLayerQG.jl:221-250 (KE_1 + KE_2)
+        k = spectral_diag(h, DIAG_QG_K2PSI2, 0, &e) / A; CK(e);
+        k += spectral_diag(h, DIAG_QG_K2PSI2, 1, &e) / A; CK(e);
+        p = L.aux0 * spectral_diag(h, DIAG_QG_DPSI2, 0, &e) / (2 * A); CK(e);
+    } else {                                   // rsw/RotatingShallowWater.jl:323-336
+        k = spectral_diag(h, DIAG_ABS2_VAR, 0, &e) / (2 * A); CK(e);
+        k += spectral_diag(h, DIAG_ABS2_VAR, 1, &e) / (2 * A); CK(e);
+        p = 0.5 * L.Cg2 * spectral_diag(h, DIAG_ABS2_VAR, 2, &e) / A; CK(e);
+    }
+    if (ke) *ke = k;
+    if (pe) *pe = p;
+    return SWRT_OK;
+}
+
+int swrt_flow_layer_kinetic_energy(swrt_flow* h, int layer, double* ke) {
+    if (!h || !ke) return fail(SWRT_ERR_ARG, "null pointer");
+    if (h->d.model != SWRT_TWOLAYERQG || layer < 0 || layer > 1) return fail(SWRT_ERR_ARG, "layer kinetic energy is defined for the two-layer model");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e = cudaSuccess;
+    *ke = spectral_diag(h, DIAG_QG_K2PSI2, layer, &e) / (h->d.Lx * h->d.Ly);
+    CK(e);
     return SWRT_OK;
 }
 
@@ -451,12 +531,16 @@ int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax) {
     CK(cudaSetDevice(h->d.device));
     cudaError_t e = cudaSuccess;
     double* outs[2] = {umax, vmax};
+    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG;
     for (int v = 0; v < 2; ++v) {
         if (!outs[v]) continue;
-        int rc = spectral_to_physical(h, v, h->phys);
-        if (rc) return rc;
-        *outs[v] = reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e);
-        CK(e);
+        *outs[v] = 0.0;
+        for (int layer = 0; layer < (qg ? h->nvar : 1); ++layer) {   // QG: u = -psi_y, v = psi_x of every layer
+            int rc = spectral_to_physical(h, qg ? (v == 0 ? SWRT_FIELD_QG_U : SWRT_FIELD_QG_V) + layer : v, h->phys);
+            if (rc) return rc;
+            *outs[v] = std::fmax(*outs[v], reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e));
+            CK(e);
+        }
     }
     return SWRT_OK;
 }
@@ -465,7 +549,7 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag) {
     if (!h || !flag) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e = cudaSuccess;
-    const double c = reduce_host(h, reinterpret_cast<const double*>(h->sol), 2 * h->L.vs, 2, &e);  // vars.uh
+    const double c = reduce_host(h, reinterpret_cast<const double*>(h->sol), 2 * h->L.vs, 2, &e);  // vars.uh / vars.qh[:,:,1]
     CK(e);
     *flag = c > 0;
     return SWRT_OK;
@@ -473,10 +557,13 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag) {
 
 int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
-    if (psi_kind != SWRT_PSI_RSW_BALANCED) return fail(SWRT_ERR_UNSUPPORTED, "psi kind %d not implemented", psi_kind);
+    const bool rsw_family = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;
+    const bool ok = (psi_kind == SWRT_PSI_RSW_BALANCED && rsw_family) || (psi_kind == SWRT_PSI_SWQG && h->d.model == SWRT_SWQG) ||
+                    ((psi_kind == SWRT_PSI_TWOLAYER_BAROCLINIC || psi_kind == SWRT_PSI_TWOLAYER_MEAN) && h->d.model == SWRT_TWOLAYERQG);
+    if (!ok) return fail(SWRT_ERR_ARG, "psi kind %d does not apply to model %d", psi_kind, h->d.model);
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, h->d.f * h->d.f / L.Cg2};
+    PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0};
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st)); }
     CK(e);

@@ -9,24 +9,38 @@
 namespace swrt {
 
 template <>
-cudaError_t Launch<SWRT_N>::rsw_stage_a(const RswLoaderA& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st) {
-    return ypass_inv(ld, L, 5, G_, tw, st);
-}
-template <>
-cudaError_t Launch<SWRT_N>::rsw_stage_b(int modified, const double2* G_, double2* H, const SpecLayout& L, const double2* tw,
-                                        cudaStream_t st) {
-    const double s1 = 1.0 / ((double)L.nx * (double)L.ny);
-    if (modified) {
-        RswXOp<SWRT_N, true> op{G_, H, 0.5 * s1 * s1, s1};
-        return xpass(op, L, tw, st);
+cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+    switch (model) {
+        case MODEL_RSW:
+        case MODEL_RSW_MODIFIED: return ypass_inv(RswLoaderA{sol, L.vs}, L, 5, G_, tw, st);
+        case MODEL_RSW_LINDBORG: return ypass_inv(LindborgLoaderA{sol, L.vs}, L, 8, G_, tw, st);
+        case MODEL_SWQG: return ypass_inv(QgLoaderA{sol, L.vs, 1, L.aux0}, L, 3, G_, tw, st);
+        case MODEL_TWOLAYERQG: return ypass_inv(QgLoaderA{sol, L.vs, 2, L.aux0}, L, 6, G_, tw, st);
     }
-    RswXOp<SWRT_N, false> op{G_, H, 0.5 * s1 * s1, s1};
-    return xpass(op, L, tw, st);
+    return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::rsw_stage_c(const RswCombiner& cb, const SpecLayout& L, const double2* H, double2* Nout, const double2* tw,
-                                        cudaStream_t st) {
-    return ypass_fwd(cb, L, 3, H, Nout, tw, st);
+cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+    const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
+    switch (model) {
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1}, L, tw, st);
+        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1}, L, tw, st);
+        case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc}, L, tw, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc}, L, tw, st);
+    }
+    return cudaErrorInvalidValue;
+}
+template <>
+cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+    switch (model) {
+        case MODEL_RSW: return ypass_fwd(RswCombiner{0, L.Cg2}, L, 3, H, Nout, tw, st);
+        case MODEL_RSW_MODIFIED: return ypass_fwd(RswCombiner{1, L.Cg2}, L, 3, H, Nout, tw, st);
+        case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, H, Nout, tw, st);
+        case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, H, Nout, tw, st);
+        case MODEL_TWOLAYERQG: return ypass_fwd(QgCombiner{}, L, 2, H, Nout, tw, st);
+    }
+    return cudaErrorInvalidValue;
 }
 template <>
 cudaError_t Launch<SWRT_N>::field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st) {

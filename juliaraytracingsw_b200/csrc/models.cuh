@@ -11,7 +11,12 @@
 
 namespace swrt {
 
-enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2 };
+enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5 };
+
+// per-model sizes: state variables, y-transformed intermediates (stage A jobs), x-transformed products (stage B outputs)
+__host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (m == MODEL_TWOLAYERQG ? 2 : 3); }
+__host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_SWQG ? 3 : (m == MODEL_TWOLAYERQG ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
+__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : (m == MODEL_RSW_MODIFIED ? 5 : 4))); }
 
 // ---------------------------------------------------------------- RSW family, stage A
 // jobs: 0 uh, 1 vh, 2 etah, 3 i l uh, 4 i l vh     (ux, vx are derived in the x-pass as i k G)
@@ -115,18 +120,173 @@ struct RswCombiner {
     }
 };
 
+// ---------------------------------------------------------------- Lindborg RSW (rsw/LinborgShallowWater.jl:144-241)
+// advecting velocity = rotational part: urh = -l (k vh - l uh)/K^2, vrh = k (k vh - l uh)/K^2
+// jobs: 0 urh, 1 vrh, 2 uh (ux = i k G), 3 i l uh, 4 vh (vx = i k G), 5 i l vh, 6 etah (eta_x = i k G), 7 i l etah
+struct LindborgLoaderA {
+    const double2* sol;
+    long long vs;
+    __device__ __forceinline__ double2 operator()(int job, int, int, double kw, double lw, long long off) const {
+        if (job < 2) {
+            const double2 u = sol[off], v = sol[vs + off];
+            const double K2 = kw * kw + lw * lw, inv = K2 > 0.0 ? 1.0 / K2 : 0.0;
+            const double rx = (kw * v.x - lw * u.x) * inv, ry = (kw * v.y - lw * u.y) * inv;
+            return job == 0 ? make_double2(-lw * rx, -lw * ry) : make_double2(kw * rx, kw * ry);
+        }
+        const int var = (job - 2) >> 1;
+        const double2 a = sol[var * vs + off];
+        return (job & 1) ? make_double2(-lw * a.y, lw * a.x) : a;
+    }
+};
+
+template <int N>
+struct LindborgXOp {
+    static constexpr int NBUF = 2;
+    const double2* G;  // [8][ny][kr_pad]
+    double2* H;        // [3][ny][kr_pad]
+    double sc;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G;
+        const long long ro = (long long)y * L.kr_pad;
+        double *ur = cx.re(0), *vr = cx.im(0);
+        double2 v[16];
+        double p1[16];
+        cx.template load_pair<MUL_ONE, MUL_ONE>(1, G + ro, G + L.vs + ro);
+        cx.ifft_regs_out(1, v);                          // ur + i vr
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            ur[x] = v[m].x;
+            vr[x] = v[m].y;
+        }
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 2 * L.vs + ro, G + 3 * L.vs + ro);
+        cx.ifft_regs_out(1, v);                          // ux + i uy
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            p1[m] = sc * (ur[x] * v[m].x + vr[x] * v[m].y);
+        }
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 4 * L.vs + ro, G + 5 * L.vs + ro);
+        cx.ifft_regs_out(1, v);                          // vx + i vy
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
+        }
+        cx.fft_regs_in(v, 1);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 6 * L.vs + ro, G + 7 * L.vs + ro);
+        cx.ifft_regs_out(1, v);                          // eta_x + i eta_y
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            v[m] = make_double2(sc * (ur[x] * v[m].x + vr[x] * v[m].y), 0.0);
+        }
+        cx.fft_regs_in(v, 1);
+        cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 2 * L.vs + ro, nullptr);
+    }
+};
+
+struct NegateCombiner {  // N_var = -P_var
+    __device__ __forceinline__ int nin(int) const { return 1; }
+    __device__ __forceinline__ int src(int var, int) const { return var; }
+    __device__ __forceinline__ double2 apply(int, int, double2 v, double, double) const { return make_double2(-v.x, -v.y); }
+};
+
+// ---------------------------------------------------------------- QG models (swqg/SWQG.jl:140-170, swqg/TwoLayerQG.jl:152-182)
+// psi inversion on the fly; per layer: q, psi (psi_x = i k G in the x-pass), i l psi
+__device__ __forceinline__ double2 qg_streamfunction(const double2* sol, long long vs, int nlayers, int layer, double K2, double P,
+                                                     long long off) {
+    if (nlayers == 1) {                                  // psih = -qh / (K^2 + Kd2)
+        const double2 q = sol[off];
+        const double inv = -1.0 / (K2 + P);
+        return make_double2(inv * q.x, inv * q.y);
+    }
+    const double2 q1 = sol[off], q2 = sol[vs + off];     // psi_j = -(K^2 q_j + F (q1 + q2)) / ((K^2 + 2F) K^2)
+    const double2 qj = layer == 0 ? q1 : q2;
+    const double inv = K2 > 0.0 ? -1.0 / ((K2 + 2.0 * P) * K2) : 0.0;
+    return make_double2(inv * (K2 * qj.x + P * (q1.x + q2.x)), inv * (K2 * qj.y + P * (q1.y + q2.y)));
+}
+
+struct QgLoaderA {  // jobs: layer*3 + {0 q, 1 psi, 2 i l psi}
+    const double2* sol;
+    long long vs;
+    int nlayers;
+    double P;  // Kd2 (SWQG) or F (two-layer)
+    __device__ __forceinline__ double2 operator()(int job, int, int, double kw, double lw, long long off) const {
+        const int layer = job / 3, which = job - 3 * layer;
+        if (which == 0) return sol[layer * vs + off];
+        const double2 psi = qg_streamfunction(sol, vs, nlayers, layer, kw * kw + lw * lw, P, off);
+        return which == 1 ? psi : make_double2(-lw * psi.y, lw * psi.x);
+    }
+};
+
+template <int N, int NL>
+struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 layer + 1]
+    static constexpr int NBUF = 2;
+    const double2* G;  // [3 NL][ny][kr_pad]
+    double2* H;        // [2 NL][ny][kr_pad]
+    double sc;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G;
+        const long long ro = (long long)y * L.kr_pad;
+        double *q1 = cx.re(0), *q2 = cx.im(0);
+        double2 v[16];
+        if (NL == 2) cx.template load_pair<MUL_ONE, MUL_ONE>(1, G + ro, G + 3 * L.vs + ro);
+        else cx.template load_pair<MUL_ONE, MUL_ZERO>(1, G + ro, nullptr);
+        cx.ifft_regs_out(1, v);                          // q1 + i q2
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            q1[x] = v[m].x;
+            q2[x] = v[m].y;
+        }
+#pragma unroll
+        for (int layer = 0; layer < NL; ++layer) {
+            const double* q = layer == 0 ? q1 : q2;
+            cx.template load_pair<MUL_IK, MUL_ONE>(1, G + (3 * layer + 1) * L.vs + ro, G + (3 * layer + 2) * L.vs + ro);
+            cx.ifft_regs_out(1, v);                      // psi_x + i psi_y
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const double qq = sc * q[pad_index(cx.g + m * Gt)];
+                v[m] = make_double2(qq * v[m].x, qq * v[m].y);
+            }
+            cx.fft_regs_in(v, 1);
+            cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + (2 * layer) * L.vs + ro, H + (2 * layer + 1) * L.vs + ro);
+        }
+    }
+};
+
+struct QgCombiner {  // N_layer = -i l F[psi_x q] + i k F[psi_y q]
+    __device__ __forceinline__ int nin(int) const { return 2; }
+    __device__ __forceinline__ int src(int var, int i) const { return 2 * var + i; }
+    __device__ __forceinline__ double2 apply(int, int i, double2 v, double kw, double lw) const {
+        return i == 0 ? make_double2(lw * v.y, -lw * v.x) : make_double2(-kw * v.y, kw * v.x);
+    }
+};
+
 // ---------------------------------------------------------------- plain spectral -> physical
 // one job: an expression of the state selected by `which` (see swrt.h SWRT_FIELD_*)
 struct FieldLoader {
     const double2* sol;
     long long vs;
-    int which;
-    double f;
+    int which, nlayers;
+    double f, P;
     __device__ __forceinline__ double2 operator()(int, int, int, double kw, double lw, long long off) const {
         if (which < 16) return sol[(long long)which * vs + off];
-        // 16: RSW linear PV  zeta = i k vh - i l uh - f etah   (rsw/RotatingShallowWater.jl:108)
-        const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
-        return make_double2(-(kw * v.y - lw * u.y) - f * e.x, (kw * v.x - lw * u.x) - f * e.y);
+        if (which == 16) {   // RSW linear PV  zeta = i k vh - i l uh - f etah   (rsw/RotatingShallowWater.jl:108)
+            const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
+            return make_double2(-(kw * v.y - lw * u.y) - f * e.x, (kw * v.x - lw * u.x) - f * e.y);
+        }
+        // QG diagnostics (swqg/SWQG.jl:109-125, swqg/TwoLayerQG.jl:113-129): 32+j psi_j, 40+j u_j = -i l psi, 48+j v_j = i k psi,
+        // 56+j zeta_j = -K^2 psi
+        const int kind = (which - 32) >> 3, layer = (which - 32) & 7;
+        const double K2 = kw * kw + lw * lw;
+        const double2 psi = qg_streamfunction(sol, vs, nlayers, layer, K2, P, off);
+        if (kind == 0) return psi;
+        if (kind == 1) return make_double2(lw * psi.y, -lw * psi.x);
+        if (kind == 2) return make_double2(-kw * psi.y, kw * psi.x);
+        return make_double2(-K2 * psi.x, -K2 * psi.y);
     }
 };
 
@@ -148,17 +308,27 @@ struct C2ROp {
 
 // ---------------------------------------------------------------- velocity snapshot for packets
 // psi kinds
-enum { PSI_RSW_BALANCED = 0 };
+enum { PSI_RSW_BALANCED = 0, PSI_SWQG = 1, PSI_TWOLAYER_BAROCLINIC = 2, PSI_TWOLAYER_MEAN = 3 };
 // jobs: 0 psih, 1 -i l psih (u), 2 l^2 psih (uy);   v = i k G0, ux = i k G1, vx = -k^2 G0
 struct PsiLoader {
     const double2* sol;
     long long vs;
     int kind;
-    double f, Kd2;
+    double f, P;   // P: Kd2 = f^2/Cg^2 (RSW balanced, SWQG) or F (two-layer)
+    __device__ __forceinline__ double2 psi_of(double kw, double lw, long long off) const {
+        const double K2 = kw * kw + lw * lw;
+        if (kind == PSI_RSW_BALANCED) {   // -(i k vh - i l uh - f etah)/(K^2 + f^2/Cg^2)   rsw/RSWRaytracingDriver.jl:63-67
+            const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
+            const double inv = -1.0 / (K2 + P);
+            return make_double2(inv * (-(kw * v.y - lw * u.y) - f * e.x), inv * ((kw * v.x - lw * u.x) - f * e.y));
+        }
+        if (kind == PSI_SWQG) return qg_streamfunction(sol, vs, 1, 0, K2, P, off);
+        const double2 a = qg_streamfunction(sol, vs, 2, 0, K2, P, off), b = qg_streamfunction(sol, vs, 2, 1, K2, P, off);
+        // baroclinic 0.5 (psi1 - psi2): swqg/TwoLayerRaytracingDriver.jl:232 ; mean (psi1 + psi2)/2: raytracing/TwoLayerRaytracing.jl:122
+        return kind == PSI_TWOLAYER_BAROCLINIC ? make_double2(0.5 * (a.x - b.x), 0.5 * (a.y - b.y)) : make_double2((a.x + b.x) / 2, (a.y + b.y) / 2);
+    }
     __device__ __forceinline__ double2 operator()(int job, int, int, double kw, double lw, long long off) const {
-        const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];
-        const double inv = -1.0 / (kw * kw + lw * lw + Kd2);
-        const double2 psi = make_double2(inv * (-(kw * v.y - lw * u.y) - f * e.x), inv * ((kw * v.x - lw * u.x) - f * e.y));
+        const double2 psi = psi_of(kw, lw, off);
         if (job == 0) return psi;
         if (job == 1) return make_double2(lw * psi.y, -lw * psi.x);
         return make_double2(lw * lw * psi.x, lw * lw * psi.y);
@@ -258,10 +428,10 @@ struct Launch {
         return cudaGetLastError();
     }
 
-    // concrete entry points (explicitly instantiated per size in inst.cu)
-    static cudaError_t rsw_stage_a(const RswLoaderA& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
-    static cudaError_t rsw_stage_b(int modified, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st);
-    static cudaError_t rsw_stage_c(const RswCombiner& cb, const SpecLayout& L, const double2* H, double2* Nout, const double2* tw, cudaStream_t st);
+    // concrete entry points (explicitly specialised per size in inst.cu); `model` = SWRT_* model id
+    static cudaError_t stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t stage_c(int model, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);

@@ -2,7 +2,7 @@
 // Reference: utils/IFMAB3.jl:129-169 (IFMAB3update! + filter + history), closed-form exp(L dt)
 // per SURVEY App. A.4.  Included by api.cu only (non-template kernels live in one TU).
 #pragma once
-#include "passes.cuh"
+#include "models.cuh"
 
 namespace swrt {
 
@@ -81,6 +81,140 @@ __global__ void __launch_bounds__(256) ifmab3_update_rsw_kernel(UpdateArgs a, Rs
 #pragma unroll
         for (int v = 0; v < 3; ++v) a.sol[v * L.vs + off] = make_double2(cf.w * y[v].x, cf.w * y[v].y);
     }
+}
+
+
+// ---------------------------------------------------------------- IFMAB3 with tabulated exp(L dt), exp(2 L dt)
+// General NV x NV complex blocks (two-layer QG: swqg/TwoLayerQG.jl:184-198 has no skew structure to exploit).
+// Tables are SoA: E[(a NV + b)][l][kr_pad]; y_a = sum_b E[a,b] x_b (utils/IFMAB3.jl:90-100, orientation K2).
+template <int NV>
+__global__ void __launch_bounds__(256) ifmab3_update_table_kernel(UpdateArgs a, const double2* __restrict__ E,
+                                                                  const double2* __restrict__ E2, SpecLayout L) {
+    const int nlk = L.ny - (L.lz1 - L.lz0);
+    const long long total = (long long)nlk * L.kr_keep;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
+        const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
+        const long long off = (long long)l * L.kr_pad + kr;
+        double2 e[NV][NV], x[NV], n[NV];
+#pragma unroll
+        for (int p = 0; p < NV; ++p)
+#pragma unroll
+            for (int q = 0; q < NV; ++q) e[p][q] = E[(p * NV + q) * L.vs + off];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            x[v] = a.sol[v * L.vs + off];
+            n[v] = a.N[v * L.vs + off];
+        }
+        if (a.euler) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) x[v] = make_double2(x[v].x + a.dt * n[v].x, x[v].y + a.dt * n[v].y);
+        } else {
+            const double h1 = 23.0 / 12.0, h2 = 16.0 / 12.0, h3 = 5.0 / 12.0;
+            double2 n1[NV], n2[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                n1[v] = a.Nm1[v * L.vs + off];
+                n2[v] = a.Nm2[v * L.vs + off];
+            }
+#pragma unroll
+            for (int p = 0; p < NV; ++p) {
+                double2 A = make_double2(0.0, 0.0), B = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const double2 e2 = E2[(p * NV + q) * L.vs + off];
+                    A = cadd(A, cmul(e[p][q], n1[q]));
+                    B = cadd(B, cmul(e2, n2[q]));
+                }
+                x[p].x += a.dt * (h1 * n[p].x - h2 * A.x + h3 * B.x);
+                x[p].y += a.dt * (h1 * n[p].y - h2 * A.y + h3 * B.y);
+            }
+        }
+        const double filt = a.coef[off].w;
+#pragma unroll
+        for (int p = 0; p < NV; ++p) {
+            double2 y = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) y = cadd(y, cmul(e[p][q], x[q]));
+            a.sol[p * L.vs + off] = make_double2(filt * y.x, filt * y.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- diagonal (real) L: IFMAB3(diagonal=true) and FilteredAB3
+// coef = { e^{D dt}, D, -, filter }.  utils/IFMAB3.jl:72-74,102-108 ; FourierFlows FilteredAB3:
+// RHS = N + L .* sol kept in the history ring (written back into `Nrw`), sol += dt (23/12 RHS - 16/12 RHS1 + 5/12 RHS2), filter.
+template <int NV, bool FILTERED_AB3>
+__global__ void __launch_bounds__(256) update_diag_kernel(UpdateArgs a, double2* __restrict__ Nrw, SpecLayout L) {
+    const int nlk = L.ny - (L.lz1 - L.lz0);
+    const long long total = (long long)nlk * L.kr_keep;
+    const double h1 = 23.0 / 12.0, h2 = 16.0 / 12.0, h3 = 5.0 / 12.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
+        const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
+        const long long off = (long long)l * L.kr_pad + kr;
+        const double4 cf = a.coef[off];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const long long o = v * L.vs + off;
+            double2 x = a.sol[o], n = Nrw[o];
+            if (FILTERED_AB3) {
+                n = make_double2(n.x + cf.y * x.x, n.y + cf.y * x.y);
+                Nrw[o] = n;
+                if (a.euler) x = make_double2(x.x + a.dt * n.x, x.y + a.dt * n.y);
+                else {
+                    const double2 n1 = a.Nm1[o], n2 = a.Nm2[o];
+                    x.x += a.dt * (h1 * n.x - h2 * n1.x + h3 * n2.x);
+                    x.y += a.dt * (h1 * n.y - h2 * n1.y + h3 * n2.y);
+                }
+                a.sol[o] = make_double2(cf.w * x.x, cf.w * x.y);
+            } else {
+                if (a.euler) x = make_double2(x.x + a.dt * n.x, x.y + a.dt * n.y);
+                else {
+                    const double2 n1 = a.Nm1[o], n2 = a.Nm2[o];
+                    const double e1 = cf.x, e2 = cf.x * cf.x;
+                    x.x += a.dt * (h1 * n.x - h2 * e1 * n1.x + h3 * e2 * n2.x);
+                    x.y += a.dt * (h1 * n.y - h2 * e1 * n1.y + h3 * e2 * n2.y);
+                }
+                a.sol[o] = make_double2(cf.w * cf.x * x.x, cf.w * cf.x * x.y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- spectral diagnostics (parseval-weighted sums)
+// value(kr,l) per `which`, summed with weights 1 (kr = 0, Nyquist) / 2 (parsevalsum / parsevalsum2 of FourierFlows)
+enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3 };
+__global__ void __launch_bounds__(256) spectral_diag_kernel(const double2* __restrict__ sol, SpecLayout L, int which, int arg, int nlayers,
+                                                            double P, double* __restrict__ partial) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    const long long total = (long long)L.ny * L.kr_keep;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(i / L.kr_keep), kr = (int)(i - (long long)l * L.kr_keep);
+        if (!l_retained(L, l)) continue;
+        const long long off = (long long)l * L.kr_pad + kr;
+        const double kw = kr * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
+        double val;
+        if (which == DIAG_ABS2_VAR) {
+            const double2 v = sol[arg * L.vs + off];
+            val = v.x * v.x + v.y * v.y;
+        } else if (which == DIAG_QG_DPSI2) {
+            const double2 a = qg_streamfunction(sol, L.vs, 2, 0, K2, P, off), b = qg_streamfunction(sol, L.vs, 2, 1, K2, P, off);
+            val = (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y);
+        } else {
+            const double2 p = qg_streamfunction(sol, L.vs, nlayers, arg, K2, P, off);
+            val = (which == DIAG_QG_K2PSI2 ? K2 : 1.0) * (p.x * p.x + p.y * p.y);
+        }
+        acc += ((kr == 0 || kr == L.nx / 2) ? 1.0 : 2.0) * val;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
 }  // namespace swrt

@@ -19,6 +19,8 @@ MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowW
           "TwoLayerQG": 5, "ThomasYamada": 6}
 STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3}
 FIELD_U, FIELD_V, FIELD_ETA, FIELD_ZETA = 0, 1, 2, 16
+FIELD_QG_PSI, FIELD_QG_U, FIELD_QG_V, FIELD_QG_ZETA = 32, 40, 48, 56
+NVAR = {0: 3, 1: 3, 2: 3, 4: 1, 5: 2}
 
 
 class Grid:
@@ -59,7 +61,9 @@ class Clock:
 
 
 class Vars:
-    """`prob.vars`: physical fields computed on demand from the device state (u, v, η, ζ)."""
+    """`prob.vars`: physical fields computed on demand from the device state.
+    RSW family: u, v, η, ζ (rsw/RotatingShallowWater.jl:101-116); QG models: q, ψ, ζ, u, v
+    (swqg/SWQG.jl:109-125; swqg/TwoLayerQG.jl:113-129 with a trailing layer axis)."""
 
     def __init__(self, prob):
         self._p = prob
@@ -69,12 +73,20 @@ class Vars:
         check(lib().swrt_flow_get_field(self._p._h, which, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    u = property(lambda s: s._field(FIELD_U))
-    v = property(lambda s: s._field(FIELD_V))
-    η = property(lambda s: s._field(FIELD_ETA))
-    eta = η
-    ζ = property(lambda s: s._field(FIELD_ZETA))
-    zeta = ζ
+    def _qg(self, base):
+        n = self._p.nvar
+        if n == 1:
+            return self._field(base)
+        return np.stack([self._field(base + j) for j in range(n)], axis=-1)
+
+    def __getattr__(self, name):
+        qg = self._p.desc.model in (4, 5)
+        table = ({"q": 0, "ψ": FIELD_QG_PSI, "psi": FIELD_QG_PSI, "u": FIELD_QG_U, "v": FIELD_QG_V, "ζ": FIELD_QG_ZETA,
+                  "zeta": FIELD_QG_ZETA} if qg else
+                 {"u": FIELD_U, "v": FIELD_V, "η": FIELD_ETA, "eta": FIELD_ETA, "ζ": FIELD_ZETA, "zeta": FIELD_ZETA})
+        if name not in table:
+            raise AttributeError(name)
+        return self._qg(table[name]) if qg else self._field(table[name])
 
 
 class Problem:
@@ -83,19 +95,26 @@ class Problem:
 
     def __init__(self, dev=0, *, model="RotatingShallowWater", nx=128, ny=None, Lx=2 * np.pi, Ly=None, ν=1.0e-16,
                  nν=4, f=1.0, Cg=1.0, stepper="IFMAB3", dt=5e-2, aliased_fraction=1 / 3, T=np.float64,
-                 use_filter=False, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15, nu=None, nnu=None):
+                 use_filter=False, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15, nu=None, nnu=None,
+                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None):
+        """Two-layer QG (swqg/TwoLayerQG.jl:55-72) takes U, μ, f0, Cg, δρρ0 (F = 2 f0²/Cg²/δρρ0); SWQG takes f, Cg (Kd2 = f²/Cg²)."""
         if T not in (np.float64, float, "Float64"):
             raise _lib.SwrtError("only T=Float64 is implemented (the north star's arithmetic)")
         ny = nx if ny is None else ny
         Ly = Lx if Ly is None else Ly
         ν = ν if nu is None else nu
         nν = nν if nnu is None else nnu
+        μ = μ if mu is None else mu
+        f0 = f if f0 is None else f0
+        F = 2 * f0 ** 2 / Cg ** 2 / δρρ0
         d = FlowDesc(model=MODELS[model], stepper=STEPPERS[stepper], nx=nx, ny=ny, nnu=nν, use_filter=int(use_filter),
                      filter_order=order, device=int(dev), Lx=Lx, Ly=Ly, dt=dt, nu=ν, f=f, Cg=Cg,
-                     aliased_fraction=aliased_fraction, filter_innerK=innerK, filter_outerK=outerK, filter_tol=tol)
+                     aliased_fraction=aliased_fraction, filter_innerK=innerK, filter_outerK=outerK, filter_tol=tol,
+                     U=U, mu=μ, F=F)
         self._h = C.c_void_p()
         check(lib().swrt_flow_create(C.byref(d), C.byref(self._h)))
-        self.desc, self.dt, self.nvar = d, dt, 3
+        self.desc, self.dt, self.nvar = d, dt, NVAR[d.model]
+        self.F = F
         self.grid = Grid(nx, ny, Lx, Ly, aliased_fraction)
         self.clock = Clock(self)
         self.vars = Vars(self)
@@ -113,11 +132,14 @@ class Problem:
     def sol(self):
         out = np.empty((self.grid.nkr, self.grid.nl, self.nvar), dtype=np.complex128, order="F")
         check(lib().swrt_flow_get_solution(self._h, out.ctypes.data_as(C.c_void_p)))
-        return out
+        return out[:, :, 0] if self.desc.model == 4 else out        # SWQG's sol is (nkr, nl)
 
     @sol.setter
     def sol(self, value):
-        a = np.asfortranarray(value, dtype=np.complex128)
+        a = np.asarray(value, dtype=np.complex128)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        a = np.asfortranarray(a)
         if a.shape != (self.grid.nkr, self.grid.nl, self.nvar):
             raise ValueError(f"sol must have shape {(self.grid.nkr, self.grid.nl, self.nvar)}")
         check(lib().swrt_flow_set_solution(self._h, a.ctypes.data_as(C.c_void_p)))
@@ -182,6 +204,14 @@ def stepforward(prob, diags=(), nsteps=1):
 
 
 def kinetic_energy(prob):
+    """kinetic_energy(prob); the two-layer model returns (KE_1, KE_2) like swqg/TwoLayerQG.jl:221-233."""
+    if prob.desc.model == 5:
+        out = []
+        for layer in range(2):
+            v = C.c_double()
+            check(lib().swrt_flow_layer_kinetic_energy(prob._h, layer, C.byref(v)))
+            out.append(v.value)
+        return tuple(out)
     ke, pe = C.c_double(), C.c_double()
     check(lib().swrt_flow_energies(prob._h, C.byref(ke), C.byref(pe)))
     return ke.value

@@ -13,7 +13,7 @@ import numpy as np
 
 from ._lib import PacketsDesc, check, lib
 
-PSI_RSW_BALANCED = 0
+PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2, 3
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
 
 

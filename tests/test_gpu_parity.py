@@ -40,7 +40,8 @@ def test_set_solution_dealiases_and_ignores_nonhermitian_dc_column():
     assert rel_l2(prob.vars.u, g.irfft2(want[:, :, 0])) < 2e-14    # c2r semantics: Re of the kr=0 column after the l-transform
 
 
-@pytest.mark.parametrize("model,variant", [("RotatingShallowWater", orsw.RSW), ("ModifiedShallowWater", orsw.MODIFIED)])
+@pytest.mark.parametrize("model,variant", [("RotatingShallowWater", orsw.RSW), ("ModifiedShallowWater", orsw.MODIFIED),
+                                           ("LinborgShallowWater", orsw.LINDBORG)])
 @pytest.mark.parametrize("nx", [64, 128])
 def test_rsw_100_steps_parity(model, variant, nx):
     g, p, sol0, c = config2_setup(nx)
@@ -234,3 +235,67 @@ def test_full_size_properties_2048():
     assert abs(e1 / e0 - 1) < 1e-3 and not flow.has_nan(prob)
     sol = prob.sol
     assert np.all(sol[g.kr_alias[0]:] == 0) and np.all(sol[:, g.l_alias[0]:g.l_alias[1]] == 0)   # stays dealiased
+
+
+# ------------------------------------------------------------------------------------------------ QG models
+def _qg_state(nx, nlayers, seed):
+    g, sol3 = random_state(nx, seed=seed, amp=1.0, slope=1.0)
+    return g, np.ascontiguousarray(sol3[:, :, :nlayers])
+
+
+@pytest.mark.parametrize("stepper", ["IFMAB3", "FilteredAB3"])
+def test_swqg_parity(stepper):
+    from oracle import ifmab3 as oif, qg as oqg
+    nx, f, Cg, nnu, dt = 128, 3.0, 1.0, 4, 2e-3
+    nu = 2 * np.pi / nx / ((nx / 2 - 1) ** (2 * nnu)) / dt
+    g, sol0 = _qg_state(nx, 1, 5)
+    sol0 = sol0[:, :, 0]
+    Kd2 = f * f / (Cg * Cg)
+    prob = swrt.Problem(model="SWQG", stepper=stepper, nx=nx, dt=dt, f=f, Cg=Cg, nu=nu, nnu=nnu)
+    prob.sol = sol0
+    np.testing.assert_array_equal(prob.sol, sol0)
+    psi = g.irfft2(oqg.swqg_streamfunction(sol0, g, Kd2))
+    assert rel_l2(prob.vars.ψ, psi) < 1e-13
+    assert rel_l2(prob.vars.u, g.irfft2(-1j * g.l * oqg.swqg_streamfunction(sol0, g, Kd2))) < 1e-13
+    ke, pe = oqg.swqg_energies(sol0, g, Kd2)
+    assert abs(flow.kinetic_energy(prob) / ke - 1) < 1e-13 and abs(flow.potential_energy(prob) / pe - 1) < 1e-13
+    L = oqg.swqg_L(g, nu, nnu)
+    calcN = lambda s: oqg.swqg_calcN(s, g, Kd2)
+    ts = oif.IFMAB3(L, dt, calcN) if stepper == "IFMAB3" else oqg.FilteredAB3(L, dt, calcN, makefilter(g))
+    want = sol0.copy()
+    for n in (1, 3, 46):
+        flow.stepforward(prob, (), n)
+        for _ in range(n):
+            ts.stepforward(want)
+        assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10, n
+    vel, grad = raytracing.get_velocity_info(prob, 0, raytracing.PSI_SWQG)
+    ref = oray.get_velocity_info(oqg.swqg_streamfunction(g.dealias(want.copy()), g, Kd2), g)
+    assert rel_l2(vel._arr(), ref) < 1e-12
+
+
+def test_twolayerqg_parity():
+    from oracle import ifmab3 as oif, qg as oqg
+    nx, U, mu, f0, Cg, drr, nnu, dt = 128, 0.5, 1e-2, 3.0, 1.0, 0.2, 4, 1e-3
+    nu = 40 * 2 * np.pi / nx / ((nx / 2 - 1) ** (2 * nnu)) / dt
+    F = 2 * f0 ** 2 / Cg ** 2 / drr
+    g, sol0 = _qg_state(nx, 2, 9)
+    prob = swrt.Problem(model="TwoLayerQG", nx=nx, dt=dt, U=U, mu=mu, f0=f0, Cg=Cg, δρρ0=drr, nu=nu, nnu=nnu)
+    prob.sol = sol0
+    psih = oqg.twolayer_streamfunction(sol0, g, F)
+    assert rel_l2(prob.vars.ψ, np.stack([g.irfft2(psih[:, :, j]) for j in range(2)], axis=-1)) < 1e-13
+    (ke1, ke2), pe = oqg.twolayer_energies(sol0, g, F)
+    k1, k2 = flow.kinetic_energy(prob)
+    assert abs(k1 / ke1 - 1) < 1e-12 and abs(k2 / ke2 - 1) < 1e-12 and abs(flow.potential_energy(prob) / pe - 1) < 1e-12
+    L = oqg.twolayer_L(g, F, U, mu, nu, nnu)
+    ts = oif.IFMAB3(L, dt, lambda s: oqg.twolayer_calcN(s, g, F))      # general matrix exponential, like the reference
+    want = sol0.copy()
+    for n in (1, 3, 46):
+        flow.stepforward(prob, (), n)
+        for _ in range(n):
+            ts.stepforward(want)
+        assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10, n
+    for kind, comb in ((raytracing.PSI_TWOLAYER_BAROCLINIC, lambda p: 0.5 * (p[:, :, 0] - p[:, :, 1])),
+                       (raytracing.PSI_TWOLAYER_MEAN, lambda p: (p[:, :, 0] + p[:, :, 1]) / 2)):
+        vel, _ = raytracing.get_velocity_info(prob, 1, kind)
+        ref = oray.get_velocity_info(comb(oqg.twolayer_streamfunction(g.dealias(want.copy()), g, F)), g)
+        assert rel_l2(vel._arr(), ref) < 1e-12

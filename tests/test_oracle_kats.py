@@ -226,3 +226,22 @@ def test_ifmab3_third_order_and_energy_conservation():
     E0 = rsw.kinetic_energy(sol0, g) + rsw.potential_energy(sol0, g, p)
     E1 = rsw.kinetic_energy(ref, g) + rsw.potential_energy(ref, g, p)
     assert abs(E1 - E0) / E0 < 5e-3   # quadratic (linearised) energy is only approximately conserved
+
+
+def test_qg_operators_closed_forms():
+    from oracle import qg
+    g = TwoDGrid(32)
+    L = qg.twolayer_L(g, F=2 * 9.0 / 0.2, U=0.5, mu=1e-2, nu=1e-10, nnu=4)
+    E = qg.expm2x2_closed_form(L, 3e-3)
+    np.testing.assert_allclose(E, scipy.linalg.expm(L * 3e-3), rtol=0, atol=1e-13)
+    # pv <-> streamfunction inversion round trip (swqg/TwoLayerQG.jl:92-111)
+    rng = np.random.default_rng(3)
+    psih = rng.standard_normal((g.nkr, g.nl, 2)) + 1j * rng.standard_normal((g.nkr, g.nl, 2))
+    psih[0, 0] = 0
+    F = 90.0
+    qh = np.stack([-g.Krsq * psih[:, :, 0] + F * (psih[:, :, 1] - psih[:, :, 0]),
+                   -g.Krsq * psih[:, :, 1] + F * (psih[:, :, 0] - psih[:, :, 1])], axis=-1)
+    np.testing.assert_allclose(qg.twolayer_streamfunction(qh, g, F), psih, rtol=0, atol=1e-12)
+    # the Jacobian conserves the mean of q: N[0, 0] == 0
+    sol = g.dealias(g.rfft2(rng.standard_normal((32, 32))))
+    assert abs(qg.swqg_calcN(sol.copy(), g, 9.0)[0, 0]) < 1e-9
