@@ -65,6 +65,8 @@ struct swrt_flow {
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
+    double4* coef2 = nullptr;                   // ETDRK4 coefficients {zeta, alpha, beta, Gamma}
+    double2 *S1 = nullptr, *S2 = nullptr, *N4 = nullptr;   // stage states and 4th N buffer of the multi-stage steppers
     double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
     double* snap = nullptr;      // S[ny][nx][2][5]: both snapshot halves interleaved (snapshot_layout.cuh)
     int slot_map[2] = {0, 1};    // slot (0 = old, 1 = new) -> half
@@ -253,7 +255,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
-    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab);
+    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     cudaFree(h->snap); cudaFree(h->phys); cudaFree(h->red);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
@@ -270,9 +272,11 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     const swrt_flow_desc& d = *desc;
     if (!supported_n(d.nx) || !supported_n(d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "nx, ny must be powers of two in [32, 4096] (got %d x %d)", d.nx, d.ny);
     const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG;
-    if (!rsw_family && d.model != SWRT_SWQG && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
-    if (d.stepper != SWRT_IFMAB3 && !(d.stepper == SWRT_FILTEREDAB3 && d.model == SWRT_SWQG))
-        return fail(SWRT_ERR_UNSUPPORTED, "stepper %d not implemented for model %d (FilteredAB3 needs a diagonal L)", d.stepper, d.model);
+    const bool diag_L = d.model == SWRT_SWQG || d.model == SWRT_THOMASYAMADA;
+    if (!rsw_family && !diag_L && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
+    if (d.stepper < SWRT_IFMAB3 || d.stepper > SWRT_FILTEREDRK4) return fail(SWRT_ERR_ARG, "unknown stepper %d", d.stepper);
+    if (d.stepper != SWRT_IFMAB3 && !diag_L)
+        return fail(SWRT_ERR_UNSUPPORTED, "stepper %d needs a diagonal L (FourierFlows applies L .* sol); model %d has matrix blocks", d.stepper, d.model);
     if (!(d.Lx > 0 && d.Ly > 0 && d.dt > 0)) return fail(SWRT_ERR_ARG, "Lx, Ly, dt must be positive");
     if (!(d.aliased_fraction >= 0 && d.aliased_fraction < 1)) return fail(SWRT_ERR_ARG, "aliased_fraction must be in [0,1)");
     int ndev = 0;
@@ -295,9 +299,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     L.kr_pad = (L.kr_keep + 15) / 16 * 16;
     L.vs = (long long)L.ny * L.kr_pad;
     L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
-    L.f = d.f; L.Cg2 = d.Cg * d.Cg; L.aux1 = 0;
+    L.f = d.f; L.Cg2 = d.Cg * d.Cg;
     // model constant used by the loaders: Kd2 = f^2/Cg^2 (SWQG, swqg/SWQG.jl:85; RSW balanced psi) or F (two-layer, swqg/TwoLayerQG.jl:79)
     L.aux0 = d.model == SWRT_TWOLAYERQG ? d.F : (d.Kd2 > 0 ? d.Kd2 : d.f * d.f / L.Cg2);
+    L.aux1 = d.Ro;   // Thomas-Yamada Rossby number
 
     auto bail = [&](int code) { swrt_flow_destroy(h); return code; };
 #define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
@@ -308,6 +313,11 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->sol, fb * h->nvar));
     CKB(cudaMemset(h->sol, 0, fb * h->nvar));
     for (int i = 0; i < 3; ++i) { CKB(cudaMalloc(&h->Nb[i], fb * h->nvar)); CKB(cudaMemset(h->Nb[i], 0, fb * h->nvar)); }
+    if (d.stepper == SWRT_ETDRK4 || d.stepper == SWRT_FILTEREDRK4) {
+        CKB(cudaMalloc(&h->S1, fb * h->nvar)); CKB(cudaMemset(h->S1, 0, fb * h->nvar));
+        CKB(cudaMalloc(&h->S2, fb * h->nvar)); CKB(cudaMemset(h->S2, 0, fb * h->nvar));
+        CKB(cudaMalloc(&h->N4, fb * h->nvar)); CKB(cudaMemset(h->N4, 0, fb * h->nvar));
+    }
     CKB(cudaMalloc(&h->G, fb * h->njobs_a)); CKB(cudaMemset(h->G, 0, fb * h->njobs_a));
     CKB(cudaMalloc(&h->H, fb * h->njobs_b)); CKB(cudaMemset(h->H, 0, fb * h->njobs_b));
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
@@ -322,6 +332,8 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     {
         std::vector<double4> cf((size_t)L.vs, make_double4(1.0, 0.0, 0.0, 1.0));
         std::vector<double2> E, E2;
+        std::vector<double4> cf2;
+        if (d.stepper == SWRT_ETDRK4) cf2.assign((size_t)L.vs, make_double4(0, 0, 0, 0));
         if (d.model == SWRT_TWOLAYERQG) { E.assign((size_t)4 * L.vs, make_double2(0, 0)); E2 = E; }
         const double w2c = d.model == SWRT_RSW_MODIFIED ? 0.0 : L.Cg2;
         const double innerK = d.filter_innerK > 0 ? d.filter_innerK : 2.0 / 3.0, outerK = d.filter_outerK > 0 ? d.filter_outerK : 1.0;
@@ -342,7 +354,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
                 const double D = -d.nu * std::pow(K2, (double)d.nnu);
                 const size_t off = (size_t)l * L.kr_pad + kr;
                 double filt = 1.0;
-                if (d.use_filter || d.stepper == SWRT_FILTEREDAB3) {
+                if (d.use_filter || d.stepper == SWRT_FILTEREDAB3 || d.stepper == SWRT_FILTEREDRK4) {
                     const double Kn = std::sqrt((kw * dx / M_PI) * (kw * dx / M_PI) + (lw * dy / M_PI) * (lw * dy / M_PI));
                     if (Kn >= innerK) filt = std::exp(-decay * std::pow(Kn - innerK, order));
                 }
@@ -352,8 +364,20 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
                     if (w > 0) { s = std::sin(th) / w; const double sh = std::sin(0.5 * th); c = 2.0 * sh * sh / w2; }
                     else { s = d.dt; c = 0.5 * d.dt * d.dt; }
                     cf[off] = make_double4(std::exp(D * d.dt), s, c, filt);
-                } else if (d.model == SWRT_SWQG) {
-                    cf[off] = make_double4(std::exp(D * d.dt), D, 0.0, filt);
+                } else if (diag_L) {
+                    cf[off] = make_double4(std::exp(D * d.dt), D, std::exp(0.5 * D * d.dt), filt);
+                    if (d.stepper == SWRT_ETDRK4) {   // FourierFlows getetdcoeffs: 32-point contour mean around dt L
+                        cplx z(0), a(0), b(0), g(0);
+                        for (int j = 0; j < 32; ++j) {
+                            const cplx zc = D * d.dt + std::exp(cplx(0.0, 2.0 * M_PI / 32 * (j + 0.5)));
+                            const cplx ez = std::exp(zc), z3 = zc * zc * zc;
+                            z += (std::exp(0.5 * zc) - 1.0) / zc;
+                            a += (-4.0 - zc + ez * (4.0 - 3.0 * zc + zc * zc)) / z3;
+                            b += (2.0 + zc + ez * (-2.0 + zc)) / z3;
+                            g += (-4.0 - 3.0 * zc - zc * zc + ez * (4.0 - zc)) / z3;
+                        }
+                        cf2[off] = make_double4(d.dt * z.real() / 32, d.dt * a.real() / 32, d.dt * b.real() / 32, d.dt * g.real() / 32);
+                    }
                 } else {   // two-layer QG, swqg/TwoLayerQG.jl:184-198 (evaluated in double; the reference's Float32 temporaries are a bug)
                     const double F = d.F, U = d.U, K2inv = K2 > 0 ? 1.0 / K2 : 0.0;
                     const cplx p0(0.0, -2.0 * kw * F * U), p1 = cplx(0.0, 2.0 * kw * F * U) + d.mu * K2;
@@ -371,6 +395,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
         }
         CKB(cudaMalloc(&h->coef, sizeof(double4) * cf.size()));
         CKB(cudaMemcpy(h->coef, cf.data(), sizeof(double4) * cf.size(), cudaMemcpyHostToDevice));
+        if (!cf2.empty()) {
+            CKB(cudaMalloc(&h->coef2, sizeof(double4) * cf2.size()));
+            CKB(cudaMemcpy(h->coef2, cf2.data(), sizeof(double4) * cf2.size(), cudaMemcpyHostToDevice));
+        }
         if (!E.empty()) {
             CKB(cudaMalloc(&h->Etab, sizeof(double2) * E.size()));
             CKB(cudaMemcpy(h->Etab, E.data(), sizeof(double2) * E.size(), cudaMemcpyHostToDevice));
@@ -412,41 +440,83 @@ int swrt_flow_enforce_reality(swrt_flow* h) {
     return SWRT_OK;
 }
 
+// N = calcN!(state): the three transform passes of the model
+static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
+    const SpecLayout& L = h->L;
+    const int model = h->d.model;
+    cudaError_t e;
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, state, h->G, L, h->tw_y, h->st)); }
+    CK(e);
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->st)); }
+    CK(e);
+    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, state, h->H, Nout, L, h->tw_y, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
+
 int swrt_flow_step(swrt_flow* h, int nsteps) {
     if (!h || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    const int model = h->d.model;
+    const int model = h->d.model, stepper = h->d.stepper;
     const bool modified = model == SWRT_RSW_MODIFIED;
     RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
     const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
     const int ublocks = (int)((nmodes + 255) / 256);
+    const double dt = h->d.dt;
+    auto stage = [&](int mode, double2* out, const double2* x, double2* n1, const double2* n2, const double2* n3, const double2* n4,
+                     const double2* xs, double c) {
+        StageArgs sa{out, x, n1, n2, n3, n4, xs, h->coef, h->coef2, c, mode, h->nvar};
+        ProfScope ps(h, K_UPDATE);
+        diag_stage_kernel<<<ublocks, 256, 0, h->st>>>(sa, L);
+        return cudaGetLastError();
+    };
     for (int s = 0; s < nsteps; ++s) {
-        double2* Ncur = h->Nb[h->ring];
-        const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
-        const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
-        cudaError_t e;
-        { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, h->sol, h->G, L, h->tw_y, h->st)); }
-        CK(e);
-        { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->st)); }
-        CK(e);
-        { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, h->H, Ncur, L, h->tw_y, h->st)); }
-        CK(e);
-        UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, h->d.dt, h->step < 3 ? 1 : 0};
-        {
-            ProfScope ps(h, K_UPDATE);
-            if (model == SWRT_SWQG) {
-                if (h->d.stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-                else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-            } else if (model == SWRT_TWOLAYERQG) {
-                ifmab3_update_table_kernel<2><<<ublocks, 256, 0, h->st>>>(ua, h->Etab, h->E2tab, L);
-            } else {
-                ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+        int rc;
+        if (stepper == SWRT_ETDRK4) {            // FourierFlows ETDRK4 stepforward!
+            double2 *N1 = h->Nb[0], *N2 = h->Nb[1], *N3 = h->Nb[2], *N4 = h->N4;
+            if ((rc = compute_N(h, h->sol, N1))) return rc;
+            CK(stage(ST_ETD_SUB12, h->S1, h->sol, N1, nullptr, nullptr, nullptr, nullptr, 0));
+            if ((rc = compute_N(h, h->S1, N2))) return rc;
+            CK(stage(ST_ETD_SUB12, h->S2, h->sol, N2, nullptr, nullptr, nullptr, nullptr, 0));
+            if ((rc = compute_N(h, h->S2, N3))) return rc;
+            CK(stage(ST_ETD_SUB3, h->S2, h->S1, N1, nullptr, N3, nullptr, nullptr, 0));
+            if ((rc = compute_N(h, h->S2, N4))) return rc;
+            CK(stage(ST_ETD_UPDATE, h->sol, h->sol, N1, N2, N3, N4, nullptr, 0));
+        } else if (stepper == SWRT_FILTEREDRK4) {   // FourierFlows (Filtered)RK4: RHS = N + L .* state
+            double2 *R1 = h->Nb[0], *R2 = h->Nb[1], *R3 = h->Nb[2], *R4 = h->N4;
+            if ((rc = compute_N(h, h->sol, R1))) return rc;
+            CK(stage(ST_RK4_STAGE, h->S1, h->sol, R1, nullptr, nullptr, nullptr, h->sol, 0.5 * dt));
+            if ((rc = compute_N(h, h->S1, R2))) return rc;
+            CK(stage(ST_RK4_STAGE, h->S2, h->sol, R2, nullptr, nullptr, nullptr, h->S1, 0.5 * dt));
+            if ((rc = compute_N(h, h->S2, R3))) return rc;
+            CK(stage(ST_RK4_STAGE, h->S1, h->sol, R3, nullptr, nullptr, nullptr, h->S2, dt));
+            if ((rc = compute_N(h, h->S1, R4))) return rc;
+            CK(stage(ST_RK4_FINAL, h->sol, h->sol, R1, R2, R3, R4, h->S1, dt));
+        } else {
+            double2* Ncur = h->Nb[h->ring];
+            const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
+            const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
+            if ((rc = compute_N(h, h->sol, Ncur))) return rc;
+            UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, dt, h->step < 3 ? 1 : 0};
+            {
+                ProfScope ps(h, K_UPDATE);
+                if (model == SWRT_SWQG) {
+                    if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+                    else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+                } else if (model == SWRT_THOMASYAMADA) {
+                    if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<4, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+                    else update_diag_kernel<4, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+                } else if (model == SWRT_TWOLAYERQG) {
+                    ifmab3_update_table_kernel<2><<<ublocks, 256, 0, h->st>>>(ua, h->Etab, h->E2tab, L);
+                } else {
+                    ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+                }
             }
+            CK(cudaGetLastError());
+            h->ring = (h->ring + 1) % 3;
         }
-        CK(cudaGetLastError());
-        h->ring = (h->ring + 1) % 3;
-        h->t += h->d.dt;
+        h->t += dt;
         h->step += 1;
     }
     return SWRT_OK;
@@ -506,6 +576,10 @@ int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
         k = spectral_diag(h, DIAG_QG_K2PSI2, 0, &e) / A; CK(e);
         k += spectral_diag(h, DIAG_QG_K2PSI2, 1, &e) / A; CK(e);
         p = L.aux0 * spectral_diag(h, DIAG_QG_DPSI2, 0, &e) / (2 * A); CK(e);
+    } else if (h->d.model == SWRT_THOMASYAMADA) {  // thomasyamada/ThomasYamada.jl:333-338 baroclinic_energy(prob) = (P2(uc)+P2(vc), P2(pc))
+        k = spectral_diag(h, DIAG_ABS2_VAR, 1, &e); CK(e);      // baroclinic_energy: raw parsevalsum2 values, no 1/(2A)
+        k += spectral_diag(h, DIAG_ABS2_VAR, 2, &e); CK(e);
+        p = spectral_diag(h, DIAG_ABS2_VAR, 3, &e); CK(e);
     } else {                                   // rsw/RotatingShallowWater.jl:323-336
         k = spectral_diag(h, DIAG_ABS2_VAR, 0, &e) / (2 * A); CK(e);
         k += spectral_diag(h, DIAG_ABS2_VAR, 1, &e) / (2 * A); CK(e);
@@ -532,11 +606,12 @@ int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax) {
     cudaError_t e = cudaSuccess;
     double* outs[2] = {umax, vmax};
     const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG;
+    const int uv0 = h->d.model == SWRT_THOMASYAMADA ? 1 : 0;   // TY: baroclinic (u_c, v_c) are state variables 1, 2
     for (int v = 0; v < 2; ++v) {
         if (!outs[v]) continue;
         *outs[v] = 0.0;
         for (int layer = 0; layer < (qg ? h->nvar : 1); ++layer) {   // QG: u = -psi_y, v = psi_x of every layer
-            int rc = spectral_to_physical(h, qg ? (v == 0 ? SWRT_FIELD_QG_U : SWRT_FIELD_QG_V) + layer : v, h->phys);
+            int rc = spectral_to_physical(h, qg ? (v == 0 ? SWRT_FIELD_QG_U : SWRT_FIELD_QG_V) + layer : v + uv0, h->phys);
             if (rc) return rc;
             *outs[v] = std::fmax(*outs[v], reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e));
             CK(e);

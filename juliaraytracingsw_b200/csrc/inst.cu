@@ -16,6 +16,7 @@ cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, double2* G_, 
         case MODEL_RSW_LINDBORG: return ypass_inv(LindborgLoaderA{sol, L.vs}, L, 8, G_, tw, st);
         case MODEL_SWQG: return ypass_inv(QgLoaderA{sol, L.vs, 1, L.aux0}, L, 3, G_, tw, st);
         case MODEL_TWOLAYERQG: return ypass_inv(QgLoaderA{sol, L.vs, 2, L.aux0}, L, 6, G_, tw, st);
+        case MODEL_THOMASYAMADA: return ypass_inv(TyLoaderA{sol, L.vs}, L, 9, G_, tw, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -28,17 +29,19 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
         case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc}, L, tw, st);
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc}, L, tw, st);
+        case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N>{G_, H, sc}, L, tw, st);
     }
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
         case MODEL_RSW: return ypass_fwd(RswCombiner{0, L.Cg2}, L, 3, H, Nout, tw, st);
         case MODEL_RSW_MODIFIED: return ypass_fwd(RswCombiner{1, L.Cg2}, L, 3, H, Nout, tw, st);
         case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, H, Nout, tw, st);
         case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, H, Nout, tw, st);
         case MODEL_TWOLAYERQG: return ypass_fwd(QgCombiner{}, L, 2, H, Nout, tw, st);
+        case MODEL_THOMASYAMADA: return ypass_fwd(TyCombiner{sol, L.vs, L.aux1}, L, 4, H, Nout, tw, st);
     }
     return cudaErrorInvalidValue;
 }

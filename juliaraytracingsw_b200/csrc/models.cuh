@@ -11,12 +11,12 @@
 
 namespace swrt {
 
-enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5 };
+enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5, MODEL_THOMASYAMADA = 6 };
 
 // per-model sizes: state variables, y-transformed intermediates (stage A jobs), x-transformed products (stage B outputs)
-__host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (m == MODEL_TWOLAYERQG ? 2 : 3); }
-__host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_SWQG ? 3 : (m == MODEL_TWOLAYERQG ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
-__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : (m == MODEL_RSW_MODIFIED ? 5 : 4))); }
+__host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (m == MODEL_TWOLAYERQG ? 2 : (m == MODEL_THOMASYAMADA ? 4 : 3)); }
+__host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 3 : (m == MODEL_TWOLAYERQG ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
+__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : (m == MODEL_RSW_MODIFIED ? 5 : 4))); }
 
 // ---------------------------------------------------------------- RSW family, stage A
 // jobs: 0 uh, 1 vh, 2 etah, 3 i l uh, 4 i l vh     (ux, vx are derived in the x-pass as i k G)
@@ -107,6 +107,7 @@ struct RswXOp {
 struct RswCombiner {
     int modified;
     double c2;
+    __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int var) const { return var == 2 ? 2 : (modified ? 2 : 1); }
     __device__ __forceinline__ int src(int var, int i) const { return var == 2 ? 2 + i : (i == 0 ? var : 4); }
     __device__ __forceinline__ double2 apply(int var, int i, double2 v, double kw, double lw) const {
@@ -188,6 +189,7 @@ struct LindborgXOp {
 };
 
 struct NegateCombiner {  // N_var = -P_var
+    __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int) const { return 1; }
     __device__ __forceinline__ int src(int var, int) const { return var; }
     __device__ __forceinline__ double2 apply(int, int, double2 v, double, double) const { return make_double2(-v.x, -v.y); }
@@ -258,10 +260,140 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
 };
 
 struct QgCombiner {  // N_layer = -i l F[psi_x q] + i k F[psi_y q]
+    __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int) const { return 2; }
     __device__ __forceinline__ int src(int var, int i) const { return 2 * var + i; }
     __device__ __forceinline__ double2 apply(int, int i, double2 v, double kw, double lw) const {
         return i == 0 ? make_double2(lw * v.y, -lw * v.x) : make_double2(-kw * v.y, kw * v.x);
+    }
+};
+
+// ---------------------------------------------------------------- Thomas-Yamada (thomasyamada/ThomasYamada.jl:129-274)
+// state (zeta_t, u_c, v_c, p_c); psi_t = -zeta_t/K^2, u_t = -i l psi_t, v_t = i k psi_t
+// y-jobs: 0 zeta_t, 1 psi_t, 2 u_t, 3 d_y u_t = l^2 psi_t, 4 u_c, 5 d_y u_c, 6 v_c, 7 p_c, 8 d_y p_c
+struct TyLoaderA {
+    const double2* sol;
+    long long vs;
+    __device__ __forceinline__ double2 operator()(int job, int, int, double kw, double lw, long long off) const {
+        if (job < 4) {
+            const double2 z = sol[off];
+            if (job == 0) return z;
+            const double K2 = kw * kw + lw * lw, inv = K2 > 0.0 ? -1.0 / K2 : 0.0;
+            const double2 psi = make_double2(inv * z.x, inv * z.y);
+            if (job == 1) return psi;
+            if (job == 2) return make_double2(lw * psi.y, -lw * psi.x);
+            return make_double2(lw * lw * psi.x, lw * lw * psi.y);
+        }
+        if (job == 4) return sol[vs + off];
+        if (job == 5) { const double2 a = sol[vs + off]; return make_double2(-lw * a.y, lw * a.x); }
+        if (job == 6) return sol[2 * vs + off];
+        const double2 p = sol[3 * vs + off];
+        return job == 7 ? p : make_double2(-lw * p.y, lw * p.x);
+    }
+};
+
+// products (linear terms merged): p1 = vt zt, p2 = ut zt, p3 = uc vc, p4 = uc^2 - vc^2, p5 = ut uc, p6 = vt uc_y + vc ut_y,
+// p7 = vt vc, p8 = ut vc_x + uc vt_x, p9 = ut pc_x + vt pc_y   ->  H[0..8]
+template <int N>
+struct TyXOp {
+    static constexpr int NBUF = 3;
+    const double2* G;  // [9][ny][kr_pad]
+    double2* H;        // [9][ny][kr_pad]
+    double sc;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G;
+        const long long ro = (long long)y * L.kr_pad;
+        auto Gp = [&](int j) { return G + j * L.vs + ro; };
+        auto Hp = [&](int j) { return H + j * L.vs + ro; };
+        double *ut = cx.re(0), *vt = cx.im(0), *uc = cx.re(1), *vc = cx.im(1);
+        double2 v[16];
+        double ta[16], tb[16];
+        cx.template load_pair<MUL_ONE, MUL_IK>(2, Gp(2), Gp(1));
+        cx.ifft_regs_out(2, v);                          // ut + i vt
+#pragma unroll
+        for (int m = 0; m < 16; ++m) { const int x = pad_index(cx.g + m * Gt); ut[x] = v[m].x; vt[x] = v[m].y; }
+        cx.template load_pair<MUL_ONE, MUL_ONE>(2, Gp(4), Gp(6));
+        cx.ifft_regs_out(2, v);                          // uc + i vc
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            uc[x] = v[m].x; vc[x] = v[m].y;
+            ta[m] = sc * (ut[x] * v[m].x);               // p5
+            tb[m] = sc * (vt[x] * v[m].y);               // p7
+            v[m] = make_double2(sc * (v[m].x * v[m].y), sc * (v[m].x * v[m].x - v[m].y * v[m].y));   // p3, p4
+        }
+        cx.fft_regs_in(v, 2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, Hp(2), Hp(3));
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = make_double2(ta[m], tb[m]);
+        cx.fft_regs_in(v, 2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, Hp(4), Hp(6));
+        cx.template load_pair<MUL_ONE, MUL_MK2>(2, Gp(0), Gp(1));
+        cx.ifft_regs_out(2, v);                          // zeta_t + i d_x v_t
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            tb[m] = sc * (uc[x] * v[m].y);               // uc vt_x  (half of p8)
+            v[m] = make_double2(sc * (vt[x] * v[m].x), sc * (ut[x] * v[m].x));   // p1, p2
+        }
+        cx.fft_regs_in(v, 2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, Hp(0), Hp(1));
+        cx.template load_pair<MUL_ONE, MUL_ONE>(2, Gp(5), Gp(3));
+        cx.ifft_regs_out(2, v);                          // d_y u_c + i d_y u_t
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            ta[m] = sc * (vt[x] * v[m].x + vc[x] * v[m].y);   // p6
+        }
+        cx.template load_pair<MUL_IK, MUL_IK>(2, Gp(6), Gp(7));
+        cx.ifft_regs_out(2, v);                          // d_x v_c + i d_x p_c
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            const double p9a = sc * (ut[x] * v[m].y);
+            v[m] = make_double2(ta[m], tb[m] + sc * (ut[x] * v[m].x));   // p6, p8
+            ta[m] = p9a;
+        }
+        cx.fft_regs_in(v, 2);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(2, Hp(5), Hp(7));
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(2, Gp(8), nullptr);
+        cx.ifft_regs_out(2, v);                          // d_y p_c
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int x = pad_index(cx.g + m * Gt);
+            v[m] = make_double2(ta[m] + sc * (vt[x] * v[m].x), 0.0);    // p9
+        }
+        cx.fft_regs_in(v, 2);
+        cx.template store_pair<MUL_ONE, MUL_ZERO>(2, Hp(8), nullptr);
+    }
+};
+
+struct TyCombiner {
+    const double2* sol;
+    long long vs;
+    double Ro;
+    __device__ __forceinline__ int nin(int var) const { return var == 0 ? 4 : (var == 3 ? 1 : 2); }
+    __device__ __forceinline__ int src(int var, int i) const { return var == 0 ? i : (var == 1 ? 4 + i : (var == 2 ? 6 + i : 8)); }
+    __device__ __forceinline__ double2 apply(int var, int i, double2 v, double kw, double lw) const {
+        if (var == 0) {
+            if (i == 0) return make_double2(Ro * lw * v.y, -Ro * lw * v.x);                  // -Ro i l
+            if (i == 1) return make_double2(Ro * kw * v.y, -Ro * kw * v.x);                  // -Ro i k
+            const double w = i == 2 ? -Ro * (lw * lw - kw * kw) : -Ro * kw * lw;
+            return make_double2(w * v.x, w * v.y);
+        }
+        if (var != 3 && i == 0) {
+            const double w = Ro * (var == 1 ? kw : lw);
+            return make_double2(w * v.y, -w * v.x);                                          // -Ro i k | -Ro i l
+        }
+        return make_double2(-Ro * v.x, -Ro * v.y);
+    }
+    // linear f-plane wave terms (:143-146)
+    __device__ __forceinline__ double2 init(int var, double kw, double lw, long long off) const {
+        if (var == 0) return make_double2(0.0, 0.0);
+        const double2 u = sol[vs + off], v = sol[2 * vs + off], p = sol[3 * vs + off];
+        if (var == 1) return make_double2(v.x + kw * p.y, v.y - kw * p.x);                   // vc - i k pc
+        if (var == 2) return make_double2(-u.x + lw * p.y, -u.y - lw * p.x);                 // -uc - i l pc
+        return make_double2(kw * u.y + lw * v.y, -(kw * u.x + lw * v.x));                    // -i k uc - i l vc
     }
 };
 
@@ -431,7 +563,7 @@ struct Launch {
     // concrete entry points (explicitly specialised per size in inst.cu); `model` = SWRT_* model id
     static cudaError_t stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st);
-    static cudaError_t stage_c(int model, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
 // y-pass, forward direction, with combination into output variables.
 // Combiner:  int nin(int var); int src(int var, int i);
 //            double2 apply(int var, int i, double2 v, double kw, double lw)
-// out[var][l][kr] = sum_i apply(var, i, FFT_y(H[src(var,i)])[kr, l])
+//            double2 init(int var, double kw, double lw, long long off)      (terms of N that are linear in the state)
+// out[var][l][kr] = init + sum_i apply(var, i, FFT_y(H[src(var,i)])[kr, l])
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
 __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
@@ -128,11 +129,10 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
                     const int l = g + m * G;
                     if (!l_retained(L, l)) continue;
                     double2 r = cb.apply(var, i_in, v[m], kw, wave_l(L, l));
-                    if (i_in > 0) {
-                        const double2 prev = o[(long long)l * L.kr_pad];
-                        r.x += prev.x;
-                        r.y += prev.y;
-                    }
+                    const double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
+                                                  : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                    r.x += prev.x;
+                    r.y += prev.y;
                     o[(long long)l * L.kr_pad] = r;
                 }
             }

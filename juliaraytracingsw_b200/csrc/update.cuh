@@ -182,6 +182,62 @@ __global__ void __launch_bounds__(256) update_diag_kernel(UpdateArgs a, double2*
     }
 }
 
+// ---------------------------------------------------------------- multi-stage steppers on a diagonal (real) L
+// FourierFlows ETDRK4 and (Filtered)RK4 (third party, parity unpinned).
+// coef = { e^{D dt}, D, e^{D dt/2}, filter }, coef2 = { zeta, alpha, beta, Gamma } (contour-integral ETD coefficients).
+enum { ST_ETD_SUB12 = 0, ST_ETD_SUB3 = 1, ST_ETD_UPDATE = 2, ST_RK4_STAGE = 3, ST_RK4_FINAL = 4 };
+struct StageArgs {
+    double2* out;        // state written by this stage
+    const double2* x;    // state the stage starts from
+    double2* n1;         // N buffers (n1 may be updated in place: RK4 stores RHS = N + D x_stage there)
+    const double2* n2;
+    const double2* n3;
+    const double2* n4;
+    const double2* xs;   // RK4: the stage state N was evaluated at
+    const double4* coef;
+    const double4* coef2;
+    double c;            // RK4: stage weight * dt
+    int mode, nvar;
+};
+__global__ void __launch_bounds__(256) diag_stage_kernel(StageArgs a, SpecLayout L) {
+    const int nlk = L.ny - (L.lz1 - L.lz0);
+    const long long total = (long long)nlk * L.kr_keep;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
+        const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
+        const long long off = (long long)l * L.kr_pad + kr;
+        const double4 cf = a.coef[off];
+        const double4 c2 = a.coef2 ? a.coef2[off] : make_double4(0, 0, 0, 0);
+        for (int v = 0; v < a.nvar; ++v) {
+            const long long o = v * L.vs + off;
+            if (a.mode == ST_ETD_SUB12) {                 // out = e^{L dt/2} x + zeta N
+                const double2 x = a.x[o], n = a.n1[o];
+                a.out[o] = make_double2(cf.z * x.x + c2.x * n.x, cf.z * x.y + c2.x * n.y);
+            } else if (a.mode == ST_ETD_SUB3) {           // out = e^{L dt/2} x + zeta (2 N3 - N1)
+                const double2 x = a.x[o], n1 = a.n1[o], n3 = a.n3[o];
+                a.out[o] = make_double2(cf.z * x.x + c2.x * (2.0 * n3.x - n1.x), cf.z * x.y + c2.x * (2.0 * n3.y - n1.y));
+            } else if (a.mode == ST_ETD_UPDATE) {         // sol = e^{L dt} sol + alpha N1 + 2 beta (N2 + N3) + Gamma N4
+                const double2 x = a.x[o], n1 = a.n1[o], n2 = a.n2[o], n3 = a.n3[o], n4 = a.n4[o];
+                a.out[o] = make_double2(cf.x * x.x + c2.y * n1.x + 2.0 * c2.z * (n2.x + n3.x) + c2.w * n4.x,
+                                        cf.x * x.y + c2.y * n1.y + 2.0 * c2.z * (n2.y + n3.y) + c2.w * n4.y);
+            } else if (a.mode == ST_RK4_STAGE) {          // RHS = N + D x_stage (kept); out = sol + c RHS
+                const double2 xs = a.xs[o], x = a.x[o];
+                double2 r = a.n1[o];
+                r = make_double2(r.x + cf.y * xs.x, r.y + cf.y * xs.y);
+                a.n1[o] = r;
+                a.out[o] = make_double2(x.x + a.c * r.x, x.y + a.c * r.y);
+            } else {                                      // RK4 final: sol += dt (R1/6 + R2/3 + R3/3 + R4/6); filter
+                const double2 xs = a.xs[o], x = a.x[o], r1 = a.n1[o], r2 = a.n2[o], r3 = a.n3[o];
+                double2 r4 = a.n4[o];
+                r4 = make_double2(r4.x + cf.y * xs.x, r4.y + cf.y * xs.y);
+                const double sx = x.x + a.c * (r1.x / 6.0 + r2.x / 3.0 + r3.x / 3.0 + r4.x / 6.0);
+                const double sy = x.y + a.c * (r1.y / 6.0 + r2.y / 3.0 + r3.y / 3.0 + r4.y / 6.0);
+                a.out[o] = make_double2(cf.w * sx, cf.w * sy);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- spectral diagnostics (parseval-weighted sums)
 // value(kr,l) per `which`, summed with weights 1 (kr = 0, Nyquist) / 2 (parsevalsum / parsevalsum2 of FourierFlows)
 enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3 };

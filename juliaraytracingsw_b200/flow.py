@@ -20,7 +20,7 @@ MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowW
 STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3}
 FIELD_U, FIELD_V, FIELD_ETA, FIELD_ZETA = 0, 1, 2, 16
 FIELD_QG_PSI, FIELD_QG_U, FIELD_QG_V, FIELD_QG_ZETA = 32, 40, 48, 56
-NVAR = {0: 3, 1: 3, 2: 3, 4: 1, 5: 2}
+NVAR = {0: 3, 1: 3, 2: 3, 4: 1, 5: 2, 6: 4}
 
 
 class Grid:
@@ -81,6 +81,11 @@ class Vars:
 
     def __getattr__(self, name):
         qg = self._p.desc.model in (4, 5)
+        if self._p.desc.model == 6:     # Thomas-Yamada state fields (thomasyamada/ThomasYamada.jl:76-88)
+            ty = {"ζt": 0, "zetat": 0, "uc": 1, "vc": 2, "pc": 3}
+            if name not in ty:
+                raise AttributeError(name)
+            return self._field(ty[name])
         table = ({"q": 0, "ψ": FIELD_QG_PSI, "psi": FIELD_QG_PSI, "u": FIELD_QG_U, "v": FIELD_QG_V, "ζ": FIELD_QG_ZETA,
                   "zeta": FIELD_QG_ZETA} if qg else
                  {"u": FIELD_U, "v": FIELD_V, "η": FIELD_ETA, "eta": FIELD_ETA, "ζ": FIELD_ZETA, "zeta": FIELD_ZETA})
@@ -96,7 +101,7 @@ class Problem:
     def __init__(self, dev=0, *, model="RotatingShallowWater", nx=128, ny=None, Lx=2 * np.pi, Ly=None, ν=1.0e-16,
                  nν=4, f=1.0, Cg=1.0, stepper="IFMAB3", dt=5e-2, aliased_fraction=1 / 3, T=np.float64,
                  use_filter=False, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15, nu=None, nnu=None,
-                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None):
+                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None, Ro=0.2):
         """Two-layer QG (swqg/TwoLayerQG.jl:55-72) takes U, μ, f0, Cg, δρρ0 (F = 2 f0²/Cg²/δρρ0); SWQG takes f, Cg (Kd2 = f²/Cg²)."""
         if T not in (np.float64, float, "Float64"):
             raise _lib.SwrtError("only T=Float64 is implemented (the north star's arithmetic)")
@@ -110,7 +115,7 @@ class Problem:
         d = FlowDesc(model=MODELS[model], stepper=STEPPERS[stepper], nx=nx, ny=ny, nnu=nν, use_filter=int(use_filter),
                      filter_order=order, device=int(dev), Lx=Lx, Ly=Ly, dt=dt, nu=ν, f=f, Cg=Cg,
                      aliased_fraction=aliased_fraction, filter_innerK=innerK, filter_outerK=outerK, filter_tol=tol,
-                     U=U, mu=μ, F=F)
+                     U=U, mu=μ, F=F, Ro=Ro)
         self._h = C.c_void_p()
         check(lib().swrt_flow_create(C.byref(d), C.byref(self._h)))
         self.desc, self.dt, self.nvar = d, dt, NVAR[d.model]
@@ -174,9 +179,13 @@ class Problem:
         return ms.value
 
 
-def set_solution(prob, u0h, v0h, η0h):
-    """set_solution!(prob, u0h, v0h, η0h)  rsw/RotatingShallowWater.jl:309-321"""
-    prob.sol = np.stack([np.asarray(u0h), np.asarray(v0h), np.asarray(η0h)], axis=-1)
+def set_solution(prob, *fields):
+    """set_solution!(prob, u0h, v0h, η0h) rsw/RotatingShallowWater.jl:309-321; (prob, ζ0h, u0h, v0h, p0h)
+    thomasyamada/ThomasYamada.jl:292-317; (prob, q0h) swqg/TwoLayerQG.jl:211-219."""
+    if len(fields) == 1:
+        prob.sol = np.asarray(fields[0])
+    else:
+        prob.sol = np.stack([np.asarray(f) for f in fields], axis=-1)
 
 
 def enforce_reality_condition(prob):

@@ -299,3 +299,59 @@ def test_twolayerqg_parity():
         vel, _ = raytracing.get_velocity_info(prob, 1, kind)
         ref = oray.get_velocity_info(comb(oqg.twolayer_streamfunction(g.dealias(want.copy()), g, F)), g)
         assert rel_l2(vel._arr(), ref) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ Thomas-Yamada + multi-stage steppers
+@pytest.mark.parametrize("stepper", ["ETDRK4", "FilteredRK4", "IFMAB3"])
+def test_thomasyamada_parity(stepper):
+    from oracle import ifmab3 as oif, ty as oty
+    nx, Lx, Ro, nnu, dt = 64, 6 * np.pi, 1.0, 8, 5e-3
+    nu = 5e-34 * (Lx / (2 * np.pi)) ** 16 * 1e12          # thomasyamada/gpu-setup/Parameters.jl recipe, scaled so that it acts at 64^2
+    g, s3 = random_state(nx, seed=21, amp=0.3, slope=1.0, Lx=Lx)
+    _, s1 = random_state(nx, seed=22, amp=0.3, slope=1.0, Lx=Lx)
+    sol0 = np.concatenate([s3, s1[:, :, :1]], axis=-1)
+    prob = swrt.Problem(model="ThomasYamada", stepper=stepper, nx=nx, Lx=Lx, dt=dt, nu=nu, nnu=nnu, Ro=Ro)
+    flow.set_solution(prob, *(sol0[:, :, i] for i in range(4)))
+    np.testing.assert_array_equal(prob.sol, sol0)
+    assert rel_l2(prob.vars.uc, g.irfft2(sol0[:, :, 1])) < 1e-13
+    L = oty.ty_L(g, nu, nnu)
+    calcN = lambda s: oty.ty_calcN(s, g, Ro)
+    ts = {"ETDRK4": lambda: oty.ETDRK4(L, dt, calcN), "FilteredRK4": lambda: oty.FilteredRK4(L, dt, calcN, makefilter(g)),
+          "IFMAB3": lambda: oif.IFMAB3(L, dt, calcN)}[stepper]()
+    want = sol0.copy()
+    for n in (1, 3, 26):
+        flow.stepforward(prob, (), n)
+        for _ in range(n):
+            ts.stepforward(want)
+        assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10, n
+    ke, pe = flow.kinetic_energy(prob), flow.potential_energy(prob)
+    from oracle.grid import parsevalsum2
+    w = g.dealias(want.copy())
+    assert abs(ke / (parsevalsum2(w[:, :, 1], g) + parsevalsum2(w[:, :, 2], g)) - 1) < 1e-9
+    assert abs(pe / parsevalsum2(w[:, :, 3], g) - 1) < 1e-9
+
+
+@pytest.mark.parametrize("stepper", ["ETDRK4", "FilteredRK4"])
+def test_swqg_multistage_steppers(stepper):
+    from oracle import qg as oqg, ty as oty
+    nx, f, Cg, nnu, dt = 64, 3.0, 1.0, 4, 4e-3
+    nu = 2 * np.pi / nx / ((nx / 2 - 1) ** (2 * nnu)) / dt
+    g, sol0 = _qg_state(nx, 1, 15)
+    sol0 = sol0[:, :, 0]
+    prob = swrt.Problem(model="SWQG", stepper=stepper, nx=nx, dt=dt, f=f, Cg=Cg, nu=nu, nnu=nnu)
+    prob.sol = sol0
+    L = oqg.swqg_L(g, nu, nnu)
+    calcN = lambda s: oqg.swqg_calcN(s, g, f * f / (Cg * Cg))
+    ts = oty.ETDRK4(L, dt, calcN) if stepper == "ETDRK4" else oty.FilteredRK4(L, dt, calcN, makefilter(g))
+    want = sol0.copy()
+    flow.stepforward(prob, (), 25)
+    for _ in range(25):
+        ts.stepforward(want)
+    assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10
+
+
+def test_unsupported_combinations_fail_loudly():
+    with pytest.raises(swrt.SwrtError):
+        swrt.Problem(model="RotatingShallowWater", stepper="ETDRK4", nx=64)      # matrix L: FourierFlows steppers need a diagonal L
+    with pytest.raises(swrt.SwrtError):
+        swrt.Problem(nx=48)                                                      # not a power of two
