@@ -145,12 +145,12 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 5))
-    r = cpu_sample(args, steps, min(args.warmup, 1), cores)
+    steps, warm = max(1, min(args.steps, 30)), max(0, min(args.warmup, 3))   # a step costs seconds on the host: bounded
+    r = cpu_sample(args, steps, warm, cores)
     ntot = args.sqrt_packets ** 2
     line = {
         "impl": "reference", "metric": "packet-steps/s", "value": r["value"], "unit": "packet-steps/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "nsub": args.nsub,
                    "integrator": "RK4", "interp": "bilinear"},

@@ -68,8 +68,8 @@ struct swrt_flow {
     double4* coef2 = nullptr;                   // ETDRK4 coefficients {zeta, alpha, beta, Gamma}
     double2 *S1 = nullptr, *S2 = nullptr, *N4 = nullptr;   // stage states and 4th N buffer of the multi-stage steppers
     double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
-    double* snap = nullptr;      // S[ny][nx][2][5]: both snapshot halves interleaved (snapshot_layout.cuh)
-    int slot_map[2] = {0, 1};    // slot (0 = old, 1 = new) -> half
+    double* snap[2] = {nullptr, nullptr};   // S[ny][nx][6] per time level (snapshot_layout.cuh)
+    int slot_map[2] = {0, 1};               // slot (0 = old, 1 = new) -> array
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
     int ring = 0;
@@ -256,7 +256,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
-    cudaFree(h->snap); cudaFree(h->phys); cudaFree(h->red);
+    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -323,8 +323,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
-    CKB(cudaMalloc(&h->snap, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
-    CKB(cudaMemset(h->snap, 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
+    for (int lev = 0; lev < 2; ++lev) {
+        CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
+        CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
+    }
     CKB(upload_twiddles(d.nx, &h->tw_x));
     CKB(upload_twiddles(d.ny, &h->tw_y));
 
@@ -642,7 +644,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap + h->slot_map[slot] * SNAP_NC, L, h->tw_x, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -660,7 +662,7 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     const long long n = (long long)h->d.nx * h->d.ny;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * SNAP_NC));
-    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap, h->slot_map[slot], n, tmp); }
+    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, tmp); }
     cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * SNAP_NC, cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     cudaFree(tmp);
@@ -677,7 +679,7 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * SNAP_NC, cudaMemcpyHostToDevice, h->st);
     if (e == cudaSuccess) {
         ProfScope ps(h, K_OTHER);
-        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, h->slot_map[slot], n, h->snap);
+        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, n, h->snap[h->slot_map[slot]]);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
@@ -871,24 +873,18 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
         int rc = sort_packets(p);
         if (rc) return rc;
     }
-    RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp, f->slot_map[0], f->slot_map[1]};
+    RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
+    const double *So = f->snap[f->slot_map[0]], *Sn = f->snap[f->slot_map[1]];
     const long long n = p->d.n;
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
-    static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3..6 = cached kernel with that many CTAs/SM
+    static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
-      if (cached) {
-#define SWRT_RT(MB, OH, NH) raytrace_rk4_cached_kernel<MB, OH, NH><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp)
-          const int oh = rp.old_half, nh = rp.new_half;
-#define SWRT_RT4(MB) { if (oh == 0 && nh == 1) SWRT_RT(MB, 0, 1); else if (oh == 1 && nh == 0) SWRT_RT(MB, 1, 0); else if (oh == 0) SWRT_RT(MB, 0, 0); else SWRT_RT(MB, 1, 1); }
-          if (cached == 3) SWRT_RT4(3) else if (cached == 5) SWRT_RT4(5) else if (cached == 6) SWRT_RT4(6) else SWRT_RT4(4)
-#undef SWRT_RT4
-#undef SWRT_RT
-      }
-      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
-      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
-      else if (minb <= 7) raytrace_rk4_kernel<6><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp);
-      else raytrace_rk4_kernel<8><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, f->snap, packet_grid(f), rp); }
+      if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else raytrace_rk4_kernel<6><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
     CK(cudaGetLastError());
     p->since_sort++;
     return SWRT_OK;
@@ -899,7 +895,7 @@ int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_hos
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap, f->slot_map[slot], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
+    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
     if (g_host) CK(cudaMemcpyAsync(g_host, p->Gd, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));

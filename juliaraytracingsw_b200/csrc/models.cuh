@@ -471,7 +471,7 @@ template <int N>
 struct SnapshotXOp {
     static constexpr int NBUF = 3;
     const double2* G;  // [3][ny][kr_pad]
-    double* out;       // [ny][nx][2][5], already offset to the half being written
+    double* out;       // [ny][nx][6] of the level being written
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
@@ -487,12 +487,10 @@ struct SnapshotXOp {
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {
             const int x = cx.g + i * Gt, p = pad_index(x);
-            double* q = o + (long long)x * SNAP_STRIDE;   // the point's 40-byte half is written in one go
-            q[0] = s1 * cx.re(0)[p];
-            q[1] = s1 * cx.im(0)[p];
-            q[2] = s1 * cx.re(1)[p];
-            q[3] = s1 * cx.im(1)[p];
-            q[4] = s1 * cx.re(2)[p];
+            double2* q = reinterpret_cast<double2*>(o + (long long)x * SNAP_STRIDE);   // 48-byte record, three 16-byte stores
+            q[0] = make_double2(s1 * cx.re(0)[p], s1 * cx.im(0)[p]);
+            q[1] = make_double2(s1 * cx.re(1)[p], s1 * cx.im(1)[p]);
+            q[2] = make_double2(s1 * cx.re(2)[p], 0.0);
         }
     }
 };

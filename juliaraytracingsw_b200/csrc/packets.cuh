@@ -2,11 +2,9 @@
 // `nsub` classical RK4 steps per launch, bilinear gathers from the two time levels of the
 // background field.
 //
-// Field layout: S[y][x][2][5] doubles -- both time levels (halves A, B) of (u, v, ux, uy, vx)
-// interleaved per grid point (vy = -ux), 80 B = five 16-byte vectors per point, so the two x-taps of
-// a bilinear stencil are 160 contiguous bytes and one pass of ten LDG.128 per row fetches both
-// time levels.  Which half is "old" is a launch parameter (the snapshot kernel overwrites the
-// other half each flow step).
+// Field layout (snapshot_layout.cuh): one array per time level, S[y][x][6] doubles = (u, v, ux, uy, vx, pad), 48 B =
+// three 16-byte vectors per point, so the two x-taps of a bilinear stencil are 96 contiguous bytes (six LDG.128).
+// Which array is "old" is a launch parameter (the snapshot kernel overwrites the other one each flow step).
 //
 // Locality: packets are kept sorted by an 8x8-cell-tiled cell key (counting sort, re-run every
 // `sort_every` raytrace calls); `idx` remembers each packet's original row so that every
@@ -40,55 +38,48 @@ __device__ __forceinline__ void cell(double x, double x0, double inv_dx, int n, 
     i1 = (i0 + 1) & (n - 1);
 }
 
-// one x-row of the stencil: (1-a) S[j][i0] + a S[j][i1] for all ten interleaved values
-__device__ __forceinline__ void lerp_row(const double* __restrict__ S, long long p0, long long p1, double a, double (&r)[10]) {
+// one x-row of the stencil of one level: (1-a) S[j][i0] + a S[j][i1] for the five fields
+__device__ __forceinline__ void lerp_row(const double* __restrict__ S, long long p0, long long p1, double a, double (&r)[5]) {
     const double2* q0 = reinterpret_cast<const double2*>(S + p0 * SNAP_STRIDE);
     const double2* q1 = reinterpret_cast<const double2*>(S + p1 * SNAP_STRIDE);
-    double2 u[5], v[5];
+    double2 u[3], v[3];
 #pragma unroll
-    for (int q = 0; q < 5; ++q) u[q] = __ldg(q0 + q);
+    for (int q = 0; q < 3; ++q) u[q] = __ldg(q0 + q);
 #pragma unroll
-    for (int q = 0; q < 5; ++q) v[q] = __ldg(q1 + q);
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-        r[2 * q] = (1.0 - a) * u[q].x + a * v[q].x;
-        r[2 * q + 1] = (1.0 - a) * u[q].y + a * v[q].y;
-    }
+    for (int q = 0; q < 3; ++q) v[q] = __ldg(q1 + q);
+    r[0] = (1.0 - a) * u[0].x + a * v[0].x;
+    r[1] = (1.0 - a) * u[0].y + a * v[0].y;
+    r[2] = (1.0 - a) * u[1].x + a * v[1].x;
+    r[3] = (1.0 - a) * u[1].y + a * v[1].y;
+    r[4] = (1.0 - a) * u[2].x + a * v[2].x;
 }
 
-// bilinear interpolation of both halves at once; out[h*5 + c]
-__device__ __forceinline__ void bilinear10(const double* __restrict__ S, const PacketGrid& g, int i0, int i1, int j0, int j1,
-                                           double a, double b, double (&out)[10]) {
-    double bottom[10], top[10];
+__device__ __forceinline__ void bilinear5(const double* __restrict__ S, const PacketGrid& g, int i0, int i1, int j0, int j1,
+                                          double a, double b, double (&out)[5]) {
+    double bottom[5], top[5];
     lerp_row(S, (long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, a, bottom);
     lerp_row(S, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1, a, top);
 #pragma unroll
-    for (int c = 0; c < 10; ++c) out[c] = (1.0 - b) * bottom[c] + b * top[c];
+    for (int c = 0; c < 5; ++c) out[c] = (1.0 - b) * bottom[c] + b * top[c];
 }
 
 struct RayParams {
     double f, Cg, t0, t1;
     int nsub, lerp;  // lerp: 0 physical ((1-a) old + a new), 1 reference GPU (a old + (1-a) new)
-    int old_half, new_half;
 };
 
-__device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, double alpha, const double* __restrict__ S,
-                                        const PacketGrid& g, const RayParams& p, double (&d)[4]) {
+__device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, double alpha, const double* __restrict__ So,
+                                        const double* __restrict__ Sn, const PacketGrid& g, const RayParams& p, double (&d)[4]) {
     int i0, i1, j0, j1;
     double a, b;
     cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-    double V[10];
-    bilinear10(S, g, i0, i1, j0, j1, a, b, V);
+    double o[5], nw[5], W[5];
+    bilinear5(So, g, i0, i1, j0, j1, a, b, o);
+    bilinear5(Sn, g, i0, i1, j0, j1, a, b, nw);
     const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
-    // weights of half A (V[0..5)) and half B (V[5..10)); wo*old + wn*new, the sum is commutative so the
-    // rounding equals the oracle's whichever half is "old"
-    const double wA = (p.old_half == 0 ? wo : 0.0) + (p.new_half == 0 ? wn : 0.0);
-    const double wB = (p.old_half == 1 ? wo : 0.0) + (p.new_half == 1 ? wn : 0.0);
-    double W[5];
 #pragma unroll
-    for (int c = 0; c < 5; ++c) W[c] = p.old_half == p.new_half ? (p.old_half == 0 ? wo * V[c] + wn * V[c] : wo * V[5 + c] + wn * V[5 + c])
-                                                                : wA * V[c] + wB * V[5 + c];
+    for (int c = 0; c < 5; ++c) W[c] = wo * o[c] + wn * nw[c];
     const double k = s[2], l = s[3];
     const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));   // Cg^2 / omega
     d[0] = W[0] + cg * k;
@@ -100,7 +91,8 @@ __device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, doubl
 // xk: (N,4) column-major = 4 arrays of N
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
-                                                              const double* __restrict__ S, PacketGrid g, RayParams p) {
+                                                                 const double* __restrict__ So, const double* __restrict__ Sn,
+                                                                 PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
@@ -109,16 +101,16 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
     for (int it = 0; it < p.nsub; ++it) {
         const double t = p.t0 + it * h;
         double k1[4], k2[4], k3[4], k4[4], y[4];
-        ray_rhs(s, sg, (t - p.t0) * inv_span, S, g, p, k1);
+        ray_rhs(s, sg, (t - p.t0) * inv_span, So, Sn, g, p, k1);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k1[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, k2);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k2);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k2[c];
-        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, k3);
+        ray_rhs(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k3);
 #pragma unroll
         for (int c = 0; c < 4; ++c) y[c] = s[c] + h * k3[c];
-        ray_rhs(y, sg, (t + h - p.t0) * inv_span, S, g, p, k4);
+        ray_rhs(y, sg, (t + h - p.t0) * inv_span, So, Sn, g, p, k4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
     }
@@ -134,25 +126,26 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
 // the cell changes: ~4x fewer L1 wavefronts, which is what bounds the plain kernel (ncu: l1tex data-pipe
 // 76 %).  A time level whose lerp weight is exactly 0 (alpha = 0 at stage 1, alpha = 1 at stage 4) is
 // skipped; 0*x + 1*y == y, so the result equals the full formula bit for bit for finite fields.
-struct Stencil {
-    double2 c00[5], c10[5], c01[5], c11[5];
+struct Stencil {   // [level][corner 00,10,01,11][3 vectors]
+    double2 c[2][4][3];
     int ci, cj;
 };
-#define SWRT_EL(arr, idx) (((idx) & 1) ? arr[(idx) >> 1].y : arr[(idx) >> 1].x)
 
-template <int H>
-__device__ __forceinline__ void bilinear5_cached(const Stencil& st, double a, double b, double (&out)[5]) {
+__device__ __forceinline__ void bilinear5_cached(const double2 (&c)[4][3], double a, double b, double (&out)[5]) {
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const double bottom = (1.0 - a) * SWRT_EL(st.c00, H * 5 + c) + a * SWRT_EL(st.c10, H * 5 + c);
-        const double top = (1.0 - a) * SWRT_EL(st.c01, H * 5 + c) + a * SWRT_EL(st.c11, H * 5 + c);
-        out[c] = (1.0 - b) * bottom + b * top;
+    for (int f = 0; f < 5; ++f) {
+        const int q = f >> 1;
+        const double v00 = (f & 1) ? c[0][q].y : c[0][q].x, v10 = (f & 1) ? c[1][q].y : c[1][q].x;
+        const double v01 = (f & 1) ? c[2][q].y : c[2][q].x, v11 = (f & 1) ? c[3][q].y : c[3][q].x;
+        const double bottom = (1.0 - a) * v00 + a * v10;
+        const double top = (1.0 - a) * v01 + a * v11;
+        out[f] = (1.0 - b) * bottom + b * top;
     }
 }
 
-template <int OH, int NH>
-__device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign, double alpha, const double* __restrict__ S,
-                                               const PacketGrid& g, const RayParams& p, Stencil& st, double (&d)[4]) {
+__device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign, double alpha, const double* __restrict__ So,
+                                               const double* __restrict__ Sn, const PacketGrid& g, const RayParams& p, Stencil& st,
+                                               double (&d)[4]) {
     int i0, i1, j0, j1;
     double a, b;
     cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
@@ -160,35 +153,34 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
     if (i0 != st.ci || j0 != st.cj) {
         st.ci = i0;
         st.cj = j0;
-        const double2* q00 = reinterpret_cast<const double2*>(S + ((long long)j0 * g.nx + i0) * SNAP_STRIDE);
-        const double2* q10 = reinterpret_cast<const double2*>(S + ((long long)j0 * g.nx + i1) * SNAP_STRIDE);
-        const double2* q01 = reinterpret_cast<const double2*>(S + ((long long)j1 * g.nx + i0) * SNAP_STRIDE);
-        const double2* q11 = reinterpret_cast<const double2*>(S + ((long long)j1 * g.nx + i1) * SNAP_STRIDE);
+        const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
 #pragma unroll
-        for (int q = 0; q < 5; ++q) st.c00[q] = __ldg(q00 + q);
+        for (int lev = 0; lev < 2; ++lev) {
+            const double* S = lev == 0 ? So : Sn;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) st.c10[q] = __ldg(q10 + q);
+            for (int cr = 0; cr < 4; ++cr) {
+                const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
 #pragma unroll
-        for (int q = 0; q < 5; ++q) st.c01[q] = __ldg(q01 + q);
-#pragma unroll
-        for (int q = 0; q < 5; ++q) st.c11[q] = __ldg(q11 + q);
+                for (int k = 0; k < 3; ++k) st.c[lev][cr][k] = __ldg(q + k);
+            }
+        }
     }
     const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
     double W[5];
     if (wn == 0.0) {
         double o[5];
-        bilinear5_cached<OH>(st, a, b, o);
+        bilinear5_cached(st.c[0], a, b, o);
 #pragma unroll
         for (int c = 0; c < 5; ++c) W[c] = wo * o[c];
     } else if (wo == 0.0) {
         double nw[5];
-        bilinear5_cached<NH>(st, a, b, nw);
+        bilinear5_cached(st.c[1], a, b, nw);
 #pragma unroll
         for (int c = 0; c < 5; ++c) W[c] = wn * nw[c];
     } else {
         double o[5], nw[5];
-        bilinear5_cached<OH>(st, a, b, o);
-        bilinear5_cached<NH>(st, a, b, nw);
+        bilinear5_cached(st.c[0], a, b, o);
+        bilinear5_cached(st.c[1], a, b, nw);
 #pragma unroll
         for (int c = 0; c < 5; ++c) W[c] = wo * o[c] + wn * nw[c];
     }
@@ -200,10 +192,10 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
     d[3] = -(W[3] * k - W[2] * l);
 }
 
-template <int MINB, int OH, int NH>
+template <int MINB>
 __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* __restrict__ xk, const double* __restrict__ sign,
-                                                                        long long n, const double* __restrict__ S, PacketGrid g,
-                                                                        RayParams p) {
+                                                                        long long n, const double* __restrict__ So,
+                                                                        const double* __restrict__ Sn, PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
@@ -215,18 +207,18 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* 
     for (int it = 0; it < p.nsub; ++it) {
         const double t = p.t0 + it * h;
         double k[4], acc[4], y[4];
-        ray_rhs_cached<OH, NH>(s, sg, (t - p.t0) * inv_span, S, g, p, st, k);
+        ray_rhs_cached(s, sg, (t - p.t0) * inv_span, So, Sn, g, p, st, k);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
-        ray_rhs_cached<OH, NH>(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, st, k);
+        ray_rhs_cached(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, st, k);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
-        ray_rhs_cached<OH, NH>(y, sg, (t + 0.5 * h - p.t0) * inv_span, S, g, p, st, k);
+        ray_rhs_cached(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, st, k);
 #pragma unroll
         for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
         // the last stage of the last sub-step sits at t1: alpha = 1 exactly (the oracle's (t + h - t0)/(t1 - t0) can be 1 - ulp)
         const double a4 = it == p.nsub - 1 ? 1.0 : (t + h - p.t0) * inv_span;
-        ray_rhs_cached<OH, NH>(y, sg, a4, S, g, p, st, k);
+        ray_rhs_cached(y, sg, a4, So, Sn, g, p, st, k);
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
@@ -238,18 +230,15 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* 
 
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
-                                                     const double* __restrict__ S, int half, PacketGrid g, double* __restrict__ U,
+                                                     const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
                                                      double* __restrict__ Gd) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int i0, i1, j0, j1;
-    double a, b, V[10];
+    double a, b, Sv[5];
     cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
-    bilinear10(S, g, i0, i1, j0, j1, a, b, V);
-    double Sv[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) Sv[c] = half == 0 ? V[c] : V[5 + c];
+    bilinear5(S, g, i0, i1, j0, j1, a, b, Sv);
     const long long o = idx[i];
     U[o] = Sv[0];
     U[n + o] = Sv[1];
@@ -358,17 +347,18 @@ __global__ void unpermute_kernel(const double* __restrict__ xk, const unsigned* 
 }
 
 // snapshot half <-> planar (nx, ny, 5) host layout staging
-__global__ void snap_to_planar_kernel(const double* __restrict__ S, int half, long long npts, double* __restrict__ planar) {
+__global__ void snap_to_planar_kernel(const double* __restrict__ S, long long npts, double* __restrict__ planar) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= npts) return;
 #pragma unroll
-    for (int c = 0; c < SNAP_NC; ++c) planar[c * npts + i] = S[i * SNAP_STRIDE + half * SNAP_NC + c];
+    for (int c = 0; c < SNAP_NC; ++c) planar[c * npts + i] = S[i * SNAP_STRIDE + c];
 }
-__global__ void planar_to_snap_kernel(const double* __restrict__ planar, int half, long long npts, double* __restrict__ S) {
+__global__ void planar_to_snap_kernel(const double* __restrict__ planar, long long npts, double* __restrict__ S) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= npts) return;
 #pragma unroll
-    for (int c = 0; c < SNAP_NC; ++c) S[i * SNAP_STRIDE + half * SNAP_NC + c] = planar[c * npts + i];
+    for (int c = 0; c < SNAP_NC; ++c) S[i * SNAP_STRIDE + c] = planar[c * npts + i];
+    S[i * SNAP_STRIDE + SNAP_NC] = 0.0;
 }
 
 }  // namespace swrt
