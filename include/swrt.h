@@ -100,7 +100,7 @@ int swrt_flow_timer_start(swrt_flow* h);
 int swrt_flow_timer_stop(swrt_flow* h, float* ms);
 int swrt_flow_sync(swrt_flow* h);
 /* per-kernel device timing: enable = 1 brackets every launch with CUDA events on the handle's stream, 2 also clears the
- * accumulators, 0 switches it off.  profile_get(id) -> accumulated ms, launch count and kernel name for id in [0, 11) */
+ * accumulators, 0 switches it off.  profile_get(id) -> accumulated ms, launch count and kernel name for id in [0, 13) */
 int swrt_flow_profile(swrt_flow* h, int enable);
 int swrt_flow_profile_get(swrt_flow* h, int id, double* ms_total, long long* count, const char** name);
 /* number of kernels this handle has launched so far */

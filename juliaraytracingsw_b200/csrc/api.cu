@@ -65,6 +65,7 @@ struct swrt_flow {
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
+    double2* psih = nullptr;                    // materialised streamfunction for the packet snapshot
     double4* coef2 = nullptr;                   // ETDRK4 coefficients {zeta, alpha, beta, Gamma}
     double2 *S1 = nullptr, *S2 = nullptr, *N4 = nullptr;   // stage states and 4th N buffer of the multi-stage steppers
     double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
@@ -84,11 +85,11 @@ struct swrt_flow {
     long long prof_n[16] = {0};
 };
 
-enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_OTHER, K_COUNT };
+enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_PSI, K_OTHER, K_COUNT };
 static const char* kKernelNames[K_COUNT] = {"ypass_inv_kernel<RswLoaderA>", "xpass_kernel<RswXOp>", "ypass_fwd_kernel<RswCombiner>",
                                             "ifmab3_update_rsw_kernel", "ypass_inv_kernel<PsiLoader>", "xpass_kernel<SnapshotXOp>",
                                             "raytrace_rk4_kernel", "sample_kernel", "ypass_inv_kernel<FieldLoader>", "xpass_kernel<C2ROp>",
-                                            "packet_sort_kernels", "other"};
+                                            "packet_sort_kernels", "psi_kernel", "other"};
 
 struct ProfScope {
     swrt_flow* h;
@@ -255,7 +256,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
-    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
+    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
@@ -320,6 +321,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     }
     CKB(cudaMalloc(&h->G, fb * h->njobs_a)); CKB(cudaMemset(h->G, 0, fb * h->njobs_a));
     CKB(cudaMalloc(&h->H, fb * h->njobs_b)); CKB(cudaMemset(h->H, 0, fb * h->njobs_b));
+    CKB(cudaMalloc(&h->psih, fb)); CKB(cudaMemset(h->psih, 0, fb));
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
@@ -642,7 +644,16 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     const SpecLayout& L = h->L;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0};
     cudaError_t e;
-    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, L, h->G, h->tw_y, h->st)); }
+    bool materialise = false;
+    SWRT_DISPATCH(L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
+    CK(e);
+    if (materialise) {
+        const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+        ProfScope ps(h, K_PSI);
+        psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, L, h->psih);
+        CK(cudaGetLastError());
+    }
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, h->G, h->tw_y, h->st)); }
     CK(e);
     { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st)); }
     CK(e);

@@ -12,7 +12,12 @@ template <>
 cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
         case MODEL_RSW:
-        case MODEL_RSW_MODIFIED: return ypass_inv(RswLoaderA{sol, L.vs}, L, 5, G_, tw, st);
+        case MODEL_RSW_MODIFIED: {
+            SimpleJobs sj{};
+            const int fld[5] = {0, 1, 2, 0, 1}, mul[5] = {YMUL_ONE, YMUL_ONE, YMUL_ONE, YMUL_IL, YMUL_IL};
+            for (int j = 0; j < 5; ++j) { sj.src[j] = sol + fld[j] * L.vs; sj.mul[j] = mul[j]; }
+            return ypass_inv_simple(sj, RswLoaderA{sol, L.vs}, L, 5, G_, tw, st);
+        }
         case MODEL_RSW_LINDBORG: return ypass_inv(LindborgLoaderA{sol, L.vs}, L, 8, G_, tw, st);
         case MODEL_SWQG: return ypass_inv(QgLoaderA{sol, L.vs, 1, L.aux0}, L, 3, G_, tw, st);
         case MODEL_TWOLAYERQG: return ypass_inv(QgLoaderA{sol, L.vs, 2, L.aux0}, L, 6, G_, tw, st);
@@ -55,7 +60,14 @@ cudaError_t Launch<SWRT_N>::field_stage_b(const double2* G_, double* out, const 
     return xpass(op, L, tw, st);
 }
 template <>
-cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw,
+                                        cudaStream_t st) {
+    if (psih) {   // jobs: psih, -i l psih, l^2 psih from the materialised field
+        SimpleJobs sj{};
+        const int mul[3] = {YMUL_ONE, YMUL_NEG_IL, YMUL_L2};
+        for (int j = 0; j < 3; ++j) { sj.src[j] = psih; sj.mul[j] = mul[j]; }
+        return ypass_inv_simple(sj, ld, L, 3, G_, tw, st);
+    }
     return ypass_inv(ld, L, 3, G_, tw, st);
 }
 template <>

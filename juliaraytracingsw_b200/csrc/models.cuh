@@ -6,6 +6,8 @@
 //   rsw/RSWRaytracingDriver.jl:63-67      get_streamfunction!
 //   raytracing/RaytracingDriver.jl:132-154 get_velocity_info
 #pragma once
+#include <cstdlib>
+
 #include "passes.cuh"
 #include "snapshot_layout.cuh"
 
@@ -499,7 +501,7 @@ struct SnapshotXOp {
 #ifndef SWRT_TK_LARGE
 #define SWRT_TK_LARGE 4   // columns per y-pass CTA for N >= 2048 (tuning knob)
 #endif
-__host__ __device__ constexpr int tile_k(int N) { return N >= 2048 ? SWRT_TK_LARGE : (N >= 256 ? 4096 / N : 16); }
+__host__ __device__ constexpr int tile_k(int N) { return N >= 4096 ? 2 : (N >= 2048 ? SWRT_TK_LARGE : (N >= 256 ? 4096 / N : 16)); }
 template <int N>
 struct Launch {
     static constexpr int TK = tile_k(N);
@@ -536,9 +538,45 @@ struct Launch {
         k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(ld, L, njobs, out, tw);
         return cudaGetLastError();
     }
+    // prefetching variant for simple jobs; falls back to the plain kernel when the staging buffer does not fit
+    static constexpr bool kPrefetchFits = ysmem + (size_t)ypass_stage_smem(N, TK) * 2 / 3 + 4096 <= (size_t)kSmemPerSM;
+    template <class Loader>
+    static cudaError_t ypass_inv_simple(const SimpleJobs& jobs, const Loader& fallback, const SpecLayout& L, int njobs, double2* out,
+                                        const double2* tw, cudaStream_t st) {
+        const size_t stage = (size_t)(L.ny - (L.lz1 - L.lz0)) * TK * 16;
+        static const int enabled = [] { const char* e = getenv("SWRT_YPASS_PREFETCH"); return e ? atoi(e) : 1; }();
+        if constexpr (kPrefetchFits) {
+            if (enabled && ysmem + stage + 1024 <= (size_t)kSmemPerSM) {
+                auto k = ypass_inv_prefetch_kernel<N, TK>;
+                int mc = 1;
+                cudaError_t e = prep(k, ysmem + stage, TK * G, &mc);
+                if (e != cudaSuccess) return e;
+                const int work = ((L.kr_keep + TK - 1) / TK) * njobs;
+                k<<<work < mc ? work : mc, TK * G, ysmem + stage, st>>>(jobs, L, njobs, out, tw);
+                return cudaGetLastError();
+            }
+        }
+        return ypass_inv(fallback, L, njobs, out, tw, st);
+    }
     template <class Combiner>
     static cudaError_t ypass_fwd(const Combiner& cb, const SpecLayout& L, int nvars, const double2* H, double2* out,
                                  const double2* tw, cudaStream_t st) {
+        static const int enabled = [] { const char* e = getenv("SWRT_YPASS_PREFETCH"); return e ? atoi(e) : 1; }();
+        if constexpr (kPrefetchFits) {
+            if (enabled) {
+                // as many staged rows as fit beside the work buffers
+                int rows_s = (int)(((size_t)kSmemPerSM - ysmem - 1024) / ((size_t)TK * 16));
+                if (rows_s > L.ny) rows_s = L.ny;
+                const size_t smem = ysmem + (size_t)rows_s * TK * 16;
+                auto kp = ypass_fwd_prefetch_kernel<N, TK, Combiner>;
+                int mcp = 1;
+                cudaError_t ep = prep(kp, smem, TK * G, &mcp);
+                if (ep != cudaSuccess) return ep;
+                const int workp = ((L.kr_keep + TK - 1) / TK) * nvars;
+                kp<<<workp < mcp ? workp : mcp, TK * G, smem, st>>>(cb, L, nvars, rows_s, H, out, tw);
+                return cudaGetLastError();
+            }
+        }
         auto k = ypass_fwd_kernel<N, TK, Combiner>;
         int mc = 1;
         cudaError_t e = prep(k, ysmem, TK * G, &mc);
@@ -564,7 +602,8 @@ struct Launch {
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
-    static cudaError_t psi_stage_a(const PsiLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
     static cudaError_t snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
 };
 

@@ -91,6 +91,79 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
 }
 
 // ------------------------------------------------------------------------------------
+// y-pass, inverse direction, with an asynchronous input prefetch (cp.async -> shared-memory staging).
+// For "simple" jobs whose source is one stored spectral field times a multiplier that depends on l only
+// (1, i l, -i l, l^2): while the CTA transforms tile w, the retained rows of tile w+1 stream into the staging
+// buffer without passing through registers, so the global-load latency (the dominant stall of the plain kernel:
+// ncu long_scoreboard) is hidden behind the FFT.  One CTA per SM: 4 columns x (work 139.5 KB + staging 87.3 KB) at N = 2048.
+// ------------------------------------------------------------------------------------
+enum { YMUL_ONE = 0, YMUL_IL = 1, YMUL_NEG_IL = 2, YMUL_L2 = 3 };
+struct SimpleJobs {
+    const double2* src[8];  // source spectral field of each job ([l][kr_pad])
+    int mul[8];
+};
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__host__ __device__ constexpr long long ypass_stage_smem(int N, int TK) { return (long long)N * TK * 16; }  // upper bound (all rows)
+
+template <int N, int TK>
+__global__ void __launch_bounds__(TK* group_size(N), 1)
+    ypass_inv_prefetch_kernel(SimpleJobs jobs, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
+    extern __shared__ double smem[];
+    constexpr int G = group_size(N), NP = col_stride(N, TK), NT = TK * G;
+    const int tid = threadIdx.x;
+    const int c = tid % TK, g = tid / TK;
+    double* re = smem + c * NP;
+    double* im = smem + (TK + c) * NP;
+    double2* stg = reinterpret_cast<double2*>(smem + 2 * TK * NP);   // [retained row][TK]
+    const int ntiles = (L.kr_keep + TK - 1) / TK;
+    const int nz = L.lz1 - L.lz0, rows = L.ny - nz;
+    const int nwork = ntiles * njobs;
+    auto prefetch = [&](int w) {
+        const int job = w / ntiles, kr0 = (w % ntiles) * TK;
+        const double2* src = jobs.src[job];
+        for (int ch = tid; ch < rows * TK; ch += NT) {
+            const int r = ch / TK, cc = ch - r * TK;
+            const int l = r < L.lz0 ? r : r + nz;
+            // columns beyond kr_keep inside the padded row are zero in every stored field: safe to copy
+            cp_async16(&stg[ch], &src[(long long)l * L.kr_pad + kr0 + cc]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    int w = blockIdx.x;
+    if (w < nwork) prefetch(w);
+    for (; w < nwork; w += gridDim.x) {
+        const int job = w / ntiles, kr = (w % ntiles) * TK + c;
+        const int mul = jobs.mul[job];
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int l = g + m * G;
+            v[m] = make_double2(0.0, 0.0);
+            if (l_retained(L, l)) {
+                const int r = l < L.lz0 ? l : l - nz;
+                const double2 a = stg[r * TK + c];
+                const double lw = wave_l(L, l);
+                v[m] = mul == YMUL_ONE ? a : mul == YMUL_IL ? make_double2(-lw * a.y, lw * a.x)
+                     : mul == YMUL_NEG_IL ? make_double2(lw * a.y, -lw * a.x) : make_double2(lw * lw * a.x, lw * lw * a.y);
+            }
+        }
+        __syncthreads();                       // staging consumed: the next tile may stream in
+        if (w + (int)gridDim.x < nwork) prefetch(w + gridDim.x);
+        block_fft_regs<N, +1>(v, re, im, g, tw);
+        if (kr < L.kr_keep) {
+            double2* o = out + (long long)job * L.vs + kr;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) o[(long long)(g + m * G) * L.kr_pad] = v[m];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // y-pass, forward direction, with combination into output variables.
 // Combiner:  int nin(int var); int src(int var, int i);
 //            double2 apply(int var, int i, double2 v, double kw, double lw)
@@ -137,6 +210,79 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// y-pass, forward direction, with the same asynchronous prefetch.  All N rows of a product column are non-zero and the
+// staging buffer only holds `rows_s` of them (1436 of 2048 at N = 2048, TK = 4): rows >= rows_s are loaded directly, issued
+// before the wait on the staged part so that both latencies overlap.
+// ------------------------------------------------------------------------------------
+template <int N, int TK, class Combiner>
+__global__ void __launch_bounds__(TK* group_size(N), 1)
+    ypass_fwd_prefetch_kernel(Combiner cb, SpecLayout L, int nvars, int rows_s, const double2* __restrict__ H, double2* __restrict__ out,
+                              const double2* __restrict__ tw) {
+    extern __shared__ double smem[];
+    constexpr int G = group_size(N), NP = col_stride(N, TK), NT = TK * G;
+    const int tid = threadIdx.x;
+    const int c = tid % TK, g = tid / TK;
+    double* re = smem + c * NP;
+    double* im = smem + (TK + c) * NP;
+    double2* stg = reinterpret_cast<double2*>(smem + 2 * TK * NP);   // [row < rows_s][TK]
+    const int ntiles = (L.kr_keep + TK - 1) / TK;
+    const int nwork = ntiles * nvars;
+    auto prefetch = [&](int w, int i_in) {
+        const int var = w / ntiles, kr0 = (w % ntiles) * TK;
+        const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr0;
+        for (int ch = tid; ch < rows_s * TK; ch += NT) {
+            const int r = ch / TK, cc = ch - r * TK;
+            cp_async16(&stg[ch], &h[(long long)r * L.kr_pad + cc]);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    int w = blockIdx.x, i_in = 0;
+    if (w < nwork) prefetch(w, 0);
+    while (w < nwork) {
+        const int var = w / ntiles, kr = (w % ntiles) * TK + c;
+        const double kw = kr * L.dk;
+        const bool col_ok = kr < L.kr_keep;
+        const int nin = cb.nin(var);
+        const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr;
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {           // rows outside the staging buffer: direct, issued first
+            const int y = g + m * G;
+            v[m] = make_double2(0.0, 0.0);
+            if (y >= rows_s && col_ok) v[m] = h[(long long)y * L.kr_pad];
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int y = g + m * G;
+            if (y < rows_s) v[m] = stg[y * TK + c];
+        }
+        __syncthreads();                         // staging consumed
+        int wn = w, in = i_in + 1;               // next FFT task of this CTA
+        if (in >= nin) { wn = w + gridDim.x; in = 0; }
+        if (wn < nwork) prefetch(wn, in);
+        block_fft_regs<N, -1>(v, re, im, g, tw);
+        if (col_ok) {
+            double2* o = out + (long long)var * L.vs + kr;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int l = g + m * G;
+                if (!l_retained(L, l)) continue;
+                double2 r = cb.apply(var, i_in, v[m], kw, wave_l(L, l));
+                const double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
+                                              : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                r.x += prev.x;
+                r.y += prev.y;
+                o[(long long)l * L.kr_pad] = r;
+            }
+        }
+        w = wn;
+        i_in = in;
     }
 }
 

@@ -238,6 +238,20 @@ __global__ void __launch_bounds__(256) diag_stage_kernel(StageArgs a, SpecLayout
     }
 }
 
+// ---------------------------------------------------------------- streamfunction for the packet snapshot
+// psih[l][kr] = PsiLoader::psi_of(...)  (get_streamfunction!, rsw/RSWRaytracingDriver.jl:56-67 and the QG variants), materialised
+// once so that the three y-transform jobs of the snapshot read one plain field (prefetchable, see passes.cuh)
+__global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, double2* __restrict__ psih) {
+    const int nlk = L.ny - (L.lz1 - L.lz0);
+    const long long total = (long long)nlk * L.kr_keep;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
+        const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
+        const long long off = (long long)l * L.kr_pad + kr;
+        psih[off] = ld.psi_of(kr * L.dk, wave_l(L, l), off);
+    }
+}
+
 // ---------------------------------------------------------------- spectral diagnostics (parseval-weighted sums)
 // value(kr,l) per `which`, summed with weights 1 (kr = 0, Nyquist) / 2 (parsevalsum / parsevalsum2 of FourierFlows)
 enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3 };

@@ -163,7 +163,7 @@ class Problem:
 
     def profile_report(self):
         out = {}
-        for i in range(11):
+        for i in range(13):
             ms, n, name = C.c_double(), C.c_longlong(), C.c_char_p()
             check(lib().swrt_flow_profile_get(self._h, i, C.byref(ms), C.byref(n), C.byref(name)))
             if n.value:
