@@ -109,6 +109,7 @@ struct RswXOp {
 struct RswCombiner {
     int modified;
     double c2;
+    __device__ __forceinline__ int var_of(int slot) const { return slot == 0 ? 2 : slot - 1; }   // eta (two inputs) first
     __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int var) const { return var == 2 ? 2 : (modified ? 2 : 1); }
     __device__ __forceinline__ int src(int var, int i) const { return var == 2 ? 2 + i : (i == 0 ? var : 4); }
@@ -191,6 +192,7 @@ struct LindborgXOp {
 };
 
 struct NegateCombiner {  // N_var = -P_var
+    __device__ __forceinline__ int var_of(int slot) const { return slot; }
     __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int) const { return 1; }
     __device__ __forceinline__ int src(int var, int) const { return var; }
@@ -262,6 +264,7 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
 };
 
 struct QgCombiner {  // N_layer = -i l F[psi_x q] + i k F[psi_y q]
+    __device__ __forceinline__ int var_of(int slot) const { return slot; }
     __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
     __device__ __forceinline__ int nin(int) const { return 2; }
     __device__ __forceinline__ int src(int var, int i) const { return 2 * var + i; }
@@ -374,6 +377,7 @@ struct TyCombiner {
     const double2* sol;
     long long vs;
     double Ro;
+    __device__ __forceinline__ int var_of(int slot) const { return slot; }
     __device__ __forceinline__ int nin(int var) const { return var == 0 ? 4 : (var == 3 ? 1 : 2); }
     __device__ __forceinline__ int src(int var, int i) const { return var == 0 ? i : (var == 1 ? 4 + i : (var == 2 ? 6 + i : 8)); }
     __device__ __forceinline__ double2 apply(int var, int i, double2 v, double kw, double lw) const {

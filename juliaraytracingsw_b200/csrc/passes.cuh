@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
 // Combiner:  int nin(int var); int src(int var, int i);
 //            double2 apply(int var, int i, double2 v, double kw, double lw)
 //            double2 init(int var, double kw, double lw, long long off)      (terms of N that are linear in the state)
+//            int var_of(int slot)      (processing order: variables with more inputs first)
 // out[var][l][kr] = init + sum_i apply(var, i, FFT_y(H[src(var,i)])[kr, l])
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
     double* im = smem + (TK + c) * NP;
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     for (int w = blockIdx.x; w < ntiles * nvars; w += gridDim.x) {
-        const int var = w / ntiles, kr = (w % ntiles) * TK + c;
+        const int var = cb.var_of(w / ntiles), kr = (w % ntiles) * TK + c;   // heaviest variables first (static balance)
         const double kw = kr * L.dk;
         const bool col_ok = kr < L.kr_keep;
         double2* o = out + (long long)var * L.vs + kr;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     const int nwork = ntiles * nvars;
     auto prefetch = [&](int w, int i_in) {
-        const int var = w / ntiles, kr0 = (w % ntiles) * TK;
+        const int var = cb.var_of(w / ntiles), kr0 = (w % ntiles) * TK;
         const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr0;
         for (int ch = tid; ch < rows_s * TK; ch += NT) {
             const int r = ch / TK, cc = ch - r * TK;
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     int w = blockIdx.x, i_in = 0;
     if (w < nwork) prefetch(w, 0);
     while (w < nwork) {
-        const int var = w / ntiles, kr = (w % ntiles) * TK + c;
+        const int var = cb.var_of(w / ntiles), kr = (w % ntiles) * TK + c;
         const double kw = kr * L.dk;
         const bool col_ok = kr < L.kr_keep;
         const int nin = cb.nin(var);
