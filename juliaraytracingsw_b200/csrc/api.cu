@@ -73,6 +73,7 @@ struct swrt_flow {
     int slot_map[2] = {0, 1};               // slot (0 = old, 1 = new) -> array
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
+    unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
     int ring = 0;
     double t = 0.0;
     long long step = 0, launches = 0;
@@ -233,7 +234,7 @@ static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
     cudaError_t e;
     { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_FIELD_B); SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->st)); }
+    { ProfScope ps(h, K_FIELD_B); SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -257,7 +258,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
-    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red);
+    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -325,6 +326,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
+    CKB(cudaMalloc(&h->sched, sizeof(unsigned) * 4)); CKB(cudaMemset(h->sched, 0, sizeof(unsigned) * 4));
     for (int lev = 0; lev < 2; ++lev) {
         CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
         CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
@@ -451,7 +453,7 @@ static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
     cudaError_t e;
     { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, state, h->G, L, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->st)); }
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->sched, h->st)); }
     CK(e);
     { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, state, h->H, Nout, L, h->tw_y, h->st)); }
     CK(e);
@@ -655,7 +657,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     }
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, h->G, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }

@@ -26,15 +26,16 @@ cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, double2* G_, 
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched,
+                                    cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1}, L, tw, st);
-        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1}, L, tw, st);
-        case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, st);
-        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc}, L, tw, st);
-        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc}, L, tw, st);
-        case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N>{G_, H, sc}, L, tw, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1}, L, tw, sched, st);
+        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1}, L, tw, sched, st);
+        case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc}, L, tw, sched, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc}, L, tw, sched, st);
+        case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -55,9 +56,10 @@ cudaError_t Launch<SWRT_N>::field_stage_a(const FieldLoader& ld, const SpecLayou
     return ypass_inv(ld, L, 1, G_, tw, st);
 }
 template <>
-cudaError_t Launch<SWRT_N>::field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
+                                          cudaStream_t st) {
     C2ROp<SWRT_N> op{G_, out, 1.0 / ((double)L.nx * (double)L.ny)};
-    return xpass(op, L, tw, st);
+    return xpass(op, L, tw, sched, st);
 }
 template <>
 cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw,
@@ -71,9 +73,10 @@ cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih
     return ypass_inv(ld, L, 3, G_, tw, st);
 }
 template <>
-cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
+                                         cudaStream_t st) {
     SnapshotXOp<SWRT_N> op{G_, out, 1.0 / ((double)L.nx * (double)L.ny)};
-    return xpass(op, L, tw, st);
+    return xpass(op, L, tw, sched, st);
 }
 
 }  // namespace swrt

@@ -590,25 +590,25 @@ struct Launch {
         return cudaGetLastError();
     }
     template <class Op>
-    static cudaError_t xpass(const Op& op, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+    static cudaError_t xpass(const Op& op, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st) {
         auto k = xpass_kernel<N, Op>;
         constexpr size_t smem = (size_t)xpass_smem(N, Op::NBUF);
         int mc = 1;
         cudaError_t e = prep(k, smem, G, &mc);
         if (e != cudaSuccess) return e;
-        k<<<L.ny < mc ? L.ny : mc, G, smem, st>>>(op, L, tw);
+        k<<<L.ny < mc ? L.ny : mc, G, smem, st>>>(op, L, tw, sched);
         return cudaGetLastError();
     }
 
     // concrete entry points (explicitly specialised per size in inst.cu); `model` = SWRT_* model id
     static cudaError_t stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
-    static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
-    static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
-    static cudaError_t snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
 };
 
 }  // namespace swrt

@@ -380,16 +380,34 @@ struct XCtx {
     }
 };
 
+// Rows are handed out dynamically (one atomic per row): 2048 rows over 444 resident CTAs would otherwise leave an
+// 8 % tail (5 rounds for 4.6 rounds of work).  `sched` = {next row, finished CTAs}; the last CTA re-arms it for the next launch.
 template <int N, class Op>
-__global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N, Op::NBUF), group_size(N))) xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw) {
+__global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N, Op::NBUF), group_size(N)))
+    xpass_kernel(Op op, SpecLayout L, const double2* __restrict__ tw, unsigned* __restrict__ sched) {
     extern __shared__ double smem[];
+    __shared__ int next_row;
     XCtx<N> cx;
     cx.smem = smem;
     cx.tw = tw;
     cx.g = threadIdx.x;
     cx.kr_keep = L.kr_keep;
     cx.dk = L.dk;
-    for (int y = blockIdx.x; y < L.ny; y += gridDim.x) op.row(cx, L, y);
+    int y = blockIdx.x;                      // first row: static
+    while (y < L.ny) {
+        if (threadIdx.x == 0) next_row = (int)(gridDim.x + atomicAdd(&sched[0], 1u));
+        op.row(cx, L, y);                    // (contains barriers: next_row is visible afterwards)
+        __syncthreads();
+        y = next_row;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+        }
+    }
 }
 
 }  // namespace swrt
