@@ -85,11 +85,15 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag);
  * and layer mean (psi1+psi2)/2 (raytracing/TwoLayerRaytracing.jl:122) */
 enum { SWRT_PSI_RSW_BALANCED = 0, SWRT_PSI_SWQG = 1, SWRT_PSI_TWOLAYER_BAROCLINIC = 2, SWRT_PSI_TWOLAYER_MEAN = 3 };
 int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot);
+/* which node data velocity_snapshot produces (SWRT_INTERP_*): 5 fields u,v,ux,uy,vx or 7 fields (+ uxy, vxy); packets created with
+ * the same interpolant read them.  snapshot_fields returns 5 or 7 (the third extent of get/set_snapshot arrays). */
+int swrt_flow_set_interp(swrt_flow* h, int interp);
+int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields);
 /* old_velocity = new_velocity; old_grad_v = new_grad_v (raytracing/RaytracingDriver.jl:269-270).
  * alias != 0 reproduces the reference's rebinding (both names then refer to the same buffers);
  * alias == 0 swaps the two slots. */
 int swrt_flow_swap_snapshots(swrt_flow* h, int alias);
-/* Array(u), Array(v), ... of a snapshot: out is float64 (nx, ny, 5) column-major = u, v, ux, uy, vx */
+/* Array(u), Array(v), ... of a snapshot: out is float64 (nx, ny, nfields) column-major = u, v, ux, uy, vx[, uxy, vxy] */
 int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host);
 /* load a snapshot from host fields (same layout) -- used for steady/analytic background flows
  * (raytracing/SteadyRaytracing.jl) and by tests */
@@ -106,7 +110,9 @@ int swrt_flow_profile_get(swrt_flow* h, int id, double* ms_total, long long* cou
 /* number of kernels this handle has launched so far */
 int swrt_flow_launch_count(swrt_flow* h, long long* n);
 
-enum { SWRT_INTERP_BILINEAR = 0 };
+/* BILINEAR = the reference's texture sampling (raytracing/GPURaytracing.jl:118-127); HERMITE_BICUBIC = u, v from (f, f_x, f_y, f_xy)
+ * node data (utils/CUDAInterpolations.jl:71-108) with the analytic gradient of the interpolant in dk/dt */
+enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1 };
 enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };
 typedef struct swrt_packets_desc {
     long long n;            /* Npackets */

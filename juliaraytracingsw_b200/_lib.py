@@ -57,6 +57,8 @@ SIGNATURES = {
     "swrt_flow_has_nan": (_I, [_P, _PI]),
     "swrt_flow_velocity_snapshot": (_I, [_P, _I, _I]),
     "swrt_flow_swap_snapshots": (_I, [_P, _I]),
+    "swrt_flow_set_interp": (_I, [_P, _I]),
+    "swrt_flow_snapshot_fields": (_I, [_P, _PI]),
     "swrt_flow_get_snapshot": (_I, [_P, _I, _P]),
     "swrt_flow_set_snapshot": (_I, [_P, _I, _P]),
     "swrt_flow_timer_start": (_I, [_P]),

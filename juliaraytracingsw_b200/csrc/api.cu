@@ -71,6 +71,7 @@ struct swrt_flow {
     double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
     double* snap[2] = {nullptr, nullptr};   // S[ny][nx][6] per time level (snapshot_layout.cuh)
     int slot_map[2] = {0, 1};               // slot (0 = old, 1 = new) -> array
+    int interp = 0;                         // snapshot node data: 0 bilinear (5 fields / 48 B), 1 Hermite bicubic (7 fields / 64 B)
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
     unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
@@ -328,8 +329,8 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
     CKB(cudaMalloc(&h->sched, sizeof(unsigned) * 4)); CKB(cudaMemset(h->sched, 0, sizeof(unsigned) * 4));
     for (int lev = 0; lev < 2; ++lev) {
-        CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
-        CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP_STRIDE));
+        CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));   // sized for either node record
+        CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));
     }
     CKB(upload_twiddles(d.nx, &h->tw_x));
     CKB(upload_twiddles(d.ny, &h->tw_y));
@@ -657,8 +658,20 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     }
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, h->G, h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp, L, h->tw_x, h->sched, h->st)); }
     CK(e);
+    return SWRT_OK;
+}
+
+int swrt_flow_set_interp(swrt_flow* h, int interp) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (interp != SWRT_INTERP_BILINEAR && interp != SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    h->interp = interp;
+    return SWRT_OK;
+}
+int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields) {
+    if (!h || !nfields) return fail(SWRT_ERR_ARG, "null pointer");
+    *nfields = h->interp ? SNAP3_NC : SNAP_NC;
     return SWRT_OK;
 }
 
@@ -673,10 +686,11 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const long long n = (long long)h->d.nx * h->d.ny;
+    const int nc = h->interp ? SNAP3_NC : SNAP_NC, stride = h->interp ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(double) * n * SNAP_NC));
-    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, tmp); }
-    cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * SNAP_NC, cudaMemcpyDeviceToHost, h->st);
+    CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
+    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, nc, stride, tmp); }
+    cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     cudaFree(tmp);
     CK(e);
@@ -687,12 +701,13 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const long long n = (long long)h->d.nx * h->d.ny;
+    const int nc = h->interp ? SNAP3_NC : SNAP_NC, stride = h->interp ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(double) * n * SNAP_NC));
-    cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * SNAP_NC, cudaMemcpyHostToDevice, h->st);
+    CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
+    cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * nc, cudaMemcpyHostToDevice, h->st);
     if (e == cudaSuccess) {
         ProfScope ps(h, K_OTHER);
-        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, n, h->snap[h->slot_map[slot]]);
+        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, n, nc, stride, h->snap[h->slot_map[slot]]);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
@@ -759,7 +774,8 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
     if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
-    if (desc->interp != SWRT_INTERP_BILINEAR) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
+    if (desc->interp != SWRT_INTERP_BILINEAR && desc->interp != SWRT_INTERP_HERMITE_BICUBIC)
+        return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
     if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
     if (desc->sort_every < 0) return fail(SWRT_ERR_ARG, "sort_every must be >= 0");
     CK(cudaSetDevice(flow->d.device));
@@ -886,6 +902,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
         int rc = sort_packets(p);
         if (rc) return rc;
     }
+    if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d (swrt_flow_set_interp)", p->d.interp, f->interp);
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
     const double *So = f->snap[f->slot_map[0]], *Sn = f->snap[f->slot_map[1]];
     const long long n = p->d.n;
@@ -893,7 +910,8 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
-      if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
@@ -908,6 +926,11 @@ int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_hos
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
+    if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
+    if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
+        ProfScope ps(f, K_SAMPLE);
+        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    } else
     { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));

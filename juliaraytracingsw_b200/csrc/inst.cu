@@ -73,10 +73,11 @@ cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih
     return ypass_inv(ld, L, 3, G_, tw, st);
 }
 template <>
-cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
+cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched,
                                          cudaStream_t st) {
-    SnapshotXOp<SWRT_N> op{G_, out, 1.0 / ((double)L.nx * (double)L.ny)};
-    return xpass(op, L, tw, sched, st);
+    const double s1 = 1.0 / ((double)L.nx * (double)L.ny);
+    if (cubic) return xpass(SnapshotCubicXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);
+    return xpass(SnapshotXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);
 }
 
 }  // namespace swrt

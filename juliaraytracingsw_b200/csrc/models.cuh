@@ -501,6 +501,39 @@ struct SnapshotXOp {
     }
 };
 
+// Hermite-bicubic node data from the same three y-jobs (G0 = psi, G1 = -i l psi, G2 = l^2 psi):
+// u = G1, v = i k G0, ux = i k G1, uy = G2, vx = -k^2 G0, uxy = i k G2, vxy = psi_xxy = k^2 G1
+template <int N>
+struct SnapshotCubicXOp {
+    static constexpr int NBUF = 2;
+    const double2* G;  // [3][ny][kr_pad]
+    double* out;       // [ny][nx][8]
+    double s1;
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G;
+        const long long ro = (long long)y * L.kr_pad;
+        const double2 *Gp = G + ro, *Gu = G + L.vs + ro, *Guy = G + 2 * L.vs + ro;
+        double2* o = reinterpret_cast<double2*>(out + (long long)y * N * SNAP3_STRIDE);
+        double2 v[16];
+        auto put = [&](int slot) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) o[(long long)(cx.g + m * Gt) * (SNAP3_STRIDE / 2) + slot] = make_double2(s1 * v[m].x, s1 * v[m].y);
+        };
+        cx.template load_pair<MUL_ONE, MUL_IK>(1, Gu, Gp);
+        cx.ifft_regs_out(1, v);
+        put(0);                                          // u, v
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
+        cx.ifft_regs_out(1, v);
+        put(1);                                          // ux, uy
+        cx.template load_pair<MUL_MK2, MUL_IK>(1, Gp, Guy);
+        cx.ifft_regs_out(1, v);
+        put(2);                                          // vx, uxy
+        cx.template load_pair<MUL_K2, MUL_ZERO>(1, Gu, nullptr);
+        cx.ifft_regs_out(1, v);
+        put(3);                                          // vxy, 0
+    }
+};
+
 // ---------------------------------------------------------------- per-size launchers
 #ifndef SWRT_TK_LARGE
 #define SWRT_TK_LARGE 4   // columns per y-pass CTA for N >= 2048 (tuning knob)
@@ -608,7 +641,7 @@ struct Launch {
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
-    static cudaError_t snap_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
 };
 
 }  // namespace swrt

@@ -228,6 +228,131 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* 
     xk[3 * n + i] = s[3];
 }
 
+// ---------------------------------------------------------------- Hermite-bicubic mode
+// u, v interpolated from (f, f_x, f_y, f_xy) node data (utils/CUDAInterpolations.jl:39-53,71-108); the gradient that enters
+// dk/dt is the analytic gradient of that interpolant.  Node record (snapshot_layout.cuh): u, v, ux, uy, vx, uxy, vxy, pad.
+__device__ __forceinline__ double hcubic(double al, double f0, double f1, double m0, double m1) {
+    return f0 + m0 * al + (-3.0 * f0 + 3.0 * f1 - 2.0 * m0 - m1) * (al * al) + (2.0 * f0 - 2.0 * f1 + m0 + m1) * (al * al * al);
+}
+__device__ __forceinline__ double hdcubic(double al, double f0, double f1, double m0, double m1) {
+    return m0 + 2.0 * (-3.0 * f0 + 3.0 * f1 - 2.0 * m0 - m1) * al + 3.0 * (2.0 * f0 - 2.0 * f1 + m0 + m1) * (al * al);
+}
+// value and gradient of the bicubic of one scalar from its four corner records (f, fx, fy, fxy)
+__device__ __forceinline__ void hermite2d(const double (&f)[4], const double (&fx)[4], const double (&fy)[4], const double (&fxy)[4],
+                                          double a, double b, double dx, double dy, double& val, double& ddx, double& ddy) {
+    // corner order 00, 10, 01, 11
+    const double f0 = hcubic(a, f[0], f[1], fx[0] * dx, fx[1] * dx), f1 = hcubic(a, f[2], f[3], fx[2] * dx, fx[3] * dx);
+    const double g0 = hcubic(a, fy[0] * dy, fy[1] * dy, fxy[0] * (dx * dy), fxy[1] * (dx * dy));
+    const double g1 = hcubic(a, fy[2] * dy, fy[3] * dy, fxy[2] * (dx * dy), fxy[3] * (dx * dy));
+    val = hcubic(b, f0, f1, g0, g1);
+    const double d0 = hdcubic(a, f[0], f[1], fx[0] * dx, fx[1] * dx), d1 = hdcubic(a, f[2], f[3], fx[2] * dx, fx[3] * dx);
+    const double e0 = hdcubic(a, fy[0] * dy, fy[1] * dy, fxy[0] * (dx * dy), fxy[1] * (dx * dy));
+    const double e1 = hdcubic(a, fy[2] * dy, fy[3] * dy, fxy[2] * (dx * dy), fxy[3] * (dx * dy));
+    ddx = hcubic(b, d0, d1, e0, e1) / dx;
+    ddy = hdcubic(b, f0, f1, g0, g1) / dy;
+}
+// out = u, v, ux, uy, vx of one level at (i0 + a, j0 + b)
+__device__ __forceinline__ void sample_hermite5(const double* __restrict__ S, const PacketGrid& g, int i0, int i1, int j0, int j1,
+                                                double a, double b, double (&out)[5]) {
+    const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+    double u[4], v[4], ux[4], uy[4], vx[4], uxy[4], vxy[4], vy[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double2* q = reinterpret_cast<const double2*>(S + pt[c] * SNAP3_STRIDE);
+        const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+        u[c] = q0.x; v[c] = q0.y; ux[c] = q1.x; uy[c] = q1.y; vx[c] = q2.x; uxy[c] = q2.y; vxy[c] = q3.x;
+        vy[c] = -q1.x;
+    }
+    double dvy;
+    hermite2d(u, ux, uy, uxy, a, b, g.dx, g.dy, out[0], out[2], out[3]);
+    hermite2d(v, vx, vy, vxy, a, b, g.dx, g.dy, out[1], out[4], dvy);
+}
+
+__device__ __forceinline__ void ray_rhs_cubic(const double (&s)[4], double sign, double alpha, const double* __restrict__ So,
+                                              const double* __restrict__ Sn, const PacketGrid& g, const RayParams& p, double (&d)[4]) {
+    int i0, i1, j0, j1;
+    double a, b;
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
+    double W[5];
+    if (wn == 0.0) {
+        double o[5];
+        sample_hermite5(So, g, i0, i1, j0, j1, a, b, o);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) W[c] = wo * o[c];
+    } else if (wo == 0.0) {
+        double nw[5];
+        sample_hermite5(Sn, g, i0, i1, j0, j1, a, b, nw);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) W[c] = wn * nw[c];
+    } else {
+        double o[5], nw[5];
+        sample_hermite5(So, g, i0, i1, j0, j1, a, b, o);
+        sample_hermite5(Sn, g, i0, i1, j0, j1, a, b, nw);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) W[c] = wo * o[c] + wn * nw[c];
+    }
+    const double k = s[2], l = s[3];
+    const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));
+    d[0] = W[0] + cg * k;
+    d[1] = W[1] + cg * l;
+    d[2] = -(W[2] * k + W[4] * l);
+    d[3] = -(W[3] * k - W[2] * l);
+}
+
+__global__ void __launch_bounds__(128, 4) raytrace_rk4_cubic_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
+                                                                    const double* __restrict__ So, const double* __restrict__ Sn,
+                                                                    PacketGrid g, RayParams p) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    const double sg = sign[i];
+    const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
+    for (int it = 0; it < p.nsub; ++it) {
+        const double t = p.t0 + it * h;
+        double k[4], acc[4], y[4];
+        ray_rhs_cubic(s, sg, (t - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        ray_rhs_cubic(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        ray_rhs_cubic(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+        const double a4 = it == p.nsub - 1 ? 1.0 : (t + h - p.t0) * inv_span;
+        ray_rhs_cubic(y, sg, a4, So, Sn, g, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+    }
+    xk[i] = s[0];
+    xk[n + i] = s[1];
+    xk[2 * n + i] = s[2];
+    xk[3 * n + i] = s[3];
+}
+
+__global__ void __launch_bounds__(128) sample_cubic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
+                                                           const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
+                                                           double* __restrict__ Gd) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int i0, i1, j0, j1;
+    double a, b, Sv[5];
+    cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    sample_hermite5(S, g, i0, i1, j0, j1, a, b, Sv);
+    const long long o = idx[i];
+    U[o] = Sv[0];
+    U[n + o] = Sv[1];
+    if (Gd) {
+        Gd[o] = Sv[2];
+        Gd[n + o] = Sv[3];
+        Gd[2 * n + o] = Sv[4];
+        Gd[3 * n + o] = -Sv[2];
+    }
+}
+
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                      const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
@@ -347,18 +472,15 @@ __global__ void unpermute_kernel(const double* __restrict__ xk, const unsigned* 
 }
 
 // snapshot half <-> planar (nx, ny, 5) host layout staging
-__global__ void snap_to_planar_kernel(const double* __restrict__ S, long long npts, double* __restrict__ planar) {
+__global__ void snap_to_planar_kernel(const double* __restrict__ S, long long npts, int nc, int stride, double* __restrict__ planar) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= npts) return;
-#pragma unroll
-    for (int c = 0; c < SNAP_NC; ++c) planar[c * npts + i] = S[i * SNAP_STRIDE + c];
+    for (int c = 0; c < nc; ++c) planar[c * npts + i] = S[i * stride + c];
 }
-__global__ void planar_to_snap_kernel(const double* __restrict__ planar, long long npts, double* __restrict__ S) {
+__global__ void planar_to_snap_kernel(const double* __restrict__ planar, long long npts, int nc, int stride, double* __restrict__ S) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= npts) return;
-#pragma unroll
-    for (int c = 0; c < SNAP_NC; ++c) S[i * SNAP_STRIDE + c] = planar[c * npts + i];
-    S[i * SNAP_STRIDE + SNAP_NC] = 0.0;
+    for (int c = 0; c < stride; ++c) S[i * stride + c] = c < nc ? planar[c * npts + i] : 0.0;
 }
 
 }  // namespace swrt

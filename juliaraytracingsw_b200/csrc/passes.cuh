@@ -291,12 +291,13 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
 // x-pass helpers: one CTA of G = N/16 threads owns NB complex work buffers of length N.
 // Two real fields travel through one complex transform: z = a + i b.
 // ------------------------------------------------------------------------------------
-enum { MUL_ONE = 0, MUL_IK = 1, MUL_MK2 = 2, MUL_ZERO = 3 };
+enum { MUL_ONE = 0, MUL_IK = 1, MUL_MK2 = 2, MUL_ZERO = 3, MUL_K2 = 4 };
 
 template <int M>
 __device__ __forceinline__ double2 apply_mul(double2 v, double kw) {
     if (M == MUL_IK) return make_double2(-kw * v.y, kw * v.x);
     if (M == MUL_MK2) return make_double2(-kw * kw * v.x, -kw * kw * v.y);
+    if (M == MUL_K2) return make_double2(kw * kw * v.x, kw * kw * v.y);
     return v;
 }
 

@@ -6,4 +6,7 @@
 namespace swrt {
 constexpr int SNAP_NC = 5;      // u, v, ux, uy, vx   (vy = -ux)
 constexpr int SNAP_STRIDE = 6;  // doubles per grid point of one level
+// Hermite-bicubic mode (utils/CUDAInterpolations.jl:71-108): node data (u, v, ux, uy, vx, uxy, vxy, pad), 64 B per point
+constexpr int SNAP3_NC = 7;
+constexpr int SNAP3_STRIDE = 8;
 }  // namespace swrt

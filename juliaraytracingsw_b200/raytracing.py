@@ -15,6 +15,7 @@ from ._lib import PacketsDesc, check, lib
 
 PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2, 3
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
+INTERP_BILINEAR, INTERP_HERMITE_BICUBIC = 0, 1
 
 
 class Velocity:
@@ -25,7 +26,9 @@ class Velocity:
 
     def _arr(self):
         g = self.prob.grid
-        out = np.empty((g.nx, g.ny, 5), dtype=np.float64, order="F")
+        nf = C.c_int()
+        check(lib().swrt_flow_snapshot_fields(self.prob._h, C.byref(nf)))
+        out = np.empty((g.nx, g.ny, nf.value), dtype=np.float64, order="F")
         check(lib().swrt_flow_get_snapshot(self.prob._h, self.slot, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -48,9 +51,17 @@ def get_velocity_info(prob, slot, psi_kind=PSI_RSW_BALANCED):
     return Velocity(prob, slot), VelocityGradient(prob, slot)
 
 
+def set_interpolation(prob, interp):
+    """Choose the node data the flow's snapshots hold: INTERP_BILINEAR (5 fields) or INTERP_HERMITE_BICUBIC (7 fields)."""
+    check(lib().swrt_flow_set_interp(prob._h, int(interp)))
+
+
 def set_velocity_info(prob, slot, fields):
-    """Load (nx, ny, 5) = u, v, ux, uy, vx host fields into a slot (steady/analytic flows)."""
+    """Load (nx, ny, 5) = u, v, ux, uy, vx (or (nx, ny, 7) with uxy, vxy in Hermite mode) host fields into a slot."""
     a = np.asfortranarray(fields, dtype=np.float64)
+    nf = C.c_int()
+    check(lib().swrt_flow_snapshot_fields(prob._h, C.byref(nf)))
+    assert a.shape == (prob.grid.nx, prob.grid.ny, nf.value), a.shape
     check(lib().swrt_flow_set_snapshot(prob._h, slot, a.ctypes.data_as(C.c_void_p)))
 
 
@@ -62,9 +73,9 @@ def swap_snapshots(prob, alias=False):
 class Packets:
     """Device-resident wave packets = `create_template_ode(packets)` + the packet arrays."""
 
-    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16):
+    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16, interp=INTERP_BILINEAR):
         self.prob, self.n = prob, int(n)
-        d = PacketsDesc(n=self.n, interp=0, nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
+        d = PacketsDesc(n=self.n, interp=int(interp), nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
         self._h = C.c_void_p()
         check(lib().swrt_packets_create(C.byref(d), prob._h, C.byref(self._h)))
 

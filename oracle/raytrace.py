@@ -97,14 +97,61 @@ def sample_bicubic_hermite(f, fx, fy, fxy, x, y, grid):
     return _cubic(b, f0, f1, g0, g1)
 
 
+def _dcubic(al, f0, f1, m0, m1):
+    """d/d(alpha) of the Hermite cubic above."""
+    return m0 + 2 * (-3 * f0 + 3 * f1 - 2 * m0 - m1) * al + 3 * (2 * f0 - 2 * f1 + m0 + m1) * al ** 2
+
+
+def get_velocity_info_cubic(psih, grid):
+    """Node data of the Hermite-bicubic mode: u, v, ux, uy, vx, uxy, vxy from a streamfunction (nx, ny, 7)."""
+    k, l = grid.kr, grid.l
+    F5 = get_velocity_info(psih, grid)
+    uxy = grid.irfft2(1j * k * l * l * psih)          # -psi_xyy
+    vxy = grid.irfft2(-1j * k * k * l * psih)         # psi_xxy
+    return np.concatenate([F5, uxy[:, :, None], vxy[:, :, None]], axis=-1)
+
+
+def sample_hermite(F7, x, y, grid):
+    """Hermite-bicubic interpolation of u and v from (f, f_x, f_y, f_xy) node data, utils/CUDAInterpolations.jl:71-108,
+    and the ANALYTIC gradient of the interpolant (our specification of the cubic mode: the gradient that enters
+    dk/dt is consistent with the velocity that enters dx/dt).  Returns (N, 5) = u, v, ux, uy, vx."""
+    i, a = cell_index(x, grid.x[0], grid.dx, grid.nx)
+    j, b = cell_index(y, grid.y[0], grid.dy, grid.ny)
+    i1, j1 = (i + 1) % grid.nx, (j + 1) % grid.ny
+    dx, dy = grid.dx, grid.dy
+    out = np.empty((x.shape[0], 5))
+    defs = ((F7[:, :, 0], F7[:, :, 2], F7[:, :, 3], F7[:, :, 5]),       # u, ux, uy, uxy
+            (F7[:, :, 1], F7[:, :, 4], -F7[:, :, 2], F7[:, :, 6]))      # v, vx, vy = -ux, vxy
+    for n, (f, fx, fy, fxy) in enumerate(defs):
+        c = lambda A, s: (A[i, j] * s, A[i1, j] * s, A[i, j1] * s, A[i1, j1] * s)
+        f00, f10, f01, f11 = c(f, 1.0)
+        x00, x10, x01, x11 = c(fx, dx)
+        y00, y10, y01, y11 = c(fy, dy)
+        m00, m10, m01, m11 = c(fxy, dx * dy)
+        f0, f1 = _cubic(a, f00, f10, x00, x10), _cubic(a, f01, f11, x01, x11)
+        g0, g1 = _cubic(a, y00, y10, m00, m10), _cubic(a, y01, y11, m01, m11)
+        val = _cubic(b, f0, f1, g0, g1)
+        d0, d1 = _dcubic(a, f00, f10, x00, x10), _dcubic(a, f01, f11, x01, x11)
+        e0, e1 = _dcubic(a, y00, y10, m00, m10), _dcubic(a, y01, y11, m01, m11)
+        ddx = _cubic(b, d0, d1, e0, e1) / dx
+        ddy = _dcubic(b, f0, f1, g0, g1) / dy
+        if n == 0:
+            out[:, 0], out[:, 2], out[:, 3] = val, ddx, ddy
+        else:
+            out[:, 1], out[:, 4] = val, ddx
+    return out
+
+
 def rhs(xk, sign, t, t0, t1, F_old, F_new, grid, f, Cg, lerp=LERP_PHYSICAL):
-    """dxkdt of GPURaytracing.jl:32-65.  F_* are (nx, ny, 5) = u, v, ux, uy, vx."""
+    """dxkdt of GPURaytracing.jl:32-65.  F_* are (nx, ny, 5) = u, v, ux, uy, vx (bilinear mode) or (nx, ny, 7) with
+    uxy, vxy appended (Hermite-bicubic mode)."""
     alpha = (t - t0) / (t1 - t0)
     x, y, k, l = xk[:, 0], xk[:, 1], xk[:, 2], xk[:, 3]
     w = sign * np.sqrt(f * f + Cg * Cg * (k * k + l * l))
     cgx, cgy = Cg * Cg * k / w, Cg * Cg * l / w
-    So = sample_bilinear(F_old, x, y, grid)
-    Sn = sample_bilinear(F_new, x, y, grid)
+    sampler = sample_bilinear if F_old.shape[-1] == 5 else sample_hermite
+    So = sampler(F_old, x, y, grid)
+    Sn = sampler(F_new, x, y, grid)
     if lerp == LERP_PHYSICAL:
         W = (1 - alpha) * So + alpha * Sn
     else:
@@ -134,5 +181,5 @@ def raytrace(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, lerp=LERP_PHYS
 def interpolate_velocity(F, pos, grid):
     """interpolate_velocity!/interpolate_gradients! (GPURaytracing.jl:67-109): u,v and
     ux,uy,vx,vy at packet positions.  Returns (N,2), (N,4)."""
-    S = sample_bilinear(F, pos[:, 0], pos[:, 1], grid)
+    S = (sample_bilinear if F.shape[-1] == 5 else sample_hermite)(F, pos[:, 0], pos[:, 1], grid)
     return S[:, 0:2].copy(), np.stack([S[:, 2], S[:, 3], S[:, 4], -S[:, 2]], axis=1)

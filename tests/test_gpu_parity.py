@@ -355,3 +355,38 @@ def test_unsupported_combinations_fail_loudly():
         swrt.Problem(model="RotatingShallowWater", stepper="ETDRK4", nx=64)      # matrix L: FourierFlows steppers need a diagonal L
     with pytest.raises(swrt.SwrtError):
         swrt.Problem(nx=48)                                                      # not a power of two
+
+
+# ------------------------------------------------------------------------------------------------ Hermite-bicubic interpolant
+@pytest.mark.parametrize("nsub", [1, 3])
+def test_hermite_bicubic_mode_parity(nsub):
+    g, p, sol0, c = config2_setup(128)
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 4)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_interpolation(prob, raytracing.INTERP_HERMITE_BICUBIC)
+    prob.sol = sol0
+    vel, _ = raytracing.get_velocity_info(prob, 0)
+    Fo = oray.get_velocity_info_cubic(orsw.get_streamfunction(sol0, g, p), g)
+    got = vel._arr()
+    assert got.shape[-1] == 7
+    for k in range(7):
+        assert rel_l2(got[:, :, k], Fo[:, :, k]) < 1e-12, k
+    flow.stepforward(prob, (), 4)
+    raytracing.get_velocity_info(prob, 1)
+    Fn = oray.get_velocity_info_cubic(orsw.get_streamfunction(sol1, g, p), g)
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 40)
+    xk[:, 0:2] += np.random.default_rng(8).uniform(-20, 20, size=(xk.shape[0], 2))
+    pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=nsub, interp=raytracing.INTERP_HERMITE_BICUBIC)
+    pk.set(xk, sign)
+    t0, t1 = 0.0, 4 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t0, t1))
+    want = oray.raytrace(xk.copy(), sign, t0, t1, Fo, Fn, g, c["f"], c["Cg"], nsub=nsub)
+    assert np.abs(pk.get() - want).max() / np.abs(want).max() < 1e-8
+    assert rel_l2(pk.get(), want) < 1e-11
+    U, G = oray.interpolate_velocity(Fn, want[:, 0:2], g)
+    pk.set(want, sign)
+    np.testing.assert_allclose(raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 1), pk), G, rtol=0, atol=1e-10)
+    # a bilinear packet set on a flow holding Hermite node data must be refused, not silently mis-sampled
+    pk2 = raytracing.Packets(prob, 16, c["f"], c["Cg"])
+    with pytest.raises(swrt.SwrtError):
+        raytracing.raytrace(pk2, None, None, None, None, prob.grid, pk2, c["dt"], (t0, t1))
