@@ -301,6 +301,8 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     L.kr_keep = klo;
     L.kr_pad = (L.kr_keep + 15) / 16 * 16;
     L.vs = (long long)L.ny * L.kr_pad;
+    L.kr_off = 0; L.kr_keep_g = L.kr_keep; L.yrows = L.ny;
+    L.yshift = 0; while ((1 << L.yshift) < L.ny) ++L.yshift;
     L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
     L.f = d.f; L.Cg2 = d.Cg * d.Cg;
     // model constant used by the loaders: Kd2 = f^2/Cg^2 (SWQG, swqg/SWQG.jl:85; RSW balanced psi) or F (two-layer, swqg/TwoLayerQG.jl:79)

@@ -42,12 +42,12 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
 template <>
 cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
-        case MODEL_RSW: return ypass_fwd(RswCombiner{0, L.Cg2}, L, 3, H, Nout, tw, st);
-        case MODEL_RSW_MODIFIED: return ypass_fwd(RswCombiner{1, L.Cg2}, L, 3, H, Nout, tw, st);
-        case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, H, Nout, tw, st);
-        case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, H, Nout, tw, st);
-        case MODEL_TWOLAYERQG: return ypass_fwd(QgCombiner{}, L, 2, H, Nout, tw, st);
-        case MODEL_THOMASYAMADA: return ypass_fwd(TyCombiner{sol, L.vs, L.aux1}, L, 4, H, Nout, tw, st);
+        case MODEL_RSW: return ypass_fwd(RswCombiner{0, L.Cg2}, L, 3, 4, H, Nout, tw, st);
+        case MODEL_RSW_MODIFIED: return ypass_fwd(RswCombiner{1, L.Cg2}, L, 3, 5, H, Nout, tw, st);
+        case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, 3, H, Nout, tw, st);
+        case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, 2, H, Nout, tw, st);
+        case MODEL_TWOLAYERQG: return ypass_fwd(QgCombiner{}, L, 2, 4, H, Nout, tw, st);
+        case MODEL_THOMASYAMADA: return ypass_fwd(TyCombiner{sol, L.vs, L.aux1}, L, 4, 9, H, Nout, tw, st);
     }
     return cudaErrorInvalidValue;
 }

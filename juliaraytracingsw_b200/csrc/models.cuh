@@ -38,7 +38,7 @@ struct RswLoaderA {
 
 // ---------------------------------------------------------------- RSW family, stage B
 // p1 = u ux + v uy, p2 = u vx + v vy, p3 = u eta, p4 = v eta [, p5 = 1.5 - 0.5/(1+eta)^2]
-template <int N, bool MODIFIED>
+template <int N, bool MODIFIED, bool SLAB = false>
 struct RswXOp {
     static constexpr int NBUF = 2;
     const double2* G;  // [5][ny][kr_pad]
@@ -47,9 +47,10 @@ struct RswXOp {
     double s1;         // 1/(nx ny)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const long long ro = (long long)y * L.kr_pad;
-        const double2 *Gu = G + ro, *Gv = G + L.vs + ro, *Ge = G + 2 * L.vs + ro, *Guy = G + 3 * L.vs + ro,
-                      *Gvy = G + 4 * L.vs + ro;
+        const auto Gu = row_ref<SLAB>(L, G, 5, 0, y), Gv = row_ref<SLAB>(L, G, 5, 1, y), Ge = row_ref<SLAB>(L, G, 5, 2, y), Guy = row_ref<SLAB>(L, G, 5, 3, y),
+                   Gvy = row_ref<SLAB>(L, G, 5, 4, y);
+        const RowPlain none{};
+        constexpr int NH = MODIFIED ? 5 : 4;
         // Thread g owns x = g + m N/16 (m = 0..15) of the physical row.  Inverse transforms are loaded through shared
         // memory (Hermitian extension needs k and N-k) but deliver their result in registers (last FFT stage); products
         // are formed there and enter the forward transform's first stage directly.  Buffer 0 only parks u, v at the
@@ -80,8 +81,8 @@ struct RswXOp {
             v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
-        cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, nullptr);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_ref<SLAB>(L, H, NH, 0, y), row_ref<SLAB>(L, H, NH, 1, y));
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, none);
         cx.ifft_regs_out(1, v);                          // eta
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -94,12 +95,12 @@ struct RswXOp {
             v[m] = make_double2(sc * (ur[x] * e), sc * (vr[x] * e));
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + 2 * L.vs + ro, H + 3 * L.vs + ro);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_ref<SLAB>(L, H, NH, 2, y), row_ref<SLAB>(L, H, NH, 3, y));
         if (MODIFIED) {
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = make_double2(p1[m], 0.0);
             cx.fft_regs_in(v, 1);
-            cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 4 * L.vs + ro, nullptr);
+            cx.template store_pair<MUL_ONE, MUL_ZERO>(1, row_ref<SLAB>(L, H, NH, 4, y), none);
         }
     }
 };
@@ -143,7 +144,7 @@ struct LindborgLoaderA {
     }
 };
 
-template <int N>
+template <int N, bool SLAB = false>
 struct LindborgXOp {
     static constexpr int NBUF = 2;
     const double2* G;  // [8][ny][kr_pad]
@@ -151,11 +152,13 @@ struct LindborgXOp {
     double sc;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const long long ro = (long long)y * L.kr_pad;
+        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 8, j, y); };
+        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 3, j, y); };
+        const RowPlain none{};
         double *ur = cx.re(0), *vr = cx.im(0);
         double2 v[16];
         double p1[16];
-        cx.template load_pair<MUL_ONE, MUL_ONE>(1, G + ro, G + L.vs + ro);
+        cx.template load_pair<MUL_ONE, MUL_ONE>(1, Gp(0), Gp(1));
         cx.ifft_regs_out(1, v);                          // ur + i vr
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -163,14 +166,14 @@ struct LindborgXOp {
             ur[x] = v[m].x;
             vr[x] = v[m].y;
         }
-        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 2 * L.vs + ro, G + 3 * L.vs + ro);
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gp(2), Gp(3));
         cx.ifft_regs_out(1, v);                          // ux + i uy
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int x = pad_index(cx.g + m * Gt);
             p1[m] = sc * (ur[x] * v[m].x + vr[x] * v[m].y);
         }
-        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 4 * L.vs + ro, G + 5 * L.vs + ro);
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gp(4), Gp(5));
         cx.ifft_regs_out(1, v);                          // vx + i vy
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -178,8 +181,8 @@ struct LindborgXOp {
             v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + ro, H + L.vs + ro);
-        cx.template load_pair<MUL_IK, MUL_ONE>(1, G + 6 * L.vs + ro, G + 7 * L.vs + ro);
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, Hp(0), Hp(1));
+        cx.template load_pair<MUL_IK, MUL_ONE>(1, Gp(6), Gp(7));
         cx.ifft_regs_out(1, v);                          // eta_x + i eta_y
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -187,7 +190,7 @@ struct LindborgXOp {
             v[m] = make_double2(sc * (ur[x] * v[m].x + vr[x] * v[m].y), 0.0);
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ZERO>(1, H + 2 * L.vs + ro, nullptr);
+        cx.template store_pair<MUL_ONE, MUL_ZERO>(1, Hp(2), none);
     }
 };
 
@@ -227,7 +230,7 @@ struct QgLoaderA {  // jobs: layer*3 + {0 q, 1 psi, 2 i l psi}
     }
 };
 
-template <int N, int NL>
+template <int N, int NL, bool SLAB = false>
 struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 layer + 1]
     static constexpr int NBUF = 2;
     const double2* G;  // [3 NL][ny][kr_pad]
@@ -235,11 +238,12 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
     double sc;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const long long ro = (long long)y * L.kr_pad;
+        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 3 * NL, j, y); };
+        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 2 * NL, j, y); };
         double *q1 = cx.re(0), *q2 = cx.im(0);
         double2 v[16];
-        if (NL == 2) cx.template load_pair<MUL_ONE, MUL_ONE>(1, G + ro, G + 3 * L.vs + ro);
-        else cx.template load_pair<MUL_ONE, MUL_ZERO>(1, G + ro, nullptr);
+        if (NL == 2) cx.template load_pair<MUL_ONE, MUL_ONE>(1, Gp(0), Gp(3));
+        else cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Gp(0), RowPlain{});
         cx.ifft_regs_out(1, v);                          // q1 + i q2
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -250,7 +254,7 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
 #pragma unroll
         for (int layer = 0; layer < NL; ++layer) {
             const double* q = layer == 0 ? q1 : q2;
-            cx.template load_pair<MUL_IK, MUL_ONE>(1, G + (3 * layer + 1) * L.vs + ro, G + (3 * layer + 2) * L.vs + ro);
+            cx.template load_pair<MUL_IK, MUL_ONE>(1, Gp(3 * layer + 1), Gp(3 * layer + 2));
             cx.ifft_regs_out(1, v);                      // psi_x + i psi_y
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
@@ -258,7 +262,7 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
                 v[m] = make_double2(qq * v[m].x, qq * v[m].y);
             }
             cx.fft_regs_in(v, 1);
-            cx.template store_pair<MUL_ONE, MUL_ONE>(1, H + (2 * layer) * L.vs + ro, H + (2 * layer + 1) * L.vs + ro);
+            cx.template store_pair<MUL_ONE, MUL_ONE>(1, Hp(2 * layer), Hp(2 * layer + 1));
         }
     }
 };
@@ -299,7 +303,7 @@ struct TyLoaderA {
 
 // products (linear terms merged): p1 = vt zt, p2 = ut zt, p3 = uc vc, p4 = uc^2 - vc^2, p5 = ut uc, p6 = vt uc_y + vc ut_y,
 // p7 = vt vc, p8 = ut vc_x + uc vt_x, p9 = ut pc_x + vt pc_y   ->  H[0..8]
-template <int N>
+template <int N, bool SLAB = false>
 struct TyXOp {
     static constexpr int NBUF = 3;
     const double2* G;  // [9][ny][kr_pad]
@@ -307,9 +311,9 @@ struct TyXOp {
     double sc;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const long long ro = (long long)y * L.kr_pad;
-        auto Gp = [&](int j) { return G + j * L.vs + ro; };
-        auto Hp = [&](int j) { return H + j * L.vs + ro; };
+        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 9, j, y); };
+        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 9, j, y); };
+        const RowPlain none{};
         double *ut = cx.re(0), *vt = cx.im(0), *uc = cx.re(1), *vc = cx.im(1);
         double2 v[16];
         double ta[16], tb[16];
@@ -361,7 +365,7 @@ struct TyXOp {
         }
         cx.fft_regs_in(v, 2);
         cx.template store_pair<MUL_ONE, MUL_ONE>(2, Hp(5), Hp(7));
-        cx.template load_pair<MUL_ONE, MUL_ZERO>(2, Gp(8), nullptr);
+        cx.template load_pair<MUL_ONE, MUL_ZERO>(2, Gp(8), none);
         cx.ifft_regs_out(2, v);                          // d_y p_c
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
@@ -369,7 +373,7 @@ struct TyXOp {
             v[m] = make_double2(ta[m] + sc * (vt[x] * v[m].x), 0.0);    // p9
         }
         cx.fft_regs_in(v, 2);
-        cx.template store_pair<MUL_ONE, MUL_ZERO>(2, Hp(8), nullptr);
+        cx.template store_pair<MUL_ONE, MUL_ZERO>(2, Hp(8), none);
     }
 };
 
@@ -428,7 +432,7 @@ struct FieldLoader {
     }
 };
 
-template <int N>
+template <int N, bool SLAB = false>
 struct C2ROp {
     static constexpr int NBUF = 2;
     const double2* G;  // [1][ny][kr_pad]
@@ -437,7 +441,7 @@ struct C2ROp {
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
         double2 v[16];
-        cx.template load_pair_regs<MUL_ONE, MUL_ZERO>(v, G + (long long)y * L.kr_pad, nullptr);
+        cx.template load_pair_regs<MUL_ONE, MUL_ZERO>(v, row_ref<SLAB>(L, G, 1, 0, y), RowPlain{});
         cx.ifft_regs(v, 1);
 #pragma unroll
         for (int m = 0; m < 16; ++m) out[(long long)y * N + cx.g + m * Gt] = s1 * v[m].x;
@@ -473,7 +477,7 @@ struct PsiLoader {
     }
 };
 
-template <int N>
+template <int N, bool SLAB = false>
 struct SnapshotXOp {
     static constexpr int NBUF = 3;
     const double2* G;  // [3][ny][kr_pad]
@@ -481,13 +485,12 @@ struct SnapshotXOp {
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
-        const long long ro = (long long)y * L.kr_pad;
-        const double2 *Gp = G + ro, *Gu = G + L.vs + ro, *Guy = G + 2 * L.vs + ro;
+        const auto Gp = row_ref<SLAB>(L, G, 3, 0, y), Gu = row_ref<SLAB>(L, G, 3, 1, y), Guy = row_ref<SLAB>(L, G, 3, 2, y);
         cx.template load_pair<MUL_ONE, MUL_IK>(0, Gu, Gp);
         cx.ifft(0);  // u + i v
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
         cx.ifft(1);  // ux + i uy
-        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, nullptr);
+        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, RowPlain{});
         cx.ifft(2);  // vx
         double* o = out + (long long)y * N * SNAP_STRIDE;
 #pragma unroll
@@ -503,7 +506,7 @@ struct SnapshotXOp {
 
 // Hermite-bicubic node data from the same three y-jobs (G0 = psi, G1 = -i l psi, G2 = l^2 psi):
 // u = G1, v = i k G0, ux = i k G1, uy = G2, vx = -k^2 G0, uxy = i k G2, vxy = psi_xxy = k^2 G1
-template <int N>
+template <int N, bool SLAB = false>
 struct SnapshotCubicXOp {
     static constexpr int NBUF = 2;
     const double2* G;  // [3][ny][kr_pad]
@@ -511,8 +514,7 @@ struct SnapshotCubicXOp {
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const long long ro = (long long)y * L.kr_pad;
-        const double2 *Gp = G + ro, *Gu = G + L.vs + ro, *Guy = G + 2 * L.vs + ro;
+        const auto Gp = row_ref<SLAB>(L, G, 3, 0, y), Gu = row_ref<SLAB>(L, G, 3, 1, y), Guy = row_ref<SLAB>(L, G, 3, 2, y);
         double2* o = reinterpret_cast<double2*>(out + (long long)y * N * SNAP3_STRIDE);
         double2 v[16];
         auto put = [&](int slot) {
@@ -528,7 +530,7 @@ struct SnapshotCubicXOp {
         cx.template load_pair<MUL_MK2, MUL_IK>(1, Gp, Guy);
         cx.ifft_regs_out(1, v);
         put(2);                                          // vx, uxy
-        cx.template load_pair<MUL_K2, MUL_ZERO>(1, Gu, nullptr);
+        cx.template load_pair<MUL_K2, MUL_ZERO>(1, Gu, RowPlain{});
         cx.ifft_regs_out(1, v);
         put(3);                                          // vxy, 0
     }
@@ -596,7 +598,7 @@ struct Launch {
         return ypass_inv(fallback, L, njobs, out, tw, st);
     }
     template <class Combiner>
-    static cudaError_t ypass_fwd(const Combiner& cb, const SpecLayout& L, int nvars, const double2* H, double2* out,
+    static cudaError_t ypass_fwd(const Combiner& cb, const SpecLayout& L, int nvars, int nh, const double2* H, double2* out,
                                  const double2* tw, cudaStream_t st) {
         static const int enabled = [] { const char* e = getenv("SWRT_YPASS_PREFETCH"); return e ? atoi(e) : 1; }();
         if constexpr (kPrefetchFits) {
@@ -610,7 +612,7 @@ struct Launch {
                 cudaError_t ep = prep(kp, smem, TK * G, &mcp);
                 if (ep != cudaSuccess) return ep;
                 const int workp = ((L.kr_keep + TK - 1) / TK) * nvars;
-                kp<<<workp < mcp ? workp : mcp, TK * G, smem, st>>>(cb, L, nvars, rows_s, H, out, tw);
+                kp<<<workp < mcp ? workp : mcp, TK * G, smem, st>>>(cb, L, nvars, nh, rows_s, H, out, tw);
                 return cudaGetLastError();
             }
         }
@@ -619,7 +621,7 @@ struct Launch {
         cudaError_t e = prep(k, ysmem, TK * G, &mc);
         if (e != cudaSuccess) return e;
         const int work = ((L.kr_keep + TK - 1) / TK) * nvars;
-        k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(cb, L, nvars, H, out, tw);
+        k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(cb, L, nvars, nh, H, out, tw);
         return cudaGetLastError();
     }
     template <class Op>
@@ -629,7 +631,7 @@ struct Launch {
         int mc = 1;
         cudaError_t e = prep(k, smem, G, &mc);
         if (e != cudaSuccess) return e;
-        k<<<L.ny < mc ? L.ny : mc, G, smem, st>>>(op, L, tw, sched);
+        k<<<L.yrows < mc ? L.yrows : mc, G, smem, st>>>(op, L, tw, sched);
         return cudaGetLastError();
     }
 

@@ -25,7 +25,50 @@ struct SpecLayout {
     double dk, dl;     // 2 pi / Lx, 2 pi / Ly
     double f, Cg2;     // model constants used by loaders
     double aux0, aux1; // model specific (Kd2, ...)
+    // Slab decomposition over P ranks (all equal to the single-GPU values when P = 1): a rank owns `kr_keep` columns starting at
+    // global column kr_off (kr_pad = columns per rank, the same on every rank) and `yrows` = ny / P physical rows.  The
+    // y-transformed / x-transformed intermediates are stored [y block][job][row in block][kr_pad]: exactly the send / receive
+    // layout of the all-to-all transposes, and the plain [job][y][kr_pad] array when P = 1.
+    int kr_off, kr_keep_g, yshift, yrows;
 };
+
+// element offset of (job, y, column 0) in an intermediate array holding `njobs` jobs
+__device__ __forceinline__ long long inter_off(const SpecLayout& L, int njobs, int job, int y) {
+    const int blk = y >> L.yshift, yl = y & ((1 << L.yshift) - 1);
+    return ((((long long)blk * njobs + job) << L.yshift) + yl) * L.kr_pad;
+}
+// One x-pass row (fixed job and local row).  Single GPU: kr_pad contiguous columns (RowPlain).  Slab mode: P segments of
+// kr_pad columns (one per source/destination rank), `skip + chunk` elements apart (RowSeg).  The row type is a template
+// parameter of the x-pass ops so that the single-GPU kernels carry no segment arithmetic at all.
+struct RowPlain {
+    double2* base;
+    __device__ __forceinline__ double2* at(int k) const { return base + k; }
+};
+struct RowSeg {
+    double2* base;
+    long long skip;   // segment stride - chunk: added once per segment boundary crossed
+    int chunk, nseg;
+    __device__ __forceinline__ double2* at(int k) const {
+        long long off = k;
+        for (int j = 1; j < nseg; ++j) off += k >= j * chunk ? skip : 0;   // branch-free, no division
+        return base + off;
+    }
+};
+template <bool SLAB>
+struct RowOf { using type = RowPlain; };
+template <>
+struct RowOf<true> { using type = RowSeg; };
+template <bool SLAB>
+__device__ __forceinline__ typename RowOf<SLAB>::type row_ref(const SpecLayout& L, const double2* arr, int njobs, int job, int yl) {
+    typename RowOf<SLAB>::type r;
+    r.base = const_cast<double2*>(arr) + (((long long)job << L.yshift) + yl) * L.kr_pad;
+    if constexpr (SLAB) {
+        r.skip = ((long long)njobs << L.yshift) * L.kr_pad - L.kr_pad;
+        r.chunk = L.kr_pad;
+        r.nseg = L.ny >> L.yshift;
+    }
+    return r;
+}
 
 __device__ __forceinline__ double wave_l(const SpecLayout& L, int j) {
     return (double)(j < L.ny / 2 ? j : j - L.ny) * L.dl;
@@ -72,7 +115,7 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     for (int w = blockIdx.x; w < ntiles * njobs; w += gridDim.x) {
         const int job = w / ntiles, kr = (w % ntiles) * TK + c;
-        const double kw = kr * L.dk;
+        const double kw = (L.kr_off + kr) * L.dk;
         const bool col_ok = kr < L.kr_keep;
         double2 v[16];
 #pragma unroll
@@ -83,9 +126,8 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
         }
         block_fft_regs<N, +1>(v, re, im, g, tw);
         if (col_ok) {
-            double2* o = out + (long long)job * L.vs + kr;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) o[(long long)(g + m * G) * L.kr_pad] = v[m];
+            for (int m = 0; m < 16; ++m) out[inter_off(L, njobs, job, g + m * G) + kr] = v[m];
         }
     }
 }
@@ -156,9 +198,8 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
         if (w + (int)gridDim.x < nwork) prefetch(w + gridDim.x);
         block_fft_regs<N, +1>(v, re, im, g, tw);
         if (kr < L.kr_keep) {
-            double2* o = out + (long long)job * L.vs + kr;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) o[(long long)(g + m * G) * L.kr_pad] = v[m];
+            for (int m = 0; m < 16; ++m) out[inter_off(L, njobs, job, g + m * G) + kr] = v[m];
         }
     }
 }
@@ -173,7 +214,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
 __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
-    ypass_fwd_kernel(Combiner cb, SpecLayout L, int nvars, const double2* __restrict__ H, double2* __restrict__ out,
+    ypass_fwd_kernel(Combiner cb, SpecLayout L, int nvars, int nh, const double2* __restrict__ H, double2* __restrict__ out,
                      const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     constexpr int G = group_size(N), NP = col_stride(N, TK);
@@ -184,17 +225,17 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     for (int w = blockIdx.x; w < ntiles * nvars; w += gridDim.x) {
         const int var = cb.var_of(w / ntiles), kr = (w % ntiles) * TK + c;   // heaviest variables first (static balance)
-        const double kw = kr * L.dk;
+        const double kw = (L.kr_off + kr) * L.dk;
         const bool col_ok = kr < L.kr_keep;
         double2* o = out + (long long)var * L.vs + kr;
         const int nin = cb.nin(var);
         for (int i_in = 0; i_in < nin; ++i_in) {
-            const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr;
+            const int srcj = cb.src(var, i_in);
             double2 v[16];
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 v[m] = make_double2(0.0, 0.0);
-                if (col_ok) v[m] = h[(long long)(g + m * G) * L.kr_pad];
+                if (col_ok) v[m] = H[inter_off(L, nh, srcj, g + m * G) + kr];
             }
             block_fft_regs<N, -1>(v, re, im, g, tw);
             if (col_ok) {
@@ -221,8 +262,8 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
 __global__ void __launch_bounds__(TK* group_size(N), 1)
-    ypass_fwd_prefetch_kernel(Combiner cb, SpecLayout L, int nvars, int rows_s, const double2* __restrict__ H, double2* __restrict__ out,
-                              const double2* __restrict__ tw) {
+    ypass_fwd_prefetch_kernel(Combiner cb, SpecLayout L, int nvars, int nh, int rows_s, const double2* __restrict__ H,
+                              double2* __restrict__ out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     constexpr int G = group_size(N), NP = col_stride(N, TK), NT = TK * G;
     const int tid = threadIdx.x;
@@ -234,10 +275,10 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     const int nwork = ntiles * nvars;
     auto prefetch = [&](int w, int i_in) {
         const int var = cb.var_of(w / ntiles), kr0 = (w % ntiles) * TK;
-        const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr0;
+        const int srcj = cb.src(var, i_in);
         for (int ch = tid; ch < rows_s * TK; ch += NT) {
             const int r = ch / TK, cc = ch - r * TK;
-            cp_async16(&stg[ch], &h[(long long)r * L.kr_pad + cc]);
+            cp_async16(&stg[ch], &H[inter_off(L, nh, srcj, r) + kr0 + cc]);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -245,16 +286,16 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     if (w < nwork) prefetch(w, 0);
     while (w < nwork) {
         const int var = cb.var_of(w / ntiles), kr = (w % ntiles) * TK + c;
-        const double kw = kr * L.dk;
+        const double kw = (L.kr_off + kr) * L.dk;
         const bool col_ok = kr < L.kr_keep;
         const int nin = cb.nin(var);
-        const double2* h = H + (long long)cb.src(var, i_in) * L.vs + kr;
+        const int srcj = cb.src(var, i_in);
         double2 v[16];
 #pragma unroll
         for (int m = 0; m < 16; ++m) {           // rows outside the staging buffer: direct, issued first
             const int y = g + m * G;
             v[m] = make_double2(0.0, 0.0);
-            if (y >= rows_s && col_ok) v[m] = h[(long long)y * L.kr_pad];
+            if (y >= rows_s && col_ok) v[m] = H[inter_off(L, nh, srcj, y) + kr];
         }
         asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
@@ -306,23 +347,23 @@ struct XCtx {
     static constexpr int G = group_size(N), NP = padded_len(N), EPT = N / G;
     double* smem;
     const double2* tw;
-    int g, kr_keep;
+    int g, kr_keep;   // kr_keep: GLOBAL number of retained columns (rows are whole in the x-pass)
     double dk;
     __device__ __forceinline__ double* re(int b) const { return smem + (2 * b) * NP; }
     __device__ __forceinline__ double* im(int b) const { return smem + (2 * b + 1) * NP; }
 
     // Build the Hermitian-extended spectrum of z = a + i b from the half spectra A, B (rows of
     // kr_pad complex).  Only the real parts of A[0], B[0] enter, like a c2r transform.
-    template <int MA, int MB>
-    __device__ __forceinline__ void load_pair(int b, const double2* __restrict__ A, const double2* __restrict__ B) const {
+    template <int MA, int MB, class RA, class RB>
+    __device__ __forceinline__ void load_pair(int b, const RA& A, const RB& B) const {
         double *r = re(b), *m = im(b);
         __syncthreads();  // earlier pointwise readers of this buffer are done
         for (int k = g; k < N / 2; k += G) {
             double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
             if (k < kr_keep) {
                 const double kw = k * dk;
-                za = apply_mul<MA>(__ldg(&A[k]), kw);
-                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(&B[k]), kw);
+                za = apply_mul<MA>(__ldg(A.at(k)), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(B.at(k)), kw);
             }
             if (k == 0) {
                 r[0] = za.x;
@@ -342,8 +383,8 @@ struct XCtx {
 
     // Register-interface versions (fft.cuh): v[m] <-> x (or k) = g + m N/16.
     // Hermitian-extended spectrum of z = a + i b straight from the half spectra in global memory.
-    template <int MA, int MB>
-    __device__ __forceinline__ void load_pair_regs(double2 (&v)[16], const double2* __restrict__ A, const double2* __restrict__ B) const {
+    template <int MA, int MB, class RA, class RB>
+    __device__ __forceinline__ void load_pair_regs(double2 (&v)[16], const RA& A, const RB& B) const {
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int x = g + m * G;
@@ -351,8 +392,8 @@ struct XCtx {
             double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
             if (k < kr_keep) {                           // also excludes k = N/2 (kr_keep <= N/2)
                 const double kw = k * dk;
-                za = apply_mul<MA>(__ldg(&A[k]), kw);
-                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(&B[k]), kw);
+                za = apply_mul<MA>(__ldg(A.at(k)), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(B.at(k)), kw);
             }
             if (m < 8) v[m] = (m == 0 && x == 0) ? make_double2(za.x, zb.x) : make_double2(za.x - zb.y, za.y + zb.x);
             else v[m] = make_double2(za.x + zb.y, zb.x - za.y);
@@ -367,15 +408,15 @@ struct XCtx {
 
     // After a forward transform of z = p + i q:  2 P[k] = Z[k] + conj Z[N-k],  2i Q[k] = Z[k] - conj Z[N-k].
     // Writes 2P and 2Q (callers fold the 1/2 into their scaling) for k < kr_keep.
-    template <int MP, int MQ>
-    __device__ __forceinline__ void store_pair(int b, double2* __restrict__ P, double2* __restrict__ Q) const {
+    template <int MP, int MQ, class RA, class RB>
+    __device__ __forceinline__ void store_pair(int b, const RA& P, const RB& Q) const {
         const double *r = re(b), *m = im(b);
         for (int k = g; k < kr_keep; k += G) {
             const int kn = (N - k) & (N - 1);
             const double a = r[pad_index(k)], bb = m[pad_index(k)], c = r[pad_index(kn)], d = m[pad_index(kn)];
             const double kw = k * dk;
-            P[k] = apply_mul<MP>(make_double2(a + c, bb - d), kw);
-            if (MQ != MUL_ZERO) Q[k] = apply_mul<MQ>(make_double2(bb + d, c - a), kw);
+            *P.at(k) = apply_mul<MP>(make_double2(a + c, bb - d), kw);
+            if (MQ != MUL_ZERO) *Q.at(k) = apply_mul<MQ>(make_double2(bb + d, c - a), kw);
         }
         __syncthreads();
     }
@@ -392,10 +433,10 @@ __global__ void __launch_bounds__(group_size(N), clamp_blocks(xpass_smem(N, Op::
     cx.smem = smem;
     cx.tw = tw;
     cx.g = threadIdx.x;
-    cx.kr_keep = L.kr_keep;
+    cx.kr_keep = L.kr_keep_g;
     cx.dk = L.dk;
     int y = blockIdx.x;                      // first row: static
-    while (y < L.ny) {
+    while (y < L.yrows) {
         if (threadIdx.x == 0) next_row = (int)(gridDim.x + atomicAdd(&sched[0], 1u));
         op.row(cx, L, y);                    // (contains barriers: next_row is visible afterwards)
         __syncthreads();

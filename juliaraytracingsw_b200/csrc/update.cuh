@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) ifmab3_update_rsw_kernel(UpdateArgs a, Rs
         const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
         const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
         const long long off = (long long)l * L.kr_pad + kr;
-        const double kw = kr * L.dk, lw = wave_l(L, l);
+        const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l);
         const double4 cf = a.coef[off];
         const double eD = cf.x, s = cf.y, c = cf.z;
         double2 x[3], n[3];
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, do
         const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
         const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
         const long long off = (long long)l * L.kr_pad + kr;
-        psih[off] = ld.psi_of(kr * L.dk, wave_l(L, l), off);
+        psih[off] = ld.psi_of((L.kr_off + kr) * L.dk, wave_l(L, l), off);
     }
 }
 
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) spectral_diag_kernel(const double2* __res
         const int l = (int)(i / L.kr_keep), kr = (int)(i - (long long)l * L.kr_keep);
         if (!l_retained(L, l)) continue;
         const long long off = (long long)l * L.kr_pad + kr;
-        const double kw = kr * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
+        const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
         double val;
         if (which == DIAG_ABS2_VAR) {
             const double2 v = sol[arg * L.vs + off];
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) spectral_diag_kernel(const double2* __res
             const double2 p = qg_streamfunction(sol, L.vs, nlayers, arg, K2, P, off);
             val = (which == DIAG_QG_K2PSI2 ? K2 : 1.0) * (p.x * p.x + p.y * p.y);
         }
-        acc += ((kr == 0 || kr == L.nx / 2) ? 1.0 : 2.0) * val;
+        acc += ((L.kr_off + kr == 0 || L.kr_off + kr == L.nx / 2) ? 1.0 : 2.0) * val;
     }
     sh[threadIdx.x] = acc;
     __syncthreads();
