@@ -45,6 +45,7 @@ typedef struct swrt_flow_desc {
     double aliased_fraction;
     double filter_innerK, filter_outerK, filter_tol;   /* <=0: FourierFlows defaults 2/3, 1, 1e-15 */
     double U, mu, F, Ro, Kd2;                            /* model specific (two-layer, TY, SWQG) */
+    int slab_rank, slab_size;                            /* slab-decomposed flow over slab_size GPUs (0 or 1: off), see swrt_slab_* */
 } swrt_flow_desc;
 
 const char* swrt_last_error(void);
@@ -98,6 +99,28 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host);
 /* load a snapshot from host fields (same layout) -- used for steady/analytic background flows
  * (raytracing/SteadyRaytracing.jl) and by tests */
 int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host);
+
+/* ---- slab-decomposed flow step (grids >= 4096^2; one process per GPU) ------------------------------------
+ * Rank r owns retained kr columns [r*chunk, (r+1)*chunk) in spectral space and ny/P rows in physical space.  A step is
+ *   slab_stage_a  (y-transforms of the local columns)      -> buffer A_SEND, laid out [dest][job][row][chunk]
+ *   all-to-all A_SEND -> A_RECV                              (the caller: ncclAllToAll / torch.distributed.all_to_all_single)
+ *   slab_stage_b  (x-pass on the local rows)                 A_RECV -> B_SEND
+ *   all-to-all B_SEND -> B_RECV
+ *   slab_stage_c  (y-transforms back, IFMAB3 update, clock)  from B_RECV
+ * and a velocity snapshot is slab_psi_a, all-to-all, slab_snap_b (writes this rank's rows of the full snapshot), all-gather.
+ * The exchange buffers are owned by the handle; swrt_slab_buffer returns their device pointers so that the caller's
+ * communication library can work on them in place.  swrt_flow_set_stream makes the handle launch on the caller's stream
+ * (e.g. torch's current stream) so that kernels and collectives are ordered without host synchronisation. */
+enum { SWRT_SLAB_A_SEND = 0, SWRT_SLAB_A_RECV = 1, SWRT_SLAB_B_SEND = 2, SWRT_SLAB_B_RECV = 3, SWRT_SLAB_SNAP0 = 4, SWRT_SLAB_SNAP1 = 5 };
+int swrt_flow_set_stream(swrt_flow* h, void* cuda_stream);
+int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbytes);
+/* elements (complex128) per destination of the two all-to-alls for njobs jobs, rows per rank, columns per rank */
+int swrt_slab_info(swrt_flow* h, int* yrows, int* chunk, int* njobs_a, int* njobs_b);
+int swrt_slab_stage_a(swrt_flow* h);
+int swrt_slab_stage_b(swrt_flow* h);
+int swrt_slab_stage_c(swrt_flow* h);
+int swrt_slab_psi_a(swrt_flow* h, int psi_kind);
+int swrt_slab_snap_b(swrt_flow* h, int slot);
 
 /* timing helpers on the handle's stream (CUDA events) */
 int swrt_flow_timer_start(swrt_flow* h);

@@ -22,7 +22,7 @@ class FlowDesc(C.Structure):
         ("Lx", C.c_double), ("Ly", C.c_double), ("dt", C.c_double), ("nu", C.c_double), ("f", C.c_double),
         ("Cg", C.c_double), ("aliased_fraction", C.c_double), ("filter_innerK", C.c_double),
         ("filter_outerK", C.c_double), ("filter_tol", C.c_double), ("U", C.c_double), ("mu", C.c_double),
-        ("F", C.c_double), ("Ro", C.c_double), ("Kd2", C.c_double),
+        ("F", C.c_double), ("Ro", C.c_double), ("Kd2", C.c_double), ("slab_rank", C.c_int), ("slab_size", C.c_int),
     ]
 
 
@@ -61,6 +61,14 @@ SIGNATURES = {
     "swrt_flow_snapshot_fields": (_I, [_P, _PI]),
     "swrt_flow_get_snapshot": (_I, [_P, _I, _P]),
     "swrt_flow_set_snapshot": (_I, [_P, _I, _P]),
+    "swrt_flow_set_stream": (_I, [_P, _P]),
+    "swrt_slab_buffer": (_I, [_P, _I, C.POINTER(_P), _PLL]),
+    "swrt_slab_info": (_I, [_P, _PI, _PI, _PI, _PI]),
+    "swrt_slab_stage_a": (_I, [_P]),
+    "swrt_slab_stage_b": (_I, [_P]),
+    "swrt_slab_stage_c": (_I, [_P]),
+    "swrt_slab_psi_a": (_I, [_P, _I]),
+    "swrt_slab_snap_b": (_I, [_P, _I]),
     "swrt_flow_timer_start": (_I, [_P]),
     "swrt_flow_timer_stop": (_I, [_P, _PF]),
     "swrt_flow_sync": (_I, [_P]),

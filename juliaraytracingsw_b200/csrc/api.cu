@@ -74,6 +74,9 @@ struct swrt_flow {
     int interp = 0;                         // snapshot node data: 0 bilinear (5 fields / 48 B), 1 Hermite bicubic (7 fields / 64 B)
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
+    double2 *G2 = nullptr, *H2 = nullptr;   // slab mode: A_RECV / B_SEND (G = A_SEND, H = B_RECV)
+    int P = 1, rank = 0;
+    bool own_stream = true;
     unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
     int ring = 0;
     double t = 0.0;
@@ -144,18 +147,18 @@ __global__ void pack_sol_kernel(const double2* __restrict__ host_layout, double2
         const long long r = i / L.kr_pad;
         const int l = (int)(r % L.ny), v = (int)(r / L.ny);
         double2 val = make_double2(0.0, 0.0);
-        if (kr < L.kr_keep && l_retained(L, l)) val = host_layout[((long long)v * L.ny + l) * nkr + kr];
+        if (kr < L.kr_keep && l_retained(L, l)) val = host_layout[((long long)v * L.ny + l) * nkr + L.kr_off + kr];
         sol[i] = val;
     }
 }
 __global__ void unpack_sol_kernel(const double2* __restrict__ sol, double2* __restrict__ host_layout, SpecLayout L, int nkr, int nvar) {
     const long long total = (long long)nvar * L.ny * nkr;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int kr = (int)(i % nkr);
+        const int kg = (int)(i % nkr), kr = kg - L.kr_off;    // slab mode: only this rank's columns are filled, the rest stay zero
         const long long r = i / nkr;
         const int l = (int)(r % L.ny), v = (int)(r / L.ny);
         double2 val = make_double2(0.0, 0.0);
-        if (kr < L.kr_keep && l_retained(L, l)) val = sol[((long long)v * L.ny + l) * L.kr_pad + kr];
+        if (kr >= 0 && kr < L.kr_keep && l_retained(L, l)) val = sol[((long long)v * L.ny + l) * L.kr_pad + kr];
         host_layout[i] = val;
     }
 }
@@ -231,6 +234,7 @@ static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, 
 }
 
 static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
+    if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "physical-space fields of a slab-decomposed flow are not gathered by the library");
     FieldLoader ld{h->sol, h->L.vs, which, h->nvar, h->d.f, h->L.aux0};
     cudaError_t e;
     { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st)); }
@@ -259,12 +263,12 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
-    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched);
+    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->st) cudaStreamDestroy(h->st);
+    if (h->st && h->own_stream) cudaStreamDestroy(h->st);
     delete h;
     return SWRT_OK;
 }
@@ -303,6 +307,20 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     L.vs = (long long)L.ny * L.kr_pad;
     L.kr_off = 0; L.kr_keep_g = L.kr_keep; L.yrows = L.ny;
     L.yshift = 0; while ((1 << L.yshift) < L.ny) ++L.yshift;
+    if (d.slab_size > 1) {
+        const int P = d.slab_size;
+        if ((P & (P - 1)) || P > 16 || d.slab_rank < 0 || d.slab_rank >= P || d.ny % P || d.ny / P < 16) { delete h; return fail(SWRT_ERR_ARG, "slab_size must be a power of two <= 16 dividing ny (>= 16 rows per rank), 0 <= slab_rank < slab_size"); }
+        if (!(d.model == SWRT_RSW || d.model == SWRT_SWQG || d.model == SWRT_TWOLAYERQG) || d.stepper != SWRT_IFMAB3) { delete h; return fail(SWRT_ERR_UNSUPPORTED, "slab mode is built for RSW / SWQG / two-layer QG with IFMAB3"); }
+        h->P = P; h->rank = d.slab_rank;
+        const int chunk = ((L.kr_keep_g + P - 1) / P + 15) / 16 * 16;
+        L.kr_off = d.slab_rank * chunk;
+        int mine = L.kr_keep_g - L.kr_off;
+        L.kr_keep = mine < 0 ? 0 : (mine > chunk ? chunk : mine);
+        L.kr_pad = chunk;
+        L.vs = (long long)L.ny * chunk;
+        L.yrows = d.ny / P;
+        L.yshift = 0; while ((1 << L.yshift) < L.yrows) ++L.yshift;
+    }
     L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
     L.f = d.f; L.Cg2 = d.Cg * d.Cg;
     // model constant used by the loaders: Kd2 = f^2/Cg^2 (SWQG, swqg/SWQG.jl:85; RSW balanced psi) or F (two-layer, swqg/TwoLayerQG.jl:79)
@@ -325,6 +343,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     }
     CKB(cudaMalloc(&h->G, fb * h->njobs_a)); CKB(cudaMemset(h->G, 0, fb * h->njobs_a));
     CKB(cudaMalloc(&h->H, fb * h->njobs_b)); CKB(cudaMemset(h->H, 0, fb * h->njobs_b));
+    if (h->P > 1) {
+        CKB(cudaMalloc(&h->G2, fb * h->njobs_a)); CKB(cudaMemset(h->G2, 0, fb * h->njobs_a));
+        CKB(cudaMalloc(&h->H2, fb * h->njobs_b)); CKB(cudaMemset(h->H2, 0, fb * h->njobs_b));
+    }
     CKB(cudaMalloc(&h->psih, fb)); CKB(cudaMemset(h->psih, 0, fb));
     CKB(cudaMalloc(&h->stage, sizeof(double2) * (size_t)h->nkr * d.ny * h->nvar));
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
@@ -359,7 +381,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
         for (int l = 0; l < d.ny; ++l) {
             const double lw = (double)(l < d.ny / 2 ? l : l - d.ny) * L.dl;
             for (int kr = 0; kr < L.kr_keep; ++kr) {
-                const double kw = kr * L.dk, K2 = kw * kw + lw * lw;
+                const double kw = (L.kr_off + kr) * L.dk, K2 = kw * kw + lw * lw;
                 const double D = -d.nu * std::pow(K2, (double)d.nnu);
                 const size_t off = (size_t)l * L.kr_pad + kr;
                 double filt = 1.0;
@@ -449,6 +471,36 @@ int swrt_flow_enforce_reality(swrt_flow* h) {
     return SWRT_OK;
 }
 
+// IFMAB3 / FilteredAB3 update of the state from the freshly computed N (history = the two other ring buffers)
+static int ifmab3_update_launch(swrt_flow* h, double2* Ncur) {
+    const SpecLayout& L = h->L;
+    const int model = h->d.model, stepper = h->d.stepper;
+    const bool modified = model == SWRT_RSW_MODIFIED;
+    RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
+    const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+    if (nmodes == 0) return SWRT_OK;
+    const int ublocks = (int)((nmodes + 255) / 256);
+    const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
+    const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
+    UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, h->d.dt, h->step < 3 ? 1 : 0};
+    {
+        ProfScope ps(h, K_UPDATE);
+        if (model == SWRT_SWQG) {
+            if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+            else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+        } else if (model == SWRT_THOMASYAMADA) {
+            if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<4, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+            else update_diag_kernel<4, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+        } else if (model == SWRT_TWOLAYERQG) {
+            ifmab3_update_table_kernel<2><<<ublocks, 256, 0, h->st>>>(ua, h->Etab, h->E2tab, L);
+        } else {
+            ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
+        }
+    }
+    CK(cudaGetLastError());
+    return SWRT_OK;
+}
+
 // N = calcN!(state): the three transform passes of the model
 static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
     const SpecLayout& L = h->L;
@@ -465,11 +517,10 @@ static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
 
 int swrt_flow_step(swrt_flow* h, int nsteps) {
     if (!h || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
+    if (h->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: drive the step with swrt_slab_stage_a/b/c and the two all-to-alls");
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    const int model = h->d.model, stepper = h->d.stepper;
-    const bool modified = model == SWRT_RSW_MODIFIED;
-    RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
+    const int stepper = h->d.stepper;
     const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
     const int ublocks = (int)((nmodes + 255) / 256);
     const double dt = h->d.dt;
@@ -504,25 +555,8 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
             CK(stage(ST_RK4_FINAL, h->sol, h->sol, R1, R2, R3, R4, h->S1, dt));
         } else {
             double2* Ncur = h->Nb[h->ring];
-            const double2* Nm1 = h->Nb[(h->ring + 2) % 3];
-            const double2* Nm2 = h->Nb[(h->ring + 1) % 3];
             if ((rc = compute_N(h, h->sol, Ncur))) return rc;
-            UpdateArgs ua{h->sol, Ncur, Nm1, Nm2, h->coef, dt, h->step < 3 ? 1 : 0};
-            {
-                ProfScope ps(h, K_UPDATE);
-                if (model == SWRT_SWQG) {
-                    if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-                    else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-                } else if (model == SWRT_THOMASYAMADA) {
-                    if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<4, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-                    else update_diag_kernel<4, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
-                } else if (model == SWRT_TWOLAYERQG) {
-                    ifmab3_update_table_kernel<2><<<ublocks, 256, 0, h->st>>>(ua, h->Etab, h->E2tab, L);
-                } else {
-                    ifmab3_update_rsw_kernel<<<ublocks, 256, 0, h->st>>>(ua, lin, L);
-                }
-            }
-            CK(cudaGetLastError());
+            if ((rc = ifmab3_update_launch(h, Ncur))) return rc;
             h->ring = (h->ring + 1) % 3;
         }
         h->t += dt;
@@ -639,12 +673,109 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag) {
     return SWRT_OK;
 }
 
-int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
-    if (!h || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+static int check_psi_kind(swrt_flow* h, int psi_kind) {
     const bool rsw_family = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;
     const bool ok = (psi_kind == SWRT_PSI_RSW_BALANCED && rsw_family) || (psi_kind == SWRT_PSI_SWQG && h->d.model == SWRT_SWQG) ||
                     ((psi_kind == SWRT_PSI_TWOLAYER_BAROCLINIC || psi_kind == SWRT_PSI_TWOLAYER_MEAN) && h->d.model == SWRT_TWOLAYERQG);
-    if (!ok) return fail(SWRT_ERR_ARG, "psi kind %d does not apply to model %d", psi_kind, h->d.model);
+    return ok ? SWRT_OK : fail(SWRT_ERR_ARG, "psi kind %d does not apply to model %d", psi_kind, h->d.model);
+}
+
+// ------------------------------------------------------------------ slab-decomposed step (phases between the caller's all-to-alls)
+int swrt_flow_set_stream(swrt_flow* h, void* cuda_stream) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaStreamSynchronize(h->st));
+    if (h->own_stream && h->st) cudaStreamDestroy(h->st);
+    h->st = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return SWRT_OK;
+}
+int swrt_slab_info(swrt_flow* h, int* yrows, int* chunk, int* njobs_a, int* njobs_b) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (yrows) *yrows = h->L.yrows;
+    if (chunk) *chunk = h->L.kr_pad;
+    if (njobs_a) *njobs_a = model_njobs_a(h->d.model);
+    if (njobs_b) *njobs_b = model_njobs_b(h->d.model);
+    return SWRT_OK;
+}
+int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbytes) {
+    if (!h || !device_ptr) return fail(SWRT_ERR_ARG, "null pointer");
+    if (h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    const long long fb = (long long)sizeof(double2) * h->L.vs;
+    void* p = nullptr;
+    long long nb = 0;
+    switch (which) {
+        case SWRT_SLAB_A_SEND: p = h->G; nb = fb * h->njobs_a; break;
+        case SWRT_SLAB_A_RECV: p = h->G2; nb = fb * h->njobs_a; break;
+        case SWRT_SLAB_B_SEND: p = h->H2; nb = fb * h->njobs_b; break;
+        case SWRT_SLAB_B_RECV: p = h->H; nb = fb * h->njobs_b; break;
+        case SWRT_SLAB_SNAP0: case SWRT_SLAB_SNAP1:
+            p = h->snap[h->slot_map[which - SWRT_SLAB_SNAP0]];
+            nb = (long long)sizeof(double) * h->d.nx * h->d.ny * (h->interp ? SNAP3_STRIDE : SNAP_STRIDE);
+            break;
+        default: return fail(SWRT_ERR_ARG, "unknown slab buffer %d", which);
+    }
+    *device_ptr = p;
+    if (nbytes) *nbytes = nb;
+    return SWRT_OK;
+}
+int swrt_slab_stage_a(swrt_flow* h) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e;
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(h->L.ny, e, LN::stage_a(h->d.model, h->sol, h->G, h->L, h->tw_y, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
+int swrt_slab_stage_b(swrt_flow* h) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e;
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, h->G2, h->H2, h->L, h->tw_x, h->sched, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
+static int ifmab3_update_launch(swrt_flow* h, double2* Ncur);
+int swrt_slab_stage_c(swrt_flow* h) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    CK(cudaSetDevice(h->d.device));
+    double2* Ncur = h->Nb[h->ring];
+    cudaError_t e;
+    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(h->L.ny, e, LN::stage_c(h->d.model, h->sol, h->H, Ncur, h->L, h->tw_y, h->st)); }
+    CK(e);
+    int rc = ifmab3_update_launch(h, Ncur);
+    if (rc) return rc;
+    h->ring = (h->ring + 1) % 3;
+    h->t += h->d.dt;
+    h->step += 1;
+    return SWRT_OK;
+}
+int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    int rc = check_psi_kind(h, psi_kind);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->d.device));
+    PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0};
+    cudaError_t e;
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, h->G, h->tw_y, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
+int swrt_slab_snap_b(swrt_flow* h, int slot) {
+    if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
+    if (h->interp) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the bilinear node data");
+    CK(cudaSetDevice(h->d.device));
+    double* rows = h->snap[h->slot_map[slot]] + (long long)h->rank * h->L.yrows * h->d.nx * SNAP_STRIDE;   // this rank's rows of the full field
+    cudaError_t e;
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(h->G2, rows, h->L, h->tw_x, h->sched, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
+
+int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    if (h->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: use swrt_slab_psi_a / swrt_slab_snap_b around the all-to-all");
+    { int rc = check_psi_kind(h, psi_kind); if (rc) return rc; }
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0};

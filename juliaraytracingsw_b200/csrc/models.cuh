@@ -638,6 +638,9 @@ struct Launch {
     // concrete entry points (explicitly specialised per size in inst.cu); `model` = SWRT_* model id
     static cudaError_t stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    // slab mode (P > 1): segmented rows; built for the models of the >= 4096^2 configurations (RSW, SWQG, two-layer QG)
+    static cudaError_t stage_b_slab(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t snap_stage_b_slab(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);

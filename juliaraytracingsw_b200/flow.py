@@ -101,7 +101,7 @@ class Problem:
     def __init__(self, dev=0, *, model="RotatingShallowWater", nx=128, ny=None, Lx=2 * np.pi, Ly=None, ν=1.0e-16,
                  nν=4, f=1.0, Cg=1.0, stepper="IFMAB3", dt=5e-2, aliased_fraction=1 / 3, T=np.float64,
                  use_filter=False, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15, nu=None, nnu=None,
-                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None, Ro=0.2):
+                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None, Ro=0.2, slab=None):
         """Two-layer QG (swqg/TwoLayerQG.jl:55-72) takes U, μ, f0, Cg, δρρ0 (F = 2 f0²/Cg²/δρρ0); SWQG takes f, Cg (Kd2 = f²/Cg²)."""
         if T not in (np.float64, float, "Float64"):
             raise _lib.SwrtError("only T=Float64 is implemented (the north star's arithmetic)")
@@ -115,7 +115,8 @@ class Problem:
         d = FlowDesc(model=MODELS[model], stepper=STEPPERS[stepper], nx=nx, ny=ny, nnu=nν, use_filter=int(use_filter),
                      filter_order=order, device=int(dev), Lx=Lx, Ly=Ly, dt=dt, nu=ν, f=f, Cg=Cg,
                      aliased_fraction=aliased_fraction, filter_innerK=innerK, filter_outerK=outerK, filter_tol=tol,
-                     U=U, mu=μ, F=F, Ro=Ro)
+                     U=U, mu=μ, F=F, Ro=Ro, slab_rank=0 if slab is None else int(slab[0]),
+                     slab_size=0 if slab is None else int(slab[1]))
         self._h = C.c_void_p()
         check(lib().swrt_flow_create(C.byref(d), C.byref(self._h)))
         self.desc, self.dt, self.nvar = d, dt, NVAR[d.model]
