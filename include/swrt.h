@@ -116,6 +116,13 @@ int swrt_flow_set_stream(swrt_flow* h, void* cuda_stream);
 int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbytes);
 /* elements (complex128) per destination of the two all-to-alls for njobs jobs, rows per rank, columns per rank */
 int swrt_slab_info(swrt_flow* h, int* yrows, int* chunk, int* njobs_a, int* njobs_b);
+/* Direct NVLink transposes: every rank exports the IPC handles (64 bytes each) of its two RECEIVE buffers, the caller distributes
+ * them, and each rank opens its peers'.  Once all are open (slab_p2p -> 1) stage_a / stage_b / psi_a store their output straight
+ * into the destination ranks' receive buffers; the caller then only needs a stream-ordered barrier (e.g. a one-element all-reduce)
+ * where the all-to-all used to be. */
+int swrt_slab_ipc_handle(swrt_flow* h, int which, void* handle64);
+int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handle64);
+int swrt_slab_p2p(swrt_flow* h, int* enabled);
 int swrt_slab_stage_a(swrt_flow* h);
 int swrt_slab_stage_b(swrt_flow* h);
 int swrt_slab_stage_c(swrt_flow* h);

@@ -64,6 +64,9 @@ SIGNATURES = {
     "swrt_flow_set_stream": (_I, [_P, _P]),
     "swrt_slab_buffer": (_I, [_P, _I, C.POINTER(_P), _PLL]),
     "swrt_slab_info": (_I, [_P, _PI, _PI, _PI, _PI]),
+    "swrt_slab_ipc_handle": (_I, [_P, _I, _P]),
+    "swrt_slab_ipc_open": (_I, [_P, _I, _I, _P]),
+    "swrt_slab_p2p": (_I, [_P, _PI]),
     "swrt_slab_stage_a": (_I, [_P]),
     "swrt_slab_stage_b": (_I, [_P]),
     "swrt_slab_stage_c": (_I, [_P]),

@@ -77,6 +77,9 @@ struct swrt_flow {
     double2 *G2 = nullptr, *H2 = nullptr;   // slab mode: A_RECV / B_SEND (G = A_SEND, H = B_RECV)
     int P = 1, rank = 0;
     bool own_stream = true;
+    // peer receive buffers (cudaIpcOpenMemHandle) of the two transposes: [0] = A_RECV (G2), [1] = B_RECV (H) of every rank
+    double2* peer[2][kMaxPeers] = {};
+    bool p2p = false;
     unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
     int ring = 0;
     double t = 0.0;
@@ -188,6 +191,26 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ 
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// destination table of a pass output: local array (single GPU), local send buffer split per destination (slab, NCCL exchange),
+// or the peers' receive buffers (slab, direct NVLink stores)
+static OutPeers out_local(double2* arr) {
+    OutPeers o{};
+    o.p[0] = arr;
+    o.self = 0;
+    return o;
+}
+static OutPeers out_slab(const swrt_flow* h, int which /*0: A, 1: B*/, double2* send, int njobs) {
+    OutPeers o{};
+    if (h->p2p) {
+        for (int d = 0; d < h->P; ++d) o.p[d] = h->peer[which][d];
+        o.self = h->rank;
+    } else {   // send buffer laid out [dest][job][row][chunk]: block d starts at d * njobs * yrows * chunk
+        for (int d = 0; d < h->P; ++d) o.p[d] = send + (long long)d * njobs * h->L.yrows * h->L.kr_pad;
+        o.self = 0;
+    }
+    return o;
+}
+
 // ------------------------------------------------------------------ helpers
 static bool supported_n(int n) { return n >= 32 && n <= 4096 && (n & (n - 1)) == 0; }
 
@@ -237,7 +260,7 @@ static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
     if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "physical-space fields of a slab-decomposed flow are not gathered by the library");
     FieldLoader ld{h->sol, h->L.vs, which, h->nvar, h->d.f, h->L.aux0};
     cudaError_t e;
-    { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, h->G, h->tw_y, h->st)); }
+    { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(h->L.ny, e, LN::field_stage_a(ld, h->L, out_local(h->G), h->tw_y, h->st)); }
     CK(e);
     { ProfScope ps(h, K_FIELD_B); SWRT_DISPATCH(h->L.nx, e, LN::field_stage_b(h->G, dev_out, h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
@@ -264,6 +287,9 @@ int swrt_flow_destroy(swrt_flow* h) {
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
+    for (int w = 0; w < 2; ++w)
+        for (int r = 0; r < h->P; ++r)
+            if (h->peer[w][r] && r != h->rank) cudaIpcCloseMemHandle(h->peer[w][r]);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -506,7 +532,7 @@ static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
     const SpecLayout& L = h->L;
     const int model = h->d.model;
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, state, h->G, L, h->tw_y, h->st)); }
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a(model, state, out_local(h->G), L, h->tw_y, h->st)); }
     CK(e);
     { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->sched, h->st)); }
     CK(e);
@@ -719,11 +745,46 @@ int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbyt
     if (nbytes) *nbytes = nb;
     return SWRT_OK;
 }
+int swrt_slab_ipc_handle(swrt_flow* h, int which, void* handle64) {
+    if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    if (which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV) return fail(SWRT_ERR_ARG, "only the receive buffers are shared");
+    CK(cudaSetDevice(h->d.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, which == SWRT_SLAB_A_RECV ? (void*)h->G2 : (void*)h->H));
+    memcpy(handle64, &mh, 64);
+    return SWRT_OK;
+}
+int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handle64) {
+    if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    if ((which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV) || peer_rank < 0 || peer_rank >= h->P) return fail(SWRT_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(h->d.device));
+    const int w = which == SWRT_SLAB_A_RECV ? 0 : 1;
+    if (peer_rank == h->rank) {
+        h->peer[w][peer_rank] = w == 0 ? h->G2 : h->H;
+    } else {
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handle64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer[w][peer_rank] = (double2*)p;
+    }
+    bool all = true;
+    for (int w2 = 0; w2 < 2; ++w2)
+        for (int r = 0; r < h->P; ++r) all = all && h->peer[w2][r] != nullptr;
+    h->p2p = all;     // both transposes become direct peer stores once every receive buffer is mapped
+    return SWRT_OK;
+}
+int swrt_slab_p2p(swrt_flow* h, int* enabled) {
+    if (!h || !enabled) return fail(SWRT_ERR_ARG, "null pointer");
+    *enabled = h->p2p ? 1 : 0;
+    return SWRT_OK;
+}
 int swrt_slab_stage_a(swrt_flow* h) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(h->L.ny, e, LN::stage_a(h->d.model, h->sol, h->G, h->L, h->tw_y, h->st)); }
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(h->L.ny, e, LN::stage_a(h->d.model, h->sol, out_slab(h, 0, h->G, model_njobs_a(h->d.model)), h->L, h->tw_y, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -731,7 +792,7 @@ int swrt_slab_stage_b(swrt_flow* h) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, h->G2, h->H2, h->L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, h->G2, out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -757,7 +818,7 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     CK(cudaSetDevice(h->d.device));
     PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0};
     cudaError_t e;
-    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, h->G, h->tw_y, h->st)); }
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -789,7 +850,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
         psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, L, h->psih);
         CK(cudaGetLastError());
     }
-    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, h->G, h->tw_y, h->st)); }
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, out_local(h->G), h->tw_y, h->st)); }
     CK(e);
     { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp, L, h->tw_x, h->sched, h->st)); }
     CK(e);

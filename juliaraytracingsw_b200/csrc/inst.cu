@@ -9,7 +9,7 @@
 namespace swrt {
 
 template <>
-cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
         case MODEL_RSW:
         case MODEL_RSW_MODIFIED: {
@@ -30,23 +30,23 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
                                     cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1}, L, tw, sched, st);
-        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
+        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
         case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
-        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc}, L, tw, sched, st);
-        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc}, L, tw, sched, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
         case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched,
-                                         cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const double2* G_, const OutPeers& H, const SpecLayout& L, const double2* tw,
+                                         unsigned* sched, cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false, true>{G_, H, sc, s1}, L, tw, sched, st);
-        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{G_, H, sc}, L, tw, sched, st);
-        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{G_, H, sc}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false, true>{G_, nullptr, sc, s1, H}, L, tw, sched, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{G_, nullptr, sc, H}, L, tw, sched, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{G_, nullptr, sc, H}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -68,7 +68,7 @@ cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st) {
+cudaError_t Launch<SWRT_N>::field_stage_a(const FieldLoader& ld, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st) {
     return ypass_inv(ld, L, 1, G_, tw, st);
 }
 template <>
@@ -78,7 +78,7 @@ cudaError_t Launch<SWRT_N>::field_stage_b(const double2* G_, double* out, const 
     return xpass(op, L, tw, sched, st);
 }
 template <>
-cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw,
+cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw,
                                         cudaStream_t st) {
     if (psih) {   // jobs: psih, -i l psih, l^2 psih from the materialised field
         SimpleJobs sj{};

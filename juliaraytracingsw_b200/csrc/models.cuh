@@ -45,6 +45,7 @@ struct RswXOp {
     double2* H;        // [4 or 5][ny][kr_pad]
     double sc;         // (1/(nx ny))^2 / 2
     double s1;         // 1/(nx ny)
+    OutPeers peers;    // slab mode: destinations of the output column segments
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
         const auto Gu = row_ref<SLAB>(L, G, 5, 0, y), Gv = row_ref<SLAB>(L, G, 5, 1, y), Ge = row_ref<SLAB>(L, G, 5, 2, y), Guy = row_ref<SLAB>(L, G, 5, 3, y),
@@ -81,7 +82,7 @@ struct RswXOp {
             v[m] = make_double2(p1[m], sc * (ur[x] * v[m].x + vr[x] * v[m].y));
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_ref<SLAB>(L, H, NH, 0, y), row_ref<SLAB>(L, H, NH, 1, y));
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_out<SLAB>(L, H, peers, NH, 0, y), row_out<SLAB>(L, H, peers, NH, 1, y));
         cx.template load_pair<MUL_ONE, MUL_ZERO>(1, Ge, none);
         cx.ifft_regs_out(1, v);                          // eta
 #pragma unroll
@@ -95,12 +96,12 @@ struct RswXOp {
             v[m] = make_double2(sc * (ur[x] * e), sc * (vr[x] * e));
         }
         cx.fft_regs_in(v, 1);
-        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_ref<SLAB>(L, H, NH, 2, y), row_ref<SLAB>(L, H, NH, 3, y));
+        cx.template store_pair<MUL_ONE, MUL_ONE>(1, row_out<SLAB>(L, H, peers, NH, 2, y), row_out<SLAB>(L, H, peers, NH, 3, y));
         if (MODIFIED) {
 #pragma unroll
             for (int m = 0; m < 16; ++m) v[m] = make_double2(p1[m], 0.0);
             cx.fft_regs_in(v, 1);
-            cx.template store_pair<MUL_ONE, MUL_ZERO>(1, row_ref<SLAB>(L, H, NH, 4, y), none);
+            cx.template store_pair<MUL_ONE, MUL_ZERO>(1, row_out<SLAB>(L, H, peers, NH, 4, y), none);
         }
     }
 };
@@ -236,10 +237,11 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
     const double2* G;  // [3 NL][ny][kr_pad]
     double2* H;        // [2 NL][ny][kr_pad]
     double sc;
+    OutPeers peers;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
         auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 3 * NL, j, y); };
-        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 2 * NL, j, y); };
+        auto Hp = [&](int j) { return row_out<SLAB>(L, H, peers, 2 * NL, j, y); };
         double *q1 = cx.re(0), *q2 = cx.im(0);
         double2 v[16];
         if (NL == 2) cx.template load_pair<MUL_ONE, MUL_ONE>(1, Gp(0), Gp(3));
@@ -567,7 +569,7 @@ struct Launch {
         return cudaSuccess;
     }
     template <class Loader>
-    static cudaError_t ypass_inv(const Loader& ld, const SpecLayout& L, int njobs, double2* out, const double2* tw,
+    static cudaError_t ypass_inv(const Loader& ld, const SpecLayout& L, int njobs, const OutPeers& out, const double2* tw,
                                  cudaStream_t st) {
         auto k = ypass_inv_kernel<N, TK, Loader>;
         int mc = 1;
@@ -580,7 +582,7 @@ struct Launch {
     // prefetching variant for simple jobs; falls back to the plain kernel when the staging buffer does not fit
     static constexpr bool kPrefetchFits = ysmem + (size_t)ypass_stage_smem(N, TK) * 2 / 3 + 4096 <= (size_t)kSmemPerSM;
     template <class Loader>
-    static cudaError_t ypass_inv_simple(const SimpleJobs& jobs, const Loader& fallback, const SpecLayout& L, int njobs, double2* out,
+    static cudaError_t ypass_inv_simple(const SimpleJobs& jobs, const Loader& fallback, const SpecLayout& L, int njobs, const OutPeers& out,
                                         const double2* tw, cudaStream_t st) {
         const size_t stage = (size_t)(L.ny - (L.lz1 - L.lz0)) * TK * 16;
         static const int enabled = [] { const char* e = getenv("SWRT_YPASS_PREFETCH"); return e ? atoi(e) : 1; }();
@@ -636,15 +638,15 @@ struct Launch {
     }
 
     // concrete entry points (explicitly specialised per size in inst.cu); `model` = SWRT_* model id
-    static cudaError_t stage_a(int model, const double2* sol, double2* G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
+    static cudaError_t stage_a(int model, const double2* sol, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     // slab mode (P > 1): segmented rows; built for the models of the >= 4096^2 configurations (RSW, SWQG, two-layer QG)
-    static cudaError_t stage_b_slab(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t stage_b_slab(int model, const double2* G_, const OutPeers& H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t snap_stage_b_slab(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
-    static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
-    static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, double2* G_, const double2* tw, cudaStream_t st);
+    static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
     static cudaError_t snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
 };

@@ -37,6 +37,20 @@ __device__ __forceinline__ long long inter_off(const SpecLayout& L, int njobs, i
     const int blk = y >> L.yshift, yl = y & ((1 << L.yshift) - 1);
     return ((((long long)blk * njobs + job) << L.yshift) + yl) * L.kr_pad;
 }
+// Where a transform pass writes its output.  Single GPU: one local array.  Slab mode: the block of rows (y-pass) or of
+// columns (x-pass) destined for rank d is stored straight into rank d's receive buffer over NVLink (peer memory mapped
+// with cudaIpcOpenMemHandle) at the position reserved for this rank -- the all-to-all transpose IS the store of the FFT
+// pass; no send buffer, no separate exchange kernel.  Without peer mapping p[d] points into the local send buffer.
+constexpr int kMaxPeers = 16;
+struct OutPeers {
+    double2* p[kMaxPeers];
+    int self;    // index of this rank's block inside a peer's receive buffer
+};
+__device__ __forceinline__ double2* out_at(const OutPeers& o, const SpecLayout& L, int njobs, int job, int y) {
+    const int blk = y >> L.yshift, yl = y & ((1 << L.yshift) - 1);
+    return o.p[blk] + ((((long long)o.self * njobs + job) << L.yshift) + yl) * L.kr_pad;
+}
+
 // One x-pass row (fixed job and local row).  Single GPU: kr_pad contiguous columns (RowPlain).  Slab mode: P segments of
 // kr_pad columns (one per source/destination rank), `skip + chunk` elements apart (RowSeg).  The row type is a template
 // parameter of the x-pass ops so that the single-GPU kernels carry no segment arithmetic at all.
@@ -54,6 +68,16 @@ struct RowSeg {
         return base + off;
     }
 };
+struct RowSegOut {   // x-pass output row in slab mode: column segment s goes to peer s
+    const OutPeers* peers;
+    long long off;    // offset of (this rank's block, job, local row) inside a peer's buffer
+    int chunk, nseg;
+    __device__ __forceinline__ double2* at(int k) const {
+        int s = 0;
+        for (int j = 1; j < nseg; ++j) s += k >= j * chunk ? 1 : 0;
+        return peers->p[s] + off + (k - s * chunk);
+    }
+};
 template <bool SLAB>
 struct RowOf { using type = RowPlain; };
 template <>
@@ -66,6 +90,25 @@ __device__ __forceinline__ typename RowOf<SLAB>::type row_ref(const SpecLayout& 
         r.skip = ((long long)njobs << L.yshift) * L.kr_pad - L.kr_pad;
         r.chunk = L.kr_pad;
         r.nseg = L.ny >> L.yshift;
+    }
+    return r;
+}
+template <bool SLAB>
+struct RowOutOf { using type = RowPlain; };
+template <>
+struct RowOutOf<true> { using type = RowSegOut; };
+// output row of the x-pass: `arr` is the local array on a single GPU, `peers` the destination table in slab mode
+template <bool SLAB>
+__device__ __forceinline__ typename RowOutOf<SLAB>::type row_out(const SpecLayout& L, double2* arr, const OutPeers& peers, int njobs, int job,
+                                                                 int yl) {
+    typename RowOutOf<SLAB>::type r;
+    if constexpr (SLAB) {
+        r.peers = &peers;
+        r.off = ((((long long)peers.self * njobs + job) << L.yshift) + yl) * L.kr_pad;
+        r.chunk = L.kr_pad;
+        r.nseg = L.ny >> L.yshift;
+    } else {
+        r.base = arr + (((long long)job << L.yshift) + yl) * L.kr_pad;
     }
     return r;
 }
@@ -105,7 +148,7 @@ __host__ __device__ constexpr long long xpass_smem(int N, int nbuf) { return 2LL
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Loader>
 __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, TK), TK* group_size(N)))
-    ypass_inv_kernel(Loader ld, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
+    ypass_inv_kernel(Loader ld, SpecLayout L, int njobs, OutPeers out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     constexpr int G = group_size(N), NP = col_stride(N, TK);
     const int tid = threadIdx.x;
@@ -127,7 +170,7 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
         block_fft_regs<N, +1>(v, re, im, g, tw);
         if (col_ok) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) out[inter_off(L, njobs, job, g + m * G) + kr] = v[m];
+            for (int m = 0; m < 16; ++m) out_at(out, L, njobs, job, g + m * G)[kr] = v[m];
         }
     }
 }
@@ -152,7 +195,7 @@ __host__ __device__ constexpr long long ypass_stage_smem(int N, int TK) { return
 
 template <int N, int TK>
 __global__ void __launch_bounds__(TK* group_size(N), 1)
-    ypass_inv_prefetch_kernel(SimpleJobs jobs, SpecLayout L, int njobs, double2* __restrict__ out, const double2* __restrict__ tw) {
+    ypass_inv_prefetch_kernel(SimpleJobs jobs, SpecLayout L, int njobs, OutPeers out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     constexpr int G = group_size(N), NP = col_stride(N, TK), NT = TK * G;
     const int tid = threadIdx.x;
@@ -199,7 +242,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
         block_fft_regs<N, +1>(v, re, im, g, tw);
         if (kr < L.kr_keep) {
 #pragma unroll
-            for (int m = 0; m < 16; ++m) out[inter_off(L, njobs, job, g + m * G) + kr] = v[m];
+            for (int m = 0; m < 16; ++m) out_at(out, L, njobs, job, g + m * G)[kr] = v[m];
         }
     }
 }

@@ -30,7 +30,9 @@ class SlabProblem(flow.Problem):
     """`Problem` whose step is distributed over the ranks of `dist` (a torch.distributed process group).
     Supported: RotatingShallowWater, SWQG, TwoLayerQG with the IFMAB3 stepper."""
 
-    def __init__(self, dist, dev=0, **kw):
+    def __init__(self, dist, dev=0, p2p=True, **kw):
+        """p2p=True: the transposes are direct NVLink stores into the peers' receive buffers (CUDA IPC) followed by a
+        stream-ordered barrier; p2p=False: NCCL all_to_all_single on send/receive buffers."""
         import torch
         self.dist, self.torch = dist, torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
@@ -45,8 +47,37 @@ class SlabProblem(flow.Problem):
             check(lib().swrt_slab_buffer(self._h, which, C.byref(p), C.byref(n)))
             self._buf[which] = torch.as_tensor(_DevBuf(p.value, n.value), device=f"cuda:{dev}")
         self.kr_lo = self.rank * self.chunk
+        self._flag = torch.zeros(1, device=f"cuda:{dev}")
+        self.p2p = False
+        if p2p:
+            self._open_peers()
+
+    def _open_peers(self):
+        """Exchange the CUDA IPC handles of the two receive buffers and map every peer's."""
+        L = lib()
+        mine = {}
+        for which in (A_RECV, B_RECV):
+            buf = C.create_string_buffer(64)
+            check(L.swrt_slab_ipc_handle(self._h, which, buf))
+            mine[which] = buf.raw
+        allh = [None] * self.world
+        self.dist.all_gather_object(allh, mine)
+        for r, hs in enumerate(allh):
+            for which in (A_RECV, B_RECV):
+                check(L.swrt_slab_ipc_open(self._h, which, r, hs[which]))
+        en = C.c_int()
+        check(L.swrt_slab_p2p(self._h, C.byref(en)))
+        self.p2p = bool(en.value)
+        self._barrier()
+
+    def _barrier(self):
+        """Stream-ordered barrier: every rank's earlier kernels (and their peer stores) are complete before anything after it runs."""
+        self.dist.all_reduce(self._flag)
 
     def _a2a(self, recv, send, njobs):
+        if self.p2p:                                                # the pass already stored into the peers' buffers
+            self._barrier()
+            return
         n = self.world * njobs * self.yrows * self.chunk * 2        # doubles: [dest][job][row][chunk] complex128
         self.dist.all_to_all_single(self._buf[recv][:n], self._buf[send][:n])
 

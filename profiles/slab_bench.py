@@ -19,6 +19,7 @@ from juliaraytracingsw_b200.slab import SlabProblem  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--nx", type=int, default=4096)
 ap.add_argument("--model", default="TwoLayerQG")
+ap.add_argument("--no-p2p", action="store_true")
 ap.add_argument("--steps", type=int, default=30)
 a = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -36,7 +37,7 @@ if a.model == "TwoLayerQG":
 rng = np.random.default_rng(0)
 sol = np.zeros((nx // 2 + 1, nx, nvar), dtype=np.complex128)
 sol[1:24, :24] = (rng.standard_normal((23, 24, nvar)) + 1j * rng.standard_normal((23, 24, nvar))) * nx * nx * 1e-3
-prob = SlabProblem(dist, local, **kw) if world > 1 else swrt.Problem(local, **kw)
+prob = SlabProblem(dist, local, p2p=not a.no_p2p, **kw) if world > 1 else swrt.Problem(local, **kw)
 prob.sol = sol if nvar > 1 else sol[:, :, 0]
 step = (lambda n: prob.stepforward(n)) if world > 1 else (lambda n: flow.stepforward(prob, (), n))
 step(5)

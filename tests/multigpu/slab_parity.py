@@ -42,13 +42,14 @@ def main():
     cases = [("RotatingShallowWater", 3, dict(f=3.0, Cg=1.0), raytracing.PSI_RSW_BALANCED),
              ("TwoLayerQG", 2, dict(U=0.5, mu=1e-2, f0=3.0, Cg=1.0), raytracing.PSI_TWOLAYER_BAROCLINIC),
              ("SWQG", 1, dict(f=3.0, Cg=1.0), raytracing.PSI_SWQG)]
-    for nx in (128, 512):
+    for nx, p2p in ((128, True), (512, True), (256, False)):
         for model, nvar, kw, psi in cases:
             dt = 0.05 * 2 * np.pi / nx
             nu = 2 * np.pi / nx / ((nx / 2 - 1) ** 8) / dt
             sol0 = smooth_state(nx, nvar, 7 + nx)
             ref = swrt.Problem(local, model=model, nx=nx, dt=dt, nu=nu, nnu=4, **kw)
-            sp = SlabProblem(dist, local, model=model, nx=nx, dt=dt, nu=nu, nnu=4, **kw)
+            sp = SlabProblem(dist, local, p2p=p2p, model=model, nx=nx, dt=dt, nu=nu, nnu=4, **kw)
+            assert sp.p2p == p2p
             ref.sol = sol0 if nvar > 1 else sol0[:, :, 0]
             sp.sol = sol0 if nvar > 1 else sol0[:, :, 0]
             for n in (1, 3, 8):
