@@ -7,7 +7,6 @@ from juliaraytracingsw_b200._lib import check, lib
 from juliaraytracingsw_b200.slab import SlabProblem, A_RECV, A_SEND, B_RECV, B_SEND
 
 ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=4096); ap.add_argument("--model", default="TwoLayerQG"); ap.add_argument("--no-p2p", action="store_true")
-ap.add_argument("--no-p2p", action="store_true")
 a = ap.parse_args()
 local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
