@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--nx", type=int, default=2048)
     ap.add_argument("--sqrt-packets", type=int, default=4096)
     ap.add_argument("--nsub", type=int, default=1)
+    ap.add_argument("--workload", default="config4", choices=["config4", "config5"],
+                    help="config4 (default): RSW 2048^2 + 16.8M packets, flow replicated; config5: two-layer QG 4096^2 slab-decomposed "
+                         "over the ranks + 67M packets (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -330,9 +333,91 @@ def run_swrt(args):
         dist.destroy_process_group()
 
 
+def run_config5(args):
+    """BASELINE config 5: two-layer QG 4096^2, flow slab-decomposed over the ranks (direct NVLink transposes), 8192^2 packets
+    sharded over the ranks.  Separate, smaller JSON line (not the driver's default workload)."""
+    import torch
+    import torch.distributed as dist
+
+    import juliaraytracingsw_b200 as swrt
+    from juliaraytracingsw_b200 import flow, raytracing
+    from juliaraytracingsw_b200.slab import SlabProblem
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx = 4096 if args.nx == 2048 else args.nx
+    sq = 8192 if args.sqrt_packets == 4096 else args.sqrt_packets
+    ntot = sq * sq
+    lo, hi = rank * ntot // world, (rank + 1) * ntot // world
+    # swqg/TwoLayerParameters.jl recipe: f=3, Cg=1, rd=1/6, l=1, ug=0.025, cfltune=0.025, nutune=40, nnu=4
+    f, Cg, ug = 3.0, 1.0, 0.025
+    dt = 0.025 / ug * (2 * np.pi / nx) * ug
+    nu = 40 * 2 * np.pi / nx / ((nx / 2 - 1) ** 8) / dt
+    kw = dict(model="TwoLayerQG", nx=nx, dt=dt, nu=nu, nnu=4, f=f, Cg=Cg, U=ug, mu=1e-2, f0=f)
+    prob = SlabProblem(dist, local, **kw) if world > 1 else swrt.Problem(local, **kw)
+    rng = np.random.default_rng(0)
+    sol = np.zeros((nx // 2 + 1, nx, 2), dtype=np.complex128)
+    sol[1:24, :24] = (rng.standard_normal((23, 24, 2)) + 1j * rng.standard_normal((23, 24, 2))) * nx * nx * 1e-3
+    prob.sol = sol
+    k0 = (3.0 ** 0.5) * f / Cg
+    packets = raytracing.generate_initial_wavepackets(prob, 2 * np.pi, k0, hi - lo, sq, f, Cg, nsub=args.nsub, first=lo)
+    psi = raytracing.PSI_TWOLAYER_BAROCLINIC
+
+    def snapshot(slot):
+        if world > 1:
+            prob.velocity_snapshot(slot, psi)
+        else:
+            raytracing.get_velocity_info(prob, slot, psi)
+
+    def step(t):
+        if world > 1:
+            prob.stepforward(1)
+        else:
+            flow.stepforward(prob, (), 1)
+        snapshot(1)
+        tn = prob.clock.t
+        raytracing.raytrace(packets, None, None, None, None, prob.grid, packets, dt, (t, tn))
+        raytracing.swap_snapshots(prob)
+        return tn
+
+    snapshot(0)
+    t = prob.clock.t
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        t = step(t)
+    torch.cuda.synchronize(); prob.sync(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        e0.record()
+        for _ in range(K):
+            t = step(t)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    else:
+        prob.timer_start()
+        for _ in range(K):
+            t = step(t)
+        ms = prob.timer_stop()
+    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(tt)
+        print(json.dumps({"metric": "packet-steps/s", "value": ntot * K / (ms * 1e-3), "unit": "packet-steps/s", "n_gpus": world, "steps": K,
+                          "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"two-layer QG {nx}^2 IFMAB3, flow slab-decomposed over {world} GPU(s) with direct NVLink "
+                                                 f"transposes, + RK4 ray tracing of {ntot} packets sharded over the ranks (BASELINE config 5)",
+                                     "nx": nx, "packets": ntot, "packet_positions": "reference lattice", "parallelism": f"slab x{world}"}}),
+              flush=True)
+    dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "config5":
+        run_config5(a)
     else:
         run_swrt(a)

@@ -844,7 +844,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     bool materialise = false;
     SWRT_DISPATCH(L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
     CK(e);
-    if (materialise) {
+    if (materialise && L.kr_keep > 0) {
         const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
         ProfScope ps(h, K_PSI);
         psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, L, h->psih);

@@ -576,6 +576,7 @@ struct Launch {
         cudaError_t e = prep(k, ysmem, TK * G, &mc);
         if (e != cudaSuccess) return e;
         const int work = ((L.kr_keep + TK - 1) / TK) * njobs;
+        if (work == 0) return cudaSuccess;   // a slab rank beyond the retained columns owns nothing
         k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(ld, L, njobs, out, tw);
         return cudaGetLastError();
     }
@@ -593,6 +594,7 @@ struct Launch {
                 cudaError_t e = prep(k, ysmem + stage, TK * G, &mc);
                 if (e != cudaSuccess) return e;
                 const int work = ((L.kr_keep + TK - 1) / TK) * njobs;
+                if (work == 0) return cudaSuccess;
                 k<<<work < mc ? work : mc, TK * G, ysmem + stage, st>>>(jobs, L, njobs, out, tw);
                 return cudaGetLastError();
             }
@@ -614,6 +616,7 @@ struct Launch {
                 cudaError_t ep = prep(kp, smem, TK * G, &mcp);
                 if (ep != cudaSuccess) return ep;
                 const int workp = ((L.kr_keep + TK - 1) / TK) * nvars;
+                if (workp == 0) return cudaSuccess;
                 kp<<<workp < mcp ? workp : mcp, TK * G, smem, st>>>(cb, L, nvars, nh, rows_s, H, out, tw);
                 return cudaGetLastError();
             }
@@ -623,6 +626,7 @@ struct Launch {
         cudaError_t e = prep(k, ysmem, TK * G, &mc);
         if (e != cudaSuccess) return e;
         const int work = ((L.kr_keep + TK - 1) / TK) * nvars;
+        if (work == 0) return cudaSuccess;
         k<<<work < mc ? work : mc, TK * G, ysmem, st>>>(cb, L, nvars, nh, H, out, tw);
         return cudaGetLastError();
     }
