@@ -390,3 +390,79 @@ def test_hermite_bicubic_mode_parity(nsub):
     pk2 = raytracing.Packets(prob, 16, c["f"], c["Cg"])
     with pytest.raises(swrt.SwrtError):
         raytracing.raytrace(pk2, None, None, None, None, prob.grid, pk2, c["dt"], (t0, t1))
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_single_packet_and_far_outside_domain():
+    """generate_single_wavepacket (raytracing/RaytracingDriver.jl:16-25): N = 1; packets are never wrapped (they drift to |x| ~ 60)."""
+    g, c, Fo, Fn, _, _ = _packet_case(64, 4, 1)
+    prob = swrt.Problem(nx=64, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_velocity_info(prob, 0, Fo)
+    raytracing.set_velocity_info(prob, 1, Fn)
+    for x0 in ((0.3, -1.2), (-61.7, 59.9), (1e4 + 0.25, -1e4 - 0.75)):
+        xk = np.array([[x0[0], x0[1], 2.0, -4.5]])
+        pk = raytracing.Packets(prob, 1, c["f"], c["Cg"], nsub=3)
+        pk.set(xk, np.ones(1))
+        raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (0.0, 0.2))
+        want = oray.raytrace(xk.copy(), np.ones(1), 0.0, 0.2, Fo, Fn, g, c["f"], c["Cg"], nsub=3)
+        np.testing.assert_allclose(pk.get(), want, rtol=1e-9, atol=1e-9)
+
+
+def test_zero_flow_packets_move_with_group_velocity_only():
+    prob = swrt.Problem(nx=64, f=3.0, Cg=1.0, dt=1e-2)
+    xk, sign = oray.generate_initial_wavepackets(2 * np.pi, 5.0, 8)
+    pk = raytracing.Packets(prob, 64, 3.0, 1.0, nsub=1)
+    pk.set(xk, sign)
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, 1e-2, (0.0, 0.5))
+    got = pk.get()
+    w = sign * np.sqrt(9.0 + xk[:, 2] ** 2 + xk[:, 3] ** 2)
+    np.testing.assert_allclose(got[:, 0], xk[:, 0] + 0.5 * xk[:, 2] / w, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(got[:, 1], xk[:, 1] + 0.5 * xk[:, 3] / w, rtol=0, atol=1e-13)
+    np.testing.assert_array_equal(got[:, 2:4], xk[:, 2:4])          # k is exactly conserved without a background flow
+
+
+def test_zero_state_stays_zero_and_aliased_fraction_zero():
+    prob = swrt.Problem(nx=64, f=3.0, dt=1e-2)
+    flow.stepforward(prob, (), 5)
+    assert np.all(prob.sol == 0) and prob.clock.step == 5
+    # aliased_fraction = 0 (all MultiLayerQG runs, raytracing/TwoLayerRaytracing.jl:174): only the Nyquist row/column is dropped
+    g = TwoDGrid(64, aliased_fraction=0)
+    rng = np.random.default_rng(3)
+    sol = rng.standard_normal((g.nkr, g.nl, 3)) + 1j * rng.standard_normal((g.nkr, g.nl, 3))
+    p0 = swrt.Problem(nx=64, f=3.0, dt=1e-3, aliased_fraction=0)
+    p0.sol = sol
+    want = g.dealias(sol.copy())
+    np.testing.assert_array_equal(p0.sol, want)
+    assert np.count_nonzero(want[:, :, 0]) == (g.nkr - 1) * (g.nl - 1)
+    assert rel_l2(p0.vars.u, g.irfft2(want[:, :, 0])) < 2e-14
+
+
+def test_rectangular_grid_step_parity():
+    from oracle import ifmab3 as oif
+    nx, ny, Lx, Ly = 128, 64, 2 * np.pi, np.pi
+    g, sol0 = random_state(nx, ny, seed=33, amp=0.2, Lx=Lx, Ly=Ly)
+    p = orsw.Params(1e-9, 4, 3.0, 1.0)
+    prob = swrt.Problem(nx=nx, ny=ny, Lx=Lx, Ly=Ly, dt=2e-3, f=3.0, Cg=1.0, nu=1e-9, nnu=4)
+    prob.sol = sol0
+    flow.stepforward(prob, (), 12)
+    assert rel_l2(prob.sol, oracle_steps(g, p, sol0, 2e-3, 12)) < 1e-11
+
+
+def test_4096_transform_properties():
+    """Largest supported size: Parseval and a round trip through the physical field (size-independent properties)."""
+    nx = 4096
+    g = TwoDGrid(nx)
+    rng = np.random.default_rng(4)
+    sol = np.zeros((g.nkr, g.nl, 3), dtype=np.complex128)
+    sol[:40, :40] = rng.standard_normal((40, 40, 3)) + 1j * rng.standard_normal((40, 40, 3))
+    sol[:40, -40:] = rng.standard_normal((40, 40, 3)) + 1j * rng.standard_normal((40, 40, 3))
+    sol[0, :, :] = 0                                              # keep the kr = 0 column trivially Hermitian
+    prob = swrt.Problem(nx=nx, f=3.0, dt=1e-4)
+    prob.sol = sol
+    u = prob.vars.u
+    assert rel_l2(u, g.irfft2(sol[:, :, 0])) < 1e-13
+    ke = flow.kinetic_energy(prob)
+    v = prob.vars.v
+    assert abs(0.5 * ((u ** 2).sum() + (v ** 2).sum()) * g.dx * g.dy / (g.Lx * g.Ly) / ke - 1) < 1e-12
+    flow.stepforward(prob, (), 2)
+    assert not flow.has_nan(prob)
