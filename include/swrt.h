@@ -25,7 +25,7 @@ enum { SWRT_OK = 0, SWRT_ERR_ARG = -1, SWRT_ERR_CUDA = -2, SWRT_ERR_UNSUPPORTED 
 
 /* models: rsw/RotatingShallowWater.jl, rsw/ModifiedShallowWater.jl, rsw/LinborgShallowWater.jl,
  * swqg/SWQG.jl, swqg/TwoLayerQG.jl, thomasyamada/ThomasYamada.jl */
-enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_SWQG = 4, SWRT_TWOLAYERQG = 5, SWRT_THOMASYAMADA = 6 };
+enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_RSW_QUADHEIGHT = 3 /* rsw/QuadHeightModifiedShallowWater.jl */, SWRT_SWQG = 4, SWRT_TWOLAYERQG = 5, SWRT_THOMASYAMADA = 6 };
 /* steppers: utils/IFMAB3.jl; FourierFlows FilteredAB3 / ETDRK4 / FilteredRK4 (raytracing/CPUParameters.jl:7) */
 enum { SWRT_IFMAB3 = 0, SWRT_FILTEREDAB3 = 1, SWRT_ETDRK4 = 2, SWRT_FILTEREDRK4 = 3 };
 
@@ -72,6 +72,9 @@ enum { SWRT_FIELD_U = 0, SWRT_FIELD_V = 1, SWRT_FIELD_ETA = 2, SWRT_FIELD_ZETA =
        /* QG models (swqg/SWQG.jl:109-125, swqg/TwoLayerQG.jl:113-129): state variable j = q_j; add the layer index */
        SWRT_FIELD_QG_PSI = 32, SWRT_FIELD_QG_U = 40, SWRT_FIELD_QG_V = 48, SWRT_FIELD_QG_ZETA = 56 };
 int swrt_flow_get_field(swrt_flow* h, int which, double* real_host);
+/* mul!(varh, grid.rfftplan, field): forward transform of a physical (nx, ny) field into state variable `var` (dealiased),
+ * e.g. m0h = rfft(1/(1+eta0)) of rsw/QuadHeightModifiedShallowWater.jl:333-347 or initial conditions given on the grid */
+int swrt_flow_set_field_physical(swrt_flow* h, int var, const double* real_host);
 /* kinetic_energy(prob), potential_energy(prob): rsw/RotatingShallowWater.jl:323-336, swqg/SWQG.jl:205-222,
  * swqg/TwoLayerQG.jl:221-250 (two-layer: ke = KE_1 + KE_2; the per-layer values through swrt_flow_layer_kinetic_energy) */
 int swrt_flow_energies(swrt_flow* h, double* ke, double* pe);

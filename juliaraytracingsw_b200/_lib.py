@@ -51,6 +51,7 @@ SIGNATURES = {
     "swrt_flow_clock": (_I, [_P, _PD, _PLL]),
     "swrt_flow_set_clock": (_I, [_P, _D, _LL]),
     "swrt_flow_get_field": (_I, [_P, _I, _P]),
+    "swrt_flow_set_field_physical": (_I, [_P, _I, _P]),
     "swrt_flow_energies": (_I, [_P, _PD, _PD]),
     "swrt_flow_layer_kinetic_energy": (_I, [_P, _I, _PD]),
     "swrt_flow_max_abs_uv": (_I, [_P, _PD, _PD]),

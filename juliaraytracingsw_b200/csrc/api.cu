@@ -304,7 +304,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     *out = nullptr;
     const swrt_flow_desc& d = *desc;
     if (!supported_n(d.nx) || !supported_n(d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "nx, ny must be powers of two in [32, 4096] (got %d x %d)", d.nx, d.ny);
-    const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG;
+    const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG || d.model == SWRT_RSW_QUADHEIGHT;
     const bool diag_L = d.model == SWRT_SWQG || d.model == SWRT_THOMASYAMADA;
     if (!rsw_family && !diag_L && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
     if (d.stepper < SWRT_IFMAB3 || d.stepper > SWRT_FILTEREDRK4) return fail(SWRT_ERR_ARG, "unknown stepper %d", d.stepper);
@@ -392,7 +392,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
         std::vector<double4> cf2;
         if (d.stepper == SWRT_ETDRK4) cf2.assign((size_t)L.vs, make_double4(0, 0, 0, 0));
         if (d.model == SWRT_TWOLAYERQG) { E.assign((size_t)4 * L.vs, make_double2(0, 0)); E2 = E; }
-        const double w2c = d.model == SWRT_RSW_MODIFIED ? 0.0 : L.Cg2;
+        const double w2c = (d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_QUADHEIGHT) ? 0.0 : L.Cg2;
         const double innerK = d.filter_innerK > 0 ? d.filter_innerK : 2.0 / 3.0, outerK = d.filter_outerK > 0 ? d.filter_outerK : 1.0;
         const double tol = d.filter_tol > 0 ? d.filter_tol : 1e-15;
         const int order = d.filter_order > 0 ? d.filter_order : 4;
@@ -501,8 +501,8 @@ int swrt_flow_enforce_reality(swrt_flow* h) {
 static int ifmab3_update_launch(swrt_flow* h, double2* Ncur) {
     const SpecLayout& L = h->L;
     const int model = h->d.model, stepper = h->d.stepper;
-    const bool modified = model == SWRT_RSW_MODIFIED;
-    RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2};
+    const bool modified = model == SWRT_RSW_MODIFIED || model == SWRT_RSW_QUADHEIGHT;
+    RswLin lin{h->d.f, modified ? 0.0 : L.Cg2, modified ? 0.0 : L.Cg2, model == SWRT_RSW_QUADHEIGHT ? 0.0 : 1.0};
     const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
     if (nmodes == 0) return SWRT_OK;
     const int ublocks = (int)((nmodes + 255) / 256);
@@ -631,6 +631,22 @@ static double spectral_diag(swrt_flow* h, int which, int arg, cudaError_t* err) 
     return acc * h->d.Lx * h->d.Ly / ((double)L.nx * L.nx * (double)L.ny * L.ny);   // parsevalsum normalisation
 }
 
+int swrt_flow_set_field_physical(swrt_flow* h, int var, const double* real_host) {
+    if (!h || !real_host) return fail(SWRT_ERR_ARG, "null pointer");
+    if (var < 0 || var >= h->nvar) return fail(SWRT_ERR_ARG, "state variable %d out of range", var);
+    if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow");
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    CK(cudaMemcpyAsync(h->phys, real_host, sizeof(double) * (size_t)h->d.nx * h->d.ny, cudaMemcpyHostToDevice, h->st));
+    cudaError_t e;
+    { ProfScope ps(h, K_FIELD_B); SWRT_DISPATCH(L.nx, e, LN::forward_field(h->phys, h->H, nullptr, L, h->tw_x, h->sched, h->st)); }
+    CK(e);
+    { ProfScope ps(h, K_FIELD_A); SWRT_DISPATCH(L.ny, e, LN::forward_field_y(h->H, h->sol + (long long)var * L.vs, L, h->tw_y, h->st)); }
+    CK(e);
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
 int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
@@ -652,7 +668,16 @@ int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
     } else {                                   // rsw/RotatingShallowWater.jl:323-336
         k = spectral_diag(h, DIAG_ABS2_VAR, 0, &e) / (2 * A); CK(e);
         k += spectral_diag(h, DIAG_ABS2_VAR, 1, &e) / (2 * A); CK(e);
-        p = 0.5 * L.Cg2 * spectral_diag(h, DIAG_ABS2_VAR, 2, &e) / A; CK(e);
+        if (h->d.model == SWRT_RSW_QUADHEIGHT) {   // rsw/QuadHeightModifiedShallowWater.jl:355-358: 0.5 Cg2 Re(mh[1,1]) / (Lx Ly)
+            double2 m00 = make_double2(0, 0);
+            if (L.kr_off == 0) {
+                CK(cudaMemcpyAsync(&m00, h->sol + 2 * L.vs, sizeof m00, cudaMemcpyDeviceToHost, h->st));
+                CK(cudaStreamSynchronize(h->st));
+            }
+            p = 0.5 * L.Cg2 * m00.x / A;
+        } else {
+            p = 0.5 * L.Cg2 * spectral_diag(h, DIAG_ABS2_VAR, 2, &e) / A; CK(e);
+        }
     }
     if (ke) *ke = k;
     if (pe) *pe = p;
@@ -700,7 +725,7 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag) {
 }
 
 static int check_psi_kind(swrt_flow* h, int psi_kind) {
-    const bool rsw_family = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;
+    const bool rsw_family = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;   // (QuadHeight carries m, not eta)
     const bool ok = (psi_kind == SWRT_PSI_RSW_BALANCED && rsw_family) || (psi_kind == SWRT_PSI_SWQG && h->d.model == SWRT_SWQG) ||
                     ((psi_kind == SWRT_PSI_TWOLAYER_BAROCLINIC || psi_kind == SWRT_PSI_TWOLAYER_MEAN) && h->d.model == SWRT_TWOLAYERQG);
     return ok ? SWRT_OK : fail(SWRT_ERR_ARG, "psi kind %d does not apply to model %d", psi_kind, h->d.model);

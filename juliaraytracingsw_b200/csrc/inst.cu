@@ -12,6 +12,7 @@ template <>
 cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
         case MODEL_RSW:
+        case MODEL_RSW_QUADHEIGHT:
         case MODEL_RSW_MODIFIED: {
             SimpleJobs sj{};
             const int fld[5] = {0, 1, 2, 0, 1}, mul[5] = {YMUL_ONE, YMUL_ONE, YMUL_ONE, YMUL_IL, YMUL_IL};
@@ -30,8 +31,9 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
                                     cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
-        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, true>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
+        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, 1>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
+        case MODEL_RSW_QUADHEIGHT: return xpass(RswXOp<SWRT_N, 2>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
         case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
@@ -44,7 +46,7 @@ cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const double2* G_, const Out
                                          unsigned* sched, cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, false, true>{G_, nullptr, sc, s1, H}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{G_, nullptr, sc, s1, H}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{G_, nullptr, sc, H}, L, tw, sched, st);
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{G_, nullptr, sc, H}, L, tw, sched, st);
     }
@@ -59,6 +61,7 @@ template <>
 cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {
     switch (model) {
         case MODEL_RSW: return ypass_fwd(RswCombiner{0, L.Cg2}, L, 3, 4, H, Nout, tw, st);
+        case MODEL_RSW_QUADHEIGHT:
         case MODEL_RSW_MODIFIED: return ypass_fwd(RswCombiner{1, L.Cg2}, L, 3, 5, H, Nout, tw, st);
         case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, 3, H, Nout, tw, st);
         case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, 2, H, Nout, tw, st);
@@ -76,6 +79,15 @@ cudaError_t Launch<SWRT_N>::field_stage_b(const double2* G_, double* out, const 
                                           cudaStream_t st) {
     C2ROp<SWRT_N> op{G_, out, 1.0 / ((double)L.nx * (double)L.ny)};
     return xpass(op, L, tw, sched, st);
+}
+template <>
+cudaError_t Launch<SWRT_N>::forward_field(const double* in, double2* H, double2*, const SpecLayout& L, const double2* tw_x, unsigned* sched,
+                                          cudaStream_t st) {
+    return xpass(R2COp<SWRT_N>{in, H}, L, tw_x, sched, st);
+}
+template <>
+cudaError_t Launch<SWRT_N>::forward_field_y(const double2* H, double2* out, const SpecLayout& L, const double2* tw_y, cudaStream_t st) {
+    return ypass_fwd(IdentityCombiner{}, L, 1, 1, H, out, tw_y, st);
 }
 template <>
 cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw,

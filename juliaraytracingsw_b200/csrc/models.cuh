@@ -13,12 +13,12 @@
 
 namespace swrt {
 
-enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5, MODEL_THOMASYAMADA = 6 };
+enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_RSW_QUADHEIGHT = 3, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5, MODEL_THOMASYAMADA = 6 };
 
 // per-model sizes: state variables, y-transformed intermediates (stage A jobs), x-transformed products (stage B outputs)
 __host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (m == MODEL_TWOLAYERQG ? 2 : (m == MODEL_THOMASYAMADA ? 4 : 3)); }
 __host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 3 : (m == MODEL_TWOLAYERQG ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
-__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : (m == MODEL_RSW_MODIFIED ? 5 : 4))); }
+__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : ((m == MODEL_RSW_MODIFIED || m == MODEL_RSW_QUADHEIGHT) ? 5 : 4))); }
 
 // ---------------------------------------------------------------- RSW family, stage A
 // jobs: 0 uh, 1 vh, 2 etah, 3 i l uh, 4 i l vh     (ux, vx are derived in the x-pass as i k G)
@@ -38,7 +38,8 @@ struct RswLoaderA {
 
 // ---------------------------------------------------------------- RSW family, stage B
 // p1 = u ux + v uy, p2 = u vx + v vy, p3 = u eta, p4 = v eta [, p5 = 1.5 - 0.5/(1+eta)^2]
-template <int N, bool MODIFIED, bool SLAB = false>
+// MODIFIED: 0 plain RSW, 1 Modified (G = 1.5 - 0.5/(1+eta)^2), 2 QuadHeight (third variable m, G = 1.5 - 0.5 m^2)
+template <int N, int MODIFIED, bool SLAB = false>
 struct RswXOp {
     static constexpr int NBUF = 2;
     const double2* G;  // [5][ny][kr_pad]
@@ -89,9 +90,12 @@ struct RswXOp {
         for (int m = 0; m < 16; ++m) {
             const int x = pad_index(cx.g + m * Gt);
             const double e = v[m].x;
-            if (MODIFIED) {
+            if (MODIFIED == 1) {
                 const double e1 = 1.0 + s1 * e;
                 p1[m] = 0.5 * (1.5 - 0.5 / (e1 * e1));
+            } else if (MODIFIED == 2) {
+                const double mm = s1 * e;
+                p1[m] = 0.5 * (1.5 - 0.5 * (mm * mm));
             }
             v[m] = make_double2(sc * (ur[x] * e), sc * (vr[x] * e));
         }
@@ -450,6 +454,30 @@ struct C2ROp {
     }
 };
 
+// physical -> spectral: forward transform of one real field (set a state variable from physical space,
+// e.g. m = 1/(1+eta) of the QuadHeight model, or initial conditions given on the grid)
+template <int N, bool SLAB = false>
+struct R2COp {
+    static constexpr int NBUF = 2;
+    const double* in;  // [ny][nx]
+    double2* H;        // [1][ny][kr_pad]
+    __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
+        constexpr int Gt = XCtx<N>::G;
+        double2 v[16];
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = make_double2(0.5 * in[(long long)y * N + cx.g + m * Gt], 0.0);   // store_pair returns 2 P
+        cx.fft_regs_in(v, 1);
+        cx.template store_pair<MUL_ONE, MUL_ZERO>(1, row_ref<SLAB>(L, H, 1, 0, y), RowPlain{});
+    }
+};
+struct IdentityCombiner {
+    __device__ __forceinline__ int var_of(int slot) const { return slot; }
+    __device__ __forceinline__ int nin(int) const { return 1; }
+    __device__ __forceinline__ int src(int, int) const { return 0; }
+    __device__ __forceinline__ double2 apply(int, int, double2 v, double, double) const { return v; }
+    __device__ __forceinline__ double2 init(int, double, double, long long) const { return make_double2(0.0, 0.0); }
+};
+
 // ---------------------------------------------------------------- velocity snapshot for packets
 // psi kinds
 enum { PSI_RSW_BALANCED = 0, PSI_SWQG = 1, PSI_TWOLAYER_BAROCLINIC = 2, PSI_TWOLAYER_MEAN = 3 };
@@ -650,6 +678,9 @@ struct Launch {
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    // physical field -> spectral field `out` ([l][kr_pad]) through H scratch
+    static cudaError_t forward_field(const double* in, double2* H, double2* out, const SpecLayout& L, const double2* tw_x, unsigned* sched, cudaStream_t st);
+    static cudaError_t forward_field_y(const double2* H, double2* out, const SpecLayout& L, const double2* tw_y, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
     static cudaError_t snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);

@@ -10,13 +10,14 @@ namespace swrt {
 // coef[l][kr] = { e^{D dt}, sin(w dt)/w, (1-cos(w dt))/w^2, filter }
 // exp(L dt) x = e^{D dt} [ x + s L0 x + c L0 L0 x ],  L0 = L - D I  
 struct RswLin {
-    double f, c2;  // c2 = Cg^2 for RSW/Lindborg, 0 for Modified (no -i k c2 coupling)
+    double f, c2;  // c2 = Cg^2 for RSW/Lindborg, 0 for Modified / QuadHeight (no -i k c2 coupling)
     double w2c;    // w^2 = f^2 + w2c K^2
+    double d3;     // 1: third row (-i k, -i l, 0); 0: QuadHeight (third row of L0 vanishes)
     __device__ __forceinline__ void L0(const double2 (&x)[3], double k, double l, double2 (&y)[3]) const {
         // [0, f, -i k c2; -f, 0, -i l c2; -i k, -i l, 0]
         y[0] = make_double2(f * x[1].x + k * c2 * x[2].y, f * x[1].y - k * c2 * x[2].x);
         y[1] = make_double2(-f * x[0].x + l * c2 * x[2].y, -f * x[0].y - l * c2 * x[2].x);
-        y[2] = make_double2(k * x[0].y + l * x[1].y, -(k * x[0].x + l * x[1].x));
+        y[2] = make_double2(d3 * (k * x[0].y + l * x[1].y), -d3 * (k * x[0].x + l * x[1].x));
     }
     __device__ __forceinline__ void expmul(const double2 (&x)[3], double k, double l, double eD, double s, double c,
                                            double2 (&y)[3]) const {

@@ -15,12 +15,12 @@ import numpy as np
 from . import _lib
 from ._lib import FlowDesc, check, lib
 
-MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowWater": 2, "SWQG": 4,
+MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowWater": 2, "QuadHeightModifiedShallowWater": 3, "SWQG": 4,
           "TwoLayerQG": 5, "ThomasYamada": 6}
 STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3}
 FIELD_U, FIELD_V, FIELD_ETA, FIELD_ZETA = 0, 1, 2, 16
 FIELD_QG_PSI, FIELD_QG_U, FIELD_QG_V, FIELD_QG_ZETA = 32, 40, 48, 56
-NVAR = {0: 3, 1: 3, 2: 3, 4: 1, 5: 2, 6: 4}
+NVAR = {0: 3, 1: 3, 2: 3, 3: 3, 4: 1, 5: 2, 6: 4}
 
 
 class Grid:
@@ -86,6 +86,8 @@ class Vars:
             if name not in ty:
                 raise AttributeError(name)
             return self._field(ty[name])
+        if self._p.desc.model == 3 and name in ("m",):
+            return self._field(FIELD_ETA)
         table = ({"q": 0, "ψ": FIELD_QG_PSI, "psi": FIELD_QG_PSI, "u": FIELD_QG_U, "v": FIELD_QG_V, "ζ": FIELD_QG_ZETA,
                   "zeta": FIELD_QG_ZETA} if qg else
                  {"u": FIELD_U, "v": FIELD_V, "η": FIELD_ETA, "eta": FIELD_ETA, "ζ": FIELD_ZETA, "zeta": FIELD_ZETA})
@@ -185,8 +187,19 @@ def set_solution(prob, *fields):
     thomasyamada/ThomasYamada.jl:292-317; (prob, q0h) swqg/TwoLayerQG.jl:211-219."""
     if len(fields) == 1:
         prob.sol = np.asarray(fields[0])
+    elif prob.desc.model == 3:
+        # rsw/QuadHeightModifiedShallowWater.jl:333-347: the third variable is m = 1/(1+eta), formed in physical space
+        prob.sol = np.stack([np.asarray(f) for f in fields], axis=-1)
+        set_field_physical(prob, 2, 1.0 / (1.0 + prob.vars._field(FIELD_ETA)))
     else:
         prob.sol = np.stack([np.asarray(f) for f in fields], axis=-1)
+
+
+def set_field_physical(prob, var, field):
+    """mul!(varh, grid.rfftplan, field): overwrite state variable `var` with the (dealiased) transform of a physical field."""
+    a = np.asfortranarray(field, dtype=np.float64)
+    assert a.shape == (prob.grid.nx, prob.grid.ny)
+    check(lib().swrt_flow_set_field_physical(prob._h, int(var), a.ctypes.data_as(C.c_void_p)))
 
 
 def enforce_reality_condition(prob):

@@ -39,7 +39,7 @@ def expL_closed_form(grid, params, dt, variant="rsw"):
     s = np.where(x > 1e-8, np.sin(x) / np.where(w > 0, w, 1), dt)
     c = np.where(x > 1e-4, (1 - np.cos(x)) / np.where(w2 > 0, w2, 1), dt * dt * (0.5 - x * x / 24))
     I = np.eye(3)
-    L02 = L0 @ L0
+    L02 = L0 @ L0   # (QuadHeight: third row of L0 is zero, L0^3 = -f^2 L0 still holds)
     return np.exp(D * dt)[..., None, None] * (I + s[..., None, None] * L0 + c[..., None, None] * L02)
 
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from .grid import TwoDGrid, parsevalsum2
 
-RSW, MODIFIED, LINDBORG = "rsw", "modified", "lindborg"
+RSW, MODIFIED, LINDBORG, QUADHEIGHT = "rsw", "modified", "lindborg", "quadheight"
 
 
 class Params:
@@ -32,8 +32,9 @@ def populate_L(grid: TwoDGrid, p: Params, variant=RSW):
     L[..., 0, 1] = p.f
     L[..., 1, 0] = -p.f
     L[..., 1, 1] = D
-    L[..., 2, 0] = -1j * k
-    L[..., 2, 1] = -1j * l
+    if variant != QUADHEIGHT:                 # QuadHeightModifiedShallowWater.jl:280-281: no longer linear in m
+        L[..., 2, 0] = -1j * k
+        L[..., 2, 1] = -1j * l
     L[..., 2, 2] = D
     if variant in (RSW, LINDBORG):
         L[..., 0, 2] = -1j * k * p.Cg2
@@ -73,8 +74,9 @@ def calcN(sol, grid: TwoDGrid, p: Params, variant=RSW):
         return N
 
     eta = g.irfft2(eh)
-    if variant == MODIFIED:
-        Fh = g.rfft2(1.5 - 0.5 / (1 + eta) ** 2)
+    if variant in (MODIFIED, QUADHEIGHT):
+        # QuadHeight carries m = 1/(1+eta) in the third slot: F = 1.5 - 0.5 m^2 (QuadHeightModifiedShallowWater.jl:219-225)
+        Fh = g.rfft2(1.5 - 0.5 / (1 + eta) ** 2 if variant == MODIFIED else 1.5 - 0.5 * eta ** 2)
         N[:, :, 0] += -1j * p.Cg2 * g.kr * Fh
         N[:, :, 1] += -1j * p.Cg2 * g.l * Fh
     N[:, :, 2] = -ik * g.rfft2(a * eta)
@@ -150,3 +152,9 @@ def load_from_snapshot(snapshot, grid: TwoDGrid):
     new[:snkr, :half_nl] = scale * snapshot[:, :half_nl]
     new[:snkr, grid.nl - half_nl:] = scale * snapshot[:, half_nl:]
     return new
+
+
+def quadheight_set_solution(u0h, v0h, eta0h, grid: TwoDGrid):
+    """QuadHeightModifiedShallowWater.set_solution! :333-347: the third variable is m = 1/(1+eta), through physical space."""
+    m0h = grid.rfft2(1.0 / (1.0 + grid.irfft2(eta0h)))
+    return np.stack([u0h, v0h, m0h], axis=-1)

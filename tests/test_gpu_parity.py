@@ -466,3 +466,20 @@ def test_4096_transform_properties():
     assert abs(0.5 * ((u ** 2).sum() + (v ** 2).sum()) * g.dx * g.dy / (g.Lx * g.Ly) / ke - 1) < 1e-12
     flow.stepforward(prob, (), 2)
     assert not flow.has_nan(prob)
+
+
+def test_quadheight_variant_and_physical_forward_transform():
+    nx = 64
+    g, p, sol0, c = config2_setup(nx)
+    sol0 = sol0 * 0.3                                            # keep 1 + eta well away from zero
+    prob = swrt.Problem(model="QuadHeightModifiedShallowWater", nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    flow.set_solution(prob, sol0[:, :, 0], sol0[:, :, 1], sol0[:, :, 2])
+    want0 = g.dealias(orsw.quadheight_set_solution(sol0[:, :, 0], sol0[:, :, 1], sol0[:, :, 2], g))
+    assert rel_l2(prob.sol, want0) < 1e-13                       # exercises the physical -> spectral path (R2C x-pass + forward y-pass)
+    assert abs(flow.potential_energy(prob) - 0.5 * p.Cg2 * want0[0, 0, 2].real / (g.Lx * g.Ly)) < 1e-12
+    flow.stepforward(prob, (), 30)
+    assert rel_l2(prob.sol, oracle_steps(g, p, want0, c["dt"], 30, orsw.QUADHEIGHT)) < 1e-10
+    # round trip of an arbitrary physical field through set_field_physical
+    f = np.random.default_rng(1).standard_normal((nx, nx))
+    flow.set_field_physical(prob, 0, f)
+    assert rel_l2(prob.sol[:, :, 0], g.dealias(g.rfft2(f))) < 1e-13
