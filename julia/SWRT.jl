@@ -24,41 +24,52 @@ Base.@kwdef struct FlowDesc
     aliased_fraction::Cdouble = 1/3
     filter_innerK::Cdouble = 2/3; filter_outerK::Cdouble = 1.0; filter_tol::Cdouble = 1e-15
     U::Cdouble = 0.0; mu::Cdouble = 0.0; F::Cdouble = 0.0; Ro::Cdouble = 0.0; Kd2::Cdouble = 0.0
+    slab_rank::Cint = 0; slab_size::Cint = 0
 end
 
 Base.@kwdef struct PacketsDesc
     n::Clonglong
-    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16
+    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic
     f::Cdouble = 1.0; Cg::Cdouble = 1.0
 end
 
-const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1)
+const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1, "LinborgShallowWater" => 2,
+                    "QuadHeightModifiedShallowWater" => 3, "SWQG" => 4, "TwoLayerQG" => 5, "ThomasYamada" => 6)
+const STEPPERS = Dict("IFMAB3" => 0, "FilteredAB3" => 1, "ETDRK4" => 2, "FilteredRK4" => 3)
+const NVAR = Dict(0 => 3, 1 => 3, 2 => 3, 3 => 3, 4 => 1, 5 => 2, 6 => 4)
 
 # --- flow: RotatingShallowWater.Problem and friends (rsw/RotatingShallowWater.jl:70-133, 309-336) ---------------
 mutable struct Problem
     h::Ptr{Cvoid}
-    nx::Int; ny::Int; nkr::Int; dt::Float64
-    function Problem(; model = "RotatingShallowWater", nx = 128, ny = nx, Lx = 2π, Ly = Lx, ν = 1e-16, nν = 4, f = 1.0, Cg = 1.0,
-                     dt = 5e-2, aliased_fraction = 1/3, use_filter = false, order = 4, dev = 0)
-        d = FlowDesc(model = MODELS[model], nx = nx, ny = ny, Lx = Lx, Ly = Ly, nu = ν, nnu = nν, f = f, Cg = Cg, dt = dt,
-                     aliased_fraction = aliased_fraction, use_filter = use_filter, filter_order = order, device = dev)
+    nx::Int; ny::Int; nkr::Int; dt::Float64; nvar::Int
+    function Problem(; model = "RotatingShallowWater", stepper = "IFMAB3", nx = 128, ny = nx, Lx = 2π, Ly = Lx, ν = 1e-16, nν = 4,
+                     f = 1.0, Cg = 1.0, dt = 5e-2, aliased_fraction = 1/3, use_filter = false, order = 4, dev = 0,
+                     U = 0.5, μ = 1e-2, f0 = f, δρρ0 = 0.2, Ro = 0.2)
+        d = FlowDesc(model = MODELS[model], stepper = STEPPERS[stepper], nx = nx, ny = ny, Lx = Lx, Ly = Ly, nu = ν, nnu = nν, f = f,
+                     Cg = Cg, dt = dt, aliased_fraction = aliased_fraction, use_filter = use_filter, filter_order = order, device = dev,
+                     U = U, mu = μ, F = 2 * f0^2 / Cg^2 / δρρ0, Ro = Ro)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_flow_create, libswrt), Cint, (Ref{FlowDesc}, Ref{Ptr{Cvoid}}), d, out))
-        p = new(out[], nx, ny, nx ÷ 2 + 1, dt)
+        p = new(out[], nx, ny, nx ÷ 2 + 1, dt, NVAR[MODELS[model]])
         finalizer(q -> ccall((:swrt_flow_destroy, libswrt), Cint, (Ptr{Cvoid},), q.h), p)
         return p
     end
 end
 
-"set_solution!(prob, u0h, v0h, η0h): arrays (nkr, nl) ComplexF64"
-function set_solution!(prob::Problem, u0h, v0h, η0h)
-    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, 3)
-    sol[:, :, 1] .= u0h; sol[:, :, 2] .= v0h; sol[:, :, 3] .= η0h
+"set_solution!(prob, fields...): one (nkr, nl) ComplexF64 array per state variable (u0h, v0h, η0h | q0h layers | ζ0h, u0h, v0h, p0h)"
+function set_solution!(prob::Problem, fields...)
+    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, prob.nvar)
+    for (i, f) in enumerate(fields)
+        sol[:, :, i] .= f
+    end
     check(ccall((:swrt_flow_set_solution, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, sol))
 end
+"mul!(varh, grid.rfftplan, field) into state variable `var` (1-based)"
+set_field_physical!(prob::Problem, var::Integer, field::Matrix{Float64}) =
+    check(ccall((:swrt_flow_set_field_physical, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), prob.h, var - 1, field))
 "Array(prob.sol)"
 function solution(prob::Problem)
-    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, 3)
+    sol = Array{ComplexF64}(undef, prob.nkr, prob.ny, prob.nvar)
     check(ccall((:swrt_flow_get_solution, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, sol))
     return sol
 end
@@ -100,6 +111,8 @@ potential_energy(prob::Problem) = energies(prob).potential_energy
 "get_streamfunction! + get_velocity_info into snapshot slot (0 = old, 1 = new)"
 get_velocity_info!(prob::Problem, slot::Integer; psi_kind = 0) =
     check(ccall((:swrt_flow_velocity_snapshot, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint), prob.h, psi_kind, slot))
+"node data of the snapshots: 0 bilinear (u,v,ux,uy,vx), 1 Hermite bicubic (+ uxy, vxy)"
+set_interpolation!(prob::Problem, interp::Integer) = check(ccall((:swrt_flow_set_interp, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, interp))
 "old_velocity = new_velocity; old_grad_v = new_grad_v"
 swap_snapshots!(prob::Problem; alias = false) =
     check(ccall((:swrt_flow_swap_snapshots, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, alias))
@@ -108,8 +121,8 @@ mutable struct Packets
     h::Ptr{Cvoid}
     n::Int
     prob::Problem
-    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16)
-        d = PacketsDesc(n = n, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
+    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16, interp = 0)
+        d = PacketsDesc(n = n, interp = interp, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_packets_create, libswrt), Cint, (Ref{PacketsDesc}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), d, prob.h, out))
         p = new(out[], n, prob)
