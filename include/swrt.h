@@ -145,7 +145,11 @@ int swrt_flow_launch_count(swrt_flow* h, long long* n);
 
 /* BILINEAR = the reference's texture sampling (raytracing/GPURaytracing.jl:118-127); HERMITE_BICUBIC = u, v from (f, f_x, f_y, f_xy)
  * node data (utils/CUDAInterpolations.jl:71-108) with the analytic gradient of the interpolant in dk/dt */
-enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1 };
+enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1,
+       /* quadratic B-spline of the CPU tracer (raytracing/Raytracing.jl:161-170); coefficients are prefiltered in the snapshot */
+       SWRT_INTERP_BSPLINE2 = 2 };
+/* classical RK4 (north star) or the CPU tracer's implicit midpoint (raytracing/Raytracing.jl:106-109), 12 fixed-point sweeps */
+enum { SWRT_INTEG_RK4 = 0, SWRT_INTEG_IMPLICIT_MIDPOINT = 1 };
 enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };
 typedef struct swrt_packets_desc {
     long long n;            /* Npackets */
@@ -154,6 +158,7 @@ typedef struct swrt_packets_desc {
     int time_lerp;          /* SWRT_LERP_*   */
     int sort_every;         /* re-sort the device copy by grid cell every this many raytrace calls (0 = never);
                                host-visible arrays always keep the caller's row order */
+    int integrator;         /* SWRT_INTEG_* */
     double f, Cg;           /* packet_params.f, packet_params.Cg */
 } swrt_packets_desc;
 

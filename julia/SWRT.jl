@@ -29,7 +29,8 @@ end
 
 Base.@kwdef struct PacketsDesc
     n::Clonglong
-    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic
+    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic, 2 quadratic B-spline
+    integrator::Cint = 0                                                           # 0 RK4, 1 implicit midpoint
     f::Cdouble = 1.0; Cg::Cdouble = 1.0
 end
 
@@ -121,8 +122,8 @@ mutable struct Packets
     h::Ptr{Cvoid}
     n::Int
     prob::Problem
-    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16, interp = 0)
-        d = PacketsDesc(n = n, interp = interp, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
+    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16, interp = 0, integrator = 0)
+        d = PacketsDesc(n = n, interp = interp, integrator = integrator, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_packets_create, libswrt), Cint, (Ref{PacketsDesc}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), d, prob.h, out))
         p = new(out[], n, prob)

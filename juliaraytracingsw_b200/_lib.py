@@ -28,7 +28,7 @@ class FlowDesc(C.Structure):
 
 class PacketsDesc(C.Structure):
     _fields_ = [("n", C.c_longlong), ("interp", C.c_int), ("nsub", C.c_int), ("time_lerp", C.c_int),
-                ("sort_every", C.c_int), ("f", C.c_double), ("Cg", C.c_double)]
+                ("sort_every", C.c_int), ("integrator", C.c_int), ("f", C.c_double), ("Cg", C.c_double)]
 
 
 class SeqOut(C.Structure):

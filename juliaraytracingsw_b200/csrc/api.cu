@@ -762,7 +762,7 @@ int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbyt
         case SWRT_SLAB_B_RECV: p = h->H; nb = fb * h->njobs_b; break;
         case SWRT_SLAB_SNAP0: case SWRT_SLAB_SNAP1:
             p = h->snap[h->slot_map[which - SWRT_SLAB_SNAP0]];
-            nb = (long long)sizeof(double) * h->d.nx * h->d.ny * (h->interp ? SNAP3_STRIDE : SNAP_STRIDE);
+            nb = (long long)sizeof(double) * h->d.nx * h->d.ny * (h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE);
             break;
         default: return fail(SWRT_ERR_ARG, "unknown slab buffer %d", which);
     }
@@ -841,7 +841,8 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     int rc = check_psi_kind(h, psi_kind);
     if (rc) return rc;
     CK(cudaSetDevice(h->d.device));
-    PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0};
+    const bool pf = h->interp == SWRT_INTERP_BSPLINE2;
+    PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
     CK(e);
@@ -849,7 +850,7 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
 }
 int swrt_slab_snap_b(swrt_flow* h, int slot) {
     if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
-    if (h->interp) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the bilinear node data");
+    if (h->interp == SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the 5-field node data");
     CK(cudaSetDevice(h->d.device));
     double* rows = h->snap[h->slot_map[slot]] + (long long)h->rank * h->L.yrows * h->d.nx * SNAP_STRIDE;   // this rank's rows of the full field
     cudaError_t e;
@@ -864,7 +865,8 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     { int rc = check_psi_kind(h, psi_kind); if (rc) return rc; }
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0};
+    const bool pf = h->interp == SWRT_INTERP_BSPLINE2;
+    PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
     cudaError_t e;
     bool materialise = false;
     SWRT_DISPATCH(L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
@@ -877,20 +879,21 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     }
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, out_local(h->G), h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp, L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp == SWRT_INTERP_HERMITE_BICUBIC, L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }
 
 int swrt_flow_set_interp(swrt_flow* h, int interp) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
-    if (interp != SWRT_INTERP_BILINEAR && interp != SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    if (interp != SWRT_INTERP_BILINEAR && interp != SWRT_INTERP_HERMITE_BICUBIC && interp != SWRT_INTERP_BSPLINE2)
+        return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
     h->interp = interp;
     return SWRT_OK;
 }
 int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields) {
     if (!h || !nfields) return fail(SWRT_ERR_ARG, "null pointer");
-    *nfields = h->interp ? SNAP3_NC : SNAP_NC;
+    *nfields = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC;
     return SWRT_OK;
 }
 
@@ -905,7 +908,7 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const long long n = (long long)h->d.nx * h->d.ny;
-    const int nc = h->interp ? SNAP3_NC : SNAP_NC, stride = h->interp ? SNAP3_STRIDE : SNAP_STRIDE;
+    const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
     { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, nc, stride, tmp); }
@@ -920,7 +923,7 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
     const long long n = (long long)h->d.nx * h->d.ny;
-    const int nc = h->interp ? SNAP3_NC : SNAP_NC, stride = h->interp ? SNAP3_STRIDE : SNAP_STRIDE;
+    const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
     cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * nc, cudaMemcpyHostToDevice, h->st);
@@ -993,8 +996,10 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
     if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
-    if (desc->interp != SWRT_INTERP_BILINEAR && desc->interp != SWRT_INTERP_HERMITE_BICUBIC)
+    if (desc->interp != SWRT_INTERP_BILINEAR && desc->interp != SWRT_INTERP_HERMITE_BICUBIC && desc->interp != SWRT_INTERP_BSPLINE2)
         return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
+    if (desc->integrator != SWRT_INTEG_RK4 && desc->integrator != SWRT_INTEG_IMPLICIT_MIDPOINT)
+        return fail(SWRT_ERR_UNSUPPORTED, "integrator %d not implemented", desc->integrator);
     if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
     if (desc->sort_every < 0) return fail(SWRT_ERR_ARG, "sort_every must be >= 0");
     CK(cudaSetDevice(flow->d.device));
@@ -1129,7 +1134,13 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE);
-      if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
+      if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
+          if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else SWRT_GEN(2, 1);
+      }
+      else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
+#undef SWRT_GEN
+      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
@@ -1146,7 +1157,10 @@ int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_hos
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
-    if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
+    if (p->d.interp == SWRT_INTERP_BSPLINE2) {
+        ProfScope ps(f, K_SAMPLE);
+        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    } else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
         ProfScope ps(f, K_SAMPLE);
         sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else

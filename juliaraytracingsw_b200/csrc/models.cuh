@@ -487,7 +487,18 @@ struct PsiLoader {
     long long vs;
     int kind;
     double f, P;   // P: Kd2 = f^2/Cg^2 (RSW balanced, SWQG) or F (two-layer)
+    double pdx, pdy;   // > 0: quadratic B-spline prefilter (Interpolations.jl, raytracing/Raytracing.jl:161-170) folded into psi:
+                       // every sampled field is linear in psih, and the prefilter is 1/((3/4 + cos(k dx)/4)(3/4 + cos(l dy)/4))
     __device__ __forceinline__ double2 psi_of(double kw, double lw, long long off) const {
+        double2 r = psi_raw(kw, lw, off);
+        if (pdx > 0.0) {
+            const double pf = 1.0 / ((0.75 + 0.25 * cos(kw * pdx)) * (0.75 + 0.25 * cos(lw * pdy)));
+            r.x *= pf;
+            r.y *= pf;
+        }
+        return r;
+    }
+    __device__ __forceinline__ double2 psi_raw(double kw, double lw, long long off) const {
         const double K2 = kw * kw + lw * lw;
         if (kind == PSI_RSW_BALANCED) {   // -(i k vh - i l uh - f etah)/(K^2 + f^2/Cg^2)   rsw/RSWRaytracingDriver.jl:63-67
             const double2 u = sol[off], v = sol[vs + off], e = sol[2 * vs + off];

@@ -355,6 +355,124 @@ __global__ void __launch_bounds__(128) sample_cubic_kernel(const double* __restr
     }
 }
 
+// ---------------------------------------------------------------- generic sampler / integrator combinations
+// INTERP: 0 bilinear, 1 Hermite bicubic, 2 quadratic B-spline (coefficients prefiltered in the snapshot, raytracing/Raytracing.jl:161-170)
+__device__ __forceinline__ void sample_bspline2_5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
+    const double sx = (x - g.x0) * g.inv_dx, sy = (y - g.y0) * g.inv_dy;
+    const double rx = floor(sx + 0.5), ry = floor(sy + 0.5);
+    const double dx = sx - rx, dy = sy - ry;
+    const int ic = (int)((long long)rx & (long long)(g.nx - 1)), jc = (int)((long long)ry & (long long)(g.ny - 1));
+    const double wx[3] = {0.5 * (dx - 0.5) * (dx - 0.5), 0.75 - dx * dx, 0.5 * (dx + 0.5) * (dx + 0.5)};
+    const double wy[3] = {0.5 * (dy - 0.5) * (dy - 0.5), 0.75 - dy * dy, 0.5 * (dy + 0.5) * (dy + 0.5)};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) out[c] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int i = (ic + a - 1) & (g.nx - 1);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const int j = (jc + b - 1) & (g.ny - 1);
+            const double2* q = reinterpret_cast<const double2*>(S + ((long long)j * g.nx + i) * SNAP_STRIDE);
+            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            const double w = wx[a] * wy[b];
+            out[0] += w * q0.x; out[1] += w * q0.y; out[2] += w * q1.x; out[3] += w * q1.y; out[4] += w * q2.x;
+        }
+    }
+}
+template <int INTERP>
+__device__ __forceinline__ void sample_level5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
+    if (INTERP == 2) {
+        sample_bspline2_5(S, g, x, y, out);
+    } else {
+        int i0, i1, j0, j1;
+        double a, b;
+        cell(x, g.x0, g.inv_dx, g.nx, i0, i1, a);
+        cell(y, g.y0, g.inv_dy, g.ny, j0, j1, b);
+        if (INTERP == 1) sample_hermite5(S, g, i0, i1, j0, j1, a, b, out);
+        else bilinear5(S, g, i0, i1, j0, j1, a, b, out);
+    }
+}
+template <int INTERP>
+__device__ __forceinline__ void ray_rhs_generic(const double (&s)[4], double sign, double alpha, const double* __restrict__ So,
+                                                const double* __restrict__ Sn, const PacketGrid& g, const RayParams& p, double (&d)[4]) {
+    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
+    double o[5], nw[5], W[5];
+    sample_level5<INTERP>(So, g, s[0], s[1], o);
+    sample_level5<INTERP>(Sn, g, s[0], s[1], nw);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) W[c] = wo * o[c] + wn * nw[c];
+    const double k = s[2], l = s[3];
+    const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));
+    d[0] = W[0] + cg * k;
+    d[1] = W[1] + cg * l;
+    d[2] = -(W[2] * k + W[4] * l);
+    d[3] = -(W[3] * k - W[2] * l);
+}
+// INTEG: 0 classical RK4, 1 implicit midpoint (raytracing/Raytracing.jl:106-109) by 12 fixed-point sweeps on the midpoint
+template <int INTERP, int INTEG>
+__global__ void __launch_bounds__(128, 3) raytrace_generic_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
+                                                                  const double* __restrict__ So, const double* __restrict__ Sn,
+                                                                  PacketGrid g, RayParams p) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    const double sg = sign[i];
+    const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
+    for (int it = 0; it < p.nsub; ++it) {
+        const double t = p.t0 + it * h;
+        double k[4], y[4];
+        if (INTEG == 0) {
+            double acc[4];
+            ray_rhs_generic<INTERP>(s, sg, (t - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+            ray_rhs_generic<INTERP>(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+            ray_rhs_generic<INTERP>(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+            ray_rhs_generic<INTERP>(y, sg, (t + h - p.t0) * inv_span, So, Sn, g, p, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+        } else {
+            const double alpha = (p.t0 + (it + 0.5) * h - p.t0) * inv_span;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) y[c] = s[c];
+            for (int sweep = 0; sweep < 12; ++sweep) {
+                ray_rhs_generic<INTERP>(y, sg, alpha, So, Sn, g, p, k);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) y[c] = s[c] + 0.5 * h * k[c];
+            }
+            ray_rhs_generic<INTERP>(y, sg, alpha, So, Sn, g, p, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[c] += h * k[c];
+        }
+    }
+    xk[i] = s[0];
+    xk[n + i] = s[1];
+    xk[2 * n + i] = s[2];
+    xk[3 * n + i] = s[3];
+}
+template <int INTERP>
+__global__ void __launch_bounds__(128) sample_generic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
+                                                             const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
+                                                             double* __restrict__ Gd) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double Sv[5];
+    sample_level5<INTERP>(S, g, xk[i], xk[n + i], Sv);
+    const long long o = idx[i];
+    U[o] = Sv[0];
+    U[n + o] = Sv[1];
+    if (Gd) {
+        Gd[o] = Sv[2];
+        Gd[n + o] = Sv[3];
+        Gd[2 * n + o] = Sv[4];
+        Gd[3 * n + o] = -Sv[2];
+    }
+}
+
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                      const double* __restrict__ S, PacketGrid g, double* __restrict__ U,

@@ -15,7 +15,8 @@ from ._lib import PacketsDesc, check, lib
 
 PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2, 3
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
-INTERP_BILINEAR, INTERP_HERMITE_BICUBIC = 0, 1
+INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2 = 0, 1, 2
+INTEG_RK4, INTEG_IMPLICIT_MIDPOINT = 0, 1
 
 
 class Velocity:
@@ -73,9 +74,10 @@ def swap_snapshots(prob, alias=False):
 class Packets:
     """Device-resident wave packets = `create_template_ode(packets)` + the packet arrays."""
 
-    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16, interp=INTERP_BILINEAR):
+    def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16, interp=INTERP_BILINEAR,
+                 integrator=INTEG_RK4):
         self.prob, self.n = prob, int(n)
-        d = PacketsDesc(n=self.n, interp=int(interp), nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
+        d = PacketsDesc(n=self.n, interp=int(interp), integrator=int(integrator), nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
         self._h = C.c_void_p()
         check(lib().swrt_packets_create(C.byref(d), prob._h, C.byref(self._h)))
 

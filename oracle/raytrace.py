@@ -183,3 +183,77 @@ def interpolate_velocity(F, pos, grid):
     ux,uy,vx,vy at packet positions.  Returns (N,2), (N,4)."""
     S = (sample_bilinear if F.shape[-1] == 5 else sample_hermite)(F, pos[:, 0], pos[:, 1], grid)
     return S[:, 0:2].copy(), np.stack([S[:, 2], S[:, 3], S[:, 4], -S[:, 2]], axis=1)
+
+
+# ------------------------------------------------------------------------------------ CPU-tracer semantics (raytracing/Raytracing.jl)
+# Quadratic B-spline interpolation (Interpolations.jl BSpline(Quadratic(Periodic(OnGrid()))), :161-170) and the implicit-midpoint
+# integrator (:106-109).  Interpolations.jl / OrdinaryDiffEq are third party and un-vendored: restated from their documented
+# formulas (SURVEY App. C) -- PARITY UNPINNED.
+def bspline2_prefilter(fields, grid):
+    """Spline coefficients c with c_{i-1}/8 + 3 c_i/4 + c_{i+1}/8 = f_i in x and y (periodic).  The prefilter is a
+    convolution, i.e. a division by (3/4 + cos(k dx)/4)(3/4 + cos(l dy)/4) in Fourier space."""
+    px = 0.75 + 0.25 * np.cos(grid.kr * grid.dx)
+    py = 0.75 + 0.25 * np.cos(grid.l * grid.dy)
+    out = np.empty_like(fields)
+    for c in range(fields.shape[-1]):
+        out[:, :, c] = grid.irfft2(grid.rfft2(fields[:, :, c]) / (px * py))
+    return out
+
+
+def bspline2_prefilter_direct(f):
+    """Same coefficients by solving the periodic tridiagonal systems (checks the Fourier shortcut)."""
+    def solve(a, axis):
+        n = a.shape[axis]
+        M = np.zeros((n, n))
+        idx = np.arange(n)
+        M[idx, idx] = 0.75
+        M[idx, (idx - 1) % n] = 0.125
+        M[idx, (idx + 1) % n] = 0.125
+        return np.moveaxis(np.linalg.solve(M, np.moveaxis(a, axis, 0).reshape(n, -1)).reshape(np.moveaxis(a, axis, 0).shape), 0, axis)
+    return solve(solve(f, 0), 1)
+
+
+def sample_bspline2(C, x, y, grid):
+    """Evaluate the quadratic B-spline with coefficients C (nx, ny, F): weights (1/2)(d-1/2)^2, 3/4 - d^2, (1/2)(d+1/2)^2,
+    d = s - round(s)."""
+    def axis(pos, p0, dp, n):
+        s = (pos - p0) / dp
+        r = np.floor(s + 0.5)
+        d = s - r
+        i = np.mod(r, n).astype(np.int64)
+        return i, np.stack([0.5 * (d - 0.5) ** 2, 0.75 - d * d, 0.5 * (d + 0.5) ** 2], axis=0)
+    i, wx = axis(x, grid.x[0], grid.dx, grid.nx)
+    j, wy = axis(y, grid.y[0], grid.dy, grid.ny)
+    out = np.zeros((x.shape[0], C.shape[-1]))
+    for a in range(3):
+        for b in range(3):
+            out += (wx[a] * wy[b])[:, None] * C[(i + a - 1) % grid.nx, (j + b - 1) % grid.ny]
+    return out
+
+
+def rhs_sampler(xk, sign, alpha, S_old, S_new, f, Cg, lerp=LERP_PHYSICAL):
+    """Ray RHS from already sampled (N, 5) fields of the two time levels."""
+    k, l = xk[:, 2], xk[:, 3]
+    w = sign * np.sqrt(f * f + Cg * Cg * (k * k + l * l))
+    W = (1 - alpha) * S_old + alpha * S_new if lerp == LERP_PHYSICAL else alpha * S_old + (1 - alpha) * S_new
+    out = np.empty_like(xk)
+    out[:, 0] = W[:, 0] + Cg * Cg * k / w
+    out[:, 1] = W[:, 1] + Cg * Cg * l / w
+    out[:, 2] = -(W[:, 2] * k + W[:, 4] * l)
+    out[:, 3] = -(W[:, 3] * k - W[:, 2] * l)
+    return out
+
+
+def raytrace_midpoint(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, sampler=sample_bilinear, iters=12):
+    """Implicit midpoint y+ = y + h f(t + h/2, (y + y+)/2) by fixed-point iteration on the midpoint z (a fixed number of
+    sweeps: the map contracts by ~h |grad U| per sweep, so 12 sweeps reach round-off for CFL-limited steps)."""
+    h = (t1 - t0) / nsub
+    for s in range(nsub):
+        alpha = (t0 + (s + 0.5) * h - t0) / (t1 - t0)
+        z = xk.copy()
+        for _ in range(iters):
+            fz = rhs_sampler(z, sign, alpha, sampler(F_old, z[:, 0], z[:, 1], grid), sampler(F_new, z[:, 0], z[:, 1], grid), f, Cg)
+            z = xk + 0.5 * h * fz
+        fz = rhs_sampler(z, sign, alpha, sampler(F_old, z[:, 0], z[:, 1], grid), sampler(F_new, z[:, 0], z[:, 1], grid), f, Cg)
+        xk += h * fz
+    return xk

@@ -483,3 +483,47 @@ def test_quadheight_variant_and_physical_forward_transform():
     f = np.random.default_rng(1).standard_normal((nx, nx))
     flow.set_field_physical(prob, 0, f)
     assert rel_l2(prob.sol[:, :, 0], g.dealias(g.rfft2(f))) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------------ CPU-tracer semantics
+@pytest.mark.parametrize("interp,integ", [(2, 0), (2, 1), (0, 1), (1, 1)])
+def test_bspline_and_implicit_midpoint_modes(interp, integ):
+    """Quadratic B-spline sampling and the implicit-midpoint integrator of raytracing/Raytracing.jl (a18), against the oracle."""
+    g, p, sol0, c = config2_setup(128)
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 3)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_interpolation(prob, interp)
+    prob.sol = sol0
+    vel, _ = raytracing.get_velocity_info(prob, 0)
+    flow.stepforward(prob, (), 3)
+    raytracing.get_velocity_info(prob, 1)
+    psi0, psi1 = orsw.get_streamfunction(sol0, g, p), orsw.get_streamfunction(sol1, g, p)
+    if interp == 1:
+        Fo, Fn, sampler = oray.get_velocity_info_cubic(psi0, g), oray.get_velocity_info_cubic(psi1, g), oray.sample_hermite
+    elif interp == 2:
+        Fo, Fn = (oray.bspline2_prefilter(oray.get_velocity_info(q, g), g) for q in (psi0, psi1))
+        sampler = oray.sample_bspline2
+    else:
+        Fo, Fn, sampler = oray.get_velocity_info(psi0, g), oray.get_velocity_info(psi1, g), oray.sample_bilinear
+    assert rel_l2(vel._arr(), Fo) < 1e-12                         # the snapshot holds spline coefficients in mode 2
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 24)
+    xk[:, 0:2] += np.random.default_rng(5).uniform(-20, 20, size=(xk.shape[0], 2))
+    pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=2, interp=interp, integrator=integ)
+    pk.set(xk, sign)
+    t0, t1 = 0.0, 3 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t0, t1))
+    if integ == 1:
+        want = oray.raytrace_midpoint(xk.copy(), sign, t0, t1, Fo, Fn, g, c["f"], c["Cg"], nsub=2, sampler=sampler)
+    else:
+        want = xk.copy()
+        h = (t1 - t0) / 2
+        for s_ in range(2):                                       # RK4 with the B-spline sampler
+            def f_(z, al):
+                return oray.rhs_sampler(z, sign, al, sampler(Fo, z[:, 0], z[:, 1], g), sampler(Fn, z[:, 0], z[:, 1], g), c["f"], c["Cg"])
+            a0 = (s_ * h) / (t1 - t0)
+            k1 = f_(want, a0); k2 = f_(want + 0.5 * h * k1, a0 + 0.5 * h / (t1 - t0)); k3 = f_(want + 0.5 * h * k2, a0 + 0.5 * h / (t1 - t0))
+            k4 = f_(want + h * k3, a0 + h / (t1 - t0))
+            want = want + (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    got = pk.get()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-8
+    assert rel_l2(got, want) < 1e-10
