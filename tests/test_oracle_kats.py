@@ -245,3 +245,40 @@ def test_qg_operators_closed_forms():
     # the Jacobian conserves the mean of q: N[0, 0] == 0
     sol = g.dealias(g.rfft2(rng.standard_normal((32, 32))))
     assert abs(qg.swqg_calcN(sol.copy(), g, 9.0)[0, 0]) < 1e-9
+
+
+def test_bspline2_prefilter_and_node_reproduction():
+    """Quadratic B-spline mode of the CPU tracer (raytracing/Raytracing.jl:161-170): the Fourier prefilter equals the
+    periodic tridiagonal solve, the spline reproduces node values, and it converges faster than bilinear."""
+    from oracle import raytrace as oray
+    from oracle.grid import TwoDGrid
+    g = TwoDGrid(32, 2 * np.pi)
+    X, Y = np.meshgrid(g.x, g.y, indexing="ij")
+    f = np.stack([np.sin(X) * np.cos(2 * Y), np.cos(3 * X + Y)], axis=-1)
+    C = oray.bspline2_prefilter(f, g)
+    assert np.abs(C - oray.bspline2_prefilter_direct(f)).max() < 1e-13
+    xs, ys = X.ravel(), Y.ravel()
+    assert np.abs(oray.sample_bspline2(C, xs, ys, g) - f.reshape(-1, 2)).max() < 1e-13
+    rng = np.random.default_rng(0)
+    px, py = rng.uniform(-10, 10, 500), rng.uniform(-10, 10, 500)        # periodic wrap outside the box
+    exact = np.stack([np.sin(px) * np.cos(2 * py), np.cos(3 * px + py)], axis=-1)
+    e_spline = np.abs(oray.sample_bspline2(C, px, py, g) - exact).max()
+    e_lin = np.abs(oray.sample_bilinear(f, px, py, g) - exact).max()
+    assert e_spline < 0.1 * e_lin
+
+
+def test_implicit_midpoint_is_second_order_and_symmetric():
+    """Implicit midpoint (raytracing/Raytracing.jl:106-109): integrating forward then backward returns to the start
+    (the scheme is symmetric), and halving h cuts the error about four-fold."""
+    from oracle import raytrace as oray, rsw as orsw
+    from helpers import config2_setup
+    g, p, sol0, c = config2_setup(64)
+    F = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 6)
+    T = 40 * c["dt"]
+    ref = oray.raytrace_midpoint(xk.copy(), sign, 0.0, T, F, F, g, c["f"], c["Cg"], nsub=64)
+    e = [np.abs(oray.raytrace_midpoint(xk.copy(), sign, 0.0, T, F, F, g, c["f"], c["Cg"], nsub=n) - ref).max() for n in (4, 8)]
+    assert 2.5 < e[0] / e[1] < 6.0
+    fwd = oray.raytrace_midpoint(xk.copy(), sign, 0.0, T, F, F, g, c["f"], c["Cg"], nsub=8, iters=40)
+    back = oray.raytrace_midpoint(fwd.copy(), sign, T, 0.0, F, F, g, c["f"], c["Cg"], nsub=8, iters=40)
+    assert np.abs(back - xk).max() < 1e-9 * max(1.0, np.abs(xk).max())
