@@ -25,7 +25,10 @@ enum { SWRT_OK = 0, SWRT_ERR_ARG = -1, SWRT_ERR_CUDA = -2, SWRT_ERR_UNSUPPORTED 
 
 /* models: rsw/RotatingShallowWater.jl, rsw/ModifiedShallowWater.jl, rsw/LinborgShallowWater.jl,
  * swqg/SWQG.jl, swqg/TwoLayerQG.jl, thomasyamada/ThomasYamada.jl */
-enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_RSW_QUADHEIGHT = 3 /* rsw/QuadHeightModifiedShallowWater.jl */, SWRT_SWQG = 4, SWRT_TWOLAYERQG = 5, SWRT_THOMASYAMADA = 6 };
+enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_RSW_QUADHEIGHT = 3 /* rsw/QuadHeightModifiedShallowWater.jl */, SWRT_SWQG = 4, SWRT_TWOLAYERQG = 5, SWRT_THOMASYAMADA = 6,
+       /* GeophysicalFlows MultiLayerQG with two equal layers (raytracing/TwoLayerRaytracing.jl:174; simulation/TwoLayerSimulation.jl:37-47):
+          diagonal L, mean flow / PV gradient / bottom drag inside calcN!; state q_1, q_2 */
+       SWRT_MULTILAYERQG2 = 7 };
 /* steppers: utils/IFMAB3.jl; FourierFlows FilteredAB3 / ETDRK4 / FilteredRK4 (raytracing/CPUParameters.jl:7) */
 enum { SWRT_IFMAB3 = 0, SWRT_FILTEREDAB3 = 1, SWRT_ETDRK4 = 2, SWRT_FILTEREDRK4 = 3 };
 
@@ -45,6 +48,7 @@ typedef struct swrt_flow_desc {
     double aliased_fraction;
     double filter_innerK, filter_outerK, filter_tol;   /* <=0: FourierFlows defaults 2/3, 1, 1e-15 */
     double U, mu, F, Ro, Kd2;                            /* model specific (two-layer, TY, SWQG) */
+    double U2, beta;                                     /* MultiLayerQG-2: layer flows (U, U2), planetary PV gradient; F = f0^2/(g' H_j) */
     int slab_rank, slab_size;                            /* slab-decomposed flow over slab_size GPUs (0 or 1: off), see swrt_slab_* */
 } swrt_flow_desc;
 

@@ -24,6 +24,7 @@ Base.@kwdef struct FlowDesc
     aliased_fraction::Cdouble = 1/3
     filter_innerK::Cdouble = 2/3; filter_outerK::Cdouble = 1.0; filter_tol::Cdouble = 1e-15
     U::Cdouble = 0.0; mu::Cdouble = 0.0; F::Cdouble = 0.0; Ro::Cdouble = 0.0; Kd2::Cdouble = 0.0
+    U2::Cdouble = 0.0; beta::Cdouble = 0.0
     slab_rank::Cint = 0; slab_size::Cint = 0
 end
 
@@ -35,9 +36,9 @@ Base.@kwdef struct PacketsDesc
 end
 
 const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1, "LinborgShallowWater" => 2,
-                    "QuadHeightModifiedShallowWater" => 3, "SWQG" => 4, "TwoLayerQG" => 5, "ThomasYamada" => 6)
+                    "QuadHeightModifiedShallowWater" => 3, "SWQG" => 4, "TwoLayerQG" => 5, "ThomasYamada" => 6, "MultiLayerQG" => 7)
 const STEPPERS = Dict("IFMAB3" => 0, "FilteredAB3" => 1, "ETDRK4" => 2, "FilteredRK4" => 3)
-const NVAR = Dict(0 => 3, 1 => 3, 2 => 3, 3 => 3, 4 => 1, 5 => 2, 6 => 4)
+const NVAR = Dict(0 => 3, 1 => 3, 2 => 3, 3 => 3, 4 => 1, 5 => 2, 6 => 4, 7 => 2)
 
 # --- flow: RotatingShallowWater.Problem and friends (rsw/RotatingShallowWater.jl:70-133, 309-336) ---------------
 mutable struct Problem

@@ -22,7 +22,7 @@ class FlowDesc(C.Structure):
         ("Lx", C.c_double), ("Ly", C.c_double), ("dt", C.c_double), ("nu", C.c_double), ("f", C.c_double),
         ("Cg", C.c_double), ("aliased_fraction", C.c_double), ("filter_innerK", C.c_double),
         ("filter_outerK", C.c_double), ("filter_tol", C.c_double), ("U", C.c_double), ("mu", C.c_double),
-        ("F", C.c_double), ("Ro", C.c_double), ("Kd2", C.c_double), ("slab_rank", C.c_int), ("slab_size", C.c_int),
+        ("F", C.c_double), ("Ro", C.c_double), ("Kd2", C.c_double), ("U2", C.c_double), ("beta", C.c_double), ("slab_rank", C.c_int), ("slab_size", C.c_int),
     ]
 
 

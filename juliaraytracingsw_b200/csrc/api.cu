@@ -305,7 +305,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     const swrt_flow_desc& d = *desc;
     if (!supported_n(d.nx) || !supported_n(d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "nx, ny must be powers of two in [32, 4096] (got %d x %d)", d.nx, d.ny);
     const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG || d.model == SWRT_RSW_QUADHEIGHT;
-    const bool diag_L = d.model == SWRT_SWQG || d.model == SWRT_THOMASYAMADA;
+    const bool diag_L = d.model == SWRT_SWQG || d.model == SWRT_THOMASYAMADA || d.model == SWRT_MULTILAYERQG2;
     if (!rsw_family && !diag_L && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
     if (d.stepper < SWRT_IFMAB3 || d.stepper > SWRT_FILTEREDRK4) return fail(SWRT_ERR_ARG, "unknown stepper %d", d.stepper);
     if (d.stepper != SWRT_IFMAB3 && !diag_L)
@@ -350,8 +350,9 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     L.dk = 2.0 * M_PI / d.Lx; L.dl = 2.0 * M_PI / d.Ly;
     L.f = d.f; L.Cg2 = d.Cg * d.Cg;
     // model constant used by the loaders: Kd2 = f^2/Cg^2 (SWQG, swqg/SWQG.jl:85; RSW balanced psi) or F (two-layer, swqg/TwoLayerQG.jl:79)
-    L.aux0 = d.model == SWRT_TWOLAYERQG ? d.F : (d.Kd2 > 0 ? d.Kd2 : d.f * d.f / L.Cg2);
+    L.aux0 = (d.model == SWRT_TWOLAYERQG || d.model == SWRT_MULTILAYERQG2) ? d.F : (d.Kd2 > 0 ? d.Kd2 : d.f * d.f / L.Cg2);
     L.aux1 = d.Ro;   // Thomas-Yamada Rossby number
+    L.aux2 = d.U; L.aux3 = d.U2; L.aux4 = d.beta; L.aux5 = d.mu;   // MultiLayerQG-2 mean flow, beta, bottom drag
 
     auto bail = [&](int code) { swrt_flow_destroy(h); return code; };
 #define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
@@ -514,6 +515,9 @@ static int ifmab3_update_launch(swrt_flow* h, double2* Ncur) {
         if (model == SWRT_SWQG) {
             if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<1, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
             else update_diag_kernel<1, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+        } else if (model == SWRT_MULTILAYERQG2) {
+            if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<2, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
+            else update_diag_kernel<2, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
         } else if (model == SWRT_THOMASYAMADA) {
             if (stepper == SWRT_FILTEREDAB3) update_diag_kernel<4, true><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
             else update_diag_kernel<4, false><<<ublocks, 256, 0, h->st>>>(ua, Ncur, L);
@@ -606,7 +610,7 @@ int swrt_flow_set_clock(swrt_flow* h, double t, long long step) {
 
 int swrt_flow_get_field(swrt_flow* h, int which, double* real_host) {
     if (!h || !real_host) return fail(SWRT_ERR_ARG, "null pointer");
-    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG;
+    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG || h->d.model == SWRT_MULTILAYERQG2;
     const bool ok = (which >= 0 && which < h->nvar) || (!qg && which == SWRT_FIELD_ZETA) ||
                     (qg && which >= SWRT_FIELD_QG_PSI && which < SWRT_FIELD_QG_PSI + 32 && ((which - 32) & 7) < h->nvar);
     if (!ok) return fail(SWRT_ERR_ARG, "unknown field %d for model %d", which, h->d.model);
@@ -657,7 +661,7 @@ int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
     if (h->d.model == SWRT_SWQG) {            // swqg/SWQG.jl:205-222
         k = spectral_diag(h, DIAG_QG_K2PSI2, 0, &e) / (2 * A); CK(e);
         p = L.aux0 * spectral_diag(h, DIAG_QG_PSI2, 0, &e) / (2 * A); CK(e);
-    } else if (h->d.model == SWRT_TWOLAYERQG) {   // swqg/TwoLayerQG.jl:221-250 (KE_1 + KE_2)
+    } else if (h->d.model == SWRT_TWOLAYERQG || h->d.model == SWRT_MULTILAYERQG2) {   // swqg/TwoLayerQG.jl:221-250 (KE_1 + KE_2)
         k = spectral_diag(h, DIAG_QG_K2PSI2, 0, &e) / A; CK(e);
         k += spectral_diag(h, DIAG_QG_K2PSI2, 1, &e) / A; CK(e);
         p = L.aux0 * spectral_diag(h, DIAG_QG_DPSI2, 0, &e) / (2 * A); CK(e);
@@ -686,7 +690,7 @@ int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
 
 int swrt_flow_layer_kinetic_energy(swrt_flow* h, int layer, double* ke) {
     if (!h || !ke) return fail(SWRT_ERR_ARG, "null pointer");
-    if (h->d.model != SWRT_TWOLAYERQG || layer < 0 || layer > 1) return fail(SWRT_ERR_ARG, "layer kinetic energy is defined for the two-layer model");
+    if ((h->d.model != SWRT_TWOLAYERQG && h->d.model != SWRT_MULTILAYERQG2) || layer < 0 || layer > 1) return fail(SWRT_ERR_ARG, "layer kinetic energy is defined for the two-layer model");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e = cudaSuccess;
     *ke = spectral_diag(h, DIAG_QG_K2PSI2, layer, &e) / (h->d.Lx * h->d.Ly);
@@ -699,7 +703,7 @@ int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax) {
     CK(cudaSetDevice(h->d.device));
     cudaError_t e = cudaSuccess;
     double* outs[2] = {umax, vmax};
-    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG;
+    const bool qg = h->d.model == SWRT_SWQG || h->d.model == SWRT_TWOLAYERQG || h->d.model == SWRT_MULTILAYERQG2;
     const int uv0 = h->d.model == SWRT_THOMASYAMADA ? 1 : 0;   // TY: baroclinic (u_c, v_c) are state variables 1, 2
     for (int v = 0; v < 2; ++v) {
         if (!outs[v]) continue;
@@ -727,7 +731,8 @@ int swrt_flow_has_nan(swrt_flow* h, int* flag) {
 static int check_psi_kind(swrt_flow* h, int psi_kind) {
     const bool rsw_family = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;   // (QuadHeight carries m, not eta)
     const bool ok = (psi_kind == SWRT_PSI_RSW_BALANCED && rsw_family) || (psi_kind == SWRT_PSI_SWQG && h->d.model == SWRT_SWQG) ||
-                    ((psi_kind == SWRT_PSI_TWOLAYER_BAROCLINIC || psi_kind == SWRT_PSI_TWOLAYER_MEAN) && h->d.model == SWRT_TWOLAYERQG);
+                    ((psi_kind == SWRT_PSI_TWOLAYER_BAROCLINIC || psi_kind == SWRT_PSI_TWOLAYER_MEAN) &&
+                     (h->d.model == SWRT_TWOLAYERQG || h->d.model == SWRT_MULTILAYERQG2));
     return ok ? SWRT_OK : fail(SWRT_ERR_ARG, "psi kind %d does not apply to model %d", psi_kind, h->d.model);
 }
 

@@ -21,6 +21,7 @@ cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, const OutPeer
         }
         case MODEL_RSW_LINDBORG: return ypass_inv(LindborgLoaderA{sol, L.vs}, L, 8, G_, tw, st);
         case MODEL_SWQG: return ypass_inv(QgLoaderA{sol, L.vs, 1, L.aux0}, L, 3, G_, tw, st);
+        case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return ypass_inv(QgLoaderA{sol, L.vs, 2, L.aux0}, L, 6, G_, tw, st);
         case MODEL_THOMASYAMADA: return ypass_inv(TyLoaderA{sol, L.vs}, L, 9, G_, tw, st);
     }
@@ -36,6 +37,7 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
         case MODEL_RSW_QUADHEIGHT: return xpass(RswXOp<SWRT_N, 2>{G_, H, sc, s1, OutPeers{}}, L, tw, sched, st);
         case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
+        case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2>{G_, H, sc, OutPeers{}}, L, tw, sched, st);
         case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N>{G_, H, sc}, L, tw, sched, st);
     }
@@ -66,6 +68,7 @@ cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2
         case MODEL_RSW_LINDBORG: return ypass_fwd(NegateCombiner{}, L, 3, 3, H, Nout, tw, st);
         case MODEL_SWQG: return ypass_fwd(QgCombiner{}, L, 1, 2, H, Nout, tw, st);
         case MODEL_TWOLAYERQG: return ypass_fwd(QgCombiner{}, L, 2, 4, H, Nout, tw, st);
+        case MODEL_MULTILAYERQG2: return ypass_fwd(MlqgCombiner{sol, L.vs, L.aux0, L.aux2, L.aux3, L.aux4, L.aux5}, L, 2, 4, H, Nout, tw, st);
         case MODEL_THOMASYAMADA: return ypass_fwd(TyCombiner{sol, L.vs, L.aux1}, L, 4, 9, H, Nout, tw, st);
     }
     return cudaErrorInvalidValue;

@@ -13,12 +13,13 @@
 
 namespace swrt {
 
-enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_RSW_QUADHEIGHT = 3, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5, MODEL_THOMASYAMADA = 6 };
+enum { MODEL_RSW = 0, MODEL_RSW_MODIFIED = 1, MODEL_RSW_LINDBORG = 2, MODEL_RSW_QUADHEIGHT = 3, MODEL_SWQG = 4, MODEL_TWOLAYERQG = 5, MODEL_THOMASYAMADA = 6, MODEL_MULTILAYERQG2 = 7 };
 
 // per-model sizes: state variables, y-transformed intermediates (stage A jobs), x-transformed products (stage B outputs)
-__host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (m == MODEL_TWOLAYERQG ? 2 : (m == MODEL_THOMASYAMADA ? 4 : 3)); }
-__host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 3 : (m == MODEL_TWOLAYERQG ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
-__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 2 : (m == MODEL_TWOLAYERQG ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : ((m == MODEL_RSW_MODIFIED || m == MODEL_RSW_QUADHEIGHT) ? 5 : 4))); }
+__host__ __device__ constexpr bool model_two_layer(int m) { return m == MODEL_TWOLAYERQG || m == MODEL_MULTILAYERQG2; }
+__host__ __device__ constexpr int model_nvar(int m) { return m == MODEL_SWQG ? 1 : (model_two_layer(m) ? 2 : (m == MODEL_THOMASYAMADA ? 4 : 3)); }
+__host__ __device__ constexpr int model_njobs_a(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 3 : (model_two_layer(m) ? 6 : (m == MODEL_RSW_LINDBORG ? 8 : 5)); }
+__host__ __device__ constexpr int model_njobs_b(int m) { return m == MODEL_THOMASYAMADA ? 9 : m == MODEL_SWQG ? 2 : (model_two_layer(m) ? 4 : (m == MODEL_RSW_LINDBORG ? 3 : ((m == MODEL_RSW_MODIFIED || m == MODEL_RSW_QUADHEIGHT) ? 5 : 4))); }
 
 // ---------------------------------------------------------------- RSW family, stage A
 // jobs: 0 uh, 1 vh, 2 etah, 3 i l uh, 4 i l vh     (ux, vx are derived in the x-pass as i k G)
@@ -280,6 +281,30 @@ struct QgCombiner {  // N_layer = -i l F[psi_x q] + i k F[psi_y q]
     __device__ __forceinline__ int src(int var, int i) const { return 2 * var + i; }
     __device__ __forceinline__ double2 apply(int, int i, double2 v, double kw, double lw) const {
         return i == 0 ? make_double2(lw * v.y, -lw * v.x) : make_double2(-kw * v.y, kw * v.x);
+    }
+};
+
+// GeophysicalFlows MultiLayerQG with two equal layers (raytracing/TwoLayerRaytracing.jl:174): L is the diagonal
+// hyperviscosity and calcN! carries, besides the Jacobian, the mean-flow and background-PV-gradient terms and the bottom drag:
+//   N_j = -i k F[(u_j + U_j) q_j] - i l F[v_j q_j] - F[v_j Qy_j]  (+ mu K^2 psih_2 for j = 2),  Qy = beta +- F (U_1 - U_2).
+// A constant times a field transforms exactly, so the U_j and Qy_j terms are added in spectral space.
+struct MlqgCombiner {
+    const double2* sol;
+    long long vs;
+    double F, U1, U2, beta, mu;
+    __device__ __forceinline__ int var_of(int slot) const { return slot; }
+    __device__ __forceinline__ int nin(int) const { return 2; }
+    __device__ __forceinline__ int src(int var, int i) const { return 2 * var + i; }
+    __device__ __forceinline__ double2 apply(int, int i, double2 v, double kw, double lw) const {
+        return i == 0 ? make_double2(lw * v.y, -lw * v.x) : make_double2(-kw * v.y, kw * v.x);
+    }
+    __device__ __forceinline__ double2 init(int var, double kw, double lw, long long off) const {
+        const double K2 = kw * kw + lw * lw;
+        const double2 q = sol[var * vs + off], psi = qg_streamfunction(sol, vs, 2, var, K2, F, off);
+        const double Uj = var == 0 ? U1 : U2, Qy = var == 0 ? beta + F * (U1 - U2) : beta - F * (U1 - U2);
+        const double drag = var == 1 ? mu * K2 : 0.0;
+        // -i k (U_j q + Qy psi) + drag psi
+        return make_double2(kw * (Uj * q.y + Qy * psi.y) + drag * psi.x, -kw * (Uj * q.x + Qy * psi.x) + drag * psi.y);
     }
 };
 

@@ -25,6 +25,7 @@ struct SpecLayout {
     double dk, dl;     // 2 pi / Lx, 2 pi / Ly
     double f, Cg2;     // model constants used by loaders
     double aux0, aux1; // model specific (Kd2, ...)
+    double aux2, aux3, aux4, aux5;   // MultiLayerQG-2: U1, U2, beta, mu
     // Slab decomposition over P ranks (all equal to the single-GPU values when P = 1): a rank owns `kr_keep` columns starting at
     // global column kr_off (kr_pad = columns per rank, the same on every rank) and `yrows` = ny / P physical rows.  The
     // y-transformed / x-transformed intermediates are stored [y block][job][row in block][kr_pad]: exactly the send / receive

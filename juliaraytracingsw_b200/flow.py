@@ -16,11 +16,11 @@ from . import _lib
 from ._lib import FlowDesc, check, lib
 
 MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowWater": 2, "QuadHeightModifiedShallowWater": 3, "SWQG": 4,
-          "TwoLayerQG": 5, "ThomasYamada": 6}
+          "TwoLayerQG": 5, "ThomasYamada": 6, "MultiLayerQG": 7}
 STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3}
 FIELD_U, FIELD_V, FIELD_ETA, FIELD_ZETA = 0, 1, 2, 16
 FIELD_QG_PSI, FIELD_QG_U, FIELD_QG_V, FIELD_QG_ZETA = 32, 40, 48, 56
-NVAR = {0: 3, 1: 3, 2: 3, 3: 3, 4: 1, 5: 2, 6: 4}
+NVAR = {0: 3, 1: 3, 2: 3, 3: 3, 4: 1, 5: 2, 6: 4, 7: 2}
 
 
 class Grid:
@@ -80,7 +80,7 @@ class Vars:
         return np.stack([self._field(base + j) for j in range(n)], axis=-1)
 
     def __getattr__(self, name):
-        qg = self._p.desc.model in (4, 5)
+        qg = self._p.desc.model in (4, 5, 7)
         if self._p.desc.model == 6:     # Thomas-Yamada state fields (thomasyamada/ThomasYamada.jl:76-88)
             ty = {"ζt": 0, "zetat": 0, "uc": 1, "vc": 2, "pc": 3}
             if name not in ty:
@@ -103,8 +103,10 @@ class Problem:
     def __init__(self, dev=0, *, model="RotatingShallowWater", nx=128, ny=None, Lx=2 * np.pi, Ly=None, ν=1.0e-16,
                  nν=4, f=1.0, Cg=1.0, stepper="IFMAB3", dt=5e-2, aliased_fraction=1 / 3, T=np.float64,
                  use_filter=False, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15, nu=None, nnu=None,
-                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None, Ro=0.2, slab=None):
-        """Two-layer QG (swqg/TwoLayerQG.jl:55-72) takes U, μ, f0, Cg, δρρ0 (F = 2 f0²/Cg²/δρρ0); SWQG takes f, Cg (Kd2 = f²/Cg²)."""
+                 U=0.5, μ=1e-2, f0=None, δρρ0=0.2, mu=None, Ro=0.2, slab=None, H=None, b=None, β=0.0, beta=None):
+        """Two-layer QG (swqg/TwoLayerQG.jl:55-72) takes U, μ, f0, Cg, δρρ0 (F = 2 f0²/Cg²/δρρ0); SWQG takes f, Cg (Kd2 = f²/Cg²).
+        `model="MultiLayerQG"` mirrors `MultiLayerQG.Problem(2, dev; nx, Lx, f₀, H, b, U, μ, β, dt, stepper, aliased_fraction)`
+        (raytracing/TwoLayerRaytracing.jl:174) for two equal layers: U = (U₁, U₂), F = f₀²/((b₁ - b₂) H_j)."""
         if T not in (np.float64, float, "Float64"):
             raise _lib.SwrtError("only T=Float64 is implemented (the north star's arithmetic)")
         ny = nx if ny is None else ny
@@ -114,10 +116,19 @@ class Problem:
         μ = μ if mu is None else mu
         f0 = f if f0 is None else f0
         F = 2 * f0 ** 2 / Cg ** 2 / δρρ0
+        U2 = 0.0
+        β = β if beta is None else beta
+        if model == "MultiLayerQG":
+            H = (0.5, 0.5) if H is None else tuple(float(x) for x in H)
+            b = (2.0, 1.0) if b is None else tuple(float(x) for x in b)
+            if len(H) != 2 or len(b) != 2 or H[0] != H[1]:
+                raise _lib.SwrtError("MultiLayerQG is implemented for two layers of equal depth")
+            F = f0 ** 2 / ((b[0] - b[1]) * H[0])
+            U, U2 = (float(U[0]), float(U[1])) if np.ndim(U) else (float(U), -float(U))
         d = FlowDesc(model=MODELS[model], stepper=STEPPERS[stepper], nx=nx, ny=ny, nnu=nν, use_filter=int(use_filter),
                      filter_order=order, device=int(dev), Lx=Lx, Ly=Ly, dt=dt, nu=ν, f=f, Cg=Cg,
                      aliased_fraction=aliased_fraction, filter_innerK=innerK, filter_outerK=outerK, filter_tol=tol,
-                     U=U, mu=μ, F=F, Ro=Ro, slab_rank=0 if slab is None else int(slab[0]),
+                     U=U, mu=μ, F=F, Ro=Ro, U2=U2, beta=β, slab_rank=0 if slab is None else int(slab[0]),
                      slab_size=0 if slab is None else int(slab[1]))
         self._h = C.c_void_p()
         check(lib().swrt_flow_create(C.byref(d), C.byref(self._h)))

@@ -88,6 +88,25 @@ def twolayer_calcN(sol, grid, F):
     return N
 
 
+def multilayer2_calcN(sol, grid, F, U1, U2, beta, mu):
+    """GeophysicalFlows MultiLayerQG.calcN! for two equal layers (third party, un-vendored; restated from SURVEY App. C --
+    PARITY UNPINNED): N_j = -F[(u_j+U_j) Qx] - F[v_j Qy_j] - i k F[(u_j+U_j) q_j] - i l F[v_j q_j], Qx = 0,
+    Qy = beta +- F (U1 - U2), and the bottom drag N_2 += mu K^2 psih_2.  Called by raytracing/TwoLayerRaytracing.jl:129-130
+    with aliased_fraction = 0 (:174), so the physical-space products alias exactly as written here."""
+    g = grid
+    g.dealias(sol)
+    psih = twolayer_streamfunction(sol, g, F)
+    N = np.empty_like(sol)
+    Qy = (beta + F * (U1 - U2), beta - F * (U1 - U2))
+    for j, Uj in enumerate((U1, U2)):
+        u = g.irfft2(-1j * g.l * psih[:, :, j]) + Uj
+        v = g.irfft2(1j * g.kr * psih[:, :, j])
+        q = g.irfft2(sol[:, :, j])
+        N[:, :, j] = -g.rfft2(v * Qy[j]) - 1j * g.kr * g.rfft2(u * q) - 1j * g.l * g.rfft2(v * q)
+    N[:, :, 1] += mu * g.Krsq * psih[:, :, 1]
+    return N
+
+
 def twolayer_energies(sol, grid, F):
     psih = twolayer_streamfunction(sol, grid, F)
     A = grid.Lx * grid.Ly

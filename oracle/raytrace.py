@@ -257,3 +257,18 @@ def raytrace_midpoint(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, sampl
         fz = rhs_sampler(z, sign, alpha, sampler(F_old, z[:, 0], z[:, 1], grid), sampler(F_new, z[:, 0], z[:, 1], grid), f, Cg)
         xk += h * fz
     return xk
+
+
+def generate_initial_wavepackets_twolayer(L, k0, sqrtN):
+    """raytracing/TwoLayerRaytracing.jl:10-22 (the CPU driver's lattice): packet (i-1) s + j sits at
+    (i L/s - L/2 - L/2s, j L/s - L/2 - L/2s) with wavevector angle 2 pi ((i-1) s + j)/N; all frequency signs +1."""
+    s = int(sqrtN)
+    N = s * s
+    xk = np.empty((N, 4))
+    offset = L / s / 2
+    for i in range(1, s + 1):
+        for j in range(1, s + 1):
+            r = (i - 1) * s + j
+            xk[r - 1] = (i * L / s - L / 2 - offset, j * L / s - L / 2 - offset,
+                         k0 * np.cos(2 * np.pi * r / N), k0 * np.sin(2 * np.pi * r / N))
+    return xk, np.ones(N)

@@ -527,3 +527,95 @@ def test_bspline_and_implicit_midpoint_modes(interp, integ):
     got = pk.get()
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-8
     assert rel_l2(got, want) < 1e-10
+
+
+def _config1_setup(nx, seed=1234):
+    """BASELINE config 1 recipe (simulation/Parameters.jl:33-49, simulation/TwoLayerSimulation.jl:42-47) at a small size."""
+    from oracle import qg as oqg
+    f0, rd, lv, avg_U, H0, b2 = 1.0, 1 / 15, 1 / 2, 0.1, 1.0, 1.0
+    l_star = lv / rd
+    kappa = 0.36 / np.log(l_star / 3.2)
+    U = avg_U / l_star
+    mu = 2 * U * kappa / rd
+    b1 = 4 * f0 ** 2 * rd ** 2 / H0 + b2
+    g = TwoDGrid(nx, aliased_fraction=0)
+    dt = 0.02 * g.dx / avg_U
+    F = f0 ** 2 / ((b1 - b2) * H0 / 2)
+    filt = makefilter(g)
+    rng = np.random.default_rng(seed)
+    q0 = 1e-2 * avg_U * rng.standard_normal((nx, nx, 2))
+    sol0 = np.stack([g.rfft2(q0[:, :, j]) * filt for j in range(2)], axis=-1)
+    # give the flow an O(avg_U) large-scale part so the nonlinear terms matter within a few steps
+    sol0[1:6, 1:6] += 1.0 * nx * nx * avg_U * (rng.standard_normal((5, 5, 2)) + 1j * rng.standard_normal((5, 5, 2)))
+    g.dealias(sol0)
+    return g, sol0, dict(f0=f0, H=(H0 / 2, H0 / 2), b=(b1, b2), U=(U, -U), mu=mu, beta=0.0, dt=dt, F=F, filt=filt)
+
+
+@pytest.mark.parametrize("stepper", ["FilteredAB3", "FilteredRK4", "ETDRK4"])
+def test_multilayerqg2_parity(stepper):
+    """GeophysicalFlows MultiLayerQG, two equal layers, aliased_fraction = 0 (config 1: raytracing/TwoLayerRaytracing.jl:174)."""
+    from oracle import qg as oqg, ty as oty
+    nx = 128
+    g, sol0, c = _config1_setup(nx)
+    nnu, nu = 4, 1e-14
+    prob = swrt.Problem(model="MultiLayerQG", stepper=stepper, nx=nx, dt=c["dt"], f0=c["f0"], H=c["H"], b=c["b"], U=c["U"],
+                        mu=c["mu"], beta=c["beta"], nu=nu, nnu=nnu, aliased_fraction=0)
+    assert abs(prob.desc.F / c["F"] - 1) < 1e-15
+    prob.sol = sol0
+    np.testing.assert_array_equal(prob.sol, sol0)
+    psih = oqg.twolayer_streamfunction(sol0, g, c["F"])
+    assert rel_l2(prob.vars.ψ, np.stack([g.irfft2(psih[:, :, j]) for j in range(2)], axis=-1)) < 1e-13
+    L = (-nu * g.Krsq ** nnu)[:, :, None] * np.ones(2)
+    calcN = lambda s: oqg.multilayer2_calcN(s, g, c["F"], c["U"][0], c["U"][1], c["beta"], c["mu"])
+    if stepper == "FilteredAB3":
+        ts = oqg.FilteredAB3(L, c["dt"], calcN, c["filt"][:, :, None])
+    elif stepper == "FilteredRK4":
+        ts = oty.FilteredRK4(L, c["dt"], calcN, c["filt"])
+    else:
+        ts = oty.ETDRK4(L, c["dt"], calcN)
+    want = sol0.copy()
+    for n in (1, 3, 26):
+        flow.stepforward(prob, (), n)
+        for _ in range(n):
+            ts.stepforward(want)
+        assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10, n
+    # the packet driver samples the layer-mean streamfunction (raytracing/TwoLayerRaytracing.jl:122)
+    vel, _ = raytracing.get_velocity_info(prob, 0, raytracing.PSI_TWOLAYER_MEAN)
+    psim = oqg.twolayer_streamfunction(g.dealias(want.copy()), g, c["F"]).mean(axis=-1)
+    assert rel_l2(vel._arr(), oray.get_velocity_info(psim, g)) < 1e-11
+
+
+def test_config1_twolayer_cpu_driver_parity():
+    """BASELINE config 1 end to end at a small size: raytracing/TwoLayerRaytracing.jl's loop (MultiLayerQG + FilteredAB3,
+    layer-mean streamfunction, quadratic B-spline x linear-in-time fields, implicit midpoint, k-cutoff reset)."""
+    from oracle import qg as oqg
+    from juliaraytracingsw_b200 import twolayer
+    nx = 64
+    g, sol0, c = _config1_setup(nx)
+    P = twolayer.Parameters(nx=nx, sqrtNpackets=8, npacketsubs=5, total_time=1.0, k_cutoff=1.75)
+    assert abs(P.dt - c["dt"]) < 1e-18
+    prob, packets, frames, step = twolayer.start(P, qh=sol0, max_frames=2)
+    assert len(frames) == 3 and prob.clock.step == 10 and step == 2 * (5 * 2 + 1)
+    # oracle loop
+    L = np.zeros((g.nkr, g.nl, 2))
+    ts = oqg.FilteredAB3(L, c["dt"], lambda s: oqg.multilayer2_calcN(s, g, c["F"], c["U"][0], c["U"][1], 0.0, c["mu"]),
+                         c["filt"][:, :, None])
+    k0 = np.sqrt(3.0)
+    xk, sign = oray.generate_initial_wavepackets_twolayer(P.L, k0, 8)
+    np.testing.assert_array_equal(frames[0].x, xk[:, 0:2])
+    np.testing.assert_array_equal(frames[0].k, xk[:, 2:4])
+    fields = lambda s: oray.bspline2_prefilter(oray.get_velocity_info(oqg.twolayer_streamfunction(s, g, c["F"]).mean(axis=-1), g), g)
+    want = sol0.copy()
+    Fo, t, nreset = fields(want), 0.0, 0
+    for fr in range(2):
+        for _ in range(5):
+            ts.stepforward(want)
+            Fn = fields(g.dealias(want.copy()))
+            xk = oray.raytrace_midpoint(xk, sign, t, ts.t, Fo, Fn, g, 1.0, 1.0, nsub=1, sampler=oray.sample_bspline2)
+            nreset += oray.kcutoff_reset(xk, 1.75, k0)
+            Fo, t = Fn, ts.t
+        got = np.concatenate([frames[fr + 1].x, frames[fr + 1].k], axis=1)
+        assert np.abs(got - xk).max() / np.abs(xk).max() < 1e-8, fr
+        assert rel_l2(frames[fr + 1].u, oray.sample_bspline2(Fo, xk[:, 0], xk[:, 1], g)[:, 0:2]) < 1e-8
+    assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10
+    assert nreset > 0                                              # the cutoff was exercised

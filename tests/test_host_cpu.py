@@ -56,3 +56,20 @@ def test_sequenced_output_rollover_matches_oracle_K13():
 
 def test_collated_filename_K12():
     assert outputs.collated_filename("test_dir3/sin", 1) == "test_dir3/sin_00000001.out"
+
+
+def test_twolayer_driver_lattice_and_parameters():
+    """raytracing/TwoLayerRaytracing.jl:10-22 lattice (integer indexing bit-exact against the loop restatement) and
+    simulation/Parameters.jl:6-24 derived parameters."""
+    import numpy as np
+    from oracle import raytrace as oray
+    from juliaraytracingsw_b200 import twolayer
+    for s in (1, 3, 20):
+        xk, sign = oray.generate_initial_wavepackets_twolayer(2 * np.pi, np.sqrt(3.0), s)
+        np.testing.assert_array_equal(twolayer.generate_initial_wavepackets(2 * np.pi, np.sqrt(3.0), s * s, s), xk)
+        assert np.all(sign == 1)
+    P = twolayer.Parameters()
+    mu, b1, U = P.compute_parameters()
+    assert abs(U - 0.1 / 7.5) < 1e-17 and abs(b1 - (4 / 225 + 1)) < 1e-15
+    assert abs(mu - 2 * U * (0.36 / np.log(7.5 / 3.2)) * 15) < 1e-15
+    assert abs(P.dt - 0.02 * (2 * np.pi / 512) / 0.1) < 1e-18
