@@ -107,6 +107,18 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host);
  * (raytracing/SteadyRaytracing.jl) and by tests */
 int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host);
 
+/* ---- wave / balanced projections on the device ------------------------------------------------------------
+ * wave_balanced_decomposition(prob)  rsw/RSWUtils.jl:5-22 for the eta-based RSW models, decompose_balanced_wave(sol, grid)
+ * thomasyamada/TYUtils.jl:40-51 for Thomas-Yamada: complex128 (nkr, nl, 3) arrays; either pointer may be NULL. */
+int swrt_flow_wave_balanced_decomposition(swrt_flow* h, void* balanced_host, void* wave_host);
+/* compute_balanced_wave_weights with compute_balanced_wave_bases, rsw/RSWUtils.jl:24-57: c0, c+, c- as complex128 (nkr, nl) */
+int swrt_flow_wave_balanced_weights(swrt_flow* h, void* c0_host, void* cp_host, void* cm_host);
+/* wave_geostrophic_energy(prob)  thomasyamada/ThomasYamada.jl:355-367: out[4] = {KE_wave, PE_wave, KE_balanced, PE_balanced};
+ * for RSW the parts go through kinetic_energy / potential_energy of rsw/RotatingShallowWater.jl:323-336.  Reduced on the device. */
+int swrt_flow_wave_balanced_energies(swrt_flow* h, double* out);
+/* barotropic_energy(prob)  thomasyamada/ThomasYamada.jl:343-350 */
+int swrt_flow_barotropic_energy(swrt_flow* h, double* e);
+
 /* ---- slab-decomposed flow step (grids >= 4096^2; one process per GPU) ------------------------------------
  * Rank r owns retained kr columns [r*chunk, (r+1)*chunk) in spectral space and ny/P rows in physical space.  A step is
  *   slab_stage_a  (y-transforms of the local columns)      -> buffer A_SEND, laid out [dest][job][row][chunk]

@@ -54,6 +54,10 @@ SIGNATURES = {
     "swrt_flow_set_field_physical": (_I, [_P, _I, _P]),
     "swrt_flow_energies": (_I, [_P, _PD, _PD]),
     "swrt_flow_layer_kinetic_energy": (_I, [_P, _I, _PD]),
+    "swrt_flow_wave_balanced_decomposition": (_I, [_P, _P, _P]),
+    "swrt_flow_wave_balanced_weights": (_I, [_P, _P, _P, _P]),
+    "swrt_flow_wave_balanced_energies": (_I, [_P, _PD]),
+    "swrt_flow_barotropic_energy": (_I, [_P, _PD]),
     "swrt_flow_max_abs_uv": (_I, [_P, _PD, _PD]),
     "swrt_flow_has_nan": (_I, [_P, _PI]),
     "swrt_flow_velocity_snapshot": (_I, [_P, _I, _I]),

@@ -622,9 +622,9 @@ int swrt_flow_get_field(swrt_flow* h, int which, double* real_host) {
     return SWRT_OK;
 }
 
-static double spectral_diag(swrt_flow* h, int which, int arg, cudaError_t* err) {
+static double spectral_diag(swrt_flow* h, int which, int arg, cudaError_t* err, const double2* src = nullptr) {
     const int blocks = 296;
-    { ProfScope ps(h, K_OTHER); spectral_diag_kernel<<<blocks, 256, 0, h->st>>>(h->sol, h->L, which, arg, h->nvar, h->L.aux0, h->red); }
+    { ProfScope ps(h, K_OTHER); spectral_diag_kernel<<<blocks, 256, 0, h->st>>>(src ? src : h->sol, h->L, which, arg, h->nvar, h->L.aux0, h->red); }
     std::vector<double> part(blocks);
     *err = cudaMemcpyAsync(part.data(), h->red, sizeof(double) * blocks, cudaMemcpyDeviceToHost, h->st);
     if (*err != cudaSuccess) return 0;
@@ -685,6 +685,80 @@ int swrt_flow_energies(swrt_flow* h, double* ke, double* pe) {
     }
     if (ke) *ke = k;
     if (pe) *pe = p;
+    return SWRT_OK;
+}
+
+// ---- wave / balanced projections on the device
+static int decompose_launch(swrt_flow* h, int mode) {
+    const bool rsw = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;
+    if (mode == DEC_TY ? h->d.model != SWRT_THOMASYAMADA : !rsw)
+        return fail(SWRT_ERR_UNSUPPORTED, "the wave/balanced projection is defined for the eta-based RSW models and Thomas-Yamada (model %d)", h->d.model);
+    if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow");
+    const SpecLayout& L = h->L;
+    const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+    if (nmodes == 0) return SWRT_OK;
+    { ProfScope ps(h, K_OTHER); decompose_kernel<<<(int)((nmodes + 255) / 256), 256, 0, h->st>>>(h->sol, L, mode, h->d.f, L.Cg2, h->G, h->H); }
+    CK(cudaGetLastError());
+    return SWRT_OK;
+}
+static int fetch3(swrt_flow* h, const double2* src, void* host) {
+    { ProfScope ps(h, K_OTHER); unpack_sol_kernel<<<592, 256, 0, h->st>>>(src, h->stage, h->L, h->nkr, 3); }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host, h->stage, sizeof(double2) * (size_t)h->nkr * h->d.ny * 3, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_wave_balanced_decomposition(swrt_flow* h, void* balanced_host, void* wave_host) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    int rc = decompose_launch(h, h->d.model == SWRT_THOMASYAMADA ? DEC_TY : DEC_RSW);
+    if (rc) return rc;
+    if (balanced_host && (rc = fetch3(h, h->G, balanced_host))) return rc;
+    if (wave_host && (rc = fetch3(h, h->H, wave_host))) return rc;
+    return SWRT_OK;
+}
+
+int swrt_flow_wave_balanced_weights(swrt_flow* h, void* c0_host, void* cp_host, void* cm_host) {
+    if (!h || !c0_host || !cp_host || !cm_host) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    int rc = decompose_launch(h, DEC_RSW_WTS);
+    if (rc) return rc;
+    { ProfScope ps(h, K_OTHER); unpack_sol_kernel<<<592, 256, 0, h->st>>>(h->G, h->stage, h->L, h->nkr, 3); }
+    CK(cudaGetLastError());
+    const size_t one = sizeof(double2) * (size_t)h->nkr * h->d.ny;
+    void* outs[3] = {c0_host, cp_host, cm_host};
+    for (int c = 0; c < 3; ++c) CK(cudaMemcpyAsync(outs[c], reinterpret_cast<char*>(h->stage) + c * one, one, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
+int swrt_flow_wave_balanced_energies(swrt_flow* h, double* out) {
+    if (!h || !out) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(h->d.device));
+    const bool ty = h->d.model == SWRT_THOMASYAMADA;
+    int rc = decompose_launch(h, ty ? DEC_TY : DEC_RSW);
+    if (rc) return rc;
+    // TY: raw parsevalsum2 values (thomasyamada/ThomasYamada.jl:355-367); RSW: kinetic_energy / potential_energy of each part (:323-336)
+    const double A2 = 2 * h->d.Lx * h->d.Ly, ks = ty ? 1.0 : 1.0 / A2, ps = ty ? 1.0 : h->L.Cg2 / A2;
+    cudaError_t e = cudaSuccess;
+    const double2* parts[2] = {h->H, h->G};   // wave first, like the reference's return value
+    for (int p = 0; p < 2; ++p) {
+        double k = spectral_diag(h, DIAG_ABS2_VAR, 0, &e, parts[p]); CK(e);
+        k += spectral_diag(h, DIAG_ABS2_VAR, 1, &e, parts[p]); CK(e);
+        const double pe = spectral_diag(h, DIAG_ABS2_VAR, 2, &e, parts[p]); CK(e);
+        out[2 * p] = ks * k;
+        out[2 * p + 1] = ps * pe;
+    }
+    return SWRT_OK;
+}
+
+int swrt_flow_barotropic_energy(swrt_flow* h, double* e_out) {
+    if (!h || !e_out) return fail(SWRT_ERR_ARG, "null pointer");
+    if (h->d.model != SWRT_THOMASYAMADA) return fail(SWRT_ERR_UNSUPPORTED, "barotropic_energy is defined for Thomas-Yamada");
+    CK(cudaSetDevice(h->d.device));
+    cudaError_t e = cudaSuccess;
+    *e_out = spectral_diag(h, DIAG_INVK2_ABS2_VAR, 0, &e); CK(e);
     return SWRT_OK;
 }
 

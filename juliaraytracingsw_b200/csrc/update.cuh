@@ -253,9 +253,78 @@ __global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, do
     }
 }
 
+// ---------------------------------------------------------------- wave / balanced projections
+// DEC_RSW:     wave_balanced_decomposition, rsw/RSWUtils.jl:9-22 -- balanced part from the linear PV, wave part = rest.
+// DEC_TY:      decompose_balanced_wave, thomasyamada/TYUtils.jl:10-51 -- projections of (u_c, v_c, p_c) on Phi0 and Phi+-.
+// DEC_RSW_WTS: compute_balanced_wave_weights with the bases of rsw/RSWUtils.jl:24-57 -> A = (c0, c+, c-); the sign of the
+//              eta component of Phi0 is the reference's (:33), which makes Phi0 non-orthogonal to Phi+- -- kept as written.
+enum { DEC_RSW = 0, DEC_TY = 1, DEC_RSW_WTS = 2 };
+struct cd { double x, y; };
+__device__ __forceinline__ cd cmul(cd a, cd b) { return cd{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cd cmulc(cd a, cd b) { return cd{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }   // a conj(b)
+__global__ void __launch_bounds__(256) decompose_kernel(const double2* __restrict__ sol, SpecLayout L, int mode, double f, double Cg2,
+                                                        double2* __restrict__ A, double2* __restrict__ B) {
+    const int nlk = L.ny - (L.lz1 - L.lz0);
+    const long long total = (long long)nlk * L.kr_keep;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
+        const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
+        const long long off = (long long)l * L.kr_pad + kr;
+        const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
+        const int v0 = mode == DEC_TY ? 1 : 0;
+        const double2 s0 = sol[(v0 + 0) * L.vs + off], s1 = sol[(v0 + 1) * L.vs + off], s2 = sol[(v0 + 2) * L.vs + off];
+        if (mode == DEC_RSW) {
+            // qh = i k vh - i l uh - f etah ; psih = -qh / (K^2 + f^2/Cg2)
+            const double inv = -1.0 / (K2 + f * f / Cg2);
+            const cd psi{inv * (-(kw * s1.y - lw * s0.y) - f * s2.x), inv * ((kw * s1.x - lw * s0.x) - f * s2.y)};
+            const double2 g0 = make_double2(lw * psi.y, -lw * psi.x), g1 = make_double2(-kw * psi.y, kw * psi.x);
+            const double2 g2 = make_double2(f / Cg2 * psi.x, f / Cg2 * psi.y);
+            A[off] = g0; A[L.vs + off] = g1; A[2 * L.vs + off] = g2;
+            B[off] = make_double2(s0.x - g0.x, s0.y - g0.y);
+            B[L.vs + off] = make_double2(s1.x - g1.x, s1.y - g1.y);
+            B[2 * L.vs + off] = make_double2(s2.x - g2.x, s2.y - g2.y);
+            continue;
+        }
+        const bool ty = mode == DEC_TY;
+        const double ff = ty ? 1.0 : f, Cg = ty ? 1.0 : sqrt(Cg2);
+        const double w = sqrt(ff * ff + Cg * Cg * K2), sq = K2 > 0.0 ? sqrt(0.5 / K2) : 0.0;
+        cd P0[3], Pp[3], Pm[3];
+        if (K2 > 0.0) {
+            if (ty) { P0[0] = cd{0, lw / w}; P0[1] = cd{0, -kw / w}; P0[2] = cd{-1.0 / w, 0}; }
+            else { P0[0] = cd{0, -lw * Cg / w}; P0[1] = cd{0, kw * Cg / w}; P0[2] = cd{-ff / w, 0}; }
+            Pp[0] = cd{w * kw * sq / w, ff * lw * sq / w};  Pp[1] = cd{w * lw * sq / w, -ff * kw * sq / w};
+            Pm[0] = cd{-w * kw * sq / w, ff * lw * sq / w}; Pm[1] = cd{-w * lw * sq / w, -ff * kw * sq / w};
+            Pp[2] = Pm[2] = cd{(ty ? (w * w - 1.0) : Cg * K2) * sq / w, 0};
+        } else {
+            const double r = 0.70710678118654752440;   // 1/sqrt(2)
+            P0[0] = cd{0, 0}; P0[1] = cd{0, 0}; P0[2] = cd{1, 0};
+            Pp[0] = cd{0, r}; Pp[1] = cd{r, 0}; Pp[2] = cd{0, 0};
+            if (ty) { Pm[0] = cd{0, r}; Pm[1] = cd{-r, 0}; } else { Pm[0] = cd{0, -r}; Pm[1] = cd{r, 0}; }
+            Pm[2] = cd{0, 0};
+        }
+        const cd x[3] = {cd{s0.x, s0.y}, cd{s1.x, s1.y}, cd{(ty ? 1.0 : Cg) * s2.x, (ty ? 1.0 : Cg) * s2.y}};
+        cd c0{0, 0}, cp{0, 0}, cm{0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const cd a = cmulc(x[c], P0[c]), b = cmulc(x[c], Pp[c]), d = cmulc(x[c], Pm[c]);
+            c0.x += a.x; c0.y += a.y; cp.x += b.x; cp.y += b.y; cm.x += d.x; cm.y += d.y;
+        }
+        if (mode == DEC_RSW_WTS) {
+            A[off] = make_double2(c0.x, c0.y); A[L.vs + off] = make_double2(cp.x, cp.y); A[2 * L.vs + off] = make_double2(cm.x, cm.y);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const cd g = cmul(c0, P0[c]), wp = cmul(cp, Pp[c]), wm = cmul(cm, Pm[c]);
+                A[c * L.vs + off] = make_double2(g.x, g.y);
+                B[c * L.vs + off] = make_double2(wp.x + wm.x, wp.y + wm.y);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- spectral diagnostics (parseval-weighted sums)
 // value(kr,l) per `which`, summed with weights 1 (kr = 0, Nyquist) / 2 (parsevalsum / parsevalsum2 of FourierFlows)
-enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3 };
+enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3, DIAG_INVK2_ABS2_VAR = 4 };
 __global__ void __launch_bounds__(256) spectral_diag_kernel(const double2* __restrict__ sol, SpecLayout L, int which, int arg, int nlayers,
                                                             double P, double* __restrict__ partial) {
     __shared__ double sh[256];
@@ -267,9 +336,10 @@ __global__ void __launch_bounds__(256) spectral_diag_kernel(const double2* __res
         const long long off = (long long)l * L.kr_pad + kr;
         const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
         double val;
-        if (which == DIAG_ABS2_VAR) {
+        if (which == DIAG_ABS2_VAR || which == DIAG_INVK2_ABS2_VAR) {
             const double2 v = sol[arg * L.vs + off];
             val = v.x * v.x + v.y * v.y;
+            if (which == DIAG_INVK2_ABS2_VAR) val = K2 > 0.0 ? val / K2 : 0.0;
         } else if (which == DIAG_QG_DPSI2) {
             const double2 a = qg_streamfunction(sol, L.vs, 2, 0, K2, P, off), b = qg_streamfunction(sol, L.vs, 2, 1, K2, P, off);
             val = (a.x - b.x) * (a.x - b.x) + (a.y - b.y) * (a.y - b.y);

@@ -237,9 +237,39 @@ def stepforward(prob, diags=(), nsteps=1):
                 d.increment(prob)
 
 
+def wave_balanced_decomposition(prob):
+    """`wave_balanced_decomposition(prob)` (rsw/RSWUtils.jl:5-22) / `decompose_balanced_wave(sol, grid)`
+    (thomasyamada/TYUtils.jl:40-51): (balanced, wave) as complex (nkr, nl, 3) arrays, projected on the device."""
+    shape = (prob.grid.nkr, prob.grid.nl, 3)
+    bal, wav = (np.empty(shape, dtype=np.complex128, order="F") for _ in range(2))
+    check(lib().swrt_flow_wave_balanced_decomposition(prob._h, bal.ctypes.data_as(C.c_void_p), wav.ctypes.data_as(C.c_void_p)))
+    return bal, wav
+
+
+def compute_balanced_wave_weights(prob):
+    """`compute_balanced_wave_weights(uh, vh, ηh, Φ₀, Φ₊, Φ₋, params)` with the bases of rsw/RSWUtils.jl:24-49 -> (c₀, c₊, c₋)."""
+    c = [np.empty((prob.grid.nkr, prob.grid.nl), dtype=np.complex128, order="F") for _ in range(3)]
+    check(lib().swrt_flow_wave_balanced_weights(prob._h, *(a.ctypes.data_as(C.c_void_p) for a in c)))
+    return tuple(c)
+
+
+def wave_geostrophic_energy(prob):
+    """`wave_geostrophic_energy(prob)` (thomasyamada/ThomasYamada.jl:355-367): ((KE_w, PE_w), (KE_g, PE_g)), reduced on the device."""
+    out = (C.c_double * 4)()
+    check(lib().swrt_flow_wave_balanced_energies(prob._h, out))
+    return (out[0], out[1]), (out[2], out[3])
+
+
+def barotropic_energy(prob):
+    """`barotropic_energy(prob)` (thomasyamada/ThomasYamada.jl:343-350)."""
+    v = C.c_double()
+    check(lib().swrt_flow_barotropic_energy(prob._h, C.byref(v)))
+    return v.value
+
+
 def kinetic_energy(prob):
     """kinetic_energy(prob); the two-layer model returns (KE_1, KE_2) like swqg/TwoLayerQG.jl:221-233."""
-    if prob.desc.model == 5:
+    if prob.desc.model in (5, 7):
         out = []
         for layer in range(2):
             v = C.c_double()

@@ -619,3 +619,39 @@ def test_config1_twolayer_cpu_driver_parity():
         assert rel_l2(frames[fr + 1].u, oray.sample_bspline2(Fo, xk[:, 0], xk[:, 1], g)[:, 0:2]) < 1e-8
     assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-10
     assert nreset > 0                                              # the cutoff was exercised
+
+
+def test_wave_balanced_projections_on_device():
+    """SURVEY 8f.1: rsw/RSWUtils.jl:5-64 and thomasyamada/TYUtils.jl:10-51 on the device, against the oracle restatement;
+    K10 / K11 properties on the device results."""
+    from oracle import decompose as od
+    g, p, sol0, c = config2_setup(128)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    bal, wav = flow.wave_balanced_decomposition(prob)
+    wb, ww = od.wave_balanced_decomposition(sol0, g, p)
+    assert rel_l2(bal, wb) < 1e-14 and rel_l2(wav, ww) < 1e-13
+    scale = np.abs(sol0).max()
+    assert np.abs(1j * g.kr * bal[:, :, 0] + 1j * g.l * bal[:, :, 1]).max() < 1e-12 * scale * g.kr.max()          # K10: non-divergent
+    assert np.abs(1j * g.kr * wav[:, :, 1] - 1j * g.l * wav[:, :, 0] - p.f * wav[:, :, 2]).max() < 1e-12 * scale * g.kr.max()   # K10: no PV
+    (kw, pw), (kg, pg) = flow.wave_geostrophic_energy(prob)
+    assert abs(kw / orsw.kinetic_energy(ww, g) - 1) < 1e-12 and abs(pw / orsw.potential_energy(ww, g, p) - 1) < 1e-12
+    assert abs(kg / orsw.kinetic_energy(wb, g) - 1) < 1e-12 and abs(pg / orsw.potential_energy(wb, g, p) - 1) < 1e-12
+    cw = od.rsw_weights(sol0, od.rsw_bases(g, p), p)
+    for got, want in zip(flow.compute_balanced_wave_weights(prob), cw):
+        assert rel_l2(got, g.dealias(want.copy())) < 1e-13
+    # Thomas-Yamada
+    from oracle.grid import parsevalsum2
+    rng = np.random.default_rng(8)
+    gt = TwoDGrid(64, 6 * np.pi)
+    s4 = gt.dealias(rng.standard_normal((gt.nkr, gt.nl, 4)) + 1j * rng.standard_normal((gt.nkr, gt.nl, 4)))
+    pt = swrt.Problem(model="ThomasYamada", stepper="ETDRK4", nx=64, Lx=6 * np.pi, dt=5e-3, Ro=1.0, nu=1e-20, nnu=8)
+    pt.sol = s4
+    G, W = flow.wave_balanced_decomposition(pt)
+    Go, Wo = od.ty_decompose(s4, gt)
+    assert rel_l2(G, Go) < 1e-13 and rel_l2(W, Wo) < 1e-13
+    assert np.abs(G + W - s4[:, :, 1:4]).max() < 1e-12                                   # K11: the projection is complete
+    (kw, pw), (kg, pg) = flow.wave_geostrophic_energy(pt)
+    assert abs(kw / (parsevalsum2(Wo[:, :, 0], gt) + parsevalsum2(Wo[:, :, 1], gt)) - 1) < 1e-12
+    assert abs(pg / parsevalsum2(Go[:, :, 2], gt) - 1) < 1e-12
+    assert abs(flow.barotropic_energy(pt) / parsevalsum2(np.sqrt(gt.invKrsq) * s4[:, :, 0], gt) - 1) < 1e-12

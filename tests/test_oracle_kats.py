@@ -282,3 +282,32 @@ def test_implicit_midpoint_is_second_order_and_symmetric():
     fwd = oray.raytrace_midpoint(xk.copy(), sign, 0.0, T, F, F, g, c["f"], c["Cg"], nsub=8, iters=40)
     back = oray.raytrace_midpoint(fwd.copy(), sign, T, 0.0, F, F, g, c["f"], c["Cg"], nsub=8, iters=40)
     assert np.abs(back - xk).max() < 1e-9 * max(1.0, np.abs(xk).max())
+
+
+def test_K10_K11_wave_balanced_projections():
+    """K10 (Notebooks/RSWInitialTestng.ipynb:95-96): the balanced part is non-divergent and the wave part carries no linear PV;
+    K11 (thomasyamada/Notebooks/TestDecomposition.ipynb:45,138): G + W reproduces the baroclinic state (4.7e-13 there) and a
+    purely balanced state has no wave part (1.4e-13 there)."""
+    from oracle import decompose as od, rsw as orsw
+    from oracle.grid import TwoDGrid
+    from helpers import random_state
+    g, sol = random_state(64, seed=1, amp=0.2)
+    p = orsw.Params(1e-9, 4, 3.0, 1.0)
+    bal, wav = od.wave_balanced_decomposition(sol, g, p)
+    scale = np.abs(sol).max() * g.kr.max()
+    assert np.abs(1j * g.kr * bal[:, :, 0] + 1j * g.l * bal[:, :, 1]).max() < 3.2e-13 * scale
+    assert np.abs(1j * g.kr * wav[:, :, 1] - 1j * g.l * wav[:, :, 0] - p.f * wav[:, :, 2]).max() < 3.4e-13 * scale
+    gt = TwoDGrid(64, 6 * np.pi)
+    rng = np.random.default_rng(0)
+    s4 = rng.standard_normal((gt.nkr, gt.nl, 4)) + 1j * rng.standard_normal((gt.nkr, gt.nl, 4))
+    G, W = od.ty_decompose(s4, gt)
+    assert np.abs(G + W - s4[:, :, 1:4]).max() < 4.7e-13
+    sb = s4.copy()
+    sb[:, :, 1:4] = G
+    assert np.abs(od.ty_decompose(sb, gt)[1]).max() < 1.4e-13
+    # the TY bases are orthonormal at every wavenumber
+    P0, Pp, Pm = od.ty_bases(gt)
+    for A in (P0, Pp, Pm):
+        for B in (P0, Pp, Pm):
+            ip = (A * np.conj(B)).sum(axis=-1)
+            assert np.abs(ip - (1.0 if A is B else 0.0)).max() < 1e-13
