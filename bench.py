@@ -39,6 +39,7 @@ def parse():
                          "over the ranks + 67M packets (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
     return ap.parse_args()
 
 
@@ -249,18 +250,22 @@ def run_swrt(args):
     e2e = None
     if not args.no_e2e:
         pin = lambda *shape: torch.empty(shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T  # Fortran-ordered view
-        h_xk, h_U, h_G = pin(nloc, 4), pin(nloc, 2), pin(nloc, 4)
+        h_xk, h_out, h_U, h_G = pin(nloc, 4), pin(nloc, 4), pin(nloc, 2), pin(nloc, 4)
         h_sign = torch.empty(nloc, dtype=torch.float64, pin_memory=True).numpy()
         packets.get(out=h_xk)
         h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
         Ke = max(3, min(K, 10))
+        nchunks = max(1, min(args.e2e_chunks, nloc // 65536))
+        pipe = raytracing.PacketPipeline(prob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
 
         def e2e_step(t):
-            packets.set(h_xk, h_sign)
-            t = drivers.coupled_step(prob, packets, t)
-            packets.get(out=h_xk)
-            raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), packets, output_G=h_G, output_U=h_U)
-            return t
+            # the packets of this step arrive from the host and the output frame goes back, chunk by chunk on the chunks' own
+            # streams: uploads, sort + ray-trace kernels and downloads of different chunks overlap (raytracing.PacketPipeline)
+            flow.stepforward(prob, (), 1)
+            raytracing.get_velocity_info(prob, 1)
+            new_t = prob.clock.t
+            pipe.step(h_xk, h_sign, (t, new_t), h_out, h_U, h_G, after_raytrace=lambda: raytracing.swap_snapshots(prob, alias=False))
+            return new_t
         t = e2e_step(t)
         prob.sync(); barrier()
         w0 = time.perf_counter()
@@ -273,8 +278,11 @@ def run_swrt(args):
         ms_e = max_over_ranks(max(ms_e, wall))
         e2e = {"value": ntot * Ke / (ms_e * 1e-3), "unit": "packet-steps/s", "h2d_bytes_per_step": int(8 * 5 * nloc),
                "d2h_bytes_per_step": int(8 * 10 * nloc), "steps": Ke, "ms_per_step": ms_e / Ke,
-               "what": "per step: packets (N,4)+sign from pinned host memory -> set; flow step + snapshot + raytrace; "
-                       "packets (N,4), velocity (N,2) and gradients (N,4) sampled and copied back (savepacketdata!)"}
+               "chunks": nchunks,
+               "what": "per step: flow step + snapshot; packets (N,4)+sign from pinned host memory -> set -> sort + raytrace -> "
+                       "packets (N,4), velocity (N,2) and gradients (N,4) sampled and copied back (savepacketdata!), "
+                       "in `chunks` row blocks on their own streams so copies and kernels overlap"}
+        pipe.close()
     clk = clocks.stop()
 
     if rank != 0:

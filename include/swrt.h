@@ -194,6 +194,18 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
 int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host);
 /* k-cutoff reset raytracing/GPUTwoLayerRaytracing.jl:136-138 */
 int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long long* nreset);
+/* ---- overlapped packet I/O -----------------------------------------------------------------------------
+ * Give the handle its own CUDA stream; its copies and kernels then overlap the flow's stream and other packet handles
+ * (events order them against the snapshots they read).  Split an ensemble over several handles and issue, per handle,
+ * set_async -> raytrace -> get_async / sample_async: uploads, kernels and downloads of different handles pipeline on the two
+ * copy engines and the SMs.  Host buffers must be page-locked for the copies to be asynchronous; `ld` is the host arrays'
+ * leading dimension in elements (>= n), so handles can address row blocks of one (N, ncol) column-major array.
+ * Results are valid after swrt_packets_sync. */
+int swrt_packets_use_own_stream(swrt_packets* p);
+int swrt_packets_set_async(swrt_packets* p, const double* xk_host, long long ld, const double* sign_host);
+int swrt_packets_get_async(swrt_packets* p, double* xk_host, long long ld);
+int swrt_packets_sample_async(swrt_packets* p, int slot, double* u_host, double* g_host, long long ld);
+int swrt_packets_sync(swrt_packets* p);
 
 /* Output roll-over arithmetic (host, integer only): utils/SequencedOutputs.jl:37-63, utils/Collated.jl:40-60 */
 typedef struct swrt_seqout { long long max_writes, current_writes, file_index; } swrt_seqout;

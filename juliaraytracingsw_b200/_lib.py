@@ -91,6 +91,11 @@ SIGNATURES = {
     "swrt_packets_raytrace": (_I, [_P, _D, _D]),
     "swrt_packets_sample": (_I, [_P, _I, _P, _P]),
     "swrt_packets_kcutoff_reset": (_I, [_P, _D, _D, _PLL]),
+    "swrt_packets_use_own_stream": (_I, [_P]),
+    "swrt_packets_set_async": (_I, [_P, _P, _LL, _P]),
+    "swrt_packets_get_async": (_I, [_P, _P, _LL]),
+    "swrt_packets_sample_async": (_I, [_P, _I, _P, _P, _LL]),
+    "swrt_packets_sync": (_I, [_P]),
     "swrt_seqout_init": (_I, [C.POINTER(SeqOut), _LL]),
     "swrt_seqout_write": (_I, [C.POINTER(SeqOut), _LL, _PLL]),
     "swrt_seqout_filename": (_I, [C.c_char_p, _LL, C.c_char_p, _I]),

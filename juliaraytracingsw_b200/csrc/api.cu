@@ -1,4 +1,5 @@
 // libswrt C ABI: handle management, host-side tables, kernel dispatch.  See include/swrt.h.
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdarg>
@@ -61,7 +62,7 @@ struct swrt_flow {
     SpecLayout L{};
     int nkr = 0, nvar = 3, njobs_a = 5, njobs_b = 4;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
@@ -91,6 +92,7 @@ struct swrt_flow {
     std::vector<cudaEvent_t> pool;
     double prof_ms[16] = {0};
     long long prof_n[16] = {0};
+    std::vector<struct swrt_packets*> readers;   // packet handles with their own stream (snapshot writers wait for their reads)
 };
 
 enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_PSI, K_OTHER, K_COUNT };
@@ -103,16 +105,17 @@ struct ProfScope {
     swrt_flow* h;
     int id;
     cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(swrt_flow* h_, int id_) : h(h_), id(id_) {
+    cudaStream_t st;
+    ProfScope(swrt_flow* h_, int id_, cudaStream_t st_ = nullptr) : h(h_), id(id_), st(st_ ? st_ : h_->st) {
         h->launches++;
         if (!h->prof) return;
         auto get = [&]() { cudaEvent_t e; if (h->pool.empty()) cudaEventCreate(&e); else { e = h->pool.back(); h->pool.pop_back(); } return e; };
         a = get(); b = get();
-        cudaEventRecord(a, h->st);
+        cudaEventRecord(a, st);
     }
     ~ProfScope() {
         if (!a) return;
-        cudaEventRecord(b, h->st);
+        cudaEventRecord(b, st);
         h->recs.push_back({id, a, b});
     }
 };
@@ -139,7 +142,11 @@ struct swrt_packets {
     long long nbins = 0;
     int since_sort = 1 << 30;   // raytrace calls since the last sort
     bool permuted = false;
+    cudaStream_t st = nullptr;      // the flow's stream, or the handle's own (swrt_packets_use_own_stream)
+    bool own = false;
+    cudaEvent_t ev_done = nullptr;  // last read of the flow's snapshots by this handle
 };
+static inline cudaEvent_t packets_done_event(const swrt_packets* p) { return p->ev_done; }
 
 // ------------------------------------------------------------------ small kernels (api TU only)
 // host (nkr, nl, nvar) column-major  <->  device [var][l][kr_pad], dealiased
@@ -293,6 +300,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->st && h->own_stream) cudaStreamDestroy(h->st);
     delete h;
@@ -358,6 +366,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
 #define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
     CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
     CKB(cudaEventCreate(&h->ev0));
+    CKB(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
     CKB(cudaEventCreate(&h->ev1));
     const size_t fb = sizeof(double2) * (size_t)L.vs;
     CKB(cudaMalloc(&h->sol, fb * h->nvar));
@@ -915,6 +924,14 @@ int swrt_slab_stage_c(swrt_flow* h) {
     h->step += 1;
     return SWRT_OK;
 }
+// snapshot writers wait for the reads of packet handles that run on their own streams
+static cudaError_t wait_readers(swrt_flow* h) {
+    for (swrt_packets* r : h->readers) {
+        cudaError_t e = cudaStreamWaitEvent(h->st, packets_done_event(r), 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
     int rc = check_psi_kind(h, psi_kind);
@@ -932,6 +949,7 @@ int swrt_slab_snap_b(swrt_flow* h, int slot) {
     if (h->interp == SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the 5-field node data");
     CK(cudaSetDevice(h->d.device));
     double* rows = h->snap[h->slot_map[slot]] + (long long)h->rank * h->L.yrows * h->d.nx * SNAP_STRIDE;   // this rank's rows of the full field
+    CK(wait_readers(h));
     cudaError_t e;
     { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(h->G2, rows, h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
@@ -946,6 +964,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     const SpecLayout& L = h->L;
     const bool pf = h->interp == SWRT_INTERP_BSPLINE2;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
+    CK(wait_readers(h));
     cudaError_t e;
     bool materialise = false;
     SWRT_DISPATCH(L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
@@ -1005,6 +1024,7 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
+    CK(wait_readers(h));
     cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * nc, cudaMemcpyHostToDevice, h->st);
     if (e == cudaSuccess) {
         ProfScope ps(h, K_OTHER);
@@ -1064,7 +1084,14 @@ int swrt_flow_launch_count(swrt_flow* h, long long* n) {
 // ------------------------------------------------------------------ packets
 int swrt_packets_destroy(swrt_packets* p) {
     if (!p) return SWRT_OK;
-    if (p->flow) { cudaSetDevice(p->flow->d.device); cudaStreamSynchronize(p->flow->st); }
+    if (p->flow) {
+        cudaSetDevice(p->flow->d.device);
+        cudaStreamSynchronize(p->st);
+        auto& rd = p->flow->readers;
+        rd.erase(std::remove(rd.begin(), rd.end(), p), rd.end());
+        if (p->own) cudaStreamDestroy(p->st);
+        if (p->ev_done) cudaEventDestroy(p->ev_done);
+    }
     cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->xk2); cudaFree(p->sign2); cudaFree(p->U); cudaFree(p->Gd);
     cudaFree(p->idx); cudaFree(p->idx2); cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count);
     delete p;
@@ -1085,6 +1112,7 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     swrt_packets* p = new swrt_packets;
     p->d = *desc;
     p->flow = flow;
+    p->st = flow->st;
     p->nbins = (long long)flow->d.nx * flow->d.ny;
     const size_t n = (size_t)desc->n;
     const size_t nsums = (size_t)(p->nbins / SCAN_BLOCK + 2) + (size_t)(p->nbins / SCAN_BLOCK / SCAN_BLOCK + 2) + 8;
@@ -1098,56 +1126,102 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
         swrt_packets_destroy(p);
         return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
     }
-    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, flow->st));
-    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, flow->st));
-    { ProfScope ps(flow, K_OTHER); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, flow->st>>>(p->idx, (long long)n); }
+    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, p->st));
+    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, p->st));
+    { ProfScope ps(flow, K_OTHER, p->st); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->idx, (long long)n); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(flow->st));
+    CK(cudaStreamSynchronize(p->st));
     *out = p;
     return SWRT_OK;
 }
 
-int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* sign_host) {
-    if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
+// host (n, ncol) column-major with leading dimension ld  <->  device [ncol][n]
+static cudaError_t copy_cols(void* dst, const void* src, long long n, int ncol, long long ld, cudaMemcpyKind kind, cudaStream_t st) {
+    if (ld == n) return cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)ncol * (size_t)n, kind, st);
+    const size_t hp = sizeof(double) * (size_t)ld, dp = sizeof(double) * (size_t)n;
+    return kind == cudaMemcpyHostToDevice ? cudaMemcpy2DAsync(dst, dp, src, hp, dp, (size_t)ncol, kind, st)
+                                          : cudaMemcpy2DAsync(dst, hp, src, dp, dp, (size_t)ncol, kind, st);
+}
+// Packets with their own stream read snapshots the flow's stream writes: order the two streams with events.
+static cudaError_t wait_flow(swrt_packets* p) {
+    if (!p->own) return cudaSuccess;
+    swrt_flow* f = p->flow;
+    cudaError_t e = cudaEventRecord(f->ev_sync, f->st);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(p->st, f->ev_sync, 0);
+}
+static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(p->ev_done, p->st) : cudaSuccess; }
+
+int swrt_packets_use_own_stream(swrt_packets* p) {
+    if (!p) return fail(SWRT_ERR_ARG, "null pointer");
+    if (p->own) return SWRT_OK;
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
-    const long long n = p->d.n;
-    if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
-        { ProfScope ps(f, K_OTHER); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->sign, p->idx, n, 1, p->sign2); }
-        CK(cudaGetLastError());
-        std::swap(p->sign, p->sign2);
-    }
-    CK(cudaMemcpyAsync(p->xk, xk_host, sizeof(double) * 4 * (size_t)n, cudaMemcpyHostToDevice, f->st));
-    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, f->st));
-    { ProfScope ps(f, K_OTHER); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->idx, n); }
-    CK(cudaGetLastError());
-    p->permuted = false;
-    p->since_sort = 1 << 30;
     CK(cudaStreamSynchronize(f->st));
+    CK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    p->own = true;
+    f->readers.push_back(p);
     return SWRT_OK;
 }
 
-int swrt_packets_get(swrt_packets* p, double* xk_host) {
+int swrt_packets_sync(swrt_packets* p) {
+    if (!p) return fail(SWRT_ERR_ARG, "null pointer");
+    CK(cudaSetDevice(p->flow->d.device));
+    CK(cudaStreamSynchronize(p->st));
+    return SWRT_OK;
+}
+
+static int packets_set_impl(swrt_packets* p, const double* xk_host, long long ld, const double* sign_host, bool sync) {
     if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
+    if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
+    if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
+        { ProfScope ps(f, K_OTHER, p->st); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->sign, p->idx, n, 1, p->sign2); }
+        CK(cudaGetLastError());
+        std::swap(p->sign, p->sign2);
+    }
+    CK(copy_cols(p->xk, xk_host, n, 4, ld, cudaMemcpyHostToDevice, p->st));
+    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, p->st));
+    { ProfScope ps(f, K_OTHER, p->st); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->idx, n); }
+    CK(cudaGetLastError());
+    p->permuted = false;
+    p->since_sort = 1 << 30;
+    if (sync) CK(cudaStreamSynchronize(p->st));
+    return SWRT_OK;
+}
+int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* sign_host) {
+    return packets_set_impl(p, xk_host, p ? p->d.n : 0, sign_host, true);
+}
+int swrt_packets_set_async(swrt_packets* p, const double* xk_host, long long ld, const double* sign_host) {
+    return packets_set_impl(p, xk_host, ld, sign_host, false);
+}
+
+static int packets_get_impl(swrt_packets* p, double* xk_host, long long ld, bool sync) {
+    if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
+    swrt_flow* f = p->flow;
+    CK(cudaSetDevice(f->d.device));
+    const long long n = p->d.n;
+    if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
     const double* src = p->xk;
     if (p->permuted) {
-        { ProfScope ps(f, K_OTHER); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, p->idx, n, 4, p->xk2); }
+        { ProfScope ps(f, K_OTHER, p->st); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, p->idx, n, 4, p->xk2); }
         CK(cudaGetLastError());
         src = p->xk2;
     }
-    CK(cudaMemcpyAsync(xk_host, src, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
-    CK(cudaStreamSynchronize(f->st));
+    CK(copy_cols(xk_host, src, n, 4, ld, cudaMemcpyDeviceToHost, p->st));
+    if (sync) CK(cudaStreamSynchronize(p->st));
     return SWRT_OK;
 }
+int swrt_packets_get(swrt_packets* p, double* xk_host) { return packets_get_impl(p, xk_host, p ? p->d.n : 0, true); }
+int swrt_packets_get_async(swrt_packets* p, double* xk_host, long long ld) { return packets_get_impl(p, xk_host, ld, false); }
 
 int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN, long long first) {
     if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->flow->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(p->flow, K_OTHER); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
+    { ProfScope ps(p->flow, K_OTHER, p->st); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
@@ -1163,17 +1237,18 @@ static PacketGrid packet_grid(const swrt_flow* f) {
     return g;
 }
 
-static cudaError_t exclusive_scan(swrt_flow* f, unsigned* a, long long nb, unsigned* scratch) {
+static cudaError_t exclusive_scan(swrt_packets* p, unsigned* a, long long nb, unsigned* scratch) {
+    swrt_flow* f = p->flow;
     const unsigned blocks = (unsigned)((nb + SCAN_BLOCK - 1) / SCAN_BLOCK);
     if (blocks <= 1) {
-        ProfScope ps(f, K_SORT);
-        scan_block_kernel<<<1, SCAN_BLOCK, 0, f->st>>>(a, nb, nullptr);
+        ProfScope ps(f, K_SORT, p->st);
+        scan_block_kernel<<<1, SCAN_BLOCK, 0, p->st>>>(a, nb, nullptr);
         return cudaGetLastError();
     }
-    { ProfScope ps(f, K_SORT); scan_block_kernel<<<blocks, SCAN_BLOCK, 0, f->st>>>(a, nb, scratch); }
-    cudaError_t e = exclusive_scan(f, scratch, blocks, scratch + blocks);
+    { ProfScope ps(f, K_SORT, p->st); scan_block_kernel<<<blocks, SCAN_BLOCK, 0, p->st>>>(a, nb, scratch); }
+    cudaError_t e = exclusive_scan(p, scratch, blocks, scratch + blocks);
     if (e != cudaSuccess) return e;
-    { ProfScope ps(f, K_SORT); scan_add_kernel<<<blocks, SCAN_BLOCK, 0, f->st>>>(a, nb, scratch); }
+    { ProfScope ps(f, K_SORT, p->st); scan_add_kernel<<<blocks, SCAN_BLOCK, 0, p->st>>>(a, nb, scratch); }
     return cudaGetLastError();
 }
 
@@ -1182,11 +1257,11 @@ static int sort_packets(swrt_packets* p) {
     swrt_flow* f = p->flow;
     const long long n = p->d.n;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, f->st));
-    { ProfScope ps(f, K_SORT); sort_hist_kernel<<<blocks, 256, 0, f->st>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
+    CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, p->st));
+    { ProfScope ps(f, K_SORT, p->st); sort_hist_kernel<<<blocks, 256, 0, p->st>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
     CK(cudaGetLastError());
-    CK(exclusive_scan(f, p->hist, p->nbins, p->sums));
-    { ProfScope ps(f, K_SORT); sort_scatter_kernel<<<blocks, 256, 0, f->st>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
+    CK(exclusive_scan(p, p->hist, p->nbins, p->sums));
+    { ProfScope ps(f, K_SORT, p->st); sort_scatter_kernel<<<blocks, 256, 0, p->st>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
     CK(cudaGetLastError());
     std::swap(p->xk, p->xk2);
     std::swap(p->sign, p->sign2);
@@ -1206,49 +1281,60 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
         if (rc) return rc;
     }
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d (swrt_flow_set_interp)", p->d.interp, f->interp);
+    CK(wait_flow(p));
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
     const double *So = f->snap[f->slot_map[0]], *Sn = f->snap[f->slot_map[1]];
     const long long n = p->d.n;
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
-    { ProfScope ps(f, K_RAYTRACE);
-#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
+    { ProfScope ps(f, K_RAYTRACE, p->st);
+#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
       if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
           if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else SWRT_GEN(2, 1);
       }
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
 #undef SWRT_GEN
-      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else raytrace_rk4_kernel<6><<<grid, 128, 0, f->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
+      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else raytrace_rk4_kernel<6><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
     CK(cudaGetLastError());
+    CK(mark_read(p));
     p->since_sort++;
     return SWRT_OK;
 }
 
-int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host) {
+static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double* g_host, long long ld, bool sync) {
     if (!p || !u_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
+    if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
+    CK(wait_flow(p));
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
     if (p->d.interp == SWRT_INTERP_BSPLINE2) {
-        ProfScope ps(f, K_SAMPLE);
-        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, p->st);
+        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
-        ProfScope ps(f, K_SAMPLE);
-        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, p->st);
+        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else
-    { ProfScope ps(f, K_SAMPLE); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, f->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
+    { ProfScope ps(f, K_SAMPLE, p->st); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(u_host, p->U, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
-    if (g_host) CK(cudaMemcpyAsync(g_host, p->Gd, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost, f->st));
-    CK(cudaStreamSynchronize(f->st));
+    CK(mark_read(p));
+    CK(copy_cols(u_host, p->U, n, 2, ld, cudaMemcpyDeviceToHost, p->st));
+    if (g_host) CK(copy_cols(g_host, p->Gd, n, 4, ld, cudaMemcpyDeviceToHost, p->st));
+    if (sync) CK(cudaStreamSynchronize(p->st));
     return SWRT_OK;
+}
+int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host) {
+    return packets_sample_impl(p, slot, u_host, g_host, p ? p->d.n : 0, true);
+}
+int swrt_packets_sample_async(swrt_packets* p, int slot, double* u_host, double* g_host, long long ld) {
+    return packets_sample_impl(p, slot, u_host, g_host, ld, false);
 }
 
 int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long long* nreset) {
@@ -1256,12 +1342,12 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
-    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), f->st));
-    { ProfScope ps(f, K_OTHER); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, f->st>>>(p->xk, n, kcut * kcut, k0, p->count); }
+    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), p->st));
+    { ProfScope ps(f, K_OTHER, p->st); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, n, kcut * kcut, k0, p->count); }
     CK(cudaGetLastError());
     unsigned long long c = 0;
-    CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, f->st));
-    CK(cudaStreamSynchronize(f->st));
+    CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, p->st));
+    CK(cudaStreamSynchronize(p->st));
     if (nreset) *nreset = (long long)c;
     return SWRT_OK;
 }

@@ -105,6 +105,39 @@ class Packets:
     def generate(self, L, k0, sqrtN, first=0):
         check(lib().swrt_packets_generate(self._h, L, k0, int(sqrtN), int(first)))
 
+    # -- overlapped I/O: the handle's own stream, asynchronous copies from / to page-locked row blocks -------------------
+    def use_own_stream(self):
+        check(lib().swrt_packets_use_own_stream(self._h))
+
+    def _cols(self, a, ncol):
+        """(pointer, leading dimension) of an (n, ncol) float64 block whose columns are contiguous (a row block of a
+        Fortran-ordered array qualifies)."""
+        assert a.dtype == np.float64 and a.shape == (self.n, ncol) and (self.n == 1 or a.strides[0] == 8), (a.shape, a.strides)
+        return a.ctypes.data_as(C.c_void_p), (a.strides[1] // 8 if ncol > 1 else self.n)
+
+    def set_async(self, xk, frequency_sign=None):
+        p, ld = self._cols(xk, 4)
+        s = None
+        if frequency_sign is not None:
+            assert frequency_sign.dtype == np.float64 and frequency_sign.flags.c_contiguous and frequency_sign.shape == (self.n,)
+            s = frequency_sign.ctypes.data_as(C.c_void_p)
+        check(lib().swrt_packets_set_async(self._h, p, ld, s))
+
+    def get_async(self, out):
+        p, ld = self._cols(out, 4)
+        check(lib().swrt_packets_get_async(self._h, p, ld))
+
+    def sample_async(self, slot, out_U, out_G=None):
+        pu, ld = self._cols(out_U, 2)
+        pg = None
+        if out_G is not None:
+            pg, ldg = self._cols(out_G, 4)
+            assert ldg == ld, "velocity and gradient blocks must share the leading dimension"
+        check(lib().swrt_packets_sample_async(self._h, int(slot), pu, pg, ld))
+
+    def sync(self):
+        check(lib().swrt_packets_sync(self._h))
+
     def kcutoff_reset(self, k_cutoff, k0):
         n = C.c_longlong()
         check(lib().swrt_packets_kcutoff_reset(self._h, k_cutoff, k0, C.byref(n)))
@@ -144,3 +177,36 @@ def interpolate_gradients(gradient, packets, output_G=None, output_U=None):
     G = np.empty((packets.n, 4), dtype=np.float64, order="F") if output_G is None else output_G
     check(lib().swrt_packets_sample(packets._h, gradient.slot, U.ctypes.data_as(C.c_void_p), G.ctypes.data_as(C.c_void_p)))
     return G
+
+
+class PacketPipeline:
+    """An ensemble split over `nchunks` packet handles, each on its own stream: per chunk
+    upload -> sort + ray-trace -> download, so the uploads, kernels and downloads of different chunks overlap on the two copy
+    engines and the SMs.  Host arrays are (N, ncol) Fortran-ordered and should be page-locked; chunk c owns the contiguous
+    rows [c N / nchunks, (c+1) N / nchunks), so row order is the caller's throughout."""
+
+    def __init__(self, prob, n, f, Cg, nchunks=8, **kw):
+        self.prob, self.n = prob, int(n)
+        self.bounds = [(c * self.n // nchunks, (c + 1) * self.n // nchunks) for c in range(nchunks)]
+        self.chunks = [Packets(prob, hi - lo, f, Cg, **kw) for lo, hi in self.bounds]
+        for p in self.chunks:
+            p.use_own_stream()
+
+    def close(self):
+        for p in self.chunks:
+            p.close()
+
+    def step(self, xk_in, sign, tspan, xk_out, out_U=None, out_G=None, after_raytrace=None, sample_slot=0):
+        """set -> raytrace over tspan -> (after_raytrace(): e.g. swap_snapshots) -> get [-> sample], all asynchronous; returns
+        after every chunk's results are on the host."""
+        for p, (lo, hi) in zip(self.chunks, self.bounds):
+            p.set_async(xk_in[lo:hi], None if sign is None else sign[lo:hi])
+            check(lib().swrt_packets_raytrace(p._h, float(tspan[0]), float(tspan[1])))
+        if after_raytrace is not None:
+            after_raytrace()
+        for p, (lo, hi) in zip(self.chunks, self.bounds):
+            p.get_async(xk_out[lo:hi])
+            if out_U is not None:
+                p.sample_async(sample_slot, out_U[lo:hi], None if out_G is None else out_G[lo:hi])
+        for p in self.chunks:
+            p.sync()

@@ -655,3 +655,37 @@ def test_wave_balanced_projections_on_device():
     assert abs(kw / (parsevalsum2(Wo[:, :, 0], gt) + parsevalsum2(Wo[:, :, 1], gt)) - 1) < 1e-12
     assert abs(pg / parsevalsum2(Go[:, :, 2], gt) - 1) < 1e-12
     assert abs(flow.barotropic_energy(pt) / parsevalsum2(np.sqrt(gt.invKrsq) * s4[:, :, 0], gt) - 1) < 1e-12
+
+
+def test_packet_pipeline_matches_single_handle():
+    """Chunked, stream-overlapped packet I/O gives bit-identical results to one synchronous handle."""
+    import torch
+    g, p, sol0, c = config2_setup(128)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 50)         # 2500 packets, 7 ragged chunks
+    xk[:, 0:2] += np.random.default_rng(2).uniform(-3, 3, size=(xk.shape[0], 2))
+    n = xk.shape[0]
+    pin = lambda *shape: torch.empty(shape[::-1], dtype=torch.float64).pin_memory().numpy().T
+    h_in, h_out, h_U, h_G = pin(n, 4), pin(n, 4), pin(n, 2), pin(n, 4)
+    h_sign = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    h_in[:], h_sign[:] = xk, sign
+    single = raytracing.Packets(prob, n, c["f"], c["Cg"], nsub=2)
+    pipe = raytracing.PacketPipeline(prob, n, c["f"], c["Cg"], nchunks=7, nsub=2)
+    raytracing.get_velocity_info(prob, 0)
+    t = 0.0
+    for step in range(4):
+        flow.stepforward(prob, (), 1)
+        raytracing.get_velocity_info(prob, 1)
+        t1 = prob.clock.t
+        single.set(h_in.copy(), sign)
+        raytracing.raytrace(single, None, None, None, None, prob.grid, single, c["dt"], (t, t1))
+        pipe.step(h_in, h_sign, (t, t1), h_out, h_U, h_G, after_raytrace=lambda: raytracing.swap_snapshots(prob), sample_slot=0)
+        want = single.get()
+        np.testing.assert_array_equal(h_out, want)
+        G = raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), single, output_U=(U := np.empty((n, 2), order="F")))
+        np.testing.assert_array_equal(h_U, U)
+        np.testing.assert_array_equal(h_G, G)
+        h_in[:] = h_out
+        t = t1
+    pipe.close()
