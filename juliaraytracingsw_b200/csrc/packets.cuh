@@ -194,10 +194,9 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
     d[3] = -(W[3] * k - W[2] * l);
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* __restrict__ xk, const double* __restrict__ sign,
-                                                                        long long n, const double* __restrict__ So,
-                                                                        const double* __restrict__ Sn, PacketGrid g, RayParams p) {
+__device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk, const double* __restrict__ sign, long long n,
+                                                         const double* __restrict__ So, const double* __restrict__ Sn,
+                                                         const PacketGrid& g, const RayParams& p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
@@ -230,6 +229,12 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* 
     xk[3 * n + i] = s[3];
 }
 
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* __restrict__ xk, const double* __restrict__ sign,
+                                                                        long long n, const double* __restrict__ So,
+                                                                        const double* __restrict__ Sn, PacketGrid g, RayParams p) {
+    raytrace_rk4_cached_body(xk, sign, n, So, Sn, g, p);
+}
 // ---------------------------------------------------------------- Hermite-bicubic mode
 // u, v interpolated from (f, f_x, f_y, f_xy) node data (utils/CUDAInterpolations.jl:39-53,71-108); the gradient that enters
 // dk/dt is the analytic gradient of that interpolant.  Node record (snapshot_layout.cuh): u, v, ux, uy, vx, uxy, vxy, pad.
