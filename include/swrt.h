@@ -119,6 +119,23 @@ int swrt_flow_wave_balanced_energies(swrt_flow* h, double* out);
 /* barotropic_energy(prob)  thomasyamada/ThomasYamada.jl:343-350 */
 int swrt_flow_barotropic_energy(swrt_flow* h, double* e);
 
+/* ---- k-omega accumulator ----------------------------------------------------------------------------------
+ * The reference post-processes stored snapshots with one SLURM task per kr index (thomasyamada/TY_k_omega.jl:46-110,
+ * rsw/fourier-analysis/mrsw/FourierRSW.jl:76-160).  Here the series are appended on the device while the flow runs and the
+ * windowed transforms in time run on the device at the end.  `kr_index` is 0-based (the reference's k_idx - 1).
+ * Series of SWRT_SERIES_TY: 0 ut, 1 vt, 2 ug, 3 vg, 4 uw, 5 vw; spectra 0..5 of those (Hann window, no detrend) and
+ * 6 U_balanced, 7 U_wave, 8 U_total.  Series of SWRT_SERIES_RSW: 0..2 u, v, eta; 3..5 balanced; 6..8 wave; 9..11 c0, c+, c-;
+ * spectra = clean_fft (detrend + Hann) of each.  Arrays are complex128 (nframes, nl) column-major. */
+typedef struct swrt_series swrt_series;
+enum { SWRT_SERIES_TY = 0, SWRT_SERIES_RSW = 1 };
+int swrt_series_create(swrt_flow* flow, int kind, int kr_index, long long max_frames, swrt_series** out);
+int swrt_series_destroy(swrt_series* s);
+int swrt_series_append(swrt_series* s);                       /* one frame from the flow's current state and clock */
+int swrt_series_frames(swrt_series* s, long long* nframes);
+int swrt_series_times(swrt_series* s, double* t_host);
+int swrt_series_get(swrt_series* s, int which, void* series_host);
+int swrt_series_spectrum(swrt_series* s, int which, void* spectrum_host);
+
 /* ---- slab-decomposed flow step (grids >= 4096^2; one process per GPU) ------------------------------------
  * Rank r owns retained kr columns [r*chunk, (r+1)*chunk) in spectral space and ny/P rows in physical space.  A step is
  *   slab_stage_a  (y-transforms of the local columns)      -> buffer A_SEND, laid out [dest][job][row][chunk]

@@ -91,6 +91,13 @@ SIGNATURES = {
     "swrt_packets_raytrace": (_I, [_P, _D, _D]),
     "swrt_packets_sample": (_I, [_P, _I, _P, _P]),
     "swrt_packets_kcutoff_reset": (_I, [_P, _D, _D, _PLL]),
+    "swrt_series_create": (_I, [_P, _I, _I, _LL, C.POINTER(_P)]),
+    "swrt_series_destroy": (_I, [_P]),
+    "swrt_series_append": (_I, [_P]),
+    "swrt_series_frames": (_I, [_P, _PLL]),
+    "swrt_series_times": (_I, [_P, _P]),
+    "swrt_series_get": (_I, [_P, _I, _P]),
+    "swrt_series_spectrum": (_I, [_P, _I, _P]),
     "swrt_packets_use_own_stream": (_I, [_P]),
     "swrt_packets_set_async": (_I, [_P, _P, _LL, _P]),
     "swrt_packets_get_async": (_I, [_P, _P, _LL]),

@@ -148,6 +148,14 @@ struct swrt_packets {
 };
 static inline cudaEvent_t packets_done_event(const swrt_packets* p) { return p->ev_done; }
 
+struct swrt_series {
+    swrt_flow* flow = nullptr;
+    int kind = 0, kr = 0, nser = 0;
+    long long maxf = 0;
+    double2 *buf = nullptr, *wts = nullptr;   // [series][l][maxf]; RSW: copy of the projection weights
+    std::vector<double> t;
+};
+
 // ------------------------------------------------------------------ small kernels (api TU only)
 // host (nkr, nl, nvar) column-major  <->  device [var][l][kr_pad], dealiased
 __global__ void pack_sol_kernel(const double2* __restrict__ host_layout, double2* __restrict__ sol, SpecLayout L, int nkr, int nvar) {
@@ -1351,6 +1359,102 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     if (nreset) *nreset = (long long)c;
     return SWRT_OK;
 }
+
+// ------------------------------------------------------------------ k-omega accumulator
+int swrt_series_create(swrt_flow* flow, int kind, int kr_index, long long max_frames, swrt_series** out) {
+    if (!flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
+    *out = nullptr;
+    if (kind != SWRT_SERIES_TY && kind != SWRT_SERIES_RSW) return fail(SWRT_ERR_ARG, "unknown series kind %d", kind);
+    const bool rsw = flow->d.model == SWRT_RSW || flow->d.model == SWRT_RSW_MODIFIED || flow->d.model == SWRT_RSW_LINDBORG;
+    if (kind == SWRT_SERIES_TY ? flow->d.model != SWRT_THOMASYAMADA : !rsw) return fail(SWRT_ERR_ARG, "series kind %d does not apply to model %d", kind, flow->d.model);
+    if (kr_index < 0 || kr_index >= flow->nkr || max_frames < 1) return fail(SWRT_ERR_ARG, "bad kr index / max_frames");
+    if (flow->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow");
+    CK(cudaSetDevice(flow->d.device));
+    swrt_series* s = new swrt_series;
+    s->flow = flow; s->kind = kind; s->kr = kr_index; s->maxf = max_frames;
+    s->nser = kind == SWRT_SERIES_TY ? 6 : 12;
+    cudaError_t e = cudaMalloc(&s->buf, sizeof(double2) * (size_t)s->nser * flow->d.ny * (size_t)max_frames);
+    if (e == cudaSuccess) e = cudaMalloc(&s->wts, sizeof(double2) * 3 * (size_t)flow->L.vs);
+    if (e != cudaSuccess) { swrt_series_destroy(s); return fail(SWRT_ERR_CUDA, "cudaMalloc(series): %s", cudaGetErrorString(e)); }
+    *out = s;
+    return SWRT_OK;
+}
+int swrt_series_destroy(swrt_series* s) {
+    if (!s) return SWRT_OK;
+    cudaSetDevice(s->flow->d.device);
+    cudaStreamSynchronize(s->flow->st);
+    cudaFree(s->buf); cudaFree(s->wts);
+    delete s;
+    return SWRT_OK;
+}
+int swrt_series_append(swrt_series* s) {
+    if (!s) return fail(SWRT_ERR_ARG, "null pointer");
+    swrt_flow* h = s->flow;
+    if ((long long)s->t.size() >= s->maxf) return fail(SWRT_ERR_STATE, "series is full (%lld frames)", s->maxf);
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    int rc;
+    if (s->kind == SWRT_SERIES_RSW) {   // weights first: decompose_kernel writes them to G, which the decomposition then reuses
+        if ((rc = decompose_launch(h, DEC_RSW_WTS))) return rc;
+        CK(cudaMemcpyAsync(s->wts, h->G, sizeof(double2) * 3 * (size_t)L.vs, cudaMemcpyDeviceToDevice, h->st));
+    }
+    if ((rc = decompose_launch(h, s->kind == SWRT_SERIES_TY ? DEC_TY : DEC_RSW))) return rc;
+    { ProfScope ps(h, K_OTHER);
+      series_append_kernel<<<(L.ny + 127) / 128, 128, 0, h->st>>>(h->sol, h->G, h->H, s->wts, L, s->kind, s->kr - L.kr_off, (long long)s->t.size(), s->maxf, s->buf); }
+    CK(cudaGetLastError());
+    s->t.push_back(h->t);
+    return SWRT_OK;
+}
+int swrt_series_frames(swrt_series* s, long long* n) {
+    if (!s || !n) return fail(SWRT_ERR_ARG, "null pointer");
+    *n = (long long)s->t.size();
+    return SWRT_OK;
+}
+int swrt_series_times(swrt_series* s, double* t_host) {
+    if (!s || !t_host) return fail(SWRT_ERR_ARG, "null pointer");
+    std::copy(s->t.begin(), s->t.end(), t_host);
+    return SWRT_OK;
+}
+// out(T, nl) <- rows of `which` (series) or its windowed transform (spectrum)
+static int series_fetch(swrt_series* s, int which, bool spectrum, void* host) {
+    if (!s || !host) return fail(SWRT_ERR_ARG, "null pointer");
+    swrt_flow* h = s->flow;
+    const long long T = (long long)s->t.size();
+    const int ny = h->d.ny, nspec = s->kind == SWRT_SERIES_TY ? 9 : 12;
+    if (T < 1) return fail(SWRT_ERR_STATE, "no frames recorded");
+    if (which < 0 || which >= (spectrum ? nspec : s->nser)) return fail(SWRT_ERR_ARG, "series / spectrum %d out of range", which);
+    CK(cudaSetDevice(h->d.device));
+    double2 *work = nullptr, *out = nullptr, *tw = nullptr;
+    double* tv = nullptr;
+    cudaError_t e = cudaMalloc(&work, sizeof(double2) * (size_t)ny * T);
+    if (e == cudaSuccess) e = cudaMalloc(&out, sizeof(double2) * (size_t)ny * T);
+    if (e == cudaSuccess) e = cudaMalloc(&tw, sizeof(double2) * (size_t)T);
+    if (e == cudaSuccess) e = cudaMalloc(&tv, sizeof(double) * (size_t)T);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tv, s->t.data(), sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, h->st);
+    if (e == cudaSuccess) {
+        SeriesSel sel{1, {which, 0, 0}, {-1, -1, -1}};
+        if (s->kind == SWRT_SERIES_TY && which >= 6) {   // TY_k_omega.jl:104-106
+            if (which == 6) sel = SeriesSel{2, {0, 2, 0}, {1, 3, -1}};        // (ut + ug) + i (vt + vg)
+            else if (which == 7) sel = SeriesSel{1, {4, 0, 0}, {5, -1, -1}};  // uw + i vw
+            else sel = SeriesSel{3, {4, 2, 0}, {5, 3, 1}};                    // (uw + ug + ut) + i (vw + vg + vt)
+        }
+        if (spectrum) {
+            { ProfScope ps(h, K_OTHER); twiddle_table_kernel<<<(unsigned)((T + 255) / 256), 256, 0, h->st>>>(tw, T); }
+            { ProfScope ps(h, K_OTHER); series_dft_kernel<<<ny, 256, 0, h->st>>>(s->buf, sel, ny, T, s->maxf, tv, tw, s->kind == SWRT_SERIES_RSW ? 1 : 0, work, out); }
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(host, out, sizeof(double2) * (size_t)ny * T, cudaMemcpyDeviceToHost, h->st);
+        } else {
+            e = cudaMemcpy2DAsync(host, sizeof(double2) * (size_t)T, s->buf + (size_t)which * ny * s->maxf, sizeof(double2) * (size_t)s->maxf,
+                                  sizeof(double2) * (size_t)T, (size_t)ny, cudaMemcpyDeviceToHost, h->st);
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(work); cudaFree(out); cudaFree(tw); cudaFree(tv);
+    CK(e);
+    return SWRT_OK;
+}
+int swrt_series_get(swrt_series* s, int which, void* series_host) { return series_fetch(s, which, false, series_host); }
+int swrt_series_spectrum(swrt_series* s, int which, void* spectrum_host) { return series_fetch(s, which, true, spectrum_host); }
 
 // ------------------------------------------------------------------ output roll-over arithmetic
 int swrt_seqout_init(swrt_seqout* s, long long max_writes) {

@@ -322,6 +322,111 @@ __global__ void __launch_bounds__(256) decompose_kernel(const double2* __restric
     }
 }
 
+// ---------------------------------------------------------------- k-omega accumulator
+// One frame of the spectral series at a single kr index, all l, appended to device-resident time series buf[series][l][frame]:
+//   SERIES_TY  (thomasyamada/TY_k_omega.jl:72-86): ut = -i l zeta_t, vt = i k zeta_t, (ug, vg), (uw, vw) of the Phi projections
+//   SERIES_RSW (rsw/fourier-analysis/mrsw/FourierRSW.jl:118-137): u, v, eta; balanced u, v, eta; wave u, v, eta; c0, c+, c-
+// A, B hold the projections written by decompose_kernel (A = balanced, B = wave; for SERIES_RSW C = weights).
+enum { SERIES_TY = 0, SERIES_RSW = 1 };
+__global__ void __launch_bounds__(128) series_append_kernel(const double2* __restrict__ sol, const double2* __restrict__ A,
+                                                            const double2* __restrict__ B, const double2* __restrict__ C, SpecLayout L,
+                                                            int kind, int kr, long long frame, long long maxf, double2* __restrict__ buf) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L.ny) return;
+    const int nser = kind == SERIES_TY ? 6 : 12;
+    const bool live = kr < L.kr_keep && l_retained(L, l);
+    const long long off = (long long)l * L.kr_pad + kr;
+    const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l);
+    for (int s = 0; s < nser; ++s) {
+        double2 v = make_double2(0.0, 0.0);
+        if (live) {
+            if (kind == SERIES_TY) {
+                if (s < 2) {
+                    const double2 z = sol[off];
+                    v = s == 0 ? make_double2(lw * z.y, -lw * z.x) : make_double2(-kw * z.y, kw * z.x);
+                } else v = (s < 4 ? A : B)[(s & 1) * L.vs + off];
+            } else {
+                const int j = s % 3;
+                v = (s < 3 ? sol : s < 6 ? A : s < 9 ? B : C)[j * L.vs + off];
+            }
+        }
+        buf[((long long)s * L.ny + l) * maxf + frame] = v;
+    }
+}
+// e^{-2 pi i j / T}, j = 0..T-1
+__global__ void twiddle_table_kernel(double2* __restrict__ tw, long long T) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j >= T) return;
+    double s, c;
+    sincospi(-2.0 * (double)j / (double)T, &s, &c);
+    tw[j] = make_double2(c, s);
+}
+// Windowed (periodic Hann), optionally detrended, transform in time of one series row per CTA:
+//   y = x - m t - b (detrend of FourierRSW.jl:33-36: slope from the demeaned data, intercept -m sum(t)/N), out[w] = sum_t hann[t] y[t] e^{-2 pi i w t / T}.
+// `combo` builds the input from up to three series pairs: x = sum_j a[j] + i sum_j b[j]  (U_balanced / U_wave / U_total of TY_k_omega.jl:104-106).
+struct SeriesSel { int n; int a[3]; int b[3]; };
+__global__ void __launch_bounds__(256) series_dft_kernel(const double2* __restrict__ buf, SeriesSel sel, int ny, long long T, long long maxf,
+                                                         const double* __restrict__ tv, const double2* __restrict__ tw, int detrend,
+                                                         double2* __restrict__ work, double2* __restrict__ out) {
+    const int l = blockIdx.x;
+    __shared__ double red[256][5];
+    double2* y = work + (long long)l * T;
+    // gather (and combine) the row
+    double sx = 0, sy = 0, st = 0, st2 = 0;
+    for (long long t = threadIdx.x; t < T; t += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        for (int j = 0; j < sel.n; ++j) {
+            const double2 a = buf[((long long)sel.a[j] * ny + l) * maxf + t];
+            v.x += a.x; v.y += a.y;
+            if (sel.b[j] >= 0) {
+                const double2 b = buf[((long long)sel.b[j] * ny + l) * maxf + t];
+                v.x -= b.y; v.y += b.x;
+            }
+        }
+        y[t] = v;
+        sx += v.x; sy += v.y; st += tv[t]; st2 += tv[t] * tv[t];
+    }
+    auto reduce = [&](double a0, double a1, double a2, double a3, double a4, double* r) {
+        red[threadIdx.x][0] = a0; red[threadIdx.x][1] = a1; red[threadIdx.x][2] = a2; red[threadIdx.x][3] = a3; red[threadIdx.x][4] = a4;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) for (int q = 0; q < 5; ++q) red[threadIdx.x][q] += red[threadIdx.x + s][q];
+            __syncthreads();
+        }
+        for (int q = 0; q < 5; ++q) r[q] = red[0][q];
+        __syncthreads();
+    };
+    double mx = 0, my = 0, bx = 0, by = 0;
+    if (detrend) {
+        double r[5];
+        reduce(sx, sy, st, st2, 0.0, r);
+        const double N = (double)T, meanx = r[0] / N, meany = r[1] / N, tsum = r[2], t2sum = r[3];
+        double tx = 0, ty = 0;
+        for (long long t = threadIdx.x; t < T; t += blockDim.x) { tx += tv[t] * (y[t].x - meanx); ty += tv[t] * (y[t].y - meany); }
+        reduce(tx, ty, 0.0, 0.0, 0.0, r);
+        const double den = N * t2sum - tsum * tsum;
+        mx = N * r[0] / den; my = N * r[1] / den;
+        bx = -mx * tsum / N; by = -my * tsum / N;
+    }
+    for (long long t = threadIdx.x; t < T; t += blockDim.x) {
+        const double w = 0.5 * (1.0 - cospi(2.0 * (double)t / (double)T));
+        y[t] = make_double2(w * (y[t].x - mx * tv[t] - bx), w * (y[t].y - my * tv[t] - by));
+    }
+    __syncthreads();
+    for (long long w = threadIdx.x; w < T; w += blockDim.x) {
+        double ax = 0, ay = 0;
+        long long idx = 0;   // (w t) mod T, advanced incrementally
+        for (long long t = 0; t < T; ++t) {
+            const double2 e = tw[idx], v = y[t];
+            ax = fma(v.x, e.x, fma(-v.y, e.y, ax));
+            ay = fma(v.x, e.y, fma(v.y, e.x, ay));
+            idx += w;
+            if (idx >= T) idx -= T;
+        }
+        out[(long long)l * T + w] = make_double2(ax, ay);
+    }
+}
+
 // ---------------------------------------------------------------- spectral diagnostics (parseval-weighted sums)
 // value(kr,l) per `which`, summed with weights 1 (kr = 0, Nyquist) / 2 (parsevalsum / parsevalsum2 of FourierFlows)
 enum { DIAG_ABS2_VAR = 0, DIAG_QG_K2PSI2 = 1, DIAG_QG_PSI2 = 2, DIAG_QG_DPSI2 = 3, DIAG_INVK2_ABS2_VAR = 4 };

@@ -311,3 +311,19 @@ def test_K10_K11_wave_balanced_projections():
         for B in (P0, Pp, Pm):
             ip = (A * np.conj(B)).sum(axis=-1)
             assert np.abs(ip - (1.0 if A is B else 0.0)).max() < 1e-13
+
+
+def test_komega_window_and_detrend_restatement():
+    """thomasyamada/TY_k_omega.jl:11-17 (periodic Hann) and mrsw/FourierRSW.jl:17-41 (detrend removes a linear trend's slope
+    exactly; the intercept it subtracts is -m sum(t)/N, as written)."""
+    from oracle import komega as okw
+    w = okw.hann(8)
+    assert w[0] == 0 and abs(w[4] - 1) < 1e-16 and np.allclose(w[1:], w[1:][::-1])
+    t = np.linspace(0.5, 9.5, 19)
+    data = (3.0 - 0.7j) * t[:, None] + np.ones((19, 2)) * (2.0 + 1.0j)
+    d = okw.detrend(t, data)
+    assert np.abs(d - d[0]).max() < 1e-12                       # the slope is gone, a constant is left
+    m, b = okw.linear_least_squares(t, okw.demean(data))
+    assert np.allclose(m, 3.0 - 0.7j) and np.allclose(b, -(3.0 - 0.7j) * t.sum() / 19)
+    spec = okw.clean_fft(t, data, okw.hann(19))
+    assert spec.shape == (19, 2)
