@@ -46,10 +46,13 @@ mutable struct Problem
     nx::Int; ny::Int; nkr::Int; dt::Float64; nvar::Int
     function Problem(; model = "RotatingShallowWater", stepper = "IFMAB3", nx = 128, ny = nx, Lx = 2π, Ly = Lx, ν = 1e-16, nν = 4,
                      f = 1.0, Cg = 1.0, dt = 5e-2, aliased_fraction = 1/3, use_filter = false, order = 4, dev = 0,
-                     U = 0.5, μ = 1e-2, f0 = f, δρρ0 = 0.2, Ro = 0.2)
+                     U = 0.5, μ = 1e-2, f0 = f, δρρ0 = 0.2, Ro = 0.2, H = [0.5, 0.5], b = [2.0, 1.0], β = 0.0)
+        # MultiLayerQG.Problem(2, dev; nx, Lx, f₀, H, b, U, μ, β, dt, stepper, aliased_fraction): two equal layers, U = [U₁, U₂]
+        F = model == "MultiLayerQG" ? f0^2 / ((b[1] - b[2]) * H[1]) : 2 * f0^2 / Cg^2 / δρρ0
+        U1, U2 = U isa Number ? (U, -U) : (U[1], U[2])
         d = FlowDesc(model = MODELS[model], stepper = STEPPERS[stepper], nx = nx, ny = ny, Lx = Lx, Ly = Ly, nu = ν, nnu = nν, f = f,
                      Cg = Cg, dt = dt, aliased_fraction = aliased_fraction, use_filter = use_filter, filter_order = order, device = dev,
-                     U = U, mu = μ, F = 2 * f0^2 / Cg^2 / δρρ0, Ro = Ro)
+                     U = U1, mu = μ, F = F, Ro = Ro, U2 = U2, beta = β)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_flow_create, libswrt), Cint, (Ref{FlowDesc}, Ref{Ptr{Cvoid}}), d, out))
         p = new(out[], nx, ny, nx ÷ 2 + 1, dt, NVAR[MODELS[model]])
@@ -109,6 +112,57 @@ end
 kinetic_energy(prob::Problem) = energies(prob).kinetic_energy
 potential_energy(prob::Problem) = energies(prob).potential_energy
 
+# --- wave / balanced projections on the device: rsw/RSWUtils.jl:5-57, thomasyamada/TYUtils.jl:40-51 ---------------
+"wave_balanced_decomposition(prob) / decompose_balanced_wave(sol, grid): (balanced, wave) as (nkr, nl, 3) arrays"
+function wave_balanced_decomposition(prob::Problem)
+    bal = Array{ComplexF64}(undef, prob.nkr, prob.ny, 3); wav = similar(bal)
+    check(ccall((:swrt_flow_wave_balanced_decomposition, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}), prob.h, bal, wav))
+    return bal, wav
+end
+"compute_balanced_wave_weights with compute_balanced_wave_bases: (c₀, c₊, c₋)"
+function compute_balanced_wave_weights(prob::Problem)
+    c = [Array{ComplexF64}(undef, prob.nkr, prob.ny) for _ in 1:3]
+    check(ccall((:swrt_flow_wave_balanced_weights, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}), prob.h, c[1], c[2], c[3]))
+    return Tuple(c)
+end
+"wave_geostrophic_energy(prob) (thomasyamada/ThomasYamada.jl:355-367): ((KE_w, PE_w), (KE_g, PE_g))"
+function wave_geostrophic_energy(prob::Problem)
+    out = zeros(Cdouble, 4)
+    check(ccall((:swrt_flow_wave_balanced_energies, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), prob.h, out))
+    return ((out[1], out[2]), (out[3], out[4]))
+end
+function barotropic_energy(prob::Problem)
+    e = Ref{Cdouble}(0)
+    check(ccall((:swrt_flow_barotropic_energy, libswrt), Cint, (Ptr{Cvoid}, Ref{Cdouble}), prob.h, e))
+    return e[]
+end
+
+# --- k-omega accumulator: thomasyamada/TY_k_omega.jl:46-110, rsw/fourier-analysis/mrsw/FourierRSW.jl:76-160 ------
+mutable struct KOmega
+    h::Ptr{Cvoid}
+    prob::Problem
+    "k_idx is 1-based like the reference's; kind 0 = Thomas-Yamada series, 1 = RSW series"
+    function KOmega(prob::Problem, k_idx::Integer, max_frames::Integer; kind = 0)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:swrt_series_create, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint, Clonglong, Ref{Ptr{Cvoid}}), prob.h, kind, k_idx - 1, max_frames, out))
+        s = new(out[], prob)
+        finalizer(q -> ccall((:swrt_series_destroy, libswrt), Cint, (Ptr{Cvoid},), q.h), s)
+        return s
+    end
+end
+append!(s::KOmega) = check(ccall((:swrt_series_append, libswrt), Cint, (Ptr{Cvoid},), s.h))
+function nframes(s::KOmega)
+    n = Ref{Clonglong}(0)
+    check(ccall((:swrt_series_frames, libswrt), Cint, (Ptr{Cvoid}, Ref{Clonglong}), s.h, n))
+    return Int(n[])
+end
+"fft(window .* series, 1) / clean_fft(t, series, window) of series `which` (0-based, see include/swrt.h): (nframes, nl)"
+function spectrum(s::KOmega, which::Integer)
+    out = Array{ComplexF64}(undef, nframes(s), s.prob.ny)
+    check(ccall((:swrt_series_spectrum, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}), s.h, which, out))
+    return out
+end
+
 # --- packets: raytracing/GPURaytracing.jl -----------------------------------------------------------------------
 "get_streamfunction! + get_velocity_info into snapshot slot (0 = old, 1 = new)"
 get_velocity_info!(prob::Problem, slot::Integer; psi_kind = 0) =
@@ -155,6 +209,15 @@ function interpolate_velocity_and_gradients(p::Packets, slot::Integer)
     check(ccall((:swrt_packets_sample, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}), p.h, slot, U, G))
     return U, G
 end
+# overlapped packet I/O: the handle's own stream, asynchronous copies of row blocks (ld = rows of the parent (N, ncol) array)
+use_own_stream!(p::Packets) = check(ccall((:swrt_packets_use_own_stream, libswrt), Cint, (Ptr{Cvoid},), p.h))
+set_packets_async!(p::Packets, xk::Ptr{Cdouble}, ld::Integer, ωsign::Ptr{Cdouble}) =
+    check(ccall((:swrt_packets_set_async, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong, Ptr{Cdouble}), p.h, xk, ld, ωsign))
+get_packets_async!(p::Packets, xk::Ptr{Cdouble}, ld::Integer) =
+    check(ccall((:swrt_packets_get_async, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong), p.h, xk, ld))
+sample_async!(p::Packets, slot::Integer, U::Ptr{Cdouble}, G::Ptr{Cdouble}, ld::Integer) =
+    check(ccall((:swrt_packets_sample_async, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Clonglong), p.h, slot, U, G, ld))
+sync!(p::Packets) = check(ccall((:swrt_packets_sync, libswrt), Cint, (Ptr{Cvoid},), p.h))
 function kcutoff_reset!(p::Packets, k_cutoff, k0)
     n = Ref{Clonglong}(0)
     check(ccall((:swrt_packets_kcutoff_reset, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Clonglong}), p.h, k_cutoff, k0, n))
