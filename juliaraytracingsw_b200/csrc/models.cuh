@@ -617,7 +617,9 @@ struct Launch {
     template <class K>
     static cudaError_t prep(K kernel, size_t smem, int threads, int* ctas) {
         static int cached = 0;  // one static per (N, K) instantiation
-        if (!cached) {
+        static size_t cached_smem = 0;
+        if (!cached || smem != cached_smem) {   // the staged y-passes size their buffer by the retained rows: re-derive when it changes
+            cached_smem = smem;
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -738,3 +738,23 @@ def test_komega_accumulator_parity():
     for j in range(12):
         assert rel_l2(kr.series(j), series[:, j]) < 1e-12, j
         assert rel_l2(kr.spectrum(j), okw.clean_fft(t, series[:, j], w)) < 1e-10, kr.names[j]
+
+
+def test_problems_with_different_dealiasing_in_one_process():
+    """The staged y-passes size their shared-memory buffer by the number of retained rows; two problems of one grid size but
+    different aliased fractions must both launch (regression: the opt-in size was cached from the first problem)."""
+    g3, sol3 = random_state(128, seed=4, amp=0.1)
+    pa = swrt.Problem(nx=128, f=3.0, dt=1e-3, aliased_fraction=1 / 3)
+    pa.sol = sol3
+    flow.stepforward(pa, (), 2)
+    raytracing.get_velocity_info(pa, 0)
+    pb = swrt.Problem(nx=128, f=3.0, dt=1e-3, aliased_fraction=0)
+    pb.sol = sol3
+    flow.stepforward(pb, (), 2)
+    raytracing.get_velocity_info(pb, 0)
+    pc = swrt.Problem(nx=128, f=3.0, dt=1e-3, aliased_fraction=1 / 2)
+    pc.sol = sol3
+    flow.stepforward(pc, (), 2)
+    raytracing.get_velocity_info(pc, 0)
+    flow.stepforward(pa, (), 1)
+    assert not (flow.has_nan(pa) or flow.has_nan(pb) or flow.has_nan(pc))
