@@ -39,6 +39,7 @@ def parse():
                          "over the ranks + 67M packets (BASELINE.json configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
     return ap.parse_args()
 
@@ -246,6 +247,34 @@ def run_swrt(args):
     flow.stepforward(prob, (), K)
     ms_flow = max_over_ranks(prob.timer_stop()) / K
 
+    # ---- optional fp32 packet mode (north star: "reported separately"): Float32 node data + fp32 right-hand side, fp64 state
+    fp32 = None
+    if not args.no_fp32:
+        raytracing.set_interpolation(prob, raytracing.INTERP_BILINEAR_F32)
+        p32 = raytracing.Packets(prob, nloc, P.f, P.packet_Cg, nsub=P.nsub, interp=raytracing.INTERP_BILINEAR_F32)
+        p32.set(packets.get(), np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0))
+        raytracing.get_velocity_info(prob, 0)
+        for _ in range(W):
+            t = drivers.coupled_step(prob, p32, t)
+        prob.sync(); barrier()
+        prob.timer_start()
+        for _ in range(K):
+            t = drivers.coupled_step(prob, p32, t)
+        ms32 = max_over_ranks(prob.timer_stop())
+        prob.profile(2)
+        for _ in range(K):
+            t = drivers.coupled_step(prob, p32, t)
+        prob.sync()
+        k32 = prob.profile_report()
+        prob.profile(0)
+        fp32 = {"value": ntot * K / (ms32 * 1e-3), "unit": "packet-steps/s", "ms_per_step": ms32 / K,
+                "raytrace_ms": k32["raytrace_rk4_kernel"]["ms_avg"],
+                "what": "same coupled step; the tracer samples Float32 node records with an fp32 right-hand side (packet state, "
+                        "cell coordinate and RK4 combination in fp64).  Not part of `value`."}
+        p32.close()
+        raytracing.set_interpolation(prob, raytracing.INTERP_BILINEAR)
+        raytracing.get_velocity_info(prob, 0)
+
     # ---- end to end: pinned host packets in, output frame out, every step, through the public API
     e2e = None
     if not args.no_e2e:
@@ -335,7 +364,7 @@ def run_swrt(args):
                    "nsub": args.nsub, "integrator": "RK4", "interp": "bilinear",
                    "packet_positions": "uniform random over the domain (fully mixed; the lattice start is value_lattice_t0)", "parallelism": f"packets sharded x{world}, flow replicated",
                    "l2": "inputs_exceed_l2 (2 x 168 MB snapshot fields, 0.67 GB packets/GPU at N=1, 0.47 GB spectral work set vs 126 MB L2)"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "spectral_step": spectral,
+        "clocks": clk, "e2e": e2e, "fp32_packet_mode": fp32, "gpu_launches": int(launches), "roofline": roofline, "spectral_step": spectral,
         "value_lattice_t0": ntot * K / (ms_lat * 1e-3),
         "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"]} for k, v in kern.items()},
     }

@@ -180,7 +180,10 @@ int swrt_flow_launch_count(swrt_flow* h, long long* n);
  * node data (utils/CUDAInterpolations.jl:71-108) with the analytic gradient of the interpolant in dk/dt */
 enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1,
        /* quadratic B-spline of the CPU tracer (raytracing/Raytracing.jl:161-170); coefficients are prefiltered in the snapshot */
-       SWRT_INTERP_BSPLINE2 = 2 };
+       SWRT_INTERP_BSPLINE2 = 2,
+       /* fp32 packet mode: bilinear sampling of Float32 node data with an fp32 right-hand side (the reference's texture path,
+          raytracing/GPURaytracing.jl:118-127); packet state and RK4 combination stay fp64.  Reported separately from the fp64 numbers. */
+       SWRT_INTERP_BILINEAR_F32 = 3 };
 /* classical RK4 (north star) or the CPU tracer's implicit midpoint (raytracing/Raytracing.jl:106-109), 12 fixed-point sweeps */
 enum { SWRT_INTEG_RK4 = 0, SWRT_INTEG_IMPLICIT_MIDPOINT = 1 };
 enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };

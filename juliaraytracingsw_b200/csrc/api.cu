@@ -985,15 +985,15 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     }
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, L, out_local(h->G), h->tw_y, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp == SWRT_INTERP_HERMITE_BICUBIC, L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp == SWRT_INTERP_HERMITE_BICUBIC ? 1 : (h->interp == SWRT_INTERP_BILINEAR_F32 ? 2 : 0), L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }
 
 int swrt_flow_set_interp(swrt_flow* h, int interp) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
-    if (interp != SWRT_INTERP_BILINEAR && interp != SWRT_INTERP_HERMITE_BICUBIC && interp != SWRT_INTERP_BSPLINE2)
-        return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_BILINEAR_F32) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    if (interp == SWRT_INTERP_BILINEAR_F32 && h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode is not built for a slab-decomposed flow");
     h->interp = interp;
     return SWRT_OK;
 }
@@ -1017,6 +1017,10 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
+    if (h->interp == SWRT_INTERP_BILINEAR_F32) {
+        ProfScope ps(h, K_OTHER);
+        snapf_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<const float*>(h->snap[h->slot_map[slot]]), n, tmp);
+    } else
     { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, nc, stride, tmp); }
     cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
@@ -1027,6 +1031,7 @@ int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
 
 int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
+    if (h->interp == SWRT_INTERP_BILINEAR_F32) return fail(SWRT_ERR_UNSUPPORTED, "snapshots of the fp32 packet mode are built by swrt_flow_velocity_snapshot only");
     CK(cudaSetDevice(h->d.device));
     const long long n = (long long)h->d.nx * h->d.ny;
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
@@ -1110,8 +1115,10 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
     if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
-    if (desc->interp != SWRT_INTERP_BILINEAR && desc->interp != SWRT_INTERP_HERMITE_BICUBIC && desc->interp != SWRT_INTERP_BSPLINE2)
+    if (desc->interp < SWRT_INTERP_BILINEAR || desc->interp > SWRT_INTERP_BILINEAR_F32)
         return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
+    if (desc->interp == SWRT_INTERP_BILINEAR_F32 && desc->integrator != SWRT_INTEG_RK4)
+        return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode integrates with RK4");
     if (desc->integrator != SWRT_INTEG_RK4 && desc->integrator != SWRT_INTEG_IMPLICIT_MIDPOINT)
         return fail(SWRT_ERR_UNSUPPORTED, "integrator %d not implemented", desc->integrator);
     if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
@@ -1298,7 +1305,15 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     const unsigned grid = (unsigned)((n + 127) / 128);
     { ProfScope ps(f, K_RAYTRACE, p->st);
 #define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
-      if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
+      if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
+          static const int fminb = [] { const char* e = getenv("SWRT_RAYTRACE_F32_MINB"); return e ? atoi(e) : 6; }();
+          const float4 *Fo = reinterpret_cast<const float4*>(So), *Fn = reinterpret_cast<const float4*>(Sn);
+          if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else if (fminb == 5) raytrace_rk4_f32_kernel<5><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else if (fminb == 6) raytrace_rk4_f32_kernel<6><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+      }
+      else if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
           if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else SWRT_GEN(2, 1);
       }
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
@@ -1323,7 +1338,10 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
     CK(wait_flow(p));
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
-    if (p->d.interp == SWRT_INTERP_BSPLINE2) {
+    if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
+        ProfScope ps(f, K_SAMPLE, p->st);
+        sample_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, reinterpret_cast<const float4*>(f->snap[f->slot_map[slot]]), packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    } else if (p->d.interp == SWRT_INTERP_BSPLINE2) {
         ProfScope ps(f, K_SAMPLE, p->st);
         sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {

@@ -107,6 +107,7 @@ template <>
 cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched,
                                          cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny);
+    if (cubic == 2) return xpass(SnapshotXOp<SWRT_N, false, true>{G_, out, s1}, L, tw, sched, st);   // fp32 node records
     if (cubic) return xpass(SnapshotCubicXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);
     return xpass(SnapshotXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);
 }

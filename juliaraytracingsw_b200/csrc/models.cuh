@@ -543,11 +543,11 @@ struct PsiLoader {
     }
 };
 
-template <int N, bool SLAB = false>
+template <int N, bool SLAB = false, bool F32 = false>
 struct SnapshotXOp {
     static constexpr int NBUF = 3;
     const double2* G;  // [3][ny][kr_pad]
-    double* out;       // [ny][nx][6] of the level being written
+    double* out;       // [ny][nx][6] of the level being written ([ny][nx][8] floats in the fp32 packet mode)
     double s1;
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
@@ -558,6 +558,16 @@ struct SnapshotXOp {
         cx.ifft(1);  // ux + i uy
         cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, RowPlain{});
         cx.ifft(2);  // vx
+        if (F32) {
+            float4* o = reinterpret_cast<float4*>(out) + (long long)y * N * 2;
+#pragma unroll
+            for (int i = 0; i < EPT; ++i) {
+                const int x = cx.g + i * Gt, p = pad_index(x);
+                o[2 * x] = make_float4((float)(s1 * cx.re(0)[p]), (float)(s1 * cx.im(0)[p]), (float)(s1 * cx.re(1)[p]), (float)(s1 * cx.im(1)[p]));
+                o[2 * x + 1] = make_float4((float)(s1 * cx.re(2)[p]), 0.f, 0.f, 0.f);
+            }
+            return;
+        }
         double* o = out + (long long)y * N * SNAP_STRIDE;
 #pragma unroll
         for (int i = 0; i < EPT; ++i) {

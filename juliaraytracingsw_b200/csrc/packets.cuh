@@ -478,6 +478,129 @@ __global__ void __launch_bounds__(128) sample_generic_kernel(const double* __res
     }
 }
 
+// ---------------------------------------------------------------- fp32 packet mode (north star: "optional fp32 packet mode")
+// The reference's GPU tracer samples Float32 textures (raytracing/GPURaytracing.jl:118-127).  Here the node records are
+// eight floats, the stencil (40 floats) and the whole right-hand side are evaluated in fp32, and the packet state, the cell
+// coordinate and the RK4 combination stay in fp64, so positions do not lose increments to fp32 rounding.
+struct StencilF {
+    float4 c[2][4][2];
+    int ci, cj;
+};
+__device__ __forceinline__ void ray_rhs_f32(const double (&s)[4], float sign, float alpha, const float4* __restrict__ So,
+                                            const float4* __restrict__ Sn, const PacketGrid& g, float f2, float cg2, int lerp,
+                                            StencilF& st, double (&d)[4]) {
+    int i0, i1, j0, j1;
+    double ad, bd;
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, ad);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, bd);
+    if (i0 != st.ci || j0 != st.cj) {
+        st.ci = i0;
+        st.cj = j0;
+        const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+#pragma unroll
+        for (int lev = 0; lev < 2; ++lev) {
+            const float4* S = lev == 0 ? So : Sn;
+#pragma unroll
+            for (int cr = 0; cr < 4; ++cr) {
+                st.c[lev][cr][0] = __ldg(S + 2 * pt[cr]);
+                st.c[lev][cr][1] = __ldg(S + 2 * pt[cr] + 1);
+            }
+        }
+    }
+    const float a = (float)ad, b = (float)bd, a1 = 1.f - a, b1 = 1.f - b;
+    const float wo = lerp == 0 ? 1.f - alpha : alpha, wn = lerp == 0 ? alpha : 1.f - alpha;
+    const float wb[4] = {a1 * b1, a * b1, a1 * b, a * b};
+    float W[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int lev = 0; lev < 2; ++lev) {
+        const float wl = lev == 0 ? wo : wn;
+        if (wl == 0.f) continue;
+#pragma unroll
+        for (int cr = 0; cr < 4; ++cr) {
+            const float w = wl * wb[cr];
+            const float4 q0 = st.c[lev][cr][0];
+            W[0] = fmaf(w, q0.x, W[0]); W[1] = fmaf(w, q0.y, W[1]); W[2] = fmaf(w, q0.z, W[2]); W[3] = fmaf(w, q0.w, W[3]);
+            W[4] = fmaf(w, st.c[lev][cr][1].x, W[4]);
+        }
+    }
+    const float k = (float)s[2], l = (float)s[3];
+    const float cg = cg2 * sign * rsqrtf(fmaf(cg2, fmaf(k, k, l * l), f2));
+    d[0] = (double)fmaf(cg, k, W[0]);
+    d[1] = (double)fmaf(cg, l, W[1]);
+    d[2] = (double)(-(W[2] * k + W[4] * l));
+    d[3] = (double)(-(W[3] * k - W[2] * l));
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) raytrace_rk4_f32_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n,
+                                                                  const float4* __restrict__ So, const float4* __restrict__ Sn, PacketGrid g,
+                                                                  RayParams p) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    const float sg = (float)sign[i], f2 = (float)(p.f * p.f), cg2 = (float)(p.Cg * p.Cg);
+    const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
+    StencilF st;
+    st.ci = -1;
+    st.cj = -1;
+    for (int it = 0; it < p.nsub; ++it) {
+        const double t = p.t0 + it * h;
+        double k[4], acc[4], y[4];
+        ray_rhs_f32(s, sg, (float)((t - p.t0) * inv_span), So, Sn, g, f2, cg2, p.lerp, st, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        ray_rhs_f32(y, sg, (float)((t + 0.5 * h - p.t0) * inv_span), So, Sn, g, f2, cg2, p.lerp, st, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        ray_rhs_f32(y, sg, (float)((t + 0.5 * h - p.t0) * inv_span), So, Sn, g, f2, cg2, p.lerp, st, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+        const float a4 = it == p.nsub - 1 ? 1.f : (float)((t + h - p.t0) * inv_span);
+        ray_rhs_f32(y, sg, a4, So, Sn, g, f2, cg2, p.lerp, st, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+    }
+    xk[i] = s[0];
+    xk[n + i] = s[1];
+    xk[2 * n + i] = s[2];
+    xk[3 * n + i] = s[3];
+}
+__global__ void __launch_bounds__(128) sample_f32_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
+                                                         const float4* __restrict__ S, PacketGrid g, double* __restrict__ U,
+                                                         double* __restrict__ Gd) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int i0, i1, j0, j1;
+    double ad, bd;
+    cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, ad);
+    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, bd);
+    const float a = (float)ad, b = (float)bd;
+    const float wb[4] = {(1.f - a) * (1.f - b), a * (1.f - b), (1.f - a) * b, a * b};
+    const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+    float W[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int cr = 0; cr < 4; ++cr) {
+        const float4 q0 = __ldg(S + 2 * pt[cr]), q1 = __ldg(S + 2 * pt[cr] + 1);
+        W[0] = fmaf(wb[cr], q0.x, W[0]); W[1] = fmaf(wb[cr], q0.y, W[1]); W[2] = fmaf(wb[cr], q0.z, W[2]); W[3] = fmaf(wb[cr], q0.w, W[3]);
+        W[4] = fmaf(wb[cr], q1.x, W[4]);
+    }
+    const long long o = idx[i];
+    U[o] = W[0];
+    U[n + o] = W[1];
+    if (Gd) {
+        Gd[o] = W[2];
+        Gd[n + o] = W[3];
+        Gd[2 * n + o] = W[4];
+        Gd[3 * n + o] = -W[2];
+    }
+}
+// fp32 node records -> planar (nx, ny, 5) doubles for swrt_flow_get_snapshot
+__global__ void snapf_to_planar_kernel(const float* __restrict__ S, long long npts, double* __restrict__ out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) out[c * npts + i] = (double)S[i * SNAPF_STRIDE + c];
+}
+
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                      const double* __restrict__ S, PacketGrid g, double* __restrict__ U,

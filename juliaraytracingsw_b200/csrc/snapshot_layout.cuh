@@ -9,4 +9,6 @@ constexpr int SNAP_STRIDE = 6;  // doubles per grid point of one level
 // Hermite-bicubic mode (utils/CUDAInterpolations.jl:71-108): node data (u, v, ux, uy, vx, uxy, vxy, pad), 64 B per point
 constexpr int SNAP3_NC = 7;
 constexpr int SNAP3_STRIDE = 8;
+// fp32 packet mode: node data (u, v, ux, uy | vx, 0, 0, 0) as eight floats, 32 B = two 16-byte vectors = one sector per point
+constexpr int SNAPF_STRIDE = 8;   // floats per grid point of one level
 }  // namespace swrt

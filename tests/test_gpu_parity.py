@@ -758,3 +758,38 @@ def test_problems_with_different_dealiasing_in_one_process():
     raytracing.get_velocity_info(pc, 0)
     flow.stepforward(pa, (), 1)
     assert not (flow.has_nan(pa) or flow.has_nan(pb) or flow.has_nan(pc))
+
+
+def test_fp32_packet_mode():
+    """North star's optional fp32 packet mode: Float32 node data and right-hand side, fp64 state.  Tolerance 2e-6 relative
+    against the fp64 oracle fed the same Float32-rounded fields (fp32 arithmetic: ~1e-7 per evaluation)."""
+    g, p, sol0, c = config2_setup(128)
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 3)
+    prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_interpolation(prob, raytracing.INTERP_BILINEAR_F32)
+    prob.sol = sol0
+    vel, _ = raytracing.get_velocity_info(prob, 0)
+    flow.stepforward(prob, (), 3)
+    raytracing.get_velocity_info(prob, 1)
+    Fo = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g).astype(np.float32)
+    Fn = oray.get_velocity_info(orsw.get_streamfunction(sol1, g, p), g).astype(np.float32)
+    got_F = vel._arr()
+    assert np.abs(got_F - Fo).max() <= 2.0 ** -23 * np.abs(Fo).max()          # the snapshot holds the fields rounded to fp32
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 32)
+    xk[:, 0:2] += np.random.default_rng(7).uniform(-20, 20, size=(xk.shape[0], 2))
+    pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=2, interp=raytracing.INTERP_BILINEAR_F32)
+    pk.set(xk, sign)
+    t1 = 3 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (0.0, t1))
+    want = oray.raytrace(xk.copy(), sign, 0.0, t1, Fo.astype(np.float64), Fn.astype(np.float64), g, c["f"], c["Cg"], nsub=2)
+    got = pk.get()
+    d = got - want
+    d[:, 0:2] = (d[:, 0:2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(d).max() / np.abs(want).max() < 2e-6
+    U = raytracing.interpolate_velocity(raytracing.Velocity(prob, 1), pk)
+    Uo, _ = oray.interpolate_velocity(Fn.astype(np.float64), got[:, 0:2], g)
+    assert np.abs(U - Uo).max() < 1e-6 * np.abs(Uo).max()
+    # mixing modes is refused
+    pk64 = raytracing.Packets(prob, 16, c["f"], c["Cg"])
+    with pytest.raises(swrt._lib.SwrtError):
+        raytracing.raytrace(pk64, None, None, None, None, prob.grid, pk64, c["dt"], (0.0, t1))
