@@ -344,7 +344,11 @@ def run_swrt(args):
                  "gather_achieved_gbs": 1280.0 * nloc * args.nsub / (rec["ms_avg"] * 1e-3) / 1e9,
                  "gather_note": "SURVEY 8d figure (4 stages x 2 levels x 5 fields x 4 taps x 8 B); on-chip after sort + stencil cache",
                  # ncu --set full, profiles/r01_d_ncu_raytrace_cached_16M.csv: dram read 1.007 GB + write 0.504 GB per launch
-                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, 16,777,216 packets on one GPU"}
+                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, 16,777,216 packets on one GPU",
+                 # what actually binds the kernel (one ncu --set full capture, not measured in this run):
+                 "binding_unit": {"name": "l1tex__data_pipe_lsu_wavefronts", "pct_of_peak": 69.3, "fp64_pipe_pct": 40.1,
+                                  "issue_active_pct": 41.2, "warps_per_sm": 16,
+                                  "source": "profiles/r01_i_ncu_full_raytrace_cached_details.csv, profiles/r01_i_ray_kernel_experiments.md"}}
         traffic = 1.511e9 * (nloc / 16777216.0) if args.nx == 2048 else None
     else:
         flow_bytes = {"ypass_inv_kernel<RswLoaderA>": 8 * F, "xpass_kernel<RswXOp>": 9 * F, "ypass_fwd_kernel<RswCombiner>": 7 * F,
