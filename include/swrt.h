@@ -183,7 +183,9 @@ enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1,
        SWRT_INTERP_BSPLINE2 = 2,
        /* fp32 packet mode: bilinear sampling of Float32 node data with an fp32 right-hand side (the reference's texture path,
           raytracing/GPURaytracing.jl:118-127); packet state and RK4 combination stay fp64.  Reported separately from the fp64 numbers. */
-       SWRT_INTERP_BILINEAR_F32 = 3 };
+       SWRT_INTERP_BILINEAR_F32 = 3,
+       /* cubic B-spline of the CPU tracer's steady-flow mode (raytracing/Raytracing.jl:152-159); prefiltered like BSPLINE2 */
+       SWRT_INTERP_BSPLINE3 = 4 };
 /* classical RK4 (north star) or the CPU tracer's implicit midpoint (raytracing/Raytracing.jl:106-109), 12 fixed-point sweeps */
 enum { SWRT_INTEG_RK4 = 0, SWRT_INTEG_IMPLICIT_MIDPOINT = 1 };
 enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };

@@ -30,7 +30,7 @@ end
 
 Base.@kwdef struct PacketsDesc
     n::Clonglong
-    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic, 2 quadratic B-spline
+    interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic, 2 quadratic B-spline, 3 bilinear fp32, 4 cubic B-spline
     integrator::Cint = 0                                                           # 0 RK4, 1 implicit midpoint
     f::Cdouble = 1.0; Cg::Cdouble = 1.0
 end

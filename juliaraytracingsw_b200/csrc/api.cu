@@ -945,8 +945,9 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     int rc = check_psi_kind(h, psi_kind);
     if (rc) return rc;
     CK(cudaSetDevice(h->d.device));
-    const bool pf = h->interp == SWRT_INTERP_BSPLINE2;
+    const bool pf = h->interp == SWRT_INTERP_BSPLINE2 || h->interp == SWRT_INTERP_BSPLINE3;
     PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
+    if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
     CK(e);
@@ -970,8 +971,9 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     { int rc = check_psi_kind(h, psi_kind); if (rc) return rc; }
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
-    const bool pf = h->interp == SWRT_INTERP_BSPLINE2;
+    const bool pf = h->interp == SWRT_INTERP_BSPLINE2 || h->interp == SWRT_INTERP_BSPLINE3;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
+    if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
     CK(wait_readers(h));
     cudaError_t e;
     bool materialise = false;
@@ -992,7 +994,7 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
 
 int swrt_flow_set_interp(swrt_flow* h, int interp) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
-    if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_BILINEAR_F32) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_BSPLINE3) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
     if (interp == SWRT_INTERP_BILINEAR_F32 && h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode is not built for a slab-decomposed flow");
     h->interp = interp;
     return SWRT_OK;
@@ -1115,7 +1117,7 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
     if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
-    if (desc->interp < SWRT_INTERP_BILINEAR || desc->interp > SWRT_INTERP_BILINEAR_F32)
+    if (desc->interp < SWRT_INTERP_BILINEAR || desc->interp > SWRT_INTERP_BSPLINE3)
         return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
     if (desc->interp == SWRT_INTERP_BILINEAR_F32 && desc->integrator != SWRT_INTEG_RK4)
         return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode integrates with RK4");
@@ -1314,9 +1316,10 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
           else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
       }
       else if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
-          if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else SWRT_GEN(2, 1);
+          if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else if (p->d.interp == 2) SWRT_GEN(2, 1); else SWRT_GEN(4, 1);
       }
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
+      else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
       else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
@@ -1341,6 +1344,9 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
         ProfScope ps(f, K_SAMPLE, p->st);
         sample_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, reinterpret_cast<const float4*>(f->snap[f->slot_map[slot]]), packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+    } else if (p->d.interp == SWRT_INTERP_BSPLINE3) {
+        ProfScope ps(f, K_SAMPLE, p->st);
+        sample_generic_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_BSPLINE2) {
         ProfScope ps(f, K_SAMPLE, p->st);
         sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);

@@ -512,12 +512,13 @@ struct PsiLoader {
     long long vs;
     int kind;
     double f, P;   // P: Kd2 = f^2/Cg^2 (RSW balanced, SWQG) or F (two-layer)
-    double pdx, pdy;   // > 0: quadratic B-spline prefilter (Interpolations.jl, raytracing/Raytracing.jl:161-170) folded into psi:
-                       // every sampled field is linear in psih, and the prefilter is 1/((3/4 + cos(k dx)/4)(3/4 + cos(l dy)/4))
+    double pdx, pdy;   // > 0: B-spline prefilter (Interpolations.jl, raytracing/Raytracing.jl:152-170) folded into psi: every
+                       // sampled field is linear in psih, and the prefilter is 1/((pc0 + pc1 cos(k dx))(pc0 + pc1 cos(l dy)))
+    double pc0 = 0.75, pc1 = 0.25;   // quadratic 3/4, 1/4; cubic 2/3, 1/3
     __device__ __forceinline__ double2 psi_of(double kw, double lw, long long off) const {
         double2 r = psi_raw(kw, lw, off);
         if (pdx > 0.0) {
-            const double pf = 1.0 / ((0.75 + 0.25 * cos(kw * pdx)) * (0.75 + 0.25 * cos(lw * pdy)));
+            const double pf = 1.0 / ((pc0 + pc1 * cos(kw * pdx)) * (pc0 + pc1 * cos(lw * pdy)));
             r.x *= pf;
             r.y *= pf;
         }

@@ -384,9 +384,37 @@ __device__ __forceinline__ void sample_bspline2_5(const double* __restrict__ S, 
         }
     }
 }
+// cubic B-spline (raytracing/Raytracing.jl:152-159): nodes floor(s)-1 .. floor(s)+2
+__device__ __forceinline__ void sample_bspline3_5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
+    const double sx = (x - g.x0) * g.inv_dx, sy = (y - g.y0) * g.inv_dy;
+    const double fx = floor(sx), fy = floor(sy);
+    const double dx = sx - fx, dy = sy - fy;
+    const int ic = (int)((long long)fx & (long long)(g.nx - 1)), jc = (int)((long long)fy & (long long)(g.ny - 1));
+    const double s6 = 1.0 / 6.0;
+    const double wx[4] = {(1 - dx) * (1 - dx) * (1 - dx) * s6, (3 * dx * dx * dx - 6 * dx * dx + 4) * s6,
+                          (-3 * dx * dx * dx + 3 * dx * dx + 3 * dx + 1) * s6, dx * dx * dx * s6};
+    const double wy[4] = {(1 - dy) * (1 - dy) * (1 - dy) * s6, (3 * dy * dy * dy - 6 * dy * dy + 4) * s6,
+                          (-3 * dy * dy * dy + 3 * dy * dy + 3 * dy + 1) * s6, dy * dy * dy * s6};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) out[c] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int j = (jc + b - 1) & (g.ny - 1);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = (ic + a - 1) & (g.nx - 1);
+            const double2* q = reinterpret_cast<const double2*>(S + ((long long)j * g.nx + i) * SNAP_STRIDE);
+            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            const double w = wx[a] * wy[b];
+            out[0] += w * q0.x; out[1] += w * q0.y; out[2] += w * q1.x; out[3] += w * q1.y; out[4] += w * q2.x;
+        }
+    }
+}
 template <int INTERP>
 __device__ __forceinline__ void sample_level5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
-    if (INTERP == 2) {
+    if (INTERP == 4) {
+        sample_bspline3_5(S, g, x, y, out);
+    } else if (INTERP == 2) {
         sample_bspline2_5(S, g, x, y, out);
     } else {
         int i0, i1, j0, j1;

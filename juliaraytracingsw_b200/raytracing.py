@@ -15,7 +15,7 @@ from ._lib import PacketsDesc, check, lib
 
 PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2, 3
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
-INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32 = 0, 1, 2, 3
+INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32, INTERP_BSPLINE3 = 0, 1, 2, 3, 4
 INTEG_RK4, INTEG_IMPLICIT_MIDPOINT = 0, 1
 
 

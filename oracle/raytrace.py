@@ -231,6 +231,35 @@ def sample_bspline2(C, x, y, grid):
     return out
 
 
+def bspline3_prefilter(fields, grid):
+    """Cubic B-spline coefficients, c_{i-1}/6 + 2 c_i/3 + c_{i+1}/6 = f_i (periodic) in x and y: the steady-flow interpolant
+    `BSpline(Cubic(Periodic(OnCell())))` of raytracing/Raytracing.jl:152-159 -- PARITY UNPINNED."""
+    px = 2 / 3 + np.cos(grid.kr * grid.dx) / 3
+    py = 2 / 3 + np.cos(grid.l * grid.dy) / 3
+    out = np.empty_like(fields)
+    for c in range(fields.shape[-1]):
+        out[:, :, c] = grid.irfft2(grid.rfft2(fields[:, :, c]) / (px * py))
+    return out
+
+
+def sample_bspline3(C, x, y, grid):
+    """Cubic B-spline with coefficients C (nx, ny, F): weights (1-d)^3/6, (3d^3-6d^2+4)/6, (-3d^3+3d^2+3d+1)/6, d^3/6 on nodes
+    floor(s)-1 .. floor(s)+2, d = s - floor(s)."""
+    def axis(pos, p0, dp, n):
+        s = (pos - p0) / dp
+        fl = np.floor(s)
+        d = s - fl
+        w = np.stack([(1 - d) ** 3 / 6, (3 * d ** 3 - 6 * d ** 2 + 4) / 6, (-3 * d ** 3 + 3 * d ** 2 + 3 * d + 1) / 6, d ** 3 / 6], axis=0)
+        return np.mod(fl, n).astype(np.int64), w
+    i, wx = axis(x, grid.x[0], grid.dx, grid.nx)
+    j, wy = axis(y, grid.y[0], grid.dy, grid.ny)
+    out = np.zeros((x.shape[0], C.shape[-1]))
+    for a in range(4):
+        for b in range(4):
+            out += (wx[a] * wy[b])[:, None] * C[(i + a - 1) % grid.nx, (j + b - 1) % grid.ny]
+    return out
+
+
 def rhs_sampler(xk, sign, alpha, S_old, S_new, f, Cg, lerp=LERP_PHYSICAL):
     """Ray RHS from already sampled (N, 5) fields of the two time levels."""
     k, l = xk[:, 2], xk[:, 3]

@@ -486,7 +486,7 @@ def test_quadheight_variant_and_physical_forward_transform():
 
 
 # ------------------------------------------------------------------------------------------------ CPU-tracer semantics
-@pytest.mark.parametrize("interp,integ", [(2, 0), (2, 1), (0, 1), (1, 1)])
+@pytest.mark.parametrize("interp,integ", [(2, 0), (2, 1), (0, 1), (1, 1), (4, 0), (4, 1)])
 def test_bspline_and_implicit_midpoint_modes(interp, integ):
     """Quadratic B-spline sampling and the implicit-midpoint integrator of raytracing/Raytracing.jl (a18), against the oracle."""
     g, p, sol0, c = config2_setup(128)
@@ -503,6 +503,9 @@ def test_bspline_and_implicit_midpoint_modes(interp, integ):
     elif interp == 2:
         Fo, Fn = (oray.bspline2_prefilter(oray.get_velocity_info(q, g), g) for q in (psi0, psi1))
         sampler = oray.sample_bspline2
+    elif interp == 4:
+        Fo, Fn = (oray.bspline3_prefilter(oray.get_velocity_info(q, g), g) for q in (psi0, psi1))
+        sampler = oray.sample_bspline3
     else:
         Fo, Fn, sampler = oray.get_velocity_info(psi0, g), oray.get_velocity_info(psi1, g), oray.sample_bilinear
     assert rel_l2(vel._arr(), Fo) < 1e-12                         # the snapshot holds spline coefficients in mode 2

@@ -262,6 +262,9 @@ def test_bspline2_prefilter_and_node_reproduction():
     rng = np.random.default_rng(0)
     px, py = rng.uniform(-10, 10, 500), rng.uniform(-10, 10, 500)        # periodic wrap outside the box
     exact = np.stack([np.sin(px) * np.cos(2 * py), np.cos(3 * px + py)], axis=-1)
+    C3 = oray.bspline3_prefilter(f, g)
+    assert np.abs(oray.sample_bspline3(C3, xs, ys, g) - f.reshape(-1, 2)).max() < 1e-13       # the cubic reproduces the nodes too
+    assert np.abs(oray.sample_bspline3(C3, px, py, g) - exact).max() < np.abs(oray.sample_bspline2(C, px, py, g) - exact).max()
     e_spline = np.abs(oray.sample_bspline2(C, px, py, g) - exact).max()
     e_lin = np.abs(oray.sample_bilinear(f, px, py, g) - exact).max()
     assert e_spline < 0.1 * e_lin
