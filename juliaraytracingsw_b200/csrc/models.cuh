@@ -546,26 +546,30 @@ struct PsiLoader {
 
 template <int N, bool SLAB = false, bool F32 = false>
 struct SnapshotXOp {
-    static constexpr int NBUF = 3;
+    static constexpr int NBUF = 2;
     const double2* G;  // [3][ny][kr_pad]
     double* out;       // [ny][nx][6] of the level being written ([ny][nx][8] floats in the fp32 packet mode)
     double s1;
+    // vx stays in the registers of the thread that stores it (x = g + m N/16); (u, v) and (ux, uy) wait in the two shared
+    // buffers, so that the three 16-byte pieces of a record are stored back to back (whole sectors reach L2 together)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
+        static_assert(EPT == 16, "one register per owned point");
         const auto Gp = row_ref<SLAB>(L, G, 3, 0, y), Gu = row_ref<SLAB>(L, G, 3, 1, y), Guy = row_ref<SLAB>(L, G, 3, 2, y);
+        double2 vx[16];
+        cx.template load_pair<MUL_MK2, MUL_ZERO>(1, Gp, RowPlain{});
+        cx.ifft_regs_out(1, vx);  // vx
         cx.template load_pair<MUL_ONE, MUL_IK>(0, Gu, Gp);
         cx.ifft(0);  // u + i v
         cx.template load_pair<MUL_IK, MUL_ONE>(1, Gu, Guy);
         cx.ifft(1);  // ux + i uy
-        cx.template load_pair<MUL_MK2, MUL_ZERO>(2, Gp, RowPlain{});
-        cx.ifft(2);  // vx
         if (F32) {
             float4* o = reinterpret_cast<float4*>(out) + (long long)y * N * 2;
 #pragma unroll
             for (int i = 0; i < EPT; ++i) {
                 const int x = cx.g + i * Gt, p = pad_index(x);
                 o[2 * x] = make_float4((float)(s1 * cx.re(0)[p]), (float)(s1 * cx.im(0)[p]), (float)(s1 * cx.re(1)[p]), (float)(s1 * cx.im(1)[p]));
-                o[2 * x + 1] = make_float4((float)(s1 * cx.re(2)[p]), 0.f, 0.f, 0.f);
+                o[2 * x + 1] = make_float4((float)(s1 * vx[i].x), 0.f, 0.f, 0.f);
             }
             return;
         }
@@ -576,7 +580,7 @@ struct SnapshotXOp {
             double2* q = reinterpret_cast<double2*>(o + (long long)x * SNAP_STRIDE);   // 48-byte record, three 16-byte stores
             q[0] = make_double2(s1 * cx.re(0)[p], s1 * cx.im(0)[p]);
             q[1] = make_double2(s1 * cx.re(1)[p], s1 * cx.im(1)[p]);
-            q[2] = make_double2(s1 * cx.re(2)[p], 0.0);
+            q[2] = make_double2(s1 * vx[i].x, 0.0);
         }
     }
 };
