@@ -284,7 +284,7 @@ def run_swrt(args):
         packets.get(out=h_xk)
         h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
         Ke = max(3, min(K, 10))
-        nchunks = max(1, min(args.e2e_chunks, nloc // 65536))
+        nchunks = max(2, min(args.e2e_chunks, nloc // 1048576))   # ~1M packets or more per chunk: below that the per-chunk launches dominate
         pipe = raytracing.PacketPipeline(prob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
 
         def e2e_step(t, frame, first=False):
