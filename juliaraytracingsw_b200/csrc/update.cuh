@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(256) ifmab3_update_rsw_kernel(UpdateArgs a, Rs
         const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
         const long long off = (long long)l * L.kr_pad + kr;
         const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l);
-        const double4 cf = a.coef[off];
+        // streaming loads for what this step never touches again (history, coefficients): the state written below should be the
+        // thing that stays in L2 for the next step's first pass
+        const double2 cf01 = __ldcs(reinterpret_cast<const double2*>(a.coef + off)), cf23 = __ldcs(reinterpret_cast<const double2*>(a.coef + off) + 1);
+        const double4 cf = make_double4(cf01.x, cf01.y, cf23.x, cf23.y);
         const double eD = cf.x, s = cf.y, c = cf.z;
         double2 x[3], n[3];
 #pragma unroll
@@ -63,8 +66,8 @@ __global__ void __launch_bounds__(256) ifmab3_update_rsw_kernel(UpdateArgs a, Rs
             double2 n1[3], n2[3], A[3], B[3];
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
-                n1[v] = a.Nm1[v * L.vs + off];
-                n2[v] = a.Nm2[v * L.vs + off];
+                n1[v] = __ldcs(a.Nm1 + v * L.vs + off);
+                n2[v] = __ldcs(a.Nm2 + v * L.vs + off);
             }
             lin.expmul(n1, kw, lw, eD, s, c, A);
             const double w2 = lin.f * lin.f + lin.w2c * (kw * kw + lw * lw);
