@@ -199,8 +199,9 @@ __device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk
                                                          const PacketGrid& g, const RayParams& p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
-    const double sg = sign[i];
+    // the packet state is read and written exactly once per launch: streaming accesses leave L2 to the node records
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};
+    const double sg = __ldcs(sign + i);
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     Stencil st;
     st.ci = -1;
@@ -223,10 +224,10 @@ __device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
-    xk[i] = s[0];
-    xk[n + i] = s[1];
-    xk[2 * n + i] = s[2];
-    xk[3 * n + i] = s[3];
+    __stcs(xk + i, s[0]);
+    __stcs(xk + n + i, s[1]);
+    __stcs(xk + 2 * n + i, s[2]);
+    __stcs(xk + 3 * n + i, s[3]);
 }
 
 template <int MINB>

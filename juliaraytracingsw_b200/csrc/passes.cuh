@@ -192,6 +192,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
+// Same copy for data that is dead once read (the x-transformed products): evict-first in L2, so the lines it frees go to
+// the arrays the step still needs instead of to these.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gsrc, unsigned long long policy) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(policy));
+}
 __host__ __device__ constexpr long long ypass_stage_smem(int N, int TK) { return (long long)N * TK * 16; }  // upper bound (all rows)
 
 template <int N, int TK>
@@ -317,12 +328,13 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     double2* stg = reinterpret_cast<double2*>(smem + 2 * TK * NP);   // [row < rows_s][TK]
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     const int nwork = ntiles * nvars;
+    const unsigned long long pol = l2_evict_first_policy();
     auto prefetch = [&](int w, int i_in) {
         const int var = cb.var_of(w / ntiles), kr0 = (w % ntiles) * TK;
         const int srcj = cb.src(var, i_in);
         for (int ch = tid; ch < rows_s * TK; ch += NT) {
             const int r = ch / TK, cc = ch - r * TK;
-            cp_async16(&stg[ch], &H[inter_off(L, nh, srcj, r) + kr0 + cc]);
+            cp_async16_stream(&stg[ch], &H[inter_off(L, nh, srcj, r) + kr0 + cc], pol);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
         for (int m = 0; m < 16; ++m) {           // rows outside the staging buffer: direct, issued first
             const int y = g + m * G;
             v[m] = make_double2(0.0, 0.0);
-            if (y >= rows_s && col_ok) v[m] = H[inter_off(L, nh, srcj, y) + kr];
+            if (y >= rows_s && col_ok) v[m] = __ldcs(&H[inter_off(L, nh, srcj, y) + kr]);
         }
         asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
@@ -406,8 +418,8 @@ struct XCtx {
             double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
             if (k < kr_keep) {
                 const double kw = k * dk;
-                za = apply_mul<MA>(__ldg(A.at(k)), kw);
-                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(B.at(k)), kw);
+                za = apply_mul<MA>(__ldcs(A.at(k)), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldcs(B.at(k)), kw);
             }
             if (k == 0) {
                 r[0] = za.x;
@@ -436,8 +448,8 @@ struct XCtx {
             double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
             if (k < kr_keep) {                           // also excludes k = N/2 (kr_keep <= N/2)
                 const double kw = k * dk;
-                za = apply_mul<MA>(__ldg(A.at(k)), kw);
-                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldg(B.at(k)), kw);
+                za = apply_mul<MA>(__ldcs(A.at(k)), kw);
+                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldcs(B.at(k)), kw);
             }
             if (m < 8) v[m] = (m == 0 && x == 0) ? make_double2(za.x, zb.x) : make_double2(za.x - zb.y, za.y + zb.x);
             else v[m] = make_double2(za.x + zb.y, zb.x - za.y);

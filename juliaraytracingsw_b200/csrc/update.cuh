@@ -56,8 +56,8 @@ __global__ void __launch_bounds__(256) ifmab3_update_rsw_kernel(UpdateArgs a, Rs
         double2 x[3], n[3];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            x[v] = a.sol[v * L.vs + off];
-            n[v] = a.N[v * L.vs + off];
+            x[v] = __ldcs(a.sol + v * L.vs + off);
+            n[v] = __ldcs(a.N + v * L.vs + off);
         }
         if (a.euler) {
 #pragma unroll
