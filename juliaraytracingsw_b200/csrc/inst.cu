@@ -16,7 +16,8 @@ cudaError_t Launch<SWRT_N>::stage_a(int model, const double2* sol, const OutPeer
         case MODEL_RSW_MODIFIED: {
             SimpleJobs sj{};
             const int fld[5] = {0, 1, 2, 0, 1}, mul[5] = {YMUL_ONE, YMUL_ONE, YMUL_ONE, YMUL_IL, YMUL_IL};
-            for (int j = 0; j < 5; ++j) { sj.src[j] = sol + fld[j] * L.vs; sj.mul[j] = mul[j]; }
+            const int last[5] = {0, 0, 1, 1, 1};   // eta is read once; the i l u, i l v jobs are the second readers of u, v
+            for (int j = 0; j < 5; ++j) { sj.src[j] = sol + fld[j] * L.vs; sj.mul[j] = mul[j]; sj.last[j] = last[j]; }
             return ypass_inv_simple(sj, RswLoaderA{sol, L.vs}, L, 5, G_, tw, st);
         }
         case MODEL_RSW_LINDBORG: return ypass_inv(LindborgLoaderA{sol, L.vs}, L, 8, G_, tw, st);
@@ -98,7 +99,7 @@ cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih
     if (psih) {   // jobs: psih, -i l psih, l^2 psih from the materialised field
         SimpleJobs sj{};
         const int mul[3] = {YMUL_ONE, YMUL_NEG_IL, YMUL_L2};
-        for (int j = 0; j < 3; ++j) { sj.src[j] = psih; sj.mul[j] = mul[j]; }
+        for (int j = 0; j < 3; ++j) { sj.src[j] = psih; sj.mul[j] = mul[j]; sj.last[j] = j == 2; }
         return ypass_inv_simple(sj, ld, L, 3, G_, tw, st);
     }
     return ypass_inv(ld, L, 3, G_, tw, st);

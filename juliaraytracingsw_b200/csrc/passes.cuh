@@ -187,6 +187,7 @@ enum { YMUL_ONE = 0, YMUL_IL = 1, YMUL_NEG_IL = 2, YMUL_L2 = 3 };
 struct SimpleJobs {
     const double2* src[8];  // source spectral field of each job ([l][kr_pad])
     int mul[8];
+    int last[8];            // this job is the last reader of its source in this pass: load it evict-first
 };
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -218,14 +219,17 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
     const int ntiles = (L.kr_keep + TK - 1) / TK;
     const int nz = L.lz1 - L.lz0, rows = L.ny - nz;
     const int nwork = ntiles * njobs;
+    const unsigned long long pol = l2_evict_first_policy();
     auto prefetch = [&](int w) {
         const int job = w / ntiles, kr0 = (w % ntiles) * TK;
         const double2* src = jobs.src[job];
+        const bool last = jobs.last[job] != 0;
         for (int ch = tid; ch < rows * TK; ch += NT) {
             const int r = ch / TK, cc = ch - r * TK;
             const int l = r < L.lz0 ? r : r + nz;
             // columns beyond kr_keep inside the padded row are zero in every stored field: safe to copy
-            cp_async16(&stg[ch], &src[(long long)l * L.kr_pad + kr0 + cc]);
+            if (last) cp_async16_stream(&stg[ch], &src[(long long)l * L.kr_pad + kr0 + cc], pol);
+            else cp_async16(&stg[ch], &src[(long long)l * L.kr_pad + kr0 + cc]);
         }
         asm volatile("cp.async.commit_group;\n" ::);
     };

@@ -104,11 +104,11 @@ __global__ void __launch_bounds__(256) ifmab3_update_table_kernel(UpdateArgs a, 
 #pragma unroll
         for (int p = 0; p < NV; ++p)
 #pragma unroll
-            for (int q = 0; q < NV; ++q) e[p][q] = E[(p * NV + q) * L.vs + off];
+            for (int q = 0; q < NV; ++q) e[p][q] = __ldcs(E + (p * NV + q) * L.vs + off);   // tables and history: streaming
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
-            x[v] = a.sol[v * L.vs + off];
-            n[v] = a.N[v * L.vs + off];
+            x[v] = __ldcs(a.sol + v * L.vs + off);
+            n[v] = __ldcs(a.N + v * L.vs + off);
         }
         if (a.euler) {
 #pragma unroll
@@ -118,15 +118,15 @@ __global__ void __launch_bounds__(256) ifmab3_update_table_kernel(UpdateArgs a, 
             double2 n1[NV], n2[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                n1[v] = a.Nm1[v * L.vs + off];
-                n2[v] = a.Nm2[v * L.vs + off];
+                n1[v] = __ldcs(a.Nm1 + v * L.vs + off);
+                n2[v] = __ldcs(a.Nm2 + v * L.vs + off);
             }
 #pragma unroll
             for (int p = 0; p < NV; ++p) {
                 double2 A = make_double2(0.0, 0.0), B = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int q = 0; q < NV; ++q) {
-                    const double2 e2 = E2[(p * NV + q) * L.vs + off];
+                    const double2 e2 = __ldcs(E2 + (p * NV + q) * L.vs + off);
                     A = cadd(A, cmul(e[p][q], n1[q]));
                     B = cadd(B, cmul(e2, n2[q]));
                 }
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) update_diag_kernel(UpdateArgs a, double2*
                 Nrw[o] = n;
                 if (a.euler) x = make_double2(x.x + a.dt * n.x, x.y + a.dt * n.y);
                 else {
-                    const double2 n1 = a.Nm1[o], n2 = a.Nm2[o];
+                    const double2 n1 = __ldcs(a.Nm1 + o), n2 = __ldcs(a.Nm2 + o);   // history: streaming
                     x.x += a.dt * (h1 * n.x - h2 * n1.x + h3 * n2.x);
                     x.y += a.dt * (h1 * n.y - h2 * n1.y + h3 * n2.y);
                 }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) update_diag_kernel(UpdateArgs a, double2*
             } else {
                 if (a.euler) x = make_double2(x.x + a.dt * n.x, x.y + a.dt * n.y);
                 else {
-                    const double2 n1 = a.Nm1[o], n2 = a.Nm2[o];
+                    const double2 n1 = __ldcs(a.Nm1 + o), n2 = __ldcs(a.Nm2 + o);   // history: streaming
                     const double e1 = cf.x, e2 = cf.x * cf.x;
                     x.x += a.dt * (h1 * n.x - h2 * e1 * n1.x + h3 * e2 * n2.x);
                     x.y += a.dt * (h1 * n.y - h2 * e1 * n1.y + h3 * e2 * n2.y);
