@@ -96,6 +96,11 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot);
 /* which node data velocity_snapshot produces (SWRT_INTERP_*): 5 fields u,v,ux,uy,vx or 7 fields (+ uxy, vxy); packets created with
  * the same interpolant read them.  snapshot_fields returns 5 or 7 (the third extent of get/set_snapshot arrays). */
 int swrt_flow_set_interp(swrt_flow* h, int interp);
+/* "FFT interpolation": the snapshots' node grid is `refine` (1 or 2) times finer than the flow's, by spectral zero padding
+ * (the exact trigonometric interpolant sampled on the finer grid; raytracing/NUFFTRaytracing.jl:68-84 aims at that interpolant,
+ * Notebooks/FFTInterpTest.ipynb refines the same way).  Set before creating packet handles; any interpolant then acts on the finer grid. */
+int swrt_flow_set_snapshot_refinement(swrt_flow* h, int refine);
+int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny);
 int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields);
 /* old_velocity = new_velocity; old_grad_v = new_grad_v (raytracing/RaytracingDriver.jl:269-270).
  * alias != 0 reproduces the reference's rebinding (both names then refer to the same buffers);

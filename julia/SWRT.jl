@@ -169,6 +169,9 @@ get_velocity_info!(prob::Problem, slot::Integer; psi_kind = 0) =
     check(ccall((:swrt_flow_velocity_snapshot, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint), prob.h, psi_kind, slot))
 "node data of the snapshots: 0 bilinear (u,v,ux,uy,vx), 1 Hermite bicubic (+ uxy, vxy)"
 set_interpolation!(prob::Problem, interp::Integer) = check(ccall((:swrt_flow_set_interp, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, interp))
+"FFT interpolation: snapshots on a node grid `refine` (1 or 2) times finer than the flow's, by spectral zero padding"
+set_snapshot_refinement!(prob::Problem, refine::Integer) =
+    check(ccall((:swrt_flow_set_snapshot_refinement, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, refine))
 "old_velocity = new_velocity; old_grad_v = new_grad_v"
 swap_snapshots!(prob::Problem; alias = false) =
     check(ccall((:swrt_flow_swap_snapshots, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, alias))

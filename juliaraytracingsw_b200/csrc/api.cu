@@ -67,6 +67,10 @@ struct swrt_flow {
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
     double2* psih = nullptr;                    // materialised streamfunction for the packet snapshot
+    // spectrally refined snapshots ("FFT interpolation"): node grid refine x finer than the flow's, by zero padding
+    int refine = 1;
+    SpecLayout Ls{};
+    double2 *psih_s = nullptr, *Gs = nullptr, *tw_xs = nullptr, *tw_ys = nullptr;
     double4* coef2 = nullptr;                   // ETDRK4 coefficients {zeta, alpha, beta, Gamma}
     double2 *S1 = nullptr, *S2 = nullptr, *N4 = nullptr;   // stage states and 4th N buffer of the multi-stage steppers
     double2 *Etab = nullptr, *E2tab = nullptr;   // tabulated exp(L dt), exp(2 L dt) for general NV x NV blocks (two-layer QG)
@@ -300,7 +304,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
-    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
+    cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
     for (int w = 0; w < 2; ++w)
         for (int r = 0; r < h->P; ++r)
@@ -976,6 +980,23 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
     CK(wait_readers(h));
     cudaError_t e;
+    if (h->refine > 1) {
+        const SpecLayout& Ls = h->Ls;
+        ld.pdx = pf ? h->d.Lx / Ls.nx : 0.0;
+        ld.pdy = pf ? h->d.Ly / Ls.ny : 0.0;
+        if (L.kr_keep > 0) {
+            const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+            ProfScope ps(h, K_PSI);
+            psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, L, h->psih_s, Ls.ny - L.ny);
+            CK(cudaGetLastError());
+        }
+        { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(Ls.ny, e, LN::psi_stage_a_refined(h->psih_s, Ls, out_local(h->Gs), h->tw_ys, h->st)); }
+        CK(e);
+        const int mode = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? 1 : (h->interp == SWRT_INTERP_BILINEAR_F32 ? 2 : 0);
+        { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(Ls.nx, e, LN::snap_stage_b(h->Gs, h->snap[h->slot_map[slot]], mode, Ls, h->tw_xs, h->sched, h->st, 1.0 / ((double)L.nx * (double)L.ny))); }
+        CK(e);
+        return SWRT_OK;
+    }
     bool materialise = false;
     SWRT_DISPATCH(L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
     CK(e);
@@ -989,6 +1010,47 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     CK(e);
     { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(L.nx, e, LN::snap_stage_b(h->G, h->snap[h->slot_map[slot]], h->interp == SWRT_INTERP_HERMITE_BICUBIC ? 1 : (h->interp == SWRT_INTERP_BILINEAR_F32 ? 2 : 0), L, h->tw_x, h->sched, h->st)); }
     CK(e);
+    return SWRT_OK;
+}
+
+int swrt_flow_set_snapshot_refinement(swrt_flow* h, int refine) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (refine != 1 && refine != 2) return fail(SWRT_ERR_ARG, "refinement must be 1 or 2");
+    if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow");
+    if (!supported_n(refine * h->d.nx) || !supported_n(refine * h->d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "refined grid %d x %d exceeds the supported sizes", refine * h->d.nx, refine * h->d.ny);
+    if (!h->readers.empty()) return fail(SWRT_ERR_STATE, "set the refinement before creating packet handles");
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys);
+    h->psih_s = h->Gs = h->tw_xs = h->tw_ys = nullptr;
+    h->refine = refine;
+    const size_t nodes = (size_t)refine * h->d.nx * (size_t)refine * h->d.ny;
+    for (int lev = 0; lev < 2; ++lev) {
+        cudaFree(h->snap[lev]);
+        h->snap[lev] = nullptr;
+        CK(cudaMalloc(&h->snap[lev], sizeof(double) * nodes * SNAP3_STRIDE));
+        CK(cudaMemset(h->snap[lev], 0, sizeof(double) * nodes * SNAP3_STRIDE));
+    }
+    if (refine > 1) {
+        SpecLayout& Ls = h->Ls;
+        Ls = h->L;
+        Ls.nx = refine * h->d.nx; Ls.ny = refine * h->d.ny;
+        Ls.lz1 = Ls.ny - (h->L.ny - h->L.lz1);      // the negative-l rows keep their distance from the end
+        Ls.vs = (long long)Ls.ny * Ls.kr_pad;
+        Ls.yrows = Ls.ny;
+        Ls.yshift = 0; while ((1 << Ls.yshift) < Ls.ny) ++Ls.yshift;
+        const size_t fb = sizeof(double2) * (size_t)Ls.vs;
+        CK(cudaMalloc(&h->psih_s, fb)); CK(cudaMemset(h->psih_s, 0, fb));
+        CK(cudaMalloc(&h->Gs, 3 * fb)); CK(cudaMemset(h->Gs, 0, 3 * fb));
+        CK(upload_twiddles(Ls.nx, &h->tw_xs));
+        CK(upload_twiddles(Ls.ny, &h->tw_ys));
+    }
+    return SWRT_OK;
+}
+int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny) {
+    if (!h || !nx || !ny) return fail(SWRT_ERR_ARG, "null pointer");
+    *nx = h->refine * h->d.nx;
+    *ny = h->refine * h->d.ny;
     return SWRT_OK;
 }
 
@@ -1015,7 +1077,7 @@ int swrt_flow_swap_snapshots(swrt_flow* h, int alias) {
 int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const long long n = (long long)h->d.nx * h->d.ny;
+    const long long n = (long long)h->refine * h->d.nx * h->refine * h->d.ny;
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
@@ -1035,7 +1097,7 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     if (h->interp == SWRT_INTERP_BILINEAR_F32) return fail(SWRT_ERR_UNSUPPORTED, "snapshots of the fp32 packet mode are built by swrt_flow_velocity_snapshot only");
     CK(cudaSetDevice(h->d.device));
-    const long long n = (long long)h->d.nx * h->d.ny;
+    const long long n = (long long)h->refine * h->d.nx * h->refine * h->d.ny;
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
@@ -1130,7 +1192,7 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     p->d = *desc;
     p->flow = flow;
     p->st = flow->st;
-    p->nbins = (long long)flow->d.nx * flow->d.ny;
+    p->nbins = (long long)flow->refine * flow->d.nx * flow->refine * flow->d.ny;   // cells of the snapshots' node grid
     const size_t n = (size_t)desc->n;
     const size_t nsums = (size_t)(p->nbins / SCAN_BLOCK + 2) + (size_t)(p->nbins / SCAN_BLOCK / SCAN_BLOCK + 2) + 8;
     cudaError_t e;
@@ -1247,8 +1309,8 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
 
 static PacketGrid packet_grid(const swrt_flow* f) {
     PacketGrid g;
-    g.nx = f->d.nx; g.ny = f->d.ny;
-    g.dx = f->d.Lx / f->d.nx; g.dy = f->d.Ly / f->d.ny;
+    g.nx = f->refine * f->d.nx; g.ny = f->refine * f->d.ny;    // the node grid of the snapshots
+    g.dx = f->d.Lx / g.nx; g.dy = f->d.Ly / g.ny;
     g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
     g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
     return g;
@@ -1293,6 +1355,8 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     if (!(t1 != t0)) return fail(SWRT_ERR_ARG, "t1 must differ from t0");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
+    if (p->nbins != (long long)f->refine * f->d.nx * f->refine * f->d.ny)
+        return fail(SWRT_ERR_STATE, "the snapshot refinement changed after these packets were created");
     if (p->d.sort_every > 0 && p->since_sort >= p->d.sort_every) {
         int rc = sort_packets(p);
         if (rc) return rc;

@@ -105,9 +105,29 @@ cudaError_t Launch<SWRT_N>::psi_stage_a(const PsiLoader& ld, const double2* psih
     return ypass_inv(ld, L, 3, G_, tw, st);
 }
 template <>
+cudaError_t Launch<SWRT_N>::psi_stage_a_refined(const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st) {
+    if constexpr (kPrefetchFits) {
+        const size_t stage = (size_t)(L.ny - (L.lz1 - L.lz0)) * TK * 16;
+        if (ysmem + stage + 1024 > (size_t)kSmemPerSM) return cudaErrorNotSupported;
+        SimpleJobs sj{};
+        const int mul[3] = {YMUL_ONE, YMUL_NEG_IL, YMUL_L2};
+        for (int j = 0; j < 3; ++j) { sj.src[j] = psih; sj.mul[j] = mul[j]; sj.last[j] = j == 2; }
+        auto k = ypass_inv_prefetch_kernel<SWRT_N, TK>;
+        int mc = 1;
+        cudaError_t e = prep(k, ysmem + stage, TK * G, &mc);
+        if (e != cudaSuccess) return e;
+        const int work = ((L.kr_keep + TK - 1) / TK) * 3;
+        if (work == 0) return cudaSuccess;
+        k<<<work < mc ? work : mc, TK * G, ysmem + stage, st>>>(sj, L, 3, G_, tw);
+        return cudaGetLastError();
+    } else {
+        return cudaErrorNotSupported;
+    }
+}
+template <>
 cudaError_t Launch<SWRT_N>::snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched,
-                                         cudaStream_t st) {
-    const double s1 = 1.0 / ((double)L.nx * (double)L.ny);
+                                         cudaStream_t st, double s1_in) {
+    const double s1 = s1_in > 0.0 ? s1_in : 1.0 / ((double)L.nx * (double)L.ny);
     if (cubic == 2) return xpass(SnapshotXOp<SWRT_N, false, true>{G_, out, s1}, L, tw, sched, st);   // fp32 node records
     if (cubic) return xpass(SnapshotCubicXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);
     return xpass(SnapshotXOp<SWRT_N>{G_, out, s1}, L, tw, sched, st);

@@ -736,7 +736,10 @@ struct Launch {
     static cudaError_t forward_field_y(const double2* H, double2* out, const SpecLayout& L, const double2* tw_y, cudaStream_t st);
     static cudaError_t psi_stage_a(const PsiLoader& ld, const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static constexpr bool psi_prefetch = kPrefetchFits;   // psih must have been materialised (update.cuh psi_kernel) when true
-    static cudaError_t snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t snap_stage_b(const double2* G_, double* out, int cubic, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st,
+                                    double s1 = 0.0);
+    // spectrally refined snapshot (zero-padded transform onto a finer node grid): psih is already laid out for L
+    static cudaError_t psi_stage_a_refined(const double2* psih, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
 };
 
 }  // namespace swrt

@@ -245,14 +245,15 @@ __global__ void __launch_bounds__(256) diag_stage_kernel(StageArgs a, SpecLayout
 // ---------------------------------------------------------------- streamfunction for the packet snapshot
 // psih[l][kr] = PsiLoader::psi_of(...)  (get_streamfunction!, rsw/RSWRaytracingDriver.jl:56-67 and the QG variants), materialised
 // once so that the three y-transform jobs of the snapshot read one plain field (prefetchable, see passes.cuh)
-__global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, double2* __restrict__ psih) {
+// `lshift` > 0: psih is laid out for a finer node grid (spectral zero padding): rows of negative l move up by that many rows
+__global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, double2* __restrict__ psih, int lshift = 0) {
     const int nlk = L.ny - (L.lz1 - L.lz0);
     const long long total = (long long)nlk * L.kr_keep;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int lr = (int)(i / L.kr_keep), kr = (int)(i - (long long)lr * L.kr_keep);
         const int l = lr < L.lz0 ? lr : lr + (L.lz1 - L.lz0);
         const long long off = (long long)l * L.kr_pad + kr;
-        psih[off] = ld.psi_of((L.kr_off + kr) * L.dk, wave_l(L, l), off);
+        psih[(long long)(l < L.lz0 ? l : l + lshift) * L.kr_pad + kr] = ld.psi_of((L.kr_off + kr) * L.dk, wave_l(L, l), off);
     }
 }
 

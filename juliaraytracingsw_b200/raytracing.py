@@ -29,7 +29,9 @@ class Velocity:
         g = self.prob.grid
         nf = C.c_int()
         check(lib().swrt_flow_snapshot_fields(self.prob._h, C.byref(nf)))
-        out = np.empty((g.nx, g.ny, nf.value), dtype=np.float64, order="F")
+        nx, ny = C.c_int(), C.c_int()
+        check(lib().swrt_flow_snapshot_dims(self.prob._h, C.byref(nx), C.byref(ny)))   # the node grid may be refined
+        out = np.empty((nx.value, ny.value, nf.value), dtype=np.float64, order="F")
         check(lib().swrt_flow_get_snapshot(self.prob._h, self.slot, out.ctypes.data_as(C.c_void_p)))
         return out
 
@@ -57,12 +59,21 @@ def set_interpolation(prob, interp):
     check(lib().swrt_flow_set_interp(prob._h, int(interp)))
 
 
+def set_snapshot_refinement(prob, refine):
+    """"FFT interpolation": the snapshots' node grid becomes `refine` (1 or 2) times finer than the flow's by spectral zero
+    padding, i.e. the exact trigonometric interpolant sampled on the finer grid (what raytracing/NUFFTRaytracing.jl:68-84 aims at
+    and Notebooks/FFTInterpTest.ipynb does on the host).  Call before creating packets."""
+    check(lib().swrt_flow_set_snapshot_refinement(prob._h, int(refine)))
+
+
 def set_velocity_info(prob, slot, fields):
     """Load (nx, ny, 5) = u, v, ux, uy, vx (or (nx, ny, 7) with uxy, vxy in Hermite mode) host fields into a slot."""
     a = np.asfortranarray(fields, dtype=np.float64)
     nf = C.c_int()
     check(lib().swrt_flow_snapshot_fields(prob._h, C.byref(nf)))
-    assert a.shape == (prob.grid.nx, prob.grid.ny, nf.value), a.shape
+    nx, ny = C.c_int(), C.c_int()
+    check(lib().swrt_flow_snapshot_dims(prob._h, C.byref(nx), C.byref(ny)))
+    assert a.shape == (nx.value, ny.value, nf.value), a.shape
     check(lib().swrt_flow_set_snapshot(prob._h, slot, a.ctypes.data_as(C.c_void_p)))
 
 

@@ -288,6 +288,19 @@ def raytrace_midpoint(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, sampl
     return xk
 
 
+def refine_streamfunction(psih, grid, r):
+    """Spectral zero padding of psih (nkr, nl) onto a grid r times finer (rsw/RSWDriver.jl:16-36 does the same to restart at a
+    higher resolution; Notebooks/FFTInterpTest.ipynb uses it to interpolate): returns (psih_fine, grid_fine).  The trigonometric
+    interpolant is unchanged; only its sampling grid is finer."""
+    from .grid import TwoDGrid
+    gf = TwoDGrid(r * grid.nx, grid.Lx, r * grid.ny, grid.Ly, aliased_fraction=0)
+    half = grid.nl // 2
+    new = np.zeros((gf.nkr, gf.nl), dtype=np.complex128)
+    new[:grid.nkr - 1, :half] = psih[:grid.nkr - 1, :half]
+    new[:grid.nkr - 1, gf.nl - half + 1:] = psih[:grid.nkr - 1, half + 1:]          # Nyquist row and column carry nothing (dealiased)
+    return new * (r * r), gf
+
+
 def generate_initial_wavepackets_twolayer(L, k0, sqrtN):
     """raytracing/TwoLayerRaytracing.jl:10-22 (the CPU driver's lattice): packet (i-1) s + j sits at
     (i L/s - L/2 - L/2s, j L/s - L/2 - L/2s) with wavevector angle 2 pi ((i-1) s + j)/N; all frequency signs +1."""

@@ -796,3 +796,85 @@ def test_fp32_packet_mode():
     pk64 = raytracing.Packets(prob, 16, c["f"], c["Cg"])
     with pytest.raises(swrt._lib.SwrtError):
         raytracing.raytrace(pk64, None, None, None, None, prob.grid, pk64, c["dt"], (0.0, t1))
+
+
+@pytest.mark.parametrize("interp", [0, 2, 3])
+def test_refined_snapshots_fft_interpolation(interp):
+    """"FFT interpolation": snapshots on a node grid twice finer than the flow's (spectral zero padding) against the oracle's
+    zero-padded transform; ray tracing on the refined grid; and the refined interpolant is closer to the exact trigonometric one."""
+    g, p, sol0, c = config2_setup(64)
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 3)
+    prob = swrt.Problem(nx=64, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_interpolation(prob, interp)
+    raytracing.set_snapshot_refinement(prob, 2)
+    prob.sol = sol0
+    vel, _ = raytracing.get_velocity_info(prob, 0)
+    flow.stepforward(prob, (), 3)
+    raytracing.get_velocity_info(prob, 1)
+    F = []
+    for s in (sol0, sol1):
+        psif, gf = oray.refine_streamfunction(orsw.get_streamfunction(s, g, p), g, 2)
+        Ff = oray.get_velocity_info(psif, gf)
+        F.append(oray.bspline2_prefilter(Ff, gf) if interp == 2 else Ff)
+    Fo, Fn = F
+    got = vel._arr()
+    assert got.shape == (128, 128, 5)
+    tol = 1e-6 if interp == 3 else 1e-12
+    assert rel_l2(got, Fo) < tol
+    # the refined nodes that coincide with the flow's grid carry the unrefined values
+    if interp == 0:
+        assert rel_l2(got[::2, ::2], oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)) < 1e-12
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 20)
+    xk[:, 0:2] += np.random.default_rng(3).uniform(-20, 20, size=(xk.shape[0], 2))
+    pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=2, interp=interp)
+    pk.set(xk, sign)
+    t1 = 3 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (0.0, t1))
+    if interp == 2:
+        want, h = xk.copy(), t1 / 2
+        for s_ in range(2):
+            f_ = lambda z, al: oray.rhs_sampler(z, sign, al, oray.sample_bspline2(Fo, z[:, 0], z[:, 1], gf), oray.sample_bspline2(Fn, z[:, 0], z[:, 1], gf), c["f"], c["Cg"])
+            a0 = s_ * h / t1
+            k1 = f_(want, a0); k2 = f_(want + 0.5 * h * k1, a0 + 0.5 * h / t1); k3 = f_(want + 0.5 * h * k2, a0 + 0.5 * h / t1)
+            k4 = f_(want + h * k3, a0 + h / t1)
+            want = want + (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    else:
+        cast = (lambda A: A.astype(np.float32).astype(np.float64)) if interp == 3 else (lambda A: A)
+        want = oray.raytrace(xk.copy(), sign, 0.0, t1, cast(Fo), cast(Fn), gf, c["f"], c["Cg"], nsub=2)
+    d = pk.get() - want
+    assert np.abs(d).max() / np.abs(want).max() < (2e-6 if interp == 3 else 1e-8)
+    if interp == 0:
+        # exact trigonometric value of u at random points vs bilinear on the coarse and on the refined grid
+        rng = np.random.default_rng(9)
+        px, py = rng.uniform(-np.pi, np.pi, 200), rng.uniform(-np.pi, np.pi, 200)
+        psih = orsw.get_streamfunction(sol0, g, p)
+        uh = -1j * g.l * psih
+        w = np.where((np.arange(g.nkr) == 0) | (np.arange(g.nkr) == g.nkr - 1), 1.0, 2.0)[:, None]
+        phase = np.exp(1j * (g.kr[:, :, None] * (px - g.x[0])[None, None, :] + g.l[:, :, None] * (py - g.y[0])[None, None, :]))
+        exact = ((w * uh)[:, :, None] * phase).real.sum(axis=(0, 1)) / (g.nx * g.ny)
+        Fc = oray.get_velocity_info(psih, g)
+        e_coarse = np.abs(oray.sample_bilinear(Fc, px, py, g)[:, 0] - exact).max()
+        e_fine = np.abs(oray.sample_bilinear(Fo, px, py, gf)[:, 0] - exact).max()
+        assert e_fine < 0.4 * e_coarse
+        with pytest.raises(swrt._lib.SwrtError):               # 4096 is the largest transform
+            raytracing.set_snapshot_refinement(swrt.Problem(nx=4096, f=3.0, dt=1e-4), 2)
+
+
+def test_refined_snapshot_large_grid_property():
+    """2048^2 flow, 4096^2 node grid (the largest transform): the refined nodes that coincide with the flow's grid carry the
+    unrefined snapshot exactly to round-off -- a size-independent property of spectral zero padding."""
+    g, p, sol0, c = config2_setup(2048)
+    pa = swrt.Problem(nx=2048, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    pa.sol = sol0
+    coarse = raytracing.get_velocity_info(pa, 0)[0]._arr()
+    raytracing.set_snapshot_refinement(pa, 2)
+    fine = raytracing.get_velocity_info(pa, 0)[0]._arr()
+    assert fine.shape == (4096, 4096, 5)
+    assert rel_l2(fine[::2, ::2], coarse) < 1e-12
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 64)
+    pk = raytracing.Packets(pa, xk.shape[0], c["f"], c["Cg"])
+    pk.set(xk, sign)
+    raytracing.get_velocity_info(pa, 1)
+    raytracing.raytrace(pk, None, None, None, None, pa.grid, pk, c["dt"], (0.0, c["dt"]))
+    U = raytracing.interpolate_velocity(raytracing.Velocity(pa, 0), pk)
+    assert np.isfinite(pk.get()).all() and np.abs(U).max() <= np.abs(fine[:, :, 0:2]).max() * (1 + 1e-12)
