@@ -163,6 +163,10 @@ int swrt_slab_info(swrt_flow* h, int* yrows, int* chunk, int* njobs_a, int* njob
  * where the all-to-all used to be. */
 int swrt_slab_ipc_handle(swrt_flow* h, int which, void* handle64);
 int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handle64);
+/* first transpose of the slab step: 0 = the y-pass stores its 32-64 byte pieces straight into the peers' receive buffers,
+ * 1 = the y-pass stores locally and the x-pass pulls its input segments from the peers' send buffers (needs SWRT_SLAB_A_SEND
+ * mapped too), 2 = local stores followed by a block-copy kernel that ships whole lines to the peers */
+int swrt_slab_set_mode(swrt_flow* h, int mode);
 int swrt_slab_p2p(swrt_flow* h, int* enabled);
 int swrt_slab_stage_a(swrt_flow* h);
 int swrt_slab_stage_b(swrt_flow* h);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "swrt_slab_info": (_I, [_P, _PI, _PI, _PI, _PI]),
     "swrt_slab_ipc_handle": (_I, [_P, _I, _P]),
     "swrt_slab_ipc_open": (_I, [_P, _I, _I, _P]),
+    "swrt_slab_set_mode": (_I, [_P, _I]),
     "swrt_slab_p2p": (_I, [_P, _PI]),
     "swrt_slab_stage_a": (_I, [_P]),
     "swrt_slab_stage_b": (_I, [_P]),

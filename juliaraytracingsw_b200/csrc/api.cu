@@ -83,8 +83,9 @@ struct swrt_flow {
     int P = 1, rank = 0;
     bool own_stream = true;
     // peer receive buffers (cudaIpcOpenMemHandle) of the two transposes: [0] = A_RECV (G2), [1] = B_RECV (H) of every rank
-    double2* peer[2][kMaxPeers] = {};
-    bool p2p = false;
+    double2* peer[3][kMaxPeers] = {};   // [2] = A_SEND (G) of every rank, mapped for the pull variant of the first transpose
+    bool p2p = false, pull = false;
+    int slab_mode = 0;   // first transpose: 0 = the y-pass stores into the peers (32-64 B pieces), 1 = the x-pass pulls, 2 = local stores + block copy kernel
     unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
     int ring = 0;
     double t = 0.0;
@@ -218,9 +219,30 @@ static OutPeers out_local(double2* arr) {
     o.self = 0;
     return o;
 }
+// sources of the x-pass input segments: this rank's receive buffer [src][job][row][chunk], or (pull) every rank's own send
+// buffer, where this rank's block sits at index `rank`
+// block copy of the first transpose: the send buffer [dest][job][row][chunk] goes to every peer's receive buffer in full lines
+__global__ void __launch_bounds__(256) slab_block_copy_kernel(const double2* __restrict__ send, OutPeers dst, long long blk, int P) {
+    const long long total = blk * P;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i / blk);
+        dst.p[d][(long long)dst.self * blk + (i - (long long)d * blk)] = __ldcs(send + i);
+    }
+}
+static OutPeers in_slab(const swrt_flow* h, int njobs) {
+    OutPeers o{};
+    if (h->pull && h->slab_mode == 1) {
+        for (int s = 0; s < h->P; ++s) o.p[s] = h->peer[2][s];
+        o.self = h->rank;
+    } else {
+        for (int s = 0; s < h->P; ++s) o.p[s] = h->G2 + (long long)s * njobs * h->L.yrows * h->L.kr_pad;
+        o.self = 0;
+    }
+    return o;
+}
 static OutPeers out_slab(const swrt_flow* h, int which /*0: A, 1: B*/, double2* send, int njobs) {
     OutPeers o{};
-    if (h->p2p) {
+    if (h->p2p && !(which == 0 && h->slab_mode != 0)) {
         for (int d = 0; d < h->P; ++d) o.p[d] = h->peer[which][d];
         o.self = h->rank;
     } else {   // send buffer laid out [dest][job][row][chunk]: block d starts at d * njobs * yrows * chunk
@@ -306,7 +328,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
-    for (int w = 0; w < 2; ++w)
+    for (int w = 0; w < 3; ++w)
         for (int r = 0; r < h->P; ++r)
             if (h->peer[w][r] && r != h->rank) cudaIpcCloseMemHandle(h->peer[w][r]);
     prof_collect(h);
@@ -872,21 +894,23 @@ int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbyt
 }
 int swrt_slab_ipc_handle(swrt_flow* h, int which, void* handle64) {
     if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
-    if (which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV) return fail(SWRT_ERR_ARG, "only the receive buffers are shared");
+    if (which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV && which != SWRT_SLAB_A_SEND)
+        return fail(SWRT_ERR_ARG, "shared buffers: the two receive buffers and (pull variant) the first send buffer");
     CK(cudaSetDevice(h->d.device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t mh;
-    CK(cudaIpcGetMemHandle(&mh, which == SWRT_SLAB_A_RECV ? (void*)h->G2 : (void*)h->H));
+    CK(cudaIpcGetMemHandle(&mh, which == SWRT_SLAB_A_RECV ? (void*)h->G2 : which == SWRT_SLAB_A_SEND ? (void*)h->G : (void*)h->H));
     memcpy(handle64, &mh, 64);
     return SWRT_OK;
 }
 int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handle64) {
     if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
-    if ((which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV) || peer_rank < 0 || peer_rank >= h->P) return fail(SWRT_ERR_ARG, "bad argument");
+    if ((which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV && which != SWRT_SLAB_A_SEND) || peer_rank < 0 || peer_rank >= h->P)
+        return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const int w = which == SWRT_SLAB_A_RECV ? 0 : 1;
+    const int w = which == SWRT_SLAB_A_RECV ? 0 : which == SWRT_SLAB_B_RECV ? 1 : 2;
     if (peer_rank == h->rank) {
-        h->peer[w][peer_rank] = w == 0 ? h->G2 : h->H;
+        h->peer[w][peer_rank] = w == 0 ? h->G2 : w == 1 ? h->H : h->G;
     } else {
         cudaIpcMemHandle_t mh;
         memcpy(&mh, handle64, 64);
@@ -898,6 +922,28 @@ int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handl
     for (int w2 = 0; w2 < 2; ++w2)
         for (int r = 0; r < h->P; ++r) all = all && h->peer[w2][r] != nullptr;
     h->p2p = all;     // both transposes become direct peer stores once every receive buffer is mapped
+    bool allg = all;
+    for (int r = 0; r < h->P; ++r) allg = allg && h->peer[2][r] != nullptr;
+    h->pull = allg;   // with every rank's first send buffer mapped too, the x-pass pulls its input segments instead
+    return SWRT_OK;
+}
+int swrt_slab_set_mode(swrt_flow* h, int mode) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    if (mode < 0 || mode > 2) return fail(SWRT_ERR_ARG, "mode must be 0 (push), 1 (pull) or 2 (block copy)");
+    if (mode == 1 && !h->pull) return fail(SWRT_ERR_STATE, "the pull variant needs every rank's first send buffer mapped");
+    if (mode == 2 && !h->p2p) return fail(SWRT_ERR_STATE, "the block-copy variant needs the receive buffers mapped");
+    h->slab_mode = mode;
+    return SWRT_OK;
+}
+// after a y-pass that stored into the local send buffer: ship the blocks (mode 2)
+static int slab_ship_a(swrt_flow* h, int njobs) {
+    if (h->slab_mode != 2 || !h->p2p) return SWRT_OK;
+    OutPeers dst{};
+    for (int d = 0; d < h->P; ++d) dst.p[d] = h->peer[0][d];
+    dst.self = h->rank;
+    const long long blk = (long long)njobs * h->L.yrows * h->L.kr_pad;
+    { ProfScope ps(h, K_OTHER); slab_block_copy_kernel<<<148 * 8, 256, 0, h->st>>>(h->G, dst, blk, h->P); }
+    CK(cudaGetLastError());
     return SWRT_OK;
 }
 int swrt_slab_p2p(swrt_flow* h, int* enabled) {
@@ -911,13 +957,13 @@ int swrt_slab_stage_a(swrt_flow* h) {
     cudaError_t e;
     { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(h->L.ny, e, LN::stage_a(h->d.model, h->sol, out_slab(h, 0, h->G, model_njobs_a(h->d.model)), h->L, h->tw_y, h->st)); }
     CK(e);
-    return SWRT_OK;
+    return slab_ship_a(h, model_njobs_a(h->d.model));
 }
 int swrt_slab_stage_b(swrt_flow* h) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, h->G2, out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, in_slab(h, model_njobs_a(h->d.model)), out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -955,7 +1001,7 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     cudaError_t e;
     { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
     CK(e);
-    return SWRT_OK;
+    return slab_ship_a(h, 3);
 }
 int swrt_slab_snap_b(swrt_flow* h, int slot) {
     if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
@@ -964,7 +1010,7 @@ int swrt_slab_snap_b(swrt_flow* h, int slot) {
     double* rows = h->snap[h->slot_map[slot]] + (long long)h->rank * h->L.yrows * h->d.nx * SNAP_STRIDE;   // this rank's rows of the full field
     CK(wait_readers(h));
     cudaError_t e;
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(h->G2, rows, h->L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(in_slab(h, 3), rows, h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
     return SWRT_OK;
 }

@@ -45,20 +45,20 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const double2* G_, const OutPeers& H, const SpecLayout& L, const double2* tw,
+cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const OutPeers& Gin, const OutPeers& H, const SpecLayout& L, const double2* tw,
                                          unsigned* sched, cudaStream_t st) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{G_, nullptr, sc, s1, H}, L, tw, sched, st);
-        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{G_, nullptr, sc, H}, L, tw, sched, st);
-        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{G_, nullptr, sc, H}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{nullptr, nullptr, sc, s1, H, Gin}, L, tw, sched, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin}, L, tw, sched, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
 }
 template <>
-cudaError_t Launch<SWRT_N>::snap_stage_b_slab(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
+cudaError_t Launch<SWRT_N>::snap_stage_b_slab(const OutPeers& Gin, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
                                               cudaStream_t st) {
-    return xpass(SnapshotXOp<SWRT_N, true>{G_, out, 1.0 / ((double)L.nx * (double)L.ny)}, L, tw, sched, st);
+    return xpass(SnapshotXOp<SWRT_N, true>{nullptr, out, 1.0 / ((double)L.nx * (double)L.ny), Gin}, L, tw, sched, st);
 }
 template <>
 cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {

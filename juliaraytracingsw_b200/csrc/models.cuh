@@ -48,10 +48,11 @@ struct RswXOp {
     double sc;         // (1/(nx ny))^2 / 2
     double s1;         // 1/(nx ny)
     OutPeers peers;    // slab mode: destinations of the output column segments
+    OutPeers gin;      // slab mode: sources of the input column segments
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const auto Gu = row_ref<SLAB>(L, G, 5, 0, y), Gv = row_ref<SLAB>(L, G, 5, 1, y), Ge = row_ref<SLAB>(L, G, 5, 2, y), Guy = row_ref<SLAB>(L, G, 5, 3, y),
-                   Gvy = row_ref<SLAB>(L, G, 5, 4, y);
+        const auto Gu = row_in<SLAB>(L, G, gin, 5, 0, y), Gv = row_in<SLAB>(L, G, gin, 5, 1, y), Ge = row_in<SLAB>(L, G, gin, 5, 2, y),
+                   Guy = row_in<SLAB>(L, G, gin, 5, 3, y), Gvy = row_in<SLAB>(L, G, gin, 5, 4, y);
         const RowPlain none{};
         constexpr int NH = MODIFIED ? 5 : 4;
         // Thread g owns x = g + m N/16 (m = 0..15) of the physical row.  Inverse transforms are loaded through shared
@@ -243,9 +244,10 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
     double2* H;        // [2 NL][ny][kr_pad]
     double sc;
     OutPeers peers;
+    OutPeers gin;      // slab mode: sources of the input column segments
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 3 * NL, j, y); };
+        auto Gp = [&](int j) { return row_in<SLAB>(L, G, gin, 3 * NL, j, y); };
         auto Hp = [&](int j) { return row_out<SLAB>(L, H, peers, 2 * NL, j, y); };
         double *q1 = cx.re(0), *q2 = cx.im(0);
         double2 v[16];
@@ -550,12 +552,13 @@ struct SnapshotXOp {
     const double2* G;  // [3][ny][kr_pad]
     double* out;       // [ny][nx][6] of the level being written ([ny][nx][8] floats in the fp32 packet mode)
     double s1;
+    OutPeers gin;      // slab mode: sources of the input column segments
     // vx stays in the registers of the thread that stores it (x = g + m N/16); (u, v) and (ux, uy) wait in the two shared
     // buffers, so that the three 16-byte pieces of a record are stored back to back (whole sectors reach L2 together)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
         static_assert(EPT == 16, "one register per owned point");
-        const auto Gp = row_ref<SLAB>(L, G, 3, 0, y), Gu = row_ref<SLAB>(L, G, 3, 1, y), Guy = row_ref<SLAB>(L, G, 3, 2, y);
+        const auto Gp = row_in<SLAB>(L, G, gin, 3, 0, y), Gu = row_in<SLAB>(L, G, gin, 3, 1, y), Guy = row_in<SLAB>(L, G, gin, 3, 2, y);
         double2 vx[16];
         cx.template load_pair<MUL_MK2, MUL_ZERO>(1, Gp, RowPlain{});
         cx.ifft_regs_out(1, vx);  // vx
@@ -726,8 +729,8 @@ struct Launch {
     static cudaError_t stage_a(int model, const double2* sol, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     // slab mode (P > 1): segmented rows; built for the models of the >= 4096^2 configurations (RSW, SWQG, two-layer QG)
-    static cudaError_t stage_b_slab(int model, const double2* G_, const OutPeers& H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
-    static cudaError_t snap_stage_b_slab(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t stage_b_slab(int model, const OutPeers& Gin, const OutPeers& H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t snap_stage_b_slab(const OutPeers& Gin, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);

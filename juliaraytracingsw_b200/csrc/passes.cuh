@@ -12,6 +12,7 @@
 // Model-specific arithmetic (which spectral expression feeds which transform, which
 // products are formed, how transforms combine into N) is supplied by small functors.
 #pragma once
+#include <type_traits>
 #include "fft.cuh"
 
 namespace swrt {
@@ -91,6 +92,23 @@ __device__ __forceinline__ typename RowOf<SLAB>::type row_ref(const SpecLayout& 
         r.skip = ((long long)njobs << L.yshift) * L.kr_pad - L.kr_pad;
         r.chunk = L.kr_pad;
         r.nseg = L.ny >> L.yshift;
+    }
+    return r;
+}
+// Input row of the x-pass in slab mode, addressed through a table of source buffers: entry s is where the column segment of
+// source rank s lives -- this rank's receive buffer (the y-pass pushed it there) or, in pull mode, rank s's own send buffer
+// mapped over NVLink (the y-pass stored locally in full lines and this pass fetches whole 1-3 KB column segments).
+template <bool SLAB>
+__device__ __forceinline__ typename std::conditional<SLAB, RowSegOut, RowPlain>::type row_in(const SpecLayout& L, const double2* arr,
+                                                                                           const OutPeers& src, int njobs, int job, int yl) {
+    typename std::conditional<SLAB, RowSegOut, RowPlain>::type r;
+    if constexpr (SLAB) {
+        r.peers = &src;
+        r.off = ((((long long)src.self * njobs + job) << L.yshift) + yl) * L.kr_pad;
+        r.chunk = L.kr_pad;
+        r.nseg = L.ny >> L.yshift;
+    } else {
+        r.base = const_cast<double2*>(arr) + (((long long)job << L.yshift) + yl) * L.kr_pad;
     }
     return r;
 }

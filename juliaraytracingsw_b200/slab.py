@@ -10,6 +10,7 @@ packets may sit anywhere in the domain.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -30,7 +31,7 @@ class SlabProblem(flow.Problem):
     """`Problem` whose step is distributed over the ranks of `dist` (a torch.distributed process group).
     Supported: RotatingShallowWater, SWQG, TwoLayerQG with the IFMAB3 stepper."""
 
-    def __init__(self, dist, dev=0, p2p=True, **kw):
+    def __init__(self, dist, dev=0, p2p=True, pull=None, **kw):
         """p2p=True: the transposes are direct NVLink stores into the peers' receive buffers (CUDA IPC) followed by a
         stream-ordered barrier; p2p=False: NCCL all_to_all_single on send/receive buffers."""
         import torch
@@ -49,6 +50,11 @@ class SlabProblem(flow.Problem):
         self.kr_lo = self.rank * self.chunk
         self._flag = torch.zeros(1, device=f"cuda:{dev}")
         self.p2p = False
+        # first transpose: "push" (y-pass stores into the peers), "pull" (x-pass reads the peers' send buffers) or "copy"
+        # (local stores + a block-copy kernel); measured in profiles/r01_g_multigpu_summary.md
+        default = "copy" if self.world >= 4 else "push"             # 8 GPUs: 0.489 (copy) / 0.502 (push) / 0.559 (pull) ms per step
+        self.mode = os.environ.get("SWRT_SLAB_MODE", default) if pull is None else ("pull" if pull else "push")
+        self.pull = self.mode == "pull"
         if p2p:
             self._open_peers()
 
@@ -56,18 +62,21 @@ class SlabProblem(flow.Problem):
         """Exchange the CUDA IPC handles of the two receive buffers and map every peer's."""
         L = lib()
         mine = {}
-        for which in (A_RECV, B_RECV):
+        shared = (A_RECV, B_RECV, A_SEND) if self.pull else (A_RECV, B_RECV)
+        for which in shared:
             buf = C.create_string_buffer(64)
             check(L.swrt_slab_ipc_handle(self._h, which, buf))
             mine[which] = buf.raw
         allh = [None] * self.world
         self.dist.all_gather_object(allh, mine)
         for r, hs in enumerate(allh):
-            for which in (A_RECV, B_RECV):
+            for which in shared:
                 check(L.swrt_slab_ipc_open(self._h, which, r, hs[which]))
         en = C.c_int()
         check(L.swrt_slab_p2p(self._h, C.byref(en)))
         self.p2p = bool(en.value)
+        if self.p2p:
+            check(L.swrt_slab_set_mode(self._h, {"push": 0, "pull": 1, "copy": 2}[self.mode]))
         self._barrier()
 
     def _barrier(self):
