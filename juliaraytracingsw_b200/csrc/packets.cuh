@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
                                                                  PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -114,10 +114,10 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
     }
-    xk[i] = s[0];
-    xk[n + i] = s[1];
-    xk[2 * n + i] = s[2];
-    xk[3 * n + i] = s[3];
+    __stcs(xk + i, s[0]);
+    __stcs(xk + n + i, s[1]);
+    __stcs(xk + 2 * n + i, s[2]);
+    __stcs(xk + 3 * n + i, s[3]);
 }
 
 // ---------------------------------------------------------------- stencil-cached variant
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128, 4) raytrace_rk4_cubic_kernel(double* __re
                                                                     PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(128, 4) raytrace_rk4_cubic_kernel(double* __re
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
-    xk[i] = s[0];
-    xk[n + i] = s[1];
-    xk[2 * n + i] = s[2];
-    xk[3 * n + i] = s[3];
+    __stcs(xk + i, s[0]);
+    __stcs(xk + n + i, s[1]);
+    __stcs(xk + 2 * n + i, s[2]);
+    __stcs(xk + 3 * n + i, s[3]);
 }
 
 __global__ void __launch_bounds__(128) sample_cubic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(128, 3) raytrace_generic_kernel(double* __rest
                                                                   PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -483,10 +483,10 @@ __global__ void __launch_bounds__(128, 3) raytrace_generic_kernel(double* __rest
             for (int c = 0; c < 4; ++c) s[c] += h * k[c];
         }
     }
-    xk[i] = s[0];
-    xk[n + i] = s[1];
-    xk[2 * n + i] = s[2];
-    xk[3 * n + i] = s[3];
+    __stcs(xk + i, s[0]);
+    __stcs(xk + n + i, s[1]);
+    __stcs(xk + 2 * n + i, s[2]);
+    __stcs(xk + 3 * n + i, s[3]);
 }
 template <int INTERP>
 __global__ void __launch_bounds__(128) sample_generic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_f32_kernel(double* __r
                                                                   RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {xk[i], xk[n + i], xk[2 * n + i], xk[3 * n + i]};
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
     const float sg = (float)sign[i], f2 = (float)(p.f * p.f), cg2 = (float)(p.Cg * p.Cg);
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     StencilF st;
@@ -588,10 +588,10 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_f32_kernel(double* __r
 #pragma unroll
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
-    xk[i] = s[0];
-    xk[n + i] = s[1];
-    xk[2 * n + i] = s[2];
-    xk[3 * n + i] = s[3];
+    __stcs(xk + i, s[0]);
+    __stcs(xk + n + i, s[1]);
+    __stcs(xk + 2 * n + i, s[2]);
+    __stcs(xk + 3 * n + i, s[3]);
 }
 __global__ void __launch_bounds__(128) sample_f32_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                          const float4* __restrict__ S, PacketGrid g, double* __restrict__ U,

@@ -198,7 +198,8 @@ class PacketPipeline:
 
     def __init__(self, prob, n, f, Cg, nchunks=8, **kw):
         self.prob, self.n = prob, int(n)
-        self.bounds = [(c * self.n // nchunks, (c + 1) * self.n // nchunks) for c in range(nchunks)]
+        from .parallel import shard_range
+        self.bounds = [b for b in (shard_range(self.n, c, nchunks) for c in range(nchunks)) if b[1] > b[0]]   # the rank-shard rule; empty blocks dropped
         self.chunks = [Packets(prob, hi - lo, f, Cg, **kw) for lo, hi in self.bounds]
         for p in self.chunks:
             p.use_own_stream()

@@ -60,3 +60,12 @@ def test_shard_ranges_partition_exactly():
             edges = [parallel.shard_range(n, r, w) for r in range(w)]
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+
+
+def test_pipeline_chunks_are_the_rank_shard_rule():
+    """PacketPipeline's row blocks use `shard_range`: contiguous, ordered, exact cover, also when ragged."""
+    from juliaraytracingsw_b200.parallel import shard_range
+    for n, c in ((2500, 7), (16777216, 8), (5, 8), (1, 1)):
+        b = [shard_range(n, i, c) for i in range(c)]
+        assert b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(c - 1)) and all(lo <= hi for lo, hi in b)
