@@ -98,6 +98,9 @@ struct swrt_flow {
     double prof_ms[16] = {0};
     long long prof_n[16] = {0};
     std::vector<struct swrt_packets*> readers;   // packet handles with their own stream (snapshot writers wait for their reads)
+    // CUDA graphs of the step for launch-bound grid sizes: one per ring phase (3 steps each; 1 step for the multi-stage steppers)
+    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
+    long long glaunches[3] = {0, 0, 0};
 };
 
 enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_PSI, K_OTHER, K_COUNT };
@@ -333,6 +336,7 @@ int swrt_flow_destroy(swrt_flow* h) {
             if (h->peer[w][r] && r != h->rank) cudaIpcCloseMemHandle(h->peer[w][r]);
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
+    for (auto& g : h->gexec) if (g) cudaGraphExecDestroy(g);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev_sync) cudaEventDestroy(h->ev_sync);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -604,7 +608,7 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
         diag_stage_kernel<<<ublocks, 256, 0, h->st>>>(sa, L);
         return cudaGetLastError();
     };
-    for (int s = 0; s < nsteps; ++s) {
+    auto step_body = [&]() -> int {
         int rc;
         if (stepper == SWRT_ETDRK4) {            // FourierFlows ETDRK4 stepforward!
             double2 *N1 = h->Nb[0], *N2 = h->Nb[1], *N3 = h->Nb[2], *N4 = h->N4;
@@ -634,6 +638,41 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
         }
         h->t += dt;
         h->step += 1;
+        return SWRT_OK;
+    };
+    // Small grids are launch bound (a 512^2 step is four ~10 us kernels): replay the step from a CUDA graph.  A graph holds one
+    // period of the history ring (three steps; one for the multi-stage steppers), whose kernel arguments then repeat exactly.
+    static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
+    const bool ring_stepper = stepper == SWRT_IFMAB3 || stepper == SWRT_FILTEREDAB3;
+    const int period = ring_stepper ? 3 : 1;
+    const bool use_graph = graph_mode > 0 && !h->prof && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
+    for (int s = 0; s < nsteps;) {
+        if (use_graph && h->step >= 3 && nsteps - s >= period) {
+            const int phase = ring_stepper ? h->ring : 0;
+            if (!h->gexec[phase]) {
+                const long long l0 = h->launches;
+                CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed));
+                int rc = SWRT_OK;
+                for (int p = 0; p < period && rc == SWRT_OK; ++p) rc = step_body();
+                cudaGraph_t g = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(h->st, &g);
+                if (rc != SWRT_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                CK(ce);
+                const cudaError_t ie = cudaGraphInstantiate(&h->gexec[phase], g, 0);
+                cudaGraphDestroy(g);
+                CK(ie);
+                h->glaunches[phase] = h->launches - l0;
+            } else {
+                for (int p = 0; p < period; ++p) { h->t += dt; h->step += 1; }   // the ring is back at `phase` after one period
+                h->launches += h->glaunches[phase];
+            }
+            CK(cudaGraphLaunch(h->gexec[phase], h->st));
+            s += period;
+        } else {
+            const int rc = step_body();
+            if (rc) return rc;
+            s += 1;
+        }
     }
     return SWRT_OK;
 }
