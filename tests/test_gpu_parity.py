@@ -878,3 +878,23 @@ def test_refined_snapshot_large_grid_property():
     raytracing.raytrace(pk, None, None, None, None, pa.grid, pk, c["dt"], (0.0, c["dt"]))
     U = raytracing.interpolate_velocity(raytracing.Velocity(pa, 0), pk)
     assert np.isfinite(pk.get()).all() and np.abs(U).max() <= np.abs(fine[:, :, 0:2]).max() * (1 + 1e-12)
+
+
+def test_committed_golden_vectors():
+    """The CUDA path against the committed fixture tests/golden/rsw64_config2.npz (spectral state 1e-10, packets 1e-8)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rsw64_config2.npz"))
+    L_, dt, f, Cg, nu, nnu, k0 = G["params"]
+    prob = swrt.Problem(nx=64, Lx=L_, dt=dt, f=f, Cg=Cg, nu=nu, nnu=int(nnu))
+    prob.sol = G["sol0"]
+    flow.stepforward(prob, (), 10)
+    assert rel_l2(prob.sol, G["sol10"]) < 1e-10
+    vel, _ = raytracing.get_velocity_info(prob, 0)
+    assert rel_l2(vel._arr(), G["snapshot10"]) < 1e-11
+    pk = raytracing.Packets(prob, G["xk0"].shape[0], f, Cg, nsub=3)
+    pk.set(G["xk0"], G["sign"])
+    flow.stepforward(prob, (), 3)
+    assert rel_l2(prob.sol, G["sol13"]) < 1e-10
+    raytracing.get_velocity_info(prob, 1)
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, dt, (10 * dt, 13 * dt))
+    assert np.abs(pk.get() - G["xk1"]).max() / np.abs(G["xk1"]).max() < 1e-8

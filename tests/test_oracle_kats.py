@@ -330,3 +330,19 @@ def test_komega_window_and_detrend_restatement():
     assert np.allclose(m, 3.0 - 0.7j) and np.allclose(b, -(3.0 - 0.7j) * t.sum() / 19)
     spec = okw.clean_fft(t, data, okw.hann(19))
     assert spec.shape == (19, 2)
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/rsw64_config2.npz (made by tests/golden/make_golden.py): the oracle must keep reproducing it."""
+    import os
+    from helpers import config2_setup, oracle_steps
+    from oracle import raytrace as oray, rsw as orsw
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rsw64_config2.npz"))
+    g, p, sol0, c = config2_setup(64)
+    assert np.abs(sol0 - G["sol0"]).max() <= 1e-13 * np.abs(sol0).max()
+    sol10 = oracle_steps(g, p, G["sol0"].copy(), c["dt"], 10)
+    assert np.linalg.norm(sol10 - G["sol10"]) <= 1e-12 * np.linalg.norm(sol10)
+    Fo = oray.get_velocity_info(orsw.get_streamfunction(G["sol10"], g, p), g)
+    Fn = oray.get_velocity_info(orsw.get_streamfunction(G["sol13"], g, p), g)
+    xk1 = oray.raytrace(G["xk0"].copy(), G["sign"], 10 * c["dt"], 13 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3)
+    assert np.abs(xk1 - G["xk1"]).max() <= 1e-12 * np.abs(xk1).max()
