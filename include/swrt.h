@@ -225,6 +225,11 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
 int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host);
 /* k-cutoff reset raytracing/GPUTwoLayerRaytracing.jl:136-138 */
 int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long long* nreset);
+/* the hot loop of start_raytracing! (raytracing/RaytracingDriver.jl:256-270): stepforward!(prob, [], 1); get_velocity_info(new);
+ * raytrace!(old -> new, (old_t, new_t)); [k-cutoff reset when kcut > 0, raytracing/TwoLayerRaytracing.jl:136-141]; old = new --
+ * nsteps times in one call (one ccall per output period instead of five per step; matters on launch-bound grid sizes) */
+int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double kcut, double k0);
+
 /* ---- overlapped packet I/O -----------------------------------------------------------------------------
  * Give the handle its own CUDA stream; its copies and kernels then overlap the flow's stream and other packet handles
  * (events order them against the snapshots they read).  Split an ensemble over several handles and issue, per handle,

@@ -221,6 +221,9 @@ get_packets_async!(p::Packets, xk::Ptr{Cdouble}, ld::Integer) =
 sample_async!(p::Packets, slot::Integer, U::Ptr{Cdouble}, G::Ptr{Cdouble}, ld::Integer) =
     check(ccall((:swrt_packets_sample_async, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Clonglong), p.h, slot, U, G, ld))
 sync!(p::Packets) = check(ccall((:swrt_packets_sync, libswrt), Cint, (Ptr{Cvoid},), p.h))
+"the hot loop (stepforward!; get_velocity_info; raytrace!; old = new) nsteps times in one ccall"
+coupled_steps!(p::Packets, nsteps::Integer; psi_kind = 0, k_cutoff = 0.0, k0 = 0.0) =
+    check(ccall((:swrt_packets_coupled_steps, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cdouble), p.h, psi_kind, nsteps, k_cutoff, k0))
 function kcutoff_reset!(p::Packets, k_cutoff, k0)
     n = Ref{Clonglong}(0)
     check(ccall((:swrt_packets_kcutoff_reset, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Ref{Clonglong}), p.h, k_cutoff, k0, n))

@@ -101,6 +101,7 @@ SIGNATURES = {
     "swrt_series_times": (_I, [_P, _P]),
     "swrt_series_get": (_I, [_P, _I, _P]),
     "swrt_series_spectrum": (_I, [_P, _I, _P]),
+    "swrt_packets_coupled_steps": (_I, [_P, _I, _I, _D, _D]),
     "swrt_packets_use_own_stream": (_I, [_P]),
     "swrt_packets_set_async": (_I, [_P, _P, _LL, _P]),
     "swrt_packets_get_async": (_I, [_P, _P, _LL]),

@@ -1526,10 +1526,29 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), p->st));
     { ProfScope ps(f, K_OTHER, p->st); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, n, kcut * kcut, k0, p->count); }
     CK(cudaGetLastError());
-    unsigned long long c = 0;
-    CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, p->st));
-    CK(cudaStreamSynchronize(p->st));
-    if (nreset) *nreset = (long long)c;
+    if (nreset) {   // the count is only fetched (and the stream only synchronised) when the caller asks for it
+        unsigned long long c = 0;
+        CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, p->st));
+        CK(cudaStreamSynchronize(p->st));
+        *nreset = (long long)c;
+    }
+    return SWRT_OK;
+}
+
+int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double kcut, double k0) {
+    // the hot loop of start_raytracing! (raytracing/RaytracingDriver.jl:256-270; with the k-cutoff of
+    // raytracing/TwoLayerRaytracing.jl:136-141 when kcut > 0), nsteps times, without returning to the host language
+    if (!p || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
+    swrt_flow* f = p->flow;
+    for (int s = 0; s < nsteps; ++s) {
+        const double old_t = f->t;
+        int rc = swrt_flow_step(f, 1);
+        if (rc) return rc;
+        if ((rc = swrt_flow_velocity_snapshot(f, psi_kind, 1))) return rc;
+        if ((rc = swrt_packets_raytrace(p, old_t, f->t))) return rc;
+        if (kcut > 0.0 && (rc = swrt_packets_kcutoff_reset(p, kcut, k0, nullptr))) return rc;
+        if ((rc = swrt_flow_swap_snapshots(f, 0))) return rc;
+    }
     return SWRT_OK;
 }
 

@@ -149,6 +149,13 @@ def coupled_step(prob, packets, old_t):
     return new_t
 
 
+def coupled_steps(prob, packets, nsteps, psi_kind=raytracing.PSI_RSW_BALANCED, k_cutoff=0.0, k0=0.0):
+    """`nsteps` iterations of `coupled_step` in one library call (same kernels, same order): returns the new time."""
+    from ._lib import check, lib
+    check(lib().swrt_packets_coupled_steps(packets._h, int(psi_kind), int(nsteps), float(k_cutoff), float(k0)))
+    return prob.clock.t
+
+
 @dataclass
 class Frame:
     step: int

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import juliaraytracingsw_b200 as swrt
-from juliaraytracingsw_b200 import flow, raytracing
+from juliaraytracingsw_b200 import drivers, flow, raytracing
 from oracle import raytrace as oray
 from oracle import rsw as orsw
 from oracle.grid import TwoDGrid, makefilter
@@ -898,3 +898,24 @@ def test_committed_golden_vectors():
     raytracing.get_velocity_info(prob, 1)
     raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, dt, (10 * dt, 13 * dt))
     assert np.abs(pk.get() - G["xk1"]).max() / np.abs(G["xk1"]).max() < 1e-8
+
+
+def test_coupled_steps_entry_point_is_the_python_loop():
+    """swrt_packets_coupled_steps = n x drivers.coupled_step, bit for bit (state, packets, clock)."""
+    g, p, sol0, c = config2_setup(128)
+    res = []
+    for fused in (False, True):
+        prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+        prob.sol = sol0
+        pk = raytracing.generate_initial_wavepackets(prob, c["L"], c["k0"], 900, 30, c["f"], c["Cg"], sort_every=4)
+        raytracing.get_velocity_info(prob, 0)
+        t = prob.clock.t
+        if fused:
+            t = drivers.coupled_steps(prob, pk, 11)
+        else:
+            for _ in range(11):
+                t = drivers.coupled_step(prob, pk, t)
+        res.append((prob.sol, pk.get(), t, prob.clock.step))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2] and res[0][3] == res[1][3] == 11
