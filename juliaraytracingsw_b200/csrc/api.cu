@@ -101,6 +101,7 @@ struct swrt_flow {
     // CUDA graphs of the step for launch-bound grid sizes: one per ring phase (3 steps each; 1 step for the multi-stage steppers)
     cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
     long long glaunches[3] = {0, 0, 0};
+    bool no_graph = false;   // set while an outer capture (the coupled loop) records the step
 };
 
 enum { K_STAGE_A = 0, K_STAGE_B, K_STAGE_C, K_UPDATE, K_PSI_A, K_SNAP_B, K_RAYTRACE, K_SAMPLE, K_FIELD_A, K_FIELD_B, K_SORT, K_PSI, K_OTHER, K_COUNT };
@@ -153,6 +154,9 @@ struct swrt_packets {
     cudaStream_t st = nullptr;      // the flow's stream, or the handle's own (swrt_packets_use_own_stream)
     bool own = false;
     cudaEvent_t ev_done = nullptr;  // last read of the flow's snapshots by this handle
+    // CUDA graphs of six coupled steps (ring period 3 x snapshot-slot period 2), one per parity of the sort's double buffer
+    struct Cycle { cudaGraphExec_t exec = nullptr; long long launches = 0; const void *xk = nullptr, *snap0 = nullptr; int psi_kind = 0, interp = 0; double kcut = 0, k0 = 0; };
+    Cycle cycle[2];
 };
 static inline cudaEvent_t packets_done_event(const swrt_packets* p) { return p->ev_done; }
 
@@ -645,7 +649,7 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
     static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
     const bool ring_stepper = stepper == SWRT_IFMAB3 || stepper == SWRT_FILTEREDAB3;
     const int period = ring_stepper ? 3 : 1;
-    const bool use_graph = graph_mode > 0 && !h->prof && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
+    const bool use_graph = graph_mode > 0 && !h->prof && !h->no_graph && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
     for (int s = 0; s < nsteps;) {
         if (use_graph && h->step >= 3 && nsteps - s >= period) {
             const int phase = ring_stepper ? h->ring : 0;
@@ -1251,6 +1255,7 @@ int swrt_packets_destroy(swrt_packets* p) {
         cudaStreamSynchronize(p->st);
         auto& rd = p->flow->readers;
         rd.erase(std::remove(rd.begin(), rd.end(), p), rd.end());
+        for (auto& c : p->cycle) if (c.exec) cudaGraphExecDestroy(c.exec);
         if (p->own) cudaStreamDestroy(p->st);
         if (p->ev_done) cudaEventDestroy(p->ev_done);
     }
@@ -1540,14 +1545,63 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     // raytracing/TwoLayerRaytracing.jl:136-141 when kcut > 0), nsteps times, without returning to the host language
     if (!p || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
     swrt_flow* f = p->flow;
-    for (int s = 0; s < nsteps; ++s) {
-        const double old_t = f->t;
+    auto body = [&]() -> int {
         int rc = swrt_flow_step(f, 1);
         if (rc) return rc;
         if ((rc = swrt_flow_velocity_snapshot(f, psi_kind, 1))) return rc;
-        if ((rc = swrt_packets_raytrace(p, old_t, f->t))) return rc;
+        // the tracer only sees t - t0 and t1 - t0: every step is traced over (0, dt), which makes the kernel arguments of
+        // consecutive steps identical (the absolute (old_t, new_t) of the per-call loop differ from this by rounding only)
+        if ((rc = swrt_packets_raytrace(p, 0.0, f->d.dt))) return rc;
         if (kcut > 0.0 && (rc = swrt_packets_kcutoff_reset(p, kcut, k0, nullptr))) return rc;
-        if ((rc = swrt_flow_swap_snapshots(f, 0))) return rc;
+        return swrt_flow_swap_snapshots(f, 0);
+    };
+    // Launch-bound grid sizes: replay six coupled steps from one CUDA graph.  After six steps the history ring (period 3) and
+    // the snapshot slots (period 2) are back where they started, so every kernel argument repeats -- except the packet
+    // buffers, which a sort swaps (one graph per buffer parity; steps that contain a sort run un-captured).
+    static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
+    const int period = 6;
+    const bool ring_stepper = f->d.stepper == SWRT_IFMAB3 || f->d.stepper == SWRT_FILTEREDAB3;
+    const bool eligible = graph_mode > 0 && !f->prof && !p->own && f->P == 1 && f->refine == 1 &&
+                          (graph_mode > 1 || (long long)f->d.nx * f->d.ny <= 1024LL * 1024LL);
+    for (int s = 0; s < nsteps;) {
+        const bool aligned = f->step >= 3 && f->slot_map[0] == 0 && (!ring_stepper || f->ring == 0);
+        const bool sort_inside = p->d.sort_every > 0 && p->since_sort + period > p->d.sort_every;
+        if (eligible && aligned && !sort_inside && nsteps - s >= period && p->nbins == (long long)f->d.nx * f->d.ny) {
+            swrt_packets::Cycle& c = p->cycle[p->xk < p->xk2 ? 0 : 1];
+            if (c.exec && (c.xk != p->xk || c.snap0 != f->snap[0] || c.psi_kind != psi_kind || c.interp != f->interp || c.kcut != kcut || c.k0 != k0)) {
+                cudaGraphExecDestroy(c.exec);
+                c.exec = nullptr;
+            }
+            if (!c.exec) {
+                CK(cudaSetDevice(f->d.device));
+                const long long l0 = f->launches;
+                f->no_graph = true;
+                cudaError_t be = cudaStreamBeginCapture(f->st, cudaStreamCaptureModeRelaxed);
+                if (be != cudaSuccess) { f->no_graph = false; CK(be); }
+                int rc = SWRT_OK;
+                for (int q = 0; q < period && rc == SWRT_OK; ++q) rc = body();
+                cudaGraph_t g = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(f->st, &g);
+                f->no_graph = false;
+                if (rc != SWRT_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                CK(ce);
+                const cudaError_t ie = cudaGraphInstantiate(&c.exec, g, 0);
+                cudaGraphDestroy(g);
+                CK(ie);
+                c.launches = f->launches - l0;
+                c.xk = p->xk; c.snap0 = f->snap[0]; c.psi_kind = psi_kind; c.interp = f->interp; c.kcut = kcut; c.k0 = k0;
+            } else {
+                for (int q = 0; q < period; ++q) { f->t += f->d.dt; f->step += 1; }
+                p->since_sort += period;
+                f->launches += c.launches;
+            }
+            CK(cudaGraphLaunch(c.exec, f->st));
+            s += period;
+        } else {
+            const int rc = body();
+            if (rc) return rc;
+            s += 1;
+        }
     }
     return SWRT_OK;
 }
