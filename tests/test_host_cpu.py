@@ -73,3 +73,33 @@ def test_twolayer_driver_lattice_and_parameters():
     assert abs(U - 0.1 / 7.5) < 1e-17 and abs(b1 - (4 / 225 + 1)) < 1e-15
     assert abs(mu - 2 * U * (0.36 / np.log(7.5 / 3.2)) * 15) < 1e-15
     assert abs(P.dt - 0.02 * (2 * np.pi / 512) / 0.1) < 1e-18
+
+
+def test_julia_shim_is_consistent_with_the_header():
+    """julia/SWRT.jl cannot be executed here (no Julia): check statically that every symbol it ccalls is declared in
+    include/swrt.h and that its two descriptor structs list the header's fields in the header's order (as _lib.py does)."""
+    hdr = open(os.path.join(ROOT, "include", "swrt.h")).read()
+    jl = open(os.path.join(ROOT, "julia", "SWRT.jl")).read()
+    declared = set(re.findall(r"\b(swrt_[a-z_0-9]+)\s*\(", hdr))
+    called = set(re.findall(r"\(:(swrt_[a-z_0-9]+),\s*libswrt\)", jl))
+    assert called and called <= declared, called - declared
+
+    def header_fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip() for n in decl.split(None, 1)[1].replace("long long", "").split(",")]
+        return [n.split()[-1] for n in names]
+
+    def julia_fields(struct):
+        body = re.search(r"Base\.@kwdef struct %s\n(.*?)\nend" % struct, jl, re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        return re.findall(r"([A-Za-z_0-9]+)::C", body)
+
+    for cname, jname, pycls in (("swrt_flow_desc", "FlowDesc", _lib.FlowDesc), ("swrt_packets_desc", "PacketsDesc", _lib.PacketsDesc)):
+        want = header_fields(cname)
+        assert julia_fields(jname) == want, (jname, julia_fields(jname), want)
+        assert [f[0] for f in pycls._fields_] == want, (pycls, want)
