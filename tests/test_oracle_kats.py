@@ -346,3 +346,50 @@ def test_oracle_reproduces_committed_golden_vectors():
     Fn = oray.get_velocity_info(orsw.get_streamfunction(G["sol13"], g, p), g)
     xk1 = oray.raytrace(G["xk0"].copy(), G["sign"], 10 * c["dt"], 13 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3)
     assert np.abs(xk1 - G["xk1"]).max() <= 1e-12 * np.abs(xk1).max()
+
+
+def test_recalled_steppers_have_their_formal_order():
+    """FilteredAB3 / ETDRK4 / FilteredRK4 are FourierFlows' (third party, recalled from its documentation -- parity unpinned): at
+    least check each restatement against an exact solution.  y' = L y + N(y), L = -2, N = y^2 (Bernoulli):
+    y(t) = 1 / ((1/y0 - 1/2) e^{2t} + 1/2); halving dt must cut the error 2^order-fold."""
+    from oracle import qg as oqg, ty as oty
+    L, y0, T = np.full((1, 1), -2.0), 0.7, 1.0
+    exact = 1.0 / ((1 / y0 - 0.5) * np.exp(2 * T) + 0.5)
+    N = lambda s: s * s
+
+    def err(make, n):
+        ts = make(T / n)
+        y = np.full((1, 1), y0)
+        for _ in range(n):
+            ts.stepforward(y)
+        return abs(y[0, 0] - exact)
+
+    one = np.ones((1, 1))
+    cases = (("FilteredAB3", lambda dt: oqg.FilteredAB3(L, dt, N, one), 3, (400, 800)),      # Euler start-up: measured late
+             ("ETDRK4", lambda dt: oty.ETDRK4(L, dt, N), 4, (20, 40)),
+             ("FilteredRK4", lambda dt: oty.FilteredRK4(L, dt, N, one), 4, (20, 40)))
+    for name, make, order, (n1, n2) in cases:
+        e1, e2 = err(make, n1), err(make, n2)
+        rate = np.log2(e1 / e2)
+        if name == "FilteredAB3":      # three Euler steps of size dt leave an O(dt^2) start-up error: second order globally
+            assert 1.8 < rate < 3.3, (name, rate)
+        else:
+            assert order - 0.4 < rate < order + 0.6, (name, rate)
+        assert e2 < 1e-4
+
+
+def test_etdrk4_contour_coefficients_match_the_closed_forms():
+    """The 32-point contour means (Kassam-Trefethen) against the closed-form ETD coefficients where those are well conditioned."""
+    from oracle import ty as oty
+    dt = 0.1
+    L = np.array([[-30.0, -5.0, -0.7]])
+    z = dt * L
+    zeta, alpha, beta, gamma = oty.etdrk4_coeffs(dt, L)
+    ez = np.exp(z)
+    assert np.allclose(zeta, dt * (np.exp(z / 2) - 1) / z, rtol=1e-12)
+    assert np.allclose(alpha, dt * (-4 - z + ez * (4 - 3 * z + z * z)) / z ** 3, rtol=1e-9)
+    assert np.allclose(beta, dt * (2 + z + ez * (-2 + z)) / z ** 3, rtol=1e-9)
+    assert np.allclose(gamma, dt * (-4 - 3 * z - z * z + ez * (4 - z)) / z ** 3, rtol=1e-9)
+    # and they stay finite where the closed forms cancel catastrophically
+    small = oty.etdrk4_coeffs(dt, np.array([[-1e-9, 0.0]]))
+    assert all(np.isfinite(c).all() for c in small) and abs(small[1][0, 1] - dt / 6) < 1e-12
