@@ -393,3 +393,34 @@ def test_etdrk4_contour_coefficients_match_the_closed_forms():
     # and they stay finite where the closed forms cancel catastrophically
     small = oty.etdrk4_coeffs(dt, np.array([[-1e-9, 0.0]]))
     assert all(np.isfinite(c).all() for c in small) and abs(small[1][0, 1] - dt / 6) < 1e-12
+
+
+def test_multilayerqg_restatement_agrees_with_the_in_repo_two_layer_operator():
+    """GeophysicalFlows' MultiLayerQG is third party (recalled), but for U = (U, -U), beta = 0 it must describe the same physics as
+    the reference's own swqg/TwoLayerQG.jl: calcN_MLQG(q) + D q  ==  calcN_TwoLayerQG(q) + L_2x2 q  (L_2x2 of TwoLayerQG.jl:184-198
+    carries the mean-flow advection, the PV-gradient term and the bottom drag that MultiLayerQG keeps inside calcN!)."""
+    from oracle import qg as oqg
+    from oracle.grid import TwoDGrid
+    g = TwoDGrid(64)
+    rng = np.random.default_rng(21)
+    q = np.stack([g.rfft2(rng.standard_normal((64, 64))) for _ in range(2)], axis=-1)
+    q = g.dealias(q * np.exp(-0.02 * g.Krsq)[:, :, None])
+    F, U, mu, nu, nnu = 37.5, 0.4, 0.3, 1e-6, 2
+    L2 = oqg.twolayer_L(g, F, U, mu, nu, nnu)
+    lhs = oqg.twolayer_calcN(q.copy(), g, F) + np.einsum("ijab,ijb->ija", L2, q)
+    D = (-nu * g.Krsq ** nnu)[:, :, None]
+    rhs = oqg.multilayer2_calcN(q.copy(), g, F, U, -U, 0.0, mu) + D * q
+    # the aliased band of the physical-space products differs (the in-repo model leaves it to the next dealias!): compare retained modes
+    lhs, rhs = g.dealias(lhs), g.dealias(rhs)
+    assert np.linalg.norm(lhs - rhs) < 1e-12 * np.linalg.norm(lhs)
+
+
+def test_makefilter_shape():
+    """FourierFlows.makefilter (recalled): 1 up to innerK, exp(-decay (K - innerK)^order) beyond, equal to `tol` at K = outerK."""
+    from oracle.grid import TwoDGrid, makefilter
+    g = TwoDGrid(64)
+    filt = makefilter(g, order=4, innerK=2 / 3, outerK=1.0, tol=1e-15)
+    K = np.sqrt((g.kr * g.dx / np.pi) ** 2 + (g.l * g.dy / np.pi) ** 2)
+    assert np.all(filt[K < 2 / 3] == 1.0) and np.all(np.diff(filt[:, 0]) <= 0)
+    i = np.argmin(np.abs(K[:, 0] - 1.0))            # the Nyquist mode sits at K = 1
+    assert abs(K[i, 0] - 1.0) < 1e-12 and abs(filt[i, 0] / 1e-15 - 1) < 1e-9
