@@ -424,3 +424,36 @@ def test_makefilter_shape():
     assert np.all(filt[K < 2 / 3] == 1.0) and np.all(np.diff(filt[:, 0]) <= 0)
     i = np.argmin(np.abs(K[:, 0] - 1.0))            # the Nyquist mode sits at K = 1
     assert abs(K[i, 0] - 1.0) < 1e-12 and abs(filt[i, 0] / 1e-15 - 1) < 1e-9
+
+
+def test_bsplines_match_scipy_ndimage():
+    """Independent check of the two B-spline restatements (Interpolations.jl is not available here): scipy.ndimage's periodic
+    centred B-spline interpolation (`map_coordinates(order=2|3, mode='grid-wrap')`) uses the same basis and prefilter."""
+    from scipy import ndimage
+    from oracle import raytrace as oray
+    from oracle.grid import TwoDGrid
+    g = TwoDGrid(32, 2 * np.pi)
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal((32, 32, 1))
+    ix, iy = rng.uniform(-40, 70, 300), rng.uniform(-40, 70, 300)          # index coordinates, far outside one period too
+    px, py = g.x[0] + ix * g.dx, g.y[0] + iy * g.dy
+    for order, pre, samp in ((2, oray.bspline2_prefilter, oray.sample_bspline2), (3, oray.bspline3_prefilter, oray.sample_bspline3)):
+        want = ndimage.map_coordinates(f[:, :, 0], np.stack([ix, iy]), order=order, mode="grid-wrap")
+        got = samp(pre(f, g), px, py, g)[:, 0]
+        assert np.abs(got - want).max() < 1e-12 * np.abs(want).max(), order
+
+
+def test_implicit_midpoint_fixed_point_satisfies_the_implicit_equation():
+    """The 12 fixed-point sweeps (oracle and CUDA alike) must solve y+ = y + h f(t + h/2, (y + y+)/2) -- what OrdinaryDiffEq's Newton
+    iteration solves -- to round-off for CFL-limited steps."""
+    from oracle import raytrace as oray, rsw as orsw
+    from helpers import config2_setup
+    g, p, sol0, c = config2_setup(64)
+    F = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 8)
+    h = 4 * c["dt"]
+    y1 = oray.raytrace_midpoint(xk.copy(), sign, 0.0, h, F, F, g, c["f"], c["Cg"], nsub=1)
+    z = 0.5 * (xk + y1)
+    Sz = oray.sample_bilinear(F, z[:, 0], z[:, 1], g)
+    res = y1 - xk - h * oray.rhs_sampler(z, sign, 0.5, Sz, Sz, c["f"], c["Cg"])
+    assert np.abs(res).max() < 1e-13 * np.abs(xk).max()
