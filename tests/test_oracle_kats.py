@@ -462,3 +462,26 @@ def test_implicit_midpoint_fixed_point_satisfies_the_implicit_equation():
     z = 0.5 * (xk + y4)
     Sz = oray.sample_bilinear(F, z[:, 0], z[:, 1], g)
     assert np.abs(y4 - xk - 4 * h * oray.rhs_sampler(z, sign, 0.5, Sz, Sz, c["f"], c["Cg"])).max() < 1e-13 * np.abs(xk).max()
+
+
+def test_hermite_gradient_is_the_gradient_of_the_interpolant_and_hann_matches_scipy():
+    """The Hermite-bicubic mode's (ux, uy, vx) are specified as the analytic gradient of the interpolated (u, v): check against
+    centred differences of the interpolant itself.  And the periodic Hann window of the k-omega pipeline is scipy's `sym=False`."""
+    from scipy.signal import windows
+    from oracle import komega as okw, raytrace as oray, rsw as orsw
+    from helpers import config2_setup
+    assert np.allclose(okw.hann(37), windows.hann(37, sym=False), atol=1e-15)
+    g, p, sol0, c = config2_setup(64)
+    F7 = oray.get_velocity_info_cubic(orsw.get_streamfunction(sol0, g, p), g)
+    rng = np.random.default_rng(6)
+    x, y = rng.uniform(-3, 3, 200), rng.uniform(-3, 3, 200)
+    e = 1e-6 * g.dx
+    S = oray.sample_hermite(F7, x, y, g)
+    dudx = (oray.sample_hermite(F7, x + e, y, g)[:, 0] - oray.sample_hermite(F7, x - e, y, g)[:, 0]) / (2 * e)
+    dudy = (oray.sample_hermite(F7, x, y + e, g)[:, 0] - oray.sample_hermite(F7, x, y - e, g)[:, 0]) / (2 * e)
+    dvdx = (oray.sample_hermite(F7, x + e, y, g)[:, 1] - oray.sample_hermite(F7, x - e, y, g)[:, 1]) / (2 * e)
+    scale = np.abs(S[:, 2:]).max()
+    assert np.abs(S[:, 2] - dudx).max() < 1e-6 * scale and np.abs(S[:, 3] - dudy).max() < 1e-6 * scale
+    assert np.abs(S[:, 4] - dvdx).max() < 1e-6 * scale
+    xs, ys = np.meshgrid(g.x, g.y, indexing="ij")                       # and it reproduces the node data
+    assert np.abs(oray.sample_hermite(F7, xs.ravel(), ys.ravel(), g) - F7[:, :, :5].reshape(-1, 5)).max() < 1e-12 * np.abs(F7).max()
