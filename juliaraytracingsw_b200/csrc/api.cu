@@ -1545,6 +1545,10 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     // raytracing/TwoLayerRaytracing.jl:136-141 when kcut > 0), nsteps times, without returning to the host language
     if (!p || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
     swrt_flow* f = p->flow;
+    // everything a step can reject is checked before any step (a failure inside a graph capture would leave the clock advanced)
+    if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d (swrt_flow_set_interp)", p->d.interp, f->interp);
+    if (f->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: drive the loop from the host (slab.py)");
+    { int rc = check_psi_kind(f, psi_kind); if (rc) return rc; }
     auto body = [&]() -> int {
         int rc = swrt_flow_step(f, 1);
         if (rc) return rc;
