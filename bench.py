@@ -360,7 +360,10 @@ def run_swrt(args):
                 "share_of_step": share, **extra}
     spectral = {"steps_per_s": 1e3 / ms_flow, "ms_per_step": ms_flow, "algorithmic_bytes_per_step": 42 * F,
                 "achieved": 42 * F / (ms_flow * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 42 * F / (ms_flow * 1e-3) / 1e9 / peak,
-                "contract": "B_step = 42 F, F = 8 nx^2 bytes (SURVEY.md 8d, RSW + IFMAB3)"}
+                "contract": "B_step = 42 F, F = 8 nx^2 bytes (SURVEY.md 8d, RSW + IFMAB3)",
+                "traffic": 5.8e8 if args.nx == 2048 else None,
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one step, in situ "
+                                  "(--cache-control none), profiles/r01_n_insitu_dram_bytes_no_cache_flush.csv"}
     line = {
         "metric": "packet-steps/s", "value": value, "unit": "packet-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
