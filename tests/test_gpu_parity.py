@@ -922,3 +922,25 @@ def test_coupled_steps_entry_point_is_the_python_loop(nsteps, sort_every):
     np.testing.assert_array_equal(res[0][0], res[1][0])
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-11 * np.abs(res[0][1]).max()
     assert res[0][2] == res[1][2] and res[0][3] == res[1][3] == nsteps
+
+
+def test_bench_line_contract_small_grid():
+    """`bench.py` end to end on a small grid: one JSON line carrying every key of the measurement contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--nx", "256", "--sqrt-packets", "256", "--steps", "3", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert "workload" in d["config"] and d["dtype"] == "f64" and d["fp32_packet_mode"]["value"] > 0
