@@ -105,10 +105,11 @@ def cpu_sample(args, steps, warmup, cores):
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import config2_setup
-    from oracle import ifmab3, raytrace as oray, rsw as orsw
+    from oracle import craytrace, ifmab3, raytrace as oray, rsw as orsw
 
     nx, ntot = args.nx, args.sqrt_packets ** 2
-    nsample = min(ntot, 1 << 18)
+    use_c = craytrace.available()        # compiled, OpenMP-threaded restatement (bit-identical to the NumPy tracer): all packets
+    nsample = ntot if use_c else min(ntot, 1 << 18)
     g, p, sol, c = config2_setup(nx)
     ts = ifmab3.IFMAB3(np.zeros((1, 1, 3, 3)), c["dt"], lambda s: orsw.calcN(s, g, p))
     ts.expLdt = ifmab3.expL_closed_form(g, p, c["dt"])
@@ -131,7 +132,10 @@ def cpu_sample(args, steps, warmup, cores):
             z = xk[idx].copy()
             oray.raytrace(z, sign[idx], told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub)
             xk[idx] = z
-        list(pool.map(work, chunks))
+        if use_c:
+            craytrace.raytrace(xk, sign, told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub)
+        else:
+            list(pool.map(work, chunks))
         cend = time.perf_counter()
         Fo, told = Fn, tnew
         if it >= warmup:
@@ -141,8 +145,10 @@ def cpu_sample(args, steps, warmup, cores):
     t_step = t_flow / steps + (t_pk / steps) * (ntot / nsample)
     return dict(value=ntot / t_step, ms_per_step=1e3 * t_step, flow_ms=1e3 * t_flow / steps,
                 packet_ms_sample=1e3 * t_pk / steps, nsample=nsample,
-                sample=(f"per step: full {nx}^2 oracle flow step + velocity info, RK4 of {nsample} packets on {cores} threads "
-                        f"scaled x{ntot / nsample:.0f} to {ntot} packets; {steps} steps after {warmup} warm-up"))
+                sample=(f"per step: full {nx}^2 oracle flow step + velocity info (NumPy + threaded scipy.fft), RK4 of {nsample} packets "
+                        + ("with the C/OpenMP restatement of the oracle tracer" if use_c else "with the NumPy tracer")
+                        + f" on {cores} threads" + ("" if nsample == ntot else f" scaled x{ntot / nsample:.0f} to {ntot} packets")
+                        + f"; {steps} steps after {warmup} warm-up"))
 
 
 def run_reference(args):

@@ -485,3 +485,24 @@ def test_hermite_gradient_is_the_gradient_of_the_interpolant_and_hann_matches_sc
     assert np.abs(S[:, 4] - dvdx).max() < 1e-6 * scale
     xs, ys = np.meshgrid(g.x, g.y, indexing="ij")                       # and it reproduces the node data
     assert np.abs(oray.sample_hermite(F7, xs.ravel(), ys.ravel(), g) - F7[:, :, :5].reshape(-1, 5)).max() < 1e-12 * np.abs(F7).max()
+
+
+def test_c_restatement_of_the_tracer_is_bit_identical_to_the_numpy_oracle():
+    """oracle/c/raytrace_oracle.c (compiled, OpenMP; the tracer of bench.py's CPU legs) against oracle/raytrace.py, bit for bit,
+    both time-lerp conventions, packets far outside the periodic box included."""
+    import os
+    import subprocess
+    from oracle import craytrace, raytrace as oray, rsw as orsw
+    from helpers import config2_setup
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle", "c")], check=True, capture_output=True)
+    assert craytrace.available()
+    g, p, sol0, c = config2_setup(64)
+    Fo = oray.get_velocity_info(orsw.get_streamfunction(sol0, g, p), g)
+    Fn = np.roll(Fo, 3, axis=0) * 1.02
+    xk, sign = oray.generate_initial_wavepackets(c["L"], c["k0"], 40)
+    xk[:, 0:2] += np.random.default_rng(8).uniform(-50, 50, size=(xk.shape[0], 2))
+    for lerp in (0, 1):
+        a = oray.raytrace(xk.copy(), sign, 0.25, 0.25 + 3 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3, lerp=lerp)
+        b = craytrace.raytrace(xk.copy(), sign, 0.25, 0.25 + 3 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3, lerp=lerp)
+        np.testing.assert_array_equal(a, b)
