@@ -125,3 +125,16 @@ def test_bench_reference_arm_prints_one_contract_line():
     r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--nx", "64",
                          "--sqrt-packets", "16"], capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r2.returncode == 0 and not [ln for ln in r2.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_header_is_plain_c():
+    """include/swrt.h is the C ABI: it must compile as C99 (and as C++) on its own, with no CUDA or C++ types in the signatures."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "swrt.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)            # declarations only
+    for word in ("std::", "torch", "cudastream_t", "cudaevent_t", "double2", "at::", "template", "class "):   # no C++/CUDA/torch types
+        assert word not in code.lower(), word
