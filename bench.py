@@ -109,6 +109,9 @@ def cpu_sample(args, steps, warmup, cores):
 
     nx, ntot = args.nx, args.sqrt_packets ** 2
     use_c = craytrace.available()        # compiled, OpenMP-threaded restatement (bit-identical to the NumPy tracer): all packets
+    # the thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers) and what OpenMP grants is recorded
+    omp_threads = craytrace.threads_used(cores) if use_c else cores
+    assert omp_threads == cores, (omp_threads, cores)
     nsample = ntot if use_c else min(ntot, 1 << 18)
     g, p, sol, c = config2_setup(nx)
     ts = ifmab3.IFMAB3(np.zeros((1, 1, 3, 3)), c["dt"], lambda s: orsw.calcN(s, g, p))
@@ -133,7 +136,7 @@ def cpu_sample(args, steps, warmup, cores):
             oray.raytrace(z, sign[idx], told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub)
             xk[idx] = z
         if use_c:
-            craytrace.raytrace(xk, sign, told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub)
+            craytrace.raytrace(xk, sign, told, tnew, Fo, Fn, g, c["f"], c["Cg"], nsub=args.nsub, threads=cores)
         else:
             list(pool.map(work, chunks))
         cend = time.perf_counter()
@@ -143,7 +146,7 @@ def cpu_sample(args, steps, warmup, cores):
             t_pk += cend - b
     pool.shutdown()
     t_step = t_flow / steps + (t_pk / steps) * (ntot / nsample)
-    return dict(value=ntot / t_step, ms_per_step=1e3 * t_step, flow_ms=1e3 * t_flow / steps,
+    return dict(value=ntot / t_step, ms_per_step=1e3 * t_step, flow_ms=1e3 * t_flow / steps, omp_threads=omp_threads,
                 packet_ms_sample=1e3 * t_pk / steps, nsample=nsample,
                 sample=(f"per step: full {nx}^2 oracle flow step + velocity info (NumPy + threaded scipy.fft), RK4 of {nsample} packets "
                         + ("with the C/OpenMP restatement of the oracle tracer" if use_c else "with the NumPy tracer")

@@ -98,6 +98,7 @@ struct swrt_flow {
     double prof_ms[16] = {0};
     long long prof_n[16] = {0};
     std::vector<struct swrt_packets*> readers;   // packet handles with their own stream (snapshot writers wait for their reads)
+    int npackets = 0;                            // every packet handle attached to this flow (own stream or not)
     // CUDA graphs of the step for launch-bound grid sizes: one per ring phase (3 steps each; 1 step for the multi-stage steppers)
     cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
     long long glaunches[3] = {0, 0, 0};
@@ -151,7 +152,7 @@ struct swrt_packets {
     long long nbins = 0;
     int since_sort = 1 << 30;   // raytrace calls since the last sort
     bool permuted = false;
-    cudaStream_t st = nullptr;      // the flow's stream, or the handle's own (swrt_packets_use_own_stream)
+    cudaStream_t st = nullptr;      // the handle's own stream (swrt_packets_use_own_stream); otherwise pst() resolves the flow's
     bool own = false;
     cudaEvent_t ev_done = nullptr;  // last read of the flow's snapshots by this handle
     // CUDA graphs of six coupled steps (ring period 3 x snapshot-slot period 2), one per parity of the sort's double buffer
@@ -159,6 +160,9 @@ struct swrt_packets {
     Cycle cycle[2];
 };
 static inline cudaEvent_t packets_done_event(const swrt_packets* p) { return p->ev_done; }
+// The stream a packet handle launches on: its own (swrt_packets_use_own_stream) or -- resolved at every use, because
+// swrt_flow_set_stream may replace it after the handle was created -- the flow's.
+static inline cudaStream_t pst(const swrt_packets* p) { return p->own ? p->st : p->flow->st; }
 
 struct swrt_series {
     swrt_flow* flow = nullptr;
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ 
             const double w = (kr == 0 || kr == L.nx / 2) ? 1.0 : 2.0;
             acc += w * (v.x * v.x + v.y * v.y);
         } else if (mode == 1) {
-            acc = fmax(acc, fabs(a[i]));
+            const double x = fabs(a[i]);
+            acc = (x > acc || x != x) ? x : acc;      // NaN sticks (maximum(abs.(u)) of a blown-up field is NaN in the reference)
         } else {
             acc += isnan(a[i]) ? 1.0 : 0.0;
         }
@@ -212,7 +217,10 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ 
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = mode == 1 ? fmax(sh[threadIdx.x], sh[threadIdx.x + s]) : sh[threadIdx.x] + sh[threadIdx.x + s];
+        if (threadIdx.x < s) {
+            const double a0 = sh[threadIdx.x], a1 = sh[threadIdx.x + s];
+            sh[threadIdx.x] = mode == 1 ? ((a0 != a0 || a1 != a1) ? a0 + a1 : (a1 > a0 ? a1 : a0)) : a0 + a1;
+        }
         __syncthreads();
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
@@ -300,7 +308,7 @@ static double reduce_host(swrt_flow* h, const double* a, long long n, int mode, 
     if (*err != cudaSuccess) return 0;
     *err = cudaStreamSynchronize(h->st);
     double acc = 0;
-    for (double p : part) acc = mode == 1 ? std::fmax(acc, p) : acc + p;
+    for (double p : part) acc = mode == 1 ? ((acc != acc || p != p) ? acc + p : std::max(acc, p)) : acc + p;   // NaN propagates
     return acc;
 }
 
@@ -871,7 +879,8 @@ int swrt_flow_max_abs_uv(swrt_flow* h, double* umax, double* vmax) {
         for (int layer = 0; layer < (qg ? h->nvar : 1); ++layer) {   // QG: u = -psi_y, v = psi_x of every layer
             int rc = spectral_to_physical(h, qg ? (v == 0 ? SWRT_FIELD_QG_U : SWRT_FIELD_QG_V) + layer : v + uv0, h->phys);
             if (rc) return rc;
-            *outs[v] = std::fmax(*outs[v], reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e));
+            const double m = reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e);
+            *outs[v] = (m != m || *outs[v] != *outs[v]) ? m + *outs[v] : std::max(*outs[v], m);
             CK(e);
         }
     }
@@ -1107,33 +1116,43 @@ int swrt_flow_set_snapshot_refinement(swrt_flow* h, int refine) {
     if (refine != 1 && refine != 2) return fail(SWRT_ERR_ARG, "refinement must be 1 or 2");
     if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow");
     if (!supported_n(refine * h->d.nx) || !supported_n(refine * h->d.ny)) return fail(SWRT_ERR_UNSUPPORTED, "refined grid %d x %d exceeds the supported sizes", refine * h->d.nx, refine * h->d.ny);
-    if (!h->readers.empty()) return fail(SWRT_ERR_STATE, "set the refinement before creating packet handles");
+    if (h->npackets > 0) return fail(SWRT_ERR_STATE, "set the refinement before creating packet handles (%d attached)", h->npackets);
     CK(cudaSetDevice(h->d.device));
     CK(cudaStreamSynchronize(h->st));
-    cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys);
-    h->psih_s = h->Gs = h->tw_xs = h->tw_ys = nullptr;
-    h->refine = refine;
+    // allocate everything first: a failing allocation leaves the handle exactly as it was
     const size_t nodes = (size_t)refine * h->d.nx * (size_t)refine * h->d.ny;
-    for (int lev = 0; lev < 2; ++lev) {
-        cudaFree(h->snap[lev]);
-        h->snap[lev] = nullptr;
-        CK(cudaMalloc(&h->snap[lev], sizeof(double) * nodes * SNAP3_STRIDE));
-        CK(cudaMemset(h->snap[lev], 0, sizeof(double) * nodes * SNAP3_STRIDE));
+    double* nsnap[2] = {nullptr, nullptr};
+    double2 *npsi = nullptr, *nG = nullptr, *ntx = nullptr, *nty = nullptr;
+    SpecLayout Ls = h->L;
+    cudaError_t e = cudaSuccess;
+    for (int lev = 0; lev < 2 && e == cudaSuccess; ++lev) {
+        e = cudaMalloc(&nsnap[lev], sizeof(double) * nodes * SNAP3_STRIDE);
+        if (e == cudaSuccess) e = cudaMemset(nsnap[lev], 0, sizeof(double) * nodes * SNAP3_STRIDE);
     }
-    if (refine > 1) {
-        SpecLayout& Ls = h->Ls;
-        Ls = h->L;
+    if (refine > 1 && e == cudaSuccess) {
         Ls.nx = refine * h->d.nx; Ls.ny = refine * h->d.ny;
         Ls.lz1 = Ls.ny - (h->L.ny - h->L.lz1);      // the negative-l rows keep their distance from the end
         Ls.vs = (long long)Ls.ny * Ls.kr_pad;
         Ls.yrows = Ls.ny;
         Ls.yshift = 0; while ((1 << Ls.yshift) < Ls.ny) ++Ls.yshift;
         const size_t fb = sizeof(double2) * (size_t)Ls.vs;
-        CK(cudaMalloc(&h->psih_s, fb)); CK(cudaMemset(h->psih_s, 0, fb));
-        CK(cudaMalloc(&h->Gs, 3 * fb)); CK(cudaMemset(h->Gs, 0, 3 * fb));
-        CK(upload_twiddles(Ls.nx, &h->tw_xs));
-        CK(upload_twiddles(Ls.ny, &h->tw_ys));
+        e = cudaMalloc(&npsi, fb);
+        if (e == cudaSuccess) e = cudaMemset(npsi, 0, fb);
+        if (e == cudaSuccess) e = cudaMalloc(&nG, 3 * fb);
+        if (e == cudaSuccess) e = cudaMemset(nG, 0, 3 * fb);
+        if (e == cudaSuccess) e = upload_twiddles(Ls.nx, &ntx);
+        if (e == cudaSuccess) e = upload_twiddles(Ls.ny, &nty);
     }
+    if (e != cudaSuccess) {
+        cudaFree(nsnap[0]); cudaFree(nsnap[1]); cudaFree(npsi); cudaFree(nG); cudaFree(ntx); cudaFree(nty);
+        return fail(SWRT_ERR_CUDA, "snapshot refinement: %s", cudaGetErrorString(e));
+    }
+    cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys);
+    cudaFree(h->snap[0]); cudaFree(h->snap[1]);
+    h->snap[0] = nsnap[0]; h->snap[1] = nsnap[1];
+    h->psih_s = npsi; h->Gs = nG; h->tw_xs = ntx; h->tw_ys = nty;
+    h->refine = refine;
+    if (refine > 1) h->Ls = Ls;
     return SWRT_OK;
 }
 int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny) {
@@ -1252,9 +1271,10 @@ int swrt_packets_destroy(swrt_packets* p) {
     if (!p) return SWRT_OK;
     if (p->flow) {
         cudaSetDevice(p->flow->d.device);
-        cudaStreamSynchronize(p->st);
+        cudaStreamSynchronize(pst(p));
         auto& rd = p->flow->readers;
         rd.erase(std::remove(rd.begin(), rd.end(), p), rd.end());
+        p->flow->npackets--;
         for (auto& c : p->cycle) if (c.exec) cudaGraphExecDestroy(c.exec);
         if (p->own) cudaStreamDestroy(p->st);
         if (p->ev_done) cudaEventDestroy(p->ev_done);
@@ -1281,7 +1301,7 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     swrt_packets* p = new swrt_packets;
     p->d = *desc;
     p->flow = flow;
-    p->st = flow->st;
+    flow->npackets++;
     p->nbins = (long long)flow->refine * flow->d.nx * flow->refine * flow->d.ny;   // cells of the snapshots' node grid
     const size_t n = (size_t)desc->n;
     const size_t nsums = (size_t)(p->nbins / SCAN_BLOCK + 2) + (size_t)(p->nbins / SCAN_BLOCK / SCAN_BLOCK + 2) + 8;
@@ -1295,11 +1315,11 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
         swrt_packets_destroy(p);
         return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
     }
-    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, p->st));
-    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, p->st));
-    { ProfScope ps(flow, K_OTHER, p->st); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->idx, (long long)n); }
+    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, pst(p)));
+    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, pst(p)));
+    { ProfScope ps(flow, K_OTHER, pst(p)); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->idx, (long long)n); }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(p->st));
+    CK(cudaStreamSynchronize(pst(p)));
     *out = p;
     return SWRT_OK;
 }
@@ -1316,9 +1336,9 @@ static cudaError_t wait_flow(swrt_packets* p) {
     if (!p->own) return cudaSuccess;
     swrt_flow* f = p->flow;
     cudaError_t e = cudaEventRecord(f->ev_sync, f->st);
-    return e != cudaSuccess ? e : cudaStreamWaitEvent(p->st, f->ev_sync, 0);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(pst(p), f->ev_sync, 0);
 }
-static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(p->ev_done, p->st) : cudaSuccess; }
+static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(p->ev_done, pst(p)) : cudaSuccess; }
 
 int swrt_packets_use_own_stream(swrt_packets* p) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
@@ -1336,7 +1356,7 @@ int swrt_packets_use_own_stream(swrt_packets* p) {
 int swrt_packets_sync(swrt_packets* p) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(p->flow->d.device));
-    CK(cudaStreamSynchronize(p->st));
+    CK(cudaStreamSynchronize(pst(p)));
     return SWRT_OK;
 }
 
@@ -1347,17 +1367,17 @@ static int packets_set_impl(swrt_packets* p, const double* xk_host, long long ld
     const long long n = p->d.n;
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
     if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
-        { ProfScope ps(f, K_OTHER, p->st); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->sign, p->idx, n, 1, p->sign2); }
+        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->sign, p->idx, n, 1, p->sign2); }
         CK(cudaGetLastError());
         std::swap(p->sign, p->sign2);
     }
-    CK(copy_cols(p->xk, xk_host, n, 4, ld, cudaMemcpyHostToDevice, p->st));
-    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, p->st));
-    { ProfScope ps(f, K_OTHER, p->st); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->idx, n); }
+    CK(copy_cols(p->xk, xk_host, n, 4, ld, cudaMemcpyHostToDevice, pst(p)));
+    if (sign_host) CK(cudaMemcpyAsync(p->sign, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, pst(p)));
+    { ProfScope ps(f, K_OTHER, pst(p)); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->idx, n); }
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
-    if (sync) CK(cudaStreamSynchronize(p->st));
+    if (sync) CK(cudaStreamSynchronize(pst(p)));
     return SWRT_OK;
 }
 int swrt_packets_set(swrt_packets* p, const double* xk_host, const double* sign_host) {
@@ -1375,12 +1395,12 @@ static int packets_get_impl(swrt_packets* p, double* xk_host, long long ld, bool
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
     const double* src = p->xk;
     if (p->permuted) {
-        { ProfScope ps(f, K_OTHER, p->st); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, p->idx, n, 4, p->xk2); }
+        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->idx, n, 4, p->xk2); }
         CK(cudaGetLastError());
         src = p->xk2;
     }
-    CK(copy_cols(xk_host, src, n, 4, ld, cudaMemcpyDeviceToHost, p->st));
-    if (sync) CK(cudaStreamSynchronize(p->st));
+    CK(copy_cols(xk_host, src, n, 4, ld, cudaMemcpyDeviceToHost, pst(p)));
+    if (sync) CK(cudaStreamSynchronize(pst(p)));
     return SWRT_OK;
 }
 int swrt_packets_get(swrt_packets* p, double* xk_host) { return packets_get_impl(p, xk_host, p ? p->d.n : 0, true); }
@@ -1390,7 +1410,7 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
     if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->flow->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(p->flow, K_OTHER, p->st); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
+    { ProfScope ps(p->flow, K_OTHER, pst(p)); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
@@ -1410,14 +1430,14 @@ static cudaError_t exclusive_scan(swrt_packets* p, unsigned* a, long long nb, un
     swrt_flow* f = p->flow;
     const unsigned blocks = (unsigned)((nb + SCAN_BLOCK - 1) / SCAN_BLOCK);
     if (blocks <= 1) {
-        ProfScope ps(f, K_SORT, p->st);
-        scan_block_kernel<<<1, SCAN_BLOCK, 0, p->st>>>(a, nb, nullptr);
+        ProfScope ps(f, K_SORT, pst(p));
+        scan_block_kernel<<<1, SCAN_BLOCK, 0, pst(p)>>>(a, nb, nullptr);
         return cudaGetLastError();
     }
-    { ProfScope ps(f, K_SORT, p->st); scan_block_kernel<<<blocks, SCAN_BLOCK, 0, p->st>>>(a, nb, scratch); }
+    { ProfScope ps(f, K_SORT, pst(p)); scan_block_kernel<<<blocks, SCAN_BLOCK, 0, pst(p)>>>(a, nb, scratch); }
     cudaError_t e = exclusive_scan(p, scratch, blocks, scratch + blocks);
     if (e != cudaSuccess) return e;
-    { ProfScope ps(f, K_SORT, p->st); scan_add_kernel<<<blocks, SCAN_BLOCK, 0, p->st>>>(a, nb, scratch); }
+    { ProfScope ps(f, K_SORT, pst(p)); scan_add_kernel<<<blocks, SCAN_BLOCK, 0, pst(p)>>>(a, nb, scratch); }
     return cudaGetLastError();
 }
 
@@ -1426,11 +1446,11 @@ static int sort_packets(swrt_packets* p) {
     swrt_flow* f = p->flow;
     const long long n = p->d.n;
     const unsigned blocks = (unsigned)((n + 255) / 256);
-    CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, p->st));
-    { ProfScope ps(f, K_SORT, p->st); sort_hist_kernel<<<blocks, 256, 0, p->st>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
+    CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, pst(p)));
+    { ProfScope ps(f, K_SORT, pst(p)); sort_hist_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
     CK(cudaGetLastError());
     CK(exclusive_scan(p, p->hist, p->nbins, p->sums));
-    { ProfScope ps(f, K_SORT, p->st); sort_scatter_kernel<<<blocks, 256, 0, p->st>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
+    { ProfScope ps(f, K_SORT, pst(p)); sort_scatter_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
     CK(cudaGetLastError());
     std::swap(p->xk, p->xk2);
     std::swap(p->sign, p->sign2);
@@ -1459,15 +1479,15 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
-    { ProfScope ps(f, K_RAYTRACE, p->st);
-#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
+    { ProfScope ps(f, K_RAYTRACE, pst(p));
+#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
       if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
           static const int fminb = [] { const char* e = getenv("SWRT_RAYTRACE_F32_MINB"); return e ? atoi(e) : 6; }();
           const float4 *Fo = reinterpret_cast<const float4*>(So), *Fn = reinterpret_cast<const float4*>(Sn);
-          if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else if (fminb == 5) raytrace_rk4_f32_kernel<5><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else if (fminb == 6) raytrace_rk4_f32_kernel<6><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else if (fminb == 5) raytrace_rk4_f32_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else if (fminb == 6) raytrace_rk4_f32_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
       }
       else if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
           if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else if (p->d.interp == 2) SWRT_GEN(2, 1); else SWRT_GEN(4, 1);
@@ -1475,12 +1495,12 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
-      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else raytrace_rk4_kernel<6><<<grid, 128, 0, p->st>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
+      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else raytrace_rk4_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
     CK(cudaGetLastError());
     CK(mark_read(p));
     p->since_sort++;
@@ -1496,24 +1516,24 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     CK(wait_flow(p));
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
     if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
-        ProfScope ps(f, K_SAMPLE, p->st);
-        sample_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, reinterpret_cast<const float4*>(f->snap[f->slot_map[slot]]), packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, pst(p));
+        sample_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, reinterpret_cast<const float4*>(f->snap[f->slot_map[slot]]), packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_BSPLINE3) {
-        ProfScope ps(f, K_SAMPLE, p->st);
-        sample_generic_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, pst(p));
+        sample_generic_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_BSPLINE2) {
-        ProfScope ps(f, K_SAMPLE, p->st);
-        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, pst(p));
+        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
-        ProfScope ps(f, K_SAMPLE, p->st);
-        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
+        ProfScope ps(f, K_SAMPLE, pst(p));
+        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
     } else
-    { ProfScope ps(f, K_SAMPLE, p->st); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, p->st>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
+    { ProfScope ps(f, K_SAMPLE, pst(p)); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
     CK(cudaGetLastError());
     CK(mark_read(p));
-    CK(copy_cols(u_host, p->U, n, 2, ld, cudaMemcpyDeviceToHost, p->st));
-    if (g_host) CK(copy_cols(g_host, p->Gd, n, 4, ld, cudaMemcpyDeviceToHost, p->st));
-    if (sync) CK(cudaStreamSynchronize(p->st));
+    CK(copy_cols(u_host, p->U, n, 2, ld, cudaMemcpyDeviceToHost, pst(p)));
+    if (g_host) CK(copy_cols(g_host, p->Gd, n, 4, ld, cudaMemcpyDeviceToHost, pst(p)));
+    if (sync) CK(cudaStreamSynchronize(pst(p)));
     return SWRT_OK;
 }
 int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host) {
@@ -1528,13 +1548,13 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
-    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), p->st));
-    { ProfScope ps(f, K_OTHER, p->st); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->st>>>(p->xk, n, kcut * kcut, k0, p->count); }
+    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), pst(p)));
+    { ProfScope ps(f, K_OTHER, pst(p)); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, n, kcut * kcut, k0, p->count); }
     CK(cudaGetLastError());
     if (nreset) {   // the count is only fetched (and the stream only synchronised) when the caller asks for it
         unsigned long long c = 0;
-        CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, p->st));
-        CK(cudaStreamSynchronize(p->st));
+        CK(cudaMemcpyAsync(&c, p->count, sizeof c, cudaMemcpyDeviceToHost, pst(p)));
+        CK(cudaStreamSynchronize(pst(p)));
         *nreset = (long long)c;
     }
     return SWRT_OK;
@@ -1565,10 +1585,11 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
     const int period = 6;
     const bool ring_stepper = f->d.stepper == SWRT_IFMAB3 || f->d.stepper == SWRT_FILTEREDAB3;
-    const bool eligible = graph_mode > 0 && !f->prof && !p->own && f->P == 1 && f->refine == 1 &&
+    // (other handles reading the snapshots on their own streams need the event waits a replay would skip: no graph then)
+    const bool eligible = graph_mode > 0 && !f->prof && !p->own && f->readers.empty() && f->P == 1 && f->refine == 1 &&
                           (graph_mode > 1 || (long long)f->d.nx * f->d.ny <= 1024LL * 1024LL);
     for (int s = 0; s < nsteps;) {
-        const bool aligned = f->step >= 3 && f->slot_map[0] == 0 && (!ring_stepper || f->ring == 0);
+        const bool aligned = f->step >= 3 && f->slot_map[0] == 0 && f->slot_map[1] == 1 && (!ring_stepper || f->ring == 0);   // (aliased slots {0,0} run un-captured)
         const bool sort_inside = p->d.sort_every > 0 && p->since_sort + period > p->d.sort_every;
         if (eligible && aligned && !sort_inside && nsteps - s >= period && p->nbins == (long long)f->d.nx * f->d.ny) {
             swrt_packets::Cycle& c = p->cycle[p->xk < p->xk2 ? 0 : 1];

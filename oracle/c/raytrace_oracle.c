@@ -9,6 +9,9 @@
  * Arrays are NumPy C-order: xk (n, 4), F_old / F_new (nx, ny, 5) = u, v, ux, uy, vx.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static inline void cell_index(double x, double x0, double dx, long long n, long long* i, double* a) {
     const double s = (x - x0) / dx, fl = floor(s);
@@ -47,8 +50,12 @@ static inline void rhs(const double* s, double sign, double alpha, const double*
 }
 
 void oracle_raytrace_rk4(double* xk, const double* sign, long long n, double t0, double t1, const double* Fo, const double* Fn, long long nx,
-                         long long ny, double x0, double y0, double dx, double dy, double f, double Cg, int nsub, int lerp) {
+                         long long ny, double x0, double y0, double dx, double dy, double f, double Cg, int nsub, int lerp, int threads) {
     const double h = (t1 - t0) / nsub;
+    /* `threads` > 0 is passed explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which must not decide the baseline */
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
 #pragma omp parallel for schedule(static)
     for (long long p = 0; p < n; ++p) {
         double* s = xk + 4 * p;
@@ -65,4 +72,21 @@ void oracle_raytrace_rk4(double* xk, const double* sign, long long n, double t0,
             for (int c = 0; c < 4; ++c) s[c] += (h / 6) * (k1[c] + 2 * k2[c] + 2 * k3[c] + k4[c]);
         }
     }
+}
+
+/* number of threads the next parallel region will use (what bench.py records in cpu_baseline.cores) */
+int oracle_raytrace_threads(int threads) {
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp master
+        n = omp_get_num_threads();
+    }
+    return n;
+#else
+    (void)threads;
+    return 1;
+#endif
 }

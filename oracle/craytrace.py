@@ -25,17 +25,25 @@ def _load():
         _lib.oracle_raytrace_rk4.restype = None
         _lib.oracle_raytrace_rk4.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                              C.c_longlong, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
-                                             C.c_double, C.c_int, C.c_int]
+                                             C.c_double, C.c_int, C.c_int, C.c_int]
+        _lib.oracle_raytrace_threads.restype = C.c_int
+        _lib.oracle_raytrace_threads.argtypes = [C.c_int]
     return _lib
 
 
-def raytrace(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, lerp=0):
-    """In place on a C-contiguous (N, 4) float64 array; threads = OMP_NUM_THREADS (default: all cores)."""
+def threads_used(threads=0):
+    """OpenMP threads the tracer runs on when asked for `threads` (0 = the OpenMP default, i.e. OMP_NUM_THREADS or all cores)."""
+    return int(_load().oracle_raytrace_threads(int(threads)))
+
+
+def raytrace(xk, sign, t0, t1, F_old, F_new, grid, f, Cg, nsub=1, lerp=0, threads=0):
+    """In place on a C-contiguous (N, 4) float64 array; `threads` > 0 sets the OpenMP thread count explicitly (0 = OpenMP's
+    default, which follows OMP_NUM_THREADS -- torchrun exports OMP_NUM_THREADS=1 to its workers)."""
     assert xk.flags.c_contiguous and xk.dtype == np.float64 and xk.shape[1] == 4
     sign = np.ascontiguousarray(sign, dtype=np.float64)
     Fo, Fn = np.ascontiguousarray(F_old, dtype=np.float64), np.ascontiguousarray(F_new, dtype=np.float64)
     assert Fo.shape == (grid.nx, grid.ny, 5) and Fn.shape == Fo.shape
     _load().oracle_raytrace_rk4(xk.ctypes.data, sign.ctypes.data, xk.shape[0], float(t0), float(t1), Fo.ctypes.data, Fn.ctypes.data,
                                 grid.nx, grid.ny, float(grid.x[0]), float(grid.y[0]), float(grid.dx), float(grid.dy), float(f), float(Cg),
-                                int(nsub), int(lerp))
+                                int(nsub), int(lerp), int(threads))
     return xk
