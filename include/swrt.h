@@ -221,6 +221,11 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
 /* raytrace!(tmpl, v_old, v_new, g_old, g_new, grid, packets, dt, (t0,t1), params) raytracing/GPURaytracing.jl:115-142,
  * reading the flow's snapshot slots 0 (old) and 1 (new) */
 int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
+/* Which ray kernel integrates the fp64 bilinear RK4 mode (raytracing/GPURaytracing.jl:32-65 dxkdt + :137 solve): SWRT_RAYKERNEL_AUTO
+ * (default; the environment knobs of DESIGN.md apply), SWRT_RAYKERNEL_CACHED (per-thread stencil cache, gathers through L1/L2) or
+ * SWRT_RAYKERNEL_TILE (one CTA per sort tile, node records staged in shared memory by TMA).  Same arithmetic, bit-identical results. */
+enum { SWRT_RAYKERNEL_AUTO = -1, SWRT_RAYKERNEL_CACHED = 0, SWRT_RAYKERNEL_TILE = 1 };
+int swrt_packets_set_kernel(swrt_packets* p, int kernel);
 /* interpolate_velocity! / interpolate_gradients! :67-109 + Array: u_host (N,2), g_host (N,4) or NULL */
 int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host);
 /* k-cutoff reset raytracing/GPUTwoLayerRaytracing.jl:136-138 */

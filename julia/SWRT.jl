@@ -220,6 +220,7 @@ get_packets_async!(p::Packets, xk::Ptr{Cdouble}, ld::Integer) =
     check(ccall((:swrt_packets_get_async, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong), p.h, xk, ld))
 sample_async!(p::Packets, slot::Integer, U::Ptr{Cdouble}, G::Ptr{Cdouble}, ld::Integer) =
     check(ccall((:swrt_packets_sample_async, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Clonglong), p.h, slot, U, G, ld))
+set_kernel!(p::Packets, kernel::Integer) = check(ccall((:swrt_packets_set_kernel, libswrt), Cint, (Ptr{Cvoid}, Cint), p.h, kernel))
 sync!(p::Packets) = check(ccall((:swrt_packets_sync, libswrt), Cint, (Ptr{Cvoid},), p.h))
 "the hot loop (stepforward!; get_velocity_info; raytrace!; old = new) nsteps times in one ccall"
 coupled_steps!(p::Packets, nsteps::Integer; psi_kind = 0, k_cutoff = 0.0, k0 = 0.0) =

@@ -92,6 +92,7 @@ SIGNATURES = {
     "swrt_packets_get": (_I, [_P, _P]),
     "swrt_packets_generate": (_I, [_P, _D, _D, _LL, _LL]),
     "swrt_packets_raytrace": (_I, [_P, _D, _D]),
+    "swrt_packets_set_kernel": (_I, [_P, _I]),
     "swrt_packets_sample": (_I, [_P, _I, _P, _P]),
     "swrt_packets_kcutoff_reset": (_I, [_P, _D, _D, _PLL]),
     "swrt_series_create": (_I, [_P, _I, _I, _LL, C.POINTER(_P)]),

@@ -1,4 +1,6 @@
 // libswrt C ABI: handle management, host-side tables, kernel dispatch.  See include/swrt.h.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cmath>
 #include <complex>
@@ -77,6 +79,8 @@ struct swrt_flow {
     double* snap[2] = {nullptr, nullptr};   // S[ny][nx][6] per time level (snapshot_layout.cuh)
     int slot_map[2] = {0, 1};               // slot (0 = old, 1 = new) -> array
     int interp = 0;                         // snapshot node data: 0 bilinear (5 fields / 48 B), 1 Hermite bicubic (7 fields / 64 B)
+    CUtensorMap tmap[2];                    // TMA descriptors of the two levels viewed as [ny][nx * 6] doubles, box = one tile patch
+    bool tmap_ok = false;
     double* phys = nullptr;
     double* red = nullptr;  // reduction scratch (device)
     double2 *G2 = nullptr, *H2 = nullptr;   // slab mode: A_RECV / B_SEND (G = A_SEND, H = B_RECV)
@@ -150,6 +154,8 @@ struct swrt_packets {
     unsigned *idx = nullptr, *idx2 = nullptr, *keys = nullptr, *hist = nullptr, *sums = nullptr;
     unsigned long long* count = nullptr;
     long long nbins = 0;
+    int kernel_sel = SWRT_RAYKERNEL_AUTO;   // swrt_packets_set_kernel
+    bool tiles_valid = false;   // `hist` holds the per-key end offsets of the CURRENT packet order (set by the sort)
     int since_sort = 1 << 30;   // raytrace calls since the last sort
     bool permuted = false;
     cudaStream_t st = nullptr;      // the handle's own stream (swrt_packets_use_own_stream); otherwise pst() resolves the flow's
@@ -323,6 +329,34 @@ static int spectral_to_physical(swrt_flow* h, int which, double* dev_out) {
     return SWRT_OK;
 }
 
+// TMA descriptors for the tile kernel of the ray tracer (packets.cuh): each level of the 5-field snapshot is a 2-D tensor of
+// doubles [ny][nx * SNAP_STRIDE]; one box = the PATCH x PATCH node records around a sort tile.  cuTensorMapEncodeTiled is
+// fetched through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*swrt_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void build_tmaps(swrt_flow* h) {
+    h->tmap_ok = false;
+    const long long nx = (long long)h->refine * h->d.nx, ny = (long long)h->refine * h->d.ny;
+    if (nx < PATCH || ny < PATCH) return;
+    static swrt_encode_tiled_fn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (swrt_encode_tiled_fn)fn;
+    }();
+    if (!encode) return;
+    for (int lev = 0; lev < 2; ++lev) {
+        const cuuint64_t dims[2] = {(cuuint64_t)(nx * SNAP_STRIDE), (cuuint64_t)ny};
+        const cuuint64_t strides[1] = {(cuuint64_t)(nx * SNAP_STRIDE * sizeof(double))};
+        const cuuint32_t box[2] = {(cuuint32_t)PATCH_ROW, (cuuint32_t)PATCH}, estr[2] = {1, 1};
+        if (encode(&h->tmap[lev], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->snap[lev], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+    }
+    h->tmap_ok = true;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
 #pragma GCC visibility push(default)
@@ -442,6 +476,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
         CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));   // sized for either node record
         CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));
     }
+    build_tmaps(h);
     CKB(upload_twiddles(d.nx, &h->tw_x));
     CKB(upload_twiddles(d.ny, &h->tw_y));
 
@@ -1153,6 +1188,7 @@ int swrt_flow_set_snapshot_refinement(swrt_flow* h, int refine) {
     h->psih_s = npsi; h->Gs = nG; h->tw_xs = ntx; h->tw_ys = nty;
     h->refine = refine;
     if (refine > 1) h->Ls = Ls;
+    build_tmaps(h);
     return SWRT_OK;
 }
 int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny) {
@@ -1353,6 +1389,14 @@ int swrt_packets_use_own_stream(swrt_packets* p) {
     return SWRT_OK;
 }
 
+int swrt_packets_set_kernel(swrt_packets* p, int kernel) {
+    if (!p) return fail(SWRT_ERR_ARG, "null pointer");
+    if (kernel < SWRT_RAYKERNEL_AUTO || kernel > SWRT_RAYKERNEL_TILE) return fail(SWRT_ERR_ARG, "unknown ray kernel %d", kernel);
+    p->kernel_sel = kernel;
+    for (auto& c : p->cycle) if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }   // captured launches name the old kernel
+    return SWRT_OK;
+}
+
 int swrt_packets_sync(swrt_packets* p) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(p->flow->d.device));
@@ -1377,6 +1421,7 @@ static int packets_set_impl(swrt_packets* p, const double* xk_host, long long ld
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
+    p->tiles_valid = false;
     if (sync) CK(cudaStreamSynchronize(pst(p)));
     return SWRT_OK;
 }
@@ -1414,6 +1459,7 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
+    p->tiles_valid = false;
     return SWRT_OK;
 }
 
@@ -1457,6 +1503,7 @@ static int sort_packets(swrt_packets* p) {
     std::swap(p->idx, p->idx2);
     p->permuted = true;
     p->since_sort = 0;
+    p->tiles_valid = true;
     return SWRT_OK;
 }
 
@@ -1479,6 +1526,25 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
+    // TMA-staged tile kernel (packets.cuh): fp64 bilinear RK4, packets in sorted order, enough packets per tile to pay for the patch
+    static const int tile_mode = [] { const char* e = getenv("SWRT_RAYTRACE_TILE"); return e ? atoi(e) : 1; }();
+    static const int tile_minb = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINB"); return e ? atoi(e) : 4; }();
+    static const int tile_min_pk = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINPK"); return e ? atoi(e) : 192; }();
+    const PacketGrid pg0 = packet_grid(f);
+    const long long ntiles = (long long)(pg0.nx >> TILE_SHIFT) * (pg0.ny >> TILE_SHIFT);
+    const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode > 0 && n >= ntiles * (long long)tile_min_pk);
+    const bool use_tile = want_tile && p->d.interp == SWRT_INTERP_BILINEAR && p->d.integrator == SWRT_INTEG_RK4 && p->tiles_valid &&
+                          f->tmap_ok && ntiles > 0;
+    if (use_tile) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PATCH_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PATCH_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            attr_done = true;
+        }
+    }
     { ProfScope ps(f, K_RAYTRACE, pst(p));
 #define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
       if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
@@ -1496,8 +1562,13 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
       else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached == 3) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (use_tile) {
+          const size_t smem = 2 * (size_t)PATCH_BYTES;
+          if (tile_minb >= 4) raytrace_rk4_tile_kernel<4><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, packet_grid(f), rp);
+          else raytrace_rk4_tile_kernel<3><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, packet_grid(f), rp);
+      }
+      else if (cached == 3 && p->kernel_sel == SWRT_RAYKERNEL_AUTO) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
       else raytrace_rk4_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }

@@ -15,11 +15,20 @@
 // sampling with wrap addressing, dispersion relation with frequency sign), :67-109
 // (interpolate_velocity!/gradients!), raytracing/GPUTwoLayerRaytracing.jl:136-138 (k-cutoff).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "snapshot_layout.cuh"
 
 namespace swrt {
+
+// Sort tiles: TILE x TILE cells; the packets of one tile are contiguous after the cell sort (cell_key), which is what lets a
+// CTA of the tile kernel own one tile and stage its node records in shared memory.
+constexpr int TILE_SHIFT = 4, TILE = 1 << TILE_SHIFT;
+constexpr int TILE_MARGIN = 3;                           // cells of slack around the tile (packets drift between two sorts)
+constexpr int PATCH = TILE + 2 * TILE_MARGIN + 1;        // nodes per side of the staged patch (23)
+constexpr int PATCH_ROW = PATCH * SNAP_STRIDE;           // doubles per patch row (138 = 1104 B, a multiple of 16 B)
+constexpr int PATCH_BYTES = (PATCH * PATCH_ROW * 8 + 127) / 128 * 128;   // one level, padded to the TMA destination alignment
 
 struct PacketGrid {
     int nx, ny;
@@ -236,6 +245,170 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_cached_kernel(double* 
                                                                         const double* __restrict__ Sn, PacketGrid g, RayParams p) {
     raytrace_rk4_cached_body(xk, sign, n, So, Sn, g, p);
 }
+// ---------------------------------------------------------------- TMA-staged tile variant
+// After the cell sort the packets of one TILE x TILE block of cells are contiguous (`tile_end` = the sort's per-key end
+// offsets).  One CTA owns one tile: a single thread issues two bulk-tensor copies (cp.async.bulk.tensor.2d, one per time
+// level) that land the (TILE + 2 MARGIN + 1)^2 patch of 48-byte node records in shared memory and complete on an mbarrier;
+// while they fly the threads already fetch their first packet's state.  The 2x2x2 stencil of a packet is then filled from
+// shared memory (LDS.128, ~30 cycles) instead of L1/L2 (LDG.128, 200-600 cycles): the plain stencil-cached kernel is bound by
+// exactly that latency at 16 warps/SM (ncu long_scoreboard, profiles/r01_i).  A packet that has drifted out of the patch (more
+// than MARGIN cells since the last sort) and the tiles on the domain boundary (their patch would wrap) use the global path.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TilePatch {
+    const double* lev[2];   // shared-memory patches of the old / new level
+    int pi, pj;             // node (pi, pj) of the grid is patch node (0, 0)
+    bool staged;            // false: boundary tile, everything from global memory
+};
+
+__device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, double alpha, const double* __restrict__ So,
+                                             const double* __restrict__ Sn, const PacketGrid& g, const RayParams& p, const TilePatch& tp,
+                                             Stencil& st, double (&d)[4]) {
+    int i0, i1, j0, j1;
+    double a, b;
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    if (i0 != st.ci || j0 != st.cj) {
+        st.ci = i0;
+        st.cj = j0;
+        const unsigned ri = (unsigned)(i0 - tp.pi), rj = (unsigned)(j0 - tp.pj);   // no wrap needed: staged tiles are interior
+        if (tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1)) {
+            const int o = rj * PATCH_ROW + ri * SNAP_STRIDE;
+#pragma unroll
+            for (int lev = 0; lev < 2; ++lev) {
+                const double2* q = reinterpret_cast<const double2*>(tp.lev[lev] + o);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    st.c[lev][0][k] = q[k];
+                    st.c[lev][1][k] = q[3 + k];
+                    st.c[lev][2][k] = q[PATCH_ROW / 2 + k];
+                    st.c[lev][3][k] = q[PATCH_ROW / 2 + 3 + k];
+                }
+            }
+        } else {
+            const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+#pragma unroll
+            for (int lev = 0; lev < 2; ++lev) {
+                const double* S = lev == 0 ? So : Sn;
+#pragma unroll
+                for (int cr = 0; cr < 4; ++cr) {
+                    const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) st.c[lev][cr][k] = __ldg(q + k);
+                }
+            }
+        }
+    }
+    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
+    const double a1 = 1.0 - a, b1 = 1.0 - b;
+    const double wb[4] = {a1 * b1, a * b1, a1 * b, a * b};
+    double W[5];
+    if (wn == 0.0) {
+        const double w[4] = {wo * wb[0], wo * wb[1], wo * wb[2], wo * wb[3]};
+        corners5<false>(st.c[0], w, W);
+    } else if (wo == 0.0) {
+        const double w[4] = {wn * wb[0], wn * wb[1], wn * wb[2], wn * wb[3]};
+        corners5<false>(st.c[1], w, W);
+    } else {
+        const double w0[4] = {wo * wb[0], wo * wb[1], wo * wb[2], wo * wb[3]};
+        const double w1[4] = {wn * wb[0], wn * wb[1], wn * wb[2], wn * wb[3]};
+        corners5<false>(st.c[0], w0, W);
+        corners5<true>(st.c[1], w1, W);
+    }
+    const double k = s[2], l = s[3];
+    const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));   // Cg^2 / omega
+    d[0] = W[0] + cg * k;
+    d[1] = W[1] + cg * l;
+    d[2] = -(W[2] * k + W[4] * l);
+    d[3] = -(W[3] * k - W[2] * l);
+}
+
+constexpr int TILE_THREADS = 128;
+template <int MINB>
+__global__ void __launch_bounds__(TILE_THREADS, MINB)
+    raytrace_rk4_tile_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n, const double* __restrict__ So,
+                             const double* __restrict__ Sn, const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapN,
+                             const unsigned* __restrict__ tile_end, PacketGrid g, RayParams p) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles_x = g.nx >> TILE_SHIFT;
+    const int tile = blockIdx.x, tj = tile / tiles_x, ti = tile - tj * tiles_x;
+    const long long key0 = (long long)tile << (2 * TILE_SHIFT);
+    const long long start = tile == 0 ? 0 : (long long)tile_end[key0 - 1], end = (long long)tile_end[key0 + (TILE * TILE - 1)];
+    if (start >= end) return;                                     // empty tile (uniform over the CTA)
+    TilePatch tp;
+    tp.lev[0] = reinterpret_cast<const double*>(tile_smem);
+    tp.lev[1] = reinterpret_cast<const double*>(tile_smem + PATCH_BYTES);
+    tp.pi = ti * TILE - TILE_MARGIN;
+    tp.pj = tj * TILE - TILE_MARGIN;
+    tp.staged = tp.pi >= 0 && tp.pj >= 0 && tp.pi + PATCH <= g.nx && tp.pj + PATCH <= g.ny;
+    if (tp.staged) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, 2u * PATCH * PATCH_ROW * 8);
+            tma_load_2d(tile_smem, &mapO, tp.pi * SNAP_STRIDE, tp.pj, &bar);
+            tma_load_2d(tile_smem + PATCH_BYTES, &mapN, tp.pi * SNAP_STRIDE, tp.pj, &bar);
+        }
+    }
+    const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
+    bool waited = !tp.staged;
+    for (long long i = start + threadIdx.x; i < end; i += TILE_THREADS) {
+        // the packet state is read and written exactly once per launch: streaming accesses leave L2 to the node records
+        double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};
+        const double sg = __ldcs(sign + i);
+        if (!waited) { mbar_wait(&bar, 0); waited = true; }      // the patch has landed (first state loads overlapped the copy)
+        Stencil st;
+        st.ci = -1;
+        st.cj = -1;
+        for (int it = 0; it < p.nsub; ++it) {
+            const double t = p.t0 + it * h;
+            double k[4], acc[4], y[4];
+            ray_rhs_tile(s, sg, (t - p.t0) * inv_span, So, Sn, g, p, tp, st, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+            ray_rhs_tile(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, tp, st, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+            ray_rhs_tile(y, sg, (t + 0.5 * h - p.t0) * inv_span, So, Sn, g, p, tp, st, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+            const double a4 = it == p.nsub - 1 ? 1.0 : (t + h - p.t0) * inv_span;
+            ray_rhs_tile(y, sg, a4, So, Sn, g, p, tp, st, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+        }
+        __stcs(xk + i, s[0]);
+        __stcs(xk + n + i, s[1]);
+        __stcs(xk + 2 * n + i, s[2]);
+        __stcs(xk + 3 * n + i, s[3]);
+    }
+    // (thread 0 always owns packet `start` and waits for the copy above, so the CTA never retires with a copy in flight)
+}
+
 // ---------------------------------------------------------------- Hermite-bicubic mode
 // u, v interpolated from (f, f_x, f_y, f_xy) node data (utils/CUDAInterpolations.jl:39-53,71-108); the gradient that enters
 // dk/dt is the analytic gradient of that interpolant.  Node record (snapshot_layout.cuh): u, v, ux, uy, vx, uxy, vxy, pad.
@@ -692,7 +865,7 @@ __device__ __forceinline__ unsigned cell_key(double x, double y, const PacketGri
     double a;
     cell(x, g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(y, g.y0, g.inv_dy, g.ny, j0, j1, a);
-    return (unsigned)((((j0 >> 3) * (g.nx >> 3) + (i0 >> 3)) << 6) + ((j0 & 7) << 3) + (i0 & 7));
+    return (unsigned)((((j0 >> TILE_SHIFT) * (g.nx >> TILE_SHIFT) + (i0 >> TILE_SHIFT)) << (2 * TILE_SHIFT)) + ((j0 & (TILE - 1)) << TILE_SHIFT) + (i0 & (TILE - 1)));
 }
 
 __global__ void sort_hist_kernel(const double* __restrict__ xk, long long n, PacketGrid g, unsigned* __restrict__ keys,

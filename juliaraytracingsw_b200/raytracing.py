@@ -17,6 +17,7 @@ PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
 INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32, INTERP_BSPLINE3 = 0, 1, 2, 3, 4
 INTEG_RK4, INTEG_IMPLICIT_MIDPOINT = 0, 1
+RAYKERNEL_AUTO, RAYKERNEL_CACHED, RAYKERNEL_TILE = -1, 0, 1
 
 
 class Velocity:
@@ -112,6 +113,10 @@ class Packets:
         assert out.shape == (self.n, 4) and out.flags.f_contiguous and out.dtype == np.float64
         check(lib().swrt_packets_get(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def set_kernel(self, kernel):
+        """RAYKERNEL_AUTO (-1), RAYKERNEL_CACHED (0) or RAYKERNEL_TILE (1): see swrt_packets_set_kernel."""
+        check(lib().swrt_packets_set_kernel(self._h, int(kernel)))
 
     def generate(self, L, k0, sqrtN, first=0):
         check(lib().swrt_packets_generate(self._h, L, k0, int(sqrtN), int(first)))

@@ -1,5 +1,6 @@
-"""Time the ray kernel variants selected by SWRT_RAYTRACE_CACHE (read once per process): run as
-`SWRT_RAYTRACE_CACHE=k python profiles/ray_variants.py` -- prints the average launch time from the library's CUDA-event profile."""
+"""A/B of the ray kernels on the bench workload (RSW nx^2, sq^2 packets at uniformly random positions): per kernel selected
+with swrt_packets_set_kernel, the average launch time from the library's CUDA-event profile over 32 coupled steps (two sort
+periods) and a checksum (the kernels are bit-identical).  `python profiles/ray_variants.py [cached tile ...]`."""
 import os
 import sys
 
@@ -10,22 +11,30 @@ from juliaraytracingsw_b200 import drivers, raytracing  # noqa: E402
 
 nx = int(os.environ.get("NX", 2048))
 sq = int(os.environ.get("SQ", 4096))
+lattice = int(os.environ.get("LATTICE", 0))
+names = sys.argv[1:] or ["cached", "tile"]
 P = drivers.Parameters(nx=nx, sqrtNpackets=sq)
 prob, _ = drivers.initialize_problem(P)
-pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
-xk = pk.get()
-xk[:, 0:2] = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(P.Npackets, 2))
-pk.set(xk)
-raytracing.get_velocity_info(prob, 0)
-t = 0.0
-for _ in range(4):
-    t = drivers.coupled_step(prob, pk, t)
-prob.sync()
-prob.profile(2)
-for _ in range(20):
-    t = drivers.coupled_step(prob, pk, t)
-prob.sync()
-rep = prob.profile_report()
-r = rep["raytrace_rk4_kernel"]
-print("variant", os.environ.get("SWRT_RAYTRACE_CACHE", "default"), "sgrid", os.environ.get("SWRT_RAYTRACE_SGRID", "1"),
-      "raytrace ms %.4f" % r["ms_avg"], "checksum %.15e" % float(np.abs(pk.get()).sum()))
+for name in names:
+    pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
+    pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "auto": raytracing.RAYKERNEL_AUTO}[name])
+    if not lattice:
+        xk = pk.get()
+        xk[:, 0:2] = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(P.Npackets, 2))
+        pk.set(xk)
+        del xk
+    raytracing.get_velocity_info(prob, 0)
+    t = prob.clock.t
+    for _ in range(4):
+        t = drivers.coupled_step(prob, pk, t)
+    prob.sync()
+    prob.profile(2)
+    for _ in range(32):
+        t = drivers.coupled_step(prob, pk, t)
+    prob.sync()
+    rep = prob.profile_report()
+    prob.profile(0)
+    r = rep["raytrace_rk4_kernel"]
+    print("kernel", name, "nx", nx, "packets", P.Npackets, "raytrace ms %.4f" % r["ms_avg"], "sort ms/launch %.4f x %d" %
+          (rep["packet_sort_kernels"]["ms_avg"], rep["packet_sort_kernels"]["launches"]), "checksum %.15e" % float(np.abs(pk.get()).sum()), flush=True)
+    pk.close()
