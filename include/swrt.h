@@ -152,7 +152,8 @@ int swrt_series_spectrum(swrt_series* s, int which, void* spectrum_host);
  * The exchange buffers are owned by the handle; swrt_slab_buffer returns their device pointers so that the caller's
  * communication library can work on them in place.  swrt_flow_set_stream makes the handle launch on the caller's stream
  * (e.g. torch's current stream) so that kernels and collectives are ordered without host synchronisation. */
-enum { SWRT_SLAB_A_SEND = 0, SWRT_SLAB_A_RECV = 1, SWRT_SLAB_B_SEND = 2, SWRT_SLAB_B_RECV = 3, SWRT_SLAB_SNAP0 = 4, SWRT_SLAB_SNAP1 = 5 };
+enum { SWRT_SLAB_A_SEND = 0, SWRT_SLAB_A_RECV = 1, SWRT_SLAB_B_SEND = 2, SWRT_SLAB_B_RECV = 3, SWRT_SLAB_SNAP0 = 4, SWRT_SLAB_SNAP1 = 5,
+       SWRT_SLAB_FLAGS = 6, SWRT_SLAB_BAND = 7 };
 int swrt_flow_set_stream(swrt_flow* h, void* cuda_stream);
 int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbytes);
 /* elements (complex128) per destination of the two all-to-alls for njobs jobs, rows per rank, columns per rank */
@@ -173,6 +174,28 @@ int swrt_slab_stage_b(swrt_flow* h);
 int swrt_slab_stage_c(swrt_flow* h);
 int swrt_slab_psi_a(swrt_flow* h, int psi_kind);
 int swrt_slab_snap_b(swrt_flow* h, int slot);
+
+/* ---- team mode: the slab step and the coupled loop driven natively, no communication library on the data path ------------
+ * With the peers' receive buffers, barrier flags (SWRT_SLAB_FLAGS) and band snapshots (SWRT_SLAB_BAND) mapped through
+ * swrt_slab_ipc_handle / swrt_slab_ipc_open, the host language only distributes 64-byte handles once (MPI.jl, sockets, files,
+ * torch.distributed ...); after that
+ *   swrt_slab_barrier        stream-ordered barrier: a one-CTA kernel stores this rank's epoch into every peer's flag word over
+ *                            NVLink and spins until all peers' epochs have arrived (mode 1: stream synchronise + the caller's
+ *                            host barrier -- for processes sharing one GPU, where a spinning kernel would starve the peers)
+ *   swrt_slab_step           = stepforward!(prob, [], n) of the slab-decomposed problem (stage a, barrier, stage b, barrier, stage c)
+ *   swrt_slab_band_snapshot  = get_streamfunction! + get_velocity_info (rsw/RSWRaytracingDriver.jl:56-67,
+ *                            raytracing/RaytracingDriver.jl:132-154) for THIS RANK'S BAND of ny/P rows plus `halo` rows of each
+ *                            neighbour: packets are sharded by y-band (swrt_packets_desc.band_*), so no rank ever needs the
+ *                            whole field and the all-gather of the round-1 design is gone.
+ * Packets of such a flow live on the rank whose band holds them and are handed over at every re-sort (sort_every); set / get /
+ * generate / sample / raytrace / coupled_steps keep their meaning on the caller-order block of each rank and become COLLECTIVE
+ * calls (every rank of the team must make them in the same order).  swrt_flow_get_snapshot / set_snapshot move the rank's own
+ * band, an (nx, ny/P, 5) array. */
+int swrt_slab_set_barrier(swrt_flow* h, int mode, void (*callback)(void*), void* arg);
+int swrt_slab_barrier(swrt_flow* h);
+int swrt_slab_step(swrt_flow* h, int nsteps);
+int swrt_slab_band_snapshot(swrt_flow* h, int psi_kind, int slot);
+int swrt_slab_band_info(swrt_flow* h, int* row0, int* rows, int* halo);
 
 /* timing helpers on the handle's stream (CUDA events) */
 int swrt_flow_timer_start(swrt_flow* h);
@@ -207,6 +230,10 @@ typedef struct swrt_packets_desc {
                                host-visible arrays always keep the caller's row order */
     int integrator;         /* SWRT_INTEG_* */
     double f, Cg;           /* packet_params.f, packet_params.Cg */
+    /* Packets attached to a slab-decomposed flow are sharded by y-band (team mode, below): `n` is this rank's caller-order block
+     * of rows [band_first, band_first + n) of the ensemble, band_capacity >= n the number of packets the rank can host (the same
+     * value on every rank; packets move between ranks as they are advected).  Ignored for a single-GPU flow. */
+    long long band_first, band_capacity;
 } swrt_packets_desc;
 
 /* create_template_ode(packets) raytracing/GPURaytracing.jl:111-113 -- device state for N packets */
@@ -226,6 +253,10 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
  * SWRT_RAYKERNEL_TILE (one CTA per sort tile, node records staged in shared memory by TMA).  Same arithmetic, bit-identical results. */
 enum { SWRT_RAYKERNEL_AUTO = -1, SWRT_RAYKERNEL_CACHED = 0, SWRT_RAYKERNEL_TILE = 1 };
 int swrt_packets_set_kernel(swrt_packets* p, int kernel);
+/* band-sharded packets (team mode): export / map the 64-byte IPC handle of the handle's arena; packets resident on this rank */
+int swrt_packets_ipc_handle(swrt_packets* p, void* handle64);
+int swrt_packets_ipc_open(swrt_packets* p, int peer_rank, const void* handle64);
+int swrt_packets_resident(swrt_packets* p, long long* n);
 /* interpolate_velocity! / interpolate_gradients! :67-109 + Array: u_host (N,2), g_host (N,4) or NULL */
 int swrt_packets_sample(swrt_packets* p, int slot, double* u_host, double* g_host);
 /* k-cutoff reset raytracing/GPUTwoLayerRaytracing.jl:136-138 */

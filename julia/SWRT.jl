@@ -33,6 +33,7 @@ Base.@kwdef struct PacketsDesc
     interp::Cint = 0; nsub::Cint = 1; time_lerp::Cint = 0; sort_every::Cint = 16   # interp: 0 bilinear, 1 Hermite bicubic, 2 quadratic B-spline, 3 bilinear fp32, 4 cubic B-spline
     integrator::Cint = 0                                                           # 0 RK4, 1 implicit midpoint
     f::Cdouble = 1.0; Cg::Cdouble = 1.0
+    band_first::Clonglong = 0; band_capacity::Clonglong = 0                        # team mode (slab-decomposed flow): see include/swrt.h
 end
 
 const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1, "LinborgShallowWater" => 2,

@@ -28,7 +28,8 @@ class FlowDesc(C.Structure):
 
 class PacketsDesc(C.Structure):
     _fields_ = [("n", C.c_longlong), ("interp", C.c_int), ("nsub", C.c_int), ("time_lerp", C.c_int),
-                ("sort_every", C.c_int), ("integrator", C.c_int), ("f", C.c_double), ("Cg", C.c_double)]
+                ("sort_every", C.c_int), ("integrator", C.c_int), ("f", C.c_double), ("Cg", C.c_double),
+                ("band_first", C.c_longlong), ("band_capacity", C.c_longlong)]
 
 
 class SeqOut(C.Structure):
@@ -80,6 +81,14 @@ SIGNATURES = {
     "swrt_slab_stage_c": (_I, [_P]),
     "swrt_slab_psi_a": (_I, [_P, _I]),
     "swrt_slab_snap_b": (_I, [_P, _I]),
+    "swrt_slab_set_barrier": (_I, [_P, _I, _P, _P]),
+    "swrt_slab_barrier": (_I, [_P]),
+    "swrt_slab_step": (_I, [_P, _I]),
+    "swrt_slab_band_snapshot": (_I, [_P, _I, _I]),
+    "swrt_slab_band_info": (_I, [_P, _PI, _PI, _PI]),
+    "swrt_packets_ipc_handle": (_I, [_P, _P]),
+    "swrt_packets_ipc_open": (_I, [_P, _I, _P]),
+    "swrt_packets_resident": (_I, [_P, _PLL]),
     "swrt_flow_timer_start": (_I, [_P]),
     "swrt_flow_timer_stop": (_I, [_P, _PF]),
     "swrt_flow_sync": (_I, [_P]),

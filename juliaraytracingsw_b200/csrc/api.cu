@@ -15,6 +15,7 @@
 #include "../../include/swrt.h"
 #include "models.cuh"
 #include "packets.cuh"
+#include "team.cuh"
 #include "update.cuh"
 
 using namespace swrt;
@@ -103,6 +104,17 @@ struct swrt_flow {
     long long prof_n[16] = {0};
     std::vector<struct swrt_packets*> readers;   // packet handles with their own stream (snapshot writers wait for their reads)
     int npackets = 0;                            // every packet handle attached to this flow (own stream or not)
+    // team mode (P > 1): band snapshots [2 levels][halo + yrows + halo][nx][6] in one IPC-shared allocation (snap[] point into it),
+    // barrier flags, and the peers' mappings of both
+    double* band = nullptr;
+    int halo = 0;
+    TeamFlags* flags = nullptr;
+    TeamFlags* peerflags[kMaxPeers] = {};
+    double* peerband[kMaxPeers] = {};
+    unsigned long long epoch = 0;
+    int barrier_mode = 0;                        // 0 = device flags over NVLink, 1 = host callback after a stream synchronise
+    void (*barrier_cb)(void*) = nullptr;
+    void* barrier_arg = nullptr;
     // CUDA graphs of the step for launch-bound grid sizes: one per ring phase (3 steps each; 1 step for the multi-stage steppers)
     cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
     long long glaunches[3] = {0, 0, 0};
@@ -155,6 +167,16 @@ struct swrt_packets {
     unsigned long long* count = nullptr;
     long long nbins = 0;
     int kernel_sel = SWRT_RAYKERNEL_AUTO;   // swrt_packets_set_kernel
+    // band mode (the flow is slab-decomposed over a team): one IPC-shared arena, capacity `cap` rows per column, `ncur` resident
+    // packets; idx holds GLOBAL original rows; `first` = global row of this rank's caller-order block of d.n rows
+    bool band = false;
+    long long cap = 0, ncur = 0, first = 0;
+    char* arena = nullptr;
+    double* out6 = nullptr;                  // [6][cap]: sampler output in resident order / staging block of a scatter
+    unsigned long long* tab = nullptr;       // team.cuh PacketArena::tab
+    unsigned long long* tab_host = nullptr;  // pinned mirror (resident count, overflow flag, violations)
+    char* peer_arena[kMaxPeers] = {};
+    int cur = 0;                             // which half of the double buffers `xk` currently is (0: xk = A)
     bool tiles_valid = false;   // `hist` holds the per-key end offsets of the CURRENT packet order (set by the sort)
     int since_sort = 1 << 30;   // raytrace calls since the last sort
     bool permuted = false;
@@ -337,7 +359,8 @@ typedef CUresult (*swrt_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuui
                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static void build_tmaps(swrt_flow* h) {
     h->tmap_ok = false;
-    const long long nx = (long long)h->refine * h->d.nx, ny = (long long)h->refine * h->d.ny;
+    const long long nx = (long long)h->refine * h->d.nx;
+    const long long ny = h->P > 1 ? (long long)(h->L.yrows + 2 * h->halo) : (long long)h->refine * h->d.ny;   // rows the arrays hold
     if (nx < PATCH || ny < PATCH) return;
     static swrt_encode_tiled_fn encode = [] {
         void* fn = nullptr;
@@ -376,10 +399,16 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaFree(h->sol);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
-    cudaFree(h->snap[0]); cudaFree(h->snap[1]); cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
+    if (h->band) cudaFree(h->band); else { cudaFree(h->snap[0]); cudaFree(h->snap[1]); }
+    cudaFree(h->flags);
+    cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
     for (int w = 0; w < 3; ++w)
         for (int r = 0; r < h->P; ++r)
             if (h->peer[w][r] && r != h->rank) cudaIpcCloseMemHandle(h->peer[w][r]);
+    for (int r = 0; r < h->P; ++r) {
+        if (h->peerflags[r] && r != h->rank) cudaIpcCloseMemHandle(h->peerflags[r]);
+        if (h->peerband[r] && r != h->rank) cudaIpcCloseMemHandle(h->peerband[r]);
+    }
     prof_collect(h);
     for (auto e : h->pool) cudaEventDestroy(e);
     for (auto& g : h->gexec) if (g) cudaGraphExecDestroy(g);
@@ -472,6 +501,17 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->phys, sizeof(double) * (size_t)d.nx * d.ny));
     CKB(cudaMalloc(&h->red, sizeof(double) * 1024));
     CKB(cudaMalloc(&h->sched, sizeof(unsigned) * 4)); CKB(cudaMemset(h->sched, 0, sizeof(unsigned) * 4));
+    if (h->P > 1) {
+        // team mode: a rank only ever samples its own band of rows (packets are sharded by y-band) plus `halo` rows of each neighbour
+        h->halo = L.yrows < 8 ? L.yrows : 8;
+        const size_t lev_doubles = (size_t)(L.yrows + 2 * h->halo) * d.nx * SNAP_STRIDE;
+        CKB(cudaMalloc(&h->band, sizeof(double) * 2 * lev_doubles));
+        CKB(cudaMemset(h->band, 0, sizeof(double) * 2 * lev_doubles));
+        h->snap[0] = h->band;
+        h->snap[1] = h->band + lev_doubles;
+        CKB(cudaMalloc(&h->flags, sizeof(TeamFlags)));
+        CKB(cudaMemset(h->flags, 0, sizeof(TeamFlags)));
+    } else
     for (int lev = 0; lev < 2; ++lev) {
         CKB(cudaMalloc(&h->snap[lev], sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));   // sized for either node record
         CKB(cudaMemset(h->snap[lev], 0, sizeof(double) * (size_t)d.nx * d.ny * SNAP3_STRIDE));
@@ -971,7 +1011,7 @@ int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbyt
         case SWRT_SLAB_B_RECV: p = h->H; nb = fb * h->njobs_b; break;
         case SWRT_SLAB_SNAP0: case SWRT_SLAB_SNAP1:
             p = h->snap[h->slot_map[which - SWRT_SLAB_SNAP0]];
-            nb = (long long)sizeof(double) * h->d.nx * h->d.ny * (h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE);
+            nb = (long long)sizeof(double) * h->d.nx * (h->L.yrows + 2 * h->halo) * SNAP_STRIDE;   // band + halo rows of the 5-field records
             break;
         default: return fail(SWRT_ERR_ARG, "unknown slab buffer %d", which);
     }
@@ -981,30 +1021,32 @@ int swrt_slab_buffer(swrt_flow* h, int which, void** device_ptr, long long* nbyt
 }
 int swrt_slab_ipc_handle(swrt_flow* h, int which, void* handle64) {
     if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
-    if (which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV && which != SWRT_SLAB_A_SEND)
-        return fail(SWRT_ERR_ARG, "shared buffers: the two receive buffers and (pull variant) the first send buffer");
+    void* ptr = which == SWRT_SLAB_A_RECV ? (void*)h->G2 : which == SWRT_SLAB_A_SEND ? (void*)h->G : which == SWRT_SLAB_B_RECV ? (void*)h->H
+              : which == SWRT_SLAB_FLAGS ? (void*)h->flags : which == SWRT_SLAB_BAND ? (void*)h->band : nullptr;
+    if (!ptr) return fail(SWRT_ERR_ARG, "shared buffers: the two receive buffers, (pull variant) the first send buffer, the barrier flags and the band snapshots");
     CK(cudaSetDevice(h->d.device));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaIpcMemHandle_t mh;
-    CK(cudaIpcGetMemHandle(&mh, which == SWRT_SLAB_A_RECV ? (void*)h->G2 : which == SWRT_SLAB_A_SEND ? (void*)h->G : (void*)h->H));
+    CK(cudaIpcGetMemHandle(&mh, ptr));
     memcpy(handle64, &mh, 64);
     return SWRT_OK;
 }
 int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handle64) {
     if (!h || !handle64 || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
-    if ((which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV && which != SWRT_SLAB_A_SEND) || peer_rank < 0 || peer_rank >= h->P)
+    const bool team = which == SWRT_SLAB_FLAGS || which == SWRT_SLAB_BAND;
+    if ((!team && which != SWRT_SLAB_A_RECV && which != SWRT_SLAB_B_RECV && which != SWRT_SLAB_A_SEND) || peer_rank < 0 || peer_rank >= h->P)
         return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const int w = which == SWRT_SLAB_A_RECV ? 0 : which == SWRT_SLAB_B_RECV ? 1 : 2;
-    if (peer_rank == h->rank) {
-        h->peer[w][peer_rank] = w == 0 ? h->G2 : w == 1 ? h->H : h->G;
-    } else {
+    void* p = nullptr;
+    if (peer_rank != h->rank) {
         cudaIpcMemHandle_t mh;
         memcpy(&mh, handle64, 64);
-        void* p = nullptr;
         CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
-        h->peer[w][peer_rank] = (double2*)p;
     }
+    if (which == SWRT_SLAB_FLAGS) { h->peerflags[peer_rank] = p ? (TeamFlags*)p : h->flags; return SWRT_OK; }
+    if (which == SWRT_SLAB_BAND) { h->peerband[peer_rank] = p ? (double*)p : h->band; return SWRT_OK; }
+    const int w = which == SWRT_SLAB_A_RECV ? 0 : which == SWRT_SLAB_B_RECV ? 1 : 2;
+    h->peer[w][peer_rank] = p ? (double2*)p : (w == 0 ? h->G2 : w == 1 ? h->H : h->G);
     bool all = true;
     for (int w2 = 0; w2 < 2; ++w2)
         for (int r = 0; r < h->P; ++r) all = all && h->peer[w2][r] != nullptr;
@@ -1094,11 +1136,84 @@ int swrt_slab_snap_b(swrt_flow* h, int slot) {
     if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
     if (h->interp == SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the 5-field node data");
     CK(cudaSetDevice(h->d.device));
-    double* rows = h->snap[h->slot_map[slot]] + (long long)h->rank * h->L.yrows * h->d.nx * SNAP_STRIDE;   // this rank's rows of the full field
+    double* rows = h->snap[h->slot_map[slot]] + (long long)h->halo * h->d.nx * SNAP_STRIDE;   // this rank's band: the owned rows follow the lower halo
     CK(wait_readers(h));
     cudaError_t e;
     { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(in_slab(h, 3), rows, h->L, h->tw_x, h->sched, h->st)); }
     CK(e);
+    return SWRT_OK;
+}
+
+// ---- team mode: barrier, native step, band snapshot (no communication library on the data path)
+int swrt_slab_set_barrier(swrt_flow* h, int mode, void (*callback)(void*), void* arg) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    if (mode != 0 && mode != 1) return fail(SWRT_ERR_ARG, "barrier mode must be 0 (device flags) or 1 (host callback)");
+    if (mode == 1 && !callback) return fail(SWRT_ERR_ARG, "the host barrier needs a callback");
+    h->barrier_mode = mode;
+    h->barrier_cb = callback;
+    h->barrier_arg = arg;
+    return SWRT_OK;
+}
+static int team_barrier(swrt_flow* h) {
+    if (h->barrier_mode == 1) {          // every rank's stream drained, then the caller's host barrier (processes sharing one GPU)
+        CK(cudaStreamSynchronize(h->st));
+        h->barrier_cb(h->barrier_arg);
+        return SWRT_OK;
+    }
+    TeamPeers tp{};
+    for (int r = 0; r < h->P; ++r) {
+        if (!h->peerflags[r]) return fail(SWRT_ERR_STATE, "team barrier: the flags of rank %d are not mapped (swrt_slab_ipc_open SWRT_SLAB_FLAGS)", r);
+        tp.f[r] = h->peerflags[r];
+    }
+    h->epoch += 1;
+    { ProfScope ps(h, K_OTHER); team_barrier_kernel<<<1, 32, 0, h->st>>>(tp, h->P, h->rank, h->epoch); }
+    CK(cudaGetLastError());
+    return SWRT_OK;
+}
+int swrt_slab_barrier(swrt_flow* h) {
+    if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    CK(cudaSetDevice(h->d.device));
+    return team_barrier(h);
+}
+int swrt_slab_step(swrt_flow* h, int nsteps) {
+    if (!h || h->P <= 1 || nsteps < 0) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad step count");
+    if (!h->p2p) return fail(SWRT_ERR_STATE, "swrt_slab_step needs the peers' receive buffers mapped (swrt_slab_ipc_open); without them drive the phases and the all-to-alls from the host");
+    int rc;
+    for (int s = 0; s < nsteps; ++s) {
+        if ((rc = swrt_slab_stage_a(h))) return rc;
+        if ((rc = team_barrier(h))) return rc;
+        if ((rc = swrt_slab_stage_b(h))) return rc;
+        if ((rc = team_barrier(h))) return rc;
+        if ((rc = swrt_slab_stage_c(h))) return rc;
+    }
+    return SWRT_OK;
+}
+// halo rows of one level from the two neighbours' band buffers (the caller has placed a barrier after the writes)
+static int band_halo_pull(swrt_flow* h, int slot) {
+    const int lev = h->slot_map[slot];
+    const long long row_doubles = (long long)h->d.nx * SNAP_STRIDE, lev_doubles = (long long)(h->L.yrows + 2 * h->halo) * row_doubles;
+    const int below = (h->rank + h->P - 1) % h->P, above = (h->rank + 1) % h->P;
+    if (!h->peerband[below] || !h->peerband[above]) return fail(SWRT_ERR_STATE, "band snapshots of the neighbours are not mapped (swrt_slab_ipc_open SWRT_SLAB_BAND)");
+    { ProfScope ps(h, K_OTHER);
+      team_halo_pull_kernel<<<64, 256, 0, h->st>>>(h->snap[lev], h->peerband[below] + lev * lev_doubles, h->peerband[above] + lev * lev_doubles, h->halo, h->L.yrows, row_doubles); }
+    CK(cudaGetLastError());
+    return SWRT_OK;
+}
+int swrt_slab_band_snapshot(swrt_flow* h, int psi_kind, int slot) {
+    if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
+    if (!h->p2p) return fail(SWRT_ERR_STATE, "swrt_slab_band_snapshot needs the peers' receive buffers mapped");
+    int rc;
+    if ((rc = swrt_slab_psi_a(h, psi_kind))) return rc;
+    if ((rc = team_barrier(h))) return rc;
+    if ((rc = swrt_slab_snap_b(h, slot))) return rc;
+    if ((rc = team_barrier(h))) return rc;          // every rank's band rows are written
+    return band_halo_pull(h, slot);                 // (the neighbours overwrite this level two steps later, behind >= 4 more barriers)
+}
+int swrt_slab_band_info(swrt_flow* h, int* row0, int* rows, int* halo) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (row0) *row0 = h->rank * h->L.yrows;
+    if (rows) *rows = h->L.yrows;
+    if (halo) *halo = h->halo;
     return SWRT_OK;
 }
 
@@ -1201,7 +1316,7 @@ int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny) {
 int swrt_flow_set_interp(swrt_flow* h, int interp) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
     if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_BSPLINE3) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
-    if (interp == SWRT_INTERP_BILINEAR_F32 && h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode is not built for a slab-decomposed flow");
+    if (interp != SWRT_INTERP_BILINEAR && h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "a slab-decomposed flow holds band snapshots of the 5-field bilinear node records only");
     h->interp = interp;
     return SWRT_OK;
 }
@@ -1221,15 +1336,17 @@ int swrt_flow_swap_snapshots(swrt_flow* h, int alias) {
 int swrt_flow_get_snapshot(swrt_flow* h, int slot, double* out_host) {
     if (!h || !out_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(h->d.device));
-    const long long n = (long long)h->refine * h->d.nx * h->refine * h->d.ny;
+    // (a slab-decomposed flow returns its own band: rows [rank ny/P, (rank+1) ny/P) as an (nx, ny/P, 5) array)
+    const long long n = h->P > 1 ? (long long)h->d.nx * h->L.yrows : (long long)h->refine * h->d.nx * h->refine * h->d.ny;
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
+    const double* src0 = h->snap[h->slot_map[slot]] + (h->P > 1 ? (long long)h->halo * h->d.nx * SNAP_STRIDE : 0);
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
     if (h->interp == SWRT_INTERP_BILINEAR_F32) {
         ProfScope ps(h, K_OTHER);
-        snapf_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<const float*>(h->snap[h->slot_map[slot]]), n, tmp);
+        snapf_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<const float*>(src0), n, tmp);
     } else
-    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->snap[h->slot_map[slot]], n, nc, stride, tmp); }
+    { ProfScope ps(h, K_OTHER); snap_to_planar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(src0, n, nc, stride, tmp); }
     cudaError_t e = cudaMemcpyAsync(out_host, tmp, sizeof(double) * n * nc, cudaMemcpyDeviceToHost, h->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     cudaFree(tmp);
@@ -1241,20 +1358,29 @@ int swrt_flow_set_snapshot(swrt_flow* h, int slot, const double* in_host) {
     if (!h || !in_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     if (h->interp == SWRT_INTERP_BILINEAR_F32) return fail(SWRT_ERR_UNSUPPORTED, "snapshots of the fp32 packet mode are built by swrt_flow_velocity_snapshot only");
     CK(cudaSetDevice(h->d.device));
-    const long long n = (long long)h->refine * h->d.nx * h->refine * h->d.ny;
+    // (a slab-decomposed flow takes its own band of rows, (nx, ny/P, 5); COLLECTIVE: the halo rows come from the neighbours)
+    const long long n = h->P > 1 ? (long long)h->d.nx * h->L.yrows : (long long)h->refine * h->d.nx * h->refine * h->d.ny;
     const int nc = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_NC : SNAP_NC, stride = h->interp == SWRT_INTERP_HERMITE_BICUBIC ? SNAP3_STRIDE : SNAP_STRIDE;
+    double* dst0 = h->snap[h->slot_map[slot]] + (h->P > 1 ? (long long)h->halo * h->d.nx * SNAP_STRIDE : 0);
     double* tmp = nullptr;
     CK(cudaMalloc(&tmp, sizeof(double) * n * nc));
     CK(wait_readers(h));
     cudaError_t e = cudaMemcpyAsync(tmp, in_host, sizeof(double) * n * nc, cudaMemcpyHostToDevice, h->st);
     if (e == cudaSuccess) {
         ProfScope ps(h, K_OTHER);
-        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, n, nc, stride, h->snap[h->slot_map[slot]]);
+        planar_to_snap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(tmp, n, nc, stride, dst0);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     cudaFree(tmp);
     CK(e);
+    if (h->P > 1) {
+        int rc;
+        if ((rc = team_barrier(h))) return rc;
+        if ((rc = band_halo_pull(h, slot))) return rc;
+        if ((rc = team_barrier(h))) return rc;
+        CK(cudaStreamSynchronize(h->st));
+    }
     return SWRT_OK;
 }
 
@@ -1303,6 +1429,19 @@ int swrt_flow_launch_count(swrt_flow* h, long long* n) {
 }
 
 // ------------------------------------------------------------------ packets
+static int packets_free(swrt_packets* p) {
+    if (p->band) {
+        for (int r = 0; r < (p->flow ? p->flow->P : 0); ++r)
+            if (p->peer_arena[r] && p->peer_arena[r] != p->arena) cudaIpcCloseMemHandle(p->peer_arena[r]);
+        cudaFree(p->arena);
+        if (p->tab_host) cudaFreeHost(p->tab_host);
+    } else {
+        cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->xk2); cudaFree(p->sign2); cudaFree(p->U); cudaFree(p->Gd);
+        cudaFree(p->idx); cudaFree(p->idx2);
+    }
+    cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count);
+    return SWRT_OK;
+}
 int swrt_packets_destroy(swrt_packets* p) {
     if (!p) return SWRT_OK;
     if (p->flow) {
@@ -1315,9 +1454,30 @@ int swrt_packets_destroy(swrt_packets* p) {
         if (p->own) cudaStreamDestroy(p->st);
         if (p->ev_done) cudaEventDestroy(p->ev_done);
     }
-    cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->xk2); cudaFree(p->sign2); cudaFree(p->U); cudaFree(p->Gd);
-    cudaFree(p->idx); cudaFree(p->idx2); cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count);
+    packets_free(p);
     delete p;
+    return SWRT_OK;
+}
+
+// band mode: layout of the IPC-shared arena (identical on every rank: same capacity), team.cuh PacketArena
+static size_t arena_layout(long long cap, int P, PacketArena* a, char* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* q = base ? base + off : nullptr; off += (bytes + 255) / 256 * 256; return q; };
+    for (int b = 0; b < 2; ++b) a->xk[b] = (double*)take(sizeof(double) * 4 * (size_t)cap);
+    for (int b = 0; b < 2; ++b) a->sign[b] = (double*)take(sizeof(double) * (size_t)cap);
+    for (int b = 0; b < 2; ++b) a->idx[b] = (unsigned*)take(sizeof(unsigned) * (size_t)cap);
+    a->out = (double*)take(sizeof(double) * 6 * (size_t)cap);
+    a->tab = (unsigned long long*)take(sizeof(unsigned long long) * (2 * (size_t)P + 8));
+    return off;
+}
+static ArenaPeers arena_peers(const swrt_packets* p) {
+    ArenaPeers ap{};
+    for (int r = 0; r < p->flow->P; ++r) arena_layout(p->cap, p->flow->P, &ap.a[r], p->peer_arena[r]);
+    return ap;
+}
+static int band_peers_ready(const swrt_packets* p) {
+    for (int r = 0; r < p->flow->P; ++r)
+        if (!p->peer_arena[r]) return fail(SWRT_ERR_STATE, "band packets: the arena of rank %d is not mapped (swrt_packets_ipc_open)", r);
     return SWRT_OK;
 }
 
@@ -1333,52 +1493,110 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
         return fail(SWRT_ERR_UNSUPPORTED, "integrator %d not implemented", desc->integrator);
     if (desc->nsub < 1) return fail(SWRT_ERR_ARG, "nsub must be >= 1");
     if (desc->sort_every < 0) return fail(SWRT_ERR_ARG, "sort_every must be >= 0");
+    const bool band = flow->P > 1;
+    if (band && (desc->interp != SWRT_INTERP_BILINEAR || desc->integrator != SWRT_INTEG_RK4))
+        return fail(SWRT_ERR_UNSUPPORTED, "packets of a slab-decomposed flow (y-band sharded) are built for the fp64 bilinear RK4 mode");
+    if (band && (desc->sort_every < 1 || desc->band_capacity < desc->n || desc->band_first < 0 || desc->band_first + desc->n >= (1LL << 32)))
+        return fail(SWRT_ERR_ARG, "band packets need sort_every >= 1 (the hand-over between bands rides on the sort), band_capacity >= n (the same on every rank) and a global row range below 2^32");
     CK(cudaSetDevice(flow->d.device));
     swrt_packets* p = new swrt_packets;
     p->d = *desc;
     p->flow = flow;
     flow->npackets++;
     p->nbins = (long long)flow->refine * flow->d.nx * flow->refine * flow->d.ny;   // cells of the snapshots' node grid
-    const size_t n = (size_t)desc->n;
+    p->band = band;
+    p->cap = band ? desc->band_capacity : desc->n;
+    p->ncur = band ? 0 : desc->n;
+    p->first = band ? desc->band_first : 0;
+    const size_t n = (size_t)p->cap;
     const size_t nsums = (size_t)(p->nbins / SCAN_BLOCK + 2) + (size_t)(p->nbins / SCAN_BLOCK / SCAN_BLOCK + 2) + 8;
-    cudaError_t e;
-    if ((e = cudaMalloc(&p->xk, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign, sizeof(double) * n)) != cudaSuccess ||
+    cudaError_t e = cudaSuccess;
+    if (band) {
+        PacketArena a{};
+        const size_t bytes = arena_layout(p->cap, flow->P, &a, nullptr);
+        e = cudaMalloc(&p->arena, bytes);
+        if (e == cudaSuccess) e = cudaMemset(p->arena, 0, bytes);
+        if (e == cudaSuccess) e = cudaHostAlloc(&p->tab_host, sizeof(unsigned long long) * 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) {
+            arena_layout(p->cap, flow->P, &a, p->arena);
+            p->xk = a.xk[0]; p->xk2 = a.xk[1]; p->sign = a.sign[0]; p->sign2 = a.sign[1]; p->idx = a.idx[0]; p->idx2 = a.idx[1];
+            p->out6 = a.out; p->U = a.out; p->Gd = a.out + 2 * p->cap; p->tab = a.tab;
+            p->peer_arena[flow->rank] = p->arena;
+        }
+    } else if ((e = cudaMalloc(&p->xk, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign, sizeof(double) * n)) != cudaSuccess ||
         (e = cudaMalloc(&p->xk2, sizeof(double) * 4 * n)) != cudaSuccess || (e = cudaMalloc(&p->sign2, sizeof(double) * n)) != cudaSuccess ||
         (e = cudaMalloc(&p->U, sizeof(double) * 2 * n)) != cudaSuccess || (e = cudaMalloc(&p->Gd, sizeof(double) * 4 * n)) != cudaSuccess ||
-        (e = cudaMalloc(&p->idx, sizeof(unsigned) * n)) != cudaSuccess || (e = cudaMalloc(&p->idx2, sizeof(unsigned) * n)) != cudaSuccess ||
-        (e = cudaMalloc(&p->keys, sizeof(unsigned) * n)) != cudaSuccess || (e = cudaMalloc(&p->hist, sizeof(unsigned) * (size_t)p->nbins)) != cudaSuccess ||
-        (e = cudaMalloc(&p->sums, sizeof(unsigned) * nsums)) != cudaSuccess || (e = cudaMalloc(&p->count, sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaMalloc(&p->idx, sizeof(unsigned) * n)) != cudaSuccess || (e = cudaMalloc(&p->idx2, sizeof(unsigned) * n)) != cudaSuccess) {
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&p->keys, sizeof(unsigned) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&p->hist, sizeof(unsigned) * (size_t)p->nbins);
+    if (e == cudaSuccess) e = cudaMalloc(&p->sums, sizeof(unsigned) * nsums);
+    if (e == cudaSuccess) e = cudaMalloc(&p->count, sizeof(unsigned long long) * 2);
+    if (e != cudaSuccess) {
         swrt_packets_destroy(p);
         return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
     }
-    CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, pst(p)));
-    CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, pst(p)));
-    { ProfScope ps(flow, K_OTHER, pst(p)); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->idx, (long long)n); }
-    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * 2, pst(p)));
+    if (!band) {
+        CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, pst(p)));
+        CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, pst(p)));
+        { ProfScope ps(flow, K_OTHER, pst(p)); iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->idx, (long long)n); }
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(pst(p)));
     *out = p;
     return SWRT_OK;
 }
 
-// host (n, ncol) column-major with leading dimension ld  <->  device [ncol][n]
-static cudaError_t copy_cols(void* dst, const void* src, long long n, int ncol, long long ld, cudaMemcpyKind kind, cudaStream_t st) {
-    if (ld == n) return cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)ncol * (size_t)n, kind, st);
-    const size_t hp = sizeof(double) * (size_t)ld, dp = sizeof(double) * (size_t)n;
-    return kind == cudaMemcpyHostToDevice ? cudaMemcpy2DAsync(dst, dp, src, hp, dp, (size_t)ncol, kind, st)
-                                          : cudaMemcpy2DAsync(dst, hp, src, dp, dp, (size_t)ncol, kind, st);
+// band mode: every rank exports the IPC handle of its arena and opens the peers' (like swrt_slab_ipc_handle / _open)
+int swrt_packets_ipc_handle(swrt_packets* p, void* handle64) {
+    if (!p || !handle64 || !p->band) return fail(SWRT_ERR_STATE, "not band-sharded packets (the flow is not slab-decomposed)");
+    CK(cudaSetDevice(p->flow->d.device));
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, p->arena));
+    memcpy(handle64, &mh, 64);
+    return SWRT_OK;
+}
+int swrt_packets_ipc_open(swrt_packets* p, int peer_rank, const void* handle64) {
+    if (!p || !handle64 || !p->band) return fail(SWRT_ERR_STATE, "not band-sharded packets (the flow is not slab-decomposed)");
+    if (peer_rank < 0 || peer_rank >= p->flow->P) return fail(SWRT_ERR_ARG, "peer rank out of range");
+    CK(cudaSetDevice(p->flow->d.device));
+    if (peer_rank == p->flow->rank) { p->peer_arena[peer_rank] = p->arena; return SWRT_OK; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, handle64, 64);
+    void* q = nullptr;
+    CK(cudaIpcOpenMemHandle(&q, mh, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_arena[peer_rank] = (char*)q;
+    return SWRT_OK;
+}
+// resident packets on this rank (band mode; = n otherwise)
+int swrt_packets_resident(swrt_packets* p, long long* n) {
+    if (!p || !n) return fail(SWRT_ERR_ARG, "null pointer");
+    *n = p->ncur;
+    return SWRT_OK;
+}
+
+// host (n, ncol) column-major with leading dimension ld  <->  device [ncol][ldd]
+static cudaError_t copy_cols(void* dst, const void* src, long long n, int ncol, long long ld, cudaMemcpyKind kind, cudaStream_t st, long long ldd = -1) {
+    if (ldd < 0) ldd = n;
+    if (ld == n && ldd == n) return cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)ncol * (size_t)n, kind, st);
+    const size_t hp = sizeof(double) * (size_t)ld, dp = sizeof(double) * (size_t)ldd, w = sizeof(double) * (size_t)n;
+    return kind == cudaMemcpyHostToDevice ? cudaMemcpy2DAsync(dst, dp, src, hp, w, (size_t)ncol, kind, st)
+                                          : cudaMemcpy2DAsync(dst, hp, src, dp, w, (size_t)ncol, kind, st);
 }
 // Packets with their own stream read snapshots the flow's stream writes: order the two streams with events.
 static cudaError_t wait_flow(swrt_packets* p) {
     if (!p->own) return cudaSuccess;
     swrt_flow* f = p->flow;
     cudaError_t e = cudaEventRecord(f->ev_sync, f->st);
-    return e != cudaSuccess ? e : cudaStreamWaitEvent(pst(p), f->ev_sync, 0);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(p->st, f->ev_sync, 0);
 }
-static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(p->ev_done, pst(p)) : cudaSuccess; }
+static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(p->ev_done, p->st) : cudaSuccess; }
 
 int swrt_packets_use_own_stream(swrt_packets* p) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     if (p->own) return SWRT_OK;
+    if (p->band) return fail(SWRT_ERR_UNSUPPORTED, "band-sharded packets run on the flow's stream (their hand-over is ordered by the team barrier)");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     CK(cudaStreamSynchronize(f->st));
@@ -1404,14 +1622,93 @@ int swrt_packets_sync(swrt_packets* p) {
     return SWRT_OK;
 }
 
+static PacketGrid packet_grid(const swrt_flow* f, const swrt_packets* p = nullptr) {
+    PacketGrid g{};
+    g.nx = f->refine * f->d.nx; g.ny = f->refine * f->d.ny;    // the node grid of the snapshots
+    g.dx = f->d.Lx / g.nx; g.dy = f->d.Ly / g.ny;
+    g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
+    g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
+    g.ld = p ? p->cap : 0;
+    if (f->P > 1) {
+        g.band = 1;
+        g.jb = f->rank * f->L.yrows - f->halo;
+        g.jrows = f->L.yrows + 2 * f->halo;
+        const int tiles_y = g.ny >> TILE_SHIFT;
+        int t_lo = g.jb >= 0 ? g.jb >> TILE_SHIFT : -((-g.jb + TILE - 1) >> TILE_SHIFT);
+        g.tile_row0 = ((t_lo % tiles_y) + tiles_y) % tiles_y;
+    }
+    return g;
+}
+// tile rows the tile kernel's grid covers
+static int tile_rows(const swrt_flow* f, const PacketGrid& g) {
+    const int tiles_y = g.ny >> TILE_SHIFT;
+    if (!g.band) return tiles_y;
+    const int t_lo = g.jb >= 0 ? g.jb >> TILE_SHIFT : -((-g.jb + TILE - 1) >> TILE_SHIFT);
+    const int t_hi = (g.jb + g.jrows - 1) >> TILE_SHIFT;
+    const int n = t_hi - t_lo + 1;
+    return n < tiles_y ? n : tiles_y;
+}
+
+// ---- band mode: scatter the caller-order staging block (5 columns in `out`: x, y, k, l, sign) to the band owners.  COLLECTIVE.
+static int band_scatter(swrt_packets* p, long long nrows) {
+    swrt_flow* f = p->flow;
+    int rc = band_peers_ready(p);
+    if (rc) return rc;
+    const int P = f->P;
+    unsigned long long hdr[4] = {0ULL, (unsigned long long)nrows, (unsigned long long)p->first, 0ULL};   // resident count, staging rows, first row, overflow
+    CK(cudaMemcpyAsync(p->tab + 2 * P, hdr, sizeof hdr, cudaMemcpyHostToDevice, f->st));
+    if ((rc = team_barrier(f))) return rc;                                  // every staging block and header is in place
+    int bshift = 0; while ((1 << bshift) < f->L.yrows) ++bshift;
+    { ProfScope ps(f, K_OTHER); team_scatter_scan_kernel<<<148 * 4, 256, 0, f->st>>>(arena_peers(p), P, f->rank, p->cur, p->cap, packet_grid(f, p), bshift); }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, f->st));
+    if ((rc = team_barrier(f))) return rc;                                  // the staging blocks may be overwritten again
+    CK(cudaStreamSynchronize(f->st));
+    if (p->tab_host[3]) return fail(SWRT_ERR_STATE, "band packets: more than band_capacity = %lld packets fall into the band of rank %d", p->cap, f->rank);
+    p->ncur = (long long)p->tab_host[0];
+    p->permuted = true;
+    p->since_sort = 1 << 30;
+    p->tiles_valid = false;
+    return SWRT_OK;
+}
+// ---- band mode: collect this rank's caller-order rows from wherever the packets live.  which = 0: packet state, 1: `out`
+// columns [c0, c0 + ncols) in resident order.  The result lands in dst (device, [ncols][ldd]).  COLLECTIVE; the caller
+// places the barriers.
+static int band_gather_launch(swrt_packets* p, int which, int c0, int ncols, double* dst, long long ldd) {
+    swrt_flow* f = p->flow;
+    ArenaPeers ap = arena_peers(p);
+    if (which == 1) for (int r = 0; r < f->P; ++r) ap.a[r].out += (long long)c0 * p->cap;
+    { ProfScope ps(f, K_OTHER); team_gather_scan_kernel<<<148 * 4, 256, 0, f->st>>>(ap, f->P, p->cur, which, ncols, p->cap, p->first, p->d.n, dst, ldd); }
+    CK(cudaGetLastError());
+    return SWRT_OK;
+}
+
 static int packets_set_impl(swrt_packets* p, const double* xk_host, long long ld, const double* sign_host, bool sync) {
     if (!p || !xk_host) return fail(SWRT_ERR_ARG, "null pointer");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
+    if (p->band) {
+        // caller-order block -> staging (x, y, k, l, sign); the signs of the previous ensemble are fetched first when none are given
+        if (!sign_host) {
+            int rc = band_peers_ready(p);
+            if (rc) return rc;
+            if ((rc = team_barrier(f))) return rc;
+            ArenaPeers ap = arena_peers(p);
+            for (int r = 0; r < f->P; ++r) ap.a[r].out = ap.a[r].sign[p->cur];          // gather column: the resident signs
+            { ProfScope ps(f, K_OTHER); team_gather_scan_kernel<<<148 * 4, 256, 0, f->st>>>(ap, f->P, p->cur, 1, 1, p->cap, p->first, n, p->xk2, p->cap); }
+            CK(cudaGetLastError());
+            if ((rc = team_barrier(f))) return rc;
+            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, p->xk2, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, f->st));
+        } else {
+            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, f->st));
+        }
+        CK(copy_cols(p->out6, xk_host, n, 4, ld, cudaMemcpyHostToDevice, f->st, p->cap));
+        return band_scatter(p, n);
+    }
     if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
-        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->sign, p->idx, n, 1, p->sign2); }
+        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->sign, p->idx, n, n, 1, p->sign2); }
         CK(cudaGetLastError());
         std::swap(p->sign, p->sign2);
     }
@@ -1438,9 +1735,19 @@ static int packets_get_impl(swrt_packets* p, double* xk_host, long long ld, bool
     CK(cudaSetDevice(f->d.device));
     const long long n = p->d.n;
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
+    if (p->band) {   // COLLECTIVE: every rank pulls its caller-order rows out of all ranks' resident arrays
+        int rc = band_peers_ready(p);
+        if (rc) return rc;
+        if ((rc = team_barrier(f))) return rc;
+        if ((rc = band_gather_launch(p, 0, 0, 4, p->out6, p->cap))) return rc;
+        if ((rc = team_barrier(f))) return rc;
+        CK(copy_cols(xk_host, p->out6, n, 4, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
+        CK(cudaStreamSynchronize(f->st));
+        return SWRT_OK;
+    }
     const double* src = p->xk;
     if (p->permuted) {
-        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->idx, n, 4, p->xk2); }
+        { ProfScope ps(f, K_OTHER, pst(p)); unpermute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->idx, n, n, 4, p->xk2); }
         CK(cudaGetLastError());
         src = p->xk2;
     }
@@ -1455,21 +1762,18 @@ int swrt_packets_generate(swrt_packets* p, double L, double k0, long long sqrtN,
     if (!p || sqrtN <= 0 || first < 0 || first + p->d.n > sqrtN * sqrtN) return fail(SWRT_ERR_ARG, "bad argument");
     CK(cudaSetDevice(p->flow->d.device));
     const long long n = p->d.n;
-    { ProfScope ps(p->flow, K_OTHER, pst(p)); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, n, first, sqrtN, L, k0); }
+    if (p->band) {   // the caller-order block of the lattice goes to the staging columns, then to the band owners.  COLLECTIVE.
+        if (first != p->first) return fail(SWRT_ERR_ARG, "band packets: `first` (%lld) must equal the band_first the handle was created with (%lld)", first, p->first);
+        { ProfScope ps(p->flow, K_OTHER); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->flow->st>>>(p->out6, p->out6 + 4 * p->cap, p->idx2, n, p->cap, first, sqrtN, L, k0); }
+        CK(cudaGetLastError());
+        return band_scatter(p, n);
+    }
+    { ProfScope ps(p->flow, K_OTHER, pst(p)); generate_packets_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, n, n, first, sqrtN, L, k0); }
     CK(cudaGetLastError());
     p->permuted = false;
     p->since_sort = 1 << 30;
     p->tiles_valid = false;
     return SWRT_OK;
-}
-
-static PacketGrid packet_grid(const swrt_flow* f) {
-    PacketGrid g;
-    g.nx = f->refine * f->d.nx; g.ny = f->refine * f->d.ny;    // the node grid of the snapshots
-    g.dx = f->d.Lx / g.nx; g.dy = f->d.Ly / g.ny;
-    g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
-    g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
-    return g;
 }
 
 static cudaError_t exclusive_scan(swrt_packets* p, unsigned* a, long long nb, unsigned* scratch) {
@@ -1488,23 +1792,55 @@ static cudaError_t exclusive_scan(swrt_packets* p, unsigned* a, long long nb, un
 }
 
 // counting sort of the packets by tiled cell key (packets.cuh); out of place, then swap the buffers
-static int sort_packets(swrt_packets* p) {
+static int sort_local(swrt_packets* p) {
     swrt_flow* f = p->flow;
-    const long long n = p->d.n;
+    const long long n = p->ncur;
     const unsigned blocks = (unsigned)((n + 255) / 256);
     CK(cudaMemsetAsync(p->hist, 0, sizeof(unsigned) * (size_t)p->nbins, pst(p)));
-    { ProfScope ps(f, K_SORT, pst(p)); sort_hist_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, n, packet_grid(f), p->keys, p->hist); }
-    CK(cudaGetLastError());
+    if (n > 0) {
+        { ProfScope ps(f, K_SORT, pst(p)); sort_hist_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, n, packet_grid(f, p), p->keys, p->hist, p->count + 1); }
+        CK(cudaGetLastError());
+    }
     CK(exclusive_scan(p, p->hist, p->nbins, p->sums));
-    { ProfScope ps(f, K_SORT, pst(p)); sort_scatter_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->xk2, p->sign2, p->idx2); }
-    CK(cudaGetLastError());
+    if (n > 0) {
+        { ProfScope ps(f, K_SORT, pst(p)); sort_scatter_kernel<<<blocks, 256, 0, pst(p)>>>(p->xk, p->sign, p->idx, p->keys, p->hist, n, p->cap, p->xk2, p->sign2, p->idx2); }
+        CK(cudaGetLastError());
+    }
     std::swap(p->xk, p->xk2);
     std::swap(p->sign, p->sign2);
     std::swap(p->idx, p->idx2);
+    p->cur ^= 1;
     p->permuted = true;
     p->since_sort = 0;
     p->tiles_valid = true;
     return SWRT_OK;
+}
+static int sort_packets(swrt_packets* p) {
+    int rc = sort_local(p);
+    if (rc || !p->band) return rc;
+    // ---- hand-over between bands (COLLECTIVE): the sorted order groups the packets by owner rank (the key is tile-row major)
+    swrt_flow* f = p->flow;
+    const int P = f->P;
+    if ((rc = band_peers_ready(p))) return rc;
+    const ArenaPeers ap = arena_peers(p);
+    const long long keys_per_rank = (long long)f->L.yrows * f->d.nx;
+    { ProfScope ps(f, K_SORT); team_publish_segments_kernel<<<1, 32, 0, f->st>>>(p->hist, keys_per_rank, ap, P, f->rank); }
+    CK(cudaGetLastError());
+    if ((rc = team_barrier(f))) return rc;                                  // every rank's sorted array and segment table are complete
+    { ProfScope ps(f, K_SORT); team_pull_segments_kernel<<<148 * 4, 256, 0, f->st>>>(ap, P, f->rank, p->cur, p->cur ^ 1, p->cap); }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, f->st));
+    CK(cudaMemcpyAsync(p->tab_host + 4, p->count + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, f->st));
+    if ((rc = team_barrier(f))) return rc;                                  // the peers have read my sorted array: it may be reused
+    CK(cudaStreamSynchronize(f->st));                                       // the new resident count sizes the next launches
+    if (p->tab_host[3]) return fail(SWRT_ERR_STATE, "band packets: more than band_capacity = %lld packets moved into the band of rank %d", p->cap, f->rank);
+    if (p->tab_host[4]) return fail(SWRT_ERR_STATE, "band packets: %llu packets left band + halo (%d rows) between two hand-overs; lower sort_every", p->tab_host[4], f->halo);
+    std::swap(p->xk, p->xk2);
+    std::swap(p->sign, p->sign2);
+    std::swap(p->idx, p->idx2);
+    p->cur ^= 1;
+    p->ncur = (long long)p->tab_host[0];
+    return sort_local(p);                                                   // merge the P sorted runs; rebuilds the tile offsets
 }
 
 int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
@@ -1522,16 +1858,18 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     CK(wait_flow(p));
     RayParams rp{p->d.f, p->d.Cg, t0, t1, p->d.nsub, p->d.time_lerp};
     const double *So = f->snap[f->slot_map[0]], *Sn = f->snap[f->slot_map[1]];
-    const long long n = p->d.n;
+    const long long n = p->ncur;
+    p->since_sort++;
+    if (n == 0) return SWRT_OK;
     static const int minb = [] { const char* e = getenv("SWRT_RAYTRACE_MINB"); return e ? atoi(e) : 5; }();  // tuning knobs
     static const int cached = [] { const char* e = getenv("SWRT_RAYTRACE_CACHE"); return e ? atoi(e) : 4; }();   // 0 = plain kernel, 3 / 4 = stencil-cached kernel with that many CTAs per SM
     const unsigned grid = (unsigned)((n + 127) / 128);
     // TMA-staged tile kernel (packets.cuh): fp64 bilinear RK4, packets in sorted order, enough packets per tile to pay for the patch
     static const int tile_mode = [] { const char* e = getenv("SWRT_RAYTRACE_TILE"); return e ? atoi(e) : 1; }();
-    static const int tile_minb = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINB"); return e ? atoi(e) : 4; }();
+    static const int tile_minb = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINB"); return e ? atoi(e) : 3; }();   // 3 CTAs x 128 threads: 162 registers, no spills (0.81 ms vs 1.04 ms with 4 CTAs at 128 registers + spills, profiles/r02_a)
     static const int tile_min_pk = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINPK"); return e ? atoi(e) : 192; }();
-    const PacketGrid pg0 = packet_grid(f);
-    const long long ntiles = (long long)(pg0.nx >> TILE_SHIFT) * (pg0.ny >> TILE_SHIFT);
+    const PacketGrid pg = packet_grid(f, p);
+    const long long ntiles = (long long)(pg.nx >> TILE_SHIFT) * tile_rows(f, pg);
     const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode > 0 && n >= ntiles * (long long)tile_min_pk);
     const bool use_tile = want_tile && p->d.interp == SWRT_INTERP_BILINEAR && p->d.integrator == SWRT_INTEG_RK4 && p->tiles_valid &&
                           f->tmap_ok && ntiles > 0;
@@ -1546,14 +1884,14 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
         }
     }
     { ProfScope ps(f, K_RAYTRACE, pst(p));
-#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp)
+#define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp)
       if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
           static const int fminb = [] { const char* e = getenv("SWRT_RAYTRACE_F32_MINB"); return e ? atoi(e) : 6; }();
           const float4 *Fo = reinterpret_cast<const float4*>(So), *Fn = reinterpret_cast<const float4*>(Sn);
-          if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else if (fminb == 5) raytrace_rk4_f32_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else if (fminb == 6) raytrace_rk4_f32_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
-          else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, packet_grid(f), rp);
+          if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);
+          else if (fminb == 5) raytrace_rk4_f32_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);
+          else if (fminb == 6) raytrace_rk4_f32_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);
+          else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);
       }
       else if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
           if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else if (p->d.interp == 2) SWRT_GEN(2, 1); else SWRT_GEN(4, 1);
@@ -1561,20 +1899,19 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
-      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
+      else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
       else if (use_tile) {
           const size_t smem = 2 * (size_t)PATCH_BYTES;
-          if (tile_minb >= 4) raytrace_rk4_tile_kernel<4><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, packet_grid(f), rp);
-          else raytrace_rk4_tile_kernel<3><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, packet_grid(f), rp);
+          if (tile_minb >= 4) raytrace_rk4_tile_kernel<4><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, pg, rp);
+          else raytrace_rk4_tile_kernel<3><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, pg, rp);
       }
-      else if (cached == 3 && p->kernel_sel == SWRT_RAYKERNEL_AUTO) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp);
-      else raytrace_rk4_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, packet_grid(f), rp); }
+      else if (cached == 3 && p->kernel_sel == SWRT_RAYKERNEL_AUTO) raytrace_rk4_cached_kernel<3><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else if (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) raytrace_rk4_cached_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else if (minb <= 4) raytrace_rk4_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else if (minb == 5) raytrace_rk4_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else raytrace_rk4_kernel<6><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp); }
     CK(cudaGetLastError());
     CK(mark_read(p));
-    p->since_sort++;
     return SWRT_OK;
 }
 
@@ -1582,26 +1919,38 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     if (!p || !u_host || slot < 0 || slot > 1) return fail(SWRT_ERR_ARG, "bad argument");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
-    const long long n = p->d.n;
+    const long long n = p->d.n, nres = p->ncur;
     if (ld < n) return fail(SWRT_ERR_ARG, "leading dimension %lld < n", ld);
     CK(wait_flow(p));
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d", p->d.interp, f->interp);
-    if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
+    const PacketGrid pg = packet_grid(f, p);
+    const unsigned* idx = p->band ? nullptr : p->idx;          // band mode: resident order, brought to the caller's order by the gather
+    const unsigned grid = (unsigned)((nres + 127) / 128);
+    const double* S = f->snap[f->slot_map[slot]];
+    if (nres > 0) {
         ProfScope ps(f, K_SAMPLE, pst(p));
-        sample_f32_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, reinterpret_cast<const float4*>(f->snap[f->slot_map[slot]]), packet_grid(f), p->U, g_host ? p->Gd : nullptr);
-    } else if (p->d.interp == SWRT_INTERP_BSPLINE3) {
-        ProfScope ps(f, K_SAMPLE, pst(p));
-        sample_generic_kernel<4><<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
-    } else if (p->d.interp == SWRT_INTERP_BSPLINE2) {
-        ProfScope ps(f, K_SAMPLE, pst(p));
-        sample_generic_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
-    } else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) {
-        ProfScope ps(f, K_SAMPLE, pst(p));
-        sample_cubic_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr);
-    } else
-    { ProfScope ps(f, K_SAMPLE, pst(p)); sample_kernel<<<(unsigned)((n + 127) / 128), 128, 0, pst(p)>>>(p->xk, p->idx, n, f->snap[f->slot_map[slot]], packet_grid(f), p->U, g_host ? p->Gd : nullptr); }
+        if (p->d.interp == SWRT_INTERP_BILINEAR_F32) sample_f32_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, reinterpret_cast<const float4*>(S), pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+        else if (p->d.interp == SWRT_INTERP_BSPLINE3) sample_generic_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+        else if (p->d.interp == SWRT_INTERP_BSPLINE2) sample_generic_kernel<2><<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+        else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) sample_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+        else sample_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+    }
     CK(cudaGetLastError());
     CK(mark_read(p));
+    if (p->band) {   // COLLECTIVE: resident-order samples -> caller-order rows (through the alternate state buffer, 4 columns at a time)
+        int rc = band_peers_ready(p);
+        if (rc) return rc;
+        if ((rc = team_barrier(f))) return rc;
+        if ((rc = band_gather_launch(p, 1, 0, 2, p->xk2, p->cap))) return rc;
+        CK(copy_cols(u_host, p->xk2, n, 2, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
+        if (g_host) {
+            if ((rc = band_gather_launch(p, 1, 2, 4, p->xk2, p->cap))) return rc;
+            CK(copy_cols(g_host, p->xk2, n, 4, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
+        }
+        if ((rc = team_barrier(f))) return rc;
+        CK(cudaStreamSynchronize(f->st));
+        return SWRT_OK;
+    }
     CK(copy_cols(u_host, p->U, n, 2, ld, cudaMemcpyDeviceToHost, pst(p)));
     if (g_host) CK(copy_cols(g_host, p->Gd, n, 4, ld, cudaMemcpyDeviceToHost, pst(p)));
     if (sync) CK(cudaStreamSynchronize(pst(p)));
@@ -1618,9 +1967,12 @@ int swrt_packets_kcutoff_reset(swrt_packets* p, double kcut, double k0, long lon
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
-    const long long n = p->d.n;
+    const long long n = p->ncur;     // (band mode: the resident packets; the count is this rank's share)
     CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long), pst(p)));
-    { ProfScope ps(f, K_OTHER, pst(p)); kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, n, kcut * kcut, k0, p->count); }
+    if (n > 0) {
+        ProfScope ps(f, K_OTHER, pst(p));
+        kcutoff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, pst(p)>>>(p->xk, n, p->cap, kcut * kcut, k0, p->count);
+    }
     CK(cudaGetLastError());
     if (nreset) {   // the count is only fetched (and the stream only synchronised) when the caller asks for it
         unsigned long long c = 0;
@@ -1638,12 +1990,12 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     swrt_flow* f = p->flow;
     // everything a step can reject is checked before any step (a failure inside a graph capture would leave the clock advanced)
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d (swrt_flow_set_interp)", p->d.interp, f->interp);
-    if (f->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: drive the loop from the host (slab.py)");
     { int rc = check_psi_kind(f, psi_kind); if (rc) return rc; }
+    if (f->P > 1 && !f->p2p) return fail(SWRT_ERR_STATE, "slab-decomposed flow without mapped peers: drive the loop from the host (slab.py)");
     auto body = [&]() -> int {
-        int rc = swrt_flow_step(f, 1);
+        int rc = f->P > 1 ? swrt_slab_step(f, 1) : swrt_flow_step(f, 1);
         if (rc) return rc;
-        if ((rc = swrt_flow_velocity_snapshot(f, psi_kind, 1))) return rc;
+        if ((rc = f->P > 1 ? swrt_slab_band_snapshot(f, psi_kind, 1) : swrt_flow_velocity_snapshot(f, psi_kind, 1))) return rc;
         // the tracer only sees t - t0 and t1 - t0: every step is traced over (0, dt), which makes the kernel arguments of
         // consecutive steps identical (the absolute (old_t, new_t) of the per-call loop differ from this by rounding only)
         if ((rc = swrt_packets_raytrace(p, 0.0, f->d.dt))) return rc;

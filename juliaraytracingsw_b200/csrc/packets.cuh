@@ -33,7 +33,21 @@ constexpr int PATCH_BYTES = (PATCH * PATCH_ROW * 8 + 127) / 128 * 128;   // one 
 struct PacketGrid {
     int nx, ny;
     double x0, y0, dx, dy, inv_dx, inv_dy;
+    long long ld;          // column stride of the packet arrays ((N,4) column-major: n on one GPU, the capacity in band mode)
+    // Band mode (team of GPUs, y-band-sharded packets): the snapshot arrays hold only rows [jb, jb + jrows) of the grid (this
+    // rank's band plus halo rows, jb may be negative = wraps), so a grid row j lives at local row (j - jb) mod ny.
+    int band, jb, jrows;
+    int tile_row0;         // band mode: first tile row the tile kernel's grid covers (wraps)
 };
+// grid rows (j0, j0 + 1) of a bilinear stencil -> rows of the snapshot array
+__device__ __forceinline__ void stencil_rows(const PacketGrid& g, int& j0, int& j1) {
+    if (g.band) {
+        int jl = (j0 - g.jb) & (g.ny - 1);
+        if (jl > g.jrows - 2) jl = g.jrows - 2;      // outside band + halo: clamped here, counted at the next sort (sort_hist_kernel)
+        j0 = jl;
+        j1 = jl + 1;
+    }
+}
 
 // s = (x - x0)/dx ; i = floor(s) mod n ; a = s - floor(s).  The division is a multiplication by 1/dx (fp64 division
 // costs ~15 issue slots): s can differ from the oracle's by one ulp, which moves the interpolated value by O(1e-16)
@@ -83,6 +97,7 @@ __device__ __forceinline__ void ray_rhs(const double (&s)[4], double sign, doubl
     double a, b;
     cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    stencil_rows(g, j0, j1);
     double o[5], nw[5], W[5];
     bilinear5(So, g, i0, i1, j0, j1, a, b, o);
     bilinear5(Sn, g, i0, i1, j0, j1, a, b, nw);
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
                                                                  PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -124,9 +139,9 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
     }
     __stcs(xk + i, s[0]);
-    __stcs(xk + n + i, s[1]);
-    __stcs(xk + 2 * n + i, s[2]);
-    __stcs(xk + 3 * n + i, s[3]);
+    __stcs(xk + g.ld + i, s[1]);
+    __stcs(xk + 2 * g.ld + i, s[2]);
+    __stcs(xk + 3 * g.ld + i, s[3]);
 }
 
 // ---------------------------------------------------------------- stencil-cached variant
@@ -165,6 +180,7 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
     if (i0 != st.ci || j0 != st.cj) {
         st.ci = i0;
         st.cj = j0;
+        stencil_rows(g, j0, j1);
         const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
 #pragma unroll
         for (int lev = 0; lev < 2; ++lev) {
@@ -209,7 +225,7 @@ __device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     // the packet state is read and written exactly once per launch: streaming accesses leave L2 to the node records
-    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};
     const double sg = __ldcs(sign + i);
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     Stencil st;
@@ -234,9 +250,9 @@ __device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
     __stcs(xk + i, s[0]);
-    __stcs(xk + n + i, s[1]);
-    __stcs(xk + 2 * n + i, s[2]);
-    __stcs(xk + 3 * n + i, s[3]);
+    __stcs(xk + g.ld + i, s[1]);
+    __stcs(xk + 2 * g.ld + i, s[2]);
+    __stcs(xk + 3 * g.ld + i, s[3]);
 }
 
 template <int MINB>
@@ -294,7 +310,9 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
     if (i0 != st.ci || j0 != st.cj) {
         st.ci = i0;
         st.cj = j0;
-        const unsigned ri = (unsigned)(i0 - tp.pi), rj = (unsigned)(j0 - tp.pj);   // no wrap needed: staged tiles are interior
+        // patch-relative node: masked differences, so a patch that wraps in y (band mode: halo rows beyond the domain edge) works;
+        // in x staged tiles are interior and the mask is a no-op
+        const unsigned ri = (unsigned)((i0 - tp.pi) & (g.nx - 1)), rj = (unsigned)((j0 - tp.pj) & (g.ny - 1));
         if (tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1)) {
             const int o = rj * PATCH_ROW + ri * SNAP_STRIDE;
 #pragma unroll
@@ -309,6 +327,7 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
                 }
             }
         } else {
+            stencil_rows(g, j0, j1);
             const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
 #pragma unroll
             for (int lev = 0; lev < 2; ++lev) {
@@ -354,8 +373,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
                              const unsigned* __restrict__ tile_end, PacketGrid g, RayParams p) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ __align__(8) unsigned long long bar;
-    const int tiles_x = g.nx >> TILE_SHIFT;
-    const int tile = blockIdx.x, tj = tile / tiles_x, ti = tile - tj * tiles_x;
+    const int tiles_x = g.nx >> TILE_SHIFT, tiles_y = g.ny >> TILE_SHIFT;
+    const int tjl = blockIdx.x / tiles_x, ti = blockIdx.x - tjl * tiles_x;
+    const int tj = (g.tile_row0 + tjl) % tiles_y;                // band mode: the grid covers the tile rows of band + halo only
+    const int tile = tj * tiles_x + ti;
     const long long key0 = (long long)tile << (2 * TILE_SHIFT);
     const long long start = tile == 0 ? 0 : (long long)tile_end[key0 - 1], end = (long long)tile_end[key0 + (TILE * TILE - 1)];
     if (start >= end) return;                                     // empty tile (uniform over the CTA)
@@ -364,21 +385,26 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
     tp.lev[1] = reinterpret_cast<const double*>(tile_smem + PATCH_BYTES);
     tp.pi = ti * TILE - TILE_MARGIN;
     tp.pj = tj * TILE - TILE_MARGIN;
-    tp.staged = tp.pi >= 0 && tp.pj >= 0 && tp.pi + PATCH <= g.nx && tp.pj + PATCH <= g.ny;
+    int prow = tp.pj;                                            // row of the snapshot array where the patch starts
+    if (g.band) {
+        prow = (tp.pj - g.jb) & (g.ny - 1);
+        if (prow >= g.ny / 2) prow -= g.ny;                      // signed distance from the first resident row
+    }
+    tp.staged = tp.pi >= 0 && prow >= 0 && tp.pi + PATCH <= g.nx && prow + PATCH <= (g.band ? g.jrows : g.ny);
     if (tp.staged) {
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, 2u * PATCH * PATCH_ROW * 8);
-            tma_load_2d(tile_smem, &mapO, tp.pi * SNAP_STRIDE, tp.pj, &bar);
-            tma_load_2d(tile_smem + PATCH_BYTES, &mapN, tp.pi * SNAP_STRIDE, tp.pj, &bar);
+            tma_load_2d(tile_smem, &mapO, tp.pi * SNAP_STRIDE, prow, &bar);
+            tma_load_2d(tile_smem + PATCH_BYTES, &mapN, tp.pi * SNAP_STRIDE, prow, &bar);
         }
     }
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     bool waited = !tp.staged;
     for (long long i = start + threadIdx.x; i < end; i += TILE_THREADS) {
         // the packet state is read and written exactly once per launch: streaming accesses leave L2 to the node records
-        double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};
+        double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};
         const double sg = __ldcs(sign + i);
         if (!waited) { mbar_wait(&bar, 0); waited = true; }      // the patch has landed (first state loads overlapped the copy)
         Stencil st;
@@ -402,9 +428,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
             for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
         }
         __stcs(xk + i, s[0]);
-        __stcs(xk + n + i, s[1]);
-        __stcs(xk + 2 * n + i, s[2]);
-        __stcs(xk + 3 * n + i, s[3]);
+        __stcs(xk + g.ld + i, s[1]);
+        __stcs(xk + 2 * g.ld + i, s[2]);
+        __stcs(xk + 3 * g.ld + i, s[3]);
     }
     // (thread 0 always owns packet `start` and waits for the copy above, so the CTA never retires with a copy in flight)
 }
@@ -487,7 +513,7 @@ __global__ void __launch_bounds__(128, 4) raytrace_rk4_cubic_kernel(double* __re
                                                                     PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -508,29 +534,29 @@ __global__ void __launch_bounds__(128, 4) raytrace_rk4_cubic_kernel(double* __re
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
     __stcs(xk + i, s[0]);
-    __stcs(xk + n + i, s[1]);
-    __stcs(xk + 2 * n + i, s[2]);
-    __stcs(xk + 3 * n + i, s[3]);
+    __stcs(xk + g.ld + i, s[1]);
+    __stcs(xk + 2 * g.ld + i, s[2]);
+    __stcs(xk + 3 * g.ld + i, s[3]);
 }
 
 __global__ void __launch_bounds__(128) sample_cubic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                            const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
-                                                           double* __restrict__ Gd) {
+                                                           double* __restrict__ Gd, long long ldo) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int i0, i1, j0, j1;
     double a, b, Sv[5];
     cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, a);
-    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    cell(xk[g.ld + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
     sample_hermite5(S, g, i0, i1, j0, j1, a, b, Sv);
-    const long long o = idx[i];
+    const long long o = idx ? (long long)idx[i] : i;
     U[o] = Sv[0];
-    U[n + o] = Sv[1];
+    U[ldo + o] = Sv[1];
     if (Gd) {
         Gd[o] = Sv[2];
-        Gd[n + o] = Sv[3];
-        Gd[2 * n + o] = Sv[4];
-        Gd[3 * n + o] = -Sv[2];
+        Gd[ldo + o] = Sv[3];
+        Gd[2 * ldo + o] = Sv[4];
+        Gd[3 * ldo + o] = -Sv[2];
     }
 }
 
@@ -622,7 +648,7 @@ __global__ void __launch_bounds__(128, 3) raytrace_generic_kernel(double* __rest
                                                                   PacketGrid g, RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};   // streaming: read once
     const double sg = sign[i];
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     for (int it = 0; it < p.nsub; ++it) {
@@ -657,26 +683,26 @@ __global__ void __launch_bounds__(128, 3) raytrace_generic_kernel(double* __rest
         }
     }
     __stcs(xk + i, s[0]);
-    __stcs(xk + n + i, s[1]);
-    __stcs(xk + 2 * n + i, s[2]);
-    __stcs(xk + 3 * n + i, s[3]);
+    __stcs(xk + g.ld + i, s[1]);
+    __stcs(xk + 2 * g.ld + i, s[2]);
+    __stcs(xk + 3 * g.ld + i, s[3]);
 }
 template <int INTERP>
 __global__ void __launch_bounds__(128) sample_generic_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                              const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
-                                                             double* __restrict__ Gd) {
+                                                             double* __restrict__ Gd, long long ldo) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double Sv[5];
-    sample_level5<INTERP>(S, g, xk[i], xk[n + i], Sv);
-    const long long o = idx[i];
+    sample_level5<INTERP>(S, g, xk[i], xk[g.ld + i], Sv);
+    const long long o = idx ? (long long)idx[i] : i;
     U[o] = Sv[0];
-    U[n + o] = Sv[1];
+    U[ldo + o] = Sv[1];
     if (Gd) {
         Gd[o] = Sv[2];
-        Gd[n + o] = Sv[3];
-        Gd[2 * n + o] = Sv[4];
-        Gd[3 * n + o] = -Sv[2];
+        Gd[ldo + o] = Sv[3];
+        Gd[2 * ldo + o] = Sv[4];
+        Gd[3 * ldo + o] = -Sv[2];
     }
 }
 
@@ -738,7 +764,7 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_f32_kernel(double* __r
                                                                   RayParams p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double s[4] = {__ldcs(xk + i), __ldcs(xk + n + i), __ldcs(xk + 2 * n + i), __ldcs(xk + 3 * n + i)};   // streaming: read once
+    double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};   // streaming: read once
     const float sg = (float)sign[i], f2 = (float)(p.f * p.f), cg2 = (float)(p.Cg * p.Cg);
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     StencilF st;
@@ -762,19 +788,19 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_f32_kernel(double* __r
         for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
     }
     __stcs(xk + i, s[0]);
-    __stcs(xk + n + i, s[1]);
-    __stcs(xk + 2 * n + i, s[2]);
-    __stcs(xk + 3 * n + i, s[3]);
+    __stcs(xk + g.ld + i, s[1]);
+    __stcs(xk + 2 * g.ld + i, s[2]);
+    __stcs(xk + 3 * g.ld + i, s[3]);
 }
 __global__ void __launch_bounds__(128) sample_f32_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                          const float4* __restrict__ S, PacketGrid g, double* __restrict__ U,
-                                                         double* __restrict__ Gd) {
+                                                         double* __restrict__ Gd, long long ldo) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int i0, i1, j0, j1;
     double ad, bd;
     cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, ad);
-    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, bd);
+    cell(xk[g.ld + i], g.y0, g.inv_dy, g.ny, j0, j1, bd);
     const float a = (float)ad, b = (float)bd;
     const float wb[4] = {(1.f - a) * (1.f - b), a * (1.f - b), (1.f - a) * b, a * b};
     const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
@@ -785,14 +811,14 @@ __global__ void __launch_bounds__(128) sample_f32_kernel(const double* __restric
         W[0] = fmaf(wb[cr], q0.x, W[0]); W[1] = fmaf(wb[cr], q0.y, W[1]); W[2] = fmaf(wb[cr], q0.z, W[2]); W[3] = fmaf(wb[cr], q0.w, W[3]);
         W[4] = fmaf(wb[cr], q1.x, W[4]);
     }
-    const long long o = idx[i];
+    const long long o = idx ? (long long)idx[i] : i;
     U[o] = W[0];
-    U[n + o] = W[1];
+    U[ldo + o] = W[1];
     if (Gd) {
         Gd[o] = W[2];
-        Gd[n + o] = W[3];
-        Gd[2 * n + o] = W[4];
-        Gd[3 * n + o] = -W[2];
+        Gd[ldo + o] = W[3];
+        Gd[2 * ldo + o] = W[4];
+        Gd[3 * ldo + o] = -W[2];
     }
 }
 // fp32 node records -> planar (nx, ny, 5) doubles for swrt_flow_get_snapshot
@@ -806,39 +832,40 @@ __global__ void snapf_to_planar_kernel(const float* __restrict__ S, long long np
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                      const double* __restrict__ S, PacketGrid g, double* __restrict__ U,
-                                                     double* __restrict__ Gd) {
+                                                     double* __restrict__ Gd, long long ldo) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int i0, i1, j0, j1;
     double a, b, Sv[5];
     cell(xk[i], g.x0, g.inv_dx, g.nx, i0, i1, a);
-    cell(xk[n + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    cell(xk[g.ld + i], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    stencil_rows(g, j0, j1);
     bilinear5(S, g, i0, i1, j0, j1, a, b, Sv);
-    const long long o = idx[i];
+    const long long o = idx ? (long long)idx[i] : i;
     U[o] = Sv[0];
-    U[n + o] = Sv[1];
+    U[ldo + o] = Sv[1];
     if (Gd) {
         Gd[o] = Sv[2];
-        Gd[n + o] = Sv[3];
-        Gd[2 * n + o] = Sv[4];
-        Gd[3 * n + o] = -Sv[2];
+        Gd[ldo + o] = Sv[3];
+        Gd[2 * ldo + o] = Sv[4];
+        Gd[3 * ldo + o] = -Sv[2];
     }
 }
 
-__global__ void kcutoff_kernel(double* __restrict__ xk, long long n, double kc2, double k0, unsigned long long* count) {
+__global__ void kcutoff_kernel(double* __restrict__ xk, long long n, long long ld, double kc2, double k0, unsigned long long* count) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double k = xk[2 * n + i], l = xk[3 * n + i];
+    const double k = xk[2 * ld + i], l = xk[3 * ld + i];
     if (k * k + l * l >= kc2) {
-        xk[2 * n + i] = k0;
-        xk[3 * n + i] = 0.0;
+        xk[2 * ld + i] = k0;
+        xk[3 * ld + i] = 0.0;
         atomicAdd(count, 1ULL);
     }
 }
 
 // generate_initial_wavepackets (raytracing/RaytracingDriver.jl:27-47); p = global 1-based packet index
 __global__ void generate_packets_kernel(double* __restrict__ xk, double* __restrict__ sign, unsigned* __restrict__ idx, long long n,
-                                        long long first, long long sqrtN, double L, double k0) {
+                                        long long ld, long long first, long long sqrtN, double L, double k0) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const long long p0 = first + i;  // 0-based global
@@ -846,10 +873,10 @@ __global__ void generate_packets_kernel(double* __restrict__ xk, double* __restr
     const double offset = L / (double)sqrtN / 2.0;
     const long long ix = p0 % sqrtN + 1, iy = p0 / sqrtN + 1;
     xk[i] = (double)ix * L / (double)sqrtN - L / 2.0 - offset;
-    xk[n + i] = (double)iy * L / (double)sqrtN - L / 2.0 - offset;
+    xk[ld + i] = (double)iy * L / (double)sqrtN - L / 2.0 - offset;
     const double phase = 2.0 * 3.141592653589793 * (double)(p0 + 1) / (double)ntot;
-    xk[2 * n + i] = k0 * cos(phase);
-    xk[3 * n + i] = k0 * sin(phase);
+    xk[2 * ld + i] = k0 * cos(phase);
+    xk[3 * ld + i] = k0 * sin(phase);
     sign[i] = (p0 % 2 == 0) ? -1.0 : 1.0;
     idx[i] = (unsigned)i;
 }
@@ -869,10 +896,17 @@ __device__ __forceinline__ unsigned cell_key(double x, double y, const PacketGri
 }
 
 __global__ void sort_hist_kernel(const double* __restrict__ xk, long long n, PacketGrid g, unsigned* __restrict__ keys,
-                                 unsigned* __restrict__ hist) {
+                                 unsigned* __restrict__ hist, unsigned long long* __restrict__ violations) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned k = cell_key(xk[i], xk[n + i], g);
+    const unsigned k = cell_key(xk[i], xk[g.ld + i], g);
+    if (g.band) {   // a packet that left band + halo since the last migration sampled clamped rows: report it
+        int i0, i1, j0, j1;
+        double a;
+        cell(xk[g.ld + i], g.y0, g.inv_dy, g.ny, j0, j1, a);
+        (void)i0; (void)i1;
+        if (((j0 - g.jb) & (g.ny - 1)) > g.jrows - 2) atomicAdd(violations, 1ULL);
+    }
     keys[i] = k;
     atomicAdd(&hist[k], 1u);
 }
@@ -901,24 +935,24 @@ __global__ void scan_add_kernel(unsigned* __restrict__ a, long long nb, const un
 
 // scatter packet i to its sorted slot and move its state (the order inside a cell is arbitrary)
 __global__ void sort_scatter_kernel(const double* __restrict__ xk, const double* __restrict__ sign, const unsigned* __restrict__ idx,
-                                    const unsigned* __restrict__ keys, unsigned* __restrict__ offsets, long long n,
+                                    const unsigned* __restrict__ keys, unsigned* __restrict__ offsets, long long n, long long ld,
                                     double* __restrict__ xk2, double* __restrict__ sign2, unsigned* __restrict__ idx2) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned pos = atomicAdd(&offsets[keys[i]], 1u);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) xk2[c * n + pos] = xk[c * n + i];
+    for (int c = 0; c < 4; ++c) xk2[c * ld + pos] = xk[c * ld + i];
     sign2[pos] = sign[i];
     idx2[pos] = idx[i];
 }
 
 // host-visible order: out[c][idx[i]] = xk[c][i]
-__global__ void unpermute_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n, int ncols,
+__global__ void unpermute_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n, long long ld, int ncols,
                                  double* __restrict__ out) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const long long o = idx[i];
-    for (int c = 0; c < ncols; ++c) out[c * n + o] = xk[c * n + i];
+    const long long o = idx ? (long long)idx[i] : i;
+    for (int c = 0; c < ncols; ++c) out[c * ld + o] = xk[c * ld + i];
 }
 
 // snapshot half <-> planar (nx, ny, 5) host layout staging
