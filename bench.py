@@ -41,6 +41,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--parallel", default="team", choices=["team", "replicated"],
+                    help="N > 1: `team` (default) = flow slab-decomposed over the ranks + packets sharded by y-band, all native over CUDA "
+                         "IPC; `replicated` = round-1 scheme (every rank repeats the flow step, packets sharded by index)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config2 / config3 / config5 extra keys")
     return ap.parse_args()
 
 
@@ -209,7 +213,19 @@ def run_swrt(args):
     ntot = P.Npackets
     lo, hi = rank * ntot // world, (rank + 1) * ntot // world
     nloc = hi - lo
+    team = world > 1 and args.parallel == "team"
     prob, _ = drivers.initialize_problem(P, dev=local)
+    if team:
+        # the synthetic initial condition is built once on a single-GPU problem (setup only), then handed to the team:
+        # rank r keeps its kr columns of the state and traces the packets of its band of ny / world rows
+        from juliaraytracingsw_b200.slab import SlabProblem
+        sol0 = prob.sol
+        dt, ν = drivers.timestep_and_viscosity(P)
+        prob.close()
+        prob = SlabProblem(dist, local, nx=P.nx, Lx=P.L, dt=dt, f=P.f, Cg=P.Cg, ν=ν, nν=P.nν, order=P.filter_order,
+                           use_filter=P.use_filter, aliased_fraction=P.aliased_fraction)
+        prob.sol = sol0
+        del sol0
     k0 = (P.ω0 ** 2 - P.f ** 2) ** 0.5 / P.background_Cg
     packets = raytracing.generate_initial_wavepackets(prob, P.L, k0, nloc, P.sqrtNpackets, P.f, P.packet_Cg, nsub=P.nsub, first=lo)
     raytracing.get_velocity_info(prob, 0)
@@ -253,12 +269,15 @@ def run_swrt(args):
     # ---- flow-only step (BASELINE: "RSW 2048^2 spectral steps/s (HBM %roofline)")
     prob.sync(); barrier()
     prob.timer_start()
-    flow.stepforward(prob, (), K)
+    if team:
+        prob.stepforward(K)
+    else:
+        flow.stepforward(prob, (), K)
     ms_flow = max_over_ranks(prob.timer_stop()) / K
 
     # ---- optional fp32 packet mode (north star: "reported separately"): Float32 node data + fp32 right-hand side, fp64 state
     fp32 = None
-    if not args.no_fp32:
+    if not args.no_fp32 and not team:
         raytracing.set_interpolation(prob, raytracing.INTERP_BILINEAR_F32)
         p32 = raytracing.Packets(prob, nloc, P.f, P.packet_Cg, nsub=P.nsub, interp=raytracing.INTERP_BILINEAR_F32)
         p32.set(packets.get(), np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0))

@@ -140,8 +140,11 @@ def initialize_problem(P: Parameters, dev=0):
 def coupled_step(prob, packets, old_t):
     """Body of the hot loop, raytracing/RaytracingDriver.jl:256-270: one flow step, new velocity snapshot,
     ray-trace all packets across it, new becomes old.  Returns new_t."""
-    flow.stepforward(prob, (), 1)
-    flow.updatevars(prob)
+    if getattr(prob, "world", 1) > 1:
+        prob.stepforward(1)                                        # team mode: slab-decomposed step
+    else:
+        flow.stepforward(prob, (), 1)
+        flow.updatevars(prob)
     new_velocity, new_grad_v = raytracing.get_velocity_info(prob, 1)
     new_t = prob.clock.t
     raytracing.raytrace(packets, None, new_velocity, None, new_grad_v, prob.grid, packets, prob.dt, (old_t, new_t))

@@ -27,6 +27,8 @@ class Velocity:
         self.prob, self.slot = prob, slot
 
     def _arr(self):
+        if getattr(self.prob, "world", 1) > 1:
+            return self.prob.gather_snapshot(self.slot)             # team mode: assembled from the bands of all ranks
         g = self.prob.grid
         nf = C.c_int()
         check(lib().swrt_flow_snapshot_fields(self.prob._h, C.byref(nf)))
@@ -51,7 +53,10 @@ class VelocityGradient(Velocity):
 def get_velocity_info(prob, slot, psi_kind=PSI_RSW_BALANCED):
     """get_streamfunction! + get_velocity_info (rsw/RSWRaytracingDriver.jl:56-67,
     raytracing/RaytracingDriver.jl:132-154) into snapshot `slot`; returns (Velocity, VelocityGradient)."""
-    check(lib().swrt_flow_velocity_snapshot(prob._h, psi_kind, slot))
+    if getattr(prob, "world", 1) > 1:
+        prob.velocity_snapshot(slot, psi_kind)                     # team mode: this rank's band of rows
+    else:
+        check(lib().swrt_flow_velocity_snapshot(prob._h, psi_kind, slot))
     return Velocity(prob, slot), VelocityGradient(prob, slot)
 
 
@@ -69,6 +74,8 @@ def set_snapshot_refinement(prob, refine):
 
 def set_velocity_info(prob, slot, fields):
     """Load (nx, ny, 5) = u, v, ux, uy, vx (or (nx, ny, 7) with uxy, vxy in Hermite mode) host fields into a slot."""
+    if getattr(prob, "world", 1) > 1:
+        return prob.set_snapshot(slot, fields)
     a = np.asfortranarray(fields, dtype=np.float64)
     nf = C.c_int()
     check(lib().swrt_flow_snapshot_fields(prob._h, C.byref(nf)))
@@ -87,11 +94,37 @@ class Packets:
     """Device-resident wave packets = `create_template_ode(packets)` + the packet arrays."""
 
     def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16, interp=INTERP_BILINEAR,
-                 integrator=INTEG_RK4):
+                 integrator=INTEG_RK4, first=None, capacity=None):
+        """On a slab-decomposed problem (slab.SlabProblem, team mode) the packets are sharded by y-band: `n` is this rank's
+        caller-order block, rows [first, first + n) of the ensemble (default: blocks in rank order), `capacity` the packets a
+        rank can host (default 1.5 x the mean + 4096, the same on every rank); every method becomes a collective call."""
         self.prob, self.n = prob, int(n)
-        d = PacketsDesc(n=self.n, interp=int(interp), integrator=int(integrator), nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg)
+        self.band = getattr(prob, "world", 1) > 1
+        if self.band:
+            counts = prob._gather(self.n)
+            if first is None:
+                first = sum(counts[:prob.rank])
+            if capacity is None:
+                capacity = max(int(1.5 * -(-sum(counts) // prob.world)) + 4096, max(counts))
+            if len(set(prob._gather(int(capacity)))) != 1:
+                raise ValueError("band packets: `capacity` must be the same on every rank")
+        self.first = int(first or 0)
+        d = PacketsDesc(n=self.n, interp=int(interp), integrator=int(integrator), nsub=int(nsub), time_lerp=int(time_lerp), sort_every=int(sort_every), f=f, Cg=Cg,
+                        band_first=self.first, band_capacity=int(capacity or 0))
         self._h = C.c_void_p()
         check(lib().swrt_packets_create(C.byref(d), prob._h, C.byref(self._h)))
+        if self.band:                                               # one exchange of 64-byte IPC handles
+            buf = C.create_string_buffer(64)
+            check(lib().swrt_packets_ipc_handle(self._h, buf))
+            for r, h in enumerate(prob._gather(buf.raw)):
+                check(lib().swrt_packets_ipc_open(self._h, r, h))
+            prob.dist.barrier()
+
+    def resident(self):
+        """Packets currently hosted by this rank (band mode; = n otherwise)."""
+        n = C.c_longlong()
+        check(lib().swrt_packets_resident(self._h, C.byref(n)))
+        return n.value
 
     def close(self):
         if getattr(self, "_h", None):
@@ -157,13 +190,13 @@ class Packets:
     def kcutoff_reset(self, k_cutoff, k0):
         n = C.c_longlong()
         check(lib().swrt_packets_kcutoff_reset(self._h, k_cutoff, k0, C.byref(n)))
-        return n.value
+        return sum(self.prob._gather(n.value)) if self.band else n.value
 
 
 def generate_initial_wavepackets(prob, L, k0, Npackets, sqrtNpackets, f, Cg, nsub=1, first=0, time_lerp=LERP_PHYSICAL,
                                  sort_every=16):
     """raytracing/RaytracingDriver.jl:27-47; `first`/`Npackets` select a contiguous shard of the lattice."""
-    p = Packets(prob, Npackets, f, Cg, nsub=nsub, time_lerp=time_lerp, sort_every=sort_every)
+    p = Packets(prob, Npackets, f, Cg, nsub=nsub, time_lerp=time_lerp, sort_every=sort_every, first=first)
     p.generate(L, k0, sqrtNpackets, first)
     return p
 

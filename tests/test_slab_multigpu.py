@@ -1,4 +1,7 @@
-"""Runs the slab-decomposed flow step on every visible GPU (>= 2) under torchrun and checks it against the single-GPU step."""
+"""Team mode (slab-decomposed flow step + y-band-sharded packets) under torchrun, checked against the oracle by
+tests/multigpu/team_parity.py.  With fewer GPUs than ranks every rank shares cuda:0 (CUDA IPC works between processes on one
+device; gloo process group, host-side team barrier), so the test also runs on the single-GPU box; with enough GPUs each rank
+gets its own and the barrier is the device one (flag words over NVLink)."""
 import os
 import subprocess
 import sys
@@ -8,17 +11,30 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _run(script, nproc, port, env=None, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu", script)]
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the oracle's FFT workers are set explicitly (oracle/grid.py)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=dict(os.environ, **(env or {})))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_team_parity_against_the_oracle(nproc):
+    import torch
+    same = torch.cuda.device_count() < nproc
+    r = _run("team_parity.py", nproc, 29533 + nproc, env={"SWRT_TEAM_SAME_GPU": "1" if same else "0"})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
+    assert f"team parity ok on {nproc} ranks" in r.stdout
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["push", "copy", "pull"])
-def test_slab_step_matches_single_gpu(mode):
-    """`mode` = variant of the first transpose (slab.py): peer stores from the y-pass, block-copy kernel, or x-pass pull."""
+def test_slab_step_variants_match_the_single_gpu_step(mode):
+    """`mode` = variant of the first transpose (slab.py): peer stores from the y-pass, block-copy kernel, or x-pass pull;
+    plus the NCCL all_to_all_single variant when every rank has its own GPU."""
     import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs >= 2 GPUs (slab decomposition)")
-    p = 1 << (n.bit_length() - 1)        # largest power of two
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={p}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(ROOT, "tests", "multigpu", "slab_parity.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, SWRT_SLAB_MODE=mode))
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    same = torch.cuda.device_count() < 2
+    r = _run("slab_parity.py", 2, 29541, env={"SWRT_SLAB_MODE": mode, "SWRT_TEAM_SAME_GPU": "1" if same else "0"})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
     assert "slab parity ok" in r.stdout
