@@ -163,7 +163,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    steps, warm = max(1, min(args.steps, 30)), max(0, min(args.warmup, 3))   # a step costs seconds on the host: bounded
+    steps, warm = max(1, min(args.steps, 30)), max(3, min(args.warmup, 5))   # a step costs ~1 s on the host: bounded; warm-up >= 3 like the GPU arm
     r = cpu_sample(args, steps, warm, cores)
     ntot = args.sqrt_packets ** 2
     line = {
@@ -172,12 +172,130 @@ def run_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "nsub": args.nsub,
                    "integrator": "RK4", "interp": "bilinear"},
-        "cpu_baseline": {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "omp_threads": r["omp_threads"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "packet-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference algorithm (oracle/); the reference itself is Julia and cannot run here",
     }
     print(json.dumps(line), flush=True)
 
+
+
+# ----------------------------------------------------------------------------------------------- measured-elsewhere evidence
+def load_ncu_traffic():
+    """DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum) of the kernels this bench names, from the
+    committed profiles/ncu_traffic.json (written by profiles/summarize_ncu.py from a `ncu --set full` capture; each entry says
+    which capture and which commit it came from).  Absent file or kernel -> None: nothing is hard-coded here."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+# ----------------------------------------------------------------------------------------------- the other BASELINE configs
+def extra_config2(dev):
+    """BASELINE config 2: RSW 512^2 + 65 536 packets (rsw/RSWRaytracingMain), the driver's hot loop in one library call per 120 steps
+    (six-step CUDA graphs between the cell sorts)."""
+    from juliaraytracingsw_b200 import drivers, raytracing
+    P = drivers.Parameters(nx=512, sqrtNpackets=256)
+    prob, _ = drivers.initialize_problem(P, dev=dev)
+    k0 = (P.ω0 ** 2 - P.f ** 2) ** 0.5 / P.background_Cg
+    pk = raytracing.generate_initial_wavepackets(prob, P.L, k0, P.Npackets, P.sqrtNpackets, P.f, P.packet_Cg)
+    raytracing.get_velocity_info(prob, 0)
+    drivers.coupled_steps(prob, pk, 120)
+    prob.sync()
+    n = 1200
+    l0 = prob.launch_count()
+    prob.timer_start()
+    drivers.coupled_steps(prob, pk, n)
+    ms = prob.timer_stop()
+    out = {"workload": "RSW 512^2 IFMAB3 + 65536 packets, swrt_packets_coupled_steps (BASELINE config 2)", "steps": n, "ms_per_step": ms / n,
+           "value": P.Npackets * n / (ms * 1e-3), "unit": "packet-steps/s", "flow_steps_per_s": 1e3 * n / ms,
+           "gpu_launches_per_step": (prob.launch_count() - l0) / n}
+    pk.close(); prob.close()
+    return out
+
+
+def extra_config3(dev):
+    """BASELINE config 3: Thomas-Yamada 1024^2, Lx = 6 pi, ETDRK4 (thomasyamada/gpu-setup/Parameters.jl), free evolution with the
+    k-omega accumulator appending one frame per step (thomasyamada/TY_k_omega.jl as a streaming device-side series)."""
+    import juliaraytracingsw_b200 as swrt
+    from juliaraytracingsw_b200 import flow, komega
+    nx, Lx, dt, nnu = 1024, 6 * np.pi, 5e-3, 8
+    nu = 5e-34 * (Lx / (2 * np.pi)) ** 16
+    prob = swrt.Problem(dev, model="ThomasYamada", stepper="ETDRK4", nx=nx, Lx=Lx, dt=dt, nu=nu, nnu=nnu, Ro=1.0)
+    rng = np.random.default_rng(5678)
+    g = prob.grid
+    sol = np.zeros((g.nkr, g.nl, 4), dtype=np.complex128)
+    band = (g.Krsq > 0) & (g.Krsq <= (13 / 3) ** 2)
+    for v in range(4):
+        ph = np.exp(2j * np.pi * rng.random((g.nkr, g.nl)))
+        sol[:, :, v][band] = (0.05 * nx * nx / 40.0 * ph)[band]
+    sol[0] = 0
+    prob.sol = sol
+    flow.stepforward(prob, (), 5)
+    prob.sync()
+    n = 40
+    prob.timer_start()
+    flow.stepforward(prob, (), n)
+    ms = prob.timer_stop()
+    kw = komega.KOmega(prob, k_idx=9, max_frames=n + 4)
+    kw.append()
+    prob.sync()
+    prob.timer_start()
+    for _ in range(n):
+        flow.stepforward(prob, (), 1)
+        kw.append()
+    ms_kw = prob.timer_stop()
+    F = 8.0 * nx * nx
+    out = {"workload": "Thomas-Yamada 1024^2 ETDRK4 free evolution (BASELINE config 3)", "steps": n, "ms_per_step": ms / n, "steps_per_s": 1e3 * n / ms,
+           "with_komega_frame_every_step": {"ms_per_step": ms_kw / n, "steps_per_s": 1e3 * n / ms_kw, "append_ms": (ms_kw - ms) / n},
+           "algorithmic_bytes_per_step": 268 * F, "achieved_gbs": 268 * F / (ms / n * 1e-3) / 1e9,
+           "contract": "B_step ~ 268 F (SURVEY.md 8d, 4 calcN! of 20 min. transforms + 11 pointwise + 16 stepper streams each)",
+           "finite": bool(np.isfinite(flow.kinetic_energy(prob)))}
+    kw.close(); prob.close()
+    return out
+
+
+def extra_config5(dist, local, world, steps):
+    """BASELINE config 5: two-layer QG 4096^2 slab-decomposed over the ranks + 8192^2 packets sharded by y-band (team mode)."""
+    from juliaraytracingsw_b200 import drivers, raytracing
+    from juliaraytracingsw_b200.slab import SlabProblem
+    nx, sq = 4096, 8192
+    f, Cg, ug = 3.0, 1.0, 0.025
+    dt = 0.025 * (2 * np.pi / nx)
+    nu = 40 * 2 * np.pi / nx / ((nx / 2 - 1) ** 8) / dt
+    prob = SlabProblem(dist, local, model="TwoLayerQG", nx=nx, dt=dt, nu=nu, nnu=4, f=f, Cg=Cg, U=ug, mu=1e-2, f0=f)
+    rng = np.random.default_rng(0)
+    sol = np.zeros((nx // 2 + 1, nx, 2), dtype=np.complex128)
+    sol[1:24, :24] = (rng.standard_normal((23, 24, 2)) + 1j * rng.standard_normal((23, 24, 2))) * nx * nx * 1e-3
+    prob.sol = sol
+    del sol
+    ntot = sq * sq
+    rank = dist.get_rank()
+    lo, hi = rank * ntot // world, (rank + 1) * ntot // world
+    k0 = (3.0 ** 0.5) * f / Cg
+    pk = raytracing.generate_initial_wavepackets(prob, 2 * np.pi, k0, hi - lo, sq, f, Cg, first=lo)
+    psi = raytracing.PSI_TWOLAYER_BAROCLINIC
+    raytracing.get_velocity_info(prob, 0, psi)
+    drivers.coupled_steps(prob, pk, 3, psi_kind=psi)
+    prob.sync(); dist.barrier()
+    prob.timer_start()
+    drivers.coupled_steps(prob, pk, steps, psi_kind=psi)
+    ms = prob.timer_stop()
+    prob.sync(); dist.barrier()
+    prob.timer_start()
+    prob.stepforward(steps)
+    ms_flow = prob.timer_stop()
+    both = [None] * world
+    dist.all_gather_object(both, (ms, ms_flow))
+    ms, ms_flow = max(b[0] for b in both), max(b[1] for b in both)
+    out = {"workload": f"two-layer QG 4096^2 IFMAB3 slab-decomposed over {world} GPUs (NVLink peer stores + device barrier) + RK4 ray tracing of "
+                       f"{ntot} packets sharded by y-band (BASELINE config 5)", "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
+           "value": ntot * steps / (ms * 1e-3), "unit": "packet-steps/s", "flow_only_ms_per_step": ms_flow / steps,
+           "flow_steps_per_s": 1e3 * steps / ms_flow, "packet_positions": "reference lattice"}
+    pk.close(); prob.close()
+    return out
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_swrt(args):
@@ -238,8 +356,11 @@ def run_swrt(args):
         prob.sync(); barrier()
         l0 = prob.launch_count()
         prob.timer_start()
-        for _ in range(nsteps):
-            t = drivers.coupled_step(prob, packets, t)
+        if team:                                     # the whole loop natively (swrt_packets_coupled_steps): ~15 small launches per step
+            t = drivers.coupled_steps(prob, packets, nsteps)
+        else:
+            for _ in range(nsteps):
+                t = drivers.coupled_step(prob, packets, t)
         ms = prob.timer_stop()
         barrier()
         return max_over_ranks(ms), prob.launch_count() - l0, t
@@ -296,7 +417,7 @@ def run_swrt(args):
         k32 = prob.profile_report()
         prob.profile(0)
         fp32 = {"value": ntot * K / (ms32 * 1e-3), "unit": "packet-steps/s", "ms_per_step": ms32 / K,
-                "raytrace_ms": k32["raytrace_rk4_kernel"]["ms_avg"],
+                "raytrace_ms": next(v for k, v in k32.items() if k.startswith("raytrace_rk4"))["ms_avg"],
                 "what": "same coupled step; the tracer samples Float32 node records with an fp32 right-hand side (packet state, "
                         "cell coordinate and RK4 combination in fp64).  Not part of `value`."}
         p32.close()
@@ -312,13 +433,22 @@ def run_swrt(args):
         packets.get(out=h_xk)
         h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
         Ke = max(3, min(K, 10))
-        nchunks = max(2, min(args.e2e_chunks, nloc // 1048576))   # ~1M packets or more per chunk: below that the per-chunk launches dominate
-        pipe = raytracing.PacketPipeline(prob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
+        nchunks = max(4, min(args.e2e_chunks, nloc // 524288))   # >= 4 row blocks at every N so that uploads, kernels and downloads overlap
+        pipe = None if team else raytracing.PacketPipeline(prob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
 
         def e2e_step(t, frame, first=False):
             # the packets of this step arrive from the host and go back to it, chunk by chunk on the chunks' own streams:
             # uploads, sort + ray-trace kernels and downloads of different chunks overlap (raytracing.PacketPipeline).
             # frame=True also samples velocity and gradients at the new positions and copies them back (savepacketdata!).
+            if team:
+                # team mode: this rank's caller-order block goes to the band owners (pull scan over NVLink), is traced there and
+                # collected back into the caller's rows -- set / coupled_step / get are collective calls
+                packets.set(h_xk, h_sign if first else None)
+                new_t = drivers.coupled_step(prob, packets, t)
+                packets.get(out=h_out)
+                if frame:
+                    raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), packets, output_G=h_G, output_U=h_U)
+                return new_t
             flow.stepforward(prob, (), 1)
             raytracing.get_velocity_info(prob, 1)
             new_t = prob.clock.t
@@ -347,8 +477,21 @@ def run_swrt(args):
                "with_output_frame": {"value": ntot * Ke / (ms_f * 1e-3), "ms_per_step": ms_f / Ke, "d2h_bytes_per_step": int(8 * 10 * nloc),
                                      "what": "the same plus velocity (N,2) and gradients (N,4) sampled at the new positions and copied "
                                              "back every step (savepacketdata! with write_gradients)"}}
-        pipe.close()
+        if pipe is not None:
+            pipe.close()
     clk = clocks.stop()
+    # ---- the other BASELINE configs as extra keys of the same line (single-GPU ones on rank 0's GPU at N = 1; config 5 at N = 8)
+    extra_cfg = {}
+    if not args.no_extra_configs and args.nx == 2048:
+        try:
+            packets.close(); prob.close()
+            if world == 1:
+                extra_cfg["config2"] = extra_config2(local)
+                extra_cfg["config3"] = extra_config3(local)
+            elif world == 8 and team:
+                extra_cfg["config5"] = extra_config5(dist, local, world, 5)
+        except Exception as ex:          # an extra key must never cost the headline line
+            extra_cfg["extra_configs_error"] = repr(ex)[:300]
 
     if rank != 0:
         if dist is not None:
@@ -361,23 +504,22 @@ def run_swrt(args):
     kern_k = {k: v for k, v in kern.items() if k != "packet_sort_kernels"}
     name, rec = max(kern_k.items(), key=lambda kv: kv[1]["ms_total"])
     share = rec["ms_total"] / sum(v["ms_total"] for v in kern.values())
-    if name == "raytrace_rk4_kernel":
+    if name.startswith("raytrace_rk4"):
         # Compulsory HBM bytes of one launch: packet state in and out (x,y,k,l,sign read; x,y,k,l written = 72 B) plus
         # every grid point of the two-level snapshot field once (80 B per point).  The 1280 B per packet-step that the
         # four RK4 stages GATHER are served from registers/L1/L2 once packets are cell-sorted and the
         # stencil is cached, so they are reported separately (gather_*), not as HBM traffic.
         by = 72.0 * nloc * args.nsub + 80.0 * args.nx * args.nx
         what = "72 B packet state per packet-step + 80 B per grid point of the two-level snapshot field once per launch"
+        traffic = None
         extra = {"gather_bytes_per_launch": 1280.0 * nloc * args.nsub,
                  "gather_achieved_gbs": 1280.0 * nloc * args.nsub / (rec["ms_avg"] * 1e-3) / 1e9,
                  "gather_note": "SURVEY 8d figure (4 stages x 2 levels x 5 fields x 4 taps x 8 B); on-chip after sort + stencil cache",
-                 # ncu --set full, profiles/r01_d_ncu_raytrace_cached_16M.csv: dram read 1.007 GB + write 0.504 GB per launch
-                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, 16,777,216 packets on one GPU",
-                 # what actually binds the kernel (one ncu --set full capture, not measured in this run):
-                 "binding_unit": {"name": "l1tex__data_pipe_lsu_wavefronts", "pct_of_peak": 69.3, "fp64_pipe_pct": 40.1,
-                                  "issue_active_pct": 41.2, "warps_per_sm": 16,
-                                  "source": "profiles/r01_i_ncu_full_raytrace_cached_details.csv, profiles/r01_i_ray_kernel_experiments.md"}}
-        traffic = 1.511e9 * (nloc / 16777216.0) if args.nx == 2048 else None
+                 }
+        nt = load_ncu_traffic().get("raytrace")
+        if nt and args.nx == nt.get("nx") and nloc == nt.get("packets") and name == nt.get("kernel"):   # only for the kernel and configuration the capture was taken on
+            traffic = nt["dram_bytes_per_launch"]
+            extra.update({"traffic_source": nt["source"], "binding_unit": nt.get("binding_unit")})
     else:
         flow_bytes = {"ypass_inv_kernel<RswLoaderA>": 8 * F, "xpass_kernel<RswXOp>": 9 * F, "ypass_fwd_kernel<RswCombiner>": 7 * F,
                       "ifmab3_update_rsw_kernel": 15 * F, "ypass_inv_kernel<PsiLoader>": 4 * F, "xpass_kernel<SnapshotXOp>": 8 * F}
@@ -389,24 +531,27 @@ def run_swrt(args):
     spectral = {"steps_per_s": 1e3 / ms_flow, "ms_per_step": ms_flow, "algorithmic_bytes_per_step": 42 * F,
                 "achieved": 42 * F / (ms_flow * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": 42 * F / (ms_flow * 1e-3) / 1e9 / peak,
                 "contract": "B_step = 42 F, F = 8 nx^2 bytes (SURVEY.md 8d, RSW + IFMAB3)",
-                "traffic": 5.8e8 if args.nx == 2048 else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the four kernels of one step, in situ "
-                                  "(--cache-control none), profiles/r01_n_insitu_dram_bytes_no_cache_flush.csv"}
+                "traffic": None, "traffic_source": None}
+    ft = load_ncu_traffic().get("spectral_step")
+    if ft and args.nx == ft.get("nx") and world == 1:
+        spectral.update({"traffic": ft["dram_bytes_per_step"], "traffic_source": ft["source"]})
     line = {
         "metric": "packet-steps/s", "value": value, "unit": "packet-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(nx=args.nx, n=ntot), "nx": args.nx, "packets": ntot, "packets_per_gpu": nloc,
                    "nsub": args.nsub, "integrator": "RK4", "interp": "bilinear",
-                   "packet_positions": "uniform random over the domain (fully mixed; the lattice start is value_lattice_t0)", "parallelism": f"packets sharded x{world}, flow replicated",
+                   "packet_positions": "uniform random over the domain (fully mixed; the lattice start is value_lattice_t0)", "parallelism": (f"team x{world}: flow slab-decomposed (NVLink peer stores + device barrier), packets sharded by y-band" if team
+                                   else f"packets sharded x{world}, flow replicated"),
                    "l2": "inputs_exceed_l2 (2 x 168 MB snapshot fields, 0.67 GB packets/GPU at N=1, 0.47 GB spectral work set vs 126 MB L2)"},
         "clocks": clk, "e2e": e2e, "fp32_packet_mode": fp32, "gpu_launches": int(launches), "roofline": roofline, "spectral_step": spectral,
         "value_lattice_t0": ntot * K / (ms_lat * 1e-3),
         "kernels": {k: {"ms_avg": round(v["ms_avg"], 5), "launches": v["launches"]} for k, v in kern.items()},
+        **extra_cfg,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         r = cpu_sample(args, 3, 1, cores)
-        line["cpu_baseline"] = {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "kind": "port", "sample": r["sample"],
+        line["cpu_baseline"] = {"value": r["value"], "unit": "packet-steps/s", "cores": cores, "omp_threads": r["omp_threads"], "kind": "port", "sample": r["sample"],
                                 "flow_ms": r["flow_ms"], "spectral_steps_per_s": 1e3 / r["flow_ms"]}
     print(json.dumps(line), flush=True)
     if dist is not None:

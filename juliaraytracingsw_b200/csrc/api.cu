@@ -100,6 +100,7 @@ struct swrt_flow {
     struct Rec { int id; cudaEvent_t a, b; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
+    const char* ray_name = "raytrace_rk4_cached_kernel<4>";   // the ray kernel the last raytrace call launched (profile label)
     double prof_ms[16] = {0};
     long long prof_n[16] = {0};
     std::vector<struct swrt_packets*> readers;   // packet handles with their own stream (snapshot writers wait for their reads)
@@ -1419,7 +1420,7 @@ int swrt_flow_profile_get(swrt_flow* h, int id, double* ms_total, long long* cou
     prof_collect(h);
     if (ms_total) *ms_total = h->prof_ms[id];
     if (count) *count = h->prof_n[id];
-    if (name) *name = kKernelNames[id];
+    if (name) *name = id == K_RAYTRACE ? h->ray_name : kKernelNames[id];
     return SWRT_OK;
 }
 int swrt_flow_launch_count(swrt_flow* h, long long* n) {
@@ -1883,6 +1884,11 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
             attr_done = true;
         }
     }
+    f->ray_name = p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
+                : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3) ? "raytrace_generic_kernel"
+                : p->d.interp == SWRT_INTERP_HERMITE_BICUBIC ? "raytrace_rk4_cubic_kernel"
+                : use_tile ? (tile_minb >= 4 ? "raytrace_rk4_tile_kernel<4>" : "raytrace_rk4_tile_kernel<3>")
+                : (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) ? "raytrace_rk4_cached_kernel<4>" : "raytrace_rk4_kernel";
     { ProfScope ps(f, K_RAYTRACE, pst(p));
 #define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp)
       if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {

@@ -34,7 +34,7 @@ for name in names:
     prob.sync()
     rep = prob.profile_report()
     prob.profile(0)
-    r = rep["raytrace_rk4_kernel"]
+    r = next(v for k, v in rep.items() if k.startswith("raytrace_rk4"))
     print("kernel", name, "nx", nx, "packets", P.Npackets, "raytrace ms %.4f" % r["ms_avg"], "sort ms/launch %.4f x %d" %
           (rep["packet_sort_kernels"]["ms_avg"], rep["packet_sort_kernels"]["launches"]), "checksum %.15e" % float(np.abs(pk.get()).sum()), flush=True)
     pk.close()
