@@ -108,3 +108,54 @@ class FrameRoller:
             self.current_writes = 0
             self.file_index += 1
             self.files[self.name()] = []
+
+
+def load_packet_analysis_files_collated(open_file, indices, packet_idxs=None, load_velocity=False):
+    """analysis/load_file.jl:89-160 restated: reassemble (times, x, k[, u]) from a sequence of packet files whose last frame
+    may be split over two files (`open_file(idx)` returns an object with `keys(group)`, `__getitem__`, `__contains__`).
+
+    Quirks kept on purpose (it is the reader the writer has to satisfy): the frame count of a file is the number of `p/t`
+    keys in it; the LAST `p/t` key of every file gets its x, k, u from this file or, for what is missing, from the next
+    one (:131-148) -- and its time is never stored (`times` stays 0 there, the loop :121 runs over `[1:end-1]`)."""
+    import numpy as np
+    grp = "p/"
+    total_N, Npackets = 0, 0
+    for idx in indices:
+        f = open_file(idx)
+        total_N += len(f.keys(grp + "t"))
+        first_key = f.keys(grp + "x")[0]
+        Npackets = f[grp + "x/" + first_key].shape[0]
+    sel = slice(None) if packet_idxs is None else np.asarray(packet_idxs)
+    if packet_idxs is not None:
+        Npackets = len(packet_idxs)
+    times = np.zeros(total_N)
+    x, k, u = (np.zeros((total_N, Npackets, 2)) for _ in range(3))
+    base = 0
+    for idx in indices:
+        f = open_file(idx)
+        nxt = open_file(idx + 1) if idx < indices[-1] else None
+        tkeys = f.keys(grp + "t")
+        N = len(tkeys)
+        index = 0
+        for ts in tkeys[:-1]:
+            times[base + index] = f[grp + f"t/{ts}"]
+            x[base + index] = f[grp + f"x/{ts}"][sel]
+            k[base + index] = f[grp + f"k/{ts}"][sel]
+            if load_velocity:
+                u[base + index] = f[grp + f"u/{ts}"][sel]
+            index += 1
+        ts = tkeys[-1]
+        src = {name: (f if (grp + f"{name}/{ts}") in f else nxt) for name in ("x", "k", "u")}
+        if (grp + f"u/{ts}") in f:
+            pass
+        elif (grp + f"k/{ts}") in f:
+            src["u"] = nxt
+        elif (grp + f"x/{ts}") in f:
+            src["k"] = src["u"] = nxt
+        else:
+            src["x"] = src["k"] = src["u"] = nxt
+        x[base + index] = src["x"][grp + f"x/{ts}"][sel]
+        k[base + index] = src["k"][grp + f"k/{ts}"][sel]
+        u[base + index] = src["u"][grp + f"u/{ts}"][sel]
+        base += N
+    return (times, x, k, u) if load_velocity else (times, x, k)

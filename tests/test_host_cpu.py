@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 import juliaraytracingsw_b200 as swrt
@@ -138,3 +139,52 @@ def test_header_is_plain_c():
     code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)            # declarations only
     for word in ("std::", "torch", "cudastream_t", "cudaevent_t", "double2", "at::", "template", "class "):   # no C++/CUDA/torch types
         assert word not in code.lower(), word
+
+
+@pytest.mark.parametrize("max_writes", [8, 9, 10, 11, 12, 23])
+@pytest.mark.parametrize("write_gradients", [False, True])
+def test_frame_writer_is_accepted_by_the_reference_reader_K13_K14(tmp_path, max_writes, write_gradients):
+    """f2 acceptance: the writer stores frames under the reference's keys (params/* then p/t, p/x, p/k, p/u[, p/g] per frame,
+    raytracing/RaytracingDriver.jl:87-108), rolling to the next file after ANY key (utils/SequencedOutputs.jl:37-44,58-63), and
+    the oracle's restatement of analysis/load_file.jl:89-160 puts the frames back together -- whichever key the roll-over fell on."""
+    from juliaraytracingsw_b200.outputs import KeyedFile, SequencedOutput
+    from oracle import outputs as oout
+    rng = np.random.default_rng(max_writes)
+    N, nframes = 13, 17
+    out = SequencedOutput("packets", max_writes, store=True, directory=str(tmp_path))
+    ref = oout.SequencedOutput(lambda i: oout.packet_filename("packets", i), max_writes)
+    for key in ("f0", "Cg", "dt", "N", "k0", "ωsign"):
+        out["params/" + key] = 1.0
+    oout.savepacketproblem(ref)
+    frames = []
+    fr = -1
+    # (the reference reader needs the LAST file to hold a p/t key whose frame is complete in that file -- there is no next file to
+    # look into, analysis/load_file.jl:131-148 -- so the run is extended until the current file holds a whole frame)
+    while fr + 1 < nframes or not any(k.startswith("p/t/") for k in ref.files[ref.current]):
+        fr += 1
+        step = 10 * fr
+        t, x, k, u, g = 0.5 * fr, rng.standard_normal((N, 2)), rng.standard_normal((N, 2)), rng.standard_normal((N, 2)), rng.standard_normal((N, 4))
+        frames.append((t, x, k, u))
+        out[f"p/t/{step}"] = t
+        out[f"p/x/{step}"] = x
+        out[f"p/k/{step}"] = k
+        out[f"p/u/{step}"] = u
+        if write_gradients:
+            out[f"p/g/{step}"] = g
+        oout.write_packets(ref, step, write_gradients)
+    out.close()
+    assert out.files == {n: ks for n, ks in ref.files.items() if ks}          # same keys in the same files, in the same order
+    nfiles = out.file_index + (1 if out.current_writes else 0)
+    files = [KeyedFile.load(str(tmp_path / oout.packet_filename("packets", i))) for i in range(nfiles)]
+    splits = sum(1 for f in files[:-1] if f"p/u/{f.keys('p/t')[-1]}" not in f)
+    times, x, k, u = oout.load_packet_analysis_files_collated(lambda i: files[i], list(range(nfiles)), load_velocity=True)
+    # the reader counts one frame per `p/t` key: all frames are there, in order, whichever key the roll-over fell on
+    assert x.shape[0] == len(frames) >= nframes
+    for fr, (t, xf, kf, uf) in enumerate(frames):
+        np.testing.assert_array_equal(x[fr], xf)
+        np.testing.assert_array_equal(k[fr], kf)
+        np.testing.assert_array_equal(u[fr], uf)
+    last = np.cumsum([len(f.keys("p/t")) for f in files]) - 1                   # (reader quirk: the last time of every file stays 0)
+    np.testing.assert_array_equal(np.delete(times, last), np.delete(np.array([f[0] for f in frames]), last))
+    if max_writes in ((8, 9, 12) if write_gradients else (8, 9, 10, 11)):
+        assert splits > 0                                                       # frames did straddle files in these cases
