@@ -64,6 +64,11 @@ int swrt_flow_destroy(swrt_flow* h);
 int swrt_flow_set_solution(swrt_flow* h, const void* sol_host);
 /* Array(prob.sol) as left by updatevars!/calcN! (aliased modes are zero) */
 int swrt_flow_get_solution(swrt_flow* h, void* sol_host);
+/* set_initial_condition! rsw/RSWRaytracingDriver.jl:15-54: random-phase geostrophic band [Kg0, Kg1] scaled to max|u_g| = ag plus wave band
+ * [Kw0, Kw1] scaled to max|u_w| = aw (K15), built on the device from the host's random numbers phase = 2 pi rand(nkr, nl) and
+ * sgn = sign(rand - 0.5) (column-major (nkr, nl)); scales_out (may be NULL) receives the two normalisation factors */
+int swrt_flow_set_rsw_initial_condition(swrt_flow* h, const double* phase_host, const double* sgn_host, double Kg0, double Kg1, double ag,
+                                        double Kw0, double Kw1, double aw, double* scales_out);
 /* enforce_reality_condition!(prob) :118-133 -- in the reference this leaves sol dealiased and refreshes vars */
 int swrt_flow_enforce_reality(swrt_flow* h);
 /* stepforward!(prob, [], nsteps): utils/IFMAB3.jl:157-169 looped by FourierFlows.stepforward!(prob, diags, n) */

@@ -626,6 +626,46 @@ int swrt_flow_get_solution(swrt_flow* h, void* sol_host) {
     return SWRT_OK;
 }
 
+int swrt_flow_set_rsw_initial_condition(swrt_flow* h, const double* phase_host, const double* sgn_host, double Kg0, double Kg1, double ag,
+                                        double Kw0, double Kw1, double aw, double* scales_out) {
+    // set_initial_condition! (rsw/RSWRaytracingDriver.jl:15-54) with the mode arithmetic, both normalising inverse transforms
+    // and both maxima on the device; only the random numbers come from the host (Julia's / NumPy's stream)
+    if (!h || !phase_host || !sgn_host) return fail(SWRT_ERR_ARG, "null pointer");
+    const bool rsw = h->d.model == SWRT_RSW || h->d.model == SWRT_RSW_MODIFIED || h->d.model == SWRT_RSW_LINDBORG;
+    if (!rsw) return fail(SWRT_ERR_UNSUPPORTED, "the RSW initial condition needs an (u, v, eta) model (model %d)", h->d.model);
+    if (h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "not available for a slab-decomposed flow (build it on one GPU and hand the state over)");
+    if (!(ag > 0 && aw >= 0 && Kg1 >= Kg0 && Kw1 >= Kw0)) return fail(SWRT_ERR_ARG, "bad band / amplitude");
+    const SpecLayout& L = h->L;
+    const double kmax_keep = (L.kr_keep - 1) * L.dk;
+    if (Kg1 > kmax_keep || Kw1 > kmax_keep) return fail(SWRT_ERR_ARG, "the bands must lie inside the retained (dealiased) wavenumbers");
+    CK(cudaSetDevice(h->d.device));
+    const size_t nm = (size_t)h->nkr * h->d.ny;
+    std::vector<double2> rnd(nm);
+    for (size_t i = 0; i < nm; ++i) rnd[i] = make_double2(phase_host[i], sgn_host[i]);
+    CK(cudaMemcpyAsync(h->stage, rnd.data(), sizeof(double2) * nm, cudaMemcpyHostToDevice, h->st));
+    const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+    const unsigned blocks = (unsigned)((nmodes + 255) / 256);
+    double scale[2] = {1.0, 1.0};
+    const double amp[2] = {ag, aw};
+    for (int part = 0; part < 2; ++part) {
+        if (amp[part] == 0.0) { scale[part] = 0.0; continue; }
+        { ProfScope ps(h, K_OTHER); rsw_ic_kernel<<<blocks, 256, 0, h->st>>>(h->stage, h->nkr, L, part, h->d.f, L.Cg2, Kg0, Kg1, Kw0, Kw1, 1.0, 1.0, h->sol); }
+        CK(cudaGetLastError());
+        int rc = spectral_to_physical(h, 0, h->phys);
+        if (rc) return rc;
+        cudaError_t e = cudaSuccess;
+        const double m = reduce_host(h, h->phys, (long long)h->d.nx * h->d.ny, 1, &e);
+        CK(e);
+        if (!(m > 0)) return fail(SWRT_ERR_ARG, "band %d holds no mode (max|u| = %g)", part, m);
+        scale[part] = amp[part] / m;
+    }
+    { ProfScope ps(h, K_OTHER); rsw_ic_kernel<<<blocks, 256, 0, h->st>>>(h->stage, h->nkr, L, 2, h->d.f, L.Cg2, Kg0, Kg1, Kw0, Kw1, scale[0], scale[1], h->sol); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->st));
+    if (scales_out) { scales_out[0] = scale[0]; scales_out[1] = scale[1]; }
+    return SWRT_OK;
+}
+
 int swrt_flow_enforce_reality(swrt_flow* h) {
     // rsw/RotatingShallowWater.jl:118-133: dealias!(sol) (already an invariant here); the round-tripped
     // fields go to vars.*h, which calcN! overwrites from sol on the next step -- sol is otherwise untouched.

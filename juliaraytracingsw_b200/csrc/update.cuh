@@ -257,6 +257,44 @@ __global__ void __launch_bounds__(256) psi_kernel(PsiLoader ld, SpecLayout L, do
     }
 }
 
+// ---------------------------------------------------------------- RSW initial condition on the device
+// set_initial_condition! of rsw/RSWRaytracingDriver.jl:15-54: a random-phase geostrophic band Kg and a wave band Kw.  `rnd`
+// holds the host's random numbers in the reference layout, (phase, sgn) per mode of the (nkr, nl) array.
+// part 0: geostrophic modes, part 1: wave modes, each UNSCALED into sol (the caller measures max|u|, :39-52);
+// part 2: sol = sg * geostrophic + sw * wave.
+__global__ void __launch_bounds__(256) rsw_ic_kernel(const double2* __restrict__ rnd, int nkr, SpecLayout L, int part, double f, double Cg2,
+                                                     double Kg0, double Kg1, double Kw0, double Kw1, double sg, double sw, double2* __restrict__ sol) {
+    const int rows = L.ny - (L.lz1 - L.lz0);
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * L.kr_keep) return;
+    const int kr = (int)(i % L.kr_keep), r = (int)(i / L.kr_keep), l = r < L.lz0 ? r : r + (L.lz1 - L.lz0);
+    const double kw = (L.kr_off + kr) * L.dk, lw = wave_l(L, l), K2 = kw * kw + lw * lw;
+    const double2 pr = rnd[(long long)l * nkr + L.kr_off + kr];
+    double sn, cs;
+    sincos(pr.x, &sn, &cs);                                       // shift = exp(i phase)
+    double2 u = make_double2(0.0, 0.0), v = u, e = u;
+    if (part != 1 && Kg0 * Kg0 <= K2 && K2 <= Kg1 * Kg1) {        // eta = 0.5 shift, u = -0.5 i Cg2/f l shift, v = 0.5 i Cg2/f k shift
+        const double a = 0.5 * Cg2 / f * (part == 2 ? sg : 1.0), h = 0.5 * (part == 2 ? sg : 1.0);
+        e = make_double2(h * cs, h * sn);
+        u = make_double2(a * lw * sn, -a * lw * cs);
+        v = make_double2(-a * kw * sn, a * kw * cs);
+    }
+    if (part != 0 && Kw0 * Kw0 <= K2 && K2 <= Kw1 * Kw1 && K2 > 0.0) {
+        const double s = part == 2 ? sw : 1.0, wK = pr.y * sqrt(f * f + Cg2 * K2), inv = s / K2;
+        // u = (0.5 k wK shift + 0.5 i f l shift)/K2 ; v = (0.5 l wK shift - 0.5 i f k shift)/K2 ; eta = 0.5 shift
+        u.x += inv * (0.5 * kw * wK * cs - 0.5 * f * lw * sn);
+        u.y += inv * (0.5 * kw * wK * sn + 0.5 * f * lw * cs);
+        v.x += inv * (0.5 * lw * wK * cs + 0.5 * f * kw * sn);
+        v.y += inv * (0.5 * lw * wK * sn - 0.5 * f * kw * cs);
+        e.x += 0.5 * s * cs;
+        e.y += 0.5 * s * sn;
+    }
+    const long long off = (long long)l * L.kr_pad + kr;
+    sol[off] = u;
+    sol[L.vs + off] = v;
+    sol[2 * L.vs + off] = e;
+}
+
 // ---------------------------------------------------------------- wave / balanced projections
 // DEC_RSW:     wave_balanced_decomposition, rsw/RSWUtils.jl:9-22 -- balanced part from the linear PV, wave part = rest.
 // DEC_TY:      decompose_balanced_wave, thomasyamada/TYUtils.jl:10-51 -- projections of (u_c, v_c, p_c) on Phi0 and Phi+-.

@@ -89,35 +89,20 @@ def create_fourier_flows_problem(dev, P: Parameters, dt, ν):
 
 def set_initial_condition(prob, P: Parameters, rng: np.random.Generator):
     """rsw/RSWRaytracingDriver.jl:15-54: random-phase geostrophic band + wave band, scaled so that
-    max|u_g| = ag and max|u_w| = aw (K15).  The two normalising inverse transforms and maxima run on the
-    device (set_solution!/maximum(abs.(u))).  Random numbers come from NumPy, not Julia's stream."""
+    max|u_g| = ag and max|u_w| = aw (K15).  Only the random numbers are drawn on the host (NumPy's stream, not Julia's);
+    the mode arithmetic, the two normalising inverse transforms and the maxima run on the device
+    (swrt_flow_set_rsw_initial_condition)."""
+    import ctypes as C
+    from ._lib import check, lib
     g = prob.grid
-    Cg2, f = P.Cg ** 2, P.f
     shape = (g.nkr, g.nl)
-    geo = (P.Kg[0] ** 2 <= g.Krsq) & (g.Krsq <= P.Kg[1] ** 2)
-    wav = (P.Kw[0] ** 2 <= g.Krsq) & (g.Krsq <= P.Kw[1] ** 2) & (g.Krsq > 0)
-    phase = 2 * np.pi * rng.random(shape)
-    sgn = np.sign(rng.random(shape) - 0.5)
-    shift = np.exp(1j * phase)
-    z = lambda: np.zeros(shape, dtype=np.complex128)
-    ugh, vgh, ηgh, uwh, vwh, ηwh = z(), z(), z(), z(), z(), z()
-    ηgh[geo] = (0.5 * shift)[geo]
-    ugh[geo] = (-0.5j * Cg2 / f * g.l * shift)[geo]
-    vgh[geo] = (0.5j * Cg2 / f * g.kr * shift)[geo]
-
-    def max_abs_u(uh):
-        flow.set_solution(prob, uh, z(), z())
-        return flow.max_abs_uv(prob)[0]
-
-    s = P.ag / max_abs_u(ugh)
-    ugh, vgh, ηgh = ugh * s, vgh * s, ηgh * s
-    ωK = sgn * np.sqrt(f ** 2 + Cg2 * g.Krsq)
-    ηwh[wav] = (0.5 * shift)[wav]
-    uwh[wav] = (g.invKrsq * (0.5 * g.kr * ωK * shift + 0.5j * f * g.l * shift))[wav]
-    vwh[wav] = (g.invKrsq * (0.5 * g.l * ωK * shift - 0.5j * f * g.kr * shift))[wav]
-    s = P.aw / max_abs_u(uwh)
-    uwh, vwh, ηwh = uwh * s, vwh * s, ηwh * s
-    flow.set_solution(prob, ugh + uwh, vgh + vwh, ηgh + ηwh)
+    phase = np.asfortranarray(2 * np.pi * rng.random(shape))
+    sgn = np.asfortranarray(np.sign(rng.random(shape) - 0.5))
+    scales = (C.c_double * 2)()
+    check(lib().swrt_flow_set_rsw_initial_condition(prob._h, phase.ctypes.data_as(C.c_void_p), sgn.ctypes.data_as(C.c_void_p),
+                                                    float(P.Kg[0]), float(P.Kg[1]), float(P.ag), float(P.Kw[0]), float(P.Kw[1]),
+                                                    float(P.aw), scales))
+    return scales[0], scales[1]
 
 
 def initialize_problem(P: Parameters, dev=0):

@@ -235,3 +235,18 @@ def _tile_case(nx, n_side, shift):
     rng = np.random.default_rng(5)
     xk[:, 0:2] = rng.uniform(-c["L"] / 2, c["L"] / 2, size=(xk.shape[0], 2)) + shift * c["L"]
     return g, c, Fo, Fn, xk, sign
+
+
+@pytest.mark.parametrize("nx", [128, 512])
+def test_device_initial_condition_generator_K15(nx):
+    """set_initial_condition! (rsw/RSWRaytracingDriver.jl:15-54) built on the device from the host's random numbers: the state
+    equals the oracle's restatement fed the same numbers, and K15 holds: max|u_g| = ag, max|u_w| = aw."""
+    g, p, want, c = config2_setup(nx)              # the oracle's recipe with default_rng(1234)
+    P = drivers.Parameters(nx=nx)
+    prob, _ = drivers.initialize_problem(P)        # drivers.set_initial_condition with default_rng(P.seed = 1234)
+    got = prob.sol
+    assert rel_l2(got, want) < 1e-13
+    _, (ugh, vgh, egh), (uwh, vwh, ewh) = orsw.initial_condition(g, p, P.Kg, P.ag, P.Kw, P.aw, np.random.default_rng(1234))
+    for part, amp in (((ugh, vgh, egh), P.ag), ((uwh, vwh, ewh), P.aw)):
+        prob.sol = np.stack(part, axis=-1)
+        assert abs(flow.max_abs_uv(prob)[0] / amp - 1) < 1e-12
