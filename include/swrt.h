@@ -107,6 +107,8 @@ int swrt_flow_set_interp(swrt_flow* h, int interp);
 int swrt_flow_set_snapshot_refinement(swrt_flow* h, int refine);
 int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny);
 int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields);
+/* kernel width of the NUFFT mode in nodes of the oversampled grid, 4 <= nw <= 16 (default 8; FINUFFT: nw = ceil(log10(1/tol)) + 1) */
+int swrt_flow_set_nufft_width(swrt_flow* h, int nw);
 /* old_velocity = new_velocity; old_grad_v = new_grad_v (raytracing/RaytracingDriver.jl:269-270).
  * alias != 0 reproduces the reference's rebinding (both names then refer to the same buffers);
  * alias == 0 swaps the two slots. */
@@ -222,7 +224,11 @@ enum { SWRT_INTERP_BILINEAR = 0, SWRT_INTERP_HERMITE_BICUBIC = 1,
           raytracing/GPURaytracing.jl:118-127); packet state and RK4 combination stay fp64.  Reported separately from the fp64 numbers. */
        SWRT_INTERP_BILINEAR_F32 = 3,
        /* cubic B-spline of the CPU tracer's steady-flow mode (raytracing/Raytracing.jl:152-159); prefiltered like BSPLINE2 */
-       SWRT_INTERP_BSPLINE3 = 4 };
+       SWRT_INTERP_BSPLINE3 = 4,
+       /* type-2 NUFFT: spectrally exact values of u, v, ux, uy, vx at the packet positions (the intent of raytracing/NUFFTRaytracing.jl:68-84,
+          nufft2d2 with tol 1e-5): 2x oversampled node grid (swrt_flow_set_snapshot_refinement(h, 2) first) of the spectrum deconvolved by the
+          kernel's transform, sampled with an nw x nw "exponential of semicircle" kernel; error ~ 10^(1 - nw), swrt_flow_set_nufft_width */
+       SWRT_INTERP_NUFFT = 5 };
 /* classical RK4 (north star) or the CPU tracer's implicit midpoint (raytracing/Raytracing.jl:106-109), 12 fixed-point sweeps */
 enum { SWRT_INTEG_RK4 = 0, SWRT_INTEG_IMPLICIT_MIDPOINT = 1 };
 enum { SWRT_LERP_PHYSICAL = 0, SWRT_LERP_REFERENCE_GPU = 1 };

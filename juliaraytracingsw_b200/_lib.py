@@ -66,6 +66,7 @@ SIGNATURES = {
     "swrt_flow_swap_snapshots": (_I, [_P, _I]),
     "swrt_flow_set_interp": (_I, [_P, _I]),
     "swrt_flow_snapshot_fields": (_I, [_P, _PI]),
+    "swrt_flow_set_nufft_width": (_I, [_P, _I]),
     "swrt_flow_set_snapshot_refinement": (_I, [_P, _I]),
     "swrt_flow_snapshot_dims": (_I, [_P, _PI, _PI]),
     "swrt_flow_get_snapshot": (_I, [_P, _I, _P]),

@@ -80,6 +80,9 @@ struct swrt_flow {
     double* snap[2] = {nullptr, nullptr};   // S[ny][nx][6] per time level (snapshot_layout.cuh)
     int slot_map[2] = {0, 1};               // slot (0 = old, 1 = new) -> array
     int interp = 0;                         // snapshot node data: 0 bilinear (5 fields / 48 B), 1 Hermite bicubic (7 fields / 64 B)
+    int nufft_w = 8;                        // SWRT_INTERP_NUFFT: kernel width; ptab = 1 / phihat per kr index (nkr) then per l index (ny)
+    double* ptab = nullptr;
+    int ptab_w = 0, ptab_refine = 0;
     CUtensorMap tmap[2];                    // TMA descriptors of the two levels viewed as [ny][nx * 6] doubles, box = one tile patch
     bool tmap_ok = false;
     double* phys = nullptr;
@@ -381,6 +384,31 @@ static void build_tmaps(swrt_flow* h) {
     h->tmap_ok = true;
 }
 
+// NUFFT mode: 1 / phihat(xi) of the sampling kernel phi(z) = exp(beta (sqrt(1 - z^2) - 1)) on |t| <= w/2 (t in nodes of the
+// oversampled grid, z = 2 t / w):  phihat(xi) = int phi cos(xi t) dt = (w/2) int_{-pi/2}^{pi/2} exp(beta (cos th - 1)) cos(xi w sin(th) / 2) cos th dth
+// (smooth after z = sin th; composite Simpson with 4096 panels is exact to rounding).
+static double nufft_beta(int w) { return 2.30 * w; }
+static double nufft_phihat(double xi, int w) {
+    const int n = 4096;
+    const double beta = nufft_beta(w), a = -0.5 * M_PI, hh = M_PI / n;
+    auto f = [&](double th) { return std::exp(beta * (std::cos(th) - 1.0)) * std::cos(0.5 * xi * w * std::sin(th)) * std::cos(th); };
+    double acc = f(a) + f(a + M_PI);
+    for (int i = 1; i < n; ++i) acc += (i & 1 ? 4.0 : 2.0) * f(a + i * hh);
+    return 0.5 * w * acc * hh / 3.0;
+}
+static int nufft_tables(swrt_flow* h) {
+    if (h->ptab && h->ptab_w == h->nufft_w && h->ptab_refine == h->refine) return SWRT_OK;
+    const int nkr = h->nkr, ny = h->d.ny, w = h->nufft_w;
+    std::vector<double> t((size_t)nkr + ny);
+    for (int k = 0; k < nkr; ++k) t[k] = 1.0 / nufft_phihat(2.0 * M_PI * k / ((double)h->refine * h->d.nx), w);
+    for (int l = 0; l < ny; ++l) t[nkr + l] = 1.0 / nufft_phihat(2.0 * M_PI * (l < ny / 2 ? l : l - ny) / ((double)h->refine * ny), w);
+    if (!h->ptab) CK(cudaMalloc(&h->ptab, sizeof(double) * t.size()));
+    CK(cudaMemcpy(h->ptab, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
+    h->ptab_w = w;
+    h->ptab_refine = h->refine;
+    return SWRT_OK;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
 #pragma GCC visibility push(default)
@@ -401,7 +429,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     if (h->band) cudaFree(h->band); else { cudaFree(h->snap[0]); cudaFree(h->snap[1]); }
-    cudaFree(h->flags);
+    cudaFree(h->flags); cudaFree(h->ptab);
     cudaFree(h->phys); cudaFree(h->red); cudaFree(h->sched); cudaFree(h->G2); cudaFree(h->H2);
     for (int w = 0; w < 3; ++w)
         for (int r = 0; r < h->P; ++r)
@@ -1267,6 +1295,12 @@ int swrt_flow_velocity_snapshot(swrt_flow* h, int psi_kind, int slot) {
     const bool pf = h->interp == SWRT_INTERP_BSPLINE2 || h->interp == SWRT_INTERP_BSPLINE3;
     PsiLoader ld{h->sol, L.vs, psi_kind, h->d.f, L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
     if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
+    if (h->interp == SWRT_INTERP_NUFFT) {
+        if (h->refine != 2) return fail(SWRT_ERR_STATE, "the NUFFT mode samples a 2x oversampled node grid: call swrt_flow_set_snapshot_refinement(h, 2) first");
+        int rc = nufft_tables(h);
+        if (rc) return rc;
+        ld.ptab_x = h->ptab; ld.ptab_y = h->ptab + h->nkr; ld.tab_kr_pad = L.kr_pad; ld.tab_kr_off = L.kr_off;
+    }
     CK(wait_readers(h));
     cudaError_t e;
     if (h->refine > 1) {
@@ -1356,9 +1390,15 @@ int swrt_flow_snapshot_dims(swrt_flow* h, int* nx, int* ny) {
 
 int swrt_flow_set_interp(swrt_flow* h, int interp) {
     if (!h) return fail(SWRT_ERR_ARG, "null pointer");
-    if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_BSPLINE3) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
+    if (interp < SWRT_INTERP_BILINEAR || interp > SWRT_INTERP_NUFFT) return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", interp);
     if (interp != SWRT_INTERP_BILINEAR && h->P > 1) return fail(SWRT_ERR_UNSUPPORTED, "a slab-decomposed flow holds band snapshots of the 5-field bilinear node records only");
     h->interp = interp;
+    return SWRT_OK;
+}
+int swrt_flow_set_nufft_width(swrt_flow* h, int nw) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    if (nw < 4 || nw > NUFFT_MAXW) return fail(SWRT_ERR_ARG, "NUFFT kernel width must be in [4, %d]", NUFFT_MAXW);
+    h->nufft_w = nw;
     return SWRT_OK;
 }
 int swrt_flow_snapshot_fields(swrt_flow* h, int* nfields) {
@@ -1526,7 +1566,7 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (!desc || !flow || !out) return fail(SWRT_ERR_ARG, "null pointer");
     *out = nullptr;
     if (desc->n <= 0 || desc->n >= (1LL << 32)) return fail(SWRT_ERR_ARG, "n must be in [1, 2^32)");
-    if (desc->interp < SWRT_INTERP_BILINEAR || desc->interp > SWRT_INTERP_BSPLINE3)
+    if (desc->interp < SWRT_INTERP_BILINEAR || desc->interp > SWRT_INTERP_NUFFT)
         return fail(SWRT_ERR_UNSUPPORTED, "interpolant %d not implemented", desc->interp);
     if (desc->interp == SWRT_INTERP_BILINEAR_F32 && desc->integrator != SWRT_INTEG_RK4)
         return fail(SWRT_ERR_UNSUPPORTED, "the fp32 packet mode integrates with RK4");
@@ -1670,6 +1710,8 @@ static PacketGrid packet_grid(const swrt_flow* f, const swrt_packets* p = nullpt
     g.x0 = -f->d.Lx / 2; g.y0 = -f->d.Ly / 2;
     g.inv_dx = 1.0 / g.dx; g.inv_dy = 1.0 / g.dy;
     g.ld = p ? p->cap : 0;
+    g.nw = f->nufft_w;
+    g.nbeta = nufft_beta(f->nufft_w);
     if (f->P > 1) {
         g.band = 1;
         g.jb = f->rank * f->L.yrows - f->halo;
@@ -1925,7 +1967,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
         }
     }
     f->ray_name = p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
-                : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3) ? "raytrace_generic_kernel"
+                : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3 || p->d.interp == SWRT_INTERP_NUFFT) ? "raytrace_generic_kernel"
                 : p->d.interp == SWRT_INTERP_HERMITE_BICUBIC ? "raytrace_rk4_cubic_kernel"
                 : use_tile ? (tile_minb >= 4 ? "raytrace_rk4_tile_kernel<4>" : "raytrace_rk4_tile_kernel<3>")
                 : (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) ? "raytrace_rk4_cached_kernel<4>" : "raytrace_rk4_kernel";
@@ -1940,8 +1982,9 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
           else raytrace_rk4_f32_kernel<8><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);
       }
       else if (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT) {
-          if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else if (p->d.interp == 2) SWRT_GEN(2, 1); else SWRT_GEN(4, 1);
+          if (p->d.interp == 0) SWRT_GEN(0, 1); else if (p->d.interp == 1) SWRT_GEN(1, 1); else if (p->d.interp == 2) SWRT_GEN(2, 1); else if (p->d.interp == 5) SWRT_GEN(5, 1); else SWRT_GEN(4, 1);
       }
+      else if (p->d.interp == SWRT_INTERP_NUFFT) SWRT_GEN(5, 0);
       else if (p->d.interp == SWRT_INTERP_BSPLINE2) SWRT_GEN(2, 0);
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
@@ -1976,6 +2019,7 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     if (nres > 0) {
         ProfScope ps(f, K_SAMPLE, pst(p));
         if (p->d.interp == SWRT_INTERP_BILINEAR_F32) sample_f32_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, reinterpret_cast<const float4*>(S), pg, p->U, g_host ? p->Gd : nullptr, p->cap);
+        else if (p->d.interp == SWRT_INTERP_NUFFT) sample_generic_kernel<5><<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
         else if (p->d.interp == SWRT_INTERP_BSPLINE3) sample_generic_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
         else if (p->d.interp == SWRT_INTERP_BSPLINE2) sample_generic_kernel<2><<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);
         else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) sample_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, idx, nres, S, pg, p->U, g_host ? p->Gd : nullptr, p->cap);

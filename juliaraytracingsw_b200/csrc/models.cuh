@@ -517,9 +517,17 @@ struct PsiLoader {
     double pdx, pdy;   // > 0: B-spline prefilter (Interpolations.jl, raytracing/Raytracing.jl:152-170) folded into psi: every
                        // sampled field is linear in psih, and the prefilter is 1/((pc0 + pc1 cos(k dx))(pc0 + pc1 cos(l dy)))
     double pc0 = 0.75, pc1 = 0.25;   // quadratic 3/4, 1/4; cubic 2/3, 1/3
+    // type-2 NUFFT mode: deconvolution by the sampling kernel's Fourier transform, tabulated per kr index and per l index
+    // (1 / phihat; api.cu nufft_tables); kr_pad / kr_off recover the indices from the element offset
+    const double *ptab_x = nullptr, *ptab_y = nullptr;
+    int tab_kr_pad = 1, tab_kr_off = 0;
     __device__ __forceinline__ double2 psi_of(double kw, double lw, long long off) const {
         double2 r = psi_raw(kw, lw, off);
-        if (pdx > 0.0) {
+        if (ptab_x) {
+            const double pf = ptab_x[tab_kr_off + (int)(off % tab_kr_pad)] * ptab_y[(int)(off / tab_kr_pad)];
+            r.x *= pf;
+            r.y *= pf;
+        } else if (pdx > 0.0) {
             const double pf = 1.0 / ((pc0 + pc1 * cos(kw * pdx)) * (pc0 + pc1 * cos(lw * pdy)));
             r.x *= pf;
             r.y *= pf;

@@ -38,6 +38,8 @@ struct PacketGrid {
     // rank's band plus halo rows, jb may be negative = wraps), so a grid row j lives at local row (j - jb) mod ny.
     int band, jb, jrows;
     int tile_row0;         // band mode: first tile row the tile kernel's grid covers (wraps)
+    int nw;                // type-2 NUFFT mode: kernel width in nodes of the (2x oversampled) snapshot grid
+    double nbeta;          //                    shape parameter of the "exponential of semicircle" kernel
 };
 // grid rows (j0, j0 + 1) of a bilinear stencil -> rows of the snapshot array
 __device__ __forceinline__ void stencil_rows(const PacketGrid& g, int& j0, int& j1) {
@@ -610,9 +612,42 @@ __device__ __forceinline__ void sample_bspline3_5(const double* __restrict__ S, 
         }
     }
 }
+// Type-2 NUFFT evaluation (the intent of raytracing/NUFFTRaytracing.jl:68-84, nufft2d2 of every spectral field at the packet
+// positions): the snapshot grid is the 2x oversampled grid of the deconvolved spectrum (the snapshot builder divides psih by the
+// kernel's Fourier transform), and the value at (x, y) is the sum over nw x nw nodes weighted by the separable
+// "exponential of semicircle" kernel phi(z) = exp(beta (sqrt(1 - z^2) - 1)), |z| <= 1 (FINUFFT's kernel; error ~ 10^(1 - nw)).
+constexpr int NUFFT_MAXW = 16;
+__device__ __forceinline__ void sample_nufft_5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
+    const double sx = (x - g.x0) * g.inv_dx, sy = (y - g.y0) * g.inv_dy, half = 0.5 * g.nw, ih = 1.0 / half;
+    const double fx = ceil(sx - half), fy = ceil(sy - half);
+    double wx[NUFFT_MAXW], wy[NUFFT_MAXW];
+    for (int a = 0; a < g.nw; ++a) {
+        const double zx = (sx - (fx + a)) * ih, zy = (sy - (fy + a)) * ih;
+        const double qx = 1.0 - zx * zx, qy = 1.0 - zy * zy;
+        wx[a] = qx > 0.0 ? exp(g.nbeta * (sqrt(qx) - 1.0)) : 0.0;
+        wy[a] = qy > 0.0 ? exp(g.nbeta * (sqrt(qy) - 1.0)) : 0.0;
+    }
+    const long long ix0 = (long long)fx, iy0 = (long long)fy;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) out[c] = 0.0;
+    for (int b = 0; b < g.nw; ++b) {
+        const long long row = (long long)(int)((iy0 + b) & (long long)(g.ny - 1)) * g.nx;
+        double r[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int a = 0; a < g.nw; ++a) {
+            const int i = (int)((ix0 + a) & (long long)(g.nx - 1));
+            const double2* q = reinterpret_cast<const double2*>(S + (row + i) * SNAP_STRIDE);
+            const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            r[0] += wx[a] * q0.x; r[1] += wx[a] * q0.y; r[2] += wx[a] * q1.x; r[3] += wx[a] * q1.y; r[4] += wx[a] * q2.x;
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) out[c] += wy[b] * r[c];
+    }
+}
 template <int INTERP>
 __device__ __forceinline__ void sample_level5(const double* __restrict__ S, const PacketGrid& g, double x, double y, double (&out)[5]) {
-    if (INTERP == 4) {
+    if (INTERP == 5) {
+        sample_nufft_5(S, g, x, y, out);
+    } else if (INTERP == 4) {
         sample_bspline3_5(S, g, x, y, out);
     } else if (INTERP == 2) {
         sample_bspline2_5(S, g, x, y, out);

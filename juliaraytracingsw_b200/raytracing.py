@@ -15,7 +15,7 @@ from ._lib import PacketsDesc, check, lib
 
 PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2, 3
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
-INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32, INTERP_BSPLINE3 = 0, 1, 2, 3, 4
+INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32, INTERP_BSPLINE3, INTERP_NUFFT = 0, 1, 2, 3, 4, 5
 INTEG_RK4, INTEG_IMPLICIT_MIDPOINT = 0, 1
 RAYKERNEL_AUTO, RAYKERNEL_CACHED, RAYKERNEL_TILE = -1, 0, 1
 
@@ -63,6 +63,11 @@ def get_velocity_info(prob, slot, psi_kind=PSI_RSW_BALANCED):
 def set_interpolation(prob, interp):
     """Choose the node data the flow's snapshots hold: INTERP_BILINEAR (5 fields) or INTERP_HERMITE_BICUBIC (7 fields)."""
     check(lib().swrt_flow_set_interp(prob._h, int(interp)))
+
+
+def set_nufft_width(prob, nw):
+    """Kernel width of INTERP_NUFFT (nodes of the 2x oversampled grid); the sampling error is ~ 10^(1 - nw)."""
+    check(lib().swrt_flow_set_nufft_width(prob._h, int(nw)))
 
 
 def set_snapshot_refinement(prob, refine):

@@ -314,3 +314,18 @@ def generate_initial_wavepackets_twolayer(L, k0, sqrtN):
             xk[r - 1] = (i * L / s - L / 2 - offset, j * L / s - L / 2 - offset,
                          k0 * np.cos(2 * np.pi * r / N), k0 * np.sin(2 * np.pi * r / N))
     return xk, np.ones(N)
+
+
+def sample_trigonometric(psih, x, y, grid):
+    """Exact spectral evaluation of u, v, ux, uy, vx at arbitrary points: what raytracing/NUFFTRaytracing.jl:68-84 approximates with
+    nufft2d2 (tol 1e-5) of the spectral fields -i l psih, i k psih, k l psih, l^2 psih, -k^2 psih.  Direct sum over the rfft
+    half plane with c2r semantics (weight 1 on kr = 0 and the Nyquist column, 2 elsewhere; real part).  O(N nkr nl): small cases."""
+    k, l = grid.kr, grid.l
+    specs = (-1j * l * psih, 1j * k * psih, k * l * psih, l * l * psih, -k * k * psih)
+    w = np.where((np.arange(grid.nkr) == 0) | (np.arange(grid.nkr) == grid.nkr - 1), 1.0, 2.0)[:, None]
+    out = np.empty((x.shape[0], 5))
+    ex = np.exp(1j * k[:, 0][None, :] * (x - grid.x[0])[:, None])            # (N, nkr)
+    ey = np.exp(1j * l[0, :][None, :] * (y - grid.y[0])[:, None])            # (N, nl)
+    for c, fh in enumerate(specs):
+        out[:, c] = np.einsum("nk,kl,nl->n", ex, w * fh, ey).real / (grid.nx * grid.ny)
+    return out

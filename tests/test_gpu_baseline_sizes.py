@@ -250,3 +250,54 @@ def test_device_initial_condition_generator_K15(nx):
     for part, amp in (((ugh, vgh, egh), P.ag), ((uwh, vwh, ewh), P.aw)):
         prob.sol = np.stack(part, axis=-1)
         assert abs(flow.max_abs_uv(prob)[0] / amp - 1) < 1e-12
+
+
+@pytest.mark.parametrize("nw,tol", [(6, 3e-5), (8, 3e-7), (12, 2e-10)])
+def test_nufft_sampler_against_the_exact_trigonometric_sum(nw, tol):
+    """f4: type-2 NUFFT sampling (2x oversampled grid of the deconvolved spectrum + nw x nw exponential-of-semicircle kernel) against
+    the exact trigonometric sum at arbitrary points (what raytracing/NUFFTRaytracing.jl:68-84 aims at with nufft2d2, tol 1e-5),
+    and a short ray trace against the oracle's RK4 with the exact sampler."""
+    nx = 64
+    g, p, sol0, c = config2_setup(nx)
+    from helpers import oracle_steps
+    sol1 = oracle_steps(g, p, sol0, c["dt"], 2)
+    prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    raytracing.set_interpolation(prob, raytracing.INTERP_NUFFT)
+    raytracing.set_nufft_width(prob, nw)
+    with pytest.raises(swrt._lib.SwrtError):
+        raytracing.get_velocity_info(prob, 0)                  # needs the 2x oversampled node grid
+    raytracing.set_snapshot_refinement(prob, 2)
+    prob.sol = sol0
+    raytracing.get_velocity_info(prob, 0)
+    flow.stepforward(prob, (), 2)
+    raytracing.get_velocity_info(prob, 1)
+    assert rel_l2(prob.sol, sol1) < 1e-12
+    psi0, psi1 = orsw.get_streamfunction(sol0, g, p), orsw.get_streamfunction(sol1, g, p)
+    rng = np.random.default_rng(4)
+    n = 300
+    xk = np.zeros((n, 4))
+    xk[:, 0:2] = rng.uniform(-3 * np.pi, 3 * np.pi, size=(n, 2))         # also outside the domain (periodic)
+    xk[:, 2:4] = c["k0"] * rng.standard_normal((n, 2))
+    sign = np.where(np.arange(n) % 2 == 0, -1.0, 1.0)
+    pk = raytracing.Packets(prob, n, c["f"], c["Cg"], nsub=2, interp=raytracing.INTERP_NUFFT)
+    pk.set(xk, sign)
+    exact = oray.sample_trigonometric(psi0, xk[:, 0], xk[:, 1], g)
+    U = np.empty((n, 2), order="F")
+    G = raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), pk, output_U=U)
+    scale_u, scale_g = np.abs(exact[:, 0:2]).max(), np.abs(exact[:, 2:5]).max()
+    assert np.abs(U - exact[:, 0:2]).max() / scale_u < tol
+    assert np.abs(G[:, 0:3] - exact[:, 2:5]).max() / scale_g < tol
+    np.testing.assert_array_equal(G[:, 3], -G[:, 0])
+    # RK4 over the two flow steps with the exact sampler on the oracle side
+    t1 = 2 * c["dt"]
+    raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (0.0, t1))
+    want, h = xk.copy(), t1 / 2
+    rhs = lambda z, al: oray.rhs_sampler(z, sign, al, oray.sample_trigonometric(psi0, z[:, 0], z[:, 1], g),
+                                         oray.sample_trigonometric(psi1, z[:, 0], z[:, 1], g), c["f"], c["Cg"])
+    for s_ in range(2):
+        a0 = s_ * h / t1
+        k1 = rhs(want, a0); k2 = rhs(want + 0.5 * h * k1, a0 + 0.5 * h / t1); k3 = rhs(want + 0.5 * h * k2, a0 + 0.5 * h / t1)
+        k4 = rhs(want + h * k3, a0 + h / t1)
+        want = want + (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    d = pk.get() - want
+    assert np.abs(d).max() / np.abs(want).max() < tol          # the packets move by O(dt): the sampling error barely shows
