@@ -232,4 +232,46 @@ function kcutoff_reset!(p::Packets, k_cutoff, k0)
     return Int(n[])
 end
 
+# --- team mode: slab-decomposed flow + y-band-sharded packets, one Julia process per GPU (include/swrt.h "team mode") ----------
+# The host only distributes 64-byte CUDA-IPC handles once (here: any `allgather(bytes)::Vector` the caller supplies, e.g.
+# MPI.Allgather); every step after that is native.  which: 1 A_RECV, 3 B_RECV, 6 FLAGS, 7 BAND.
+const TEAM_SHARED = (1, 3, 6, 7)
+function open_team!(prob::Problem, rank::Integer, world::Integer, allgather)
+    for which in TEAM_SHARED
+        mine = Vector{UInt8}(undef, 64)
+        check(ccall((:swrt_slab_ipc_handle, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), prob.h, which, mine))
+        for (r, h) in enumerate(allgather(mine))
+            check(ccall((:swrt_slab_ipc_open, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), prob.h, which, r - 1, h))
+        end
+    end
+    check(ccall((:swrt_slab_set_mode, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, world >= 4 ? 2 : 0))
+end
+"stepforward!(prob, [], n) of the slab-decomposed problem"
+slab_stepforward!(prob::Problem, n::Integer = 1) = check(ccall((:swrt_slab_step, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, n))
+"get_streamfunction! + get_velocity_info for this rank's band of rows (+ halo)"
+slab_velocity_snapshot!(prob::Problem, slot::Integer; psi_kind = 0) =
+    check(ccall((:swrt_slab_band_snapshot, libswrt), Cint, (Ptr{Cvoid}, Cint, Cint), prob.h, psi_kind, slot))
+team_barrier!(prob::Problem) = check(ccall((:swrt_slab_barrier, libswrt), Cint, (Ptr{Cvoid},), prob.h))
+function open_team!(p::Packets, allgather)
+    mine = Vector{UInt8}(undef, 64)
+    check(ccall((:swrt_packets_ipc_handle, libswrt), Cint, (Ptr{Cvoid}, Ptr{UInt8}), p.h, mine))
+    for (r, h) in enumerate(allgather(mine))
+        check(ccall((:swrt_packets_ipc_open, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), p.h, r - 1, h))
+    end
+end
+function resident(p::Packets)
+    n = Ref{Clonglong}(0)
+    check(ccall((:swrt_packets_resident, libswrt), Cint, (Ptr{Cvoid}, Ref{Clonglong}), p.h, n))
+    return Int(n[])
+end
+"set_initial_condition! (rsw/RSWRaytracingDriver.jl:15-54) on the device from phase = 2π rand(nkr, nl), sgn = sign.(rand(nkr, nl) .- 0.5)"
+function set_rsw_initial_condition!(prob::Problem, phase::Matrix{Float64}, sgn::Matrix{Float64}, Kg, ag, Kw, aw)
+    scales = zeros(2)
+    check(ccall((:swrt_flow_set_rsw_initial_condition, libswrt), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}),
+                prob.h, phase, sgn, Kg[1], Kg[2], ag, Kw[1], Kw[2], aw, scales))
+    return scales
+end
+set_nufft_width!(prob::Problem, nw::Integer) = check(ccall((:swrt_flow_set_nufft_width, libswrt), Cint, (Ptr{Cvoid}, Cint), prob.h, nw))
+
 end # module
