@@ -47,13 +47,14 @@ mutable struct Problem
     nx::Int; ny::Int; nkr::Int; dt::Float64; nvar::Int
     function Problem(; model = "RotatingShallowWater", stepper = "IFMAB3", nx = 128, ny = nx, Lx = 2π, Ly = Lx, ν = 1e-16, nν = 4,
                      f = 1.0, Cg = 1.0, dt = 5e-2, aliased_fraction = 1/3, use_filter = false, order = 4, dev = 0,
-                     U = 0.5, μ = 1e-2, f0 = f, δρρ0 = 0.2, Ro = 0.2, H = [0.5, 0.5], b = [2.0, 1.0], β = 0.0)
+                     U = 0.5, μ = 1e-2, f0 = f, δρρ0 = 0.2, Ro = 0.2, H = [0.5, 0.5], b = [2.0, 1.0], β = 0.0,
+                     slab_rank = 0, slab_size = 0)
         # MultiLayerQG.Problem(2, dev; nx, Lx, f₀, H, b, U, μ, β, dt, stepper, aliased_fraction): two equal layers, U = [U₁, U₂]
         F = model == "MultiLayerQG" ? f0^2 / ((b[1] - b[2]) * H[1]) : 2 * f0^2 / Cg^2 / δρρ0
         U1, U2 = U isa Number ? (U, -U) : (U[1], U[2])
         d = FlowDesc(model = MODELS[model], stepper = STEPPERS[stepper], nx = nx, ny = ny, Lx = Lx, Ly = Ly, nu = ν, nnu = nν, f = f,
                      Cg = Cg, dt = dt, aliased_fraction = aliased_fraction, use_filter = use_filter, filter_order = order, device = dev,
-                     U = U1, mu = μ, F = F, Ro = Ro, U2 = U2, beta = β)
+                     U = U1, mu = μ, F = F, Ro = Ro, U2 = U2, beta = β, slab_rank = slab_rank, slab_size = slab_size)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_flow_create, libswrt), Cint, (Ref{FlowDesc}, Ref{Ptr{Cvoid}}), d, out))
         p = new(out[], nx, ny, nx ÷ 2 + 1, dt, NVAR[MODELS[model]])
@@ -181,8 +182,9 @@ mutable struct Packets
     h::Ptr{Cvoid}
     n::Int
     prob::Problem
-    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16, interp = 0, integrator = 0)
-        d = PacketsDesc(n = n, interp = interp, integrator = integrator, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg)
+    function Packets(prob::Problem, n; f, Cg, nsub = 1, time_lerp = 0, sort_every = 16, interp = 0, integrator = 0, band_first = 0, band_capacity = 0)
+        d = PacketsDesc(n = n, interp = interp, integrator = integrator, nsub = nsub, time_lerp = time_lerp, sort_every = sort_every, f = f, Cg = Cg,
+                        band_first = band_first, band_capacity = band_capacity)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:swrt_packets_create, libswrt), Cint, (Ref{PacketsDesc}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), d, prob.h, out))
         p = new(out[], n, prob)
@@ -196,6 +198,8 @@ function generate_initial_wavepackets(prob, L, k0, Npackets, sqrtNpackets; f, Cg
     check(ccall((:swrt_packets_generate, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Clonglong, Clonglong), p.h, L, k0, sqrtNpackets, first))
     return p
 end
+generate!(p::Packets, L, k0, sqrtNpackets, first = 0) =
+    check(ccall((:swrt_packets_generate, libswrt), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Clonglong, Clonglong), p.h, L, k0, sqrtNpackets, first))
 set_packets!(p::Packets, xk::Matrix{Float64}, ωsign::Vector{Float64}) =
     check(ccall((:swrt_packets_set, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), p.h, xk, ωsign))
 function Base.Array(p::Packets)
