@@ -246,15 +246,19 @@ __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ 
             acc += isnan(a[i]) ? 1.0 : 0.0;
         }
     }
-    sh[threadIdx.x] = acc;
+    // warp-shuffle tree, then the 8 warp results through shared memory (NaN sticks in the max: a0 + a1 is NaN if either is)
+    auto comb = [mode](double a0, double a1) { return mode == 1 ? ((a0 != a0 || a1 != a1) ? a0 + a1 : (a1 > a0 ? a1 : a0)) : a0 + a1; };
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc = comb(acc, __shfl_down_sync(0xffffffffu, acc, off));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            const double a0 = sh[threadIdx.x], a1 = sh[threadIdx.x + s];
-            sh[threadIdx.x] = mode == 1 ? ((a0 != a0 || a1 != a1) ? a0 + a1 : (a1 > a0 ? a1 : a0)) : a0 + a1;
-        }
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        double r = threadIdx.x < 8 ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) r = comb(r, __shfl_down_sync(0xffffffffu, r, off));
+        if (threadIdx.x == 0) sh[0] = r;
     }
+    __syncthreads();
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 

@@ -949,19 +949,33 @@ __global__ void sort_hist_kernel(const double* __restrict__ xk, long long n, Pac
 // exclusive scan of `hist` (nb elements) in three launches: per-block scan, scan of block sums (one block), add
 constexpr int SCAN_BLOCK = 1024;
 __global__ void __launch_bounds__(SCAN_BLOCK) scan_block_kernel(unsigned* __restrict__ a, long long nb, unsigned* __restrict__ sums) {
-    __shared__ unsigned sh[SCAN_BLOCK];
+    // warp-shuffle scan: inclusive scan inside every warp (5 shuffle steps), the 32 warp totals scanned by the first warp,
+    // two barriers per block (the shared-memory Hillis-Steele version it replaces needed twenty)
+    __shared__ unsigned wsum[SCAN_BLOCK / 32];
     const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned v = i < nb ? a[i] : 0u;
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int off = 1; off < SCAN_BLOCK; off <<= 1) {
-        const unsigned t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0u;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
+    unsigned x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += t;
     }
-    if (i < nb) a[i] = sh[threadIdx.x] - v;  // exclusive
-    if (threadIdx.x == SCAN_BLOCK - 1 && sums) sums[blockIdx.x] = sh[threadIdx.x];
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned w = wsum[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += t;
+        }
+        wsum[lane] = w;                                   // inclusive totals of warps 0..lane
+    }
+    __syncthreads();
+    const unsigned base = wid ? wsum[wid - 1] : 0u;
+    if (i < nb) a[i] = base + x - v;                      // exclusive
+    if (threadIdx.x == SCAN_BLOCK - 1 && sums) sums[blockIdx.x] = base + x;
 }
 __global__ void scan_add_kernel(unsigned* __restrict__ a, long long nb, const unsigned* __restrict__ sums) {
     const long long i = blockIdx.x * (long long)SCAN_BLOCK + threadIdx.x;
