@@ -1963,8 +1963,8 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     if (use_tile) {
         static bool attr_done = false;
         if (!attr_done) {
-            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PATCH_BYTES));
-            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PATCH_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_done = true;
@@ -1994,7 +1994,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
 #undef SWRT_GEN
       else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
       else if (use_tile) {
-          const size_t smem = 2 * (size_t)PATCH_BYTES;
+          const size_t smem = (size_t)TILE_SMEM_BYTES;
           if (tile_minb >= 4) raytrace_rk4_tile_kernel<4><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, pg, rp);
           else raytrace_rk4_tile_kernel<3><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, pg, rp);
       }

@@ -27,8 +27,15 @@ namespace swrt {
 constexpr int TILE_SHIFT = 4, TILE = 1 << TILE_SHIFT;
 constexpr int TILE_MARGIN = 3;                           // cells of slack around the tile (packets drift between two sorts)
 constexpr int PATCH = TILE + 2 * TILE_MARGIN + 1;        // nodes per side of the staged patch (23)
-constexpr int PATCH_ROW = PATCH * SNAP_STRIDE;           // doubles per patch row (138 = 1104 B, a multiple of 16 B)
+// Row pitch of the patch in shared memory: 24 nodes (one more than needed).  With 23 nodes the pitch is 69 sixteen-byte chunks
+// = 5 (mod 8 bank groups), which puts cell (r, 15) and cell (r + 1, 0) -- neighbours in the sorted packet order -- on the same
+// banks (ncu: 29 % excess shared wavefronts, profiles/r02_b); 72 chunks = 0 (mod 8) only collides cells 8 columns apart.
+constexpr int PATCH_PITCH = PATCH + 1;
+constexpr int PATCH_ROW = PATCH_PITCH * SNAP_STRIDE;     // doubles per patch row (144 = 1152 B); the TMA box is PATCH_ROW x PATCH
 constexpr int PATCH_BYTES = (PATCH * PATCH_ROW * 8 + 127) / 128 * 128;   // one level, padded to the TMA destination alignment
+constexpr int TILE_THREADS = 128;
+constexpr int TILE_STAGE_BYTES = 2 * 5 * TILE_THREADS * 8;               // double-buffered packet state of the CTA's next round
+constexpr int TILE_SMEM_BYTES = 2 * PATCH_BYTES + TILE_STAGE_BYTES;
 
 struct PacketGrid {
     int nx, ny;
@@ -190,8 +197,9 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
 #pragma unroll
             for (int cr = 0; cr < 4; ++cr) {
                 const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) st.c[lev][cr][k] = __ldg(q + k);
+                st.c[lev][cr][0] = __ldg(q);
+                st.c[lev][cr][1] = __ldg(q + 1);
+                st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
             }
         }
     }
@@ -321,12 +329,17 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
             for (int lev = 0; lev < 2; ++lev) {
                 const double2* q = reinterpret_cast<const double2*>(tp.lev[lev] + o);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     st.c[lev][0][k] = q[k];
                     st.c[lev][1][k] = q[3 + k];
                     st.c[lev][2][k] = q[PATCH_ROW / 2 + k];
                     st.c[lev][3][k] = q[PATCH_ROW / 2 + 3 + k];
                 }
+                // fifth field (vx): an 8-byte load, the record's pad is never read (two wavefronts instead of four)
+                st.c[lev][0][2].x = reinterpret_cast<const double*>(q + 2)[0];
+                st.c[lev][1][2].x = reinterpret_cast<const double*>(q + 5)[0];
+                st.c[lev][2][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 2)[0];
+                st.c[lev][3][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 5)[0];
             }
         } else {
             stencil_rows(g, j0, j1);
@@ -337,8 +350,9 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
 #pragma unroll
                 for (int cr = 0; cr < 4; ++cr) {
                     const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) st.c[lev][cr][k] = __ldg(q + k);
+                    st.c[lev][cr][0] = __ldg(q);
+                    st.c[lev][cr][1] = __ldg(q + 1);
+                    st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
                 }
             }
         }
@@ -367,7 +381,10 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
     d[3] = -(W[3] * k - W[2] * l);
 }
 
-constexpr int TILE_THREADS = 128;
+// 8-byte asynchronous copy global -> shared (LDGSTS), evict-first in L2: the packet state is touched once per launch
+__device__ __forceinline__ void cp_async8_stream(void* smem_dst, const void* gsrc, unsigned long long policy) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(policy));
+}
 template <int MINB>
 __global__ void __launch_bounds__(TILE_THREADS, MINB)
     raytrace_rk4_tile_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n, const double* __restrict__ So,
@@ -397,18 +414,37 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         if (threadIdx.x == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, 2u * PATCH * PATCH_ROW * 8);
+            mbar_expect_tx(&bar, 2u * PATCH * PATCH_ROW * 8);   // (a box that sticks out of the tensor still delivers its full byte count, zero filled)
             tma_load_2d(tile_smem, &mapO, tp.pi * SNAP_STRIDE, prow, &bar);
             tma_load_2d(tile_smem + PATCH_BYTES, &mapN, tp.pi * SNAP_STRIDE, prow, &bar);
         }
     }
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
+    // The state of a thread's NEXT packet streams into shared memory (cp.async, no registers) while it integrates the current
+    // one: the first use of a freshly loaded state was the largest single stall of the kernel (ncu: 24 % of all samples,
+    // long_scoreboard).  A thread only ever reads the slots it copied itself, so no barrier is needed.
+    double* stage = reinterpret_cast<double*>(tile_smem + 2 * PATCH_BYTES);     // [2][5][TILE_THREADS]
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    auto prefetch = [&](long long i, int buf) {
+        if (i < end) {
+            double* d = stage + buf * 5 * TILE_THREADS + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async8_stream(d + c * TILE_THREADS, xk + c * g.ld + i, pol);
+            cp_async8_stream(d + 4 * TILE_THREADS, sign + i, pol);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    prefetch(start + threadIdx.x, 0);
     bool waited = !tp.staged;
-    for (long long i = start + threadIdx.x; i < end; i += TILE_THREADS) {
-        // the packet state is read and written exactly once per launch: streaming accesses leave L2 to the node records
-        double s[4] = {__ldcs(xk + i), __ldcs(xk + g.ld + i), __ldcs(xk + 2 * g.ld + i), __ldcs(xk + 3 * g.ld + i)};
-        const double sg = __ldcs(sign + i);
-        if (!waited) { mbar_wait(&bar, 0); waited = true; }      // the patch has landed (first state loads overlapped the copy)
+    int buf = 0;
+    for (long long i = start + threadIdx.x; i < end; i += TILE_THREADS, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        const double* sv = stage + buf * 5 * TILE_THREADS + threadIdx.x;
+        double s[4] = {sv[0], sv[TILE_THREADS], sv[2 * TILE_THREADS], sv[3 * TILE_THREADS]};
+        const double sg = sv[4 * TILE_THREADS];
+        prefetch(i + TILE_THREADS, buf ^ 1);
+        if (!waited) { mbar_wait(&bar, 0); waited = true; }      // the patch has landed (the first state copy overlapped it)
         Stencil st;
         st.ci = -1;
         st.cj = -1;
