@@ -310,13 +310,21 @@ def run_swrt(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl swrt needs a CUDA device (no CPU fallback)")
+    # SWRT_TEAM_SAME_GPU=1: functional check of the N > 1 path on a one-GPU box -- all ranks on cuda:0, gloo, host team barrier
+    same_gpu = os.environ.get("SWRT_TEAM_SAME_GPU", "0") == "1"
+    if same_gpu:
+        local = 0
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if same_gpu:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -324,6 +332,10 @@ def run_swrt(args):
     def max_over_ranks(x):
         if dist is None:
             return x
+        if same_gpu:
+            parts = [None] * world
+            dist.all_gather_object(parts, float(x))
+            return max(parts)
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
@@ -341,7 +353,7 @@ def run_swrt(args):
         sol0 = prob.sol
         dt, ν = drivers.timestep_and_viscosity(P)
         prob.close()
-        prob = SlabProblem(dist, local, nx=P.nx, Lx=P.L, dt=dt, f=P.f, Cg=P.Cg, ν=ν, nν=P.nν, order=P.filter_order,
+        prob = SlabProblem(dist, local, barrier="host" if same_gpu else None, nx=P.nx, Lx=P.L, dt=dt, f=P.f, Cg=P.Cg, ν=ν, nν=P.nν, order=P.filter_order,
                            use_filter=P.use_filter, aliased_fraction=P.aliased_fraction)
         prob.sol = sol0
         del sol0
