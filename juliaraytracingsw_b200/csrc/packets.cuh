@@ -27,11 +27,13 @@ namespace swrt {
 constexpr int TILE_SHIFT = 4, TILE = 1 << TILE_SHIFT;
 constexpr int TILE_MARGIN = 3;                           // cells of slack around the tile (packets drift between two sorts)
 constexpr int PATCH = TILE + 2 * TILE_MARGIN + 1;        // nodes per side of the staged patch (23)
-// Row pitch of the patch in shared memory: 24 nodes (one more than needed).  With 23 nodes the pitch is 69 sixteen-byte chunks
-// = 5 (mod 8 bank groups), which puts cell (r, 15) and cell (r + 1, 0) -- neighbours in the sorted packet order -- on the same
-// banks (ncu: 29 % excess shared wavefronts, profiles/r02_b); 72 chunks = 0 (mod 8) only collides cells 8 columns apart.
-constexpr int PATCH_PITCH = PATCH + 1;
-constexpr int PATCH_ROW = PATCH_PITCH * SNAP_STRIDE;     // doubles per patch row (144 = 1152 B); the TMA box is PATCH_ROW x PATCH
+// Row pitch of the patch in shared memory, in doubles.  A stencil fill is LDS.128s whose lanes sit in a small neighbourhood of
+// cells (the sorted order is up to 16 steps stale): cell (r, c) starts at 16-byte chunk r * pitch + 3 c, and the eight bank
+// groups of a wavefront are chunk mod 8.  Pitch = 69 chunks (the dense 23 nodes, = 5 mod 8) collides (r, c) with (r + 1, c + 1),
+// pitch = 72 (= 0) collides every row with the next (ncu: 29 % / 27 % excess shared wavefronts, profiles/r02_b, r02_d); 73 chunks
+// = 1 (mod 8) keeps a 3 x 3 neighbourhood of cells on distinct bank groups except one pair.
+constexpr int PATCH_ROW = 146;                           // doubles per patch row (73 chunks = 1168 B >= 23 nodes); the TMA box is PATCH_ROW x PATCH
+static_assert(PATCH_ROW >= PATCH * SNAP_STRIDE && PATCH_ROW % 2 == 0 && PATCH_ROW <= 256, "patch row must hold the nodes, stay 16-byte granular and fit a TMA box");
 constexpr int PATCH_BYTES = (PATCH * PATCH_ROW * 8 + 127) / 128 * 128;   // one level, padded to the TMA destination alignment
 constexpr int TILE_THREADS = 128;
 constexpr int TILE_STAGE_BYTES = 2 * 5 * TILE_THREADS * 8;               // double-buffered packet state of the CTA's next round
