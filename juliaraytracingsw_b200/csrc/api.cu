@@ -115,7 +115,7 @@ struct swrt_flow {
     TeamFlags* flags = nullptr;
     TeamFlags* peerflags[kMaxPeers] = {};
     double* peerband[kMaxPeers] = {};
-    unsigned long long epoch = 0;
+    unsigned long long epoch[2] = {0, 0};       // channel 0: the flow's stream, channel 1: packet collectives (may run on the packets' own stream)
     int barrier_mode = 0;                        // 0 = device flags over NVLink, 1 = host callback after a stream synchronise
     void (*barrier_cb)(void*) = nullptr;
     void* barrier_arg = nullptr;
@@ -1201,7 +1201,18 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
     if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
     cudaError_t e;
-    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
+    // like the single-GPU snapshot: psih materialised once (this rank's columns), so that the three y-jobs run through the
+    // prefetching y-pass instead of re-deriving the streamfunction three times
+    bool materialise = false;
+    SWRT_DISPATCH(h->L.ny, e, (materialise = LN::psi_prefetch, cudaSuccess));
+    CK(e);
+    if (materialise && h->L.kr_keep > 0) {
+        const long long nmodes = (long long)(h->L.ny - (h->L.lz1 - h->L.lz0)) * h->L.kr_keep;
+        ProfScope ps(h, K_PSI);
+        psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, h->L, h->psih);
+        CK(cudaGetLastError());
+    }
+    { ProfScope ps(h, K_PSI_A); SWRT_DISPATCH(h->L.ny, e, LN::psi_stage_a(ld, materialise ? h->psih : nullptr, h->L, out_slab(h, 0, h->G, 3), h->tw_y, h->st)); }
     CK(e);
     return slab_ship_a(h, 3);
 }
@@ -1227,9 +1238,12 @@ int swrt_slab_set_barrier(swrt_flow* h, int mode, void (*callback)(void*), void*
     h->barrier_arg = arg;
     return SWRT_OK;
 }
-static int team_barrier(swrt_flow* h) {
+static int team_barrier(swrt_flow* h, int channel = 0, cudaStream_t st = nullptr) {
+    // Two independent channels (flag words + epochs): every rank issues the same sequence of barriers PER CHANNEL, but the flow's
+    // stream and a packet handle's own stream advance independently, so their barriers must not share a counter.
+    if (!st) st = h->st;
     if (h->barrier_mode == 1) {          // every rank's stream drained, then the caller's host barrier (processes sharing one GPU)
-        CK(cudaStreamSynchronize(h->st));
+        CK(cudaStreamSynchronize(st));
         h->barrier_cb(h->barrier_arg);
         return SWRT_OK;
     }
@@ -1238,8 +1252,8 @@ static int team_barrier(swrt_flow* h) {
         if (!h->peerflags[r]) return fail(SWRT_ERR_STATE, "team barrier: the flags of rank %d are not mapped (swrt_slab_ipc_open SWRT_SLAB_FLAGS)", r);
         tp.f[r] = h->peerflags[r];
     }
-    h->epoch += 1;
-    { ProfScope ps(h, K_OTHER); team_barrier_kernel<<<1, 32, 0, h->st>>>(tp, h->P, h->rank, h->epoch); }
+    h->epoch[channel] += 1;
+    { ProfScope ps(h, K_OTHER, st); team_barrier_kernel<<<1, 32, 0, st>>>(tp, h->P, h->rank, h->epoch[channel], channel); }
     CK(cudaGetLastError());
     return SWRT_OK;
 }
@@ -1681,7 +1695,6 @@ static cudaError_t mark_read(swrt_packets* p) { return p->own ? cudaEventRecord(
 int swrt_packets_use_own_stream(swrt_packets* p) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
     if (p->own) return SWRT_OK;
-    if (p->band) return fail(SWRT_ERR_UNSUPPORTED, "band-sharded packets run on the flow's stream (their hand-over is ordered by the team barrier)");
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     CK(cudaStreamSynchronize(f->st));
@@ -1743,14 +1756,14 @@ static int band_scatter(swrt_packets* p, long long nrows) {
     if (rc) return rc;
     const int P = f->P;
     unsigned long long hdr[4] = {0ULL, (unsigned long long)nrows, (unsigned long long)p->first, 0ULL};   // resident count, staging rows, first row, overflow
-    CK(cudaMemcpyAsync(p->tab + 2 * P, hdr, sizeof hdr, cudaMemcpyHostToDevice, f->st));
-    if ((rc = team_barrier(f))) return rc;                                  // every staging block and header is in place
+    CK(cudaMemcpyAsync(p->tab + 2 * P, hdr, sizeof hdr, cudaMemcpyHostToDevice, pst(p)));
+    if ((rc = team_barrier(f, 1, pst(p)))) return rc;                                  // every staging block and header is in place
     int bshift = 0; while ((1 << bshift) < f->L.yrows) ++bshift;
-    { ProfScope ps(f, K_OTHER); team_scatter_scan_kernel<<<148 * 4, 256, 0, f->st>>>(arena_peers(p), P, f->rank, p->cur, p->cap, packet_grid(f, p), bshift); }
+    { ProfScope ps(f, K_OTHER, pst(p)); team_scatter_scan_kernel<<<148 * 4, 256, 0, pst(p)>>>(arena_peers(p), P, f->rank, p->cur, p->cap, packet_grid(f, p), bshift); }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, f->st));
-    if ((rc = team_barrier(f))) return rc;                                  // the staging blocks may be overwritten again
-    CK(cudaStreamSynchronize(f->st));
+    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, pst(p)));
+    if ((rc = team_barrier(f, 1, pst(p)))) return rc;                                  // the staging blocks may be overwritten again
+    CK(cudaStreamSynchronize(pst(p)));
     if (p->tab_host[3]) return fail(SWRT_ERR_STATE, "band packets: more than band_capacity = %lld packets fall into the band of rank %d", p->cap, f->rank);
     p->ncur = (long long)p->tab_host[0];
     p->permuted = true;
@@ -1765,7 +1778,7 @@ static int band_gather_launch(swrt_packets* p, int which, int c0, int ncols, dou
     swrt_flow* f = p->flow;
     ArenaPeers ap = arena_peers(p);
     if (which == 1) for (int r = 0; r < f->P; ++r) ap.a[r].out += (long long)c0 * p->cap;
-    { ProfScope ps(f, K_OTHER); team_gather_scan_kernel<<<148 * 4, 256, 0, f->st>>>(ap, f->P, p->cur, which, ncols, p->cap, p->first, p->d.n, dst, ldd); }
+    { ProfScope ps(f, K_OTHER, pst(p)); team_gather_scan_kernel<<<148 * 4, 256, 0, pst(p)>>>(ap, f->P, p->cur, which, ncols, p->cap, p->first, p->d.n, dst, ldd); }
     CK(cudaGetLastError());
     return SWRT_OK;
 }
@@ -1781,17 +1794,17 @@ static int packets_set_impl(swrt_packets* p, const double* xk_host, long long ld
         if (!sign_host) {
             int rc = band_peers_ready(p);
             if (rc) return rc;
-            if ((rc = team_barrier(f))) return rc;
+            if ((rc = team_barrier(f, 1, pst(p)))) return rc;
             ArenaPeers ap = arena_peers(p);
             for (int r = 0; r < f->P; ++r) ap.a[r].out = ap.a[r].sign[p->cur];          // gather column: the resident signs
-            { ProfScope ps(f, K_OTHER); team_gather_scan_kernel<<<148 * 4, 256, 0, f->st>>>(ap, f->P, p->cur, 1, 1, p->cap, p->first, n, p->xk2, p->cap); }
+            { ProfScope ps(f, K_OTHER, pst(p)); team_gather_scan_kernel<<<148 * 4, 256, 0, pst(p)>>>(ap, f->P, p->cur, 1, 1, p->cap, p->first, n, p->xk2, p->cap); }
             CK(cudaGetLastError());
-            if ((rc = team_barrier(f))) return rc;
-            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, p->xk2, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, f->st));
+            if ((rc = team_barrier(f, 1, pst(p)))) return rc;
+            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, p->xk2, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, pst(p)));
         } else {
-            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, f->st));
+            CK(cudaMemcpyAsync(p->out6 + 4 * p->cap, sign_host, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, pst(p)));
         }
-        CK(copy_cols(p->out6, xk_host, n, 4, ld, cudaMemcpyHostToDevice, f->st, p->cap));
+        CK(copy_cols(p->out6, xk_host, n, 4, ld, cudaMemcpyHostToDevice, pst(p), p->cap));
         return band_scatter(p, n);
     }
     if (!sign_host && p->permuted) {   // keep the frequency signs: bring them back to the caller's order first
@@ -1825,11 +1838,11 @@ static int packets_get_impl(swrt_packets* p, double* xk_host, long long ld, bool
     if (p->band) {   // COLLECTIVE: every rank pulls its caller-order rows out of all ranks' resident arrays
         int rc = band_peers_ready(p);
         if (rc) return rc;
-        if ((rc = team_barrier(f))) return rc;
+        if ((rc = team_barrier(f, 1, pst(p)))) return rc;
         if ((rc = band_gather_launch(p, 0, 0, 4, p->out6, p->cap))) return rc;
-        if ((rc = team_barrier(f))) return rc;
-        CK(copy_cols(xk_host, p->out6, n, 4, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
-        CK(cudaStreamSynchronize(f->st));
+        if ((rc = team_barrier(f, 1, pst(p)))) return rc;
+        CK(copy_cols(xk_host, p->out6, n, 4, ld, cudaMemcpyDeviceToHost, pst(p), p->cap));
+        CK(cudaStreamSynchronize(pst(p)));
         return SWRT_OK;
     }
     const double* src = p->xk;
@@ -1911,15 +1924,15 @@ static int sort_packets(swrt_packets* p) {
     if ((rc = band_peers_ready(p))) return rc;
     const ArenaPeers ap = arena_peers(p);
     const long long keys_per_rank = (long long)f->L.yrows * f->d.nx;
-    { ProfScope ps(f, K_SORT); team_publish_segments_kernel<<<1, 32, 0, f->st>>>(p->hist, keys_per_rank, ap, P, f->rank); }
+    { ProfScope ps(f, K_SORT, pst(p)); team_publish_segments_kernel<<<1, 32, 0, pst(p)>>>(p->hist, keys_per_rank, ap, P, f->rank); }
     CK(cudaGetLastError());
-    if ((rc = team_barrier(f))) return rc;                                  // every rank's sorted array and segment table are complete
-    { ProfScope ps(f, K_SORT); team_pull_segments_kernel<<<148 * 4, 256, 0, f->st>>>(ap, P, f->rank, p->cur, p->cur ^ 1, p->cap); }
+    if ((rc = team_barrier(f, 1, pst(p)))) return rc;                                  // every rank's sorted array and segment table are complete
+    { ProfScope ps(f, K_SORT, pst(p)); team_pull_segments_kernel<<<148 * 4, 256, 0, pst(p)>>>(ap, P, f->rank, p->cur, p->cur ^ 1, p->cap); }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, f->st));
-    CK(cudaMemcpyAsync(p->tab_host + 4, p->count + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, f->st));
-    if ((rc = team_barrier(f))) return rc;                                  // the peers have read my sorted array: it may be reused
-    CK(cudaStreamSynchronize(f->st));                                       // the new resident count sizes the next launches
+    CK(cudaMemcpyAsync(p->tab_host, p->tab + 2 * P, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, pst(p)));
+    CK(cudaMemcpyAsync(p->tab_host + 4, p->count + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, pst(p)));
+    if ((rc = team_barrier(f, 1, pst(p)))) return rc;                                  // the peers have read my sorted array: it may be reused
+    CK(cudaStreamSynchronize(pst(p)));                                       // the new resident count sizes the next launches
     if (p->tab_host[3]) return fail(SWRT_ERR_STATE, "band packets: more than band_capacity = %lld packets moved into the band of rank %d", p->cap, f->rank);
     if (p->tab_host[4]) return fail(SWRT_ERR_STATE, "band packets: %llu packets left band + halo (%d rows) between two hand-overs; lower sort_every", p->tab_host[4], f->halo);
     std::swap(p->xk, p->xk2);
@@ -2034,15 +2047,15 @@ static int packets_sample_impl(swrt_packets* p, int slot, double* u_host, double
     if (p->band) {   // COLLECTIVE: resident-order samples -> caller-order rows (through the alternate state buffer, 4 columns at a time)
         int rc = band_peers_ready(p);
         if (rc) return rc;
-        if ((rc = team_barrier(f))) return rc;
+        if ((rc = team_barrier(f, 1, pst(p)))) return rc;
         if ((rc = band_gather_launch(p, 1, 0, 2, p->xk2, p->cap))) return rc;
-        CK(copy_cols(u_host, p->xk2, n, 2, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
+        CK(copy_cols(u_host, p->xk2, n, 2, ld, cudaMemcpyDeviceToHost, pst(p), p->cap));
         if (g_host) {
             if ((rc = band_gather_launch(p, 1, 2, 4, p->xk2, p->cap))) return rc;
-            CK(copy_cols(g_host, p->xk2, n, 4, ld, cudaMemcpyDeviceToHost, f->st, p->cap));
+            CK(copy_cols(g_host, p->xk2, n, 4, ld, cudaMemcpyDeviceToHost, pst(p), p->cap));
         }
-        if ((rc = team_barrier(f))) return rc;
-        CK(cudaStreamSynchronize(f->st));
+        if ((rc = team_barrier(f, 1, pst(p)))) return rc;
+        CK(cudaStreamSynchronize(pst(p)));
         return SWRT_OK;
     }
     CK(copy_cols(u_host, p->U, n, 2, ld, cudaMemcpyDeviceToHost, pst(p)));
@@ -2145,6 +2158,8 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
             s += 1;
         }
     }
+    // packets on their own stream: whatever the caller times or reads on the flow's stream after this call includes their last trace
+    if (p->own && nsteps > 0) CK(cudaStreamWaitEvent(f->st, p->ev_done, 0));
     return SWRT_OK;
 }
 

@@ -19,21 +19,21 @@
 
 namespace swrt {
 
-struct TeamFlags {                      // lives in every rank's shared arena
-    unsigned long long arrive[kMaxPeers];
+struct TeamFlags {                      // lives in every rank's shared arena; [channel][source rank]
+    unsigned long long arrive[2][kMaxPeers];
 };
 struct TeamPeers {
     TeamFlags* f[kMaxPeers];
 };
 
-__global__ void team_barrier_kernel(TeamPeers peers, int P, int self, unsigned long long epoch) {
+__global__ void team_barrier_kernel(TeamPeers peers, int P, int self, unsigned long long epoch, int channel) {
     const int d = threadIdx.x;
     if (d >= P) return;
     __threadfence_system();                                            // everything this stream did before is visible to the peers
-    volatile unsigned long long* theirs = &peers.f[d]->arrive[self];
+    volatile unsigned long long* theirs = &peers.f[d]->arrive[channel][self];
     *theirs = epoch;
     __threadfence_system();
-    volatile unsigned long long* mine = &peers.f[self]->arrive[d];
+    volatile unsigned long long* mine = &peers.f[self]->arrive[channel][d];
     while (*mine < epoch) __nanosleep(64);
     __threadfence_system();
 }
@@ -96,16 +96,30 @@ __global__ void __launch_bounds__(256) team_pull_segments_kernel(ArenaPeers peer
 __global__ void __launch_bounds__(256) team_scatter_scan_kernel(ArenaPeers peers, int P, int self, int dst_buf, long long cap, PacketGrid g,
                                                                 int band_shift) {
     const PacketArena me = peers.a[self];
+    const unsigned lane = threadIdx.x & 31;
     for (int s = 0; s < P; ++s) {
         const PacketArena src = peers.a[s];
         const long long rows = (long long)src.tab[2 * P + 1], first = (long long)src.tab[2 * P + 2];
-        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-            const double y = __ldcs(src.out + cap + i);
-            int j0, j1;
-            double b;
-            cell(y, g.y0, g.inv_dy, g.ny, j0, j1, b);
-            if (band_owner(j0, band_shift) != self) continue;
-            const unsigned long long pos = atomicAdd(&me.tab[2 * P], 1ULL);
+        // uniform trip count per warp: the append position comes from ONE atomic per warp (ballot + popc), not one per packet
+        for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < rows; i0 += (long long)gridDim.x * blockDim.x) {
+            const long long i = i0 + threadIdx.x;
+            double y = 0.0;
+            bool mine = false;
+            if (i < rows) {
+                y = __ldcs(src.out + cap + i);
+                int j0, j1;
+                double b;
+                cell(y, g.y0, g.inv_dy, g.ny, j0, j1, b);
+                mine = band_owner(j0, band_shift) == self;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (m == 0u) continue;
+            unsigned long long base = 0ULL;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane == leader) base = atomicAdd(&me.tab[2 * P], (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!mine) continue;
+            const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
             if (pos >= (unsigned long long)cap) { me.tab[2 * P + 3] = 1ULL; continue; }
             me.xk[dst_buf][pos] = __ldcs(src.out + i);
             me.xk[dst_buf][cap + pos] = y;

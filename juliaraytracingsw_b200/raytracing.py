@@ -99,10 +99,11 @@ class Packets:
     """Device-resident wave packets = `create_template_ode(packets)` + the packet arrays."""
 
     def __init__(self, prob, n, f, Cg, nsub=1, time_lerp=LERP_PHYSICAL, sort_every=16, interp=INTERP_BILINEAR,
-                 integrator=INTEG_RK4, first=None, capacity=None):
+                 integrator=INTEG_RK4, first=None, capacity=None, overlap=True):
         """On a slab-decomposed problem (slab.SlabProblem, team mode) the packets are sharded by y-band: `n` is this rank's
         caller-order block, rows [first, first + n) of the ensemble (default: blocks in rank order), `capacity` the packets a
-        rank can host (default 1.5 x the mean + 4096, the same on every rank); every method becomes a collective call."""
+        rank can host (default 1.5 x the mean + 4096, the same on every rank); every method becomes a collective call.
+        `overlap` puts the band packets on their own stream, so the ray tracing of step n runs beside the flow step n + 1."""
         self.prob, self.n = prob, int(n)
         self.band = getattr(prob, "world", 1) > 1
         if self.band:
@@ -123,6 +124,8 @@ class Packets:
             check(lib().swrt_packets_ipc_handle(self._h, buf))
             for r, h in enumerate(prob._gather(buf.raw)):
                 check(lib().swrt_packets_ipc_open(self._h, r, h))
+            if overlap:
+                self.use_own_stream()
             prob.dist.barrier()
 
     def resident(self):

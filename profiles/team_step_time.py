@@ -30,7 +30,8 @@ sp = SlabProblem(dist, local, barrier="host" if same else None, nx=P.nx, Lx=P.L,
 sp.sol = sol0
 N = P.Npackets
 lo, hi = rank * N // world, (rank + 1) * N // world
-pk = raytracing.generate_initial_wavepackets(sp, P.L, 5.196, hi - lo, sq, P.f, P.Cg, first=lo)
+pk = raytracing.Packets(sp, hi - lo, P.f, P.Cg, first=lo, overlap=int(os.environ.get("OVERLAP", 1)) != 0)
+pk.generate(P.L, 5.196, sq, lo)
 if not int(os.environ.get("LATTICE", 0)):
     xk = pk.get()
     xk[:, 0:2] = np.random.default_rng(1000 + rank).uniform(-np.pi, np.pi, size=(hi - lo, 2))
@@ -40,9 +41,10 @@ raytracing.get_velocity_info(sp, 0)
 
 
 def timed(fn, n):
-    sp.sync(); dist.barrier()
+    pk.sync(); sp.sync(); dist.barrier()
     sp.timer_start()
     fn(n)
+    pk.sync()                       # (packets on their own stream: the host waits for them before the flow-stream timer stops)
     ms = sp.timer_stop()
     parts = [None] * world
     dist.all_gather_object(parts, ms)
@@ -50,7 +52,7 @@ def timed(fn, n):
 
 
 drivers.coupled_steps(sp, pk, 20)
-res = {"ranks": world, "nx": nx, "packets": N, "resident": sp._gather(pk.resident())}
+res = {"ranks": world, "nx": nx, "packets": N, "overlap": int(os.environ.get("OVERLAP", 1)), "slab_mode": sp.mode, "resident": sp._gather(pk.resident())}
 res["coupled_ms"] = timed(lambda n: drivers.coupled_steps(sp, pk, n), 64)
 res["flow_ms"] = timed(lambda n: sp.stepforward(n), 64)
 res["snapshot_ms"] = timed(lambda n: [sp.velocity_snapshot(1, 0) for _ in range(n)], 32)

@@ -36,7 +36,7 @@ def main():
     worst = {}
 
     # ---- 1. RSW coupled loop: flow parity, packet parity through several hand-overs, output frame, k-cutoff, set()
-    nx = int(os.environ.get("SWRT_TEAM_NX", 128))
+    nx = int(os.environ.get("SWRT_TEAM_NX", max(128, 16 * world)))
     side, nsteps, sort_every = 64, 41, 8
     g, p, sol0, c = config2_setup(nx)
     sp = SlabProblem(dist, local, barrier=barrier, nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
@@ -100,7 +100,7 @@ def main():
     pk.close(); sp.close()
 
     # ---- 2. lattice generator on the team: bit-exact rows, every rank's block
-    sp = SlabProblem(dist, local, barrier=barrier, nx=64, dt=1e-3, f=3.0)
+    sp = SlabProblem(dist, local, barrier=barrier, nx=max(64, 16 * world), dt=1e-3, f=3.0)
     n_side = 24
     wantl, _ = oray.generate_initial_wavepackets(2 * np.pi, 5.196152422706632, n_side)
     Nl = n_side * n_side
@@ -112,7 +112,7 @@ def main():
     pl.close(); sp.close()
 
     # ---- 3. two-layer QG (config 5's model) and SWQG: flow steps + band snapshot against the oracle
-    nx2, U, mu, f0, Cg, drr, nnu, dt = 128, 0.5, 1e-2, 3.0, 1.0, 0.2, 4, 1e-3
+    nx2, U, mu, f0, Cg, drr, nnu, dt = max(128, 16 * world), 0.5, 1e-2, 3.0, 1.0, 0.2, 4, 1e-3
     nu = 40 * 2 * np.pi / nx2 / ((nx2 / 2 - 1) ** (2 * nnu)) / dt
     F = 2 * f0 ** 2 / Cg ** 2 / drr
     from helpers import random_state
