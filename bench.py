@@ -181,6 +181,23 @@ def run_reference(args):
 
 
 
+def gpu_local_cpus(dev):
+    """CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(dev)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        return cpus or None
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------- measured-elsewhere evidence
 def load_ncu_traffic():
     """DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum) of the kernels this bench names, from the
@@ -440,6 +457,10 @@ def run_swrt(args):
     # ---- end to end: pinned host packets in, output frame out, every step, through the public API
     e2e = None
     if not args.no_e2e:
+        # page-locked buffers are allocated (first touched) by a thread running on the GPU's own NUMA node
+        old_aff, near = os.sched_getaffinity(0), gpu_local_cpus(local)
+        if near:
+            os.sched_setaffinity(0, near)
         pin = lambda *shape: torch.empty(shape[::-1], dtype=torch.float64, pin_memory=True).numpy().T  # Fortran-ordered view
         h_xk, h_out, h_U, h_G = pin(nloc, 4), pin(nloc, 4), pin(nloc, 2), pin(nloc, 4)
         h_sign = torch.empty(nloc, dtype=torch.float64, pin_memory=True).numpy()
@@ -492,6 +513,8 @@ def run_swrt(args):
                                              "back every step (savepacketdata! with write_gradients)"}}
         if pipe is not None:
             pipe.close()
+        e2e["numa_local_cpus"] = len(near) if near else None
+        os.sched_setaffinity(0, old_aff)
     clk = clocks.stop()
     # ---- the other BASELINE configs as extra keys of the same line (single-GPU ones on rank 0's GPU at N = 1; config 5 at N = 8)
     extra_cfg = {}

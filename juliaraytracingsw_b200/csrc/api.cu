@@ -510,7 +510,12 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
 
     auto bail = [&](int code) { swrt_flow_destroy(h); return code; };
 #define CKB(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { fail(SWRT_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); return bail(SWRT_ERR_CUDA); } } while (0)
-    CKB(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    {   // the flow's stream gets the greatest priority: its short, latency-bound kernels then take SM slots ahead of the CTAs of a
+        // long ray-tracing kernel that runs beside it on a packet handle's own stream (team mode, PacketPipeline)
+        int lo = 0, hi = 0;
+        CKB(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CKB(cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi));
+    }
     CKB(cudaEventCreate(&h->ev0));
     CKB(cudaEventCreateWithFlags(&h->ev_sync, cudaEventDisableTiming));
     CKB(cudaEventCreate(&h->ev1));
@@ -1698,7 +1703,11 @@ int swrt_packets_use_own_stream(swrt_packets* p) {
     swrt_flow* f = p->flow;
     CK(cudaSetDevice(f->d.device));
     CK(cudaStreamSynchronize(f->st));
-    CK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&p->st, cudaStreamNonBlocking, lo));      // least priority: fills what the flow's stream leaves
+    }
     CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
     p->own = true;
     f->readers.push_back(p);

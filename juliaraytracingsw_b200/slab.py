@@ -50,7 +50,9 @@ class SlabProblem(flow.Problem):
         self.p2p = False
         # first transpose: "push" (y-pass stores into the peers), "pull" (x-pass reads the peers' send buffers) or "copy"
         # (local stores + a block-copy kernel); measured in profiles/r01_g_multigpu_summary.md
-        default = "copy" if self.world >= 4 else "push"
+        # (r02_h, 8 GPUs, 2048^2: push 0.331 / copy 0.341 ms per coupled step -- 64-byte pieces from 4-column y tiles; at 4096^2
+        # the tiles are 2 columns wide and the block copy wins from 4 ranks on)
+        default = "copy" if (self.world >= 4 and kw.get("nx", 128) > 2048) else "push"
         self.mode = os.environ.get("SWRT_SLAB_MODE", default) if pull is None else ("pull" if pull else "push")
         self.pull = self.mode == "pull"
         self.barrier = os.environ.get("SWRT_TEAM_BARRIER", "device") if barrier is None else barrier
