@@ -476,6 +476,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     h->nkr = d.nx / 2 + 1;
     h->nvar = model_nvar(d.model);
     h->njobs_a = model_njobs_a(d.model) > 3 ? model_njobs_a(d.model) : 3;   // the snapshot pass needs 3 slots of G
+    if (d.slab_size > 1) h->njobs_a = model_njobs_a(d.model) + 3;           // team mode: the snapshot's psi jobs can ride behind the model's
     h->njobs_b = model_njobs_b(d.model);
     SpecLayout& L = h->L;
     L.nx = d.nx; L.ny = d.ny;
@@ -1166,14 +1167,15 @@ int swrt_slab_stage_a(swrt_flow* h) {
     CK(e);
     return slab_ship_a(h, model_njobs_a(h->d.model));
 }
-int swrt_slab_stage_b(swrt_flow* h) {
+static int slab_stage_b(swrt_flow* h, int nj_total) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
     CK(cudaSetDevice(h->d.device));
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, in_slab(h, model_njobs_a(h->d.model)), out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, in_slab(h, nj_total), out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st, nj_total)); }
     CK(e);
     return SWRT_OK;
 }
+int swrt_slab_stage_b(swrt_flow* h) { return slab_stage_b(h, h ? model_njobs_a(h->d.model) : 0); }
 static int ifmab3_update_launch(swrt_flow* h, double2* Ncur);
 int swrt_slab_stage_c(swrt_flow* h) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
@@ -1221,16 +1223,40 @@ int swrt_slab_psi_a(swrt_flow* h, int psi_kind) {
     CK(e);
     return slab_ship_a(h, 3);
 }
-int swrt_slab_snap_b(swrt_flow* h, int slot) {
+static PsiLoader slab_psi_loader(swrt_flow* h, int psi_kind) {
+    const bool pf = h->interp == SWRT_INTERP_BSPLINE2 || h->interp == SWRT_INTERP_BSPLINE3;
+    PsiLoader ld{h->sol, h->L.vs, psi_kind, h->d.f, h->L.aux0, pf ? h->d.Lx / h->d.nx : 0.0, pf ? h->d.Ly / h->d.ny : 0.0};
+    if (h->interp == SWRT_INTERP_BSPLINE3) { ld.pc0 = 2.0 / 3.0; ld.pc1 = 1.0 / 3.0; }
+    return ld;
+}
+static int slab_snap_b(swrt_flow* h, int slot, int nj_total, int j0) {
     if (!h || h->P <= 1 || slot < 0 || slot > 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad slot");
     if (h->interp == SWRT_INTERP_HERMITE_BICUBIC) return fail(SWRT_ERR_UNSUPPORTED, "slab snapshots are built for the 5-field node data");
     CK(cudaSetDevice(h->d.device));
     double* rows = h->snap[h->slot_map[slot]] + (long long)h->halo * h->d.nx * SNAP_STRIDE;   // this rank's band: the owned rows follow the lower halo
     CK(wait_readers(h));
     cudaError_t e;
-    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(in_slab(h, 3), rows, h->L, h->tw_x, h->sched, h->st)); }
+    { ProfScope ps(h, K_SNAP_B); SWRT_DISPATCH(h->L.nx, e, LN::snap_stage_b_slab(in_slab(h, nj_total), rows, h->L, h->tw_x, h->sched, h->st, nj_total, j0)); }
     CK(e);
     return SWRT_OK;
+}
+int swrt_slab_snap_b(swrt_flow* h, int slot) { return slab_snap_b(h, slot, 3, 0); }
+// team mode, fused: stage A of the flow step AND the snapshot's y-jobs of the same state in one y-pass / one transpose
+static int slab_stage_a_fused(swrt_flow* h, int psi_kind) {
+    CK(cudaSetDevice(h->d.device));
+    const SpecLayout& L = h->L;
+    const PsiLoader ld = slab_psi_loader(h, psi_kind);
+    if (L.kr_keep > 0) {
+        const long long nmodes = (long long)(L.ny - (L.lz1 - L.lz0)) * L.kr_keep;
+        ProfScope ps(h, K_PSI);
+        psi_kernel<<<(unsigned)((nmodes + 255) / 256), 256, 0, h->st>>>(ld, L, h->psih);
+        CK(cudaGetLastError());
+    }
+    const int nj = model_njobs_a(h->d.model) + 3;
+    cudaError_t e;
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(L.ny, e, LN::stage_a_fused(h->d.model, h->sol, h->psih, out_slab(h, 0, h->G, nj), L, h->tw_y, h->st)); }
+    CK(e);
+    return slab_ship_a(h, nj);
 }
 
 // ---- team mode: barrier, native step, band snapshot (no communication library on the data path)
@@ -2108,6 +2134,40 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     if (p->d.interp != f->interp) return fail(SWRT_ERR_STATE, "packets use interpolant %d but the flow's snapshots hold node data for %d (swrt_flow_set_interp)", p->d.interp, f->interp);
     { int rc = check_psi_kind(f, psi_kind); if (rc) return rc; }
     if (f->P > 1 && !f->p2p) return fail(SWRT_ERR_STATE, "slab-decomposed flow without mapped peers: drive the loop from the host (slab.py)");
+    // Team mode, fused loop.  The snapshot of state n and stage A of the flow step n -> n+1 transform the SAME state, so their
+    // y-jobs share one y-pass, one transpose and one barrier (two barriers per coupled step instead of four):
+    //   step 1 (plain) | step k >= 2: [psi; stage A + psi jobs] B [x-pass snapshot(k-1); x-pass products] B [halo; trace(k-2 -> k-1)] stage C
+    //   after the last step: the plain band snapshot of the final state and the last trace.
+    // Same kernels on the same data as the plain loop below (only the job layout of the exchange buffer differs).
+    static const int fused_mode = [] { const char* e = getenv("SWRT_TEAM_FUSED"); return e ? atoi(e) : 1; }();
+    if (f->P > 1 && fused_mode && nsteps > 0) {
+        const int nj = model_njobs_a(f->d.model) + 3, j0 = model_njobs_a(f->d.model);
+        auto trace = [&]() -> int {
+            int rc = swrt_packets_raytrace(p, 0.0, f->d.dt);
+            if (rc) return rc;
+            if (kcut > 0.0 && (rc = swrt_packets_kcutoff_reset(p, kcut, k0, nullptr))) return rc;
+            return swrt_flow_swap_snapshots(f, 0);
+        };
+        int rc;
+        for (int s = 0; s < nsteps; ++s) {
+            if (s == 0) {
+                if ((rc = swrt_slab_step(f, 1))) return rc;
+                continue;
+            }
+            if ((rc = slab_stage_a_fused(f, psi_kind))) return rc;
+            if ((rc = team_barrier(f))) return rc;
+            if ((rc = slab_snap_b(f, 1, nj, j0))) return rc;               // snapshot of the state the previous step produced
+            if ((rc = slab_stage_b(f, nj))) return rc;
+            if ((rc = team_barrier(f))) return rc;                         // product rows are with their owners, band rows are written
+            if ((rc = band_halo_pull(f, 1))) return rc;
+            if ((rc = trace())) return rc;                                 // (on the packets' own stream when they have one)
+            if ((rc = swrt_slab_stage_c(f))) return rc;
+        }
+        if ((rc = swrt_slab_band_snapshot(f, psi_kind, 1))) return rc;
+        if ((rc = trace())) return rc;
+        if (p->own) CK(cudaStreamWaitEvent(f->st, p->ev_done, 0));
+        return SWRT_OK;
+    }
     auto body = [&]() -> int {
         int rc = f->P > 1 ? swrt_slab_step(f, 1) : swrt_flow_step(f, 1);
         if (rc) return rc;

@@ -46,19 +46,38 @@ cudaError_t Launch<SWRT_N>::stage_b(int model, const double2* G_, double2* H, co
 }
 template <>
 cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const OutPeers& Gin, const OutPeers& H, const SpecLayout& L, const double2* tw,
-                                         unsigned* sched, cudaStream_t st) {
+                                         unsigned* sched, cudaStream_t st, int nj_total) {
     const double s1 = 1.0 / ((double)L.nx * (double)L.ny), sc = 0.5 * s1 * s1;
+    const int nj = nj_total > 0 ? nj_total : model_njobs_a(model);
     switch (model) {
-        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{nullptr, nullptr, sc, s1, H, Gin}, L, tw, sched, st);
-        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin}, L, tw, sched, st);
-        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin}, L, tw, sched, st);
+        case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
 }
 template <>
 cudaError_t Launch<SWRT_N>::snap_stage_b_slab(const OutPeers& Gin, double* out, const SpecLayout& L, const double2* tw, unsigned* sched,
-                                              cudaStream_t st) {
-    return xpass(SnapshotXOp<SWRT_N, true>{nullptr, out, 1.0 / ((double)L.nx * (double)L.ny), Gin}, L, tw, sched, st);
+                                              cudaStream_t st, int nj_total, int j0) {
+    return xpass(SnapshotXOp<SWRT_N, true>{nullptr, out, 1.0 / ((double)L.nx * (double)L.ny), Gin, nj_total, j0}, L, tw, sched, st);
+}
+template <>
+cudaError_t Launch<SWRT_N>::stage_a_fused(int model, const double2* sol, const double2* psih, const OutPeers& G_, const SpecLayout& L, const double2* tw,
+                                          cudaStream_t st) {
+    switch (model) {
+        case MODEL_RSW: {   // 5 + 3 simple jobs: the prefetching y-pass
+            SimpleJobs sj{};
+            const int fld[5] = {0, 1, 2, 0, 1}, mul[8] = {YMUL_ONE, YMUL_ONE, YMUL_ONE, YMUL_IL, YMUL_IL, YMUL_ONE, YMUL_NEG_IL, YMUL_L2};
+            const int last[8] = {0, 0, 1, 1, 1, 0, 0, 1};
+            for (int j = 0; j < 5; ++j) sj.src[j] = sol + fld[j] * L.vs;
+            for (int j = 5; j < 8; ++j) sj.src[j] = psih;
+            for (int j = 0; j < 8; ++j) { sj.mul[j] = mul[j]; sj.last[j] = last[j]; }
+            return ypass_inv_simple(sj, FusedLoaderA<RswLoaderA>{RswLoaderA{sol, L.vs}, psih, 5}, L, 8, G_, tw, st);
+        }
+        case MODEL_SWQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 1, L.aux0}, psih, 3}, L, 6, G_, tw, st);
+        case MODEL_TWOLAYERQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 2, L.aux0}, psih, 6}, L, 9, G_, tw, st);
+    }
+    return cudaErrorInvalidValue;
 }
 template <>
 cudaError_t Launch<SWRT_N>::stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st) {

@@ -49,10 +49,11 @@ struct RswXOp {
     double s1;         // 1/(nx ny)
     OutPeers peers;    // slab mode: destinations of the output column segments
     OutPeers gin;      // slab mode: sources of the input column segments
+    int nj = 5;        // jobs the y-pass put into G (8 when the snapshot's three psi jobs ride along, team mode)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        const auto Gu = row_in<SLAB>(L, G, gin, 5, 0, y), Gv = row_in<SLAB>(L, G, gin, 5, 1, y), Ge = row_in<SLAB>(L, G, gin, 5, 2, y),
-                   Guy = row_in<SLAB>(L, G, gin, 5, 3, y), Gvy = row_in<SLAB>(L, G, gin, 5, 4, y);
+        const auto Gu = row_in<SLAB>(L, G, gin, nj, 0, y), Gv = row_in<SLAB>(L, G, gin, nj, 1, y), Ge = row_in<SLAB>(L, G, gin, nj, 2, y),
+                   Guy = row_in<SLAB>(L, G, gin, nj, 3, y), Gvy = row_in<SLAB>(L, G, gin, nj, 4, y);
         const RowPlain none{};
         constexpr int NH = MODIFIED ? 5 : 4;
         // Thread g owns x = g + m N/16 (m = 0..15) of the physical row.  Inverse transforms are loaded through shared
@@ -245,9 +246,10 @@ struct QgXOp {  // per layer: a = psi_x q, b = psi_y q  ->  H[2 layer], H[2 laye
     double sc;
     OutPeers peers;
     OutPeers gin;      // slab mode: sources of the input column segments
+    int nj = 3 * NL;   // jobs the y-pass put into G (+ 3 when the snapshot's psi jobs ride along)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        auto Gp = [&](int j) { return row_in<SLAB>(L, G, gin, 3 * NL, j, y); };
+        auto Gp = [&](int j) { return row_in<SLAB>(L, G, gin, nj, j, y); };
         auto Hp = [&](int j) { return row_out<SLAB>(L, H, peers, 2 * NL, j, y); };
         double *q1 = cx.re(0), *q2 = cx.im(0);
         double2 v[16];
@@ -554,6 +556,20 @@ struct PsiLoader {
     }
 };
 
+// Team mode: the snapshot's three y-jobs (psih, -i l psih, l^2 psih from the materialised streamfunction of the SAME state) appended
+// to the model's own stage-A jobs, so that one y-pass, one transpose and one barrier serve both the flow step and the snapshot.
+template <class A>
+struct FusedLoaderA {
+    A a;
+    const double2* psih;
+    int na;
+    __device__ __forceinline__ double2 operator()(int job, int kr, int l, double kw, double lw, long long off) const {
+        if (job < na) return a(job, kr, l, kw, lw, off);
+        const double2 p = psih[off];
+        return job == na ? p : job == na + 1 ? make_double2(lw * p.y, -lw * p.x) : make_double2(lw * lw * p.x, lw * lw * p.y);
+    }
+};
+
 template <int N, bool SLAB = false, bool F32 = false>
 struct SnapshotXOp {
     static constexpr int NBUF = 2;
@@ -561,12 +577,13 @@ struct SnapshotXOp {
     double* out;       // [ny][nx][6] of the level being written ([ny][nx][8] floats in the fp32 packet mode)
     double s1;
     OutPeers gin;      // slab mode: sources of the input column segments
+    int nj = 3, j0 = 0;   // the three psi jobs are jobs j0 .. j0 + 2 of nj (they ride behind the model's jobs in team mode)
     // vx stays in the registers of the thread that stores it (x = g + m N/16); (u, v) and (ux, uy) wait in the two shared
     // buffers, so that the three 16-byte pieces of a record are stored back to back (whole sectors reach L2 together)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
         static_assert(EPT == 16, "one register per owned point");
-        const auto Gp = row_in<SLAB>(L, G, gin, 3, 0, y), Gu = row_in<SLAB>(L, G, gin, 3, 1, y), Guy = row_in<SLAB>(L, G, gin, 3, 2, y);
+        const auto Gp = row_in<SLAB>(L, G, gin, nj, j0, y), Gu = row_in<SLAB>(L, G, gin, nj, j0 + 1, y), Guy = row_in<SLAB>(L, G, gin, nj, j0 + 2, y);
         double2 vx[16];
         cx.template load_pair<MUL_MK2, MUL_ZERO>(1, Gp, RowPlain{});
         cx.ifft_regs_out(1, vx);  // vx
@@ -737,8 +754,12 @@ struct Launch {
     static cudaError_t stage_a(int model, const double2* sol, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_b(int model, const double2* G_, double2* H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
     // slab mode (P > 1): segmented rows; built for the models of the >= 4096^2 configurations (RSW, SWQG, two-layer QG)
-    static cudaError_t stage_b_slab(int model, const OutPeers& Gin, const OutPeers& H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
-    static cudaError_t snap_stage_b_slab(const OutPeers& Gin, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
+    static cudaError_t stage_b_slab(int model, const OutPeers& Gin, const OutPeers& H, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st,
+                                    int nj_total = 0);
+    static cudaError_t snap_stage_b_slab(const OutPeers& Gin, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st,
+                                         int nj_total = 3, int j0 = 0);
+    // team mode: stage A of the model + the three psi jobs of the snapshot of the same state (psih materialised by psi_kernel)
+    static cudaError_t stage_a_fused(int model, const double2* sol, const double2* psih, const OutPeers& G_, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t stage_c(int model, const double2* sol, const double2* H, double2* Nout, const SpecLayout& L, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_a(const FieldLoader& ld, const SpecLayout& L, const OutPeers& G_, const double2* tw, cudaStream_t st);
     static cudaError_t field_stage_b(const double2* G_, double* out, const SpecLayout& L, const double2* tw, unsigned* sched, cudaStream_t st);
