@@ -468,37 +468,36 @@ def run_swrt(args):
         h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
         Ke = max(3, min(K, 10))
         nchunks = max(4, min(args.e2e_chunks, nloc // 524288))   # >= 4 row blocks at every N so that uploads, kernels and downloads overlap
-        pipe = None if team else raytracing.PacketPipeline(prob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
+        # Host-resident packets every step are served by the chunked pipeline API (raytracing.PacketPipeline): row blocks of this
+        # rank's packets on their own streams against a flow that every rank steps itself -- PCIe, not the flow step, bounds
+        # this path, so at N > 1 it runs beside the team (which keeps its packets on the GPUs) on a replicated problem.
+        eprob = prob
+        if team:
+            eprob, _ = drivers.initialize_problem(P, dev=local)
+            raytracing.get_velocity_info(eprob, 0)
+            t = eprob.clock.t
+        pipe = raytracing.PacketPipeline(eprob, nloc, P.f, P.packet_Cg, nchunks=nchunks, nsub=P.nsub)
 
         def e2e_step(t, frame, first=False):
             # the packets of this step arrive from the host and go back to it, chunk by chunk on the chunks' own streams:
             # uploads, sort + ray-trace kernels and downloads of different chunks overlap (raytracing.PacketPipeline).
             # frame=True also samples velocity and gradients at the new positions and copies them back (savepacketdata!).
-            if team:
-                # team mode: this rank's caller-order block goes to the band owners (pull scan over NVLink), is traced there and
-                # collected back into the caller's rows -- set / coupled_step / get are collective calls
-                packets.set(h_xk, h_sign if first else None)
-                new_t = drivers.coupled_step(prob, packets, t)
-                packets.get(out=h_out)
-                if frame:
-                    raytracing.interpolate_gradients(raytracing.VelocityGradient(prob, 0), packets, output_G=h_G, output_U=h_U)
-                return new_t
-            flow.stepforward(prob, (), 1)
-            raytracing.get_velocity_info(prob, 1)
-            new_t = prob.clock.t
+            flow.stepforward(eprob, (), 1)
+            raytracing.get_velocity_info(eprob, 1)
+            new_t = eprob.clock.t
             pipe.step(h_xk, h_sign if first else None, (t, new_t), h_out, h_U if frame else None, h_G if frame else None,
-                      after_raytrace=lambda: raytracing.swap_snapshots(prob, alias=False))
+                      after_raytrace=lambda: raytracing.swap_snapshots(eprob, alias=False))
             return new_t
 
         def e2e_time(frame):
             nonlocal t
             t = e2e_step(t, frame, first=True)   # the frequency signs are a parameter of the ensemble: uploaded once
-            prob.sync(); barrier()
+            eprob.sync(); barrier()
             w0 = time.perf_counter()
-            prob.timer_start()
+            eprob.timer_start()
             for _ in range(Ke):
                 t = e2e_step(t, frame)
-            ms = prob.timer_stop()
+            ms = eprob.timer_stop()
             wall = (time.perf_counter() - w0) * 1e3
             barrier()
             return max_over_ranks(max(ms, wall))
@@ -511,8 +510,10 @@ def run_swrt(args):
                "with_output_frame": {"value": ntot * Ke / (ms_f * 1e-3), "ms_per_step": ms_f / Ke, "d2h_bytes_per_step": int(8 * 10 * nloc),
                                      "what": "the same plus velocity (N,2) and gradients (N,4) sampled at the new positions and copied "
                                              "back every step (savepacketdata! with write_gradients)"}}
-        if pipe is not None:
-            pipe.close()
+        pipe.close()
+        if team:
+            eprob.close()
+        e2e["flow"] = "replicated on every rank (chunked pipeline API)" if world > 1 else "single GPU"
         e2e["numa_local_cpus"] = len(near) if near else None
         os.sched_setaffinity(0, old_aff)
     clk = clocks.stop()

@@ -94,6 +94,7 @@ struct swrt_flow {
     double2* peer[3][kMaxPeers] = {};   // [2] = A_SEND (G) of every rank, mapped for the pull variant of the first transpose
     bool p2p = false, pull = false;
     int slab_mode = 0;   // first transpose: 0 = the y-pass stores into the peers (32-64 B pieces), 1 = the x-pass pulls, 2 = local stores + block copy kernel
+    int slab_b_copy = 0; // second transpose: 0 = the x-pass stores into the peers, 1 = local stores + block copy kernel
     unsigned* sched = nullptr;   // {next row, finished CTAs} of the dynamically scheduled x-pass (self re-arming)
     int ring = 0;
     double t = 0.0;
@@ -293,7 +294,7 @@ static OutPeers in_slab(const swrt_flow* h, int njobs) {
 }
 static OutPeers out_slab(const swrt_flow* h, int which /*0: A, 1: B*/, double2* send, int njobs) {
     OutPeers o{};
-    if (h->p2p && !(which == 0 && h->slab_mode != 0)) {
+    if (h->p2p && !(which == 0 && h->slab_mode != 0) && !(which == 1 && h->slab_b_copy)) {
         for (int d = 0; d < h->P; ++d) o.p[d] = h->peer[which][d];
         o.self = h->rank;
     } else {   // send buffer laid out [dest][job][row][chunk]: block d starts at d * njobs * yrows * chunk
@@ -1137,7 +1138,9 @@ int swrt_slab_ipc_open(swrt_flow* h, int which, int peer_rank, const void* handl
 }
 int swrt_slab_set_mode(swrt_flow* h, int mode) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
-    if (mode < 0 || mode > 2) return fail(SWRT_ERR_ARG, "mode must be 0 (push), 1 (pull) or 2 (block copy)");
+    if (mode >= 16) { h->slab_b_copy = 1; mode -= 16; }     // + 16: the second transpose ships through a block-copy kernel too
+    else h->slab_b_copy = 0;
+    if (mode < 0 || mode > 2) return fail(SWRT_ERR_ARG, "mode must be 0 (push), 1 (pull) or 2 (block copy) [+ 16: block copy for the second transpose]");
     if (mode == 1 && !h->pull) return fail(SWRT_ERR_STATE, "the pull variant needs every rank's first send buffer mapped");
     if (mode == 2 && !h->p2p) return fail(SWRT_ERR_STATE, "the block-copy variant needs the receive buffers mapped");
     h->slab_mode = mode;
@@ -1173,6 +1176,14 @@ static int slab_stage_b(swrt_flow* h, int nj_total) {
     cudaError_t e;
     { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(h->L.nx, e, LN::stage_b_slab(h->d.model, in_slab(h, nj_total), out_slab(h, 1, h->H2, model_njobs_b(h->d.model)), h->L, h->tw_x, h->sched, h->st, nj_total)); }
     CK(e);
+    if (h->slab_b_copy && h->p2p) {   // ship the product blocks in full lines
+        OutPeers dst{};
+        for (int d = 0; d < h->P; ++d) dst.p[d] = h->peer[1][d];
+        dst.self = h->rank;
+        const long long blk = (long long)model_njobs_b(h->d.model) * h->L.yrows * h->L.kr_pad;
+        { ProfScope ps(h, K_OTHER); slab_block_copy_kernel<<<148 * 8, 256, 0, h->st>>>(h->H2, dst, blk, h->P); }
+        CK(cudaGetLastError());
+    }
     return SWRT_OK;
 }
 int swrt_slab_stage_b(swrt_flow* h) { return slab_stage_b(h, h ? model_njobs_a(h->d.model) : 0); }

@@ -84,7 +84,7 @@ class SlabProblem(flow.Problem):
         check(L.swrt_slab_p2p(self._h, C.byref(en)))
         self.p2p = bool(en.value)
         assert self.p2p
-        check(L.swrt_slab_set_mode(self._h, {"push": 0, "pull": 1, "copy": 2}[self.mode]))
+        check(L.swrt_slab_set_mode(self._h, {"push": 0, "pull": 1, "copy": 2}[self.mode] + (16 if int(os.environ.get("SWRT_SLAB_B_COPY", "0")) else 0)))
         if self.barrier == "host":
             self._cb = _BARRIER_CB(lambda _arg: self.dist.barrier())          # keep the callback object alive
             check(L.swrt_slab_set_barrier(self._h, 1, C.cast(self._cb, C.c_void_p), None))
