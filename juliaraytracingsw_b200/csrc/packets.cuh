@@ -161,9 +161,9 @@ __global__ void __launch_bounds__(128, MINB) raytrace_rk4_kernel(double* __restr
 // the cell changes: ~4x fewer L1 wavefronts, which is what bounds the plain kernel (ncu: l1tex data-pipe
 // 76 %).  A time level whose lerp weight is exactly 0 (alpha = 0 at stage 1, alpha = 1 at stage 4) is
 // skipped; 0*x + 1*y == y, so the result equals the full formula bit for bit for finite fields.
-struct Stencil {   // [level][corner 00,10,01,11][3 vectors]; each level remembers the cell it holds (filled lazily: a level whose
-    double2 c[2][4][3];   // lerp weight is 0 at this stage -- old at t1, new at t0 -- is not fetched for the cell of that stage)
-    int ci[2], cj[2];
+struct Stencil {   // [level][corner 00,10,01,11][3 vectors]
+    double2 c[2][4][3];
+    int ci, cj;
 };
 
 // weighted sum of the four corners of one level: out[f] (+)= sum_c w[c] * field f at corner c   (1 DMUL + 3 DFMA per field)
@@ -188,26 +188,26 @@ __device__ __forceinline__ void ray_rhs_cached(const double (&s)[4], double sign
     double a, b;
     cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
+    if (i0 != st.ci || j0 != st.cj) {
+        st.ci = i0;
+        st.cj = j0;
+        stencil_rows(g, j0, j1);
+        const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
 #pragma unroll
-    for (int lev = 0; lev < 2; ++lev) {
-        if ((lev == 0 ? wo : wn) == 0.0 || (i0 == st.ci[lev] && j0 == st.cj[lev])) continue;    // not needed at this stage / already held
-        st.ci[lev] = i0;
-        st.cj[lev] = j0;
-        int r0 = j0, r1 = j1;
-        stencil_rows(g, r0, r1);
-        const long long pt[4] = {(long long)r0 * g.nx + i0, (long long)r0 * g.nx + i1, (long long)r1 * g.nx + i0, (long long)r1 * g.nx + i1};
-        const double* S = lev == 0 ? So : Sn;
+        for (int lev = 0; lev < 2; ++lev) {
+            const double* S = lev == 0 ? So : Sn;
 #pragma unroll
-        for (int cr = 0; cr < 4; ++cr) {
-            const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
-            st.c[lev][cr][0] = __ldg(q);
-            st.c[lev][cr][1] = __ldg(q + 1);
-            st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
+            for (int cr = 0; cr < 4; ++cr) {
+                const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
+                st.c[lev][cr][0] = __ldg(q);
+                st.c[lev][cr][1] = __ldg(q + 1);
+                st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
+            }
         }
     }
     // W = wo * bilinear(old) + wn * bilinear(new) evaluated as one weighted sum over the (up to) eight stencil values per
     // field: the same polynomial as the oracle's nested lerps, associated differently (agreement ~1e-16 relative)
+    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
     const double a1 = 1.0 - a, b1 = 1.0 - b;
     const double wb[4] = {a1 * b1, a * b1, a1 * b, a * b};
     double W[5];
@@ -241,8 +241,8 @@ __device__ __forceinline__ void raytrace_rk4_cached_body(double* __restrict__ xk
     const double sg = __ldcs(sign + i);
     const double h = (p.t1 - p.t0) / p.nsub, inv_span = 1.0 / (p.t1 - p.t0);
     Stencil st;
-    st.ci[0] = st.ci[1] = -1;
-    st.cj[0] = st.cj[1] = -1;
+    st.ci = -1;
+    st.cj = -1;
     for (int it = 0; it < p.nsub; ++it) {
         const double t = p.t0 + it * h;
         double k[4], acc[4], y[4];
@@ -319,44 +319,47 @@ __device__ __forceinline__ void ray_rhs_tile(const double (&s)[4], double sign, 
     double a, b;
     cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
     cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
-    // patch-relative node: masked differences, so a patch that wraps in y (band mode: halo rows beyond the domain edge) works;
-    // in x staged tiles are interior and the mask is a no-op
-    const unsigned ri = (unsigned)((i0 - tp.pi) & (g.nx - 1)), rj = (unsigned)((j0 - tp.pj) & (g.ny - 1));
-    const bool in_patch = tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1);
+    if (i0 != st.ci || j0 != st.cj) {
+        st.ci = i0;
+        st.cj = j0;
+        // patch-relative node: masked differences, so a patch that wraps in y (band mode: halo rows beyond the domain edge) works;
+        // in x staged tiles are interior and the mask is a no-op
+        const unsigned ri = (unsigned)((i0 - tp.pi) & (g.nx - 1)), rj = (unsigned)((j0 - tp.pj) & (g.ny - 1));
+        if (tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1)) {
+            const int o = rj * PATCH_ROW + ri * SNAP_STRIDE;
 #pragma unroll
-    for (int lev = 0; lev < 2; ++lev) {
-        if ((lev == 0 ? wo : wn) == 0.0 || (i0 == st.ci[lev] && j0 == st.cj[lev])) continue;    // not needed at this stage / already held
-        st.ci[lev] = i0;
-        st.cj[lev] = j0;
-        if (in_patch) {
-            const double2* q = reinterpret_cast<const double2*>(tp.lev[lev] + rj * PATCH_ROW + ri * SNAP_STRIDE);
+            for (int lev = 0; lev < 2; ++lev) {
+                const double2* q = reinterpret_cast<const double2*>(tp.lev[lev] + o);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                st.c[lev][0][k] = q[k];
-                st.c[lev][1][k] = q[3 + k];
-                st.c[lev][2][k] = q[PATCH_ROW / 2 + k];
-                st.c[lev][3][k] = q[PATCH_ROW / 2 + 3 + k];
+                for (int k = 0; k < 2; ++k) {
+                    st.c[lev][0][k] = q[k];
+                    st.c[lev][1][k] = q[3 + k];
+                    st.c[lev][2][k] = q[PATCH_ROW / 2 + k];
+                    st.c[lev][3][k] = q[PATCH_ROW / 2 + 3 + k];
+                }
+                // fifth field (vx): an 8-byte load, the record's pad is never read (two wavefronts instead of four)
+                st.c[lev][0][2].x = reinterpret_cast<const double*>(q + 2)[0];
+                st.c[lev][1][2].x = reinterpret_cast<const double*>(q + 5)[0];
+                st.c[lev][2][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 2)[0];
+                st.c[lev][3][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 5)[0];
             }
-            // fifth field (vx): an 8-byte load, the record's pad is never read (two wavefronts instead of four)
-            st.c[lev][0][2].x = reinterpret_cast<const double*>(q + 2)[0];
-            st.c[lev][1][2].x = reinterpret_cast<const double*>(q + 5)[0];
-            st.c[lev][2][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 2)[0];
-            st.c[lev][3][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 5)[0];
         } else {
-            int r0 = j0, r1 = j1;
-            stencil_rows(g, r0, r1);
-            const long long pt[4] = {(long long)r0 * g.nx + i0, (long long)r0 * g.nx + i1, (long long)r1 * g.nx + i0, (long long)r1 * g.nx + i1};
-            const double* S = lev == 0 ? So : Sn;
+            stencil_rows(g, j0, j1);
+            const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
 #pragma unroll
-            for (int cr = 0; cr < 4; ++cr) {
-                const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
-                st.c[lev][cr][0] = __ldg(q);
-                st.c[lev][cr][1] = __ldg(q + 1);
-                st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
+            for (int lev = 0; lev < 2; ++lev) {
+                const double* S = lev == 0 ? So : Sn;
+#pragma unroll
+                for (int cr = 0; cr < 4; ++cr) {
+                    const double2* q = reinterpret_cast<const double2*>(S + pt[cr] * SNAP_STRIDE);
+                    st.c[lev][cr][0] = __ldg(q);
+                    st.c[lev][cr][1] = __ldg(q + 1);
+                    st.c[lev][cr][2].x = __ldg(reinterpret_cast<const double*>(q + 2));
+                }
             }
         }
     }
+    const double wo = p.lerp == 0 ? 1.0 - alpha : alpha, wn = p.lerp == 0 ? alpha : 1.0 - alpha;
     const double a1 = 1.0 - a, b1 = 1.0 - b;
     const double wb[4] = {a1 * b1, a * b1, a1 * b, a * b};
     double W[5];
@@ -445,8 +448,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
         prefetch(i + TILE_THREADS, buf ^ 1);
         if (!waited) { mbar_wait(&bar, 0); waited = true; }      // the patch has landed (the first state copy overlapped it)
         Stencil st;
-        st.ci[0] = st.ci[1] = -1;
-        st.cj[0] = st.cj[1] = -1;
+        st.ci = -1;
+        st.cj = -1;
         for (int it = 0; it < p.nsub; ++it) {
             const double t = p.t0 + it * h;
             double k[4], acc[4], y[4];
