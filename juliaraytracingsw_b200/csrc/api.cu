@@ -1753,7 +1753,7 @@ int swrt_packets_use_own_stream(swrt_packets* p) {
 
 int swrt_packets_set_kernel(swrt_packets* p, int kernel) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
-    if (kernel < SWRT_RAYKERNEL_AUTO || kernel > SWRT_RAYKERNEL_TILE) return fail(SWRT_ERR_ARG, "unknown ray kernel %d", kernel);
+    if (kernel < SWRT_RAYKERNEL_AUTO || kernel > SWRT_RAYKERNEL_TILE3) return fail(SWRT_ERR_ARG, "unknown ray kernel %d", kernel);
     p->kernel_sel = kernel;
     for (auto& c : p->cycle) if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }   // captured launches name the old kernel
     return SWRT_OK;
@@ -2016,12 +2016,17 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int tile_min_pk = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINPK"); return e ? atoi(e) : 192; }();
     const PacketGrid pg = packet_grid(f, p);
     const long long ntiles = (long long)(pg.nx >> TILE_SHIFT) * tile_rows(f, pg);
-    const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode > 0 && n >= ntiles * (long long)tile_min_pk);
+    const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || p->kernel_sel == SWRT_RAYKERNEL_TILE3 ||
+                           (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode > 0 && n >= ntiles * (long long)tile_min_pk);
     const bool use_tile = want_tile && p->d.interp == SWRT_INTERP_BILINEAR && p->d.integrator == SWRT_INTEG_RK4 && p->tiles_valid &&
                           f->tmap_ok && ntiles > 0;
+    // one RK4 step per call: the three-level kernel (first level, mean, last level in shared memory); SWRT_RAYTRACE_TILE=2 keeps the two-level one
+    const bool use_tile3 = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_TILE3 || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode != 2));
     if (use_tile) {
         static bool attr_done = false;
         if (!attr_done) {
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE3_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -2032,6 +2037,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     f->ray_name = p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
                 : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3 || p->d.interp == SWRT_INTERP_NUFFT) ? "raytrace_generic_kernel"
                 : p->d.interp == SWRT_INTERP_HERMITE_BICUBIC ? "raytrace_rk4_cubic_kernel"
+                : use_tile3 ? "raytrace_rk4_tile3_kernel"
                 : use_tile ? (tile_minb >= 4 ? "raytrace_rk4_tile_kernel<4>" : "raytrace_rk4_tile_kernel<3>")
                 : (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) ? "raytrace_rk4_cached_kernel<4>" : "raytrace_rk4_kernel";
     { ProfScope ps(f, K_RAYTRACE, pst(p));
@@ -2052,6 +2058,11 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
       else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else if (use_tile3) {
+          const int first = p->d.time_lerp == 0 ? 0 : 1;          // the level whose weight is 1 at t0
+          raytrace_rk4_tile3_kernel<<<(unsigned)ntiles, TILE3_THREADS, (size_t)TILE3_SMEM_BYTES, pst(p)>>>(
+              p->xk, p->sign, n, first == 0 ? So : Sn, first == 0 ? Sn : So, f->tmap[f->slot_map[first]], f->tmap[f->slot_map[first ^ 1]], p->hist, pg, rp);
+      }
       else if (use_tile) {
           const size_t smem = (size_t)TILE_SMEM_BYTES;
           if (tile_minb >= 4) raytrace_rk4_tile_kernel<4><<<(unsigned)ntiles, TILE_THREADS, smem, pst(p)>>>(p->xk, p->sign, n, So, Sn, f->tmap[f->slot_map[0]], f->tmap[f->slot_map[1]], p->hist, pg, rp);

@@ -475,6 +475,203 @@ __global__ void __launch_bounds__(TILE_THREADS, MINB)
     // (thread 0 always owns packet `start` and waits for the copy above, so the CTA never retires with a copy in flight)
 }
 
+// ---------------------------------------------------------------- three-level tile variant (nsub == 1)
+// With one RK4 step per flow step the four stages sample the background at exactly three times: the first level (lerp weight
+// 1, 0), the midpoint (1/2, 1/2) twice, and the last level (0, 1).  The CTA therefore keeps THREE patches in shared memory --
+// the two levels staged by TMA and their mean, computed once per tile by the CTA -- and every stage reads the 2x2 stencil of
+// ONE patch: 20 doubles per thread instead of the 40 of the two-level stencil cache (128 registers, 16 warps per SM instead of
+// 12 at 160), no lerp weights in time (64 fewer fp64 instructions per packet-step of ~306), no "has the cell changed" refill
+// logic except between the two midpoint stages.  Bilinear interpolation is linear in the node values, so
+// bilinear(mean of levels) = mean of bilinear(levels): the same polynomial as the oracle's, associated differently.
+// Patches that wrap around the domain edge are filled by the CTA's threads (masked node indices) instead of TMA, so every tile
+// whose rows are resident is staged; a packet that has left the patch gathers from global memory with the same arithmetic.
+constexpr int TILE3_THREADS = 256;
+constexpr int TILE3_STAGE_BYTES = 2 * 5 * TILE3_THREADS * 8;
+constexpr int TILE3_SMEM_BYTES = 3 * PATCH_BYTES + TILE3_STAGE_BYTES;
+
+struct Stencil1 {   // [corner 00,10,01,11][3 vectors] of one time level
+    double2 c[4][3];
+};
+struct TilePatch3 {
+    const double* lev[3];   // shared-memory patches: first level, mean, last level
+    int pi, pj;
+    bool staged;
+};
+__device__ __forceinline__ double2 mean2(double2 a, double2 b) { return make_double2(0.5 * (a.x + b.x), 0.5 * (a.y + b.y)); }
+
+// LEV: 0 first level (S1), 1 mean of the two, 2 last level (S4)
+template <int LEV>
+__device__ __forceinline__ void fill_stencil1(Stencil1& st, int i0, int j0, const double* __restrict__ S1, const double* __restrict__ S4,
+                                              const PacketGrid& g, const TilePatch3& tp) {
+    const unsigned ri = (unsigned)((i0 - tp.pi) & (g.nx - 1)), rj = (unsigned)((j0 - tp.pj) & (g.ny - 1));
+    if (tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1)) {
+        const double2* q = reinterpret_cast<const double2*>(tp.lev[LEV] + rj * PATCH_ROW + ri * SNAP_STRIDE);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            st.c[0][k] = q[k];
+            st.c[1][k] = q[3 + k];
+            st.c[2][k] = q[PATCH_ROW / 2 + k];
+            st.c[3][k] = q[PATCH_ROW / 2 + 3 + k];
+        }
+        st.c[0][2].x = reinterpret_cast<const double*>(q + 2)[0];
+        st.c[1][2].x = reinterpret_cast<const double*>(q + 5)[0];
+        st.c[2][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 2)[0];
+        st.c[3][2].x = reinterpret_cast<const double*>(q + PATCH_ROW / 2 + 5)[0];
+    } else {
+        const int i1 = (i0 + 1) & (g.nx - 1);
+        int j1 = (j0 + 1) & (g.ny - 1);
+        stencil_rows(g, j0, j1);
+        const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+#pragma unroll
+        for (int cr = 0; cr < 4; ++cr) {
+            const double2* qa = reinterpret_cast<const double2*>((LEV == 2 ? S4 : S1) + pt[cr] * SNAP_STRIDE);
+            st.c[cr][0] = __ldg(qa);
+            st.c[cr][1] = __ldg(qa + 1);
+            st.c[cr][2].x = __ldg(reinterpret_cast<const double*>(qa + 2));
+            if (LEV == 1) {
+                const double2* qb = reinterpret_cast<const double2*>(S4 + pt[cr] * SNAP_STRIDE);
+                st.c[cr][0] = mean2(st.c[cr][0], __ldg(qb));
+                st.c[cr][1] = mean2(st.c[cr][1], __ldg(qb + 1));
+                st.c[cr][2].x = 0.5 * (st.c[cr][2].x + __ldg(reinterpret_cast<const double*>(qb + 2)));
+            }
+        }
+    }
+}
+__device__ __forceinline__ void ray_rhs1(const Stencil1& st, double a, double b, double k, double l, double sign, const RayParams& p,
+                                         double (&d)[4]) {
+    const double a1 = 1.0 - a, b1 = 1.0 - b;
+    const double w[4] = {a1 * b1, a * b1, a1 * b, a * b};
+    double W[5];
+    corners5<false>(st.c, w, W);
+    const double cg = p.Cg * p.Cg * sign * rsqrt(p.f * p.f + p.Cg * p.Cg * (k * k + l * l));   // Cg^2 / omega
+    d[0] = W[0] + cg * k;
+    d[1] = W[1] + cg * l;
+    d[2] = -(W[2] * k + W[4] * l);
+    d[3] = -(W[3] * k - W[2] * l);
+}
+
+// S1 / map1: the level whose lerp weight is 1 at t0 (the old one for the physical convention, the new one for the reference's
+// GPU convention, RayParams::lerp -- resolved by the caller); S4 / map4: the other one.
+__global__ void __launch_bounds__(TILE3_THREADS, 2)
+    raytrace_rk4_tile3_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n, const double* __restrict__ S1,
+                              const double* __restrict__ S4, const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map4,
+                              const unsigned* __restrict__ tile_end, PacketGrid g, RayParams p) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles_x = g.nx >> TILE_SHIFT, tiles_y = g.ny >> TILE_SHIFT;
+    const int tjl = blockIdx.x / tiles_x, ti = blockIdx.x - tjl * tiles_x;
+    const int tj = (g.tile_row0 + tjl) % tiles_y;
+    const int tile = tj * tiles_x + ti;
+    const long long key0 = (long long)tile << (2 * TILE_SHIFT);
+    const long long start = tile == 0 ? 0 : (long long)tile_end[key0 - 1], end = (long long)tile_end[key0 + (TILE * TILE - 1)];
+    if (start >= end) return;                                     // empty tile (uniform over the CTA)
+    double* const patch1 = reinterpret_cast<double*>(tile_smem);
+    double* const patchm = reinterpret_cast<double*>(tile_smem + PATCH_BYTES);
+    double* const patch4 = reinterpret_cast<double*>(tile_smem + 2 * PATCH_BYTES);
+    TilePatch3 tp;
+    tp.lev[0] = patch1;
+    tp.lev[1] = patchm;
+    tp.lev[2] = patch4;
+    tp.pi = ti * TILE - TILE_MARGIN;
+    tp.pj = tj * TILE - TILE_MARGIN;
+    int prow = tp.pj;                                            // row of the snapshot array where the patch starts
+    bool rows_ok = true;                                         // all PATCH rows resident (band mode: inside band + halo)
+    if (g.band) {
+        prow = (tp.pj - g.jb) & (g.ny - 1);
+        if (prow >= g.ny / 2) prow -= g.ny;                      // signed distance from the first resident row
+        rows_ok = prow >= 0 && prow + PATCH <= g.jrows;
+    }
+    const bool by_tma = rows_ok && tp.pi >= 0 && tp.pi + PATCH <= g.nx && prow >= 0 && prow + PATCH <= (g.band ? g.jrows : g.ny);
+    tp.staged = rows_ok;
+    if (by_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, 2u * PATCH * PATCH_ROW * 8);
+            tma_load_2d(patch1, &map1, tp.pi * SNAP_STRIDE, prow, &bar);
+            tma_load_2d(patch4, &map4, tp.pi * SNAP_STRIDE, prow, &bar);
+        }
+    }
+    const double h = p.t1 - p.t0;
+    double* stage = reinterpret_cast<double*>(tile_smem + 3 * PATCH_BYTES);     // [2][5][TILE3_THREADS]
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    auto prefetch = [&](long long i, int buf) {
+        if (i < end) {
+            double* d = stage + buf * 5 * TILE3_THREADS + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async8_stream(d + c * TILE3_THREADS, xk + c * g.ld + i, pol);
+            cp_async8_stream(d + 4 * TILE3_THREADS, sign + i, pol);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    prefetch(start + threadIdx.x, 0);
+    if (by_tma) {
+        mbar_wait(&bar, 0);                                      // every thread observes the completed phase before reading the patches
+        double2* m = reinterpret_cast<double2*>(patchm);
+        const double2 *a = reinterpret_cast<const double2*>(patch1), *b = reinterpret_cast<const double2*>(patch4);
+        for (int c = threadIdx.x; c < PATCH * PATCH_ROW / 2; c += TILE3_THREADS) m[c] = mean2(a[c], b[c]);
+        __syncthreads();
+    } else if (rows_ok) {
+        // the patch wraps around the domain edge (or starts left of column 0): filled node by node with masked indices
+        for (int e = threadIdx.x; e < PATCH * PATCH * 3; e += TILE3_THREADS) {
+            const int node = e / 3, q = e - node * 3, r = node / PATCH, c = node - r * PATCH;
+            const int col = (tp.pi + c) & (g.nx - 1), row = g.band ? prow + r : ((tp.pj + r) & (g.ny - 1));
+            const long long src = ((long long)row * g.nx + col) * SNAP_STRIDE + 2 * q;
+            const double2 va = __ldg(reinterpret_cast<const double2*>(S1 + src)), vb = __ldg(reinterpret_cast<const double2*>(S4 + src));
+            const int dst = r * PATCH_ROW + c * SNAP_STRIDE + 2 * q;
+            *reinterpret_cast<double2*>(patch1 + dst) = va;
+            *reinterpret_cast<double2*>(patch4 + dst) = vb;
+            *reinterpret_cast<double2*>(patchm + dst) = mean2(va, vb);
+        }
+        __syncthreads();
+    }
+    int buf = 0;
+    for (long long i = start + threadIdx.x; i < end; i += TILE3_THREADS, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        const double* sv = stage + buf * 5 * TILE3_THREADS + threadIdx.x;
+        double s[4] = {sv[0], sv[TILE3_THREADS], sv[2 * TILE3_THREADS], sv[3 * TILE3_THREADS]};
+        const double sg = sv[4 * TILE3_THREADS];
+        prefetch(i + TILE3_THREADS, buf ^ 1);
+        Stencil1 st;
+        int i0, i1, j0, j1, ci, cj;
+        double a, b, k[4], acc[4], y[4];
+        // stage 1: first level at t0
+        cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+        cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+        fill_stencil1<0>(st, i0, j0, S1, S4, g, tp);
+        ray_rhs1(st, a, b, s[2], s[3], sg, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        // stages 2 and 3: mean of the levels at t0 + h/2
+        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+        fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
+        ci = i0;
+        cj = j0;
+        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+        if (i0 != ci || j0 != cj) fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
+        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+        // stage 4: last level at t1
+        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+        fill_stencil1<2>(st, i0, j0, S1, S4, g, tp);
+        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+        __stcs(xk + i, s[0]);
+        __stcs(xk + g.ld + i, s[1]);
+        __stcs(xk + 2 * g.ld + i, s[2]);
+        __stcs(xk + 3 * g.ld + i, s[3]);
+    }
+}
+
 // ---------------------------------------------------------------- Hermite-bicubic mode
 // u, v interpolated from (f, f_x, f_y, f_xy) node data (utils/CUDAInterpolations.jl:39-53,71-108); the gradient that enters
 // dk/dt is the analytic gradient of that interpolant.  Node record (snapshot_layout.cuh): u, v, ux, uy, vx, uxy, vxy, pad.

@@ -184,6 +184,12 @@ class Problem:
                 out[name.value.decode()] = dict(ms_total=ms.value, launches=n.value, ms_avg=ms.value / n.value)
         return out
 
+    def ray_kernel_name(self):
+        """Name of the ray kernel the last `raytrace` call on this flow's packets launched (the profile label)."""
+        name = C.c_char_p()
+        check(lib().swrt_flow_profile_get(self._h, 6, None, None, C.byref(name)))
+        return name.value.decode()
+
     def timer_start(self):
         check(lib().swrt_flow_timer_start(self._h))
 

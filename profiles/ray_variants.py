@@ -1,6 +1,6 @@
 """A/B of the ray kernels on the bench workload (RSW nx^2, sq^2 packets at uniformly random positions): per kernel selected
 with swrt_packets_set_kernel, the average launch time from the library's CUDA-event profile over 32 coupled steps (two sort
-periods) and a checksum (the kernels are bit-identical).  `python profiles/ray_variants.py [cached tile ...]`."""
+periods) and a checksum (cached and tile are bit-identical, tile3 agrees to rounding).  `python profiles/ray_variants.py [cached tile ...]`."""
 import os
 import sys
 
@@ -12,12 +12,12 @@ from juliaraytracingsw_b200 import drivers, raytracing  # noqa: E402
 nx = int(os.environ.get("NX", 2048))
 sq = int(os.environ.get("SQ", 4096))
 lattice = int(os.environ.get("LATTICE", 0))
-names = sys.argv[1:] or ["cached", "tile"]
+names = sys.argv[1:] or ["cached", "tile", "tile3"]
 P = drivers.Parameters(nx=nx, sqrtNpackets=sq)
 prob, _ = drivers.initialize_problem(P)
 for name in names:
     pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
-    pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "auto": raytracing.RAYKERNEL_AUTO}[name])
+    pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "tile3": raytracing.RAYKERNEL_TILE3, "auto": raytracing.RAYKERNEL_AUTO}[name])
     if not lattice:
         xk = pk.get()
         xk[:, 0:2] = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(P.Npackets, 2))
