@@ -262,9 +262,11 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1);
 /* Which ray kernel integrates the fp64 bilinear RK4 mode (raytracing/GPURaytracing.jl:32-65 dxkdt + :137 solve): SWRT_RAYKERNEL_AUTO
  * (default; the environment knobs of DESIGN.md apply), SWRT_RAYKERNEL_CACHED (per-thread stencil cache, gathers through L1/L2) or
  * SWRT_RAYKERNEL_TILE (one CTA per sort tile, node records of the two levels staged in shared memory by TMA; same arithmetic as
- * CACHED, bit-identical results) or SWRT_RAYKERNEL_TILE3 (nsub == 1 only, what AUTO picks then: three staged patches -- first level,
- * mean of the levels, last level -- one per RK4 stage time; agrees with the other two to rounding, ~1e-16 relative per step). */
-enum { SWRT_RAYKERNEL_AUTO = -1, SWRT_RAYKERNEL_CACHED = 0, SWRT_RAYKERNEL_TILE = 1, SWRT_RAYKERNEL_TILE3 = 2 };
+ * CACHED, bit-identical results), SWRT_RAYKERNEL_TILE3 (nsub == 1 only, what AUTO picks then: three staged patches -- first level,
+ * mean of the levels, last level -- one per RK4 stage time; agrees with the other two to rounding, ~1e-16 relative per step) or
+ * SWRT_RAYKERNEL_PIPE (nsub == 1 only: the TILE3 arithmetic, bit-identical to it, in one persistent CTA per SM whose producer warp
+ * stages the next tile while the consumer warps integrate the current one; measured slower than TILE3, kept for comparison). */
+enum { SWRT_RAYKERNEL_AUTO = -1, SWRT_RAYKERNEL_CACHED = 0, SWRT_RAYKERNEL_TILE = 1, SWRT_RAYKERNEL_TILE3 = 2, SWRT_RAYKERNEL_PIPE = 3 };
 int swrt_packets_set_kernel(swrt_packets* p, int kernel);
 /* band-sharded packets (team mode): export / map the 64-byte IPC handle of the handle's arena; packets resident on this rank */
 int swrt_packets_ipc_handle(swrt_packets* p, void* handle64);

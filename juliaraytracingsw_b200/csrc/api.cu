@@ -169,6 +169,7 @@ struct swrt_packets {
     // state (sorted order) + alternates for the out-of-place sort; idx = original row of each packet
     double *xk = nullptr, *sign = nullptr, *xk2 = nullptr, *sign2 = nullptr, *U = nullptr, *Gd = nullptr;
     unsigned *idx = nullptr, *idx2 = nullptr, *keys = nullptr, *hist = nullptr, *sums = nullptr;
+    unsigned* rsched = nullptr;             // {next tile, finished CTAs} of the persistent ray kernel (re-armed by its last CTA)
     unsigned long long* count = nullptr;
     long long nbins = 0;
     int kernel_sel = SWRT_RAYKERNEL_AUTO;   // swrt_packets_set_kernel
@@ -1580,7 +1581,7 @@ static int packets_free(swrt_packets* p) {
         cudaFree(p->xk); cudaFree(p->sign); cudaFree(p->xk2); cudaFree(p->sign2); cudaFree(p->U); cudaFree(p->Gd);
         cudaFree(p->idx); cudaFree(p->idx2);
     }
-    cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count);
+    cudaFree(p->keys); cudaFree(p->hist); cudaFree(p->sums); cudaFree(p->count); cudaFree(p->rsched);
     return SWRT_OK;
 }
 int swrt_packets_destroy(swrt_packets* p) {
@@ -1673,11 +1674,13 @@ int swrt_packets_create(const swrt_packets_desc* desc, swrt_flow* flow, swrt_pac
     if (e == cudaSuccess) e = cudaMalloc(&p->hist, sizeof(unsigned) * (size_t)p->nbins);
     if (e == cudaSuccess) e = cudaMalloc(&p->sums, sizeof(unsigned) * nsums);
     if (e == cudaSuccess) e = cudaMalloc(&p->count, sizeof(unsigned long long) * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&p->rsched, sizeof(unsigned) * 2);
     if (e != cudaSuccess) {
         swrt_packets_destroy(p);
         return fail(SWRT_ERR_CUDA, "cudaMalloc(packets): %s", cudaGetErrorString(e));
     }
     CK(cudaMemsetAsync(p->count, 0, sizeof(unsigned long long) * 2, pst(p)));
+    CK(cudaMemsetAsync(p->rsched, 0, sizeof(unsigned) * 2, pst(p)));
     if (!band) {
         CK(cudaMemsetAsync(p->xk, 0, sizeof(double) * 4 * n, pst(p)));
         CK(cudaMemsetAsync(p->sign, 0, sizeof(double) * n, pst(p)));
@@ -1753,7 +1756,7 @@ int swrt_packets_use_own_stream(swrt_packets* p) {
 
 int swrt_packets_set_kernel(swrt_packets* p, int kernel) {
     if (!p) return fail(SWRT_ERR_ARG, "null pointer");
-    if (kernel < SWRT_RAYKERNEL_AUTO || kernel > SWRT_RAYKERNEL_TILE3) return fail(SWRT_ERR_ARG, "unknown ray kernel %d", kernel);
+    if (kernel < SWRT_RAYKERNEL_AUTO || kernel > SWRT_RAYKERNEL_PIPE) return fail(SWRT_ERR_ARG, "unknown ray kernel %d", kernel);
     p->kernel_sel = kernel;
     for (auto& c : p->cycle) if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }   // captured launches name the old kernel
     return SWRT_OK;
@@ -2016,15 +2019,19 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     static const int tile_min_pk = [] { const char* e = getenv("SWRT_RAYTRACE_TILE_MINPK"); return e ? atoi(e) : 192; }();
     const PacketGrid pg = packet_grid(f, p);
     const long long ntiles = (long long)(pg.nx >> TILE_SHIFT) * tile_rows(f, pg);
-    const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || p->kernel_sel == SWRT_RAYKERNEL_TILE3 ||
+    const bool want_tile = p->kernel_sel == SWRT_RAYKERNEL_TILE || p->kernel_sel == SWRT_RAYKERNEL_TILE3 || p->kernel_sel == SWRT_RAYKERNEL_PIPE ||
                            (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode > 0 && n >= ntiles * (long long)tile_min_pk);
     const bool use_tile = want_tile && p->d.interp == SWRT_INTERP_BILINEAR && p->d.integrator == SWRT_INTEG_RK4 && p->tiles_valid &&
                           f->tmap_ok && ntiles > 0;
-    // one RK4 step per call: the three-level kernel (first level, mean, last level in shared memory); SWRT_RAYTRACE_TILE=2 keeps the two-level one
-    const bool use_tile3 = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_TILE3 || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode != 2));
+    // one RK4 step per call: the three-level kernel (first level, mean, last level in shared memory), one CTA per tile (default);
+    // SWRT_RAYTRACE_TILE=2 keeps the two-level kernel, =4 selects the persistent warp-specialised variant (measured slower:
+    // 0.62-0.68 ms against 0.52 ms, profiles/r02_o_ray_kernel_ab.log)
+    const bool use_pipe = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_PIPE || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode == 4));
+    const bool use_tile3 = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_TILE3 || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && (tile_mode == 1 || tile_mode == 3)));
     if (use_tile) {
         static bool attr_done = false;
         if (!attr_done) {
+            CK(cudaFuncSetAttribute(raytrace_rk4_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE3_SMEM_BYTES));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CK(cudaFuncSetAttribute(raytrace_rk4_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
@@ -2037,6 +2044,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     f->ray_name = p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
                 : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3 || p->d.interp == SWRT_INTERP_NUFFT) ? "raytrace_generic_kernel"
                 : p->d.interp == SWRT_INTERP_HERMITE_BICUBIC ? "raytrace_rk4_cubic_kernel"
+                : use_pipe ? "raytrace_rk4_pipe_kernel"
                 : use_tile3 ? "raytrace_rk4_tile3_kernel"
                 : use_tile ? (tile_minb >= 4 ? "raytrace_rk4_tile_kernel<4>" : "raytrace_rk4_tile_kernel<3>")
                 : (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) ? "raytrace_rk4_cached_kernel<4>" : "raytrace_rk4_kernel";
@@ -2058,6 +2066,14 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
       else if (p->d.interp == SWRT_INTERP_BSPLINE3) SWRT_GEN(4, 0);
 #undef SWRT_GEN
       else if (p->d.interp == SWRT_INTERP_HERMITE_BICUBIC) raytrace_rk4_cubic_kernel<<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp);
+      else if (use_pipe) {
+          const int first = p->d.time_lerp == 0 ? 0 : 1;          // the level whose weight is 1 at t0
+          static const int sms = [] { int d = 0, v = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }();
+          const unsigned ctas = (unsigned)std::min<long long>(ntiles, sms);
+          raytrace_rk4_pipe_kernel<<<ctas, PIPE_THREADS, (size_t)PIPE_SMEM_BYTES, pst(p)>>>(
+              p->xk, p->sign, n, first == 0 ? So : Sn, first == 0 ? Sn : So, f->tmap[f->slot_map[first]], f->tmap[f->slot_map[first ^ 1]], p->hist,
+              (int)ntiles, p->rsched, pg, rp);
+      }
       else if (use_tile3) {
           const int first = p->d.time_lerp == 0 ? 0 : 1;          // the level whose weight is 1 at t0
           raytrace_rk4_tile3_kernel<<<(unsigned)ntiles, TILE3_THREADS, (size_t)TILE3_SMEM_BYTES, pst(p)>>>(

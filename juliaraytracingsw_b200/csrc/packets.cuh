@@ -550,6 +550,43 @@ __device__ __forceinline__ void ray_rhs1(const Stencil1& st, double a, double b,
     d[3] = -(W[3] * k - W[2] * l);
 }
 
+// one classical RK4 step of one packet over (t0, t0 + h) against the three patches (first level, mean, last level)
+__device__ __forceinline__ void rk4_three_level(double (&s)[4], double sg, double h, const double* __restrict__ S1, const double* __restrict__ S4,
+                                                const PacketGrid& g, const RayParams& p, const TilePatch3& tp) {
+    Stencil1 st;
+    int i0, i1, j0, j1, ci, cj;
+    double a, b, k[4], acc[4], y[4];
+    // stage 1: first level at t0
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1<0>(st, i0, j0, S1, S4, g, tp);
+    ray_rhs1(st, a, b, s[2], s[3], sg, p, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+    // stages 2 and 3: mean of the levels at t0 + h/2
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
+    ci = i0;
+    cj = j0;
+    ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    if (i0 != ci || j0 != cj) fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
+    ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+    // stage 4: last level at t1
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1<2>(st, i0, j0, S1, S4, g, tp);
+    ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+}
+
 // S1 / map1: the level whose lerp weight is 1 at t0 (the old one for the physical convention, the new one for the reference's
 // GPU convention, RayParams::lerp -- resolved by the caller); S4 / map4: the other one.
 __global__ void __launch_bounds__(TILE3_THREADS, 2)
@@ -563,8 +600,8 @@ __global__ void __launch_bounds__(TILE3_THREADS, 2)
     const int tj = (g.tile_row0 + tjl) % tiles_y;
     const int tile = tj * tiles_x + ti;
     const long long key0 = (long long)tile << (2 * TILE_SHIFT);
-    const long long start = tile == 0 ? 0 : (long long)tile_end[key0 - 1], end = (long long)tile_end[key0 + (TILE * TILE - 1)];
-    if (start >= end) return;                                     // empty tile (uniform over the CTA)
+    // (the tile record is read first but not used until the bulk copies are on their way: the two latencies overlap)
+    const long long start = tile == 0 ? 0 : (long long)__ldg(&tile_end[key0 - 1]), end = (long long)__ldg(&tile_end[key0 + (TILE * TILE - 1)]);
     double* const patch1 = reinterpret_cast<double*>(tile_smem);
     double* const patchm = reinterpret_cast<double*>(tile_smem + PATCH_BYTES);
     double* const patch4 = reinterpret_cast<double*>(tile_smem + 2 * PATCH_BYTES);
@@ -592,6 +629,10 @@ __global__ void __launch_bounds__(TILE3_THREADS, 2)
             tma_load_2d(patch4, &map4, tp.pi * SNAP_STRIDE, prow, &bar);
         }
     }
+    if (start >= end) {                                           // empty tile (uniform over the CTA): no copy may be left in flight
+        if (by_tma) mbar_wait(&bar, 0);
+        return;
+    }
     const double h = p.t1 - p.t0;
     double* stage = reinterpret_cast<double*>(tile_smem + 3 * PATCH_BYTES);     // [2][5][TILE3_THREADS]
     unsigned long long pol;
@@ -610,7 +651,18 @@ __global__ void __launch_bounds__(TILE3_THREADS, 2)
         mbar_wait(&bar, 0);                                      // every thread observes the completed phase before reading the patches
         double2* m = reinterpret_cast<double2*>(patchm);
         const double2 *a = reinterpret_cast<const double2*>(patch1), *b = reinterpret_cast<const double2*>(patch4);
-        for (int c = threadIdx.x; c < PATCH * PATCH_ROW / 2; c += TILE3_THREADS) m[c] = mean2(a[c], b[c]);
+        constexpr int NCH = PATCH * PATCH_ROW / 2, NIT = (NCH + TILE3_THREADS - 1) / TILE3_THREADS;
+        double2 va[NIT], vb[NIT];
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+            const int c = threadIdx.x + u * TILE3_THREADS;
+            if (c < NCH) { va[u] = a[c]; vb[u] = b[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+            const int c = threadIdx.x + u * TILE3_THREADS;
+            if (c < NCH) m[c] = mean2(va[u], vb[u]);
+        }
         __syncthreads();
     } else if (rows_ok) {
         // the patch wraps around the domain edge (or starts left of column 0): filled node by node with masked indices
@@ -633,42 +685,270 @@ __global__ void __launch_bounds__(TILE3_THREADS, 2)
         double s[4] = {sv[0], sv[TILE3_THREADS], sv[2 * TILE3_THREADS], sv[3 * TILE3_THREADS]};
         const double sg = sv[4 * TILE3_THREADS];
         prefetch(i + TILE3_THREADS, buf ^ 1);
-        Stencil1 st;
-        int i0, i1, j0, j1, ci, cj;
-        double a, b, k[4], acc[4], y[4];
-        // stage 1: first level at t0
-        cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
-        cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-        fill_stencil1<0>(st, i0, j0, S1, S4, g, tp);
-        ray_rhs1(st, a, b, s[2], s[3], sg, p, k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
-        // stages 2 and 3: mean of the levels at t0 + h/2
-        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
-        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-        fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
-        ci = i0;
-        cj = j0;
-        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
-        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
-        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-        if (i0 != ci || j0 != cj) fill_stencil1<1>(st, i0, j0, S1, S4, g, tp);
-        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
-        // stage 4: last level at t1
-        cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
-        cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
-        fill_stencil1<2>(st, i0, j0, S1, S4, g, tp);
-        ray_rhs1(st, a, b, y[2], y[3], sg, p, k);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+        rk4_three_level(s, sg, h, S1, S4, g, p, tp);
         __stcs(xk + i, s[0]);
         __stcs(xk + g.ld + i, s[1]);
         __stcs(xk + 2 * g.ld + i, s[2]);
         __stcs(xk + 3 * g.ld + i, s[3]);
+    }
+}
+
+// ---------------------------------------------------------------- persistent, warp-specialised three-level variant
+// One CTA per SM walks through the tiles (dynamic hand-out, ascending: the ~148 tiles in flight are neighbours, their halos hit
+// L2).  Warp 15 is the PRODUCER: for the next tile it issues the two bulk-tensor copies into the other buffer set, waits for them,
+// writes the mean patch and publishes (tile, packet range) -- all while the 15 CONSUMER warps integrate the packets of the current
+// tile.  Three mbarriers per buffer set: `full` (TMA bytes landed), `ready` (producer: mean patch + tile record written),
+// `empty` (one arrival per consumer warp: nobody reads this set any more).  No CTA-wide barrier anywhere: a consumer warp that
+// has finished its share of a tile moves on to the next, and the packets of a tile are dealt round-robin CONTINUING where the
+// previous tile stopped (`rot`), so every consumer thread gets the same number of packets (+-1) over the launch.  Against the
+// one-CTA-per-tile kernel this removes the start-up chain of every tile (tile record -> TMA -> mean patch: ~2 us of a ~9 us CTA
+// life at half occupancy, ncu: 25 % of the stall samples) and the last, nearly empty round of every tile.
+// MEASURED (profiles/r02_n, r02_o): 0.62-0.68 ms against 0.52 ms for the one-CTA-per-tile kernel at 16.8 M packets.  Shared memory
+// only holds TWO buffer sets of three patches, a tile is ~2.1 packets per consumer thread (~4 us) and the producer's chain
+// empty -> TMA -> mean patch -> ready takes ~2 us, starting only when the slowest warp has left the previous tile: the consumer
+// warps wait for each other at every tile.  Kept selectable (SWRT_RAYKERNEL_PIPE), not the default.
+constexpr int PIPE_THREADS = 512, PIPE_CONSUMERS = PIPE_THREADS - 32, PIPE_CWARPS = PIPE_CONSUMERS / 32;
+constexpr int PIPE_STAGE_BYTES = 2 * 5 * PIPE_CONSUMERS * 8;
+constexpr int PIPE_SMEM_BYTES = 6 * PATCH_BYTES + PIPE_STAGE_BYTES;
+struct PipeTile {   // published by the producer with `ready`
+    int tile;       // -1: no more work
+    int staged;
+    int pi, pj;     // grid node of patch node (0, 0)
+    long long start, end;
+};
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// sched = {next tile, finished CTAs}; the last CTA re-arms it for the next launch
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+    raytrace_rk4_pipe_kernel(double* __restrict__ xk, const double* __restrict__ sign, long long n, const double* __restrict__ S1,
+                             const double* __restrict__ S4, const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map4,
+                             const unsigned* __restrict__ tile_end, int ntiles, unsigned* __restrict__ sched, PacketGrid g, RayParams p) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long full[2], ready[2], empty[2];
+    __shared__ PipeTile rec[2];
+    const int tiles_x = g.nx >> TILE_SHIFT, tiles_y = g.ny >> TILE_SHIFT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&ready[b], 1);
+            mbar_init(&empty[b], PIPE_CWARPS);
+        }
+    }
+    __syncthreads();
+    auto patch = [&](int b, int lev) { return reinterpret_cast<double*>(tile_smem + (size_t)(3 * b + lev) * PATCH_BYTES); };
+    // patch origin of a tile and whether / how it can be staged
+    auto tile_origin = [&](int tile, int& pi, int& pj, int& prow, bool& rows_ok, bool& by_tma) {
+        const int tjl = tile / tiles_x, ti = tile - tjl * tiles_x;
+        const int tj = (g.tile_row0 + tjl) % tiles_y;
+        pi = ti * TILE - TILE_MARGIN;
+        pj = tj * TILE - TILE_MARGIN;
+        prow = pj;
+        rows_ok = true;
+        if (g.band) {
+            prow = (pj - g.jb) & (g.ny - 1);
+            if (prow >= g.ny / 2) prow -= g.ny;
+            rows_ok = prow >= 0 && prow + PATCH <= g.jrows;
+        }
+        by_tma = rows_ok && pi >= 0 && pi + PATCH <= g.nx && prow >= 0 && prow + PATCH <= (g.band ? g.jrows : g.ny);
+        return tj * tiles_x + ti;                                   // global tile number (band mode: the grid covers a window of tile rows)
+    };
+    if (warp == PIPE_CWARPS) {
+        // ------------------------------------------------------------ producer warp
+        // Tile records are fetched eight at a time (one atomic per batch, lanes 0-7 load the packet ranges), one batch ahead of
+        // their use, so neither the atomic nor the loads sit on the per-tile chain  empty -> TMA -> mean patch -> ready.
+        int q_slot, n_slot;
+        long long q_start, q_end, n_start, n_end;
+        auto fetch = [&](int& slot, long long& st, long long& en) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&sched[0], 8u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            slot = lane < 8 && base + lane < (unsigned)ntiles ? (int)(base + lane) : ntiles;
+            st = en = 0;
+            if (slot < ntiles) {
+                int pi, pj, prow; bool r_ok, tma;
+                const int tile = tile_origin(slot, pi, pj, prow, r_ok, tma);
+                const long long key0 = (long long)tile << (2 * TILE_SHIFT);
+                st = tile == 0 ? 0 : (long long)__ldg(&tile_end[key0 - 1]);
+                en = (long long)__ldg(&tile_end[key0 + (TILE * TILE - 1)]);
+            }
+        };
+        fetch(q_slot, q_start, q_end);
+        fetch(n_slot, n_start, n_end);
+        int qpos = 0;
+        for (int it = 0;; ++it) {
+            const int b = it & 1, use = it >> 1;
+            int tslot = 0;
+            long long start = 0, end = 0;
+            for (;;) {                                              // next non-empty tile
+                if (qpos == 8) {
+                    q_slot = n_slot; q_start = n_start; q_end = n_end;
+                    fetch(n_slot, n_start, n_end);
+                    qpos = 0;
+                }
+                tslot = __shfl_sync(0xffffffffu, q_slot, qpos);
+                start = __shfl_sync(0xffffffffu, q_start, qpos);
+                end = __shfl_sync(0xffffffffu, q_end, qpos);
+                ++qpos;
+                if (tslot >= ntiles || start < end) break;
+            }
+            if (use >= 1) mbar_wait(&empty[b], (unsigned)((use - 1) & 1));   // every consumer warp has left this buffer set
+            if (tslot >= ntiles) {
+                if (lane == 0) {
+                    rec[b].tile = -1;
+                    mbar_arrive(&ready[b]);
+                }
+                break;
+            }
+            int pi, pj, prow; bool rows_ok, by_tma;
+            tile_origin(tslot, pi, pj, prow, rows_ok, by_tma);
+            double *p1 = patch(b, 0), *pm = patch(b, 1), *p4 = patch(b, 2);
+            if (by_tma) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // earlier generic-proxy accesses of this set before the async-proxy writes
+                    mbar_expect_tx(&full[b], 2u * PATCH * PATCH_ROW * 8);
+                    tma_load_2d(p1, &map1, pi * SNAP_STRIDE, prow, &full[b]);
+                    tma_load_2d(p4, &map4, pi * SNAP_STRIDE, prow, &full[b]);
+                }
+                mbar_wait(&full[b], (unsigned)(use & 1));
+                double2* m = reinterpret_cast<double2*>(pm);
+                const double2 *a = reinterpret_cast<const double2*>(p1), *c = reinterpret_cast<const double2*>(p4);
+                constexpr int NCH = PATCH * PATCH_ROW / 2;
+#pragma unroll 1
+                for (int c0 = lane; c0 < NCH; c0 += 32 * 4) {
+                    double2 va[4], vc[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < NCH) { va[u] = a[c0 + 32 * u]; vc[u] = c[c0 + 32 * u]; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (c0 + 32 * u < NCH) m[c0 + 32 * u] = mean2(va[u], vc[u]);
+                }
+            } else if (rows_ok) {
+                // the patch wraps around the domain edge: filled node by node with masked indices
+                if (lane == 0) mbar_arrive(&full[b]);                // keeps `full` in step with the buffer's use count (no bytes expected)
+#pragma unroll 1
+                for (int e0 = lane; e0 < PATCH * PATCH * 3; e0 += 32 * 4) {
+                    double2 va[4], vb[4];
+                    int dst[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + 32 * u;
+                        if (e < PATCH * PATCH * 3) {
+                            const int node = e / 3, q = e - node * 3, r = node / PATCH, c = node - r * PATCH;
+                            const int col = (pi + c) & (g.nx - 1), row = g.band ? prow + r : ((pj + r) & (g.ny - 1));
+                            const long long src = ((long long)row * g.nx + col) * SNAP_STRIDE + 2 * q;
+                            va[u] = __ldg(reinterpret_cast<const double2*>(S1 + src));
+                            vb[u] = __ldg(reinterpret_cast<const double2*>(S4 + src));
+                            dst[u] = r * PATCH_ROW + c * SNAP_STRIDE + 2 * q;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (e0 + 32 * u < PATCH * PATCH * 3) {
+                            *reinterpret_cast<double2*>(p1 + dst[u]) = va[u];
+                            *reinterpret_cast<double2*>(p4 + dst[u]) = vb[u];
+                            *reinterpret_cast<double2*>(pm + dst[u]) = mean2(va[u], vb[u]);
+                        }
+                    }
+                }
+            } else {
+                if (lane == 0) mbar_arrive(&full[b]);                // not staged (band mode, rows not resident): global path
+            }
+            __syncwarp();
+            if (lane == 0) {
+                rec[b].tile = tslot;
+                rec[b].staged = rows_ok ? 1 : 0;
+                rec[b].pi = pi;
+                rec[b].pj = pj;
+                rec[b].start = start;
+                rec[b].end = end;
+                mbar_arrive(&ready[b]);                               // release: the patches and the record are visible to whoever observes the phase
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ consumer warps
+        const int ctid = threadIdx.x;                                 // 0 .. PIPE_CONSUMERS-1
+        const double h = p.t1 - p.t0;
+        double* stage = reinterpret_cast<double*>(tile_smem + 6 * PATCH_BYTES);     // [2][5][PIPE_CONSUMERS]
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+        auto prefetch = [&](long long i, int buf) {
+            double* d = stage + buf * 5 * PIPE_CONSUMERS + ctid;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async8_stream(d + c * PIPE_CONSUMERS, xk + c * g.ld + i, pol);
+            cp_async8_stream(d + 4 * PIPE_CONSUMERS, sign + i, pol);
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
+        int rot = 0, buf = 0;
+        long long pf = -1;                                            // packet whose state sits (or is landing) in stage[buf]
+        for (int it = 0;; ++it) {
+            const int b = it & 1;
+            mbar_wait(&ready[b], (unsigned)((it >> 1) & 1));
+            const int tslot = rec[b].tile;
+            if (tslot < 0) break;
+            const long long start = rec[b].start, end = rec[b].end;
+            TilePatch3 tp;
+            tp.lev[0] = patch(b, 0);
+            tp.lev[1] = patch(b, 1);
+            tp.lev[2] = patch(b, 2);
+            tp.staged = rec[b].staged != 0;
+            tp.pi = rec[b].pi;
+            tp.pj = rec[b].pj;
+            int r = ctid - rot;
+            if (r < 0) r += PIPE_CONSUMERS;
+            const int ntile = (int)((end - start) % PIPE_CONSUMERS);
+            int rot_next = rot + ntile;
+            if (rot_next >= PIPE_CONSUMERS) rot_next -= PIPE_CONSUMERS;
+            for (long long i = start + r; i < end; i += PIPE_CONSUMERS) {
+                if (pf != i) prefetch(i, buf);                        // (first packet of the launch, or the look-ahead below was not possible)
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+                const double* sv = stage + buf * 5 * PIPE_CONSUMERS + ctid;
+                double s[4] = {sv[0], sv[PIPE_CONSUMERS], sv[2 * PIPE_CONSUMERS], sv[3 * PIPE_CONSUMERS]};
+                const double sg = sv[4 * PIPE_CONSUMERS];
+                // look ahead: this thread's next packet, in this tile or -- if the producer has already published it -- the next one
+                long long nxt = i + PIPE_CONSUMERS;
+                if (nxt >= end) {
+                    nxt = -1;
+                    const int bn = b ^ 1;
+                    if (mbar_test(&ready[bn], (unsigned)(((it + 1) >> 1) & 1)) && rec[bn].tile >= 0) {
+                        int rn = ctid - rot_next;
+                        if (rn < 0) rn += PIPE_CONSUMERS;
+                        const long long cand = rec[bn].start + rn;
+                        if (cand < rec[bn].end) nxt = cand;
+                    }
+                }
+                buf ^= 1;
+                pf = nxt;
+                if (nxt >= 0) prefetch(nxt, buf);
+                rk4_three_level(s, sg, h, S1, S4, g, p, tp);
+                __stcs(xk + i, s[0]);
+                __stcs(xk + g.ld + i, s[1]);
+                __stcs(xk + 2 * g.ld + i, s[2]);
+                __stcs(xk + 3 * g.ld + i, s[3]);
+            }
+            rot = rot_next;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);                    // this warp reads the buffer set no more
+        }
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0u;
+            sched[1] = 0u;
+        }
     }
 }
 

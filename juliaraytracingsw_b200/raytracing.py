@@ -17,7 +17,7 @@ PSI_RSW_BALANCED, PSI_SWQG, PSI_TWOLAYER_BAROCLINIC, PSI_TWOLAYER_MEAN = 0, 1, 2
 LERP_PHYSICAL, LERP_REFERENCE_GPU = 0, 1
 INTERP_BILINEAR, INTERP_HERMITE_BICUBIC, INTERP_BSPLINE2, INTERP_BILINEAR_F32, INTERP_BSPLINE3, INTERP_NUFFT = 0, 1, 2, 3, 4, 5
 INTEG_RK4, INTEG_IMPLICIT_MIDPOINT = 0, 1
-RAYKERNEL_AUTO, RAYKERNEL_CACHED, RAYKERNEL_TILE, RAYKERNEL_TILE3 = -1, 0, 1, 2
+RAYKERNEL_AUTO, RAYKERNEL_CACHED, RAYKERNEL_TILE, RAYKERNEL_TILE3, RAYKERNEL_PIPE = -1, 0, 1, 2, 3
 
 
 class Velocity:
@@ -156,7 +156,7 @@ class Packets:
         return out
 
     def set_kernel(self, kernel):
-        """RAYKERNEL_AUTO (-1), RAYKERNEL_CACHED (0), RAYKERNEL_TILE (1) or RAYKERNEL_TILE3 (2): see swrt_packets_set_kernel."""
+        """RAYKERNEL_AUTO (-1), RAYKERNEL_CACHED (0), RAYKERNEL_TILE (1), RAYKERNEL_TILE3 (2) or RAYKERNEL_PIPE (3): see swrt_packets_set_kernel."""
         check(lib().swrt_packets_set_kernel(self._h, int(kernel)))
 
     def generate(self, L, k0, sqrtN, first=0):

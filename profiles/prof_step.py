@@ -14,12 +14,12 @@ ap.add_argument("--nx", type=int, default=2048)
 ap.add_argument("--sqrt-packets", type=int, default=2048)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--lattice", action="store_true")
-ap.add_argument("--kernel", default="auto", choices=["auto", "cached", "tile"])
+ap.add_argument("--kernel", default="auto", choices=["auto", "cached", "tile", "tile3", "pipe"])
 a = ap.parse_args()
 P = drivers.Parameters(nx=a.nx, sqrtNpackets=a.sqrt_packets)
 prob, _ = drivers.initialize_problem(P)
 pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
-pk.set_kernel({"auto": -1, "cached": 0, "tile": 1}[a.kernel])
+pk.set_kernel({"auto": -1, "cached": 0, "tile": 1, "tile3": 2, "pipe": 3}[a.kernel])
 if not a.lattice:
     xk = pk.get()
     xk[:, 0:2] = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(P.Npackets, 2))

@@ -12,12 +12,12 @@ from juliaraytracingsw_b200 import drivers, raytracing  # noqa: E402
 nx = int(os.environ.get("NX", 2048))
 sq = int(os.environ.get("SQ", 4096))
 lattice = int(os.environ.get("LATTICE", 0))
-names = sys.argv[1:] or ["cached", "tile", "tile3"]
+names = sys.argv[1:] or ["cached", "tile", "tile3", "pipe"]
 P = drivers.Parameters(nx=nx, sqrtNpackets=sq)
 prob, _ = drivers.initialize_problem(P)
 for name in names:
     pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
-    pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "tile3": raytracing.RAYKERNEL_TILE3, "auto": raytracing.RAYKERNEL_AUTO}[name])
+    pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "tile3": raytracing.RAYKERNEL_TILE3, "pipe": raytracing.RAYKERNEL_PIPE, "auto": raytracing.RAYKERNEL_AUTO}[name])
     if not lattice:
         xk = pk.get()
         xk[:, 0:2] = np.random.default_rng(1).uniform(-np.pi, np.pi, size=(P.Npackets, 2))

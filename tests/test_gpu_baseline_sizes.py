@@ -227,14 +227,16 @@ def test_tile_kernel_is_bit_identical_to_the_cached_kernel(nsub, shift):
 
 @pytest.mark.parametrize("lerp,shift", [(0, 0.0), (1, 0.0), (0, 7.3)])
 def test_three_level_tile_kernel_against_cached_kernel_and_oracle(lerp, shift):
-    """nsub = 1: the three-level tile kernel (first level, mean of the levels, last level staged in shared memory, one patch per
+    """nsub = 1: the three-level tile kernels (one CTA per tile, and the persistent producer/consumer pipeline: first level, mean of the levels, last level staged in shared memory, one patch per
     RK4 stage time) against the stencil-cached kernel (<= 1e-12 relative after 45 steps: bilinear(mean) = mean(bilinear), only
     the association differs) and against the oracle (<= 1e-8), for both time-lerp conventions.  Interior tiles (TMA), tiles whose
     patch wraps around the domain edge (filled by the CTA's threads) and packets beyond the staged margin (global path) occur."""
     nx = 128
     g, c, Fo, Fn, xk, sign = _tile_case(nx, 160, shift)
     outs = []
-    for kernel in (raytracing.RAYKERNEL_CACHED, raytracing.RAYKERNEL_TILE3):
+    names = {raytracing.RAYKERNEL_CACHED: "raytrace_rk4_cached_kernel<4>", raytracing.RAYKERNEL_TILE3: "raytrace_rk4_tile3_kernel",
+             raytracing.RAYKERNEL_PIPE: "raytrace_rk4_pipe_kernel"}
+    for kernel in names:
         prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
         raytracing.set_velocity_info(prob, 0, Fo)
         raytracing.set_velocity_info(prob, 1, Fn)
@@ -246,7 +248,8 @@ def test_three_level_tile_kernel_against_cached_kernel_and_oracle(lerp, shift):
             raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t, t + c["dt"]))
             t += c["dt"]
         outs.append(pk.get())
-        assert prob.ray_kernel_name() == ("raytrace_rk4_tile3_kernel" if kernel == raytracing.RAYKERNEL_TILE3 else "raytrace_rk4_cached_kernel<4>")
+        assert prob.ray_kernel_name() == names[kernel]
+    np.testing.assert_array_equal(outs[1], outs[2])       # persistent warp-specialised kernel == one CTA per tile, bit for bit
     scale = np.abs(outs[0]).max()
     assert np.abs(outs[0] - outs[1]).max() / scale < 1e-12
     want = np.ascontiguousarray(xk.copy())
