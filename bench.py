@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=64)
     ap.add_argument("--parallel", default="team", choices=["team", "replicated"],
                     help="N > 1: `team` (default) = flow slab-decomposed over the ranks + packets sharded by y-band, all native over CUDA "
                          "IPC; `replicated` = round-1 scheme (every rank repeats the flow step, packets sharded by index)")
@@ -467,7 +467,7 @@ def run_swrt(args):
         packets.get(out=h_xk)
         h_sign[:] = np.where((np.arange(lo, hi) % 2) == 0, -1.0, 1.0)
         Ke = max(3, min(K, 10))
-        nchunks = max(4, min(args.e2e_chunks, nloc // 524288))   # >= 4 row blocks at every N so that uploads, kernels and downloads overlap
+        nchunks = max(4, min(args.e2e_chunks, nloc // 131072))   # >= 4 row blocks at every N so that uploads, kernels and downloads overlap
         # Host-resident packets every step are served by the chunked pipeline API (raytracing.PacketPipeline): row blocks of this
         # rank's packets on their own streams against a flow that every rank steps itself -- PCIe, not the flow step, bounds
         # this path, so at N > 1 it runs beside the team (which keeps its packets on the GPUs) on a replicated problem.

@@ -661,7 +661,8 @@ def test_wave_balanced_projections_on_device():
 
 
 def test_packet_pipeline_matches_single_handle():
-    """Chunked, stream-overlapped packet I/O gives bit-identical results to one synchronous handle."""
+    """Chunked, stream-overlapped packet I/O (transfers on the flow's upload / download streams, kernels on the
+    blocks' own streams) gives bit-identical results to one synchronous handle."""
     import torch
     g, p, sol0, c = config2_setup(128)
     prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
@@ -675,6 +676,7 @@ def test_packet_pipeline_matches_single_handle():
     h_in[:], h_sign[:] = xk, sign
     single = raytracing.Packets(prob, n, c["f"], c["Cg"], nsub=2)
     pipe = raytracing.PacketPipeline(prob, n, c["f"], c["Cg"], nchunks=7, nsub=2)
+    assert pipe.bounds[0][0] == 0 and pipe.bounds[-1][1] == n and all(a[1] == b[0] for a, b in zip(pipe.bounds, pipe.bounds[1:]))
     raytracing.get_velocity_info(prob, 0)
     t = 0.0
     for step in range(4):
