@@ -73,6 +73,12 @@ int swrt_flow_set_rsw_initial_condition(swrt_flow* h, const double* phase_host, 
 int swrt_flow_enforce_reality(swrt_flow* h);
 /* stepforward!(prob, [], nsteps): utils/IFMAB3.jl:157-169 looped by FourierFlows.stepforward!(prob, diags, n) */
 int swrt_flow_step(swrt_flow* h, int nsteps);
+/* addforcing!(N, sol, t, clock, vars::StochasticVars, params, grid) = params.calcF!(vars.Fh, ...); @. N += vars.Fh
+ * (rsw/RotatingShallowWater.jl:228-240, ModifiedShallowWater.jl:246-258, QuadHeightModifiedShallowWater.jl:252-264,
+ * LinborgShallowWater.jl:239-251).  Fh_host = the (nkr, nl) complex128 field the caller's calcF! produced; it is added to every
+ * component of N (the reference's broadcast of the 2-D Fh over the three equations) at every calcN! until replaced; NULL clears.
+ * SWRT_ERR_UNSUPPORTED for the QG / Thomas-Yamada models, whose calcN! never calls the hook. */
+int swrt_flow_set_forcing(swrt_flow* h, const void* Fh_host);
 /* prob.clock.t / prob.clock.step */
 int swrt_flow_clock(swrt_flow* h, double* t, long long* step);
 int swrt_flow_set_clock(swrt_flow* h, double t, long long step);

@@ -80,6 +80,10 @@ function solution(prob::Problem)
     check(ccall((:swrt_flow_get_solution, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, sol))
     return sol
 end
+"vars.Fh of the forcing hook (addforcing!, rsw/RotatingShallowWater.jl:228-240): added to every component of N at each calcN!; `nothing` clears"
+set_forcing!(prob::Problem, Fh::Matrix{ComplexF64}) =
+    check(ccall((:swrt_flow_set_forcing, libswrt), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), prob.h, Fh))
+set_forcing!(prob::Problem, ::Nothing) = check(ccall((:swrt_flow_set_forcing, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), prob.h, C_NULL))
 enforce_reality_condition!(prob::Problem) = check(ccall((:swrt_flow_enforce_reality, libswrt), Cint, (Ptr{Cvoid},), prob.h))
 "stepforward!(prob, diags, nsteps) -- diags: objects with .freq and increment!(d, prob)"
 function stepforward!(prob::Problem, diags = [], nsteps::Integer = 1)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "swrt_flow_destroy": (_I, [_P]),
     "swrt_flow_set_solution": (_I, [_P, _P]),
     "swrt_flow_get_solution": (_I, [_P, _P]),
+    "swrt_flow_set_forcing": (_I, [_P, _P]),
     "swrt_flow_set_rsw_initial_condition": (_I, [_P, _P, _P, _D, _D, _D, _D, _D, _D, _PD]),
     "swrt_flow_enforce_reality": (_I, [_P]),
     "swrt_flow_step": (_I, [_P, _I]),

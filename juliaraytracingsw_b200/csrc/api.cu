@@ -68,6 +68,7 @@ struct swrt_flow {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
     cudaStream_t io_up = nullptr, io_down = nullptr;   // host transfers of own-stream packet handles, one stream per direction (io_route)
     double2 *sol = nullptr, *Nb[3] = {nullptr, nullptr, nullptr}, *G = nullptr, *H = nullptr, *stage = nullptr;
+    double2* forcing = nullptr;             // vars.Fh of the forcing hook (swrt_flow_set_forcing), [l][kr_pad]; nullptr: none
     double2 *tw_x = nullptr, *tw_y = nullptr;
     double4* coef = nullptr;
     double2* psih = nullptr;                    // materialised streamfunction for the packet snapshot
@@ -434,6 +435,7 @@ int swrt_flow_destroy(swrt_flow* h) {
     cudaSetDevice(h->d.device);
     if (h->st) cudaStreamSynchronize(h->st);
     cudaFree(h->sol);
+    cudaFree(h->forcing);
     for (auto p : h->Nb) cudaFree(p);
     cudaFree(h->G); cudaFree(h->H); cudaFree(h->stage); cudaFree(h->tw_x); cudaFree(h->tw_y); cudaFree(h->coef); cudaFree(h->Etab); cudaFree(h->E2tab); cudaFree(h->coef2); cudaFree(h->psih); cudaFree(h->psih_s); cudaFree(h->Gs); cudaFree(h->tw_xs); cudaFree(h->tw_ys); cudaFree(h->S1); cudaFree(h->S2); cudaFree(h->N4);
     if (h->band) cudaFree(h->band); else { cudaFree(h->snap[0]); cudaFree(h->snap[1]); }
@@ -659,6 +661,32 @@ int swrt_flow_set_solution(swrt_flow* h, const void* sol_host) {
     return SWRT_OK;
 }
 
+// addforcing! / calcF! (rsw/RotatingShallowWater.jl:228-240 and the same lines of the Modified / QuadHeight / Lindborg variants):
+// the user's calcF! fills vars.Fh (nkr, nl) and calcN! ends with `@. N += vars.Fh`.  Here the host hands over Fh whenever its calcF!
+// has produced a new one (between steps); the field stays on the device and is added at every calcN! evaluation until it is
+// replaced or cleared (NULL).  A flow with forcing steps un-captured (the replayed CUDA graphs of the small grids bake their
+// arguments in).
+int swrt_flow_set_forcing(swrt_flow* h, const void* Fh_host) {
+    if (!h) return fail(SWRT_ERR_ARG, "null pointer");
+    const int m = h->d.model;
+    if (!(m == SWRT_RSW || m == SWRT_RSW_MODIFIED || m == SWRT_RSW_LINDBORG || m == SWRT_RSW_QUADHEIGHT))
+        return fail(SWRT_ERR_UNSUPPORTED, "the forcing hook exists in the (u, v, eta) models only (model %d: its calcN! never calls addforcing!)", m);
+    CK(cudaSetDevice(h->d.device));
+    CK(cudaStreamSynchronize(h->st));
+    for (auto& g : h->gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (!Fh_host) {
+        cudaFree(h->forcing);
+        h->forcing = nullptr;
+        return SWRT_OK;
+    }
+    if (!h->forcing) CK(cudaMalloc(&h->forcing, sizeof(double2) * (size_t)h->L.vs));
+    CK(cudaMemcpyAsync(h->stage, Fh_host, sizeof(double2) * (size_t)h->nkr * h->d.ny, cudaMemcpyHostToDevice, h->st));
+    { ProfScope ps(h, K_OTHER); pack_sol_kernel<<<592, 256, 0, h->st>>>(h->stage, h->forcing, h->L, h->nkr, 1); }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->st));
+    return SWRT_OK;
+}
+
 int swrt_flow_get_solution(swrt_flow* h, void* sol_host) {
     if (!h || !sol_host) return fail(SWRT_ERR_ARG, "null pointer");
     CK(cudaSetDevice(h->d.device));
@@ -759,7 +787,9 @@ static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
     CK(e);
     { ProfScope ps(h, K_STAGE_B); SWRT_DISPATCH(L.nx, e, LN::stage_b(model, h->G, h->H, L, h->tw_x, h->sched, h->st)); }
     CK(e);
-    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, state, h->H, Nout, L, h->tw_y, h->st)); }
+    SpecLayout Lc = L;
+    Lc.forcing = h->forcing;                 // addforcing!: the last thing calcN! does
+    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(L.ny, e, LN::stage_c(model, state, h->H, Nout, Lc, h->tw_y, h->st)); }
     CK(e);
     return SWRT_OK;
 }
@@ -817,7 +847,7 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
     static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
     const bool ring_stepper = stepper == SWRT_IFMAB3 || stepper == SWRT_FILTEREDAB3;
     const int period = ring_stepper ? 3 : 1;
-    const bool use_graph = graph_mode > 0 && !h->prof && !h->no_graph && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
+    const bool use_graph = graph_mode > 0 && !h->prof && !h->no_graph && !h->forcing && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
     for (int s = 0; s < nsteps;) {
         if (use_graph && h->step >= 3 && nsteps - s >= period) {
             const int phase = ring_stepper ? h->ring : 0;
@@ -1198,7 +1228,9 @@ int swrt_slab_stage_c(swrt_flow* h) {
     CK(cudaSetDevice(h->d.device));
     double2* Ncur = h->Nb[h->ring];
     cudaError_t e;
-    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(h->L.ny, e, LN::stage_c(h->d.model, h->sol, h->H, Ncur, h->L, h->tw_y, h->st)); }
+    SpecLayout Lc = h->L;
+    Lc.forcing = h->forcing;
+    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(h->L.ny, e, LN::stage_c(h->d.model, h->sol, h->H, Ncur, Lc, h->tw_y, h->st)); }
     CK(e);
     int rc = ifmab3_update_launch(h, Ncur);
     if (rc) return rc;
@@ -2260,7 +2292,7 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     const int period = 6;
     const bool ring_stepper = f->d.stepper == SWRT_IFMAB3 || f->d.stepper == SWRT_FILTEREDAB3;
     // (other handles reading the snapshots on their own streams need the event waits a replay would skip: no graph then)
-    const bool eligible = graph_mode > 0 && !f->prof && !p->own && f->readers.empty() && f->P == 1 && f->refine == 1 &&
+    const bool eligible = graph_mode > 0 && !f->prof && !p->own && f->readers.empty() && f->P == 1 && f->refine == 1 && !f->forcing &&
                           (graph_mode > 1 || (long long)f->d.nx * f->d.ny <= 1024LL * 1024LL);
     for (int s = 0; s < nsteps;) {
         const bool aligned = f->step >= 3 && f->slot_map[0] == 0 && f->slot_map[1] == 1 && (!ring_stepper || f->ring == 0);   // (aliased slots {0,0} run un-captured)

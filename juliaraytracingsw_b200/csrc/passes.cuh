@@ -32,6 +32,9 @@ struct SpecLayout {
     // y-transformed / x-transformed intermediates are stored [y block][job][row in block][kr_pad]: exactly the send / receive
     // layout of the all-to-all transposes, and the plain [job][y][kr_pad] array when P = 1.
     int kr_off, kr_keep_g, yshift, yrows;
+    // addforcing! (rsw/RotatingShallowWater.jl:234-240): a stored spectral field [l][kr_pad] that the forward y-pass adds to EVERY
+    // variable of N (`@. N += vars.Fh` broadcasts the 2-D Fh over the three components); nullptr = no forcing
+    const double2* forcing;
 };
 
 // element offset of (job, y, column 0) in an intermediate array holding `njobs` jobs
@@ -321,8 +324,13 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
                     const int l = g + m * G;
                     if (!l_retained(L, l)) continue;
                     double2 r = cb.apply(var, i_in, v[m], kw, wave_l(L, l));
-                    const double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
-                                                  : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                    double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
+                                            : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                    if (i_in == 0 && L.forcing) {
+                        const double2 fh = L.forcing[(long long)l * L.kr_pad + kr];
+                        prev.x += fh.x;
+                        prev.y += fh.y;
+                    }
                     r.x += prev.x;
                     r.y += prev.y;
                     o[(long long)l * L.kr_pad] = r;
@@ -394,8 +402,13 @@ __global__ void __launch_bounds__(TK* group_size(N), 1)
                 const int l = g + m * G;
                 if (!l_retained(L, l)) continue;
                 double2 r = cb.apply(var, i_in, v[m], kw, wave_l(L, l));
-                const double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
-                                              : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                double2 prev = i_in > 0 ? o[(long long)l * L.kr_pad]
+                                        : cb.init(var, kw, wave_l(L, l), (long long)l * L.kr_pad + kr);
+                if (i_in == 0 && L.forcing) {
+                    const double2 fh = L.forcing[(long long)l * L.kr_pad + kr];
+                    prev.x += fh.x;
+                    prev.y += fh.y;
+                }
                 r.x += prev.x;
                 r.y += prev.y;
                 o[(long long)l * L.kr_pad] = r;

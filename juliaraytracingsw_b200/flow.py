@@ -229,9 +229,29 @@ def updatevars(prob):
     return None
 
 
-def stepforward(prob, diags=(), nsteps=1):
+def set_forcing(prob, Fh):
+    """vars.Fh of the forcing hook (rsw/RotatingShallowWater.jl:228-240): the (nkr, nl) complex field the caller's calcF! produced.
+    calcN! adds it to every component of N from now on; `None` removes it."""
+    if Fh is None:
+        check(lib().swrt_flow_set_forcing(prob._h, None))
+        return
+    a = np.asfortranarray(Fh, dtype=np.complex128)
+    assert a.shape == (prob.grid.nkr, prob.grid.nl), a.shape
+    check(lib().swrt_flow_set_forcing(prob._h, a.ctypes.data_as(C.c_void_p)))
+
+
+def stepforward(prob, diags=(), nsteps=1, calcF=None):
     """FourierFlows.stepforward!(prob, diags, nsteps) with the IFMAB3 stepper (utils/IFMAB3.jl:157-169).
-    `diags`: objects with `.freq` and `.increment(prob)`; sampled when step % freq == 0 like FourierFlows."""
+    `diags`: objects with `.freq` and `.increment(prob)`; sampled when step % freq == 0 like FourierFlows.
+    `calcF(Fh, t, clock)`: the `calcF!` of `Problem(...; calcF!)` for the one-calcN!-per-step steppers (IFMAB3, FilteredAB3): called
+    before every step with a host (nkr, nl) complex array to fill, which then goes to the device (set_forcing)."""
+    if calcF is not None:
+        Fh = np.zeros((prob.grid.nkr, prob.grid.nl), dtype=np.complex128, order="F")
+        for _ in range(int(nsteps)):
+            calcF(Fh, prob.clock.t, prob.clock)
+            set_forcing(prob, Fh)
+            stepforward(prob, diags, 1)
+        return
     if not diags:
         check(lib().swrt_flow_step(prob._h, int(nsteps)))
         return

@@ -43,8 +43,10 @@ def populate_L(grid: TwoDGrid, p: Params, variant=RSW):
     return L
 
 
-def calcN(sol, grid: TwoDGrid, p: Params, variant=RSW):
+def calcN(sol, grid: TwoDGrid, p: Params, variant=RSW, Fh=None):
     """N = calcN!(sol); dealiases ``sol`` IN PLACE first, like the reference (:141).
+    `Fh` (nkr, nl): vars.Fh as the user's calcF! left it; addforcing! (:234-240) ends calcN! with `@. N += vars.Fh`, which
+    broadcasts the 2-D field over the three components of N.
 
     Every rfft/irfft of the reference is kept as a separate transform (no linear merging),
     so this is the arithmetic the reference performs, in its order.
@@ -71,16 +73,20 @@ def calcN(sol, grid: TwoDGrid, p: Params, variant=RSW):
     if variant == LINDBORG:
         N[:, :, 2] = -g.rfft2(g.irfft2(ik * eh) * a)
         N[:, :, 2] += -g.rfft2(g.irfft2(il * eh) * b)
+        if Fh is not None:
+            N += Fh[:, :, None]
         return N
 
     eta = g.irfft2(eh)
     if variant in (MODIFIED, QUADHEIGHT):
         # QuadHeight carries m = 1/(1+eta) in the third slot: F = 1.5 - 0.5 m^2 (QuadHeightModifiedShallowWater.jl:219-225)
-        Fh = g.rfft2(1.5 - 0.5 / (1 + eta) ** 2 if variant == MODIFIED else 1.5 - 0.5 * eta ** 2)
-        N[:, :, 0] += -1j * p.Cg2 * g.kr * Fh
-        N[:, :, 1] += -1j * p.Cg2 * g.l * Fh
+        Ph = g.rfft2(1.5 - 0.5 / (1 + eta) ** 2 if variant == MODIFIED else 1.5 - 0.5 * eta ** 2)
+        N[:, :, 0] += -1j * p.Cg2 * g.kr * Ph
+        N[:, :, 1] += -1j * p.Cg2 * g.l * Ph
     N[:, :, 2] = -ik * g.rfft2(a * eta)
     N[:, :, 2] += -il * g.rfft2(b * eta)
+    if Fh is not None:
+        N += Fh[:, :, None]                  # addforcing! :237
     return N
 
 

@@ -1,5 +1,7 @@
 """Upper bound for the e2e leg: concurrent H2D + D2H copies of 0.54 GB each from / to pinned host memory (torch streams), by chunk count.
-`python profiles/pcie_probe.py`; prints GB/s per direction.  Not a bench value."""
+`python profiles/pcie_probe.py [modes]`; prints GB/s per direction.  Run once per GPU at the same time (CUDA_VISIBLE_DEVICES) it shows
+what the host side of an 8-GPU box sustains.  Not a bench value."""
+import sys
 import time
 
 import torch
@@ -11,8 +13,9 @@ h_out = torch.empty(n, dtype=torch.float64).pin_memory()
 d_in = torch.empty(n, dtype=torch.float64, device=dev)
 d_out = torch.empty(n, dtype=torch.float64, device=dev)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-for mode in ("h2d", "d2h", "both"):
-    for chunks in (1, 4, 8, 16):
+modes = sys.argv[1].split(",") if len(sys.argv) > 1 else ("h2d", "d2h", "both")
+for mode in modes:
+    for chunks in ((8,) if len(sys.argv) > 1 else (1, 4, 8, 16)):
         c = n // chunks
         for rep in range(3):
             torch.cuda.synchronize()

@@ -66,6 +66,48 @@ def test_rsw_filter_parity():
     assert rel_l2(prob.sol, want) < 1e-10
 
 
+@pytest.mark.parametrize("model,variant", [("RotatingShallowWater", "rsw"), ("ModifiedShallowWater", "modified"), ("LinborgShallowWater", "lindborg")])
+def test_forcing_hook_parity(model, variant):
+    """addforcing! (rsw/RotatingShallowWater.jl:228-240): `calcF!` fills vars.Fh, calcN! ends with `@. N += vars.Fh` (the 2-D field
+    broadcast over the three equations).  A time-dependent calcF! through stepforward(..., calcF=) over the Euler start-up and
+    AB3 steps (64^2: the CUDA-graph replay must stay out of the way), then the forcing is removed again."""
+    from oracle import ifmab3 as oif
+    nx, nsteps = 64, 12
+    g, p, sol0, c = config2_setup(nx)
+    rng = np.random.default_rng(9)
+    shape = g.dealias((rng.standard_normal((g.nkr, g.nl)) + 1j * rng.standard_normal((g.nkr, g.nl)))[:, :, None].copy())[:, :, 0]
+    shape *= 0.05 * np.abs(sol0).max() / c["dt"] / np.abs(shape).max() * (g.Krsq < 8 ** 2)
+    shape[0, :] = 0.0
+
+    def calcF(Fh, t, clock):
+        Fh[:] = shape * np.cos(3.0 * t)
+
+    prob = swrt.Problem(model=model, nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+    prob.sol = sol0
+    flow.stepforward(prob, (), nsteps, calcF=calcF)
+    Fh = np.zeros_like(shape)
+    ts = oif.IFMAB3(oif.expL_closed_form(g, p, c["dt"], variant), c["dt"], lambda s_: orsw.calcN(s_, g, p, variant, Fh=Fh))
+    ts.expLdt = oif.expL_closed_form(g, p, c["dt"], variant)
+    ts.exp2Ldt = oif.expL_closed_form(g, p, 2 * c["dt"], variant)
+    want = sol0.copy()
+    for _ in range(nsteps):
+        calcF(Fh, ts.t, None)
+        ts.stepforward(want)
+    assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-12
+    unforced = oracle_steps(g, p, sol0, c["dt"], nsteps, variant=variant)
+    assert rel_l2(prob.sol, unforced) > 1e-4                     # the forcing did act
+    # cleared: the next steps equal the oracle's without Fh (and the replayed graphs are back)
+    flow.set_forcing(prob, None)
+    flow.stepforward(prob, (), 7)
+    Fh[:] = 0.0
+    for _ in range(7):
+        ts.stepforward(want)
+    assert rel_l2(prob.sol, g.dealias(want.copy())) < 1e-12
+    qg = swrt.Problem(model="SWQG", nx=nx, dt=c["dt"])
+    with pytest.raises(swrt._lib.SwrtError):
+        flow.set_forcing(qg, shape)                             # swqg/SWQG.jl defines the hook but its calcN! never calls it
+
+
 def test_energies_and_diagnostics():
     g, p, sol0, c = config2_setup(128)
     prob = swrt.Problem(nx=128, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])

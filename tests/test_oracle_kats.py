@@ -506,3 +506,17 @@ def test_c_restatement_of_the_tracer_is_bit_identical_to_the_numpy_oracle():
         a = oray.raytrace(xk.copy(), sign, 0.25, 0.25 + 3 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3, lerp=lerp)
         b = craytrace.raytrace(xk.copy(), sign, 0.25, 0.25 + 3 * c["dt"], Fo, Fn, g, c["f"], c["Cg"], nsub=3, lerp=lerp)
         np.testing.assert_array_equal(a, b)
+
+
+def test_addforcing_broadcasts_the_2d_field_over_the_three_equations():
+    """rsw/RotatingShallowWater.jl:234-240: vars.Fh is (nkr, nl) and `@. N += vars.Fh` adds it to N[:, :, 1], N[:, :, 2] AND N[:, :, 3]."""
+    from helpers import config2_setup
+    from oracle import rsw as orsw
+    g, p, sol0, c = config2_setup(32)
+    rng = np.random.default_rng(3)
+    Fh = rng.standard_normal((g.nkr, g.nl)) + 1j * rng.standard_normal((g.nkr, g.nl))
+    for variant in (orsw.RSW, orsw.MODIFIED, orsw.LINDBORG, orsw.QUADHEIGHT):
+        N0 = orsw.calcN(sol0.copy(), g, p, variant)
+        N1 = orsw.calcN(sol0.copy(), g, p, variant, Fh=Fh)
+        for v in range(3):
+            np.testing.assert_allclose(N1[:, :, v] - N0[:, :, v], Fh, rtol=0, atol=1e-12 * np.abs(N0).max())
