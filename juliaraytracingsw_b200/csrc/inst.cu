@@ -51,7 +51,10 @@ cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const OutPeers& Gin, const O
     const int nj = nj_total > 0 ? nj_total : model_njobs_a(model);
     switch (model) {
         case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_RSW_QUADHEIGHT: return xpass(RswXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
     }
     return cudaErrorInvalidValue;
@@ -65,6 +68,8 @@ template <>
 cudaError_t Launch<SWRT_N>::stage_a_fused(int model, const double2* sol, const double2* psih, const OutPeers& G_, const SpecLayout& L, const double2* tw,
                                           cudaStream_t st) {
     switch (model) {
+        case MODEL_RSW_MODIFIED:
+        case MODEL_RSW_QUADHEIGHT:
         case MODEL_RSW: {   // 5 + 3 simple jobs: the prefetching y-pass
             SimpleJobs sj{};
             const int fld[5] = {0, 1, 2, 0, 1}, mul[8] = {YMUL_ONE, YMUL_ONE, YMUL_ONE, YMUL_IL, YMUL_IL, YMUL_ONE, YMUL_NEG_IL, YMUL_L2};
@@ -75,6 +80,7 @@ cudaError_t Launch<SWRT_N>::stage_a_fused(int model, const double2* sol, const d
             return ypass_inv_simple(sj, FusedLoaderA<RswLoaderA>{RswLoaderA{sol, L.vs}, psih, 5}, L, 8, G_, tw, st);
         }
         case MODEL_SWQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 1, L.aux0}, psih, 3}, L, 6, G_, tw, st);
+        case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 2, L.aux0}, psih, 6}, L, 9, G_, tw, st);
     }
     return cudaErrorInvalidValue;

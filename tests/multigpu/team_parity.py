@@ -145,6 +145,34 @@ def main():
     assert worst["swqg"] < 1e-10, worst
     sp.close()
 
+    # ---- 4. the other slabbed models / steppers: MultiLayerQG-2 + FilteredAB3 (BASELINE config 1's flow, aliased_fraction = 0,
+    #         raytracing/TwoLayerRaytracing.jl:174) and Modified RSW + IFMAB3 (rsw/ModifiedShallowWater.jl), flow steps against the oracle
+    from test_gpu_parity import _config1_setup
+    from helpers import oracle_steps
+    nx1 = max(128, 16 * world)
+    g1, sol1, c1 = _config1_setup(nx1)
+    nnu1, nu1 = 4, 1e-16
+    sp = SlabProblem(dist, local, barrier=barrier, model="MultiLayerQG", stepper="FilteredAB3", nx=nx1, dt=c1["dt"], f0=c1["f0"], H=c1["H"], b=c1["b"],
+                     U=c1["U"], mu=c1["mu"], beta=c1["beta"], nu=nu1, nnu=nnu1, aliased_fraction=0)
+    sp.sol = sol1
+    Ld = (-nu1 * g1.Krsq ** nnu1)[:, :, None] * np.ones(2)
+    tsm = oqg.FilteredAB3(Ld, c1["dt"], lambda s_: oqg.multilayer2_calcN(s_, g1, c1["F"], c1["U"][0], c1["U"][1], c1["beta"], c1["mu"]), c1["filt"][:, :, None])
+    wm = sol1.copy()
+    sp.stepforward(14)
+    for _ in range(14):
+        tsm.stepforward(wm)
+    worst["multilayerqg_filteredab3"] = rel_l2(sp.gather_solution(), g1.dealias(wm.copy()))
+    assert worst["multilayerqg_filteredab3"] < 1e-10, worst
+    sp.close()
+    gm, pm, solm, cm = config2_setup(nx1)
+    sp = SlabProblem(dist, local, barrier=barrier, model="ModifiedShallowWater", nx=nx1, Lx=cm["L"], dt=cm["dt"], f=cm["f"], Cg=cm["Cg"], nu=cm["nu"], nnu=cm["nnu"])
+    sp.sol = solm
+    sp.stepforward(14)
+    worst["modified_rsw"] = rel_l2(sp.gather_solution(), oracle_steps(gm, pm, solm, cm["dt"], 14, variant=orsw.MODIFIED))
+    assert worst["modified_rsw"] < 1e-10, worst
+    raytracing.get_velocity_info(sp, 1)
+    sp.close()
+
     allw = [None] * world
     dist.all_gather_object(allw, worst)
     if rank == 0:
