@@ -716,8 +716,11 @@ struct Launch {
         static const int enabled = [] { const char* e = getenv("SWRT_YPASS_PREFETCH"); return e ? atoi(e) : 1; }();
         if constexpr (kPrefetchFits) {
             if (enabled) {
-                // as many staged rows as fit beside the work buffers
-                int rows_s = (int)(((size_t)kSmemPerSM - ysmem - 1024) / ((size_t)TK * 16));
+                // as many staged rows as fit beside the work buffers; two CTAs per SM when each can still stage half of the rows
+                // (narrow tiles: the phases of one CTA -- wait, first stage, barriers, stores -- then overlap the other's)
+                const size_t per_sm = 228 * 1024;
+                const bool two = 2 * (ysmem + 1024 + (size_t)(L.ny / 2) * TK * 16) <= per_sm;
+                int rows_s = (int)(((two ? per_sm / 2 : (size_t)kSmemPerSM) - ysmem - 1024) / ((size_t)TK * 16));
                 if (rows_s > L.ny) rows_s = L.ny;
                 const size_t smem = ysmem + (size_t)rows_s * TK * 16;
                 auto kp = ypass_fwd_prefetch_kernel<N, TK, Combiner>;

@@ -228,7 +228,7 @@ __device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gs
 __host__ __device__ constexpr long long ypass_stage_smem(int N, int TK) { return (long long)N * TK * 16; }  // upper bound (all rows)
 
 template <int N, int TK>
-__global__ void __launch_bounds__(TK* group_size(N), 1)
+__global__ void __launch_bounds__(TK* group_size(N), (TK * group_size(N) <= 256 ? 2 : 1))
     ypass_inv_prefetch_kernel(SimpleJobs jobs, SpecLayout L, int njobs, OutPeers out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
     constexpr int G = group_size(N), NP = col_stride(N, TK), NT = TK * G;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(TK* group_size(N), clamp_blocks(ypass_smem(N, 
 // before the wait on the staged part so that both latencies overlap.
 // ------------------------------------------------------------------------------------
 template <int N, int TK, class Combiner>
-__global__ void __launch_bounds__(TK* group_size(N), 1)
+__global__ void __launch_bounds__(TK* group_size(N), (TK * group_size(N) <= 256 ? 2 : 1))
     ypass_fwd_prefetch_kernel(Combiner cb, SpecLayout L, int nvars, int nh, int rows_s, const double2* __restrict__ H,
                               double2* __restrict__ out, const double2* __restrict__ tw) {
     extern __shared__ double smem[];
@@ -448,24 +448,41 @@ struct XCtx {
     template <int MA, int MB, class RA, class RB>
     __device__ __forceinline__ void load_pair(int b, const RA& A, const RB& B) const {
         double *r = re(b), *m = im(b);
+        // The global loads are issued in batches before the shared-memory stores of the batch (the compiler cannot move a load across
+        // a store through unrelated generic pointers, so a load-store loop paid one L2 round trip per iteration: ncu long_scoreboard
+        // 17 % of the x-pass).
+        constexpr int IT = (N / 2 + G - 1) / G, BATCH = IT < 4 ? IT : 4;   // (all eight iterations at once spill: 64 registers of loads)
         __syncthreads();  // earlier pointwise readers of this buffer are done
-        for (int k = g; k < N / 2; k += G) {
-            double2 za = make_double2(0.0, 0.0), zb = make_double2(0.0, 0.0);
-            if (k < kr_keep) {
-                const double kw = k * dk;
-                za = apply_mul<MA>(__ldcs(A.at(k)), kw);
-                if (MB != MUL_ZERO) zb = apply_mul<MB>(__ldcs(B.at(k)), kw);
+#pragma unroll 1
+        for (int i0 = 0; i0 < IT; i0 += BATCH) {
+            double2 za[BATCH], zb[BATCH];
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int k = g + (i0 + i) * G;
+                za[i] = make_double2(0.0, 0.0);
+                zb[i] = make_double2(0.0, 0.0);
+                if (k < N / 2 && k < kr_keep) {
+                    za[i] = __ldcs(A.at(k));
+                    if (MB != MUL_ZERO) zb[i] = __ldcs(B.at(k));
+                }
             }
-            if (k == 0) {
-                r[0] = za.x;
-                m[0] = zb.x;
-                r[pad_index(N / 2)] = 0.0;
-                m[pad_index(N / 2)] = 0.0;
-            } else {
-                r[pad_index(k)] = za.x - zb.y;
-                m[pad_index(k)] = za.y + zb.x;
-                r[pad_index(N - k)] = za.x + zb.y;
-                m[pad_index(N - k)] = zb.x - za.y;
+#pragma unroll
+            for (int i = 0; i < BATCH; ++i) {
+                const int k = g + (i0 + i) * G;
+                if (k >= N / 2) continue;
+                const double kw = k * dk;
+                const double2 a = apply_mul<MA>(za[i], kw), bb = MB != MUL_ZERO ? apply_mul<MB>(zb[i], kw) : make_double2(0.0, 0.0);
+                if (k == 0) {
+                    r[0] = a.x;
+                    m[0] = bb.x;
+                    r[pad_index(N / 2)] = 0.0;
+                    m[pad_index(N / 2)] = 0.0;
+                } else {
+                    r[pad_index(k)] = a.x - bb.y;
+                    m[pad_index(k)] = a.y + bb.x;
+                    r[pad_index(N - k)] = a.x + bb.y;
+                    m[pad_index(N - k)] = bb.x - a.y;
+                }
             }
         }
     }
