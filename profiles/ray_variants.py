@@ -12,11 +12,12 @@ from juliaraytracingsw_b200 import drivers, raytracing  # noqa: E402
 nx = int(os.environ.get("NX", 2048))
 sq = int(os.environ.get("SQ", 4096))
 lattice = int(os.environ.get("LATTICE", 0))
+sort_every = int(os.environ.get("SORT_EVERY", 16))
 names = sys.argv[1:] or ["cached", "tile", "tile3", "pipe"]
 P = drivers.Parameters(nx=nx, sqrtNpackets=sq)
 prob, _ = drivers.initialize_problem(P)
 for name in names:
-    pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg)
+    pk = raytracing.generate_initial_wavepackets(prob, P.L, 5.196, P.Npackets, P.sqrtNpackets, P.f, P.Cg, sort_every=sort_every)
     pk.set_kernel({"cached": raytracing.RAYKERNEL_CACHED, "tile": raytracing.RAYKERNEL_TILE, "tile3": raytracing.RAYKERNEL_TILE3, "pipe": raytracing.RAYKERNEL_PIPE, "auto": raytracing.RAYKERNEL_AUTO}[name])
     if not lattice:
         xk = pk.get()
@@ -35,6 +36,6 @@ for name in names:
     rep = prob.profile_report()
     prob.profile(0)
     r = next(v for k, v in rep.items() if k.startswith("raytrace_rk4"))
-    print("kernel", name, "nx", nx, "packets", P.Npackets, "raytrace ms %.4f" % r["ms_avg"], "sort ms/launch %.4f x %d" %
+    print("kernel", name, "sort_every", sort_every, "nx", nx, "packets", P.Npackets, "raytrace ms %.4f" % r["ms_avg"], "sort ms/launch %.4f x %d" %
           (rep["packet_sort_kernels"]["ms_avg"], rep["packet_sort_kernels"]["launches"]), "checksum %.15e" % float(np.abs(pk.get()).sum()), flush=True)
     pk.close()
