@@ -578,8 +578,6 @@ struct SnapshotXOp {
     double s1;
     OutPeers gin;      // slab mode: sources of the input column segments
     int nj = 3, j0 = 0;   // the three psi jobs are jobs j0 .. j0 + 2 of nj (they ride behind the model's jobs in team mode)
-    // vx stays in the registers of the thread that stores it (x = g + m N/16); (u, v) and (ux, uy) wait in the two shared
-    // buffers, so that the three 16-byte pieces of a record are stored back to back (whole sectors reach L2 together)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G, EPT = XCtx<N>::EPT;
         static_assert(EPT == 16, "one register per owned point");
@@ -609,6 +607,12 @@ struct SnapshotXOp {
             q[0] = make_double2(s1 * cx.re(0)[p], s1 * cx.im(0)[p]);
             q[1] = make_double2(s1 * cx.re(1)[p], s1 * cx.im(1)[p]);
             q[2] = make_double2(s1 * vx[i].x, 0.0);
+            // Point after point (the warp barrier is what keeps the machine code in this order).  Left to the scheduler, all 64
+            // shared-memory reads are hoisted and the 48 stores of a thread leave as one burst at the end of the row (each a
+            // 16-byte piece per lane at a 48-byte stride, 12 lines per warp instruction), which stalls the other warps' traffic
+            // behind it: 0.116 ms per launch against 0.104 ms paced; storing each transform's piece as soon as it is ready (three
+            // passes of 16 stores, no buffering) writes partial sectors and costs 0.151 ms (profiles/r02_README.md).
+            __syncwarp();
         }
     }
 };
