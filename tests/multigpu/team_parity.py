@@ -48,6 +48,8 @@ def main():
     rng = np.random.default_rng(17)
     xk0[:, 0:2] += rng.uniform(-9, 9, size=(N, 2))                   # anywhere, also far outside the domain (never wrapped)
     pk = raytracing.Packets(sp, hi - lo, c["f"], c["Cg"], sort_every=sort_every, first=lo)
+    if os.environ.get("SWRT_TEAM_KERNEL"):      # e.g. "2": the three-level tile kernel on the band buffers (AUTO keeps the cached kernel at this packet density)
+        pk.set_kernel(int(os.environ["SWRT_TEAM_KERNEL"]))
     pk.set(xk0[lo:hi], sign[lo:hi])
     assert sum(sp._gather(pk.resident())) == N
     np.testing.assert_array_equal(pk.get(), xk0[lo:hi])               # scatter to the band owners and back: bit exact
@@ -72,6 +74,9 @@ def main():
         tt = drivers.coupled_step(sp, pk, tt)
     drivers.coupled_steps(sp, pk, nsteps - 20)
     assert sp.clock.step == nsteps
+    if os.environ.get("SWRT_TEAM_KERNEL"):
+        want_name = {"1": "raytrace_rk4_tile_kernel<3>", "2": "raytrace_rk4_tile3_kernel", "3": "raytrace_rk4_pipe_kernel"}[os.environ["SWRT_TEAM_KERNEL"]]
+        assert sp.ray_kernel_name() == want_name, sp.ray_kernel_name()
     worst["flow"] = rel_l2(sp.gather_solution(), g.dealias(sol.copy()))
     assert worst["flow"] < 1e-10, worst
     got = pk.get()

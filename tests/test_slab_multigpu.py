@@ -29,6 +29,18 @@ def test_team_parity_against_the_oracle(nproc):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_team_parity_with_the_staged_ray_kernels_on_band_buffers(kernel):
+    """The three-level tile kernel (2) and its persistent variant (3) on y-band-sharded packets: patches staged from the band +
+    halo buffers (TMA where the patch is inside, cooperative fill where it wraps in x, global gathers where rows are missing)."""
+    import torch
+    same = torch.cuda.device_count() < 2
+    r = _run("team_parity.py", 2, 29551 + kernel, env={"SWRT_TEAM_SAME_GPU": "1" if same else "0", "SWRT_TEAM_KERNEL": str(kernel)})
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-5000:]
+    assert "team parity ok on 2 ranks" in r.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["push", "copy", "pull"])
 def test_slab_step_variants_match_the_single_gpu_step(mode):
     """`mode` = variant of the first transpose (slab.py): peer stores from the y-pass, block-copy kernel, or x-pass pull;
