@@ -63,24 +63,28 @@ struct RowPlain {
     double2* base;
     __device__ __forceinline__ double2* at(int k) const { return base + k; }
 };
+// (segment of column k = k / chunk as one multiply-high with magic = ceil(2^32 / chunk), exact for k < 8192 and every chunk that is a
+// multiple of 16 -- checked exhaustively; a compare-and-add loop over the segments made the slab x-pass kernels twice as long as the
+// single-GPU ones in instructions: 12 312 against 6 712 for the RSW op at N = 2048, profiles/r02_sass_summary.txt)
+__host__ __device__ inline unsigned seg_magic(int chunk) { return (unsigned)(((1ULL << 32) + (unsigned)chunk - 1) / (unsigned)chunk); }
 struct RowSeg {
     double2* base;
     long long skip;   // segment stride - chunk: added once per segment boundary crossed
+    unsigned magic;
     int chunk, nseg;
     __device__ __forceinline__ double2* at(int k) const {
-        long long off = k;
-        for (int j = 1; j < nseg; ++j) off += k >= j * chunk ? skip : 0;   // branch-free, no division
-        return base + off;
+        const int sgm = (int)__umulhi((unsigned)k, magic);
+        return base + k + (long long)sgm * skip;
     }
 };
 struct RowSegOut {   // x-pass output row in slab mode: column segment s goes to peer s
     const OutPeers* peers;
     long long off;    // offset of (this rank's block, job, local row) inside a peer's buffer
+    unsigned magic;
     int chunk, nseg;
     __device__ __forceinline__ double2* at(int k) const {
-        int s = 0;
-        for (int j = 1; j < nseg; ++j) s += k >= j * chunk ? 1 : 0;
-        return peers->p[s] + off + (k - s * chunk);
+        const int sgm = (int)__umulhi((unsigned)k, magic);
+        return peers->p[sgm] + off + (k - sgm * chunk);
     }
 };
 template <bool SLAB>
@@ -94,6 +98,7 @@ __device__ __forceinline__ typename RowOf<SLAB>::type row_ref(const SpecLayout& 
     if constexpr (SLAB) {
         r.skip = ((long long)njobs << L.yshift) * L.kr_pad - L.kr_pad;
         r.chunk = L.kr_pad;
+        r.magic = seg_magic(L.kr_pad);
         r.nseg = L.ny >> L.yshift;
     }
     return r;
@@ -109,6 +114,7 @@ __device__ __forceinline__ typename std::conditional<SLAB, RowSegOut, RowPlain>:
         r.peers = &src;
         r.off = ((((long long)src.self * njobs + job) << L.yshift) + yl) * L.kr_pad;
         r.chunk = L.kr_pad;
+        r.magic = seg_magic(L.kr_pad);
         r.nseg = L.ny >> L.yshift;
     } else {
         r.base = const_cast<double2*>(arr) + (((long long)job << L.yshift) + yl) * L.kr_pad;
@@ -128,6 +134,7 @@ __device__ __forceinline__ typename RowOutOf<SLAB>::type row_out(const SpecLayou
         r.peers = &peers;
         r.off = ((((long long)peers.self * njobs + job) << L.yshift) + yl) * L.kr_pad;
         r.chunk = L.kr_pad;
+        r.magic = seg_magic(L.kr_pad);
         r.nseg = L.ny >> L.yshift;
     } else {
         r.base = arr + (((long long)job << L.yshift) + yl) * L.kr_pad;
