@@ -56,4 +56,34 @@ for nch in counts:
         prob.sync()
         res.append((time.perf_counter() - w0) * 100)
     print(f"chunks {nch:4d}: ms/step " + " ".join(f"{r:6.2f}" for r in res) + f"   host enqueue ms/step {1e3 * np.mean(enq[2:]):5.2f}", flush=True)
+    if os.environ.get("PHASES"):
+        # the phases of one step on their own (10 repetitions each): what the full step overlaps
+        def timed(fn):
+            prob.sync()
+            w0 = time.perf_counter()
+            for _ in range(10):
+                fn()
+                for p in pipe.chunks:
+                    p.sync()
+            prob.sync()
+            return (time.perf_counter() - w0) * 100
+
+        def flow_only():
+            flow.stepforward(prob, (), 1)
+            raytracing.get_velocity_info(prob, 1)
+            raytracing.swap_snapshots(prob, alias=False)
+
+        def uploads():
+            for p, (lo, hi) in zip(pipe.chunks, pipe.bounds):
+                p.set_async(h_xk[lo:hi], None)
+
+        def kernels():
+            for p in pipe.chunks:
+                check(lib().swrt_packets_raytrace(p._h, float(t), float(t + prob.dt)))
+
+        def downloads():
+            for p, (lo, hi) in zip(pipe.chunks, pipe.bounds):
+                p.get_async(h_out[lo:hi])
+        print(f"   phases alone, ms: flow step + snapshot {timed(flow_only):5.2f} | uploads (0.54 GB) {timed(uploads):5.2f} | sort + ray trace of the "
+              f"{nch} blocks {timed(kernels):5.2f} | unpermute + downloads (0.54 GB) {timed(downloads):5.2f}", flush=True)
     pipe.close()
