@@ -85,6 +85,7 @@ struct swrt_flow {
     int nufft_w = 8;                        // SWRT_INTERP_NUFFT: kernel width; ptab = 1 / phihat per kr index (nkr) then per l index (ny)
     double* ptab = nullptr;
     int ptab_w = 0, ptab_refine = 0;
+    CUtensorMap tmapf[2];                   // the same arrays viewed as [ny][nx * 8] floats (fp32 packet mode), box = one fp32 patch
     CUtensorMap tmap[2];                    // TMA descriptors of the two levels viewed as [ny][nx * 6] doubles, box = one tile patch
     bool tmap_ok = false;
     double* phys = nullptr;
@@ -387,6 +388,12 @@ static void build_tmaps(swrt_flow* h) {
         const cuuint64_t strides[1] = {(cuuint64_t)(nx * SNAP_STRIDE * sizeof(double))};
         const cuuint32_t box[2] = {(cuuint32_t)PATCH_ROW, (cuuint32_t)PATCH}, estr[2] = {1, 1};
         if (encode(&h->tmap[lev], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->snap[lev], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+        const cuuint64_t dimsf[2] = {(cuuint64_t)(nx * SNAPF_STRIDE), (cuuint64_t)ny};
+        const cuuint64_t stridesf[1] = {(cuuint64_t)(nx * SNAPF_STRIDE * sizeof(float))};
+        const cuuint32_t boxf[2] = {(cuuint32_t)PATCHF_ROW, (cuuint32_t)PATCH};
+        if (encode(&h->tmapf[lev], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, h->snap[lev], dimsf, stridesf, boxf, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return;
     }
@@ -2096,6 +2103,21 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
     // 0.62-0.68 ms against 0.52 ms, profiles/r02_o_ray_kernel_ab.log)
     const bool use_pipe = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_PIPE || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && tile_mode == 4));
     const bool use_tile3 = use_tile && p->d.nsub == 1 && (p->kernel_sel == SWRT_RAYKERNEL_TILE3 || (p->kernel_sel == SWRT_RAYKERNEL_AUTO && (tile_mode == 1 || tile_mode == 3)));
+    // fp32 packet mode, one RK4 step per call: its own three-level staged kernel (SWRT_RAYTRACE_F32_TILE = its CTAs per SM, 2 or 3;
+    // 0: the stencil-cached fp32 kernel)
+    static const int f32_tile = [] { const char* e = getenv("SWRT_RAYTRACE_F32_TILE"); return e ? atoi(e) : 3; }();   // CTAs per SM: 3 (80 registers) 0.412 ms, 2 (114) 0.442 ms, cached fp32 kernel 0.58 ms
+    const bool use_tile3f = want_tile && f32_tile > 0 && p->d.interp == SWRT_INTERP_BILINEAR_F32 && p->d.integrator == SWRT_INTEG_RK4 && p->d.nsub == 1 &&
+                            p->tiles_valid && f->tmap_ok && ntiles > 0;
+    if (use_tile3f) {
+        static bool attr_f_done = false;
+        if (!attr_f_done) {
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE3F_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_f32_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE3F_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(raytrace_rk4_tile3_f32_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            attr_f_done = true;
+        }
+    }
     if (use_tile) {
         static bool attr_done = false;
         if (!attr_done) {
@@ -2109,7 +2131,7 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
             attr_done = true;
         }
     }
-    f->ray_name = p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
+    f->ray_name = use_tile3f ? "raytrace_rk4_tile3_f32_kernel" : p->d.interp == SWRT_INTERP_BILINEAR_F32 ? "raytrace_rk4_f32_kernel"
                 : (p->d.integrator == SWRT_INTEG_IMPLICIT_MIDPOINT || p->d.interp == SWRT_INTERP_BSPLINE2 || p->d.interp == SWRT_INTERP_BSPLINE3 || p->d.interp == SWRT_INTERP_NUFFT) ? "raytrace_generic_kernel"
                 : p->d.interp == SWRT_INTERP_HERMITE_BICUBIC ? "raytrace_rk4_cubic_kernel"
                 : use_pipe ? "raytrace_rk4_pipe_kernel"
@@ -2118,7 +2140,15 @@ int swrt_packets_raytrace(swrt_packets* p, double t0, double t1) {
                 : (cached || p->kernel_sel == SWRT_RAYKERNEL_CACHED) ? "raytrace_rk4_cached_kernel<4>" : "raytrace_rk4_kernel";
     { ProfScope ps(f, K_RAYTRACE, pst(p));
 #define SWRT_GEN(I, G) raytrace_generic_kernel<I, G><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, So, Sn, pg, rp)
-      if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
+      if (use_tile3f) {
+          const int first = p->d.time_lerp == 0 ? 0 : 1;          // the level whose weight is 1 at t0
+          const float4 *F1 = reinterpret_cast<const float4*>(first == 0 ? So : Sn), *F4 = reinterpret_cast<const float4*>(first == 0 ? Sn : So);
+          if (f32_tile >= 3) raytrace_rk4_tile3_f32_kernel<3><<<(unsigned)ntiles, TILE3_THREADS, (size_t)TILE3F_SMEM_BYTES, pst(p)>>>(
+              p->xk, p->sign, F1, F4, f->tmapf[f->slot_map[first]], f->tmapf[f->slot_map[first ^ 1]], p->hist, pg, rp);
+          else raytrace_rk4_tile3_f32_kernel<2><<<(unsigned)ntiles, TILE3_THREADS, (size_t)TILE3F_SMEM_BYTES, pst(p)>>>(
+              p->xk, p->sign, F1, F4, f->tmapf[f->slot_map[first]], f->tmapf[f->slot_map[first ^ 1]], p->hist, pg, rp);
+      }
+      else if (p->d.interp == SWRT_INTERP_BILINEAR_F32) {
           static const int fminb = [] { const char* e = getenv("SWRT_RAYTRACE_F32_MINB"); return e ? atoi(e) : 6; }();
           const float4 *Fo = reinterpret_cast<const float4*>(So), *Fn = reinterpret_cast<const float4*>(Sn);
           if (fminb <= 4) raytrace_rk4_f32_kernel<4><<<grid, 128, 0, pst(p)>>>(p->xk, p->sign, n, Fo, Fn, pg, rp);

@@ -1379,6 +1379,199 @@ __global__ void snapf_to_planar_kernel(const float* __restrict__ S, long long np
     for (int c = 0; c < 5; ++c) out[c * npts + i] = (double)S[i * SNAPF_STRIDE + c];
 }
 
+// ---------------------------------------------------------------- fp32 packet mode, three staged levels (nsub == 1)
+// The three-level tile kernel for Float32 node records (8 floats = 32 B per node: u, v, ux, uy | vx, 0, 0, 0): the patches are
+// half the bytes of the fp64 ones, the stencil of a stage is 20 floats, the right-hand side is evaluated in fp32 like
+// ray_rhs_f32; packet state, cell coordinate and the RK4 combination stay fp64.
+constexpr int PATCHF_ROW = 188;                          // floats per patch row: 47 sixteen-byte chunks (>= 23 nodes x 2, odd bank-group stride)
+static_assert(PATCHF_ROW >= PATCH * SNAPF_STRIDE && PATCHF_ROW % 4 == 0 && PATCHF_ROW <= 256, "fp32 patch row");
+constexpr int PATCHF_BYTES = (PATCH * PATCHF_ROW * 4 + 127) / 128 * 128;
+constexpr int TILE3F_SMEM_BYTES = 3 * PATCHF_BYTES + TILE3_STAGE_BYTES;
+struct Stencil1F {
+    float4 c[4];   // u, v, ux, uy at the corners 00, 10, 01, 11
+    float vx[4];
+};
+struct TilePatch3F {
+    const float* lev[3];
+    int pi, pj;
+    bool staged;
+};
+__device__ __forceinline__ float4 mean4(float4 a, float4 b) { return make_float4(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z), 0.5f * (a.w + b.w)); }
+template <int LEV>
+__device__ __forceinline__ void fill_stencil1f(Stencil1F& st, int i0, int j0, const float4* __restrict__ F1, const float4* __restrict__ F4,
+                                               const PacketGrid& g, const TilePatch3F& tp) {
+    const unsigned ri = (unsigned)((i0 - tp.pi) & (g.nx - 1)), rj = (unsigned)((j0 - tp.pj) & (g.ny - 1));
+    if (tp.staged && ri < (unsigned)(PATCH - 1) && rj < (unsigned)(PATCH - 1)) {
+        const float4* q = reinterpret_cast<const float4*>(tp.lev[LEV] + rj * PATCHF_ROW + ri * SNAPF_STRIDE);
+        st.c[0] = q[0];
+        st.c[1] = q[2];
+        st.c[2] = q[PATCHF_ROW / 4];
+        st.c[3] = q[PATCHF_ROW / 4 + 2];
+        st.vx[0] = reinterpret_cast<const float*>(q + 1)[0];
+        st.vx[1] = reinterpret_cast<const float*>(q + 3)[0];
+        st.vx[2] = reinterpret_cast<const float*>(q + PATCHF_ROW / 4 + 1)[0];
+        st.vx[3] = reinterpret_cast<const float*>(q + PATCHF_ROW / 4 + 3)[0];
+    } else {
+        const int i1 = (i0 + 1) & (g.nx - 1);
+        int j1 = (j0 + 1) & (g.ny - 1);
+        stencil_rows(g, j0, j1);
+        const long long pt[4] = {(long long)j0 * g.nx + i0, (long long)j0 * g.nx + i1, (long long)j1 * g.nx + i0, (long long)j1 * g.nx + i1};
+#pragma unroll
+        for (int cr = 0; cr < 4; ++cr) {
+            const float4* qa = (LEV == 2 ? F4 : F1) + 2 * pt[cr];
+            st.c[cr] = __ldg(qa);
+            st.vx[cr] = __ldg(reinterpret_cast<const float*>(qa + 1));
+            if (LEV == 1) {
+                const float4* qb = F4 + 2 * pt[cr];
+                st.c[cr] = mean4(st.c[cr], __ldg(qb));
+                st.vx[cr] = 0.5f * (st.vx[cr] + __ldg(reinterpret_cast<const float*>(qb + 1)));
+            }
+        }
+    }
+}
+__device__ __forceinline__ void ray_rhs1f(const Stencil1F& st, double ad, double bd, double kd, double ld, float sign, float f2, float cg2,
+                                          double (&d)[4]) {
+    const float a = (float)ad, b = (float)bd, a1 = 1.f - a, b1 = 1.f - b;
+    const float w[4] = {a1 * b1, a * b1, a1 * b, a * b};
+    float W[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int cr = 0; cr < 4; ++cr) {
+        W[0] = fmaf(w[cr], st.c[cr].x, W[0]); W[1] = fmaf(w[cr], st.c[cr].y, W[1]); W[2] = fmaf(w[cr], st.c[cr].z, W[2]);
+        W[3] = fmaf(w[cr], st.c[cr].w, W[3]); W[4] = fmaf(w[cr], st.vx[cr], W[4]);
+    }
+    const float k = (float)kd, l = (float)ld;
+    const float cg = cg2 * sign * rsqrtf(fmaf(cg2, fmaf(k, k, l * l), f2));
+    d[0] = (double)fmaf(cg, k, W[0]);
+    d[1] = (double)fmaf(cg, l, W[1]);
+    d[2] = (double)(-(W[2] * k + W[4] * l));
+    d[3] = (double)(-(W[3] * k - W[2] * l));
+}
+__device__ __forceinline__ void rk4_three_level_f32(double (&s)[4], float sg, double h, const float4* __restrict__ F1, const float4* __restrict__ F4,
+                                                    const PacketGrid& g, float f2, float cg2, const TilePatch3F& tp) {
+    Stencil1F st;
+    int i0, i1, j0, j1, ci, cj;
+    double a, b, k[4], acc[4], y[4];
+    cell(s[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(s[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1f<0>(st, i0, j0, F1, F4, g, tp);
+    ray_rhs1f(st, a, b, s[2], s[3], sg, f2, cg2, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] = k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1f<1>(st, i0, j0, F1, F4, g, tp);
+    ci = i0;
+    cj = j0;
+    ray_rhs1f(st, a, b, y[2], y[3], sg, f2, cg2, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + 0.5 * h * k[c]; }
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    if (i0 != ci || j0 != cj) fill_stencil1f<1>(st, i0, j0, F1, F4, g, tp);
+    ray_rhs1f(st, a, b, y[2], y[3], sg, f2, cg2, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { acc[c] += 2.0 * k[c]; y[c] = s[c] + h * k[c]; }
+    cell(y[0], g.x0, g.inv_dx, g.nx, i0, i1, a);
+    cell(y[1], g.y0, g.inv_dy, g.ny, j0, j1, b);
+    fill_stencil1f<2>(st, i0, j0, F1, F4, g, tp);
+    ray_rhs1f(st, a, b, y[2], y[3], sg, f2, cg2, k);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] += (h / 6.0) * (acc[c] + k[c]);
+}
+// F1 / map1: the level whose lerp weight is 1 at t0 (resolved by the caller), viewed as [ny][nx * 8] floats
+template <int MINB>
+__global__ void __launch_bounds__(TILE3_THREADS, MINB)
+    raytrace_rk4_tile3_f32_kernel(double* __restrict__ xk, const double* __restrict__ sign, const float4* __restrict__ F1, const float4* __restrict__ F4,
+                                  const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map4,
+                                  const unsigned* __restrict__ tile_end, PacketGrid g, RayParams p) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int tiles_x = g.nx >> TILE_SHIFT, tiles_y = g.ny >> TILE_SHIFT;
+    const int tjl = blockIdx.x / tiles_x, ti = blockIdx.x - tjl * tiles_x;
+    const int tj = (g.tile_row0 + tjl) % tiles_y;
+    const int tile = tj * tiles_x + ti;
+    const long long key0 = (long long)tile << (2 * TILE_SHIFT);
+    const long long start = tile == 0 ? 0 : (long long)__ldg(&tile_end[key0 - 1]), end = (long long)__ldg(&tile_end[key0 + (TILE * TILE - 1)]);
+    float* const patch1 = reinterpret_cast<float*>(tile_smem);
+    float* const patchm = reinterpret_cast<float*>(tile_smem + PATCHF_BYTES);
+    float* const patch4 = reinterpret_cast<float*>(tile_smem + 2 * PATCHF_BYTES);
+    TilePatch3F tp;
+    tp.lev[0] = patch1;
+    tp.lev[1] = patchm;
+    tp.lev[2] = patch4;
+    tp.pi = ti * TILE - TILE_MARGIN;
+    tp.pj = tj * TILE - TILE_MARGIN;
+    int prow = tp.pj;
+    bool rows_ok = true;
+    if (g.band) {
+        prow = (tp.pj - g.jb) & (g.ny - 1);
+        if (prow >= g.ny / 2) prow -= g.ny;
+        rows_ok = prow >= 0 && prow + PATCH <= g.jrows;
+    }
+    const bool by_tma = rows_ok && tp.pi >= 0 && tp.pi + PATCH <= g.nx && prow >= 0 && prow + PATCH <= (g.band ? g.jrows : g.ny);
+    tp.staged = rows_ok;
+    if (by_tma) {
+        if (threadIdx.x == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, 2u * PATCH * PATCHF_ROW * 4);
+            tma_load_2d(patch1, &map1, tp.pi * SNAPF_STRIDE, prow, &bar);
+            tma_load_2d(patch4, &map4, tp.pi * SNAPF_STRIDE, prow, &bar);
+        }
+    }
+    if (start >= end) {
+        if (by_tma) mbar_wait(&bar, 0);
+        return;
+    }
+    const double h = p.t1 - p.t0;
+    const float f2 = (float)(p.f * p.f), cg2 = (float)(p.Cg * p.Cg);
+    double* stage = reinterpret_cast<double*>(tile_smem + 3 * PATCHF_BYTES);     // [2][5][TILE3_THREADS]
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    auto prefetch = [&](long long i, int buf) {
+        if (i < end) {
+            double* d = stage + buf * 5 * TILE3_THREADS + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async8_stream(d + c * TILE3_THREADS, xk + c * g.ld + i, pol);
+            cp_async8_stream(d + 4 * TILE3_THREADS, sign + i, pol);
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    prefetch(start + threadIdx.x, 0);
+    if (by_tma) {
+        mbar_wait(&bar, 0);
+        float4* m = reinterpret_cast<float4*>(patchm);
+        const float4 *a = reinterpret_cast<const float4*>(patch1), *b = reinterpret_cast<const float4*>(patch4);
+        for (int c = threadIdx.x; c < PATCH * PATCHF_ROW / 4; c += TILE3_THREADS) m[c] = mean4(a[c], b[c]);
+        __syncthreads();
+    } else if (rows_ok) {
+        for (int e = threadIdx.x; e < PATCH * PATCH * 2; e += TILE3_THREADS) {
+            const int node = e >> 1, q = e & 1, r = node / PATCH, c = node - r * PATCH;
+            const int col = (tp.pi + c) & (g.nx - 1), row = g.band ? prow + r : ((tp.pj + r) & (g.ny - 1));
+            const long long src = ((long long)row * g.nx + col) * 2 + q;
+            const float4 va = __ldg(F1 + src), vb = __ldg(F4 + src);
+            const int dst = r * PATCHF_ROW + c * SNAPF_STRIDE + 4 * q;
+            *reinterpret_cast<float4*>(patch1 + dst) = va;
+            *reinterpret_cast<float4*>(patch4 + dst) = vb;
+            *reinterpret_cast<float4*>(patchm + dst) = mean4(va, vb);
+        }
+        __syncthreads();
+    }
+    int buf = 0;
+    for (long long i = start + threadIdx.x; i < end; i += TILE3_THREADS, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        const double* sv = stage + buf * 5 * TILE3_THREADS + threadIdx.x;
+        double s[4] = {sv[0], sv[TILE3_THREADS], sv[2 * TILE3_THREADS], sv[3 * TILE3_THREADS]};
+        const float sg = (float)sv[4 * TILE3_THREADS];
+        prefetch(i + TILE3_THREADS, buf ^ 1);
+        rk4_three_level_f32(s, sg, h, F1, F4, g, f2, cg2, tp);
+        __stcs(xk + i, s[0]);
+        __stcs(xk + g.ld + i, s[1]);
+        __stcs(xk + 2 * g.ld + i, s[2]);
+        __stcs(xk + 3 * g.ld + i, s[3]);
+    }
+}
+
 // interpolate_velocity!/gradients!: U (N,2), Gd (N,4) = ux, uy, vx, vy, written at the packets' ORIGINAL rows
 __global__ void __launch_bounds__(128) sample_kernel(const double* __restrict__ xk, const unsigned* __restrict__ idx, long long n,
                                                      const double* __restrict__ S, PacketGrid g, double* __restrict__ U,

@@ -261,6 +261,45 @@ def test_three_level_tile_kernel_against_cached_kernel_and_oracle(lerp, shift):
     assert np.abs(outs[1] - want).max() / np.abs(want).max() < 1e-8
 
 
+@pytest.mark.parametrize("lerp,shift", [(0, 0.0), (1, 7.3)])
+def test_fp32_three_level_tile_kernel(lerp, shift):
+    """fp32 packet mode through its staged kernel (Float32 patches: first level, mean, last level; fp32 right-hand side, fp64 state)
+    against the stencil-cached fp32 kernel and against the fp64 oracle fed the same Float32-rounded fields (2e-6 relative per the
+    fp32 mode's contract, over 30 steps with one re-sort)."""
+    nx = 128
+    g, c, Fo, Fn, xk, sign = _tile_case(nx, 160, shift)
+    Fo32, Fn32 = Fo.astype(np.float32), Fn.astype(np.float32)
+    _, _, sol0, _ = config2_setup(nx)
+    outs = []
+    names = {raytracing.RAYKERNEL_CACHED: "raytrace_rk4_f32_kernel", raytracing.RAYKERNEL_AUTO: "raytrace_rk4_tile3_f32_kernel"}
+    for kernel in names:
+        prob = swrt.Problem(nx=nx, Lx=c["L"], dt=c["dt"], f=c["f"], Cg=c["Cg"], nu=c["nu"], nnu=c["nnu"])
+        raytracing.set_interpolation(prob, raytracing.INTERP_BILINEAR_F32)
+        prob.sol = sol0                                        # (fp32 snapshots are built from the flow state only: the two levels of _tile_case)
+        raytracing.get_velocity_info(prob, 0)
+        flow.stepforward(prob, (), 1)
+        raytracing.get_velocity_info(prob, 1)
+        pk = raytracing.Packets(prob, xk.shape[0], c["f"], c["Cg"], nsub=1, sort_every=20, time_lerp=lerp, interp=raytracing.INTERP_BILINEAR_F32)
+        pk.set_kernel(kernel)
+        pk.set(xk, sign)
+        t = 0.0
+        for _ in range(30):
+            raytracing.raytrace(pk, None, None, None, None, prob.grid, pk, c["dt"], (t, t + c["dt"]))
+            t += c["dt"]
+        outs.append(pk.get())
+        assert prob.ray_kernel_name() == names[kernel]
+    want = np.ascontiguousarray(xk.copy())
+    t = 0.0
+    trace = craytrace.raytrace if craytrace.available() else oray.raytrace
+    for _ in range(30):
+        trace(want, sign, t, t + c["dt"], Fo32.astype(np.float64), Fn32.astype(np.float64), g, c["f"], c["Cg"], nsub=1, lerp=lerp)
+        t += c["dt"]
+    scale = np.abs(want).max()
+    assert np.abs(outs[0] - want).max() / scale < 2e-6
+    assert np.abs(outs[1] - want).max() / scale < 2e-6
+    assert np.abs(outs[0] - outs[1]).max() / scale < 2e-6
+
+
 def _tile_case(nx, n_side, shift):
     g, p, sol0, c = config2_setup(nx)
     from helpers import oracle_steps
