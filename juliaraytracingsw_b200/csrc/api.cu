@@ -506,10 +506,10 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     if (d.slab_size > 1) {
         const int P = d.slab_size;
         if ((P & (P - 1)) || P > 16 || d.slab_rank < 0 || d.slab_rank >= P || d.ny % P || d.ny / P < 16) { delete h; return fail(SWRT_ERR_ARG, "slab_size must be a power of two <= 16 dividing ny (>= 16 rows per rank), 0 <= slab_rank < slab_size"); }
-        const bool slab_model = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_QUADHEIGHT || d.model == SWRT_SWQG ||
+        const bool slab_model = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_QUADHEIGHT || d.model == SWRT_RSW_LINDBORG || d.model == SWRT_SWQG ||
                                 d.model == SWRT_TWOLAYERQG || d.model == SWRT_MULTILAYERQG2;
         // (the one-calcN!-per-step steppers: the slab step is stage A -> B -> C + update; the multi-stage steppers would repeat it per stage)
-        if (!slab_model || !(d.stepper == SWRT_IFMAB3 || d.stepper == SWRT_FILTEREDAB3)) { delete h; return fail(SWRT_ERR_UNSUPPORTED, "slab mode is built for RSW / Modified RSW / QuadHeight RSW / SWQG / two-layer QG / MultiLayerQG-2 with IFMAB3 or FilteredAB3"); }
+        if (!slab_model || !(d.stepper == SWRT_IFMAB3 || d.stepper == SWRT_FILTEREDAB3)) { delete h; return fail(SWRT_ERR_UNSUPPORTED, "slab mode is built for the RSW family / SWQG / two-layer QG / MultiLayerQG-2 with IFMAB3 or FilteredAB3"); }
         h->P = P; h->rank = d.slab_rank;
         const int chunk = ((L.kr_keep_g + P - 1) / P + 15) / 16 * 16;
         L.kr_off = d.slab_rank * chunk;

@@ -53,6 +53,7 @@ cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const OutPeers& Gin, const O
         case MODEL_RSW: return xpass(RswXOp<SWRT_N, 0, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
         case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
         case MODEL_RSW_QUADHEIGHT: return xpass(RswXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
         case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
@@ -79,6 +80,7 @@ cudaError_t Launch<SWRT_N>::stage_a_fused(int model, const double2* sol, const d
             for (int j = 0; j < 8; ++j) { sj.mul[j] = mul[j]; sj.last[j] = last[j]; }
             return ypass_inv_simple(sj, FusedLoaderA<RswLoaderA>{RswLoaderA{sol, L.vs}, psih, 5}, L, 8, G_, tw, st);
         }
+        case MODEL_RSW_LINDBORG: return ypass_inv(FusedLoaderA<LindborgLoaderA>{LindborgLoaderA{sol, L.vs}, psih, 8}, L, 11, G_, tw, st);
         case MODEL_SWQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 1, L.aux0}, psih, 3}, L, 6, G_, tw, st);
         case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return ypass_inv(FusedLoaderA<QgLoaderA>{QgLoaderA{sol, L.vs, 2, L.aux0}, psih, 6}, L, 9, G_, tw, st);

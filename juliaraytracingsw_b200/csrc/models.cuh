@@ -158,10 +158,13 @@ struct LindborgXOp {
     const double2* G;  // [8][ny][kr_pad]
     double2* H;        // [3][ny][kr_pad]
     double sc;
+    OutPeers peers{};  // slab mode: destinations of the output column segments
+    OutPeers gin{};    // slab mode: sources of the input column segments
+    int nj = 8;        // jobs the y-pass put into G (11 when the snapshot's three psi jobs ride along, team mode)
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 8, j, y); };
-        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 3, j, y); };
+        auto Gp = [&](int j) { return row_in<SLAB>(L, G, gin, nj, j, y); };
+        auto Hp = [&](int j) { return row_out<SLAB>(L, H, peers, 3, j, y); };
         const RowPlain none{};
         double *ur = cx.re(0), *vr = cx.im(0);
         double2 v[16];

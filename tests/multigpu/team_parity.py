@@ -177,6 +177,16 @@ def main():
     assert worst["modified_rsw"] < 1e-10, worst
     raytracing.get_velocity_info(sp, 1)
     sp.close()
+    sp = SlabProblem(dist, local, barrier=barrier, model="LinborgShallowWater", nx=nx1, Lx=cm["L"], dt=cm["dt"], f=cm["f"], Cg=cm["Cg"], nu=cm["nu"], nnu=cm["nnu"])
+    sp.sol = solm
+    pkl = raytracing.Packets(sp, 256, cm["f"], cm["Cg"], first=256 * rank)            # (also through the fused loop: 8 + 3 y-jobs)
+    xl, sl = oray.generate_initial_wavepackets(cm["L"], cm["k0"], 16 * int(np.sqrt(world)) if int(np.sqrt(world)) ** 2 == world else 16)
+    pkl.set(np.resize(xl, (256 * world, 4))[256 * rank:256 * (rank + 1)], np.resize(sl, 256 * world)[256 * rank:256 * (rank + 1)])
+    raytracing.get_velocity_info(sp, 0)
+    drivers.coupled_steps(sp, pkl, 14)
+    worst["lindborg_rsw"] = rel_l2(sp.gather_solution(), oracle_steps(gm, pm, solm, cm["dt"], 14, variant=orsw.LINDBORG))
+    assert worst["lindborg_rsw"] < 1e-10, worst
+    pkl.close(); sp.close()
 
     allw = [None] * world
     dist.all_gather_object(allw, worst)
