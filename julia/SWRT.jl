@@ -229,6 +229,7 @@ get_packets_async!(p::Packets, xk::Ptr{Cdouble}, ld::Integer) =
     check(ccall((:swrt_packets_get_async, libswrt), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Clonglong), p.h, xk, ld))
 sample_async!(p::Packets, slot::Integer, U::Ptr{Cdouble}, G::Ptr{Cdouble}, ld::Integer) =
     check(ccall((:swrt_packets_sample_async, libswrt), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Clonglong), p.h, slot, U, G, ld))
+"RAYKERNEL_AUTO = -1, CACHED = 0, TILE = 1 (two staged levels), TILE3 = 2 (three staged levels, nsub == 1), PIPE = 3 (persistent variant of TILE3)"
 set_kernel!(p::Packets, kernel::Integer) = check(ccall((:swrt_packets_set_kernel, libswrt), Cint, (Ptr{Cvoid}, Cint), p.h, kernel))
 sync!(p::Packets) = check(ccall((:swrt_packets_sync, libswrt), Cint, (Ptr{Cvoid},), p.h))
 "the hot loop (stepforward!; get_velocity_info; raytrace!; old = new) nsteps times in one ccall"

@@ -188,3 +188,14 @@ def test_frame_writer_is_accepted_by_the_reference_reader_K13_K14(tmp_path, max_
     np.testing.assert_array_equal(np.delete(times, last), np.delete(np.array([f[0] for f in frames]), last))
     if max_writes in ((8, 9, 12) if write_gradients else (8, 9, 10, 11)):
         assert splits > 0                                                       # frames did straddle files in these cases
+
+
+def test_segment_index_by_multiply_high_is_exact():
+    """csrc/passes.cuh `seg_magic`: the slab rows find the rank segment of column k as umulhi(k, ceil(2^32 / chunk)).  Exact for every
+    chunk the library can produce (multiples of 16 up to 4096) and every column index below 8192."""
+    import numpy as np
+    k = np.arange(8192, dtype=np.uint64)
+    for chunk in range(16, 4097, 16):
+        magic = ((1 << 32) + chunk - 1) // chunk
+        assert magic < (1 << 32)
+        assert np.array_equal((k * np.uint64(magic)) >> np.uint64(32), k // np.uint64(chunk)), chunk
