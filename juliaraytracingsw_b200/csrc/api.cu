@@ -506,10 +506,8 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     if (d.slab_size > 1) {
         const int P = d.slab_size;
         if ((P & (P - 1)) || P > 16 || d.slab_rank < 0 || d.slab_rank >= P || d.ny % P || d.ny / P < 16) { delete h; return fail(SWRT_ERR_ARG, "slab_size must be a power of two <= 16 dividing ny (>= 16 rows per rank), 0 <= slab_rank < slab_size"); }
-        const bool slab_model = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_QUADHEIGHT || d.model == SWRT_RSW_LINDBORG || d.model == SWRT_SWQG ||
-                                d.model == SWRT_TWOLAYERQG || d.model == SWRT_MULTILAYERQG2;
-        // (the one-calcN!-per-step steppers: the slab step is stage A -> B -> C + update; the multi-stage steppers would repeat it per stage)
-        if (!slab_model || !(d.stepper == SWRT_IFMAB3 || d.stepper == SWRT_FILTEREDAB3)) { delete h; return fail(SWRT_ERR_UNSUPPORTED, "slab mode is built for the RSW family / SWQG / two-layer QG / MultiLayerQG-2 with IFMAB3 or FilteredAB3"); }
+        // (every model; with IFMAB3 / FilteredAB3 the slab step is stage A -> B -> C + update, with the multi-stage steppers every
+        //  calcN! of a stage runs the three slab passes: slab_compute_N)
         h->P = P; h->rank = d.slab_rank;
         const int chunk = ((L.kr_keep_g + P - 1) / P + 15) / 16 * 16;
         L.kr_off = d.slab_rank * chunk;
@@ -788,8 +786,10 @@ static int ifmab3_update_launch(swrt_flow* h, double2* Ncur) {
     return SWRT_OK;
 }
 
+static int slab_compute_N(swrt_flow* h, const double2* state, double2* Nout);
 // N = calcN!(state): the three transform passes of the model
 static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
+    if (h->P > 1) return slab_compute_N(h, state, Nout);
     const SpecLayout& L = h->L;
     const int model = h->d.model;
     cudaError_t e;
@@ -804,9 +804,14 @@ static int compute_N(swrt_flow* h, const double2* state, double2* Nout) {
     return SWRT_OK;
 }
 
+static int flow_step_impl(swrt_flow* h, int nsteps);
 int swrt_flow_step(swrt_flow* h, int nsteps) {
     if (!h || nsteps < 0) return fail(SWRT_ERR_ARG, "bad argument");
-    if (h->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: drive the step with swrt_slab_stage_a/b/c and the two all-to-alls");
+    if (h->P > 1) return fail(SWRT_ERR_STATE, "slab-decomposed flow: step it with swrt_slab_step (or drive swrt_slab_stage_a/b/c and the two all-to-alls)");
+    return flow_step_impl(h, nsteps);
+}
+// (also the step of a slab-decomposed flow with a multi-stage stepper: compute_N then runs the slab passes and their barriers)
+static int flow_step_impl(swrt_flow* h, int nsteps) {
     CK(cudaSetDevice(h->d.device));
     const SpecLayout& L = h->L;
     const int stepper = h->d.stepper;
@@ -815,6 +820,7 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
     const double dt = h->d.dt;
     auto stage = [&](int mode, double2* out, const double2* x, double2* n1, const double2* n2, const double2* n3, const double2* n4,
                      const double2* xs, double c) {
+        if (ublocks == 0) return cudaSuccess;          // a slab rank beyond the retained columns owns no modes
         StageArgs sa{out, x, n1, n2, n3, n4, xs, h->coef, h->coef2, c, mode, h->nvar};
         ProfScope ps(h, K_UPDATE);
         diag_stage_kernel<<<ublocks, 256, 0, h->st>>>(sa, L);
@@ -857,7 +863,7 @@ int swrt_flow_step(swrt_flow* h, int nsteps) {
     static const int graph_mode = [] { const char* e = getenv("SWRT_GRAPH"); return e ? atoi(e) : 1; }();
     const bool ring_stepper = stepper == SWRT_IFMAB3 || stepper == SWRT_FILTEREDAB3;
     const int period = ring_stepper ? 3 : 1;
-    const bool use_graph = graph_mode > 0 && !h->prof && !h->no_graph && !h->forcing && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
+    const bool use_graph = graph_mode > 0 && h->P == 1 && !h->prof && !h->no_graph && !h->forcing && (graph_mode > 1 || (long long)h->d.nx * h->d.ny <= 1024LL * 1024LL);
     for (int s = 0; s < nsteps;) {
         if (use_graph && h->step >= 3 && nsteps - s >= period) {
             const int phase = ring_stepper ? h->ring : 0;
@@ -1351,9 +1357,29 @@ int swrt_slab_barrier(swrt_flow* h) {
     CK(cudaSetDevice(h->d.device));
     return team_barrier(h);
 }
+// calcN!(state) of a slab-decomposed flow for an arbitrary state (the stages of ETDRK4 / FilteredRK4): stage A of `state`, barrier,
+// stage B, barrier, stage C into Nout.  COLLECTIVE: every rank calls it in the same sequence.
+static int slab_compute_N(swrt_flow* h, const double2* state, double2* Nout) {
+    if (!h->p2p) return fail(SWRT_ERR_STATE, "a slab-decomposed flow with a multi-stage stepper needs the peers' receive buffers mapped (swrt_slab_ipc_open)");
+    const int nj = model_njobs_a(h->d.model);
+    cudaError_t e;
+    int rc;
+    { ProfScope ps(h, K_STAGE_A); SWRT_DISPATCH(h->L.ny, e, LN::stage_a(h->d.model, state, out_slab(h, 0, h->G, nj), h->L, h->tw_y, h->st)); }
+    CK(e);
+    if ((rc = slab_ship_a(h, nj))) return rc;
+    if ((rc = team_barrier(h))) return rc;
+    if ((rc = slab_stage_b(h, nj))) return rc;
+    if ((rc = team_barrier(h))) return rc;
+    SpecLayout Lc = h->L;
+    Lc.forcing = h->forcing;
+    { ProfScope ps(h, K_STAGE_C); SWRT_DISPATCH(h->L.ny, e, LN::stage_c(h->d.model, state, h->H, Nout, Lc, h->tw_y, h->st)); }
+    CK(e);
+    return SWRT_OK;
+}
 int swrt_slab_step(swrt_flow* h, int nsteps) {
     if (!h || h->P <= 1 || nsteps < 0) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad step count");
     if (!h->p2p) return fail(SWRT_ERR_STATE, "swrt_slab_step needs the peers' receive buffers mapped (swrt_slab_ipc_open); without them drive the phases and the all-to-alls from the host");
+    if (h->d.stepper == SWRT_ETDRK4 || h->d.stepper == SWRT_FILTEREDRK4) return flow_step_impl(h, nsteps);   // four calcN! per step
     int rc;
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = swrt_slab_stage_a(h))) return rc;
@@ -2280,7 +2306,8 @@ int swrt_packets_coupled_steps(swrt_packets* p, int psi_kind, int nsteps, double
     //   after the last step: the plain band snapshot of the final state and the last trace.
     // Same kernels on the same data as the plain loop below (only the job layout of the exchange buffer differs).
     static const int fused_mode = [] { const char* e = getenv("SWRT_TEAM_FUSED"); return e ? atoi(e) : 1; }();
-    if (f->P > 1 && fused_mode && nsteps > 0) {
+    const bool fusable = (f->d.stepper == SWRT_IFMAB3 || f->d.stepper == SWRT_FILTEREDAB3) && f->d.model != SWRT_THOMASYAMADA;
+    if (f->P > 1 && fused_mode && fusable && nsteps > 0) {
         const int nj = model_njobs_a(f->d.model) + 3, j0 = model_njobs_a(f->d.model);
         auto trace = [&]() -> int {
             int rc = swrt_packets_raytrace(p, 0.0, f->d.dt);

@@ -54,6 +54,7 @@ cudaError_t Launch<SWRT_N>::stage_b_slab(int model, const OutPeers& Gin, const O
         case MODEL_RSW_MODIFIED: return xpass(RswXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
         case MODEL_RSW_QUADHEIGHT: return xpass(RswXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, s1, H, Gin, nj}, L, tw, sched, st);
         case MODEL_RSW_LINDBORG: return xpass(LindborgXOp<SWRT_N, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
+        case MODEL_THOMASYAMADA: return xpass(TyXOp<SWRT_N, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
         case MODEL_SWQG: return xpass(QgXOp<SWRT_N, 1, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);
         case MODEL_MULTILAYERQG2:
         case MODEL_TWOLAYERQG: return xpass(QgXOp<SWRT_N, 2, true>{nullptr, nullptr, sc, H, Gin, nj}, L, tw, sched, st);

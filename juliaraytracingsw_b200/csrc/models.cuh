@@ -347,10 +347,13 @@ struct TyXOp {
     const double2* G;  // [9][ny][kr_pad]
     double2* H;        // [9][ny][kr_pad]
     double sc;
+    OutPeers peers{};  // slab mode: destinations of the output column segments
+    OutPeers gin{};    // slab mode: sources of the input column segments
+    int nj = 9;        // jobs the y-pass put into G
     __device__ __forceinline__ void row(const XCtx<N>& cx, const SpecLayout& L, int y) const {
         constexpr int Gt = XCtx<N>::G;
-        auto Gp = [&](int j) { return row_ref<SLAB>(L, G, 9, j, y); };
-        auto Hp = [&](int j) { return row_ref<SLAB>(L, H, 9, j, y); };
+        auto Gp = [&](int j) { return row_in<SLAB>(L, G, gin, nj, j, y); };
+        auto Hp = [&](int j) { return row_out<SLAB>(L, H, peers, 9, j, y); };
         const RowPlain none{};
         double *ut = cx.re(0), *vt = cx.im(0), *uc = cx.re(1), *vc = cx.im(1);
         double2 v[16];

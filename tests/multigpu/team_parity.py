@@ -188,6 +188,37 @@ def main():
     assert worst["lindborg_rsw"] < 1e-10, worst
     pkl.close(); sp.close()
 
+    # ---- 5. multi-stage steppers on the team (every calcN! of a stage runs the three slab passes and their two barriers):
+    #         Thomas-Yamada + ETDRK4 (BASELINE config 3's flow, thomasyamada/ThomasYamada.jl:129-274) and two-layer MultiLayerQG + FilteredRK4
+    from oracle import ty as oty
+    from oracle.grid import makefilter
+    Lx_t, Ro, nnu_t, dt_t = 6 * np.pi, 1.0, 8, 5e-3
+    nu_t = 5e-34 * (Lx_t / (2 * np.pi)) ** 16 * 1e12 * (64 / nx1) ** 16
+    gt, s3t = random_state(nx1, seed=21, amp=0.3, slope=1.0, Lx=Lx_t)
+    _, s1t = random_state(nx1, seed=22, amp=0.3, slope=1.0, Lx=Lx_t)
+    solt = np.concatenate([s3t, s1t[:, :, :1]], axis=-1)
+    sp = SlabProblem(dist, local, barrier=barrier, model="ThomasYamada", stepper="ETDRK4", nx=nx1, Lx=Lx_t, dt=dt_t, nu=nu_t, nnu=nnu_t, Ro=Ro)
+    sp.sol = solt
+    tst = oty.ETDRK4(oty.ty_L(gt, nu_t, nnu_t), dt_t, lambda s_: oty.ty_calcN(s_, gt, Ro))
+    wt = solt.copy()
+    sp.stepforward(6)
+    for _ in range(6):
+        tst.stepforward(wt)
+    worst["thomasyamada_etdrk4"] = rel_l2(sp.gather_solution(), gt.dealias(wt.copy()))
+    assert worst["thomasyamada_etdrk4"] < 1e-10, worst
+    sp.close()
+    sp = SlabProblem(dist, local, barrier=barrier, model="MultiLayerQG", stepper="FilteredRK4", nx=nx1, dt=c1["dt"], f0=c1["f0"], H=c1["H"], b=c1["b"],
+                     U=c1["U"], mu=c1["mu"], beta=c1["beta"], nu=nu1, nnu=nnu1, aliased_fraction=0)
+    sp.sol = sol1
+    tsr = oty.FilteredRK4(Ld, c1["dt"], lambda s_: oqg.multilayer2_calcN(s_, g1, c1["F"], c1["U"][0], c1["U"][1], c1["beta"], c1["mu"]), c1["filt"])
+    wr = sol1.copy()
+    sp.stepforward(6)
+    for _ in range(6):
+        tsr.stepforward(wr)
+    worst["multilayerqg_filteredrk4"] = rel_l2(sp.gather_solution(), g1.dealias(wr.copy()))
+    assert worst["multilayerqg_filteredrk4"] < 1e-10, worst
+    sp.close()
+
     allw = [None] * world
     dist.all_gather_object(allw, worst)
     if rank == 0:
