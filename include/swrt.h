@@ -161,6 +161,8 @@ int swrt_series_spectrum(swrt_series* s, int which, void* spectrum_host);
  *   slab_stage_b  (x-pass on the local rows)                 A_RECV -> B_SEND
  *   all-to-all B_SEND -> B_RECV
  *   slab_stage_c  (y-transforms back, IFMAB3 update, clock)  from B_RECV
+ * (the one-calcN!-per-step steppers IFMAB3 / FilteredAB3; ETDRK4 / FilteredRK4 evaluate calcN! four times per step, each time as the
+ * three passes above with a device barrier after A and B: swrt_slab_step, which needs the peers mapped, handles every model and stepper)
  * and a velocity snapshot is slab_psi_a, all-to-all, slab_snap_b (writes this rank's rows of the full snapshot), all-gather.
  * The exchange buffers are owned by the handle; swrt_slab_buffer returns their device pointers so that the caller's
  * communication library can work on them in place.  swrt_flow_set_stream makes the handle launch on the caller's stream

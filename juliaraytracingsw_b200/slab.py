@@ -33,7 +33,8 @@ class _DevBuf:
 
 class SlabProblem(flow.Problem):
     """`Problem` whose step is distributed over the ranks of `dist` (a torch.distributed process group).
-    Supported: RotatingShallowWater, SWQG, TwoLayerQG with the IFMAB3 stepper."""
+    Every model and stepper (the multi-stage steppers run the three slab passes once per stage: swrt_slab_step needs the mapped peers);
+    packets on a slab-decomposed flow use the fp64 bilinear interpolant."""
 
     def __init__(self, dist, dev=0, p2p=True, pull=None, barrier=None, **kw):
         """p2p=True: native team mode (peer stores + device barrier).  barrier = "device" (flag words over NVLink, default) or
