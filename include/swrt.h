@@ -29,8 +29,9 @@ enum { SWRT_RSW = 0, SWRT_RSW_MODIFIED = 1, SWRT_RSW_LINDBORG = 2, SWRT_RSW_QUAD
        /* GeophysicalFlows MultiLayerQG with two equal layers (raytracing/TwoLayerRaytracing.jl:174; simulation/TwoLayerSimulation.jl:37-47):
           diagonal L, mean flow / PV gradient / bottom drag inside calcN!; state q_1, q_2 */
        SWRT_MULTILAYERQG2 = 7 };
-/* steppers: utils/IFMAB3.jl; FourierFlows FilteredAB3 / ETDRK4 / FilteredRK4 (raytracing/CPUParameters.jl:7) */
-enum { SWRT_IFMAB3 = 0, SWRT_FILTEREDAB3 = 1, SWRT_ETDRK4 = 2, SWRT_FILTEREDRK4 = 3 };
+/* steppers: utils/IFMAB3.jl; FourierFlows FilteredAB3 / ETDRK4 / FilteredRK4 (raytracing/CPUParameters.jl:7) / FilteredETDRK4
+ * (raytracing/TestParameters.jl:6: ETDRK4 followed by sol *= filter) */
+enum { SWRT_IFMAB3 = 0, SWRT_FILTEREDAB3 = 1, SWRT_ETDRK4 = 2, SWRT_FILTEREDRK4 = 3, SWRT_FILTEREDETDRK4 = 4 };
 
 typedef struct swrt_flow swrt_flow;
 typedef struct swrt_packets swrt_packets;

@@ -38,7 +38,7 @@ end
 
 const MODELS = Dict("RotatingShallowWater" => 0, "ModifiedShallowWater" => 1, "LinborgShallowWater" => 2,
                     "QuadHeightModifiedShallowWater" => 3, "SWQG" => 4, "TwoLayerQG" => 5, "ThomasYamada" => 6, "MultiLayerQG" => 7)
-const STEPPERS = Dict("IFMAB3" => 0, "FilteredAB3" => 1, "ETDRK4" => 2, "FilteredRK4" => 3)
+const STEPPERS = Dict("IFMAB3" => 0, "FilteredAB3" => 1, "ETDRK4" => 2, "FilteredRK4" => 3, "FilteredETDRK4" => 4)
 const NVAR = Dict(0 => 3, 1 => 3, 2 => 3, 3 => 3, 4 => 1, 5 => 2, 6 => 4, 7 => 2)
 
 # --- flow: RotatingShallowWater.Problem and friends (rsw/RotatingShallowWater.jl:70-133, 309-336) ---------------

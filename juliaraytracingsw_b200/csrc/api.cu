@@ -135,6 +135,8 @@ static const char* kKernelNames[K_COUNT] = {"ypass_inv_kernel<RswLoaderA>", "xpa
                                             "raytrace_rk4_kernel", "sample_kernel", "ypass_inv_kernel<FieldLoader>", "xpass_kernel<C2ROp>",
                                             "packet_sort_kernels", "psi_kernel", "other"};
 
+static inline bool is_etd(int stepper) { return stepper == SWRT_ETDRK4 || stepper == SWRT_FILTEREDETDRK4; }
+
 struct ProfScope {
     swrt_flow* h;
     int id;
@@ -476,7 +478,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     const bool rsw_family = d.model == SWRT_RSW || d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_LINDBORG || d.model == SWRT_RSW_QUADHEIGHT;
     const bool diag_L = d.model == SWRT_SWQG || d.model == SWRT_THOMASYAMADA || d.model == SWRT_MULTILAYERQG2;
     if (!rsw_family && !diag_L && d.model != SWRT_TWOLAYERQG) return fail(SWRT_ERR_UNSUPPORTED, "model %d not implemented", d.model);
-    if (d.stepper < SWRT_IFMAB3 || d.stepper > SWRT_FILTEREDRK4) return fail(SWRT_ERR_ARG, "unknown stepper %d", d.stepper);
+    if (d.stepper < SWRT_IFMAB3 || d.stepper > SWRT_FILTEREDETDRK4) return fail(SWRT_ERR_ARG, "unknown stepper %d", d.stepper);
     if (d.stepper != SWRT_IFMAB3 && !diag_L)
         return fail(SWRT_ERR_UNSUPPORTED, "stepper %d needs a diagonal L (FourierFlows applies L .* sol); model %d has matrix blocks", d.stepper, d.model);
     if (!(d.Lx > 0 && d.Ly > 0 && d.dt > 0)) return fail(SWRT_ERR_ARG, "Lx, Ly, dt must be positive");
@@ -540,7 +542,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
     CKB(cudaMalloc(&h->sol, fb * h->nvar));
     CKB(cudaMemset(h->sol, 0, fb * h->nvar));
     for (int i = 0; i < 3; ++i) { CKB(cudaMalloc(&h->Nb[i], fb * h->nvar)); CKB(cudaMemset(h->Nb[i], 0, fb * h->nvar)); }
-    if (d.stepper == SWRT_ETDRK4 || d.stepper == SWRT_FILTEREDRK4) {
+    if (is_etd(d.stepper) || d.stepper == SWRT_FILTEREDRK4) {
         CKB(cudaMalloc(&h->S1, fb * h->nvar)); CKB(cudaMemset(h->S1, 0, fb * h->nvar));
         CKB(cudaMalloc(&h->S2, fb * h->nvar)); CKB(cudaMemset(h->S2, 0, fb * h->nvar));
         CKB(cudaMalloc(&h->N4, fb * h->nvar)); CKB(cudaMemset(h->N4, 0, fb * h->nvar));
@@ -580,7 +582,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
         std::vector<double4> cf((size_t)L.vs, make_double4(1.0, 0.0, 0.0, 1.0));
         std::vector<double2> E, E2;
         std::vector<double4> cf2;
-        if (d.stepper == SWRT_ETDRK4) cf2.assign((size_t)L.vs, make_double4(0, 0, 0, 0));
+        if (is_etd(d.stepper)) cf2.assign((size_t)L.vs, make_double4(0, 0, 0, 0));
         if (d.model == SWRT_TWOLAYERQG) { E.assign((size_t)4 * L.vs, make_double2(0, 0)); E2 = E; }
         const double w2c = (d.model == SWRT_RSW_MODIFIED || d.model == SWRT_RSW_QUADHEIGHT) ? 0.0 : L.Cg2;
         const double innerK = d.filter_innerK > 0 ? d.filter_innerK : 2.0 / 3.0, outerK = d.filter_outerK > 0 ? d.filter_outerK : 1.0;
@@ -601,7 +603,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
                 const double D = -d.nu * std::pow(K2, (double)d.nnu);
                 const size_t off = (size_t)l * L.kr_pad + kr;
                 double filt = 1.0;
-                if (d.use_filter || d.stepper == SWRT_FILTEREDAB3 || d.stepper == SWRT_FILTEREDRK4) {
+                if (d.use_filter || d.stepper == SWRT_FILTEREDAB3 || d.stepper == SWRT_FILTEREDRK4 || d.stepper == SWRT_FILTEREDETDRK4) {
                     const double Kn = std::sqrt((kw * dx / M_PI) * (kw * dx / M_PI) + (lw * dy / M_PI) * (lw * dy / M_PI));
                     if (Kn >= innerK) filt = std::exp(-decay * std::pow(Kn - innerK, order));
                 }
@@ -613,7 +615,7 @@ int swrt_flow_create(const swrt_flow_desc* desc, swrt_flow** out) {
                     cf[off] = make_double4(std::exp(D * d.dt), s, c, filt);
                 } else if (diag_L) {
                     cf[off] = make_double4(std::exp(D * d.dt), D, std::exp(0.5 * D * d.dt), filt);
-                    if (d.stepper == SWRT_ETDRK4) {   // FourierFlows getetdcoeffs: 32-point contour mean around dt L
+                    if (is_etd(d.stepper)) {   // FourierFlows getetdcoeffs: 32-point contour mean around dt L
                         cplx z(0), a(0), b(0), g(0);
                         for (int j = 0; j < 32; ++j) {
                             const cplx zc = D * d.dt + std::exp(cplx(0.0, 2.0 * M_PI / 32 * (j + 0.5)));
@@ -828,7 +830,7 @@ static int flow_step_impl(swrt_flow* h, int nsteps) {
     };
     auto step_body = [&]() -> int {
         int rc;
-        if (stepper == SWRT_ETDRK4) {            // FourierFlows ETDRK4 stepforward!
+        if (is_etd(stepper)) {            // FourierFlows ETDRK4 / FilteredETDRK4 stepforward! (the filter rides in the update stage)
             double2 *N1 = h->Nb[0], *N2 = h->Nb[1], *N3 = h->Nb[2], *N4 = h->N4;
             if ((rc = compute_N(h, h->sol, N1))) return rc;
             CK(stage(ST_ETD_SUB12, h->S1, h->sol, N1, nullptr, nullptr, nullptr, nullptr, 0));
@@ -1379,7 +1381,7 @@ static int slab_compute_N(swrt_flow* h, const double2* state, double2* Nout) {
 int swrt_slab_step(swrt_flow* h, int nsteps) {
     if (!h || h->P <= 1 || nsteps < 0) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow / bad step count");
     if (!h->p2p) return fail(SWRT_ERR_STATE, "swrt_slab_step needs the peers' receive buffers mapped (swrt_slab_ipc_open); without them drive the phases and the all-to-alls from the host");
-    if (h->d.stepper == SWRT_ETDRK4 || h->d.stepper == SWRT_FILTEREDRK4) return flow_step_impl(h, nsteps);   // four calcN! per step
+    if (is_etd(h->d.stepper) || h->d.stepper == SWRT_FILTEREDRK4) return flow_step_impl(h, nsteps);   // four calcN! per step
     int rc;
     for (int s = 0; s < nsteps; ++s) {
         if ((rc = swrt_slab_stage_a(h))) return rc;

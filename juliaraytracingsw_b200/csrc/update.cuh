@@ -222,8 +222,9 @@ __global__ void __launch_bounds__(256) diag_stage_kernel(StageArgs a, SpecLayout
                 a.out[o] = make_double2(cf.z * x.x + c2.x * (2.0 * n3.x - n1.x), cf.z * x.y + c2.x * (2.0 * n3.y - n1.y));
             } else if (a.mode == ST_ETD_UPDATE) {         // sol = e^{L dt} sol + alpha N1 + 2 beta (N2 + N3) + Gamma N4
                 const double2 x = a.x[o], n1 = a.n1[o], n2 = a.n2[o], n3 = a.n3[o], n4 = a.n4[o];
-                a.out[o] = make_double2(cf.x * x.x + c2.y * n1.x + 2.0 * c2.z * (n2.x + n3.x) + c2.w * n4.x,
-                                        cf.x * x.y + c2.y * n1.y + 2.0 * c2.z * (n2.y + n3.y) + c2.w * n4.y);
+                // (cf.w = the filter of FilteredETDRK4 / use_filter, exactly 1 otherwise: `sol *= filter` after the update)
+                a.out[o] = make_double2(cf.w * (cf.x * x.x + c2.y * n1.x + 2.0 * c2.z * (n2.x + n3.x) + c2.w * n4.x),
+                                        cf.w * (cf.x * x.y + c2.y * n1.y + 2.0 * c2.z * (n2.y + n3.y) + c2.w * n4.y));
             } else if (a.mode == ST_RK4_STAGE) {          // RHS = N + D x_stage (kept); out = sol + c RHS
                 const double2 xs = a.xs[o], x = a.x[o];
                 double2 r = a.n1[o];

@@ -17,7 +17,7 @@ from ._lib import FlowDesc, check, lib
 
 MODELS = {"RotatingShallowWater": 0, "ModifiedShallowWater": 1, "LinborgShallowWater": 2, "QuadHeightModifiedShallowWater": 3, "SWQG": 4,
           "TwoLayerQG": 5, "ThomasYamada": 6, "MultiLayerQG": 7}
-STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3}
+STEPPERS = {"IFMAB3": 0, "FilteredAB3": 1, "ETDRK4": 2, "FilteredRK4": 3, "FilteredETDRK4": 4}
 FIELD_U, FIELD_V, FIELD_ETA, FIELD_ZETA = 0, 1, 2, 16
 FIELD_QG_PSI, FIELD_QG_U, FIELD_QG_V, FIELD_QG_ZETA = 32, 40, 48, 56
 NVAR = {0: 3, 1: 3, 2: 3, 3: 3, 4: 1, 5: 2, 6: 4, 7: 2}

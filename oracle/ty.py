@@ -61,8 +61,9 @@ def etdrk4_coeffs(dt, L, ncirc=32, rcirc=1.0):
 class ETDRK4:
     """FourierFlows ETDRK4TimeStepper + stepforward! (Cox-Matthews / Kassam-Trefethen)."""
 
-    def __init__(self, L, dt, calcN):
-        self.dt, self.calcN = float(dt), calcN
+    def __init__(self, L, dt, calcN, filt=None):
+        """`filt`: FilteredETDRK4TimeStepper -- the same step followed by `sol *= filter` (raytracing/TestParameters.jl:6)."""
+        self.dt, self.calcN, self.filter = float(dt), calcN, filt
         self.expLdt, self.exphLdt = np.exp(L * dt), np.exp(L * dt / 2)
         self.zeta, self.alpha, self.beta, self.gamma = etdrk4_coeffs(self.dt, L)
         self.t, self.step = 0.0, 0
@@ -76,6 +77,8 @@ class ETDRK4:
         s2 = self.exphLdt * s1 + self.zeta * (2 * N3 - N1)
         N4 = self.calcN(s2)
         sol[...] = self.expLdt * sol + self.alpha * N1 + 2 * self.beta * (N2 + N3) + self.gamma * N4
+        if self.filter is not None:
+            sol *= self.filter
         self.t += self.dt
         self.step += 1
         return sol

@@ -373,7 +373,7 @@ def test_thomasyamada_parity(stepper):
     assert abs(pe / parsevalsum2(w[:, :, 3], g) - 1) < 1e-9
 
 
-@pytest.mark.parametrize("stepper", ["ETDRK4", "FilteredRK4"])
+@pytest.mark.parametrize("stepper", ["ETDRK4", "FilteredRK4", "FilteredETDRK4"])
 def test_swqg_multistage_steppers(stepper):
     from oracle import qg as oqg, ty as oty
     nx, f, Cg, nnu, dt = 64, 3.0, 1.0, 4, 4e-3
@@ -384,7 +384,8 @@ def test_swqg_multistage_steppers(stepper):
     prob.sol = sol0
     L = oqg.swqg_L(g, nu, nnu)
     calcN = lambda s: oqg.swqg_calcN(s, g, f * f / (Cg * Cg))
-    ts = oty.ETDRK4(L, dt, calcN) if stepper == "ETDRK4" else oty.FilteredRK4(L, dt, calcN, makefilter(g))
+    ts = {"ETDRK4": lambda: oty.ETDRK4(L, dt, calcN), "FilteredRK4": lambda: oty.FilteredRK4(L, dt, calcN, makefilter(g)),
+          "FilteredETDRK4": lambda: oty.ETDRK4(L, dt, calcN, makefilter(g))}[stepper]()
     want = sol0.copy()
     flow.stepforward(prob, (), 25)
     for _ in range(25):
