@@ -1243,6 +1243,9 @@ int swrt_slab_stage_b(swrt_flow* h) { return slab_stage_b(h, h ? model_njobs_a(h
 static int ifmab3_update_launch(swrt_flow* h, double2* Ncur);
 int swrt_slab_stage_c(swrt_flow* h) {
     if (!h || h->P <= 1) return fail(SWRT_ERR_STATE, "not a slab-decomposed flow");
+    if (is_etd(h->d.stepper) || h->d.stepper == SWRT_FILTEREDRK4)
+        return fail(SWRT_ERR_UNSUPPORTED, "the phase-by-phase slab step (stage_a / all-to-all / stage_b / all-to-all / stage_c) is the IFMAB3 / FilteredAB3 step; "
+                                          "a multi-stage stepper runs through swrt_slab_step with the peers mapped");
     CK(cudaSetDevice(h->d.device));
     double2* Ncur = h->Nb[h->ring];
     cudaError_t e;
